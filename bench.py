@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — QDense quantum-layer fwd+bwd throughput on B200 (BASELINE.json configs[1]).
+
+One "step" = one forward + adjoint backward of `QDenseUndirected_old_noise(60, 28)` (n = 10 qubits,
+600 Rot + 600 CNOT, MNIST-shaped 28x28 inputs; nn/qdense.py:71-125) over one batch of B synthetic
+circuit instances per GPU.  metric = circuit evals/s (one eval = one state-vector simulation of one
+instance, fwd+bwd), whole job over all ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): instances are sharded over ranks (weak
+scaling, no data-path collective); only the 1 800-float circuit-weight gradient is all-reduced per step.
+`--impl reference` times the CPU oracle port of the reference path on the host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+QDEPTH, SIDE = 60, 28
+PIXELS = SIDE * SIDE
+NQ = 10
+METRIC = "circuit_evals_per_sec_fwd_bwd"
+UNIT = "circuit-evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=65536, help="circuit instances per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(batch, n_gpus):
+    return {"workload": f"QDenseUndirected_old_noise({QDEPTH},{SIDE}) fwd+bwd, n={NQ} qubits, 600 Rot + 600 CNOT, "
+                        f"synthetic MNIST-shaped 28x28", "instances_per_gpu": batch, "global_instances": batch * n_gpus,
+            "parallelism": f"dp{n_gpus} (instances sharded, weight-grad all-reduce only)",
+            "l2": "inputs+grads per step (>=2x%.0f MB) exceed the 126 MB L2" % (batch * PIXELS * 4 / 1e6)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle legs (the only places bench.py may execute oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
+    """Times the complex128 oracle port of the reference path (fwd + autograd bwd) on the host cores."""
+    import torch
+    from oracle import qiddm_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(42)
+    W = (torch.randn(QDEPTH, NQ, 3, generator=g, dtype=torch.float64) * 0.4).requires_grad_(True)
+
+    def run(b):
+        x = torch.rand(b, 1, SIDE, SIDE, generator=g, dtype=torch.float64)
+        go = torch.randn(b, 1, SIDE, SIDE, generator=g, dtype=torch.float64)
+        t = time.perf_counter()
+        out = O.qdense_forward(x, W, O.REMAP_TANH)
+        (out * go).sum().backward()
+        W.grad = None
+        return time.perf_counter() - t
+
+    run(4)                                   # warm the thread pool / allocator
+    t_probe = run(16)
+    per = t_probe / 16
+    per_step = max(target_seconds / max(steps + warmup, 1), 0.5)
+    b = int(min(4096, max(16, per_step / per)))
+    for _ in range(warmup):
+        run(b)
+    times = [run(b) for _ in range(max(steps, 1))]
+    t = sum(times) / len(times)
+    return {"value": b / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{b} instances/step x {len(times)} step(s) of the same circuit, complex128 torch oracle "
+                      f"(per-gate ops on a (B,2^n) tensor + autograd, mirrors default.qubit.torch), {t:.2f} s/step"}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, t = cpu_oracle_rate(args.cpu_seconds * 2, steps=max(1, min(args.steps, 5)), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.batch, args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "PennyLane/Lightning are not installable here (no network); this is the oracle port of the "
+                    "reference's default.qubit.torch path on the host cores"}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import qiddm_b200
+    from qiddm_b200 import nn as qnn
+    from qiddm_b200._lib import Plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(42 + rank)
+    net = qnn.QDenseUndirected_old_noise(QDEPTH, SIDE).to(dev, torch.float64)
+    if world > 1:
+        dist.broadcast(net.weights.data, 0)
+    spec = net._spec()
+    plan = Plan.get(spec)
+    x = torch.rand(B, PIXELS, device=dev, dtype=torch.float32)               # resident in HBM
+    go = torch.randn(B, PIXELS, device=dev, dtype=torch.float32)
+    w = net.weights.detach()
+
+    def step_device():
+        out = plan.forward(x, w)
+        gi, gw = plan.backward(x, w, go, need_grad_in=True, need_grad_w=True)
+        if world > 1:
+            dist.all_reduce(gw)
+        return out, gi, gw
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    # --- timed region: exactly K steps, CUDA events on the launching (current) stream
+    launches0 = qiddm_b200.launch_count()
+    bwd_ev = []
+    sync_all()
+    t_wall0 = time.perf_counter()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(K):
+        out = plan.forward(x, w)
+        a, b = ev(), ev()
+        a.record()
+        gi, gw = plan.backward(x, w, go, need_grad_in=True, need_grad_w=True)
+        b.record()
+        bwd_ev.append((a, b))
+        if world > 1:
+            dist.all_reduce(gw)
+    e1.record()
+    sync_all()
+    t_wall1 = time.perf_counter()
+    launches = qiddm_b200.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_step = ms / K
+    value = B * world / (ms_step * 1e-3)
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / len(bwd_ev)
+
+    # --- e2e: host (pinned) buffers -> module API -> loss + weight gradient back on the host
+    xh = torch.rand(B, 1, SIDE, SIDE, dtype=torch.float32).pin_memory()
+    th = torch.rand(B, 1, SIDE, SIDE, dtype=torch.float32).pin_memory()
+    res_h = torch.empty(1 + net.weights.numel(), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        xd = xh.to(dev, non_blocking=True)
+        td = th.to(dev, non_blocking=True)
+        net.weights.grad = None
+        loss = torch.nn.functional.mse_loss(net(xd), td)
+        loss.backward()
+        g = net.weights.grad
+        if world > 1:
+            dist.all_reduce(g)
+        res_h.copy_(torch.cat([loss.detach().reshape(1).double(), g.reshape(-1).double()]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    ke = max(3, min(K, 5))
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(ke):
+        step_e2e()
+    e1.record()
+    sync_all()
+    ms_e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = t.item()
+    e2e_val = B * world / (ms_e / ke * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # --- roofline of the dominant kernel (adjoint backward gate kernel)
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = B * 4 * (PIXELS * 3)                       # read x, read grad_out, write grad_in (fp32)
+    achieved = alg_bytes / (bwd_ms * 1e-3) / 1e9
+    fwd_flop = QDEPTH * NQ * 14 * (1 << NQ)                # 14*A flop per Rot
+    bwd_flop = 4 * fwd_flop                                # recompute + un-apply + cotangent + apply-dagger
+    fp32_peak = 148 * 128 * 2 * (float(peaks.get("sm_max_mhz", 1965.0)) * 1e6) / 1e12
+    roofline = {"kernel": "gate_kernel<10,4,BWD> (adjoint backward, gate path)", "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "ms_per_launch": bwd_ms,
+                "note": "the gate path is FP32-FMA/shared-memory bound, not HBM bound (SURVEY.md 8d); "
+                        "fp32 view below",
+                "fp32": {"achieved_tflops": B * bwd_flop / (bwd_ms * 1e-3) / 1e12, "peak_tflops_nominal": fp32_peak,
+                         "frac": B * bwd_flop / (bwd_ms * 1e-3) / 1e12 / fp32_peak,
+                         "algorithmic_flop_per_eval_bwd": bwd_flop}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(B, world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * B * PIXELS * 4,
+                    "d2h_bytes_per_step": res_h.numel() * 8, "ms_per_step": ms_e / ke,
+                    "api": "qiddm_b200.nn.QDenseUndirected_old_noise(60,28) module fwd + mse + backward, pinned host in/out"},
+            "gpu_launches": int(launches), "roofline": roofline}
+
+    if not args.no_extras:
+        line["extras"] = extras(dev)
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_oracle_rate(args.cpu_seconds)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(dev):
+    """Secondary numbers (not the headline): forward-only rate, and QIDDM train samples/s on an
+    MNIST-shaped QIDDM_LL_noise(784,6,14,2) training step (src/mnist_exm.py:46, tau = 10)."""
+    import torch
+    from qiddm_b200 import models, nn as qnn, noise
+    from qiddm_b200._lib import Plan
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    net = qnn.QDenseUndirected_old_noise(QDEPTH, SIDE).to(dev, torch.float64)
+    plan = Plan.get(net._spec())
+    B = 65536
+    x = torch.rand(B, PIXELS, device=dev)
+    for _ in range(2):
+        plan.forward(x, net.weights.detach())
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(5):
+        plan.forward(x, net.weights.detach())
+    b.record()
+    torch.cuda.synchronize()
+    out["qdense_forward_only_evals_per_s"] = B * 5 / (a.elapsed_time(b) * 1e-3)
+    # QIDDM train samples/s
+    torch.manual_seed(0)
+    qn = qnn.QIDDM_LL_noise(784, 6, 14, 2)
+    diff = models.Diffusion(qn, noise.add_normal_noise_multiple, "data", (28, 28), torch.nn.MSELoss()).to(dev, torch.float64)
+    diff.train()
+    opt = torch.optim.Adam(diff.parameters(), lr=0.0255)
+    imgs = 4096
+    data = torch.rand(imgs, 784, device=dev, dtype=torch.float64)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        diff(x=data, T=10)
+        opt.step()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(5):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    out["qiddm_ll_train_samples_per_s"] = imgs / (ms * 1e-3)
+    out["qiddm_ll_train_circuit_evals_per_s"] = imgs * 10 * 2 / (ms * 1e-3)
+    out["qiddm_ll_config"] = "QIDDM_LL_noise(784,6,14,2), 4096 images/step, tau=10, Adam, float64 module I/O"
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+/*
+ * qiddm.h — C ABI of libqiddm_b200.so: batched state-vector simulation of the QIDDM
+ * quantum layers on NVIDIA B200 (sm_100a).
+ *
+ * The reference (aaai2026/QIDDM) is pure Python and has no FFI: the seam this library
+ * replaces is the PennyLane call `self.qnode(inputs[, weights]) -> Tensor`
+ *   nn/qdense.py:58, :115, :198, :279, :465, :549, :1633   (dense families)
+ *   nn/qconv.py:78-79  (the call that is missing there), :92-126 (eval-mode unitary)
+ * i.e. QNode.__call__ + device (`default.qubit.torch` / `lightning.qubit`) + autograd/parameter-shift.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions (PennyLane 0.29): wire 0 is the most significant bit of the basis
+ * index; Rot(phi,theta,omega) = RZ(omega) RY(theta) RZ(phi); StronglyEntanglingLayers ranges
+ * r_l = (l mod (n-1)) + 1 restarting at 0 in every block; ring = CNOT/CZ(i, (i+r) mod n), i = 0..n-1.
+ *
+ * All pointers are DEVICE pointers borrowed for the duration of the call (never freed or
+ * retained).  Work is enqueued on the caller's stream; nothing synchronises.  Every entry
+ * point returns 0 on success, a negative QIDDM_E* code on a bad argument, or a positive
+ * cudaError_t value.  No exceptions cross the ABI.  A plan is immutable after creation and
+ * may be used from several host threads as long as each call gets its own workspace.
+ */
+#ifndef QIDDM_H
+#define QIDDM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QIDDM_ABI_VERSION 1
+#define QIDDM_MAX_QUBITS 12
+
+typedef struct CUstream_st *qiddm_stream_t; /* == cudaStream_t */
+
+enum { QIDDM_OK = 0, QIDDM_EINVAL = -1, QIDDM_EUNSUPPORTED = -2, QIDDM_ENOMEM = -3, QIDDM_ENODEVICE = -4 };
+
+/* initial state */
+enum { QIDDM_INIT_ZERO = 0,      /* |0...0>                                                            */
+       QIDDM_INIT_AMPLITUDE = 1, /* AmplitudeEmbedding(features + add_offset, pad_with, normalize)     */
+       QIDDM_INIT_BASIS = 2 };   /* |basis[c]> (or |c> when basis == NULL): used to build unitaries    */
+/* per-block data gate that precedes each block's first Rot on every wire (re-upload encoding) */
+enum { QIDDM_ENC_NONE = 0, QIDDM_ENC_RZ = 1, QIDDM_ENC_RY = 2 };
+enum { QIDDM_IMP_CNOT = 0, QIDDM_IMP_CZ = 1 };
+/* weight re-mapping applied before the angles are used (nn/qdense.py:45,:97,:171; nn/qconv.py:55) */
+enum { QIDDM_REMAP_NONE = 0, QIDDM_REMAP_TANH = 1, QIDDM_REMAP_PI_TANH = 2 };
+enum { QIDDM_READ_PROBS = 0,     /* out[m] = clamp(post_scale * |psi[m*read_stride]|^2), m < read_count */
+       QIDDM_READ_EXPVAL_Z = 1,  /* out[j] = post_scale * <Z_j>, j < n_qubits                           */
+       QIDDM_READ_STATE = 2 };   /* out = (re, im) interleaved, 2 * 2^n floats                          */
+enum { QIDDM_DTYPE_F32 = 0, QIDDM_DTYPE_F64 = 1 };
+enum { QIDDM_PATH_AUTO = 0, QIDDM_PATH_GATE = 1, QIDDM_PATH_GEMM = 2 };
+
+/* One circuit "stage" = what one QNode call of the reference computes per circuit instance. */
+typedef struct qiddm_circuit_desc {
+    int32_t n_qubits;          /* 1..QIDDM_MAX_QUBITS                                                  */
+    int32_t n_blocks;          /* L: re-upload blocks (1 for plain SEL circuits)                        */
+    int32_t layers_per_block;  /* SEL depth inside a block; weights are (L, D, n, 3)                    */
+    int32_t init;              /* QIDDM_INIT_*                                                          */
+    int32_t n_features;        /* AMPLITUDE: real features per instance, <= 2^n                         */
+    float   pad_value;         /* AMPLITUDE: pad_with                                                   */
+    float   add_offset;        /* AMPLITUDE: constant added to every feature first (QConv's x + 0.1)    */
+    int32_t enc;               /* QIDDM_ENC_*: gate(enc_scale * in[j]) on wire j before every block     */
+    float   enc_scale;
+    int32_t imprimitive;       /* QIDDM_IMP_*                                                           */
+    int32_t remap;             /* QIDDM_REMAP_*                                                         */
+    int32_t readout;           /* QIDDM_READ_*                                                          */
+    int32_t read_count;        /* PROBS: K                                                              */
+    int32_t read_stride;       /* PROBS: stride between retained probabilities                          */
+    float   post_scale;
+    int32_t clamp;             /* 0/1: clamp outputs to [clamp_lo, clamp_hi] (PROBS only)               */
+    float   clamp_lo, clamp_hi;
+    int32_t path;              /* QIDDM_PATH_*                                                          */
+} qiddm_circuit_desc;
+
+/* Optional fused patch-unfold addressing for QConv (replaces torch.nn.Unfold + einops,
+ * nn/qconv.py:76-86): instance c = (b, y, x); feature f = (ch, ky, kx) reads
+ * img[b, ch, y+ky-pad_h, x+kx-pad_w] (0 outside); outputs go to out[b, m, y, x]. */
+typedef struct qiddm_unfold_desc {
+    int32_t channels, height, width;   /* input image (NCHW)        */
+    int32_t kernel_h, kernel_w, pad_h, pad_w;
+} qiddm_unfold_desc;
+
+typedef struct qiddm_plan qiddm_plan;
+
+int qiddm_abi_version(void);
+const char *qiddm_error_string(int code);
+
+/* Number of inputs / outputs per circuit instance for a descriptor (0 on invalid descriptors). */
+int qiddm_n_inputs(const qiddm_circuit_desc *desc);
+int qiddm_n_outputs(const qiddm_circuit_desc *desc);
+int qiddm_n_weights(const qiddm_circuit_desc *desc); /* L*D*n*3 */
+
+int  qiddm_plan_create(const qiddm_circuit_desc *desc, qiddm_plan **plan);
+void qiddm_plan_destroy(qiddm_plan *plan);
+
+/* Bytes of scratch a forward/backward call on `batch` instances needs (256-byte aligned). */
+size_t qiddm_workspace_bytes(const qiddm_plan *plan, int64_t batch);
+
+/* out[batch, n_outputs] = circuit(in[batch, n_inputs]; weights).  `in` may be NULL when the
+ * descriptor has no inputs; `basis` (int32[batch]) only for QIDDM_INIT_BASIS (may be NULL). */
+int qiddm_forward(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                  int weights_dtype, float *out, void *workspace, int64_t batch, qiddm_stream_t stream);
+
+/* Adjoint-method backward.  grad_in (batch, n_inputs) may be NULL; grad_weights has the shape and
+ * dtype of `weights` and is OVERWRITTEN with the batch-summed gradient (may be NULL). */
+int qiddm_backward(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                   int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
+                   void *workspace, int64_t batch, qiddm_stream_t stream);
+
+/* QConv: same circuit with the patch-unfold fused.  img (n_images, C, H, W) fp32; out
+ * (n_images, read_count, H_out, W_out) fp32; grad_img is OVERWRITTEN (col2im accumulated inside). */
+int qiddm_qconv_forward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, const float *img,
+                        const void *weights, int weights_dtype, float *out, void *workspace,
+                        int64_t n_images, qiddm_stream_t stream);
+int qiddm_qconv_backward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, const float *img,
+                         const void *weights, int weights_dtype, const float *grad_out, float *grad_img,
+                         void *grad_weights, void *workspace, int64_t n_images, qiddm_stream_t stream);
+
+/* Collapse the weight-only part of a circuit into its 2^n x 2^n unitary — the eval-mode matrix
+ * of nn/qconv.py:92-126.  Stored TRANSPOSED (row c = U|c>, i.e. unitary[c][k] = U[k][c]),
+ * interleaved re/im fp32, 2 * 4^n floats. */
+int qiddm_build_unitary(const qiddm_plan *plan, const void *weights, int weights_dtype, float *unitary,
+                        void *workspace, qiddm_stream_t stream);
+
+/* Kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
+int64_t qiddm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIDDM_H */

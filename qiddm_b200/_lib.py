@@ -1,0 +1,306 @@
+"""ctypes binding of libqiddm_b200.so (include/qiddm.h).  No torch types cross the ABI: only raw
+device pointers, sizes and the CUDA stream handle.  There is NO CPU fallback: a missing library
+or a non-CUDA tensor raises."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libqiddm_b200.so"
+
+# enums (include/qiddm.h)
+INIT_ZERO, INIT_AMPLITUDE, INIT_BASIS = 0, 1, 2
+ENC_NONE, ENC_RZ, ENC_RY = 0, 1, 2
+IMP_CNOT, IMP_CZ = 0, 1
+REMAP_NONE, REMAP_TANH, REMAP_PI_TANH = 0, 1, 2
+READ_PROBS, READ_EXPVAL_Z, READ_STATE = 0, 1, 2
+DTYPE_F32, DTYPE_F64 = 0, 1
+PATH_AUTO, PATH_GATE, PATH_GEMM = 0, 1, 2
+MAX_QUBITS = 12
+
+
+class CircuitDesc(C.Structure):
+    _fields_ = [
+        ("n_qubits", C.c_int32), ("n_blocks", C.c_int32), ("layers_per_block", C.c_int32),
+        ("init", C.c_int32), ("n_features", C.c_int32), ("pad_value", C.c_float),
+        ("add_offset", C.c_float), ("enc", C.c_int32), ("enc_scale", C.c_float),
+        ("imprimitive", C.c_int32), ("remap", C.c_int32), ("readout", C.c_int32),
+        ("read_count", C.c_int32), ("read_stride", C.c_int32), ("post_scale", C.c_float),
+        ("clamp", C.c_int32), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float), ("path", C.c_int32),
+    ]
+
+
+class UnfoldDesc(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("kernel_h", C.c_int32), ("kernel_w", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "qiddm_abi_version", "qiddm_error_string", "qiddm_n_inputs", "qiddm_n_outputs", "qiddm_n_weights",
+    "qiddm_plan_create", "qiddm_plan_destroy", "qiddm_workspace_bytes", "qiddm_forward", "qiddm_backward",
+    "qiddm_qconv_forward", "qiddm_qconv_backward", "qiddm_build_unitary", "qiddm_launch_count",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class QiddmError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[Path] = None) -> C.CDLL:
+    """Load (once) and type the shared library.  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        p = Path(path) if path else LIB_PATH
+        if not p.exists():
+            raise QiddmError(
+                f"{p} is missing: build it with `python -m qiddm_b200.build` (nvcc, sm_100a). "
+                "qiddm_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(str(p))
+        vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+        lib.qiddm_abi_version.restype = i32
+        lib.qiddm_error_string.restype = C.c_char_p
+        lib.qiddm_error_string.argtypes = [i32]
+        for f in (lib.qiddm_n_inputs, lib.qiddm_n_outputs, lib.qiddm_n_weights):
+            f.restype = i32
+            f.argtypes = [C.POINTER(CircuitDesc)]
+        lib.qiddm_plan_create.restype = i32
+        lib.qiddm_plan_create.argtypes = [C.POINTER(CircuitDesc), C.POINTER(vp)]
+        lib.qiddm_plan_destroy.restype = None
+        lib.qiddm_plan_destroy.argtypes = [vp]
+        lib.qiddm_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_workspace_bytes.argtypes = [vp, i64]
+        lib.qiddm_forward.restype = i32
+        lib.qiddm_forward.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp]
+        lib.qiddm_backward.restype = i32
+        lib.qiddm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp]
+        lib.qiddm_qconv_forward.restype = i32
+        lib.qiddm_qconv_forward.argtypes = [vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, i64, vp]
+        lib.qiddm_qconv_backward.restype = i32
+        lib.qiddm_qconv_backward.argtypes = [vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, vp, vp, i64, vp]
+        lib.qiddm_build_unitary.restype = i32
+        lib.qiddm_build_unitary.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.qiddm_launch_count.restype = i64
+        if lib.qiddm_abi_version() != 1:
+            raise QiddmError("libqiddm_b200.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load_library().qiddm_error_string(code).decode()
+        raise QiddmError(f"{what} failed: {msg} (code {code})")
+
+
+def launch_count() -> int:
+    return int(load_library().qiddm_launch_count())
+
+
+@dataclass(frozen=True)
+class StageSpec:
+    """Python mirror of qiddm_circuit_desc; hashable so plans can be cached per module."""
+    n_qubits: int
+    n_blocks: int = 1
+    layers_per_block: int = 1
+    init: int = INIT_ZERO
+    n_features: int = 0
+    pad_value: float = 0.0
+    add_offset: float = 0.0
+    enc: int = ENC_NONE
+    enc_scale: float = 1.0
+    imprimitive: int = IMP_CNOT
+    remap: int = REMAP_NONE
+    readout: int = READ_PROBS
+    read_count: int = 0
+    read_stride: int = 1
+    post_scale: float = 1.0
+    clamp: bool = False
+    clamp_lo: float = 0.0
+    clamp_hi: float = 1.0
+    path: int = PATH_AUTO
+
+    def to_c(self) -> CircuitDesc:
+        return CircuitDesc(self.n_qubits, self.n_blocks, self.layers_per_block, self.init, self.n_features,
+                           self.pad_value, self.add_offset, self.enc, self.enc_scale, self.imprimitive,
+                           self.remap, self.readout, self.read_count, self.read_stride, self.post_scale,
+                           int(self.clamp), self.clamp_lo, self.clamp_hi, self.path)
+
+    @property
+    def dim(self) -> int:
+        return 1 << self.n_qubits
+
+    @property
+    def n_in(self) -> int:
+        if self.init == INIT_AMPLITUDE:
+            return self.n_features
+        return self.n_qubits if self.enc != ENC_NONE else 0
+
+    @property
+    def n_out(self) -> int:
+        if self.readout == READ_PROBS:
+            return self.read_count
+        return self.n_qubits if self.readout == READ_EXPVAL_Z else 2 * self.dim
+
+    @property
+    def n_weights(self) -> int:
+        return self.n_blocks * self.layers_per_block * self.n_qubits * 3
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _wdtype(w: torch.Tensor) -> int:
+    if w.dtype == torch.float32:
+        return DTYPE_F32
+    if w.dtype == torch.float64:
+        return DTYPE_F64
+    raise QiddmError(f"weights must be float32 or float64, got {w.dtype}")
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise QiddmError(f"{name} must be a CUDA tensor: qiddm_b200 runs on sm_100a only (no CPU fallback)")
+
+
+class Plan:
+    """Owns a qiddm_plan*.  Thread-safe for concurrent forward/backward (each call allocates its own
+    workspace from torch's caching allocator)."""
+
+    _cache: dict = {}
+    _cache_lock = threading.Lock()
+
+    def __init__(self, spec: StageSpec):
+        self.spec = spec
+        self.lib = load_library()
+        handle = C.c_void_p()
+        desc = spec.to_c()
+        check(self.lib.qiddm_plan_create(C.byref(desc), C.byref(handle)), "qiddm_plan_create")
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.qiddm_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @classmethod
+    def get(cls, spec: StageSpec) -> "Plan":
+        with cls._cache_lock:
+            p = cls._cache.get(spec)
+            if p is None:
+                p = cls._cache[spec] = Plan(spec)
+            return p
+
+    # ------------------------------------------------------------------ helpers
+    def _workspace(self, batch: int, device) -> torch.Tensor:
+        with torch.cuda.device(device):
+            nbytes = int(self.lib.qiddm_workspace_bytes(self.handle, batch))
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+    @staticmethod
+    def _stream(device):
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def _check_weights(self, w: torch.Tensor) -> torch.Tensor:
+        _require_cuda(w, "weights")
+        if w.numel() != self.spec.n_weights:
+            raise QiddmError(f"weights has {w.numel()} elements, circuit needs {self.spec.n_weights}")
+        return w.contiguous()
+
+    # ------------------------------------------------------------------ dense rows
+    def forward(self, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int] = None,
+                basis: Optional[torch.Tensor] = None) -> torch.Tensor:
+        w = self._check_weights(weights)
+        dev = w.device
+        if self.spec.n_in > 0:
+            _require_cuda(x, "input")
+            if x.dim() != 2 or x.shape[1] != self.spec.n_in:
+                raise QiddmError(f"input must be (B, {self.spec.n_in}), got {tuple(x.shape)}")
+            x = x.to(torch.float32).contiguous()
+            batch = x.shape[0]
+        elif batch is None:
+            raise QiddmError("batch is required for circuits without inputs")
+        out = torch.empty((batch, self.spec.n_out), dtype=torch.float32, device=dev)
+        ws = self._workspace(batch, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_forward(self.handle, _ptr(x) if self.spec.n_in else None, _ptr(basis), _ptr(w),
+                                         _wdtype(w), _ptr(out), _ptr(ws), batch, self._stream(dev)),
+                  "qiddm_forward")
+        return out
+
+    def backward(self, x: Optional[torch.Tensor], weights: torch.Tensor, grad_out: torch.Tensor,
+                 need_grad_in: bool = True, need_grad_w: bool = True, basis: Optional[torch.Tensor] = None):
+        w = self._check_weights(weights)
+        dev = w.device
+        go = grad_out.to(torch.float32).contiguous()
+        batch = go.shape[0]
+        if self.spec.n_in > 0:
+            x = x.to(torch.float32).contiguous()
+        grad_in = (torch.empty((batch, self.spec.n_in), dtype=torch.float32, device=dev)
+                   if (need_grad_in and self.spec.n_in > 0) else None)
+        grad_w = torch.empty_like(w) if need_grad_w else None
+        ws = self._workspace(batch, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_backward(self.handle, _ptr(x) if self.spec.n_in else None, _ptr(basis), _ptr(w),
+                                          _wdtype(w), _ptr(go), _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
+                                          self._stream(dev)), "qiddm_backward")
+        return grad_in, grad_w
+
+    # ------------------------------------------------------------------ fused-unfold QConv
+    def qconv_forward(self, img: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc) -> torch.Tensor:
+        w = self._check_weights(weights)
+        _require_cuda(img, "input")
+        dev = w.device
+        img = img.to(torch.float32).contiguous()
+        n, c, h, wd = img.shape
+        ho = h + 2 * unfold.pad_h - unfold.kernel_h + 1
+        wo = wd + 2 * unfold.pad_w - unfold.kernel_w + 1
+        out = torch.empty((n, self.spec.read_count, ho, wo), dtype=torch.float32, device=dev)
+        ws = self._workspace(n * ho * wo, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_qconv_forward(self.handle, C.byref(unfold), _ptr(img), _ptr(w), _wdtype(w),
+                                               _ptr(out), _ptr(ws), n, self._stream(dev)), "qiddm_qconv_forward")
+        return out
+
+    def qconv_backward(self, img: torch.Tensor, weights: torch.Tensor, grad_out: torch.Tensor, unfold: UnfoldDesc,
+                       need_grad_in: bool = True, need_grad_w: bool = True):
+        w = self._check_weights(weights)
+        dev = w.device
+        img = img.to(torch.float32).contiguous()
+        go = grad_out.to(torch.float32).contiguous()
+        n = img.shape[0]
+        grad_img = torch.empty_like(img) if need_grad_in else None
+        grad_w = torch.empty_like(w) if need_grad_w else None
+        ws = self._workspace(n * go.shape[2] * go.shape[3], dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_qconv_backward(self.handle, C.byref(unfold), _ptr(img), _ptr(w), _wdtype(w),
+                                                _ptr(go), _ptr(grad_img), _ptr(grad_w), _ptr(ws), n,
+                                                self._stream(dev)), "qiddm_qconv_backward")
+        return grad_img, grad_w
+
+    def build_unitary(self, weights: torch.Tensor) -> torch.Tensor:
+        """Returns U as a (2^n, 2^n) complex64 tensor (the library writes U^T, row c = U|c>)."""
+        w = self._check_weights(weights)
+        dev = w.device
+        a = self.spec.dim
+        ut = torch.empty((a, a, 2), dtype=torch.float32, device=dev)
+        ws = self._workspace(a, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_build_unitary(self.handle, _ptr(w), _wdtype(w), _ptr(ut), _ptr(ws),
+                                               self._stream(dev)), "qiddm_build_unitary")
+        return torch.view_as_complex(ut).transpose(0, 1)

@@ -1,0 +1,260 @@
+// C-ABI entry points of libqiddm_b200.so (see include/qiddm.h).
+#include <atomic>
+#include <cstring>
+#include <new>
+#include "qiddm_internal.h"
+
+namespace qiddm {
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace qiddm
+
+struct qiddm_plan {
+    qiddm_circuit_desc d;
+    int n_rot;
+    int dim;
+};
+
+namespace {
+
+using namespace qiddm;
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) & ~(kAlign - 1); }
+
+bool desc_valid(const qiddm_circuit_desc *d) {
+    if (!d) return false;
+    if (d->n_qubits < 1 || d->n_qubits > QIDDM_MAX_QUBITS) return false;
+    if (d->n_blocks < 1 || d->layers_per_block < 1) return false;
+    const int A = 1 << d->n_qubits;
+    if (d->init < QIDDM_INIT_ZERO || d->init > QIDDM_INIT_BASIS) return false;
+    if (d->enc < QIDDM_ENC_NONE || d->enc > QIDDM_ENC_RY) return false;
+    if (d->init == QIDDM_INIT_AMPLITUDE) {
+        if (d->n_features < 1 || d->n_features > A) return false;
+        if (d->enc != QIDDM_ENC_NONE) return false;  // one input tensor per stage
+    }
+    if (d->imprimitive != QIDDM_IMP_CNOT && d->imprimitive != QIDDM_IMP_CZ) return false;
+    if (d->remap < QIDDM_REMAP_NONE || d->remap > QIDDM_REMAP_PI_TANH) return false;
+    if (d->readout < QIDDM_READ_PROBS || d->readout > QIDDM_READ_STATE) return false;
+    if (d->readout == QIDDM_READ_PROBS) {
+        if (d->read_count < 1 || d->read_stride < 1) return false;
+        if ((long long)(d->read_count - 1) * d->read_stride >= A) return false;
+    } else if (d->clamp) {
+        return false;
+    }
+    if (d->path < QIDDM_PATH_AUTO || d->path > QIDDM_PATH_GEMM) return false;
+    return true;
+}
+
+int n_inputs(const qiddm_circuit_desc *d) {
+    if (d->init == QIDDM_INIT_AMPLITUDE) return d->n_features;
+    if (d->enc != QIDDM_ENC_NONE) return d->n_qubits;
+    return 0;
+}
+int n_outputs(const qiddm_circuit_desc *d) {
+    if (d->readout == QIDDM_READ_PROBS) return d->read_count;
+    if (d->readout == QIDDM_READ_EXPVAL_Z) return d->n_qubits;
+    return 2 << d->n_qubits;
+}
+
+GateParams make_params(const qiddm_plan *pl, const qiddm_unfold_desc *u, long long B) {
+    const qiddm_circuit_desc &d = pl->d;
+    GateParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_blocks = d.n_blocks;
+    p.layers = d.layers_per_block;
+    p.init = d.init;
+    p.n_features = d.n_features;
+    p.enc = d.enc;
+    p.imprimitive = d.imprimitive;
+    p.readout = d.readout;
+    p.read_count = d.read_count;
+    p.read_stride = d.read_stride > 0 ? d.read_stride : 1;
+    p.clamp = d.clamp;
+    p.pad_value = d.pad_value;
+    p.add_offset = d.add_offset;
+    p.enc_scale = d.enc_scale;
+    p.post_scale = d.post_scale;
+    p.clamp_lo = d.clamp_lo;
+    p.clamp_hi = d.clamp_hi;
+    p.n_rot = pl->n_rot;
+    p.gates_in_smem = (size_t)pl->n_rot * 32 <= 48 * 1024;
+    p.B = B;
+    if (u) {
+        p.unfold = 1;
+        p.C = u->channels; p.H = u->height; p.W = u->width;
+        p.kh = u->kernel_h; p.kw = u->kernel_w; p.ph = u->pad_h; p.pw = u->pad_w;
+        p.Hout = u->height + 2 * u->pad_h - u->kernel_h + 1;
+        p.Wout = u->width + 2 * u->pad_w - u->kernel_w + 1;
+    }
+    return p;
+}
+
+bool unfold_valid(const qiddm_plan *pl, const qiddm_unfold_desc *u) {
+    if (!u || pl->d.init != QIDDM_INIT_AMPLITUDE || pl->d.readout != QIDDM_READ_PROBS) return false;
+    if (u->channels < 1 || u->height < 1 || u->width < 1 || u->kernel_h < 1 || u->kernel_w < 1) return false;
+    if (u->pad_h < 0 || u->pad_w < 0) return false;
+    if (u->channels * u->kernel_h * u->kernel_w != pl->d.n_features) return false;
+    if (u->height + 2 * u->pad_h - u->kernel_h + 1 < 1 || u->width + 2 * u->pad_w - u->kernel_w + 1 < 1) return false;
+    return true;
+}
+
+size_t gates_bytes(const qiddm_plan *pl) { return align_up((size_t)pl->n_rot * 8 * sizeof(float)); }
+
+int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
+                 const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s) {
+    if (!pl || !weights || !out || !ws || B < 0) return QIDDM_EINVAL;
+    if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    if (n_inputs(&pl->d) > 0 && !in) return QIDDM_EINVAL;
+    if (B == 0) return QIDDM_OK;
+    GateParams p = make_params(pl, u, B);
+    float *gates = reinterpret_cast<float *>(ws);
+    p.in = in; p.basis = basis; p.gates = gates; p.out = out;
+    cudaError_t e = launch_prepare_gates(weights, wdtype, pl->d.remap, pl->n_rot, gates, s);
+    if (e != cudaSuccess) return (int)e;
+    LaunchInfo li;
+    if ((e = gate_launch_info(pl->d.n_qubits, false, p, &li)) != cudaSuccess) return (int)e;
+    if ((e = launch_gate_forward(pl->d.n_qubits, p, li, s)) != cudaSuccess) return (int)e;
+    return QIDDM_OK;
+}
+
+int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
+                  const void *weights, int wdtype, const float *grad_out, float *grad_in, void *grad_weights,
+                  void *ws, long long B, long long grad_in_elems, cudaStream_t s) {
+    if (!pl || !weights || !grad_out || !ws || B < 0) return QIDDM_EINVAL;
+    if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    if (n_inputs(&pl->d) > 0 && !in) return QIDDM_EINVAL;
+    if (n_inputs(&pl->d) == 0) grad_in = nullptr;
+    GateParams p = make_params(pl, u, B);
+    float *gates = reinterpret_cast<float *>(ws);
+    float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + gates_bytes(pl));
+    p.in = in; p.basis = basis; p.gates = gates; p.out = nullptr;
+    p.grad_out = grad_out; p.grad_in = grad_in; p.partials = partials;
+    cudaError_t e;
+    if (B == 0) {
+        if (grad_weights) {
+            const size_t esz = wdtype == QIDDM_DTYPE_F64 ? 8 : 4;
+            if ((e = cudaMemsetAsync(grad_weights, 0, (size_t)pl->n_rot * 3 * esz, s)) != cudaSuccess) return (int)e;
+        }
+        return QIDDM_OK;
+    }
+    if (u && grad_in) {
+        if ((e = cudaMemsetAsync(grad_in, 0, (size_t)grad_in_elems * sizeof(float), s)) != cudaSuccess) return (int)e;
+    }
+    if ((e = launch_prepare_gates(weights, wdtype, pl->d.remap, pl->n_rot, gates, s)) != cudaSuccess) return (int)e;
+    LaunchInfo li;
+    if ((e = gate_launch_info(pl->d.n_qubits, true, p, &li)) != cudaSuccess) return (int)e;
+    if ((e = launch_gate_backward(pl->d.n_qubits, p, li, s)) != cudaSuccess) return (int)e;
+    if (grad_weights) {
+        if ((e = launch_finalize_grads(partials, li.grid, weights, wdtype, pl->d.remap, pl->n_rot, grad_weights, s)) !=
+            cudaSuccess)
+            return (int)e;
+    }
+    return QIDDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qiddm_abi_version(void) { return QIDDM_ABI_VERSION; }
+
+const char *qiddm_error_string(int code) {
+    switch (code) {
+        case QIDDM_OK: return "ok";
+        case QIDDM_EINVAL: return "invalid argument or descriptor";
+        case QIDDM_EUNSUPPORTED: return "unsupported configuration";
+        case QIDDM_ENOMEM: return "out of memory";
+        case QIDDM_ENODEVICE: return "no CUDA device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int qiddm_n_inputs(const qiddm_circuit_desc *d) { return desc_valid(d) ? n_inputs(d) : 0; }
+int qiddm_n_outputs(const qiddm_circuit_desc *d) { return desc_valid(d) ? n_outputs(d) : 0; }
+int qiddm_n_weights(const qiddm_circuit_desc *d) {
+    return desc_valid(d) ? d->n_blocks * d->layers_per_block * d->n_qubits * 3 : 0;
+}
+
+int qiddm_plan_create(const qiddm_circuit_desc *desc, qiddm_plan **plan) {
+    if (!plan) return QIDDM_EINVAL;
+    *plan = nullptr;
+    if (!desc_valid(desc)) return QIDDM_EINVAL;
+    const long long n_rot = (long long)desc->n_blocks * desc->layers_per_block * desc->n_qubits;
+    // the backward kernel keeps one 2x2 cotangent (8 floats) per Rot gate in shared memory
+    if (n_rot * 32 > 96 * 1024) return QIDDM_EUNSUPPORTED;
+    qiddm_plan *p = new (std::nothrow) qiddm_plan;
+    if (!p) return QIDDM_ENOMEM;
+    p->d = *desc;
+    p->n_rot = (int)n_rot;
+    p->dim = 1 << desc->n_qubits;
+    *plan = p;
+    return QIDDM_OK;
+}
+
+void qiddm_plan_destroy(qiddm_plan *plan) { delete plan; }
+
+size_t qiddm_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
+    if (!plan) return 0;
+    // gate matrices + per-CTA partial cotangents of the persistent backward grid
+    long long grid = 148 * 16;
+    if (batch > 0) {
+        GateParams p = make_params(plan, nullptr, batch);
+        LaunchInfo li;
+        if (gate_launch_info(plan->d.n_qubits, true, p, &li) == cudaSuccess) grid = li.grid;
+        else (void)cudaGetLastError();
+    }
+    return gates_bytes(plan) + align_up((size_t)grid * plan->n_rot * 8 * sizeof(float));
+}
+
+int qiddm_forward(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                  int weights_dtype, float *out, void *workspace, int64_t batch, qiddm_stream_t stream) {
+    return forward_impl(plan, nullptr, in, basis, weights, weights_dtype, out, workspace, batch, (cudaStream_t)stream);
+}
+
+int qiddm_backward(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                   int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights, void *workspace,
+                   int64_t batch, qiddm_stream_t stream) {
+    return backward_impl(plan, nullptr, in, basis, weights, weights_dtype, grad_out, grad_in, grad_weights, workspace,
+                         batch, 0, (cudaStream_t)stream);
+}
+
+int qiddm_qconv_forward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, const float *img,
+                        const void *weights, int weights_dtype, float *out, void *workspace, int64_t n_images,
+                        qiddm_stream_t stream) {
+    if (!plan || !unfold_valid(plan, unfold) || n_images < 0) return QIDDM_EINVAL;
+    const long long P = (long long)(unfold->height + 2 * unfold->pad_h - unfold->kernel_h + 1) *
+                        (unfold->width + 2 * unfold->pad_w - unfold->kernel_w + 1);
+    return forward_impl(plan, unfold, img, nullptr, weights, weights_dtype, out, workspace, n_images * P,
+                        (cudaStream_t)stream);
+}
+
+int qiddm_qconv_backward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, const float *img,
+                         const void *weights, int weights_dtype, const float *grad_out, float *grad_img,
+                         void *grad_weights, void *workspace, int64_t n_images, qiddm_stream_t stream) {
+    if (!plan || !unfold_valid(plan, unfold) || n_images < 0) return QIDDM_EINVAL;
+    const long long P = (long long)(unfold->height + 2 * unfold->pad_h - unfold->kernel_h + 1) *
+                        (unfold->width + 2 * unfold->pad_w - unfold->kernel_w + 1);
+    const long long img_elems = n_images * unfold->channels * unfold->height * unfold->width;
+    return backward_impl(plan, unfold, img, nullptr, weights, weights_dtype, grad_out, grad_img, grad_weights,
+                         workspace, n_images * P, img_elems, (cudaStream_t)stream);
+}
+
+int qiddm_build_unitary(const qiddm_plan *plan, const void *weights, int weights_dtype, float *unitary,
+                        void *workspace, qiddm_stream_t stream) {
+    if (!plan || !weights || !unitary || !workspace) return QIDDM_EINVAL;
+    if (plan->d.n_blocks != 1 && plan->d.enc != QIDDM_ENC_NONE) return QIDDM_EUNSUPPORTED;
+    // column c of U = circuit(|c>): instance c writes row c of U^T; transpose on the fly is not
+    // needed by our consumers, who take U^T (row c = U e_c) — document: unitary[c][k] = U[k][c].
+    qiddm_plan tmp = *plan;
+    tmp.d.init = QIDDM_INIT_BASIS;
+    tmp.d.enc = QIDDM_ENC_NONE;
+    tmp.d.readout = QIDDM_READ_STATE;
+    tmp.d.clamp = 0;
+    return forward_impl(&tmp, nullptr, nullptr, nullptr, weights, weights_dtype, unitary, workspace, tmp.dim,
+                        (cudaStream_t)stream);
+}
+
+int64_t qiddm_launch_count(void) { return (int64_t)qiddm::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

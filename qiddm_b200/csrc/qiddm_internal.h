@@ -1,0 +1,44 @@
+// Internal declarations shared by the translation units of libqiddm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "qiddm.h"
+
+namespace qiddm {
+
+// Everything a gate-path kernel needs, passed by value.
+struct GateParams {
+    // circuit
+    int n_blocks, layers, init, n_features, enc, imprimitive, readout, read_count, read_stride, clamp;
+    float pad_value, add_offset, enc_scale, post_scale, clamp_lo, clamp_hi;
+    int n_rot;                 // n_blocks * layers * n_qubits
+    int gates_in_smem;         // 1: stage the 2x2 matrices in shared memory
+    // fused patch-unfold (QConv); unfold == 0 -> plain (B, n_in) rows
+    int unfold, C, H, W, kh, kw, ph, pw, Hout, Wout;
+    long long B;               // circuit instances
+    const float *in;           // (B, n_in) features / angles, or NCHW image when unfold
+    const int *basis;          // INIT_BASIS start states (may be null -> instance index)
+    const float *gates;        // [n_rot][8]: re00 im00 re01 im01 re10 im10 re11 im11
+    float *out;
+    // backward only
+    const float *grad_out;
+    float *grad_in;            // nullable
+    float *partials;           // [grid][n_rot*8] per-CTA sums of the 2x2 gate cotangents
+};
+
+struct LaunchInfo {
+    int grid, block;
+    size_t smem;
+};
+
+// qiddm_gate.cu
+int gate_rb(int n_qubits, bool backward);
+cudaError_t gate_launch_info(int n_qubits, bool backward, const GateParams &p, LaunchInfo *info);
+cudaError_t launch_gate_forward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s);
+cudaError_t launch_gate_backward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s);
+cudaError_t launch_prepare_gates(const void *weights, int wdtype, int remap, int n_rot, float *gates, cudaStream_t s);
+cudaError_t launch_finalize_grads(const float *partials, int n_partials, const void *weights, int wdtype,
+                                  int remap, int n_rot, void *grad_weights, cudaStream_t s);
+void count_launch(int n = 1);
+
+}  // namespace qiddm

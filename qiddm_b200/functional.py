@@ -1,0 +1,70 @@
+"""torch.autograd.Functions over the C-ABI (forward kernel + adjoint-method backward kernel).
+
+These replace `self.qnode(inputs[, weights])` of the reference modules (nn/qdense.py:58,:465,:1633;
+nn/qconv.py H1).  Outputs are returned in the dtype of the input (weights' dtype for input-less
+circuits); the simulation itself runs in fp32 on the device."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import Plan, StageSpec, UnfoldDesc
+
+
+class _StageFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: Plan, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int]):
+        ctx.plan = plan
+        ctx.x_dtype = x.dtype if x is not None else None
+        out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch)
+        ctx.save_for_backward(x if x is not None else torch.empty(0), weights)
+        ctx.has_x = x is not None
+        return out.to(x.dtype if x is not None else weights.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weights = ctx.saved_tensors
+        x = x if ctx.has_x else None
+        need_x = ctx.has_x and ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2]
+        gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
+        if gi is not None:
+            gi = gi.to(ctx.x_dtype)
+        return None, gi, (gw.view_as(weights) if gw is not None else None), None
+
+
+def run_stage(spec: StageSpec, x: Optional[torch.Tensor], weights: torch.Tensor,
+              batch: Optional[int] = None) -> torch.Tensor:
+    """One QNode-equivalent evaluation: (B, n_in) -> (B, n_out), differentiable in x and weights."""
+    return _StageFunction.apply(Plan.get(spec), x, weights, batch)
+
+
+class _QConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: Plan, img: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc):
+        ctx.plan, ctx.unfold = plan, unfold
+        out = plan.qconv_forward(img.detach(), weights.detach(), unfold)
+        ctx.save_for_backward(img, weights)
+        return out.to(img.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        img, weights = ctx.saved_tensors
+        gi, gw = ctx.plan.qconv_backward(img, weights, grad_out, ctx.unfold,
+                                         need_grad_in=ctx.needs_input_grad[1],
+                                         need_grad_w=ctx.needs_input_grad[2])
+        if gi is not None:
+            gi = gi.to(img.dtype)
+        return None, gi, (gw.view_as(weights) if gw is not None else None), None
+
+
+def run_qconv(spec: StageSpec, img: torch.Tensor, weights: torch.Tensor, kernel_size, padding) -> torch.Tensor:
+    """Fused unfold + amplitude-embed + SEL + probs readout: (N,C,H,W) -> (N,out,H_out,W_out)."""
+    n, c, h, w = img.shape
+    unfold = UnfoldDesc(c, h, w, kernel_size[0], kernel_size[1], padding[0], padding[1])
+    return _QConvFunction.apply(Plan.get(spec), img, weights, unfold)
+
+
+def build_unitary(spec: StageSpec, weights: torch.Tensor) -> torch.Tensor:
+    return Plan.get(spec).build_unitary(weights.detach())

@@ -1,0 +1,77 @@
+"""Diffusion wrapper (reference `src/models.py:8-150`): training step (noise ladder -> net -> MSE ->
+`.backward()` INSIDE forward, as the reference does) and the fixed-point sampler.  Same constructor,
+`forward(x, T=..., verbose=...)`, `sample(...)` and `save_name()`; tensors stay on the device."""
+import typing
+
+import torch
+
+
+class Diffusion(torch.nn.Module):
+    def __init__(self, net: torch.nn.Module, noise_f, prediction_goal: str, shape: typing.Tuple[int, int],
+                 loss: torch.nn.Module = torch.nn.MSELoss(reduction="none")) -> None:
+        super().__init__()
+        self.net = net
+        self.prediction_goal = prediction_goal
+        self.add_noise = noise_f
+        self.width, self.height = shape
+        self.loss = loss
+
+    def forward(self, x: typing.Optional[torch.Tensor], **kwargs):
+        """Training mode: one training step (incl. backward).  Eval mode: sample.  src/models.py:29-42."""
+        if self.training:
+            if self.prediction_goal == "data":
+                return self.run_training_step_data(x, **kwargs)
+            return self.run_training_step_noise(x, **kwargs)
+        return self.sample(first_x=x, **kwargs)
+
+    def _ladder(self, x: torch.Tensor, T: int):
+        """src/models.py:46-63: (batch, T+1, pixels) ladder -> noisy = steps 1..T, clean = steps 0..T-1."""
+        whole = self.add_noise(x, tau=T + 1, decay_mod=3.0).reshape(-1, T + 1, x.shape[-1])
+        shape = (-1, 1, self.width, self.height)
+        return whole[:, 1:, :].reshape(shape), whole[:, :-1, :].reshape(shape)
+
+    def run_training_step_data(self, x: torch.Tensor, **kwargs):
+        noisy, clean = self._ladder(x, kwargs["T"])
+        recon = self.net.forward(x=noisy)
+        batch_loss = self.loss(recon, clean)
+        batch_loss_mean = batch_loss.mean()
+        batch_loss_mean.backward()
+        if kwargs.get("verbose", False):
+            return batch_loss.abs(), recon.abs()
+        return (batch_loss_mean.abs(),)
+
+    def run_training_step_noise(self, x: torch.Tensor, **kwargs):
+        noisy, clean = self._ladder(x, kwargs["T"])
+        predicted_noise = (self.net.forward(x=noisy) - 0.5) * 0.1
+        batch_loss = self.loss(predicted_noise, noisy - clean)
+        batch_loss_mean = batch_loss.mean()
+        batch_loss_mean.backward()
+        if kwargs.get("verbose", False):
+            return batch_loss, torch.clamp(noisy - predicted_noise, 0, 1)
+        return (batch_loss_mean,)
+
+    def sample(self, n_iters, first_x: typing.Optional[torch.Tensor] = None, labels=None, show_progress: bool = False,
+               only_last=False, step=1, noise_factor=1.0) -> torch.Tensor:
+        """x <- net(x) (goal "data") or x <- clamp(x - 0.1 nf (net(x) - 0.5), 0, 1).  src/models.py:106-147."""
+        if first_x is None:
+            p = next(self.net.parameters())
+            first_x = torch.rand((10, 1, self.width, self.height), device=p.device, dtype=p.dtype)
+        outp = [first_x]
+        with torch.no_grad():
+            x = first_x
+            for i in range(n_iters):
+                predicted = self.net(x)
+                if self.prediction_goal == "data":
+                    x = predicted
+                else:
+                    x = torch.clamp(x - (predicted - 0.5) * 0.1 * noise_factor, 0, 1)
+                if i % step == 0:
+                    outp.append(x)
+        if only_last:
+            return outp[-1]
+        outp = torch.stack(outp)                                   # iters batch 1 height width
+        it, b, _, h, w = outp.shape
+        return outp[:, :, 0].permute(0, 2, 1, 3).reshape(it * h, b * w)
+
+    def save_name(self):
+        return f"{self.net.save_name()}{'_noise' if self.prediction_goal == 'noise' else ''}"

@@ -1,0 +1,730 @@
+"""Drop-in replacements for the 27 dense quantum modules of the reference `nn/qdense.py`.
+
+Constructor positional order, `forward` shapes, `state_dict` keys (`weights` / `weights1`,
+`linear_down.*`, `linear_up.*`, `conv_layer.*`, `batchnorm.*`, `batch_norm.*`), `save_name()` and
+`__repr__` follow the reference class by class (file:line cited per class).  What changes is the
+seam `self.qnode(...)`: it is a sm_100a CUDA kernel call (qiddm_b200.functional.run_stage) with an
+adjoint-method backward; there is no PennyLane device and no CPU fallback.
+
+Deliberate deviations:
+* H2 — the reference detaches every lightning.qubit result (`torch.tensor(qnode(...))`), so its
+  circuit weights and `linear_down` never train.  Here the TRUE gradient flows; set the class
+  attribute / instance flag `detach_quantum = True` to reproduce the reference's cut gradient.
+* `add_noise in {2, 3}` (density-matrix channels on `default.mixed`) raise NotImplementedError;
+  `add_noise == 1` is kept where it is a no-op on the readout (PhaseShift / PhaseDamping before a
+  diagonal readout is NOT a no-op in general, so only the provable cases are accepted).
+* Attributes `qdev`, `qnode`, `device_type`, `diff_method` are inert (kept for drivers that read them).
+"""
+from __future__ import annotations
+
+import math
+import pickle
+
+import einops
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from ..functional import run_stage
+
+QDEV_NAME = "qiddm_b200:sm_100a"
+
+
+def _pca_fit_transform(pca, x: torch.Tensor):
+    """The reference re-fits sklearn PCA on every forward call on the current batch
+    (nn/qdense.py:456, :1429).  Kept verbatim: host round-trip, outside the kernel."""
+    return pca.fit_transform(x.detach().cpu().numpy())
+
+
+def _make_pca(n_components):
+    from sklearn.decomposition import PCA
+    return PCA(n_components=n_components)
+
+
+def _check_noise(add_noise, allow_phase: bool):
+    if add_noise in (0, None):
+        return
+    if add_noise == 1 and allow_phase:
+        return  # PhaseShift on every wire right before probs(): diagonal, no effect on probabilities
+    raise NotImplementedError(
+        f"add_noise={add_noise}: density-matrix noise channels (default.mixed) are out of scope of the "
+        "B200 state-vector path (SURVEY.md §8f-4)")
+
+
+def _shape2(shape):
+    return (shape, shape) if isinstance(shape, int) else tuple(shape)
+
+
+def _reupload_spec(n, L_, D, enc=L.ENC_RZ, enc_scale=1.0, readout=L.READ_EXPVAL_Z, read_count=0,
+                   post_scale=1.0, clamp=False):
+    return L.StageSpec(n_qubits=n, n_blocks=L_, layers_per_block=D, init=L.INIT_ZERO, enc=enc,
+                       enc_scale=enc_scale, imprimitive=L.IMP_CZ, readout=readout, read_count=read_count,
+                       post_scale=post_scale, clamp=clamp)
+
+
+class _SaveLoadMixin:
+    """save_model/load_model as in nn/qdense.py:297-307."""
+
+    def save_model(self, path, loss_values, epochs):
+        torch.save({"model_state_dict": self.state_dict(), "loss_values": loss_values, "epochs": epochs}, path)
+
+    def load_model(self, path):
+        checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+        self.load_state_dict(checkpoint["model_state_dict"])
+
+
+# ======================================================================================
+# a1 — amplitude embedding + SEL(CNOT) + probs            nn/qdense.py:15-125
+# ======================================================================================
+class _AmplitudeDense(nn.Module):
+    _remap = L.REMAP_NONE
+
+    def _setup(self, qdepth, shape):
+        self.qdepth = qdepth
+        self.width, self.height = _shape2(shape)
+        self.pixels = self.width * self.height
+        self.wires = math.ceil(math.log2(self.width * self.height))
+        self.qdev = QDEV_NAME
+        self.weights = nn.Parameter(torch.randn((qdepth, self.wires, 3)) * 0.4)
+        self.qnode = self._circuit
+
+    def _spec(self):
+        return L.StageSpec(n_qubits=self.wires, n_blocks=1, layers_per_block=self.qdepth,
+                           init=L.INIT_AMPLITUDE, n_features=self.pixels, pad_value=0.1,
+                           imprimitive=L.IMP_CNOT, remap=self._remap, readout=L.READ_PROBS,
+                           read_count=self.pixels, post_scale=float(self.pixels), clamp=True)
+
+    def _circuit(self, inp):
+        """Full probs of the circuit, (B, 2**wires) un-scaled (what the reference QNode returns)."""
+        s = self._spec()
+        s = L.StageSpec(**{**s.__dict__, "read_count": s.dim, "post_scale": 1.0, "clamp": False})
+        return run_stage(s, inp, self.weights)
+
+    def forward(self, x):
+        x = einops.rearrange(x, "b 1 w h -> b (w h)")
+        # qnode + _post_process fused in the kernel epilogue (slice, scale by pixels, clamp)
+        x = run_stage(self._spec(), x, self.weights)
+        return einops.rearrange(x, "b (w h) -> b 1 w h", w=self.width, h=self.height)
+
+
+class QDenseUndirected_old(_AmplitudeDense):
+    """Dense variational circuit. Undirected.  nn/qdense.py:15-68 (qw_map.tanh = pi*tanh remap)."""
+    _remap = L.REMAP_PI_TANH
+
+    def __init__(self, qdepth, shape) -> None:
+        super().__init__()
+        self._setup(qdepth, shape)
+
+    def __repr__(self):
+        return f"QDenseUndirected_old(qdepth={self.qdepth}, wires={self.wires})"
+
+    def save_name(self) -> str:
+        return f"QDenseUndirected_old{self.qdepth}_w{self.width}_h{self.height}"
+
+
+class QDenseUndirected_old_noise(_AmplitudeDense):
+    """nn/qdense.py:71-125 (torch.tanh remap; add_noise channels only exist on default.mixed)."""
+    _remap = L.REMAP_TANH
+
+    def __init__(self, qdepth, shape, add_noise=0, device_type="default.qubit.torch") -> None:
+        super().__init__()
+        _check_noise(add_noise, allow_phase=True)
+        self.add_noise = add_noise
+        self.device_type = device_type
+        self._setup(qdepth, shape)
+
+    def __repr__(self):
+        return f"QDenseUndirected_old_noise(qdepth={self.qdepth}, wires={self.wires}, add_noise={self.add_noise})"
+
+    def save_name(self) -> str:
+        return f"QDenseUndirected_old_noise{self.qdepth}_w{self.width}_h{self.height}_noise{self.add_noise}"
+
+
+# ======================================================================================
+# a2 — linear_down + AngleEmbedding(Y) + SEL(CNOT) + probs      nn/qdense.py:128-210
+# ======================================================================================
+class QNN_A(nn.Module):
+    """Dense variational circuit with angle encoding and dimensionality reduction.  nn/qdense.py:128-210."""
+
+    def __init__(self, qdepth, shape, add_noise=0, device_type="default.qubit.torch", diff_method="backprop") -> None:
+        super().__init__()
+        _check_noise(add_noise, allow_phase=False)
+        self.qdepth = qdepth
+        self.add_noise = add_noise
+        self.device_type = device_type
+        self.diff_method = diff_method
+        self.width, self.height = _shape2(shape)
+        self.pixels = self.width * self.height
+        self.wires = math.ceil(math.log2(self.pixels))
+        self.qdev = QDEV_NAME
+        self.linear_down = nn.Linear(self.pixels, self.wires, dtype=torch.double)
+        self.weights = nn.Parameter(torch.randn((qdepth, self.wires, 3), dtype=torch.double) * 0.4)
+        self.qnode = self._circuit
+
+    def _spec(self, full=False):
+        return L.StageSpec(n_qubits=self.wires, n_blocks=1, layers_per_block=self.qdepth, init=L.INIT_ZERO,
+                           enc=L.ENC_RY, imprimitive=L.IMP_CNOT, readout=L.READ_PROBS,
+                           read_count=(1 << self.wires) if full else self.pixels,
+                           post_scale=1.0 if full else float(self.pixels), clamp=not full)
+
+    def _circuit(self, inp):
+        return run_stage(self._spec(full=True), inp, self.weights)
+
+    def forward(self, x):
+        x = einops.rearrange(x, "b 1 w h -> b (w h)")
+        x = self.linear_down(x)
+        x = run_stage(self._spec(), x, self.weights)
+        return einops.rearrange(x, "b (w h) -> b 1 w h", w=self.width, h=self.height)
+
+    def __repr__(self):
+        return f"QNN_A(qdepth={self.qdepth}, wires={self.wires}, add_noise={self.add_noise})"
+
+    def save_name(self) -> str:
+        return f"QNN_A{self.qdepth}_w{self.width}_h{self.height}_noise{self.add_noise}"
+
+
+# ======================================================================================
+# a5 — linear_down + RZ + SEL(CZ) + <Z> + linear_up       nn/qdense.py:219-386
+# ======================================================================================
+class _QNNBase(_SaveLoadMixin, nn.Module):
+    detach_quantum = False
+
+    def _setup(self, input_dim, hidden_features, qdepth):
+        if isinstance(input_dim, str):
+            input_dim = eval(input_dim)  # "28 * 28" -> 784, as nn/qdense.py:222-223
+        self.hidden_features = hidden_features
+        self.qdepth = qdepth
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.linear_down = nn.Linear(input_dim, hidden_features, dtype=torch.double).to(self.device)
+        self.linear_up = nn.Linear(hidden_features, input_dim, dtype=torch.double).to(self.device)
+        self.qdev = QDEV_NAME
+        self.weights = nn.Parameter(
+            torch.randn((qdepth, hidden_features, 3), dtype=torch.double).to(self.device) * 0.4)
+        self.qnode = self._circuit
+
+    def _circuit(self, inputs, weights=None):
+        w = self.weights if weights is None else weights
+        return run_stage(_reupload_spec(self.hidden_features, 1, self.qdepth), inputs.reshape(-1, self.hidden_features), w)
+
+    def forward(self, x):
+        b, c, w, h = x.shape
+        x = x.view(b, -1).to(self.linear_down.weight.dtype)
+        x_reduced = self.linear_down(x)
+        x_reduced = self._circuit(x_reduced)
+        if self.detach_quantum:
+            x_reduced = x_reduced.detach()
+        x_restored = self.linear_up(x_reduced.to(self.linear_up.weight.dtype))
+        return x_restored.view(b, c, w, h)
+
+
+class QNN_noise(_QNNBase):
+    """nn/qdense.py:219-307."""
+
+    def __init__(self, input_dim, hidden_features, qdepth: int, add_noise=0) -> None:
+        super().__init__()
+        _check_noise(add_noise, allow_phase=False)
+        self.add_noise = add_noise
+        self._setup(input_dim, hidden_features, qdepth)
+
+    def __repr__(self):
+        return f"QNN(qdepth={self.qdepth}, features={self.hidden_features}, add_noise={self.add_noise})"
+
+    def save_name(self) -> str:
+        return f"QNN_linear_features={self.hidden_features}_qdepth={self.qdepth}_add_noise={self.add_noise}"
+
+
+class QNN(_QNNBase):
+    """nn/qdense.py:310-386."""
+
+    def __init__(self, input_dim, hidden_features, qdepth: int) -> None:
+        super().__init__()
+        self._setup(input_dim, hidden_features, qdepth)
+
+    def __repr__(self):
+        return f"QNN(qdepth={self.qdepth}, features={self.hidden_features})"
+
+    def save_name(self) -> str:
+        return f"QNN_linear_features={self.hidden_features}_qdepth={self.qdepth}"
+
+
+# ======================================================================================
+# a3 — RZ re-upload + SEL(CZ) + probs, N chained stages   nn/qdense.py:389-1011, 2182-2436
+# ======================================================================================
+class _DifferNBase(nn.Module):
+    """angles (B,n) -> N stages; stage k+1 reads the first n (optionally post-processed)
+    probabilities of stage k as its angles (nn/qdense.py:464-465 + :427)."""
+    _reduce = "pca"            # "pca" | "conv" | "raw"
+    _enc_scale = 1.0
+    _post_each_stage = False   # per-sample variants post-process between stages (:813-817)
+    _shared_weights = False    # QIDDM_A_sameN
+    _weight_name = "weights"
+    detach_quantum = False
+
+    def _setup(self, shape, spectrum_layer, N):
+        self.spectrum_layer = spectrum_layer
+        self.N = N
+        self.width, self.height = _shape2(shape)
+        self.pixels = self.width * self.height
+        n = math.ceil(math.log2(self.pixels))
+        self.qdev = QDEV_NAME
+        wshape = (spectrum_layer, 2, n, 3) if self._shared_weights else (N, spectrum_layer, 2, n, 3)
+        setattr(self, self._weight_name, nn.Parameter(torch.randn(wshape) * 0.4))
+        self.qnode = self._circuit
+        return n
+
+    @property
+    def _n(self):
+        return getattr(self, "wires", None) or self.hidden_features
+
+    def _stage_spec(self, last: bool):
+        n = self._n
+        if last or self._post_each_stage:
+            return _reupload_spec(n, self.spectrum_layer, 2, enc_scale=self._enc_scale, readout=L.READ_PROBS,
+                                  read_count=self.pixels if last else n, post_scale=float(self.pixels), clamp=True)
+        return _reupload_spec(n, self.spectrum_layer, 2, enc_scale=self._enc_scale, readout=L.READ_PROBS,
+                              read_count=n)
+
+    def _circuit(self, inputs, weights):
+        """Un-scaled probs (B, 2**n) of one stage, as the reference QNode returns."""
+        n = self._n
+        s = _reupload_spec(n, self.spectrum_layer, 2, enc_scale=self._enc_scale, readout=L.READ_PROBS,
+                           read_count=1 << n)
+        return run_stage(s, inputs.reshape(-1, inputs.shape[-1])[:, :n], weights)
+
+    def _angles(self, x):
+        b = x.shape[0]
+        n = self._n
+        W = getattr(self, self._weight_name)
+        if self._reduce == "pca":
+            flat = x.reshape(b, -1)
+            a = _pca_fit_transform(self.pca, flat)
+            return torch.tensor(a, dtype=torch.float32).to(W.device)
+        if self._reduce == "conv":
+            a = self.conv_layer(x)
+            return a.view(b, n, -1).mean(dim=2)
+        return x.reshape(b, -1)[:, :n]
+
+    def _chain(self, a):
+        W = getattr(self, self._weight_name)
+        n = self._n
+        for k in range(self.N):
+            w = W if self._shared_weights else W[k]
+            a = run_stage(self._stage_spec(last=(k == self.N - 1)), a[:, :n].contiguous(), w)
+            if self.detach_quantum:
+                a = a.detach()
+        return a
+
+    def forward(self, x):
+        b, c, w, h = x.shape
+        probs = self._chain(self._angles(x))
+        return einops.rearrange(probs, "b (w h) -> b 1 w h", w=self.width, h=self.height).to(x.dtype)
+
+
+class differN_noise(_DifferNBase):
+    """nn/qdense.py:389-478."""
+
+    def __init__(self, shape, spectrum_layer, N, add_noise=0) -> None:
+        super().__init__()
+        _check_noise(add_noise, allow_phase=True)
+        self.add_noise = add_noise
+        self.wires = self._setup(shape, spectrum_layer, N)
+        self.pca = _make_pca(self.wires)
+
+    def __repr__(self):
+        return f"differN_old_pca={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"differN_old_pca={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}_noise{self.add_noise}"
+
+
+class differN_noise_befor(_DifferNBase):
+    """nn/qdense.py:481-562."""
+
+    def __init__(self, shape, spectrum_layer, N, add_noise=0, device_type="default.qubit.torch") -> None:
+        super().__init__()
+        _check_noise(add_noise, allow_phase=False)
+        self.add_noise = add_noise
+        self.device_type = device_type
+        self.wires = self._setup(shape, spectrum_layer, N)
+        self.pca = _make_pca(self.wires)
+
+    def __repr__(self):
+        return f"differN_noise={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"differN_noise={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+
+class differN_old_pca(_DifferNBase):
+    """nn/qdense.py:671-743."""
+
+    def __init__(self, shape, spectrum_layer, N) -> None:
+        super().__init__()
+        self.wires = self._setup(shape, spectrum_layer, N)
+        self.pca = _make_pca(self.wires)
+
+    def __repr__(self):
+        return f"differN_old_pca={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"differN_old_pca={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+
+class differN_new_pca(_DifferNBase):
+    """Per-sample variant, post-processes between stages.  nn/qdense.py:747-835."""
+    _post_each_stage = True
+
+    def __init__(self, shape, spectrum_layer, N) -> None:
+        super().__init__()
+        self.wires = self._setup(shape, spectrum_layer, N)
+        self.pca = _make_pca(self.wires)
+
+    def __repr__(self):
+        return f"differN_new_pca={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"differN_new_pca={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+
+class differN_new_conv(_DifferNBase):
+    """nn/qdense.py:838-936."""
+    _reduce = "conv"
+    _post_each_stage = True
+
+    def __init__(self, shape, spectrum_layer, N) -> None:
+        super().__init__()
+        self.wires = self._setup(shape, spectrum_layer, N)
+        self.pca = _make_pca(self.wires)
+        self.conv_layer = nn.Conv2d(in_channels=1, out_channels=self.wires, kernel_size=3, stride=2, padding=1)
+
+    def __repr__(self):
+        return f"differN_new_conv={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"differN_new_conv={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+
+class differN_old_conv(_DifferNBase):
+    """nn/qdense.py:939-1011."""
+    _reduce = "conv"
+
+    def __init__(self, shape, spectrum_layer, N) -> None:
+        super().__init__()
+        self.wires = self._setup(shape, spectrum_layer, N)
+        self.pca = _make_pca(self.wires)
+        self.conv_layer = nn.Conv2d(in_channels=1, out_channels=self.wires, kernel_size=3, stride=2, padding=1)
+
+    def __repr__(self):
+        return f"differN_old_conv={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"differN_old_conv={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+
+class QIDDM_A_sameN(_DifferNBase):
+    """Same weights for all N stages, raw pixels as angles.  nn/qdense.py:2276-2342."""
+    _reduce = "raw"
+    _shared_weights = True
+
+    def __init__(self, shape, spectrum_layer, N) -> None:
+        super().__init__()
+        self.wires = self._setup(shape, spectrum_layer, N)
+
+    def __repr__(self):
+        return f"QIDDM_A_sameN={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+    def save_name(self) -> str:
+        return f"QIDDM_A_sameN={self.spectrum_layer}_N={self.N}_w{self.width}_h{self.height}"
+
+
+class _QIDDM_A_differN(_SaveLoadMixin, _DifferNBase):
+    """RZ(pi/2 * a), per-sample, post-processed between stages.  nn/qdense.py:2182-2273, 2345-2436.
+    (The reference re-feeds all `pixels` post-processed values; the circuit reads the first n.)"""
+    _enc_scale = math.pi * 0.5
+    _post_each_stage = True
+    _weight_name = "weights1"
+
+    def __init__(self, input_dim, spectrum_layer, N: int) -> None:
+        super().__init__()
+        self.hidden_features = self._setup(input_dim, spectrum_layer, N)
+        self.pca = _make_pca(self.hidden_features)
+
+    def _angles(self, x):
+        b = x.shape[0]
+        a = _pca_fit_transform(self.pca, x.reshape(b, -1))
+        return torch.tensor(a).to(x.device).to(x.dtype)
+
+    def __repr__(self):
+        return f"QIDDM(qlayer={self.spectrum_layer}, features={self.hidden_features}, N={self.N})"
+
+
+class QIDDM_A_differN_basePL(_QIDDM_A_differN):
+    def save_name(self) -> str:
+        return f"QIDDM_pca_features={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_A_differN_NEW(_QIDDM_A_differN):
+    def save_name(self) -> str:
+        return f"QIDDM_pca_new={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+# ======================================================================================
+# a4 — reduce -> N x [RZ re-upload + SEL(CZ) + <Z>] -> linear_up   nn/qdense.py:565-670, 1014-2161
+# ======================================================================================
+class _QIDDMExpval(_SaveLoadMixin, nn.Module):
+    _reduce = "linear"        # "linear" | "pca" | "conv"
+    _restore = "linear"       # "linear" | "pca"
+    _enc = L.ENC_RZ
+    _layers = 2
+    _bias = True
+    _repr_name = "QIDDM"
+    detach_quantum = False
+
+    def _setup(self, input_dim, hidden_features, spectrum_layer, N):
+        self.hidden_features = hidden_features
+        self.spectrum_layer = spectrum_layer
+        self.N = N
+        if self._reduce == "pca":
+            self.pca = _make_pca(hidden_features)
+        elif self._reduce == "conv":
+            self.conv_layer = nn.Conv2d(in_channels=1, out_channels=hidden_features, kernel_size=3, stride=2,
+                                        padding=1)
+        else:
+            self.linear_down = nn.Linear(input_dim, hidden_features, bias=self._bias)
+        if self._restore == "linear":
+            self.linear_up = nn.Linear(hidden_features, input_dim, bias=self._bias)
+        self.qdev = QDEV_NAME
+        self.weights1 = nn.Parameter(torch.randn((N, spectrum_layer, self._layers, hidden_features, 3)) * 0.4)
+        self.qnode = self._circuit
+
+    def _spec(self):
+        return _reupload_spec(self.hidden_features, self.spectrum_layer, self._layers, enc=self._enc)
+
+    def _circuit(self, inputs, weights1):
+        return run_stage(self._spec(), inputs.reshape(-1, self.hidden_features), weights1)
+
+    def _reduce_input(self, x):
+        b = x.shape[0]
+        if self._reduce == "pca":
+            ref = self.linear_up.weight if hasattr(self, "linear_up") else self.weights1
+            a = _pca_fit_transform(self.pca, x.reshape(b, -1))
+            return torch.tensor(a).to(ref.device).to(ref.dtype)
+        if self._reduce == "conv":
+            return self.conv_layer(x).view(b, self.hidden_features, -1).mean(dim=2)
+        return self.linear_down(x.reshape(b, -1).to(self.linear_down.weight.dtype))
+
+    def _between_stages(self, a):
+        return a
+
+    def forward(self, x):
+        b, c, w, h = x.shape
+        a = self._reduce_input(x)
+        for n in range(self.N):
+            a = self._between_stages(a)
+            a = self._circuit(a, self.weights1[n])
+            if self.detach_quantum:
+                a = a.detach()
+        a = a.view(b, -1)
+        if self._restore == "linear":
+            out = self.linear_up(a.to(self.linear_up.weight.dtype))
+        else:
+            out = torch.tensor(self.pca.inverse_transform(a.detach().cpu().numpy()), device=x.device, dtype=x.dtype,
+                               requires_grad=True)
+        return out.view(b, c, w, h)
+
+    def __repr__(self):
+        return f"{self._repr_name}(qlayer={self.spectrum_layer}, features={self.hidden_features}, N={self.N})"
+
+
+class _QIDDMExpvalNoise(_QIDDMExpval):
+    def __init__(self, input_dim, hidden_features, spectrum_layer, N: int, add_noise=0,
+                 device_type="lightning.qubit") -> None:
+        super().__init__()
+        _check_noise(add_noise, allow_phase=False)
+        self.add_noise = add_noise
+        self.device_type = device_type
+        self._setup(input_dim, hidden_features, spectrum_layer, N)
+
+    def __repr__(self):
+        return (f"{self._repr_name}(qlayer={self.spectrum_layer}, features={self.hidden_features}, "
+                f"N={self.N}, add_noise={self.add_noise})")
+
+
+class _QIDDMExpvalPlain(_QIDDMExpval):
+    def __init__(self, input_dim, hidden_features, spectrum_layer, N: int) -> None:
+        super().__init__()
+        self._setup(input_dim, hidden_features, spectrum_layer, N)
+
+
+class QIDDM_PL_noise1(_QIDDMExpvalNoise):
+    """RY re-upload variant.  nn/qdense.py:565-668."""
+    _reduce, _enc, _repr_name = "pca", L.ENC_RY, "QIDDM_PL_noise"
+
+    def save_name(self) -> str:
+        return f"QIDDM_PL_noise={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_PL_noise(_QIDDMExpvalNoise):
+    """nn/qdense.py:1371-1466 (configs 3/4 default)."""
+    _reduce, _repr_name = "pca", "QIDDM_PL_noise"
+
+    def save_name(self) -> str:
+        return f"QIDDM_PL_noise={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_LL_noise(_QIDDMExpvalNoise):
+    """nn/qdense.py:1567-1660 (config 1 default)."""
+    _repr_name = "QIDDM_LL_noise"
+
+    def save_name(self) -> str:
+        return f"QIDDM_LL_noise={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_LL_relu_noise(_QIDDMExpvalNoise):
+    """nn/qdense.py:1469-1565 (the ReLU member is created but never applied there either)."""
+    _repr_name = "QIDDM_LL_noise"
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.relu = nn.ReLU()
+
+    def save_name(self) -> str:
+        return f"QIDDM_LL_noise={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_PP_noise(_QIDDMExpvalNoise):
+    """PCA down, PCA inverse_transform up.  nn/qdense.py:1663-1753."""
+    _reduce, _restore, _repr_name = "pca", "pca", "QIDDM_PP_noise"
+
+    def save_name(self) -> str:
+        return f"QIDDM_PP_noise={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_CL_new(_QIDDMExpvalPlain):
+    """nn/qdense.py:1014-1101."""
+    _reduce = "conv"
+
+    def save_name(self) -> str:
+        return f"QIDDM_CL_new_q={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_CL_old(_QIDDMExpvalPlain):
+    """nn/qdense.py:1104-1173."""
+    _reduce = "conv"
+
+    def save_name(self) -> str:
+        return f"QIDDM_CL_old_q={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_PL_old(_QIDDMExpvalPlain):
+    """nn/qdense.py:1176-1268 (the reference passes the whole batch flattened, which only runs at
+    batch 1; evaluated per sample here)."""
+    _reduce = "pca"
+
+    def save_name(self) -> str:
+        return f"QIDDM_PL_old_q={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_PL(_QIDDMExpvalPlain):
+    """nn/qdense.py:1271-1368."""
+    _reduce, _repr_name = "pca", "QIDDM_PL"
+
+    def save_name(self) -> str:
+        return f"QIDDM_PL={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_LL_old(_QIDDMExpvalPlain):
+    """nn/qdense.py:1873-1968."""
+
+    def save_name(self) -> str:
+        return f"QIDDM_linear_features={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_bias_false(_QIDDMExpvalPlain):
+    """3-layer SEL blocks, bias-free linears.  nn/qdense.py:1971-2074."""
+    _layers, _bias = 3, False
+
+    def save_name(self) -> str:
+        return f"QIDDM_linear_features={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_L_B(_QIDDMExpvalPlain):
+    """BatchNorm1d before every stage, 3-layer SEL blocks.  nn/qdense.py:2077-2179 (the reference
+    instantiates default.qubit.jax with interface torch — dead code)."""
+    _layers, _repr_name = 3, "QIDDM_L_B"
+
+    def __init__(self, input_dim, hidden_features, spectrum_layer, N: int) -> None:
+        super().__init__(input_dim, hidden_features, spectrum_layer, N)
+        self.batchnorm = nn.BatchNorm1d(hidden_features)
+
+    def _between_stages(self, a):
+        return self.batchnorm(a.to(self.batchnorm.weight.dtype)).to(self.weights1.dtype)
+
+    def save_name(self) -> str:
+        return f"QIDDM_linear_batch_features={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+
+class QIDDM_PP_old(nn.Module):
+    """PCA(2n) fitted once -> BatchNorm1d -> linear_down -> circuit -> linear_up -> PCA inverse.
+    nn/qdense.py:1756-1870 (the output is re-created with torch.tensor, so nothing trains there)."""
+
+    def __init__(self, input_dim, hidden_features, spectrum_layer, N: int) -> None:
+        super().__init__()
+        self.hidden_features = hidden_features
+        self.spectrum_layer = spectrum_layer
+        self.input_dim = input_dim
+        self.N = N
+        self.pca = None
+        self.batch_norm = nn.BatchNorm1d(2 * hidden_features)
+        self.linear_down = nn.Linear(2 * hidden_features, hidden_features)
+        self.linear_up = nn.Linear(hidden_features, 2 * hidden_features)
+        self.qdev = QDEV_NAME
+        self.weights1 = nn.Parameter(torch.randn((N, spectrum_layer, 2, hidden_features, 3)) * 0.4)
+        self.qnode = self._circuit
+
+    def _circuit(self, inputs, weights1):
+        return run_stage(_reupload_spec(self.hidden_features, self.spectrum_layer, 2),
+                         inputs.reshape(-1, self.hidden_features), weights1)
+
+    def forward(self, x):
+        b, c, w, h = x.shape
+        x = x.view(b, -1)
+        if self.pca is None:
+            self.pca = _make_pca(2 * self.hidden_features)
+            self.pca.fit(x.detach().cpu().numpy())
+        a = torch.tensor(self.pca.transform(x.detach().cpu().numpy()), device=x.device, dtype=x.dtype,
+                         requires_grad=True)
+        a = self.linear_down(self.batch_norm(a))
+        for n in range(self.N):
+            a = self._circuit(a, self.weights1[n]).detach().to(x.dtype)
+        a = self.linear_up(a).view(b, -1)
+        out = torch.tensor(self.pca.inverse_transform(a.detach().cpu().numpy()), device=x.device, dtype=x.dtype,
+                           requires_grad=True)
+        return out.view(b, c, w, h)
+
+    def __repr__(self):
+        return f"QIDDM_PP(qlayer={self.spectrum_layer}, features={self.hidden_features}, N={self.N})"
+
+    def save_name(self) -> str:
+        return f"QIDDM_PP_features={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
+
+    def save_model(self, path):
+        model_dict = {"model_state_dict": self.state_dict()}
+        if self.pca is not None:
+            model_dict["pca_state"] = pickle.dumps(self.pca)
+        torch.save(model_dict, path)
+
+    def load_model(self, path):
+        checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+        self.load_state_dict(checkpoint["model_state_dict"])
+        if "pca_state" in checkpoint:
+            self.pca = pickle.loads(checkpoint["pca_state"])
+
+
+__all__ = [
+    "QDenseUndirected_old", "QDenseUndirected_old_noise", "QNN_A", "QNN_noise", "QNN", "differN_noise",
+    "differN_noise_befor", "QIDDM_PL_noise1", "differN_old_pca", "differN_new_pca", "differN_new_conv",
+    "differN_old_conv", "QIDDM_CL_new", "QIDDM_CL_old", "QIDDM_PL_old", "QIDDM_PL", "QIDDM_PL_noise",
+    "QIDDM_LL_relu_noise", "QIDDM_LL_noise", "QIDDM_PP_noise", "QIDDM_PP_old", "QIDDM_LL_old",
+    "QIDDM_bias_false", "QIDDM_L_B", "QIDDM_A_differN_basePL", "QIDDM_A_sameN", "QIDDM_A_differN_NEW",
+]

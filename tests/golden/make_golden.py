@@ -1,0 +1,98 @@
+"""Generates the golden fixtures under tests/golden/ (run in the build container, where
+/root/reference is mounted; the GPU box never sees /root/reference).
+
+* f1_qdense_label14.pt / f1_differn_label14.pt — weights trained by the REAL PennyLane stack, taken
+  verbatim from the reference artefact results/emnist.zip (fixture F1), plus the oracle's
+  sampler output / stage outputs for them.
+* f2_state_dict_contract.json — key names / shapes / dtypes of every shipped checkpoint family (F2).
+* stage_vectors.pt — oracle outputs and gradients for seeded inputs of each circuit family.
+"""
+import io
+import json
+import sys
+import zipfile
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import qiddm_oracle as O  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+REF = Path("/root/reference")
+
+
+def load_ck(z, name):
+    return torch.load(io.BytesIO(z.read(name)), weights_only=False, map_location="cpu")
+
+
+def main():
+    z = zipfile.ZipFile(REF / "results/emnist.zip")
+    # ---- F1 a1: QDenseUndirected_old_noise(60, 28), label 14 ("O")
+    ck = load_ck(z, "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")
+    W = ck["model_state_dict"]["net.weights"]
+    torch.manual_seed(0)
+    first_x = (torch.rand(1, 784, dtype=torch.float64) * 0.75 + 0.5).reshape(1, 1, 28, 28)
+    smp = O.sample(lambda v: O.qdense_forward(v, W, O.REMAP_TANH), first_x, 40, goal="noise")
+    img = smp[0, 0]
+    contrast = (img[6:22, 6:22].mean() - (img.sum() - img[6:22, 6:22].sum()) / (784 - 256)).item()
+    one = O.qdense_forward(first_x, W, O.REMAP_TANH)
+    torch.save({"weights": W, "first_x": first_x, "sample": smp, "contrast": contrast, "one_forward": one,
+                "source": "results/emnist.zip:emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt"},
+               OUT / "f1_qdense_label14.pt")
+    print("qdense contrast", contrast)
+
+    # ---- F1 a3: differN_old_pca(28, 15, 2), label 14 — one forward on fixed angles (PCA excluded)
+    ck = load_ck(z, "emnist14/noise_0/differN_old_pca=15_N=2_w28_h28_noise0_noise_14.pt")
+    W3 = ck["model_state_dict"]["net.weights"]
+    torch.manual_seed(1)
+    ang = torch.randn(4, 10, dtype=torch.float64)
+    out3 = O.differN_forward(ang, W3.double(), 784)
+    torch.save({"weights": W3, "angles": ang, "out": out3,
+                "source": "results/emnist.zip:emnist14/noise_0/differN_old_pca=15_N=2_w28_h28_noise0_noise_14.pt"},
+               OUT / "f1_differn_label14.pt")
+
+    # ---- F2: state-dict contract of every family shipped for label 14 + tune_results
+    contract = {}
+    for name in z.namelist():
+        if name.startswith("emnist14/") and name.endswith(".pt"):
+            sd = load_ck(z, name)["model_state_dict"]
+            contract[Path(name).name] = {k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}
+    tr = sorted((REF / "tune_results").rglob("*.pt"))
+    if tr:
+        sd = torch.load(tr[0], weights_only=False, map_location="cpu")["model_state_dict"]
+        contract["tune_results:" + tr[0].name.split("_noise_")[0]] = {k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}
+    (OUT / "f2_state_dict_contract.json").write_text(json.dumps(contract, indent=1, sort_keys=True))
+
+    # ---- seeded stage vectors (forward + gradients) per family
+    fams = {
+        "qdense_60x28": (O.desc_qdense(60, 784, O.REMAP_TANH), 3),
+        "qdense_pi_tanh_8x8": (O.desc_qdense(10, 64, O.REMAP_PI_TANH), 4),
+        "qnn_a_8x8": (O.desc_qnn_a(4, 64), 4),
+        "qiddm_ll_6_14": (O.desc_reupload(6, 14, 2), 5),
+        "qiddm_pl_8_6": (O.desc_reupload(8, 6, 2), 5),
+        "qnn_noise_8_14": (O.desc_reupload(8, 1, 14), 5),
+        "differn_10_9_chain": (O.desc_reupload(10, 9, 2, readout=O.READ_PROBS, read_count=10), 3),
+        "qconv_8_8_k3": (O.desc_qconv(8, 8, (3, 3), 3), 6),
+        "qconv_1_8_k3": (O.desc_qconv(1, 8, (3, 3), 3), 6),
+        "ry_reupload_5": (O.desc_reupload(5, 4, 2, enc=O.ENC_RY), 5),
+    }
+    vec = {}
+    for i, (name, (d, B)) in enumerate(fams.items()):
+        g = torch.Generator().manual_seed(1000 + i)
+        W = (torch.randn(d.n_blocks, d.layers_per_block, d.n_qubits, 3, generator=g, dtype=torch.float64) * 0.4)
+        x = (torch.rand(B, d.n_features, generator=g, dtype=torch.float64) if d.init == O.INIT_AMPLITUDE
+             else torch.randn(B, d.n_qubits, generator=g, dtype=torch.float64))
+        Wr, xr = W.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        out = O.run_stage(d, xr, Wr)
+        go = torch.randn(out.shape, generator=g, dtype=torch.float64)
+        (out * go).sum().backward()
+        vec[name] = {"desc": dict(d.__dict__), "weights": W, "x": x, "out": out.detach(), "grad_out": go,
+                     "grad_w": Wr.grad, "grad_x": xr.grad}
+    torch.save(vec, OUT / "stage_vectors.pt")
+    print("wrote", [p.name for p in OUT.iterdir()])
+
+
+if __name__ == "__main__":
+    main()

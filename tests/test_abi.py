@@ -1,0 +1,85 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/qiddm.h declares; descriptor
+validation and error behaviour work host-side (no compute calls)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from qiddm_b200 import build
+    build.build()
+    from qiddm_b200._lib import load_library
+    return load_library()
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "qiddm.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qiddm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/qiddm.h but not exported"
+    from qiddm_b200._lib import EXPORTS
+    assert sorted(EXPORTS) == syms
+
+
+def test_abi_version_and_error_strings(lib):
+    assert lib.qiddm_abi_version() == 1
+    assert lib.qiddm_error_string(0) == b"ok"
+    assert b"invalid" in lib.qiddm_error_string(-1)
+
+
+def test_descriptor_io_sizes(lib):
+    from qiddm_b200 import _lib as L
+    s = L.StageSpec(n_qubits=10, layers_per_block=60, init=L.INIT_AMPLITUDE, n_features=784, pad_value=0.1,
+                    readout=L.READ_PROBS, read_count=784, post_scale=784.0, clamp=True)
+    d = s.to_c()
+    assert lib.qiddm_n_inputs(C.byref(d)) == 784 == s.n_in
+    assert lib.qiddm_n_outputs(C.byref(d)) == 784 == s.n_out
+    assert lib.qiddm_n_weights(C.byref(d)) == 1800 == s.n_weights
+    s2 = L.StageSpec(n_qubits=6, n_blocks=14, layers_per_block=2, enc=L.ENC_RZ, imprimitive=L.IMP_CZ,
+                     readout=L.READ_EXPVAL_Z)
+    d2 = s2.to_c()
+    assert (lib.qiddm_n_inputs(C.byref(d2)), lib.qiddm_n_outputs(C.byref(d2)), lib.qiddm_n_weights(C.byref(d2))) == (6, 6, 504)
+
+
+@pytest.mark.parametrize("bad", [dict(n_qubits=0), dict(n_qubits=13), dict(n_qubits=4, init=1, n_features=17),
+                                 dict(n_qubits=4, readout=0, read_count=9, read_stride=2),
+                                 dict(n_qubits=4, readout=1, clamp=True), dict(n_qubits=4, layers_per_block=0)])
+def test_invalid_descriptors_are_rejected(lib, bad):
+    from qiddm_b200 import _lib as L
+    kw = dict(n_qubits=4, readout=L.READ_PROBS, read_count=4)
+    kw.update(bad)
+    d = L.StageSpec(**kw).to_c()
+    h = C.c_void_p()
+    assert lib.qiddm_plan_create(C.byref(d), C.byref(h)) == -1
+    assert not h.value
+    assert lib.qiddm_n_outputs(C.byref(d)) == 0
+
+
+def test_plan_lifecycle_and_unsupported_depth(lib):
+    from qiddm_b200 import _lib as L
+    p = L.Plan(L.StageSpec(n_qubits=3, readout=L.READ_EXPVAL_Z))
+    assert p.handle.value
+    del p
+    with pytest.raises(L.QiddmError):
+        L.Plan(L.StageSpec(n_qubits=12, layers_per_block=400, readout=L.READ_EXPVAL_Z))
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from qiddm_b200 import _lib as L, nn
+    m = nn.QIDDM_LL_noise(64, 4, 2, 1)
+    with pytest.raises(L.QiddmError):
+        m.cpu()(torch.rand(2, 1, 8, 8))
+    src = "".join(p.read_text() for p in (ROOT / "qiddm_b200").rglob("*.py"))
+    assert "oracle" not in src.replace("oracle/", "")  # the product never imports the test oracle

@@ -1,0 +1,135 @@
+"""CPU tests pinning the oracle: analytic known answers, the committed golden vectors, and (when the
+reference tree is mounted) fixture F1 — checkpoints trained by the real PennyLane stack only produce
+letters under the restated conventions."""
+import io
+import math
+import zipfile
+from pathlib import Path
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import qiddm_oracle as O
+
+REF_ZIP = Path("/root/reference/results/emnist.zip")
+
+
+def test_probs_sum_to_one_and_zero_weights_permute_basis():
+    d = O.StageDesc(n_qubits=6, layers_per_block=7, init=O.INIT_AMPLITUDE, n_features=50, pad_value=0.1,
+                    readout=O.READ_PROBS, read_count=64)
+    p = O.run_stage(d, torch.rand(5, 50, dtype=torch.float64), torch.randn(1, 7, 6, 3, dtype=torch.float64))
+    assert torch.allclose(p.sum(1), torch.ones(5, dtype=torch.float64), atol=1e-12)
+    d0 = O.desc_reupload(5, 3, 2, readout=O.READ_PROBS, read_count=32)
+    d0.imprimitive = O.IMP_CNOT
+    p0 = O.run_stage(d0, torch.randn(4, 5, dtype=torch.float64), torch.zeros(3, 2, 5, 3, dtype=torch.float64))
+    assert torch.allclose(p0[:, 0], torch.ones(4, dtype=torch.float64), atol=1e-12)
+
+
+def test_ry_expval_is_cos_theta_and_rz_on_zero_state_is_invisible():
+    d = O.StageDesc(n_qubits=1, layers_per_block=1, readout=O.READ_EXPVAL_Z)
+    for th in (0.3, 1.1, 2.5):
+        z = O.run_stage(d, None, torch.tensor([[[[0.0, th, 0.0]]]], dtype=torch.float64), batch=1)
+        assert abs(z.item() - math.cos(th)) < 1e-12
+    # QNN/QNN_noise: RZ once on |0..0> is a global phase -> output independent of the input
+    dq = O.desc_reupload(4, 1, 3)
+    W = torch.randn(1, 3, 4, 3, dtype=torch.float64)
+    a, b = O.run_stage(dq, torch.randn(2, 4, dtype=torch.float64), W), O.run_stage(dq, torch.zeros(2, 4, dtype=torch.float64), W)
+    assert torch.allclose(a, b, atol=1e-12)
+
+
+def test_cnot_direction_and_wire_order():
+    """|10> (wire 0 set) --CNOT(0->1)--> |11>; index = b0*2 + b1 (wire 0 = MSB)."""
+    st = torch.zeros(1, 4, dtype=O.CDTYPE)
+    st[0, 2] = 1
+    out = O.apply_ring(st, 2, 1, O.IMP_CNOT)  # ring on 2 wires = CNOT(0,1) then CNOT(1,0)
+    # CNOT(0,1): |10>->|11>; CNOT(1,0): |11>->|01>
+    assert out[0, 1].abs() == 1
+    sign = O.ring_cz_sign(3, 1)
+    assert sign[0b110] == -1 and sign[0b101] == -1 and sign[0b111] == -1 and sign[0b100] == 1
+
+
+def test_parameter_shift_identity_matches_autograd():
+    """d f / d theta = (f(theta + pi/2) - f(theta - pi/2)) / 2 for every Rot angle (what the reference's
+    diff_method='parameter-shift' would compute, nn/qdense.py:246)."""
+    d = O.desc_reupload(3, 2, 2)
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(2, 2, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(1, 3, generator=g, dtype=torch.float64)
+    c = torch.randn(3, generator=g, dtype=torch.float64)
+    (O.run_stage(d, x, W) @ c).sum().backward()
+    for idx in [(0, 0, 0, 0), (1, 1, 2, 1), (0, 1, 1, 2), (1, 0, 0, 1)]:
+        Wp, Wm = W.detach().clone(), W.detach().clone()
+        Wp[idx] += math.pi / 2
+        Wm[idx] -= math.pi / 2
+        ps = 0.5 * ((O.run_stage(d, x, Wp) @ c).sum() - (O.run_stage(d, x, Wm) @ c).sum())
+        assert abs(ps.item() - W.grad[idx].item()) < 1e-10
+
+
+def test_unitary_collapse_equals_gate_path():
+    """Cross-implementation (nn/qconv.py:92-126): U from basis states reproduces the gate-by-gate probs."""
+    d = O.desc_qconv(2, 4, (3, 3), 3)
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn(1, 3, d.n_qubits, 3, generator=g, dtype=torch.float64)
+    U = O.circuit_unitary(d, W)
+    assert torch.allclose(U.conj().T @ U, torch.eye(d.dim, dtype=O.CDTYPE), atol=1e-12)
+    x = torch.rand(6, d.n_features, generator=g, dtype=torch.float64)
+    psi0 = O.amplitude_embedding(x, d.n_qubits, d.pad_value, d.add_offset)
+    p = (psi0 @ U.T).abs() ** 2
+    ref = torch.clamp(p * d.post_scale, 0, 1)[:, ::2][:, : d.read_count]
+    assert torch.allclose(O.run_stage(d, x, W), ref, atol=1e-12)
+
+
+def test_golden_stage_vectors_regression():
+    vec = torch.load(GOLDEN / "stage_vectors.pt", weights_only=False)
+    assert len(vec) >= 10
+    for name, v in vec.items():
+        d = O.StageDesc(**v["desc"])
+        W, x = v["weights"].clone().requires_grad_(True), v["x"].clone().requires_grad_(True)
+        out = O.run_stage(d, x, W)
+        (out * v["grad_out"]).sum().backward()
+        assert torch.allclose(out, v["out"], atol=1e-12), name
+        assert torch.allclose(W.grad, v["grad_w"], atol=1e-10), name
+        assert torch.allclose(x.grad, v["grad_x"], atol=1e-10), name
+
+
+def test_golden_f1_qdense_one_forward():
+    gold = torch.load(GOLDEN / "f1_qdense_label14.pt", weights_only=True)
+    out = O.qdense_forward(gold["first_x"], gold["weights"], O.REMAP_TANH)
+    assert torch.allclose(out, gold["one_forward"], atol=1e-12)
+    assert gold["contrast"] > 0.45
+
+
+def test_golden_f1_differn_forward():
+    gold = torch.load(GOLDEN / "f1_differn_label14.pt", weights_only=True)
+    out = O.differN_forward(gold["angles"], gold["weights"].double(), 784)
+    assert torch.allclose(out, gold["out"], atol=1e-12)
+
+
+@pytest.mark.skipif(not REF_ZIP.exists(), reason="reference artefacts not mounted (GPU box)")
+def test_f1_reference_checkpoint_draws_letter_only_with_reference_conventions():
+    """Appendix A: label-14 QDense checkpoint -> letter 'O' (centre brighter than border by > 0.3);
+    swapping the re-map to pi*tanh destroys it."""
+    z = zipfile.ZipFile(REF_ZIP)
+    ck = torch.load(io.BytesIO(z.read(
+        "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")), weights_only=False)
+    W = ck["model_state_dict"]["net.weights"]
+    torch.manual_seed(0)
+    x0 = (torch.rand(1, 784, dtype=torch.float64) * 0.75 + 0.5).reshape(1, 1, 28, 28)
+
+    def contrast(remap, iters):
+        img = O.sample(lambda v: O.qdense_forward(v, W, remap), x0, iters, goal="noise")[0, 0]
+        return (img[6:22, 6:22].mean() - (img.sum() - img[6:22, 6:22].sum()) / (784 - 256)).item()
+
+    assert contrast(O.REMAP_TANH, 20) > 0.3
+    assert contrast(O.REMAP_PI_TANH, 20) < 0.1
+
+
+def test_noise_ladder_and_training_targets():
+    """src/noise.py:105-126 + src/models.py:46-63 layout: '(batch tau) pixels', w_0 = 0, w_last = 1."""
+    x = torch.rand(3, 16, dtype=torch.float64)
+    eps = torch.rand(3, 16, dtype=torch.float64)
+    lad = O.noise_ladder(x, eps, 11).reshape(3, 11, 16)
+    assert torch.allclose(lad[:, 0], x) and torch.allclose(lad[:, -1], eps.clamp(0, 1))
+    noisy, clean = O.training_targets(x, eps, 10, (4, 4))
+    assert noisy.shape == (30, 1, 4, 4) and torch.allclose(noisy[:9], clean[1:10])
