@@ -103,10 +103,11 @@ size_t gates_bytes(const qiddm_plan *pl) { return align_up((size_t)pl->n_rot * 8
 
 int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
                  const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s) {
-    if (!pl || !weights || !out || !ws || B < 0) return QIDDM_EINVAL;
+    if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
-    if (n_inputs(&pl->d) > 0 && !in) return QIDDM_EINVAL;
     if (B == 0) return QIDDM_OK;
+    if (n_inputs(&pl->d) > 0 && !in) return QIDDM_EINVAL;
+    if (!out) return QIDDM_EINVAL;
     GateParams p = make_params(pl, u, B);
     float *gates = reinterpret_cast<float *>(ws);
     p.in = in; p.basis = basis; p.gates = gates; p.out = out;
@@ -121,9 +122,9 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
 int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
                   const void *weights, int wdtype, const float *grad_out, float *grad_in, void *grad_weights,
                   void *ws, long long B, long long grad_in_elems, cudaStream_t s) {
-    if (!pl || !weights || !grad_out || !ws || B < 0) return QIDDM_EINVAL;
+    if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
-    if (n_inputs(&pl->d) > 0 && !in) return QIDDM_EINVAL;
+    if (B > 0 && (!grad_out || (n_inputs(&pl->d) > 0 && !in))) return QIDDM_EINVAL;
     if (n_inputs(&pl->d) == 0) grad_in = nullptr;
     GateParams p = make_params(pl, u, B);
     float *gates = reinterpret_cast<float *>(ws);
