@@ -123,6 +123,23 @@ int qiddm_qconv_backward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold
 int qiddm_build_unitary(const qiddm_plan *plan, const void *weights, int weights_dtype, float *unitary,
                         void *workspace, qiddm_stream_t stream);
 
+/* ---- Unitary-collapse (tensor-core GEMM) path for amplitude-embedding circuits with a probability
+ * readout (QDenseUndirected_old[_noise], QConv2d rows): generalises the eval-mode collapse of
+ * nn/qconv.py:92-126 to training.  `prepare` collapses the circuit for the current weights into
+ * `collapsed` (qiddm_gemm_collapsed_bytes; call again whenever the weights change); forward/backward
+ * then run every instance as one row of a tcgen05 GEMM.  precision: 3 = fp32-grade (3-term fp16 split),
+ * 1 = single fp16 pass (about 1e-3 relative).  Workspace: qiddm_gemm_workspace_bytes(plan, batch). */
+int    qiddm_gemm_supported(const qiddm_plan *plan);
+size_t qiddm_gemm_collapsed_bytes(const qiddm_plan *plan);
+size_t qiddm_gemm_workspace_bytes(const qiddm_plan *plan, int64_t batch);
+int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_dtype, void *collapsed,
+                       void *workspace, qiddm_stream_t stream);
+int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *workspace,
+                       int64_t batch, int precision, qiddm_stream_t stream);
+int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const float *in, const void *weights,
+                        int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
+                        void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
+
 /* Kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
 int64_t qiddm_launch_count(void);
 

@@ -46,6 +46,8 @@ EXPORTS = [
     "qiddm_abi_version", "qiddm_error_string", "qiddm_n_inputs", "qiddm_n_outputs", "qiddm_n_weights",
     "qiddm_plan_create", "qiddm_plan_destroy", "qiddm_workspace_bytes", "qiddm_forward", "qiddm_backward",
     "qiddm_qconv_forward", "qiddm_qconv_backward", "qiddm_build_unitary", "qiddm_launch_count",
+    "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
+    "qiddm_gemm_forward", "qiddm_gemm_backward",
 ]
 
 _lib = None
@@ -92,6 +94,18 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_build_unitary.restype = i32
         lib.qiddm_build_unitary.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.qiddm_launch_count.restype = i64
+        lib.qiddm_gemm_supported.restype = i32
+        lib.qiddm_gemm_supported.argtypes = [vp]
+        lib.qiddm_gemm_collapsed_bytes.restype = C.c_size_t
+        lib.qiddm_gemm_collapsed_bytes.argtypes = [vp]
+        lib.qiddm_gemm_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_gemm_workspace_bytes.argtypes = [vp, i64]
+        lib.qiddm_gemm_prepare.restype = i32
+        lib.qiddm_gemm_prepare.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.qiddm_gemm_forward.restype = i32
+        lib.qiddm_gemm_forward.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_gemm_backward.restype = i32
+        lib.qiddm_gemm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, i32, vp]
         if lib.qiddm_abi_version() != 1:
             raise QiddmError("libqiddm_b200.so ABI version mismatch")
         _lib = lib
@@ -130,6 +144,7 @@ class StageSpec:
     clamp_lo: float = 0.0
     clamp_hi: float = 1.0
     path: int = PATH_AUTO
+    gemm_precision: int = 3   # host-side only: 3 = fp32-grade 3-term fp16 split, 1 = single fp16 pass
 
     def to_c(self) -> CircuitDesc:
         return CircuitDesc(self.n_qubits, self.n_blocks, self.layers_per_block, self.init, self.n_features,
@@ -292,6 +307,73 @@ class Plan:
                                                 _ptr(go), _ptr(grad_img), _ptr(grad_w), _ptr(ws), n,
                                                 self._stream(dev)), "qiddm_qconv_backward")
         return grad_img, grad_w
+
+    # ------------------------------------------------------------------ unitary-collapse (GEMM) path
+    def gemm_supported(self) -> bool:
+        return bool(self.lib.qiddm_gemm_supported(self.handle))
+
+    def use_gemm(self, batch: int) -> bool:
+        """PATH_AUTO rule: the collapse costs about 2^n gate-path instances per optimizer step, so it
+        pays once the batch is a few times 2^n (SURVEY.md 8d break-even)."""
+        if self.spec.path == PATH_GATE or not self.gemm_supported():
+            return False
+        if self.spec.path == PATH_GEMM:
+            return True
+        return batch >= 2 * self.spec.dim
+
+    def gemm_prepare(self, weights: torch.Tensor) -> torch.Tensor:
+        """Collapsed operator (U^T + fp16 GEMM operands) for the current weights; cached per weights version."""
+        w = self._check_weights(weights)
+        # identity of the (base) tensor object + its version counter; the cache keeps a strong reference
+        # to that object, so its address cannot be recycled by another tensor while the entry lives
+        base = weights._base if weights._base is not None else weights
+        key = (weights.storage_offset(), weights.numel(), weights._version, w.data_ptr())
+        cached = getattr(self, "_collapsed", None)
+        if cached is not None and cached[0] is base and cached[1] == key:
+            return cached[2]
+        dev = w.device
+        buf = torch.empty(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
+        ws = self._workspace(self.spec.dim, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_gemm_prepare(self.handle, _ptr(w), _wdtype(w), _ptr(buf), _ptr(ws),
+                                              self._stream(dev)), "qiddm_gemm_prepare")
+        self._collapsed = (base, key, buf)
+        return buf
+
+    def _gemm_ws(self, batch, dev):
+        with torch.cuda.device(dev):
+            nbytes = int(self.lib.qiddm_gemm_workspace_bytes(self.handle, batch))
+        return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+
+    def gemm_forward(self, x: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x, "input")
+        col = self.gemm_prepare(weights)
+        dev = col.device
+        x = x.to(torch.float32).contiguous()
+        batch = x.shape[0]
+        out = torch.empty((batch, self.spec.n_out), dtype=torch.float32, device=dev)
+        ws = self._gemm_ws(batch, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_gemm_forward(self.handle, _ptr(col), _ptr(x), _ptr(out), _ptr(ws), batch,
+                                              self.spec.gemm_precision, self._stream(dev)), "qiddm_gemm_forward")
+        return out
+
+    def gemm_backward(self, x: torch.Tensor, weights: torch.Tensor, grad_out: torch.Tensor,
+                      need_grad_in: bool = True, need_grad_w: bool = True):
+        w = self._check_weights(weights)
+        col = self.gemm_prepare(weights)
+        dev = col.device
+        x = x.to(torch.float32).contiguous()
+        go = grad_out.to(torch.float32).contiguous()
+        batch = x.shape[0]
+        grad_in = torch.empty((batch, self.spec.n_in), dtype=torch.float32, device=dev) if need_grad_in else None
+        grad_w = torch.empty_like(w) if need_grad_w else None
+        ws = self._gemm_ws(batch, dev)
+        with torch.cuda.device(dev):
+            check(self.lib.qiddm_gemm_backward(self.handle, _ptr(col), _ptr(x), _ptr(w), _wdtype(w), _ptr(go),
+                                               _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
+                                               self.spec.gemm_precision, self._stream(dev)), "qiddm_gemm_backward")
+        return grad_in, grad_w
 
     def build_unitary(self, weights: torch.Tensor) -> torch.Tensor:
         """Returns U as a (2^n, 2^n) complex64 tensor (the library writes U^T, row c = U|c>)."""

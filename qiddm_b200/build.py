@@ -11,7 +11,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libqiddm_b200.so"
-SOURCES = ["qiddm_gate.cu", "qiddm_api.cu"]
+SOURCES = ["qiddm_gate.cu", "qiddm_gemm.cu", "qiddm_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
     cmd = [find_nvcc(), *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{CSRC}", "-o", str(LIB_PATH),
-           *[str(s) for s in sources()], "-lcuda"]
+           *[str(s) for s in sources()]]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -256,6 +256,97 @@ int qiddm_build_unitary(const qiddm_plan *plan, const void *weights, int weights
                         (cudaStream_t)stream);
 }
 
+// ----------------------------------------------------------------------------- unitary-collapse (GEMM) path
+static bool gemm_eligible(const qiddm_plan *pl) {
+    const qiddm_circuit_desc &d = pl->d;
+    return d.init == QIDDM_INIT_AMPLITUDE && d.readout == QIDDM_READ_PROBS && d.n_blocks == 1 &&
+           d.enc == QIDDM_ENC_NONE && d.n_qubits >= 3;
+}
+static qiddm_plan basis_plan(const qiddm_plan *pl) {
+    qiddm_plan t = *pl;
+    t.d.init = QIDDM_INIT_BASIS;
+    t.d.enc = QIDDM_ENC_NONE;
+    t.d.readout = QIDDM_READ_STATE;
+    t.d.clamp = 0;
+    t.d.n_features = 0;
+    return t;
+}
+static size_t basis_ws_bytes(const qiddm_plan *pl) {
+    qiddm_plan t = basis_plan(pl);
+    return qiddm_workspace_bytes(&t, t.dim);
+}
+
+int qiddm_gemm_supported(const qiddm_plan *plan) { return plan && gemm_eligible(plan) ? 1 : 0; }
+
+size_t qiddm_gemm_collapsed_bytes(const qiddm_plan *plan) {
+    if (!plan || !gemm_eligible(plan)) return 0;
+    GateParams gp = make_params(plan, nullptr, 1);
+    return gemm_collapsed_bytes(gemm_shape(gp, plan->d.n_qubits));
+}
+
+size_t qiddm_gemm_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
+    if (!plan || !gemm_eligible(plan) || batch < 0) return 0;
+    GateParams gp = make_params(plan, nullptr, 1);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    return gemm_backward_ws_bytes(g, batch > 0 ? batch : 1) + basis_ws_bytes(plan) + 256;
+}
+
+int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_dtype, void *collapsed,
+                       void *workspace, qiddm_stream_t stream) {
+    if (!plan || !weights || !collapsed || !workspace) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, nullptr, 1);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    qiddm_plan t = basis_plan(plan);
+    int rc = forward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gemm_collapsed_ut(g, collapsed),
+                          workspace, t.dim, (cudaStream_t)stream);
+    if (rc != QIDDM_OK) return rc;
+    return gemm_build_operands(g, gp, collapsed, (cudaStream_t)stream);
+}
+
+int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *workspace,
+                       int64_t batch, int precision, qiddm_stream_t stream) {
+    if (!plan || !collapsed || !workspace || batch < 0) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    if (precision != 1 && precision != 3) return QIDDM_EINVAL;
+    if (batch == 0) return QIDDM_OK;
+    if (!in || !out) return QIDDM_EINVAL;
+    if (batch > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, nullptr, batch);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    return gemm_forward(g, gp, collapsed, in, out, workspace, batch, precision, (cudaStream_t)stream);
+}
+
+int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const float *in, const void *weights,
+                        int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
+                        void *workspace, int64_t batch, int precision, qiddm_stream_t stream) {
+    if (!plan || !collapsed || !workspace || !weights || batch < 0) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    if (precision != 1 && precision != 3) return QIDDM_EINVAL;
+    if (batch > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (batch == 0) {
+        if (grad_weights) {
+            const size_t esz = weights_dtype == QIDDM_DTYPE_F64 ? 8 : 4;
+            cudaError_t e = cudaMemsetAsync(grad_weights, 0, (size_t)plan->n_rot * 3 * esz, s);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return QIDDM_OK;
+    }
+    if (!in || !grad_out) return QIDDM_EINVAL;
+    GateParams gp = make_params(plan, nullptr, batch);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    float *gut = nullptr;
+    int rc = gemm_backward(g, gp, collapsed, in, grad_out, grad_in, &gut, workspace, batch, precision, s);
+    if (rc != QIDDM_OK) return rc;
+    if (!grad_weights) return QIDDM_OK;
+    // adjoint sweep on the 2^n basis columns with the READ_STATE cotangent dL/dU^T
+    qiddm_plan t = basis_plan(plan);
+    char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, batch));
+    return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
+                         t.dim, 0, s);
+}
+
 int64_t qiddm_launch_count(void) { return (int64_t)qiddm::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -1,0 +1,819 @@
+// Unitary-collapse path for the amplitude-embedding families (QDenseUndirected_old[_noise],
+// QConv2d): the weight-only circuit is collapsed once per optimizer step into its unitary U (gate
+// kernel on the 2^n basis states), after which every circuit instance is one row of a dense real GEMM
+//     Y[b, 2m+{0,1}] = sum_c f[b,c] * {Re,Im} U[k_m, c]            (k_m = m * read_stride)
+// on the 5th-gen tensor cores: tcgen05.mma (kind::f16, fp32 accumulate in TMEM), operands staged by
+// TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-stage mbarrier ring, warp-specialised
+// (TMA warp / MMA warp / TMEM-alloc warp / 4 epilogue warps), persistent over output tiles with a
+// double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.  The
+// readout  p = |Y|^2 / |f|^2 * scale -> clamp  is fused into the epilogue (tcgen05.ld -> registers).
+//
+// Precision: "x3" mode splits every fp32 operand into fp16 hi + lo (22 mantissa bits) and runs the
+// three cross terms (hi*hi, lo*hi, hi*lo) as three K-segments of the same accumulator — fp32-grade
+// results at 3x the executed flops; "x1" runs hi*hi only (about 1e-3 relative).  Scaled copies keep the
+// lo terms in fp16's normal range: lo' = lo * 2^11 is paired with hi_small = hi * 2^-11.
+//
+// Backward (same GEMM kernel, plain fp32 epilogue): recompute Y, form G = dL/dY elementwise, then
+//   dX = G W^T  and  dW^T = G^T X  (split-K, fp32 atomics), and push dW back through the circuit with
+// the adjoint gate kernel run on the 2^n basis columns (READ_STATE cotangent).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstring>
+#include "qiddm_internal.h"
+
+namespace qiddm {
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int ACC_COLS = 256;    // TMEM columns per accumulator stage (2 stages = 512 columns)
+constexpr float LO_SCALE = 2048.f;          // 2^11
+constexpr float LO_INV = 1.f / 2048.f;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups of 1024 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// GEMM: D[M,N] (+)= sum_seg A_seg[M,K] * B_seg[N,K]^T     (fp16 in, fp32 accumulate)
+// ------------------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_PROBS = 1 };
+
+struct GemmParams {
+    alignas(64) CUtensorMap a_map[3];
+    alignas(64) CUtensorMap b_map[3];
+    int n_seg;
+    int M, N, K;          // K per segment, elements
+    int bn;               // BLOCK_N: multiple of 16, <= 256
+    int stages;
+    int k_splits;         // > 1: fp32 atomics into `out` (must be zeroed)
+    int epi;
+    float *out;
+    long long ldo;
+    float out_scale;      // EPI_STORE: out = acc * out_scale
+    // EPI_PROBS
+    const float *bias;       // [N] (may be null)
+    const float *row_scale;  // [M]
+    float post_scale, clamp_lo, clamp_hi;
+    int clamp;
+    int n_out;               // number of (re,im) pairs that are real outputs
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = BM * BK * 2;
+    const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+    // barriers: full[stages], empty[stages], tfull[2], tempty[2]; then the TMEM base slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int tiles_m = (p.M + BM - 1) / BM;
+    const int tiles_n = (p.N + p.bn - 1) / p.bn;
+    const int KB = (p.K + BK - 1) / BK;
+    const int KT = p.n_seg * KB;
+    const long long total = (long long)tiles_m * tiles_n * p.k_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = (int)(w % p.k_splits);
+                const long long tile = w / p.k_splits;
+                const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
+                const int it0 = (int)((long long)split * KT / p.k_splits);
+                const int it1 = (int)((long long)(split + 1) * KT / p.k_splits);
+                for (int it = it0; it < it1; ++it) {
+                    const int seg = it / KB, kb = it - seg * KB;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), stage_bytes);
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    tma_load_2d(sa, &p.a_map[seg], full_bar(stage), kb * BK, tm * BM);
+                    tma_load_2d(sa + a_bytes, &p.b_map[seg], full_bar(stage), kb * BK, tn * p.bn);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = (int)(w % p.k_splits);
+                const int it0 = (int)((long long)split * KT / p.k_splits);
+                const int it1 = (int)((long long)(split + 1) * KT / p.k_splits);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
+                for (int it = it0; it < it1; ++it) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + a_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 elements = 32 B along K inside the 128-B swizzle row: +2 in 16-B units
+                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (TMEM -> registers -> global) =====================
+        const int q = warp & 3;   // TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            const long long tile = w / p.k_splits;
+            const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = tm * BM + q * 32 + lane;
+            const int n0 = tn * p.bn;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS;
+            const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
+            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                float v[16];
+                tc_ld16(taddr + c0, v);
+                const int col = n0 + c0;
+                if (row >= p.M || col >= p.N) continue;
+                if (p.epi == EPI_PROBS) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float re = v[2 * j], im = v[2 * j + 1];
+                        if (p.bias != nullptr && col + 2 * j + 1 < p.N) {
+                            re += __ldg(p.bias + col + 2 * j);
+                            im += __ldg(p.bias + col + 2 * j + 1);
+                        }
+                        float pr = (re * re + im * im) * rs;
+                        if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
+                        o[j] = pr;
+                    }
+                    const int m0 = col >> 1;
+                    float *dst = p.out + (long long)row * p.ldo + m0;
+                    if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
+                        reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (m0 + j < p.n_out) dst[j] = o[j];
+                    }
+                } else {
+                    float *dst = p.out + (long long)row * p.ldo + col;
+                    if (p.k_splits > 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
+                    } else if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<float4 *>(dst)[j] =
+                                make_float4(v[4 * j] * p.out_scale, v[4 * j + 1] * p.out_scale,
+                                            v[4 * j + 2] * p.out_scale, v[4 * j + 3] * p.out_scale);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col + j < p.N) dst[j] = v[j] * p.out_scale;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3(float v, __half &hi, __half &lo, __half &hs) {
+    hi = __float2half_rn(v);
+    const float h = __half2float(hi);
+    lo = __float2half_rn((v - h) * LO_SCALE);
+    hs = __float2half_rn(h * LO_INV);
+}
+
+// x (B,F) fp32 [+ fused unfold] -> Xh/Xl/Xs (B,Kp) fp16 and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).
+// One warp per row.
+__global__ void prep_x_kernel(const GateParams gp, const float *x, long long B, int F, int Kp, int n_pad,
+                              __half *Xh, __half *Xl, __half *Xs, float *inv_n2, int want_split) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float ss = 0.f;
+    for (int c = lane; c < Kp; c += 32) {
+        float f = 0.f;
+        if (c < F) f = __ldg(x + row * F + c) + gp.add_offset;
+        __half hi, lo, hs;
+        split3(f, hi, lo, hs);
+        Xh[row * Kp + c] = hi;
+        if (want_split) {
+            Xl[row * Kp + c] = lo;
+            Xs[row * Kp + c] = hs;
+        }
+        ss += f * f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+        ss += (float)n_pad * gp.pad_value * gp.pad_value;
+        inv_n2[row] = ss > 0.f ? 1.0f / ss : 0.f;
+    }
+}
+
+// From UT (row c = U|c>, complex fp32) build the GEMM weight operands (scaled by w_scale):
+//   Wn[n][c] (N x Kp), Wt[c][n] (F x Np), with n = 2m + {re,im}, value = part(UT[c][m*stride]);
+//   bias[n] = pad * sum_{c >= F} value.   One thread per (n, c).
+__global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, int Np, int stride, float w_scale,
+                               float pad, __half *Wn_h, __half *Wn_l, __half *Wn_s, __half *Wt_h, __half *Wt_l,
+                               __half *Wt_s, float *bias) {
+    const int n = blockIdx.y;
+    const int m = n >> 1, ri = n & 1;
+    float bsum = 0.f;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < max(A, Kp); c += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (c < A) {
+            const float2 u = UT[(long long)c * A + (long long)m * stride];
+            v = (ri ? u.y : u.x) * w_scale;
+        }
+        if (c < Kp) {
+            __half hi, lo, hs;
+            split3(c < F ? v : 0.f, hi, lo, hs);
+            Wn_h[(long long)n * Kp + c] = hi;
+            Wn_l[(long long)n * Kp + c] = lo;
+            Wn_s[(long long)n * Kp + c] = hs;
+            if (c < F) {
+                Wt_h[(long long)c * Np + n] = hi;
+                Wt_l[(long long)c * Np + n] = lo;
+                Wt_s[(long long)c * Np + n] = hs;
+            }
+        }
+        if (c >= F && c < A) bsum += v;
+    }
+    // block reduce of bsum -> bias[n] (bias zeroed by the caller)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(bias + n, bsum * pad);
+}
+
+// G = dL/dY from Y (B,N), grad_out (B,n_out): per (row, m):  out = scale * inv_n2 * |Y + bias|^2,
+// mask = !clamp || lo <= out <= hi;  G[2m+ri] = 2 g mask scale inv_n2 (Y+bias)[2m+ri];  S[b] += g mask out.
+// Pass 1 finds the global max |G| (for the fp16 range), pass 2 writes the scaled fp16 splits row-major
+// and transposed (N x Bp).
+__global__ void grad_y_max_kernel(const float *Y, const float *go, const float *bias, const float *inv_n2,
+                                  long long B, int N, int n_out, float scale, int clamp, float lo, float hi,
+                                  float *G, float *S, unsigned int *gmax_bits) {
+    const long long row = blockIdx.x;
+    float s_acc = 0.f, mx = 0.f;
+    const float in2 = inv_n2[row];
+    for (int m = threadIdx.x; m < n_out; m += blockDim.x) {
+        const float re = Y[row * N + 2 * m] + bias[2 * m];
+        const float im = Y[row * N + 2 * m + 1] + bias[2 * m + 1];
+        const float outv = scale * in2 * (re * re + im * im);
+        const bool pass = !clamp || (outv >= lo && outv <= hi);
+        const float g = pass ? go[row * n_out + m] : 0.f;
+        const float coef = 2.f * g * scale * in2;
+        const float gr = coef * re, gi = coef * im;
+        G[row * N + 2 * m] = gr;
+        G[row * N + 2 * m + 1] = gi;
+        s_acc += g * outv;
+        mx = fmaxf(mx, fmaxf(fabsf(gr), fabsf(gi)));
+    }
+    __shared__ float sh_s[32], sh_m[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s_acc; sh_m[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f, m2 = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) { s += sh_s[i]; m2 = fmaxf(m2, sh_m[i]); }
+        S[row] = s;
+        atomicMax(gmax_bits, __float_as_uint(m2));
+    }
+}
+
+// power-of-two scale that maps the global max |G| into [2^12, 2^13)
+__device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
+    const float mx = __uint_as_float(bits);
+    if (!(mx > 0.f)) return 1.f;
+    int e;
+    frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 13 - e);
+}
+
+// G (B,N) fp32 -> scaled fp16 splits, row-major (B,Np) and transposed (N,Bp) through a 32x32 smem tile.
+__global__ void grad_y_split_kernel(const float *G, long long B, int N, int Np, long long Bp,
+                                    const unsigned int *gmax_bits, __half *Gh, __half *Gl, __half *Gs, __half *GTh,
+                                    __half *GTl, __half *GTs) {
+    __shared__ float tile[32][33];
+    const float gsc = g_scale_from_max(*gmax_bits);
+    const long long r0 = (long long)blockIdx.y * 32;
+    const int c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long r = r0 + i;
+        const int c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (r < B && c < N) v = G[r * N + c] * gsc;
+        tile[i][threadIdx.x] = v;
+        if (r < B && c < Np) {
+            __half hi, lo, hs;
+            split3(v, hi, lo, hs);
+            Gh[r * Np + c] = hi;
+            Gl[r * Np + c] = lo;
+            Gs[r * Np + c] = hs;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;                 // row of the transposed matrix
+        const long long r = r0 + threadIdx.x;  // column of the transposed matrix
+        if (c < N && r < Bp) {
+            __half hi, lo, hs;
+            split3(tile[threadIdx.x][i], hi, lo, hs);
+            GTh[(long long)c * Bp + r] = hi;
+            GTl[(long long)c * Bp + r] = lo;
+            GTs[(long long)c * Bp + r] = hs;
+        }
+    }
+}
+
+// X splits (B,Kp) -> transposed (Kp,Bp)
+__global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, const __half *Xs, long long B, int Kp,
+                                   long long Bp, __half *XTh, __half *XTl, __half *XTs) {
+    __shared__ __half th[32][34], tl[32][34], ts[32][34];
+    const long long r0 = (long long)blockIdx.y * 32;
+    const int c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long r = r0 + i;
+        const int c = c0 + threadIdx.x;
+        const bool ok = r < B && c < Kp;
+        th[i][threadIdx.x] = ok ? Xh[r * Kp + c] : __float2half(0.f);
+        tl[i][threadIdx.x] = ok ? Xl[r * Kp + c] : __float2half(0.f);
+        ts[i][threadIdx.x] = ok ? Xs[r * Kp + c] : __float2half(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long r = r0 + threadIdx.x;
+        if (c < Kp && r < Bp) {
+            XTh[(long long)c * Bp + r] = th[threadIdx.x][i];
+            XTl[(long long)c * Bp + r] = tl[threadIdx.x][i];
+            XTs[(long long)c * Bp + r] = ts[threadIdx.x][i];
+        }
+    }
+}
+
+// dX[b,c] = dXraw[b,c] / gsc - 2 f[b,c] inv_n2[b] S[b]      (f = x + offset), in place on dX
+__global__ void finish_dx_kernel(float *dX, const float *x, const float *inv_n2, const float *S,
+                                 const unsigned int *gmax_bits, long long B, int F, float add_offset) {
+    const float inv_gsc = 1.f / g_scale_from_max(*gmax_bits);
+    const long long n = B * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / F;
+        const float f = x[i] + add_offset;
+        dX[i] = dX[i] * inv_gsc - 2.f * f * inv_n2[b] * S[b];
+    }
+}
+
+// column sums of G (B,N) -> colsum[n] (for the constant pad rows of dW), fp32 atomics per block
+__global__ void colsum_kernel(const float *G, long long B, int N, float *colsum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const long long rows_per = (B + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * rows_per;
+    const long long r1 = r0 + rows_per < B ? r0 + rows_per : B;
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += G[r * N + c];
+    atomicAdd(colsum + c, s);
+}
+
+// Assemble the READ_STATE cotangent of UT for the adjoint gate kernel:
+//   gUT[c][k_m].{re,im} = w_scale * ( c < F ? dWT[n][c] / gsc : pad * colsum[n] )   (n = 2m+ri), 0 elsewhere.
+__global__ void assemble_gut_kernel(const float *dWT, const float *colsum, const unsigned int *gmax_bits, int A, int F,
+                                    int N, int stride, float w_scale, float pad, float *gUT) {
+    const float inv_gsc = 1.f / g_scale_from_max(*gmax_bits);
+    const long long total = (long long)A * A * 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ri = (int)(i & 1);
+        const long long ck = i >> 1;
+        const int c = (int)(ck / A), k = (int)(ck % A);
+        float v = 0.f;
+        if (k % stride == 0) {
+            const int m = k / stride;
+            const int n = 2 * m + ri;
+            if (n < N) v = w_scale * (c < F ? dWT[(long long)n * F + c] * inv_gsc : pad * colsum[n]);
+        }
+        gUT[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2-D fp16 row-major (rows x cols, pitch elements) tensor map with a (64 x box_rows) SWIZZLE_128B box.
+int make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long pitch, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return QIDDM_EUNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? QIDDM_OK : QIDDM_EINVAL;
+}
+
+int pick_bn(int N) {
+    // largest multiple of 16 <= 256 that tiles N with the least padding
+    int best = 16;
+    double best_cost = 1e30;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+        const int tiles = (N + bn - 1) / bn;
+        const double waste = (double)tiles * bn / N;               // padded work
+        const double cost = waste * (1.0 + 24.0 / bn);              // small tiles pay more per-tile overhead
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+struct Operand3 {
+    const __half *h, *l, *s;
+};
+
+// D[M,N] = sum over (hi,hi) [, (lo',hi_small), (hi_small, lo')] of A * B^T
+int run_gemm(const Operand3 &A, long long a_rows, long long a_pitch, const Operand3 &Bm, long long b_rows,
+             long long b_pitch, int M, int N, int K, int n_seg, int k_splits, GemmParams &p, cudaStream_t s) {
+    p.M = M; p.N = N; p.K = K;
+    p.n_seg = n_seg;
+    p.bn = pick_bn(N);
+    p.k_splits = k_splits;
+    const __half *as[3] = {A.h, A.l, A.s};
+    const __half *bs[3] = {Bm.h, Bm.s, Bm.l};
+    for (int i = 0; i < n_seg; ++i) {
+        int rc;
+        if ((rc = make_map(&p.a_map[i], as[i], a_rows, K, a_pitch, BM)) != QIDDM_OK) return rc;
+        if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, p.bn)) != QIDDM_OK) return rc;
+    }
+    const int stage_bytes = BM * BK * 2 + p.bn * BK * 2;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.bn - 1) / p.bn) * k_splits;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gemm_kernel<<<grid, GEMM_THREADS, smem, s>>>(p);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// layout of the collapsed operator and of the per-call workspace
+// ------------------------------------------------------------------------------------------
+GemmShape gemm_shape(const GateParams &gp, int n_qubits) {
+    GemmShape g;
+    g.A = 1 << n_qubits;
+    g.F = gp.n_features;
+    g.Kp = (g.F + 7) & ~7;
+    g.n_out = gp.read_count;
+    g.N = 2 * g.n_out;
+    g.Np = (g.N + 7) & ~7;
+    g.stride = gp.read_stride;
+    g.w_scale = ldexpf(1.f, (n_qubits + 1) / 2);     // keeps |W'| ~ O(1): |U| entries are ~ 2^(-n/2)
+    return g;
+}
+
+size_t gemm_collapsed_bytes(const GemmShape &g) {
+    size_t b = 0;
+    b += al((size_t)g.A * g.A * 8);                  // UT
+    b += 3 * al((size_t)g.N * g.Kp * 2);             // Wn h/l/s
+    b += 3 * al((size_t)g.F * g.Np * 2);             // Wt h/l/s
+    b += al((size_t)g.N * 4);                        // bias
+    return b;
+}
+
+struct CollapsedView {
+    float2 *UT;
+    __half *Wn[3], *Wt[3];
+    float *bias;
+};
+static CollapsedView collapsed_view(const GemmShape &g, void *buf) {
+    CollapsedView v;
+    char *p = reinterpret_cast<char *>(buf);
+    v.UT = reinterpret_cast<float2 *>(p); p += al((size_t)g.A * g.A * 8);
+    for (int i = 0; i < 3; ++i) { v.Wn[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.N * g.Kp * 2); }
+    for (int i = 0; i < 3; ++i) { v.Wt[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.F * g.Np * 2); }
+    v.bias = reinterpret_cast<float *>(p);
+    return v;
+}
+
+int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapsed, cudaStream_t s) {
+    CollapsedView v = collapsed_view(g, collapsed);
+    cudaError_t e = cudaMemsetAsync(v.bias, 0, (size_t)g.N * 4, s);
+    if (e != cudaSuccess) return (int)e;
+    const int cmax = g.A > g.Kp ? g.A : g.Kp;
+    dim3 grid((cmax + 255) / 256, g.N);
+    build_w_kernel<<<grid, 256, 0, s>>>(v.UT, g.A, g.F, g.Kp, g.N, g.Np, g.stride, g.w_scale, gp.pad_value, v.Wn[0],
+                                        v.Wn[1], v.Wn[2], v.Wt[0], v.Wt[1], v.Wt[2], v.bias);
+    count_launch();
+    e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+float *gemm_collapsed_ut(const GemmShape &g, void *collapsed) { return reinterpret_cast<float *>(collapsed_view(g, collapsed).UT); }
+
+size_t gemm_forward_ws_bytes(const GemmShape &g, long long B) {
+    return 3 * al((size_t)B * g.Kp * 2) + al((size_t)B * 4);
+}
+
+size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
+    const long long Bp = (B + 7) & ~7LL;
+    size_t b = gemm_forward_ws_bytes(g, B);
+    b += 2 * al((size_t)B * g.N * 4);                 // Y, G
+    b += al((size_t)B * 4) + al(256);                 // S, gmax
+    b += 3 * al((size_t)B * g.Np * 2);                // G splits row-major
+    b += 3 * al((size_t)g.N * Bp * 2);                // G splits transposed
+    b += 3 * al((size_t)g.Kp * Bp * 2);               // X splits transposed
+    b += al((size_t)g.N * g.F * 4);                   // dWT
+    b += al((size_t)g.N * 4);                         // colsum
+    b += al((size_t)g.A * g.A * 8);                   // gUT
+    return b;
+}
+
+namespace {
+struct FwdWs {
+    __half *X[3];
+    float *inv_n2;
+    char *end;
+};
+FwdWs fwd_ws(const GemmShape &g, long long B, void *ws) {
+    FwdWs w;
+    char *p = reinterpret_cast<char *>(ws);
+    for (int i = 0; i < 3; ++i) { w.X[i] = reinterpret_cast<__half *>(p); p += al((size_t)B * g.Kp * 2); }
+    w.inv_n2 = reinterpret_cast<float *>(p); p += al((size_t)B * 4);
+    w.end = p;
+    return w;
+}
+}  // namespace
+
+int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x, float *out,
+                 void *ws, long long B, int n_seg, cudaStream_t s) {
+    CollapsedView v = collapsed_view(g, const_cast<void *>(collapsed));
+    FwdWs w = fwd_ws(g, B, ws);
+    const int warps = 8;
+    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(gp, x, B, g.F, g.Kp, g.A - g.F, w.X[0],
+                                                                           w.X[1], w.X[2], w.inv_n2, n_seg > 1);
+    count_launch();
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.epi = EPI_PROBS;
+    p.out = out; p.ldo = g.n_out; p.out_scale = 1.f;
+    p.bias = v.bias; p.row_scale = w.inv_n2;
+    p.post_scale = gp.post_scale / (g.w_scale * g.w_scale);
+    p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
+    p.n_out = g.n_out;
+    Operand3 A{w.X[0], w.X[1], w.X[2]}, Bm{v.Wn[0], v.Wn[1], v.Wn[2]};
+    return run_gemm(A, B, g.Kp, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
+}
+
+// Produces grad_in (B,F) (nullable) and the READ_STATE cotangent gUT (A x 2A fp32, ACCUMULATED into
+// `gut_accum` which the caller zeroes) for the adjoint gate kernel.
+int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,
+                  const float *grad_out, float *grad_in, float **gut_out, void *ws, long long B, int n_seg,
+                  cudaStream_t s) {
+    CollapsedView v = collapsed_view(g, const_cast<void *>(collapsed));
+    FwdWs w = fwd_ws(g, B, ws);
+    const long long Bp = (B + 7) & ~7LL;
+    char *p8 = w.end;
+    float *Y = reinterpret_cast<float *>(p8); p8 += al((size_t)B * g.N * 4);
+    float *G = reinterpret_cast<float *>(p8); p8 += al((size_t)B * g.N * 4);
+    float *S = reinterpret_cast<float *>(p8); p8 += al((size_t)B * 4);
+    unsigned int *gmax = reinterpret_cast<unsigned int *>(p8); p8 += al(256);
+    __half *Gs[3], *GT[3], *XT[3];
+    for (int i = 0; i < 3; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
+    for (int i = 0; i < 3; ++i) { GT[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)g.N * Bp * 2); }
+    for (int i = 0; i < 3; ++i) { XT[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)g.Kp * Bp * 2); }
+    float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.F * 4);
+    float *colsum = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * 4);
+    float *gUT = reinterpret_cast<float *>(p8);
+    *gut_out = gUT;
+
+    cudaError_t e;
+    // (1) X splits + norms, always with all three splits (the backward GEMMs need them)
+    const int warps = 8;
+    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(gp, x, B, g.F, g.Kp, g.A - g.F, w.X[0],
+                                                                           w.X[1], w.X[2], w.inv_n2, 1);
+    count_launch();
+    // (2) Y = X W  (scaled by w_scale), plain fp32 store
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.epi = EPI_STORE; p.out = Y; p.ldo = g.N; p.out_scale = 1.f;
+    Operand3 Xo{w.X[0], w.X[1], w.X[2]}, Wn{v.Wn[0], v.Wn[1], v.Wn[2]};
+    int rc = run_gemm(Xo, B, g.Kp, Wn, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
+    if (rc != QIDDM_OK) return rc;
+    // (3) G = dL/dY', S, global max
+    if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
+    const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
+    grad_y_max_kernel<<<(unsigned)B, 256, 0, s>>>(Y, grad_out, v.bias, w.inv_n2, B, g.N, g.n_out, eff_scale, gp.clamp,
+                                                  gp.clamp_lo, gp.clamp_hi, G, S, gmax);
+    count_launch();
+    dim3 tb(32, 8);
+    dim3 tg((g.Np + 31) / 32, (unsigned)((Bp + 31) / 32));
+    grad_y_split_kernel<<<tg, tb, 0, s>>>(G, B, g.N, g.Np, Bp, gmax, Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2]);
+    count_launch();
+    // (4) dX = G W^T (scaled by gsc), then the normalisation term
+    if (grad_in != nullptr) {
+        memset(&p, 0, sizeof(p));
+        p.epi = EPI_STORE; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
+        Operand3 Go{Gs[0], Gs[1], Gs[2]}, Wt{v.Wt[0], v.Wt[1], v.Wt[2]};
+        rc = run_gemm(Go, B, g.Np, Wt, g.F, g.Np, (int)B, g.F, g.N, n_seg, 1, p, s);
+        if (rc != QIDDM_OK) return rc;
+        finish_dx_kernel<<<1184, 256, 0, s>>>(grad_in, x, w.inv_n2, S, gmax, B, g.F, gp.add_offset);
+        count_launch();
+    }
+    // (5) dW^T[n][c] = sum_b G[b,n] f[b,c]  (split-K over the batch, fp32 atomics), pad rows via column sums
+    dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
+    transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], w.X[2], B, g.Kp, Bp, XT[0], XT[1], XT[2]);
+    count_launch();
+    if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.F * 4, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(colsum, 0, (size_t)g.N * 4, s)) != cudaSuccess) return (int)e;
+    {
+        memset(&p, 0, sizeof(p));
+        p.epi = EPI_STORE; p.out = dWT; p.ldo = g.F; p.out_scale = 1.f;
+        Operand3 GTo{GT[0], GT[1], GT[2]}, XTo{XT[0], XT[1], XT[2]};
+        const int tiles = ((g.N + BM - 1) / BM) * ((g.F + pick_bn(g.F) - 1) / pick_bn(g.F));
+        long long kt = (long long)n_seg * ((Bp + BK - 1) / BK);
+        int splits = (int)((2 * 148 + tiles - 1) / tiles);
+        if (splits > kt) splits = (int)kt;
+        if (splits < 1) splits = 1;
+        rc = run_gemm(GTo, g.N, Bp, XTo, g.F, Bp, g.N, g.F, (int)Bp, n_seg, splits, p, s);
+        if (rc != QIDDM_OK) return rc;
+    }
+    if (g.F < g.A) {
+        dim3 cg((g.N + 127) / 128, 64);
+        colsum_kernel<<<cg, 128, 0, s>>>(G, B, g.N, colsum);
+        count_launch();
+    }
+    assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, colsum, gmax, g.A, g.F, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
+    count_launch();
+    e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+}  // namespace qiddm

@@ -41,4 +41,21 @@ cudaError_t launch_finalize_grads(const float *partials, int n_partials, const v
                                   int remap, int n_rot, void *grad_weights, cudaStream_t s);
 void count_launch(int n = 1);
 
+// qiddm_gemm.cu — unitary-collapse path (amplitude families)
+struct GemmShape {
+    int A, F, Kp, n_out, N, Np, stride;
+    float w_scale;
+};
+GemmShape gemm_shape(const GateParams &gp, int n_qubits);
+size_t gemm_collapsed_bytes(const GemmShape &g);
+float *gemm_collapsed_ut(const GemmShape &g, void *collapsed);
+int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapsed, cudaStream_t s);
+size_t gemm_forward_ws_bytes(const GemmShape &g, long long B);
+size_t gemm_backward_ws_bytes(const GemmShape &g, long long B);
+int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x, float *out,
+                 void *ws, long long B, int n_seg, cudaStream_t s);
+int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,
+                  const float *grad_out, float *grad_in, float **gut_out, void *ws, long long B, int n_seg,
+                  cudaStream_t s);
+
 }  // namespace qiddm

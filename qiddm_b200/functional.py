@@ -17,7 +17,11 @@ class _StageFunction(torch.autograd.Function):
     def forward(ctx, plan: Plan, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int]):
         ctx.plan = plan
         ctx.x_dtype = x.dtype if x is not None else None
-        out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch)
+        ctx.gemm = x is not None and plan.use_gemm(x.shape[0])
+        if ctx.gemm:
+            out = plan.gemm_forward(x.detach(), weights)
+        else:
+            out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch)
         ctx.save_for_backward(x if x is not None else torch.empty(0), weights)
         ctx.has_x = x is not None
         return out.to(x.dtype if x is not None else weights.dtype)
@@ -28,7 +32,10 @@ class _StageFunction(torch.autograd.Function):
         x = x if ctx.has_x else None
         need_x = ctx.has_x and ctx.needs_input_grad[1]
         need_w = ctx.needs_input_grad[2]
-        gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
+        if ctx.gemm:
+            gi, gw = ctx.plan.gemm_backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
+        else:
+            gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
         if gi is not None:
             gi = gi.to(ctx.x_dtype)
         return None, gi, (gw.view_as(weights) if gw is not None else None), None
