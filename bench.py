@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="circuit instances per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--path", default="auto", choices=["auto", "gate", "gemm"],
+                    help="auto = library dispatch (unitary-collapse tcgen05 GEMM when batch >= 2 * 2^n)")
+    ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
+                    help="GEMM path: 3 = fp32-grade 3-term fp16 split (default), 1 = single fp16 pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
@@ -159,19 +163,30 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
 
+    import dataclasses
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import models, noise
     torch.manual_seed(42 + rank)
     net = qnn.QDenseUndirected_old_noise(QDEPTH, SIDE).to(dev, torch.float64)
     if world > 1:
         dist.broadcast(net.weights.data, 0)
-    spec = net._spec()
+    path_id = {"auto": L.PATH_AUTO, "gate": L.PATH_GATE, "gemm": L.PATH_GEMM}[args.path]
+    spec = dataclasses.replace(net._spec(), path=path_id, gemm_precision=args.precision)
+    net._spec = lambda: spec                                   # the module API (e2e) uses the same dispatch
     plan = Plan.get(spec)
+    use_gemm = plan.use_gemm(B)
     x = torch.rand(B, PIXELS, device=dev, dtype=torch.float32)               # resident in HBM
-    go = torch.randn(B, PIXELS, device=dev, dtype=torch.float32)
+    go = torch.randn(B, PIXELS, device=dev, dtype=torch.float32) / (B * PIXELS)
     w = net.weights.detach()
 
     def step_device():
-        out = plan.forward(x, w)
-        gi, gw = plan.backward(x, w, go, need_grad_in=True, need_grad_w=True)
+        w.add_(0.0)            # bumps the version counter like an optimizer step: the collapse is redone
+        if use_gemm:
+            out = plan.gemm_forward(x, w)
+            gi, gw = plan.gemm_backward(x, w, go, need_grad_in=True, need_grad_w=True)
+        else:
+            out = plan.forward(x, w)
+            gi, gw = plan.backward(x, w, go, need_grad_in=True, need_grad_w=True)
         if world > 1:
             dist.all_reduce(gw)
         return out, gi, gw
@@ -191,25 +206,21 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.3)
     # --- timed region: exactly K steps, CUDA events on the launching (current) stream
+    L.timing_enable(True)
+    L.timing_collect()
     launches0 = qiddm_b200.launch_count()
-    bwd_ev = []
     sync_all()
     t_wall0 = time.perf_counter()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(K):
-        out = plan.forward(x, w)
-        a, b = ev(), ev()
-        a.record()
-        gi, gw = plan.backward(x, w, go, need_grad_in=True, need_grad_w=True)
-        b.record()
-        bwd_ev.append((a, b))
-        if world > 1:
-            dist.all_reduce(gw)
+        step_device()
     e1.record()
     sync_all()
     t_wall1 = time.perf_counter()
     launches = qiddm_b200.launch_count() - launches0
+    kinds = L.timing_collect()
+    L.timing_enable(False)
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -218,19 +229,23 @@ def run_b200(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_step = ms / K
     value = B * world / (ms_step * 1e-3)
-    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / len(bwd_ev)
 
-    # --- e2e: host (pinned) buffers -> module API -> loss + weight gradient back on the host
-    xh = torch.rand(B, 1, SIDE, SIDE, dtype=torch.float32).pin_memory()
-    th = torch.rand(B, 1, SIDE, SIDE, dtype=torch.float32).pin_memory()
+    # --- e2e: the QIDDM training step through the public module API (src/models.py:44-67): pinned host
+    # images -> H2D -> noise ladder (tau = 10 instances per image) -> QDense net -> MSE -> backward ->
+    # loss + circuit-weight gradient back on the host.  B instances/step = B/10 images/step.
+    TAU = 10
+    imgs = max(1, B // TAU)
+    diff = models.Diffusion(net, noise.add_normal_noise_multiple, "data", (SIDE, SIDE), torch.nn.MSELoss()).to(dev)
+    diff.train()
+    xh = torch.rand(imgs, PIXELS, dtype=torch.float32).pin_memory()
     res_h = torch.empty(1 + net.weights.numel(), dtype=torch.float64).pin_memory()
 
     def step_e2e():
         xd = xh.to(dev, non_blocking=True)
-        td = th.to(dev, non_blocking=True)
         net.weights.grad = None
-        loss = torch.nn.functional.mse_loss(net(xd), td)
-        loss.backward()
+        with torch.no_grad():
+            net.weights.add_(0.0)
+        (loss,) = diff(x=xd, T=TAU)
         g = net.weights.grad
         if world > 1:
             dist.all_reduce(g)
@@ -252,40 +267,57 @@ def run_b200(args):
         t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = t.item()
-    e2e_val = B * world / (ms_e / ke * 1e-3)
+    e2e_val = imgs * TAU * world / (ms_e / ke * 1e-3)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # --- roofline of the dominant kernel (adjoint backward gate kernel)
+    # --- roofline of the dominant kernel (largest share of the timed region, measured live)
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
         peaks = json.loads(pk.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = B * 4 * (PIXELS * 3)                       # read x, read grad_out, write grad_in (fp32)
-    achieved = alg_bytes / (bwd_ms * 1e-3) / 1e9
-    fwd_flop = QDEPTH * NQ * 14 * (1 << NQ)                # 14*A flop per Rot
-    bwd_flop = 4 * fwd_flop                                # recompute + un-apply + cotangent + apply-dagger
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     fp32_peak = 148 * 128 * 2 * (float(peaks.get("sm_max_mhz", 1965.0)) * 1e6) / 1e12
-    roofline = {"kernel": "gate_kernel<10,4,BWD> (adjoint backward, gate path)", "bound": "hbm",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "ms_per_launch": bwd_ms,
-                "note": "the gate path is FP32-FMA/shared-memory bound, not HBM bound (SURVEY.md 8d); "
-                        "fp32 view below",
-                "fp32": {"achieved_tflops": B * bwd_flop / (bwd_ms * 1e-3) / 1e12, "peak_tflops_nominal": fp32_peak,
-                         "frac": B * bwd_flop / (bwd_ms * 1e-3) / 1e12 / fp32_peak,
-                         "algorithmic_flop_per_eval_bwd": bwd_flop}}
+    shares = {k: v["ms"] / ms for k, v in kinds.items() if v["launches"]}
+    dom = max(shares, key=shares.get)
+    kd = kinds[dom]
+    per_launch_ms = kd["ms"] / kd["launches"]
+    if dom == "gemm":
+        achieved = kd["work"] / (kd["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": "gemm_kernel (tcgen05.mma kind::f16 + TMA, fused |Y|^2 readout epilogue)",
+                    "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tc_peak, "traffic": None,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
+                    "ms_per_launch": per_launch_ms, "launches": kd["launches"],
+                    "algorithmic_flops": "2*M*N*K per GEMM (single pass); precision %d executes %dx that"
+                                         % (args.precision, args.precision),
+                    "executed_tflops": achieved * args.precision, "share_of_step": shares[dom]}
+    else:
+        alg_bytes = B * 4 * (PIXELS * 3) * K                 # x in, grad_out in, grad_in out (fp32) per launch
+        achieved = alg_bytes / (kd["ms"] * 1e-3) / 1e9
+        tf = kd["work"] / (kd["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": f"gate_kernel<{NQ},*> ({dom}, gate path)", "bound": "hbm", "achieved": achieved,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "ms_per_launch": per_launch_ms,
+                    "launches": kd["launches"], "share_of_step": shares[dom],
+                    "note": "the gate path is FP32-FMA/shared-memory bound, not HBM bound (SURVEY.md 8d)",
+                    "fp32": {"achieved_tflops": tf, "peak_tflops_nominal": fp32_peak, "frac": tf / fp32_peak}}
+    roofline["kernel_shares_of_step"] = shares
+    roofline["kernel_ms_per_step"] = {k: v["ms"] / K for k, v in kinds.items() if v["launches"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(B, world), "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * B * PIXELS * 4,
+            "dtype": ("f32 (tcgen05 fp16 x%d split, fp32 accumulate)" % args.precision) if use_gemm else "f32",
+            "data": "synthetic", "config": workload_config(B, world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": imgs * PIXELS * 4,
                     "d2h_bytes_per_step": res_h.numel() * 8, "ms_per_step": ms_e / ke,
-                    "api": "qiddm_b200.nn.QDenseUndirected_old_noise(60,28) module fwd + mse + backward, pinned host in/out"},
+                    "api": "qiddm_b200.models.Diffusion(QDenseUndirected_old_noise(60,28)).forward(x, T=10): "
+                           f"{imgs} pinned host images/step -> {imgs * TAU} circuit instances, loss+grad to host"},
+            "path": ("gemm_x%d" % args.precision) if use_gemm else "gate",
             "gpu_launches": int(launches), "roofline": roofline}
 
     if not args.no_extras:

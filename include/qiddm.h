@@ -140,6 +140,13 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
                         int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
                         void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
 
+/* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
+ * launching stream around each main kernel.  collect() synchronises on them and returns, per kind
+ * (0 gate forward, 1 gate adjoint backward, 2 tcgen05 GEMM, 3 other), the summed milliseconds, the
+ * summed algorithmic work (flops) and the launch count, then clears the record.  Arrays of 4. */
+void qiddm_timing_enable(int enable);
+int  qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *launches_by_kind);
+
 /* Kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
 int64_t qiddm_launch_count(void);
 

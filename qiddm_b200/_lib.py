@@ -47,7 +47,7 @@ EXPORTS = [
     "qiddm_plan_create", "qiddm_plan_destroy", "qiddm_workspace_bytes", "qiddm_forward", "qiddm_backward",
     "qiddm_qconv_forward", "qiddm_qconv_backward", "qiddm_build_unitary", "qiddm_launch_count",
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
-    "qiddm_gemm_forward", "qiddm_gemm_backward",
+    "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_timing_enable", "qiddm_timing_collect",
 ]
 
 _lib = None
@@ -106,6 +106,10 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_gemm_forward.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_gemm_backward.restype = i32
         lib.qiddm_gemm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_timing_enable.restype = None
+        lib.qiddm_timing_enable.argtypes = [i32]
+        lib.qiddm_timing_collect.restype = i32
+        lib.qiddm_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
         if lib.qiddm_abi_version() != 1:
             raise QiddmError("libqiddm_b200.so ABI version mismatch")
         _lib = lib
@@ -120,6 +124,20 @@ def check(code: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load_library().qiddm_launch_count())
+
+
+TIMING_KINDS = ("gate_forward", "gate_backward", "gemm", "other")
+
+
+def timing_enable(on: bool) -> None:
+    load_library().qiddm_timing_enable(1 if on else 0)
+
+
+def timing_collect() -> dict:
+    """{kind: {"ms": .., "work": .., "launches": ..}} since the last collect (synchronises)."""
+    ms, wk, n = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int64 * 4)()
+    check(load_library().qiddm_timing_collect(ms, wk, n), "qiddm_timing_collect")
+    return {k: {"ms": ms[i], "work": wk[i], "launches": int(n[i])} for i, k in enumerate(TIMING_KINDS)}
 
 
 @dataclass(frozen=True)

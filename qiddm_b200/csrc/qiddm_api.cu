@@ -1,12 +1,43 @@
 // C-ABI entry points of libqiddm_b200.so (see include/qiddm.h).
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 #include "qiddm_internal.h"
 
 namespace qiddm {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int kind;
+    double work;
+};
+static std::mutex g_tmutex;
+static bool g_timing = false;
+static std::vector<TimedSpan> g_spans;
+static TimedSpan g_open;
+static bool g_has_open = false;
+
+void timing_begin(int kind, double work, cudaStream_t s) {
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_tmutex);
+    if (cudaEventCreate(&g_open.a) != cudaSuccess || cudaEventCreate(&g_open.b) != cudaSuccess) return;
+    g_open.kind = kind;
+    g_open.work = work;
+    cudaEventRecord(g_open.a, s);
+    g_has_open = true;
+}
+void timing_end(cudaStream_t s) {
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_tmutex);
+    if (!g_has_open) return;
+    cudaEventRecord(g_open.b, s);
+    g_spans.push_back(g_open);
+    g_has_open = false;
+}
 }  // namespace qiddm
 
 struct qiddm_plan {
@@ -345,6 +376,34 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
     char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, batch));
     return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
                          t.dim, 0, s);
+}
+
+void qiddm_timing_enable(int enable) {
+    std::lock_guard<std::mutex> lk(qiddm::g_tmutex);
+    qiddm::g_timing = enable != 0;
+}
+
+int qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *launches_by_kind) {
+    std::lock_guard<std::mutex> lk(qiddm::g_tmutex);
+    for (int i = 0; i < qiddm::TK_COUNT; ++i) {
+        if (ms_by_kind) ms_by_kind[i] = 0;
+        if (work_by_kind) work_by_kind[i] = 0;
+        if (launches_by_kind) launches_by_kind[i] = 0;
+    }
+    int rc = QIDDM_OK;
+    for (auto &sp : qiddm::g_spans) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(sp.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
+        if (e != cudaSuccess) rc = (int)e;
+        if (ms_by_kind) ms_by_kind[sp.kind] += ms;
+        if (work_by_kind) work_by_kind[sp.kind] += sp.work;
+        if (launches_by_kind) launches_by_kind[sp.kind] += 1;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    qiddm::g_spans.clear();
+    return rc;
 }
 
 int64_t qiddm_launch_count(void) { return (int64_t)qiddm::g_launches.load(std::memory_order_relaxed); }

@@ -620,7 +620,11 @@ cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
 template <int NQ, bool BWD>
 cudaError_t launch_t(const GateParams &p, const LaunchInfo &li, cudaStream_t s) {
     constexpr int RB = BWD ? rb_backward(NQ) : rb_forward(NQ);
+    // algorithmic flops: 14 * 2^n per Rot; the adjoint sweep costs 4x a forward
+    const double work = (double)p.B * p.n_rot * 14.0 * (double)(1 << NQ) * (BWD ? 4.0 : 1.0);
+    timing_begin(BWD ? TK_GATE_BWD : TK_GATE_FWD, work, s);
     gate_kernel<NQ, RB, BWD><<<li.grid, li.block, li.smem, s>>>(p);
+    timing_end(s);
     count_launch();
     return cudaGetLastError();
 }

@@ -613,7 +613,9 @@ int run_gemm(const Operand3 &A, long long a_rows, long long a_pitch, const Opera
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.bn - 1) / p.bn) * k_splits;
     const int grid = (int)(tiles < sms ? tiles : sms);
+    timing_begin(TK_GEMM, 2.0 * (double)M * (double)N * (double)K, s);   // single-pass (algorithmic) flops
     gemm_kernel<<<grid, GEMM_THREADS, smem, s>>>(p);
+    timing_end(s);
     count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;

@@ -41,6 +41,12 @@ cudaError_t launch_finalize_grads(const float *partials, int n_partials, const v
                                   int remap, int n_rot, void *grad_weights, cudaStream_t s);
 void count_launch(int n = 1);
 
+// Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream around
+// the launches of one kind; off by default.
+enum { TK_GATE_FWD = 0, TK_GATE_BWD = 1, TK_GEMM = 2, TK_OTHER = 3, TK_COUNT = 4 };
+void timing_begin(int kind, double work, cudaStream_t s);   // work = algorithmic flops (or bytes) of the launch
+void timing_end(cudaStream_t s);
+
 // qiddm_gemm.cu — unitary-collapse path (amplitude families)
 struct GemmShape {
     int A, F, Kp, n_out, N, Np, stride;

@@ -54,7 +54,7 @@ def test_gemm_path_matches_oracle_fp32_grade(n, F, K, stride):
 def test_gemm_path_qdense_60x28_clamped_fp32_grade():
     """The bench circuit: QDenseUndirected_old_noise(60,28), clamp epilogue, 784 of 1024 amplitudes."""
     d = O.desc_qdense(60, 784, O.REMAP_TANH)
-    _run(d, B=257, seed=1, precision=3, out_tol=1e-5, grad_tol=1e-4)
+    _run(d, B=257, seed=1, precision=3, out_tol=3e-5, grad_tol=1e-4)
 
 
 def test_gemm_path_single_pass_fp16_looser_bound():
