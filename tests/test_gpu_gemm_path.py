@@ -58,7 +58,9 @@ def test_gemm_path_qdense_60x28_clamped_fp32_grade():
 
 
 def test_gemm_path_single_pass_fp16_looser_bound():
-    d = O.desc_qdense(10, 784, O.REMAP_TANH)
+    """precision 1: compared PRE-clamp (a 3e-4 output error flips the clamp mask of outputs that sit on the
+    clamp boundary, which makes their gradient discontinuous — SURVEY.md §7 'hard parts')."""
+    d = dataclasses.replace(O.desc_qdense(10, 784, O.REMAP_TANH), clamp=False)
     _run(d, B=200, seed=2, precision=1, out_tol=5e-3, grad_tol=2e-2)
 
 
