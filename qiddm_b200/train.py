@@ -1,0 +1,107 @@
+"""Data-parallel training step for `Diffusion` (the reference is single-process,
+src/mnist_exm.py:148-203).
+
+One process per GPU (torchrun).  Each rank takes whole images, so the tau-ladder, the per-batch PCA (H5)
+and BatchNorm statistics stay rank-local exactly as in the reference.  `Diffusion.forward` calls
+`.backward()` itself (src/models.py:67), so DDP wrappers do not fit: after it returns, all gradients are
+packed into ONE flat bucket (circuit weights <= 2.2 k + classical <= 30 k floats), all-reduced once
+(NCCL over NVLink on GPUs, gloo on CPU for tests) and averaged.  No collective touches the data path."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Contiguous image shard of this rank (images are independent units; ragged tails go to the low ranks)."""
+    n = x.shape[0]
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return x[start:start + base + (1 if rank < rem else 0)]
+
+
+class FlatGradBucket:
+    """Flat view over the gradients of `params` (created lazily with the first gradients' dtype/device)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.flat: Optional[torch.Tensor] = None
+
+    def _ensure(self):
+        if self.flat is None:
+            p0 = self.params[0]
+            n = sum(p.numel() for p in self.params)
+            self.flat = torch.zeros(n, dtype=torch.float32 if p0.dtype == torch.float32 else torch.float64,
+                                    device=p0.device)
+
+    def pack(self):
+        self._ensure()
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        return self.flat
+
+    def unpack(self):
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            g = self.flat[off:off + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+
+
+def allreduce_gradients(bucket: FlatGradBucket, weights: Optional[float] = None) -> None:
+    """Sum the flat bucket over ranks and divide by the world size (or weight by local/global samples)."""
+    flat = bucket.pack()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if weights is not None:
+            flat.mul_(weights)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(dist.get_world_size())
+    bucket.unpack()
+
+
+class DataParallelTrainer:
+    """opt.zero_grad(); diff(x=x_local, T=tau); all-reduce; opt.step()  — the loop body of
+    src/mnist_exm.py:175-182 with the batch sharded over ranks."""
+
+    def __init__(self, diff: torch.nn.Module, optimizer: torch.optim.Optimizer, tau: int):
+        self.diff, self.opt, self.tau = diff, optimizer, tau
+        self.bucket = FlatGradBucket(diff.parameters())
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        if self.world > 1:
+            for p in self.diff.parameters():
+                dist.broadcast(p.data, src)
+            for b in self.diff.buffers():
+                dist.broadcast(b.data, src)
+
+    def step(self, x_global: torch.Tensor, already_sharded: bool = False) -> torch.Tensor:
+        x = x_global if already_sharded else shard_batch(x_global, self.rank, self.world)
+        self.diff.train()
+        self.opt.zero_grad(set_to_none=True)
+        n_global = x_global.shape[0] if not already_sharded else None
+        if x.shape[0] > 0:
+            (loss,) = self.diff(x=x, T=self.tau)
+        else:
+            loss = torch.zeros((), device=next(self.diff.parameters()).device)
+        # the local loss is a mean over local samples: weight by the shard size so the result equals the
+        # single-process mean over the global batch
+        w = (x.shape[0] / n_global) if n_global else None
+        allreduce_gradients(self.bucket, weights=w)
+        self.opt.step()
+        return loss.detach()

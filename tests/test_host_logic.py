@@ -1,0 +1,139 @@
+"""CPU tests of the host-side mirror of the reference interface: constructors, state_dict contract (F2),
+save_name strings, noise ladder, Diffusion wrapper semantics, UNet glue helpers."""
+import json
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import qiddm_oracle as O
+
+
+def test_state_dict_contract_matches_shipped_checkpoints():
+    """F2: key names / shapes of the reference checkpoints (results/emnist.zip, tune_results) load unchanged."""
+    from qiddm_b200 import models, nn
+    contract = json.loads((GOLDEN / "f2_state_dict_contract.json").read_text())
+    builders = {
+        "QDenseUndirected_old_noise60": lambda: nn.QDenseUndirected_old_noise(60, 28),
+        "differN_old_pca=15": lambda: nn.differN_noise(28, 15, 2),
+        "QIDDM_PL_noise=8": lambda: nn.QIDDM_PL_noise(784, 8, 6, 2),
+        "QNN_linear_features=8": lambda: nn.QNN_noise(784, 8, 6),
+        "unet_undirected_d3_s8_d0": lambda: nn.UNetUndirected(3, 8, 0),
+        "tune_results:differN_noise=9": lambda: nn.differN_noise_befor(28, 9, 2),
+    }
+    seen = 0
+    for fname, keys in contract.items():
+        for prefix, build in builders.items():
+            if fname.startswith(prefix):
+                diff = models.Diffusion(build(), None, "noise", (28, 28))
+                sd = diff.state_dict()
+                want = {k: v for k, v in keys.items() if "num_batches_tracked" not in k}
+                have = {k: list(v.shape) for k, v in sd.items() if "num_batches_tracked" not in k}
+                assert set(want) == set(have), (fname, set(want) ^ set(have))
+                for k, (shape, _) in want.items():
+                    assert have[k] == shape, (fname, k)
+                seen += 1
+    assert seen >= 6
+
+
+def test_save_names_and_reprs_follow_the_reference():
+    from qiddm_b200 import nn
+    assert nn.QDenseUndirected_old(60, 28).save_name() == "QDenseUndirected_old60_w28_h28"
+    assert nn.QDenseUndirected_old_noise(60, 28).save_name() == "QDenseUndirected_old_noise60_w28_h28_noise0"
+    assert nn.QIDDM_LL_noise(784, 6, 14, 2).save_name() == "QIDDM_LL_noise=6_L=14_N=2"
+    assert nn.QIDDM_PL_noise(784, 8, 6, 2).save_name() == "QIDDM_PL_noise=8_L=6_N=2"
+    assert nn.QNN_noise("28 * 28", 8, 14).save_name() == "QNN_linear_features=8_qdepth=14_add_noise=0"
+    assert nn.differN_noise(28, 9, 2).save_name() == "differN_old_pca=9_N=2_w28_h28_noise0"
+    assert nn.differN_noise_befor(28, 9, 2).save_name() == "differN_noise=9_N=2_w28_h28"
+    assert nn.UNetUndirected(3, 8, 3).save_name() == "unet_undirected_d3_s8_d3"
+    assert nn.UNetUndirectedS(2, 4, 2).save_name() == "unet_s_undirected_d2_s4_d2"
+    assert repr(nn.QConv2d(8, 8)) == "QConv2d(8, 8, kernel_size=(3, 3), padding=(1, 1), wires=7)"
+    assert nn.QIDDM_LL_noise(784, 6, 14, 2).weights1.shape == (2, 14, 2, 6, 3)
+    assert nn.QIDDM_bias_false(64, 4, 2, 1).weights1.shape == (1, 2, 3, 4, 3)
+    assert nn.QIDDM_A_sameN(8, 3, 2).weights.shape == (3, 2, 6, 3)
+
+
+def test_all_27_dense_classes_construct():
+    from qiddm_b200 import nn
+    from qiddm_b200.nn import qdense
+    assert len(qdense.__all__) == 27
+    args = {"QDenseUndirected_old": (4, 8), "QDenseUndirected_old_noise": (4, 8), "QNN_A": (4, 8),
+            "QNN_noise": (64, 4, 2), "QNN": (64, 4, 2)}
+    for name in qdense.__all__:
+        cls = getattr(nn, name)
+        if name in args:
+            m = cls(*args[name])
+        elif name.startswith("differN") or name == "QIDDM_A_sameN":
+            m = cls(8, 2, 2)
+        elif name.startswith("QIDDM_A_differN"):
+            m = cls(8, 2, 2)
+        else:
+            m = cls(64, 4, 2, 2)
+        assert callable(m.qnode) and isinstance(m.save_name(), str)
+
+
+def test_qconv_wire_count_rule_and_noise_guard():
+    from qiddm_b200 import nn
+    cases = {(1, 8, 3): 4, (8, 8, 3): 7, (16, 16, 3): 8, (32, 32, 3): 9, (32, 16, 1): 5, (8, 1, 1): 3, (1, 1, 1): 1}
+    for (cin, cout, k), wires in cases.items():
+        assert nn.QConv2d(cin, cout, kernel_size=k, padding=k // 2).wires == wires
+    with pytest.raises(NotImplementedError):
+        nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=2)
+    with pytest.raises(NotImplementedError):
+        nn.QDenseUndirected_old_noise(4, 8, add_noise=3)
+    nn.QDenseUndirected_old_noise(4, 8, add_noise=1)       # PhaseShift before probs: a no-op
+
+
+def test_noise_ladder_matches_oracle_and_reference_layout():
+    from qiddm_b200 import noise
+    x = torch.rand(3, 16, dtype=torch.float64)
+    eps = torch.rand(3, 16, dtype=torch.float64)
+    ours = noise.add_normal_noise_multiple(x, tau=11, decay_mod=3.0, eps=eps)
+    ref = O.noise_ladder(x, eps, 11, 3.0)
+    assert ours.shape == (33, 16) and torch.allclose(ours, ref, atol=1e-12)
+    torch.manual_seed(0)
+    a = noise.add_normal_noise_multiple(x[0], tau=4)
+    assert a.shape == (4, 16) and torch.allclose(a[0], x[0])
+
+
+def test_diffusion_wrapper_with_a_classical_net_on_cpu():
+    """Diffusion keeps the reference semantics (backward inside forward, verbose outputs, sampler layout)."""
+    from qiddm_b200 import models, noise, nn
+    torch.manual_seed(0)
+    net = nn.UNetUndirected(depth=2, start_channels=4, qdepth=0)
+    diff = models.Diffusion(net, noise.add_normal_noise_multiple, "data", (8, 8), torch.nn.MSELoss()).double()
+    diff.train()
+    x = torch.rand(2, 64, dtype=torch.float64)
+    loss, recon = diff(x=x, T=5, verbose=True)
+    assert recon.shape == (10, 1, 8, 8) and loss.dim() == 0
+    assert all(p.grad is not None for p in diff.parameters())
+    diff2 = models.Diffusion(net, noise.add_normal_noise_multiple, "noise", (8, 8), torch.nn.MSELoss()).double()
+    diff2.train()
+    (l2,) = diff2(x=x, T=5)
+    assert l2.dim() == 0 and diff2.save_name() == "unet_undirected_d2_s4_d0_noise"
+    diff2.eval()
+    grid = diff2(torch.rand(3, 1, 8, 8, dtype=torch.float64), n_iters=4)
+    assert grid.shape == (5 * 8, 3 * 8)
+    last = diff2(torch.rand(3, 1, 8, 8, dtype=torch.float64), n_iters=4, only_last=True)
+    assert last.shape == (3, 1, 8, 8) and last.min() >= 0 and last.max() <= 1
+
+
+def test_unet_glue_helpers():
+    from qiddm_b200.nn import autocrop, autopad, get_label_embedding
+    big, small = torch.zeros(1, 1, 7, 7), torch.ones(1, 1, 4, 5)
+    _, padded = autopad(big, small)
+    assert padded.shape == big.shape and padded.sum() == 20
+    assert padded[0, 0, 2, 1] == 1 and padded[0, 0, 1, 1] == 0     # ceil on the leading side
+    x, cropped = autocrop(small, big)
+    assert cropped.shape[2:] == (4, 5)
+    m = get_label_embedding(torch.tensor([0.0, 1.0]), 6, 4)
+    assert m.shape == (2, 1, 6, 4) and torch.allclose(m[1, 0, :, 0], 0.1 * torch.sin(1 + torch.arange(6) / 20))
+
+
+def test_shard_batch_covers_everything_once():
+    from qiddm_b200.train import shard_batch
+    x = torch.arange(11)
+    for world in (1, 2, 3, 4, 8):
+        parts = [shard_batch(x, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(parts), x)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
