@@ -134,11 +134,15 @@ size_t qiddm_gemm_collapsed_bytes(const qiddm_plan *plan);
 size_t qiddm_gemm_workspace_bytes(const qiddm_plan *plan, int64_t batch);
 int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_dtype, void *collapsed,
                        void *workspace, qiddm_stream_t stream);
-int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *workspace,
-                       int64_t batch, int precision, qiddm_stream_t stream);
+/* `saved` (qiddm_gemm_saved_bytes) is optional: when the forward is given a buffer it keeps the fp16 operand
+ * splits and Y there and the backward reuses them (no re-materialisation GEMM); pass NULL for inference, and
+ * NULL to the backward to have it recompute them. */
+size_t qiddm_gemm_saved_bytes(const qiddm_plan *plan, int64_t batch);
+int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *saved,
+                       void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
 int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const float *in, const void *weights,
-                        int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
-                        void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
+                        int weights_dtype, const float *grad_out, const void *saved, float *grad_in,
+                        void *grad_weights, void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
 
 /* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
  * launching stream around each main kernel.  collect() synchronises on them and returns, per kind

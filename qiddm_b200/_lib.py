@@ -47,7 +47,8 @@ EXPORTS = [
     "qiddm_plan_create", "qiddm_plan_destroy", "qiddm_workspace_bytes", "qiddm_forward", "qiddm_backward",
     "qiddm_qconv_forward", "qiddm_qconv_backward", "qiddm_build_unitary", "qiddm_launch_count",
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
-    "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_timing_enable", "qiddm_timing_collect",
+    "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
+    "qiddm_timing_collect",
 ]
 
 _lib = None
@@ -103,9 +104,11 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_gemm_prepare.restype = i32
         lib.qiddm_gemm_prepare.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.qiddm_gemm_forward.restype = i32
-        lib.qiddm_gemm_forward.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_gemm_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_gemm_backward.restype = i32
-        lib.qiddm_gemm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_gemm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_gemm_saved_bytes.restype = C.c_size_t
+        lib.qiddm_gemm_saved_bytes.argtypes = [vp, i64]
         lib.qiddm_timing_enable.restype = None
         lib.qiddm_timing_enable.argtypes = [i32]
         lib.qiddm_timing_collect.restype = i32
@@ -363,21 +366,30 @@ class Plan:
             nbytes = int(self.lib.qiddm_gemm_workspace_bytes(self.handle, batch))
         return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
 
-    def gemm_forward(self, x: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    def gemm_forward(self, x: torch.Tensor, weights: torch.Tensor, save: bool = False):
+        """Returns out, or (out, saved) when `save` (training): `saved` holds the operand splits and Y."""
         _require_cuda(x, "input")
         col = self.gemm_prepare(weights)
         dev = col.device
         x = x.to(torch.float32).contiguous()
         batch = x.shape[0]
         out = torch.empty((batch, self.spec.n_out), dtype=torch.float32, device=dev)
-        ws = self._gemm_ws(batch, dev)
+        saved = None
         with torch.cuda.device(dev):
-            check(self.lib.qiddm_gemm_forward(self.handle, _ptr(col), _ptr(x), _ptr(out), _ptr(ws), batch,
-                                              self.spec.gemm_precision, self._stream(dev)), "qiddm_gemm_forward")
-        return out
+            if save:
+                saved = torch.empty(int(self.lib.qiddm_gemm_saved_bytes(self.handle, batch)), dtype=torch.uint8,
+                                    device=dev)
+                ws = torch.empty(256, dtype=torch.uint8, device=dev)
+            else:
+                ws = torch.empty(3 * (batch * ((self.spec.n_features + 7) // 8 * 8) * 2 + 256) + batch * 4 + 512,
+                                 dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_gemm_forward(self.handle, _ptr(col), _ptr(x), _ptr(out), _ptr(saved), _ptr(ws),
+                                              batch, self.spec.gemm_precision, self._stream(dev)),
+                  "qiddm_gemm_forward")
+        return (out, saved) if save else out
 
     def gemm_backward(self, x: torch.Tensor, weights: torch.Tensor, grad_out: torch.Tensor,
-                      need_grad_in: bool = True, need_grad_w: bool = True):
+                      need_grad_in: bool = True, need_grad_w: bool = True, saved: Optional[torch.Tensor] = None):
         w = self._check_weights(weights)
         col = self.gemm_prepare(weights)
         dev = col.device
@@ -389,7 +401,7 @@ class Plan:
         ws = self._gemm_ws(batch, dev)
         with torch.cuda.device(dev):
             check(self.lib.qiddm_gemm_backward(self.handle, _ptr(col), _ptr(x), _ptr(w), _wdtype(w), _ptr(go),
-                                               _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
+                                               _ptr(saved), _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
                                                self.spec.gemm_precision, self._stream(dev)), "qiddm_gemm_backward")
         return grad_in, grad_w
 

@@ -335,8 +335,14 @@ int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_
     return gemm_build_operands(g, gp, collapsed, (cudaStream_t)stream);
 }
 
-int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *workspace,
-                       int64_t batch, int precision, qiddm_stream_t stream) {
+size_t qiddm_gemm_saved_bytes(const qiddm_plan *plan, int64_t batch) {
+    if (!plan || !gemm_eligible(plan) || batch < 0) return 0;
+    GateParams gp = make_params(plan, nullptr, 1);
+    return gemm_saved_bytes(gemm_shape(gp, plan->d.n_qubits), batch > 0 ? batch : 1);
+}
+
+int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *saved,
+                       void *workspace, int64_t batch, int precision, qiddm_stream_t stream) {
     if (!plan || !collapsed || !workspace || batch < 0) return QIDDM_EINVAL;
     if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
     if (precision != 1 && precision != 3) return QIDDM_EINVAL;
@@ -345,12 +351,12 @@ int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const floa
     if (batch > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
     GateParams gp = make_params(plan, nullptr, batch);
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
-    return gemm_forward(g, gp, collapsed, in, out, workspace, batch, precision, (cudaStream_t)stream);
+    return gemm_forward(g, gp, collapsed, in, out, saved, workspace, batch, precision, (cudaStream_t)stream);
 }
 
 int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const float *in, const void *weights,
-                        int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
-                        void *workspace, int64_t batch, int precision, qiddm_stream_t stream) {
+                        int weights_dtype, const float *grad_out, const void *saved, float *grad_in,
+                        void *grad_weights, void *workspace, int64_t batch, int precision, qiddm_stream_t stream) {
     if (!plan || !collapsed || !workspace || !weights || batch < 0) return QIDDM_EINVAL;
     if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
     if (precision != 1 && precision != 3) return QIDDM_EINVAL;
@@ -368,7 +374,7 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
     GateParams gp = make_params(plan, nullptr, batch);
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
     float *gut = nullptr;
-    int rc = gemm_backward(g, gp, collapsed, in, grad_out, grad_in, &gut, workspace, batch, precision, s);
+    int rc = gemm_backward(g, gp, collapsed, in, grad_out, saved, grad_in, &gut, workspace, batch, precision, s);
     if (rc != QIDDM_OK) return rc;
     if (!grad_weights) return QIDDM_OK;
     // adjoint sweep on the 2^n basis columns with the READ_STATE cotangent dL/dU^T

@@ -127,6 +127,7 @@ struct GemmParams {
     float post_scale, clamp_lo, clamp_hi;
     int clamp;
     int n_out;               // number of (re,im) pairs that are real outputs
+    float *y_out;            // optional (EPI_PROBS): Y + bias stored as fp32 (M, N) for the backward pass
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -255,10 +256,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                             re += __ldg(p.bias + col + 2 * j);
                             im += __ldg(p.bias + col + 2 * j + 1);
                         }
+                        v[2 * j] = re;
+                        v[2 * j + 1] = im;
                         float pr = (re * re + im * im) * rs;
                         if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
                         o[j] = pr;
                     }
+                    if (p.y_out != nullptr) {
+                        float *yd = p.y_out + (long long)row * p.N + col;
+                        if (col + 16 <= p.N && ((p.N & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<float4 *>(yd)[j] =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (col + j < p.N) yd[j] = v[j];
+                        }
+                    }
+                    if (p.out == nullptr) continue;
                     const int m0 = col >> 1;
                     float *dst = p.out + (long long)row * p.ldo + m0;
                     if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
@@ -376,86 +393,91 @@ __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, in
     if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(bias + n, bsum * pad);
 }
 
-// G = dL/dY from Y (B,N), grad_out (B,n_out): per (row, m):  out = scale * inv_n2 * |Y + bias|^2,
-// mask = !clamp || lo <= out <= hi;  G[2m+ri] = 2 g mask scale inv_n2 (Y+bias)[2m+ri];  S[b] += g mask out.
-// Pass 1 finds the global max |G| (for the fp16 range), pass 2 writes the scaled fp16 splits row-major
-// and transposed (N x Bp).
-__global__ void grad_y_max_kernel(const float *Y, const float *go, const float *bias, const float *inv_n2,
-                                  long long B, int N, int n_out, float scale, int clamp, float lo, float hi,
-                                  float *G, float *S, unsigned int *gmax_bits) {
-    const long long row = blockIdx.x;
-    float s_acc = 0.f, mx = 0.f;
-    const float in2 = inv_n2[row];
-    for (int m = threadIdx.x; m < n_out; m += blockDim.x) {
-        const float re = Y[row * N + 2 * m] + bias[2 * m];
-        const float im = Y[row * N + 2 * m + 1] + bias[2 * m + 1];
-        const float outv = scale * in2 * (re * re + im * im);
-        const bool pass = !clamp || (outv >= lo && outv <= hi);
-        const float g = pass ? go[row * n_out + m] : 0.f;
-        const float coef = 2.f * g * scale * in2;
-        const float gr = coef * re, gi = coef * im;
-        G[row * N + 2 * m] = gr;
-        G[row * N + 2 * m + 1] = gi;
-        s_acc += g * outv;
-        mx = fmaxf(mx, fmaxf(fabsf(gr), fabsf(gi)));
-    }
-    __shared__ float sh_s[32], sh_m[32];
+// Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
+// |G[b,n]| = 2 |g| scale inv_n2 |Y'| <= 2 max_m|g[b,m]| * scale * sqrt(inv_n2[b]) * w_scale.
+__global__ void g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out, float scale,
+                               float w_scale, unsigned int *gmax_bits) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float mx = 0.f;
+    for (int m = lane; m < n_out; m += 32) mx = fmaxf(mx, fabsf(__ldg(go + row * n_out + m)));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s_acc; sh_m[threadIdx.x >> 5] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f, m2 = 0.f;
-        for (int i = 0; i < (blockDim.x >> 5); ++i) { s += sh_s[i]; m2 = fmaxf(m2, sh_m[i]); }
-        S[row] = s;
-        atomicMax(gmax_bits, __float_as_uint(m2));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+        const float bound = 2.f * mx * scale * sqrtf(inv_n2[row]) * w_scale;
+        if (bound > 0.f && bound < 3.0e38f) atomicMax(gmax_bits, __float_as_uint(bound));
     }
 }
 
-// power-of-two scale that maps the global max |G| into [2^12, 2^13)
+// power-of-two scale that maps the bound on max |G| into [2^13, 2^14)
 __device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
     const float mx = __uint_as_float(bits);
     if (!(mx > 0.f)) return 1.f;
     int e;
     frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
-    return ldexpf(1.f, 13 - e);
+    return ldexpf(1.f, 14 - e);
 }
 
-// G (B,N) fp32 -> scaled fp16 splits, row-major (B,Np) and transposed (N,Bp) through a 32x32 smem tile.
-__global__ void grad_y_split_kernel(const float *G, long long B, int N, int Np, long long Bp,
+// One pass over Y (= X W' + bias', saved by the forward GEMM) and grad_out:
+//   out = scale inv_n2 |Y|^2, mask = !clamp || lo <= out <= hi,  G[2m+ri] = 2 g mask scale inv_n2 Y[2m+ri]
+// written as scaled fp16 splits row-major (B,Np) AND transposed (N,Bp) through a 32x32 smem tile, plus
+// S[b] += sum_m g mask out (normalisation term of dX) and colsum[n] += sum_b G (pad rows of dW).
+__global__ void grad_y_fused_kernel(const float *Y, const float *go, const float *inv_n2, long long B, int N, int Np,
+                                    long long Bp, int n_out, float scale, int clamp, float lo, float hi,
                                     const unsigned int *gmax_bits, __half *Gh, __half *Gl, __half *Gs, __half *GTh,
-                                    __half *GTl, __half *GTs) {
+                                    __half *GTl, __half *GTs, float *S, float *colsum) {
     __shared__ float tile[32][33];
     const float gsc = g_scale_from_max(*gmax_bits);
     const long long r0 = (long long)blockIdx.y * 32;
     const int c0 = blockIdx.x * 32;
+    const int c = c0 + threadIdx.x;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const long long r = r0 + i;
-        const int c = c0 + threadIdx.x;
-        float v = 0.f;
-        if (r < B && c < N) v = G[r * N + c] * gsc;
-        tile[i][threadIdx.x] = v;
+        float gv = 0.f, s_part = 0.f;
+        if (r < B) {
+            const float yv = c < N ? Y[r * N + c] : 0.f;
+            const float partner = __shfl_xor_sync(0xffffffffu, yv, 1);
+            if (c < N) {
+                const float in2 = inv_n2[r];
+                const float outv = scale * in2 * (yv * yv + partner * partner);
+                const bool pass = !clamp || (outv >= lo && outv <= hi);
+                const float g = pass ? go[r * n_out + (c >> 1)] : 0.f;
+                gv = 2.f * g * scale * in2 * yv;
+                if ((c & 1) == 0) s_part = g * outv;
+            }
+        } else {
+            (void)__shfl_xor_sync(0xffffffffu, 0.f, 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
+        if (threadIdx.x == 0 && r < B && s_part != 0.f) atomicAdd(S + r, s_part);
+        tile[i][threadIdx.x] = gv;
         if (r < B && c < Np) {
-            __half hi, lo, hs;
-            split3(v, hi, lo, hs);
-            Gh[r * Np + c] = hi;
-            Gl[r * Np + c] = lo;
-            Gs[r * Np + c] = hs;
+            __half h, l, sm;
+            split3(gv * gsc, h, l, sm);
+            Gh[r * Np + c] = h;
+            Gl[r * Np + c] = l;
+            Gs[r * Np + c] = sm;
         }
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i;                 // row of the transposed matrix
-        const long long r = r0 + threadIdx.x;  // column of the transposed matrix
-        if (c < N && r < Bp) {
-            __half hi, lo, hs;
-            split3(tile[threadIdx.x][i], hi, lo, hs);
-            GTh[(long long)c * Bp + r] = hi;
-            GTl[(long long)c * Bp + r] = lo;
-            GTs[(long long)c * Bp + r] = hs;
+        const int cc = c0 + i;                  // row of the transposed matrix
+        const long long r = r0 + threadIdx.x;   // column of the transposed matrix
+        const float gv = tile[threadIdx.x][i];
+        if (cc < N && r < Bp) {
+            __half h, l, sm;
+            split3(gv * gsc, h, l, sm);
+            GTh[(long long)cc * Bp + r] = h;
+            GTl[(long long)cc * Bp + r] = l;
+            GTs[(long long)cc * Bp + r] = sm;
+        }
+        if (colsum != nullptr) {
+            float cs = gv;                      // rows >= B hold 0
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+            if (threadIdx.x == 0 && cc < N && cs != 0.f) atomicAdd(colsum + cc, cs);
         }
     }
 }
@@ -496,18 +518,6 @@ __global__ void finish_dx_kernel(float *dX, const float *x, const float *inv_n2,
         const float f = x[i] + add_offset;
         dX[i] = dX[i] * inv_gsc - 2.f * f * inv_n2[b] * S[b];
     }
-}
-
-// column sums of G (B,N) -> colsum[n] (for the constant pad rows of dW), fp32 atomics per block
-__global__ void colsum_kernel(const float *G, long long B, int N, float *colsum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    const long long rows_per = (B + gridDim.y - 1) / gridDim.y;
-    const long long r0 = (long long)blockIdx.y * rows_per;
-    const long long r1 = r0 + rows_per < B ? r0 + rows_per : B;
-    float s = 0.f;
-    for (long long r = r0; r < r1; ++r) s += G[r * N + c];
-    atomicAdd(colsum + c, s);
 }
 
 // Assemble the READ_STATE cotangent of UT for the adjoint gate kernel:
@@ -680,18 +690,22 @@ int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapse
 
 float *gemm_collapsed_ut(const GemmShape &g, void *collapsed) { return reinterpret_cast<float *>(collapsed_view(g, collapsed).UT); }
 
+size_t gemm_saved_bytes(const GemmShape &g, long long B) {
+    const long long Bp = (B + 7) & ~7LL;
+    return 3 * al((size_t)B * g.Kp * 2) + 3 * al((size_t)g.Kp * Bp * 2) + al((size_t)B * 4) +
+           al((size_t)B * g.N * 4);
+}
+
 size_t gemm_forward_ws_bytes(const GemmShape &g, long long B) {
     return 3 * al((size_t)B * g.Kp * 2) + al((size_t)B * 4);
 }
 
 size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
     const long long Bp = (B + 7) & ~7LL;
-    size_t b = gemm_forward_ws_bytes(g, B);
-    b += 2 * al((size_t)B * g.N * 4);                 // Y, G
+    size_t b = gemm_saved_bytes(g, B);                // used when the forward did not save
     b += al((size_t)B * 4) + al(256);                 // S, gmax
     b += 3 * al((size_t)B * g.Np * 2);                // G splits row-major
     b += 3 * al((size_t)g.N * Bp * 2);                // G splits transposed
-    b += 3 * al((size_t)g.Kp * Bp * 2);               // X splits transposed
     b += al((size_t)g.N * g.F * 4);                   // dWT
     b += al((size_t)g.N * 4);                         // colsum
     b += al((size_t)g.A * g.A * 8);                   // gUT
@@ -699,33 +713,53 @@ size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
 }
 
 namespace {
-struct FwdWs {
-    __half *X[3];
-    float *inv_n2;
+struct SavedView {
+    __half *X[3], *XT[3];
+    float *inv_n2, *Y;
     char *end;
 };
-FwdWs fwd_ws(const GemmShape &g, long long B, void *ws) {
-    FwdWs w;
-    char *p = reinterpret_cast<char *>(ws);
+// full == false: only X splits + inv_n2 (inference forward)
+SavedView saved_view(const GemmShape &g, long long B, void *buf, bool full) {
+    SavedView w;
+    const long long Bp = (B + 7) & ~7LL;
+    char *p = reinterpret_cast<char *>(buf);
     for (int i = 0; i < 3; ++i) { w.X[i] = reinterpret_cast<__half *>(p); p += al((size_t)B * g.Kp * 2); }
+    if (full) {
+        for (int i = 0; i < 3; ++i) { w.XT[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.Kp * Bp * 2); }
+    } else {
+        for (int i = 0; i < 3; ++i) w.XT[i] = nullptr;
+    }
     w.inv_n2 = reinterpret_cast<float *>(p); p += al((size_t)B * 4);
+    w.Y = nullptr;
+    if (full) { w.Y = reinterpret_cast<float *>(p); p += al((size_t)B * g.N * 4); }
     w.end = p;
     return w;
 }
 }  // namespace
 
+// Forward.  `out` may be null (backward re-materialisation).  `saved` (gemm_saved_bytes) non-null: the X / X^T
+// splits, 1/|f|^2 and Y are kept there for the backward pass; null: they live in `ws` and only `out` is produced.
 int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x, float *out,
-                 void *ws, long long B, int n_seg, cudaStream_t s) {
+                 void *saved, void *ws, long long B, int n_seg, cudaStream_t s) {
     CollapsedView v = collapsed_view(g, const_cast<void *>(collapsed));
-    FwdWs w = fwd_ws(g, B, ws);
+    const bool keep = saved != nullptr;
+    SavedView w = saved_view(g, B, keep ? saved : ws, keep);
+    const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
     prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(gp, x, B, g.F, g.Kp, g.A - g.F, w.X[0],
-                                                                           w.X[1], w.X[2], w.inv_n2, n_seg > 1);
+                                                                           w.X[1], w.X[2], w.inv_n2, keep || n_seg > 1);
     count_launch();
+    if (keep) {
+        dim3 tb(32, 8);
+        dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
+        transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], w.X[2], B, g.Kp, Bp, w.XT[0], w.XT[1], w.XT[2]);
+        count_launch();
+    }
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.epi = EPI_PROBS;
     p.out = out; p.ldo = g.n_out; p.out_scale = 1.f;
+    p.y_out = w.Y;
     p.bias = v.bias; p.row_scale = w.inv_n2;
     p.post_scale = gp.post_scale / (g.w_scale * g.w_scale);
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
@@ -734,52 +768,51 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     return run_gemm(A, B, g.Kp, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
 }
 
-// Produces grad_in (B,F) (nullable) and the READ_STATE cotangent gUT (A x 2A fp32, ACCUMULATED into
-// `gut_accum` which the caller zeroes) for the adjoint gate kernel.
+// Produces grad_in (B,F) (nullable) and the READ_STATE cotangent gUT (A x 2A fp32) for the adjoint gate kernel.
+// `saved` null: X splits / Y are re-materialised first (one extra GEMM).
 int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,
-                  const float *grad_out, float *grad_in, float **gut_out, void *ws, long long B, int n_seg,
-                  cudaStream_t s) {
+                  const float *grad_out, const void *saved, float *grad_in, float **gut_out, void *ws, long long B,
+                  int n_seg, cudaStream_t s) {
     CollapsedView v = collapsed_view(g, const_cast<void *>(collapsed));
-    FwdWs w = fwd_ws(g, B, ws);
     const long long Bp = (B + 7) & ~7LL;
-    char *p8 = w.end;
-    float *Y = reinterpret_cast<float *>(p8); p8 += al((size_t)B * g.N * 4);
-    float *G = reinterpret_cast<float *>(p8); p8 += al((size_t)B * g.N * 4);
+    char *p8 = reinterpret_cast<char *>(ws);
+    void *saved_buf = const_cast<void *>(saved);
+    if (saved_buf == nullptr) {
+        saved_buf = p8;
+        int rc0 = gemm_forward(g, gp, collapsed, x, nullptr, saved_buf, nullptr, B, n_seg, s);
+        if (rc0 != QIDDM_OK) return rc0;
+    }
+    p8 += gemm_saved_bytes(g, B);
+    SavedView w = saved_view(g, B, saved_buf, true);
     float *S = reinterpret_cast<float *>(p8); p8 += al((size_t)B * 4);
     unsigned int *gmax = reinterpret_cast<unsigned int *>(p8); p8 += al(256);
-    __half *Gs[3], *GT[3], *XT[3];
+    __half *Gs[3], *GT[3];
     for (int i = 0; i < 3; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
     for (int i = 0; i < 3; ++i) { GT[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)g.N * Bp * 2); }
-    for (int i = 0; i < 3; ++i) { XT[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)g.Kp * Bp * 2); }
     float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.F * 4);
     float *colsum = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * 4);
     float *gUT = reinterpret_cast<float *>(p8);
     *gut_out = gUT;
 
     cudaError_t e;
-    // (1) X splits + norms, always with all three splits (the backward GEMMs need them)
-    const int warps = 8;
-    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(gp, x, B, g.F, g.Kp, g.A - g.F, w.X[0],
-                                                                           w.X[1], w.X[2], w.inv_n2, 1);
-    count_launch();
-    // (2) Y = X W  (scaled by w_scale), plain fp32 store
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.epi = EPI_STORE; p.out = Y; p.ldo = g.N; p.out_scale = 1.f;
-    Operand3 Xo{w.X[0], w.X[1], w.X[2]}, Wn{v.Wn[0], v.Wn[1], v.Wn[2]};
-    int rc = run_gemm(Xo, B, g.Kp, Wn, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
-    if (rc != QIDDM_OK) return rc;
-    // (3) G = dL/dY', S, global max
-    if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
     const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
-    grad_y_max_kernel<<<(unsigned)B, 256, 0, s>>>(Y, grad_out, v.bias, w.inv_n2, B, g.N, g.n_out, eff_scale, gp.clamp,
-                                                  gp.clamp_lo, gp.clamp_hi, G, S, gmax);
+    // (1) scale bound, then one fused pass: G splits (row-major + transposed), S, colsum
+    if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(S, 0, (size_t)B * 4, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(colsum, 0, (size_t)g.N * 4, s)) != cudaSuccess) return (int)e;
+    const int warps = 8;
+    g_bound_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale,
+                                                                            g.w_scale, gmax);
     count_launch();
     dim3 tb(32, 8);
     dim3 tg((g.Np + 31) / 32, (unsigned)((Bp + 31) / 32));
-    grad_y_split_kernel<<<tg, tb, 0, s>>>(G, B, g.N, g.Np, Bp, gmax, Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2]);
+    grad_y_fused_kernel<<<tg, tb, 0, s>>>(w.Y, grad_out, w.inv_n2, B, g.N, g.Np, Bp, g.n_out, eff_scale, gp.clamp,
+                                          gp.clamp_lo, gp.clamp_hi, gmax, Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2], S,
+                                          g.F < g.A ? colsum : nullptr);
     count_launch();
-    // (4) dX = G W^T (scaled by gsc), then the normalisation term
+    GemmParams p;
+    int rc;
+    // (2) dX = G W^T (scaled by gsc), then the normalisation term
     if (grad_in != nullptr) {
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
@@ -789,28 +822,20 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         finish_dx_kernel<<<1184, 256, 0, s>>>(grad_in, x, w.inv_n2, S, gmax, B, g.F, gp.add_offset);
         count_launch();
     }
-    // (5) dW^T[n][c] = sum_b G[b,n] f[b,c]  (split-K over the batch, fp32 atomics), pad rows via column sums
-    dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
-    transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], w.X[2], B, g.Kp, Bp, XT[0], XT[1], XT[2]);
-    count_launch();
+    // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]  (split-K over the batch, fp32 atomics)
     if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.F * 4, s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(colsum, 0, (size_t)g.N * 4, s)) != cudaSuccess) return (int)e;
     {
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = dWT; p.ldo = g.F; p.out_scale = 1.f;
-        Operand3 GTo{GT[0], GT[1], GT[2]}, XTo{XT[0], XT[1], XT[2]};
-        const int tiles = ((g.N + BM - 1) / BM) * ((g.F + pick_bn(g.F) - 1) / pick_bn(g.F));
+        Operand3 GTo{GT[0], GT[1], GT[2]}, XTo{w.XT[0], w.XT[1], w.XT[2]};
+        const int bn = pick_bn(g.F);
+        const int tiles = ((g.N + BM - 1) / BM) * ((g.F + bn - 1) / bn);
         long long kt = (long long)n_seg * ((Bp + BK - 1) / BK);
         int splits = (int)((2 * 148 + tiles - 1) / tiles);
         if (splits > kt) splits = (int)kt;
         if (splits < 1) splits = 1;
         rc = run_gemm(GTo, g.N, Bp, XTo, g.F, Bp, g.N, g.F, (int)Bp, n_seg, splits, p, s);
         if (rc != QIDDM_OK) return rc;
-    }
-    if (g.F < g.A) {
-        dim3 cg((g.N + 127) / 128, 64);
-        colsum_kernel<<<cg, 128, 0, s>>>(G, B, g.N, colsum);
-        count_launch();
     }
     assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, colsum, gmax, g.A, g.F, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
     count_launch();

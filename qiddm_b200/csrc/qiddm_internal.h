@@ -56,12 +56,13 @@ GemmShape gemm_shape(const GateParams &gp, int n_qubits);
 size_t gemm_collapsed_bytes(const GemmShape &g);
 float *gemm_collapsed_ut(const GemmShape &g, void *collapsed);
 int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapsed, cudaStream_t s);
+size_t gemm_saved_bytes(const GemmShape &g, long long B);
 size_t gemm_forward_ws_bytes(const GemmShape &g, long long B);
 size_t gemm_backward_ws_bytes(const GemmShape &g, long long B);
 int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x, float *out,
-                 void *ws, long long B, int n_seg, cudaStream_t s);
+                 void *saved, void *ws, long long B, int n_seg, cudaStream_t s);
 int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,
-                  const float *grad_out, float *grad_in, float **gut_out, void *ws, long long B, int n_seg,
-                  cudaStream_t s);
+                  const float *grad_out, const void *saved, float *grad_in, float **gut_out, void *ws, long long B,
+                  int n_seg, cudaStream_t s);
 
 }  // namespace qiddm

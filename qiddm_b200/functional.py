@@ -18,8 +18,12 @@ class _StageFunction(torch.autograd.Function):
         ctx.plan = plan
         ctx.x_dtype = x.dtype if x is not None else None
         ctx.gemm = x is not None and plan.use_gemm(x.shape[0])
+        ctx.gemm_saved = None
         if ctx.gemm:
-            out = plan.gemm_forward(x.detach(), weights)
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                out, ctx.gemm_saved = plan.gemm_forward(x.detach(), weights, save=True)
+            else:
+                out = plan.gemm_forward(x.detach(), weights)
         else:
             out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch)
         ctx.save_for_backward(x if x is not None else torch.empty(0), weights)
@@ -33,7 +37,9 @@ class _StageFunction(torch.autograd.Function):
         need_x = ctx.has_x and ctx.needs_input_grad[1]
         need_w = ctx.needs_input_grad[2]
         if ctx.gemm:
-            gi, gw = ctx.plan.gemm_backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
+            gi, gw = ctx.plan.gemm_backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w,
+                                            saved=ctx.gemm_saved)
+            ctx.gemm_saved = None
         else:
             gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
         if gi is not None:
