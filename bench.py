@@ -182,8 +182,8 @@ def run_b200(args):
     def step_device():
         w.add_(0.0)            # bumps the version counter like an optimizer step: the collapse is redone
         if use_gemm:
-            out = plan.gemm_forward(x, w)
-            gi, gw = plan.gemm_backward(x, w, go, need_grad_in=True, need_grad_w=True)
+            out, saved = plan.gemm_forward(x, w, save=True)      # training forward keeps Y + operand splits
+            gi, gw = plan.gemm_backward(x, w, go, need_grad_in=True, need_grad_w=True, saved=saved)
         else:
             out = plan.forward(x, w)
             gi, gw = plan.backward(x, w, go, need_grad_in=True, need_grad_w=True)
