@@ -381,8 +381,8 @@ class Plan:
                                     device=dev)
                 ws = torch.empty(256, dtype=torch.uint8, device=dev)
             else:
-                ws = torch.empty(3 * (batch * ((self.spec.n_features + 7) // 8 * 8) * 2 + 256) + batch * 4 + 512,
-                                 dtype=torch.uint8, device=dev)
+                kp = (self.spec.n_features + 1 + 7) // 8 * 8
+                ws = torch.empty(3 * (batch * kp * 2 + 256) + batch * 4 + 512, dtype=torch.uint8, device=dev)
             check(self.lib.qiddm_gemm_forward(self.handle, _ptr(col), _ptr(x), _ptr(out), _ptr(saved), _ptr(ws),
                                               batch, self.spec.gemm_precision, self._stream(dev)),
                   "qiddm_gemm_forward")

@@ -342,7 +342,9 @@ __global__ void prep_x_kernel(const GateParams gp, const float *x, long long B, 
         float f = 0.f;
         if (c < F) f = __ldg(x + row * F + c) + gp.add_offset;
         __half hi, lo, hs;
-        split3(f, hi, lo, hs);
+        // column F (when the state has constant pad rows) is a column of ones: it meets zero weights in
+        // the forward / dX GEMMs and yields sum_b G[b,n] (the pad rows of dW) in the dW GEMM
+        split3((c == F && n_pad > 0) ? 1.f : f, hi, lo, hs);
         Xh[row * Kp + c] = hi;
         if (want_split) {
             Xl[row * Kp + c] = lo;
@@ -421,64 +423,75 @@ __device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
 
 // One pass over Y (= X W' + bias', saved by the forward GEMM) and grad_out:
 //   out = scale inv_n2 |Y|^2, mask = !clamp || lo <= out <= hi,  G[2m+ri] = 2 g mask scale inv_n2 Y[2m+ri]
-// written as scaled fp16 splits row-major (B,Np) AND transposed (N,Bp) through a 32x32 smem tile, plus
-// S[b] += sum_m g mask out (normalisation term of dX) and colsum[n] += sum_b G (pad rows of dW).
-__global__ void grad_y_fused_kernel(const float *Y, const float *go, const float *inv_n2, long long B, int N, int Np,
-                                    long long Bp, int n_out, float scale, int clamp, float lo, float hi,
-                                    const unsigned int *gmax_bits, __half *Gh, __half *Gl, __half *Gs, __half *GTh,
-                                    __half *GTl, __half *GTs, float *S, float *colsum) {
-    __shared__ float tile[32][33];
+// written as scaled fp16 splits row-major (B,Np) AND transposed (N,Bp) through a 64x64 smem tile, plus
+// S[b] = sum_m g mask out (normalisation term of dX).  One block owns 64 rows and walks all columns, so S
+// needs no atomics; every global access is a 128-byte warp transaction (float2 / half2 per thread).
+__global__ void __launch_bounds__(256) grad_y_fused_kernel(
+    const float *Y, const float *go, const float *inv_n2, long long B, int N, int Np, long long Bp, int n_out,
+    float scale, int clamp, float lo, float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl, __half *Gs,
+    __half *GTh, __half *GTl, __half *GTs, float *S) {
+    __shared__ float tile[64][65];
     const float gsc = g_scale_from_max(*gmax_bits);
-    const long long r0 = (long long)blockIdx.y * 32;
-    const int c0 = blockIdx.x * 32;
-    const int c = c0 + threadIdx.x;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const long long r = r0 + i;
-        float gv = 0.f, s_part = 0.f;
-        if (r < B) {
-            const float yv = c < N ? Y[r * N + c] : 0.f;
-            const float partner = __shfl_xor_sync(0xffffffffu, yv, 1);
-            if (c < N) {
-                const float in2 = inv_n2[r];
-                const float outv = scale * in2 * (yv * yv + partner * partner);
-                const bool pass = !clamp || (outv >= lo && outv <= hi);
-                const float g = pass ? go[r * n_out + (c >> 1)] : 0.f;
-                gv = 2.f * g * scale * in2 * yv;
-                if ((c & 1) == 0) s_part = g * outv;
-            }
-        } else {
-            (void)__shfl_xor_sync(0xffffffffu, 0.f, 1);
-        }
+    const int tx = threadIdx.x, ty = threadIdx.y;     // 32 x 8
+    const long long r0 = (long long)blockIdx.x * 64;
+    float s_part[8], in2[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
-        if (threadIdx.x == 0 && r < B && s_part != 0.f) atomicAdd(S + r, s_part);
-        tile[i][threadIdx.x] = gv;
-        if (r < B && c < Np) {
-            __half h, l, sm;
-            split3(gv * gsc, h, l, sm);
-            Gh[r * Np + c] = h;
-            Gl[r * Np + c] = l;
-            Gs[r * Np + c] = sm;
-        }
+    for (int i = 0; i < 8; ++i) {
+        s_part[i] = 0.f;
+        const long long r = r0 + ty + 8 * i;
+        in2[i] = r < B ? inv_n2[r] : 0.f;
     }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int cc = c0 + i;                  // row of the transposed matrix
-        const long long r = r0 + threadIdx.x;   // column of the transposed matrix
-        const float gv = tile[threadIdx.x][i];
-        if (cc < N && r < Bp) {
-            __half h, l, sm;
-            split3(gv * gsc, h, l, sm);
-            GTh[(long long)cc * Bp + r] = h;
-            GTl[(long long)cc * Bp + r] = l;
-            GTs[(long long)cc * Bp + r] = sm;
-        }
-        if (colsum != nullptr) {
-            float cs = gv;                      // rows >= B hold 0
+    for (int c0 = 0; c0 < Np; c0 += 64) {
+        const int c = c0 + 2 * tx;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
-            if (threadIdx.x == 0 && cc < N && cs != 0.f) atomicAdd(colsum + cc, cs);
+        for (int i = 0; i < 8; ++i) {
+            const long long r = r0 + ty + 8 * i;
+            float gre = 0.f, gim = 0.f;
+            if (r < B && c < N) {
+                const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + c);
+                const float outv = scale * in2[i] * (y.x * y.x + y.y * y.y);
+                const bool pass = !clamp || (outv >= lo && outv <= hi);
+                const float g = pass ? __ldg(go + r * n_out + (c >> 1)) : 0.f;
+                const float coef = 2.f * g * scale * in2[i];
+                gre = coef * y.x;
+                gim = coef * y.y;
+                s_part[i] += g * outv;
+            }
+            tile[ty + 8 * i][2 * tx] = gre;
+            tile[ty + 8 * i][2 * tx + 1] = gim;
+            if (r < B && c < Np) {
+                __half h0, l0, s0, h1, l1, s1;
+                split3(gre * gsc, h0, l0, s0);
+                split3(gim * gsc, h1, l1, s1);
+                *reinterpret_cast<__half2 *>(Gh + r * Np + c) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2 *>(Gl + r * Np + c) = __halves2half2(l0, l1);
+                *reinterpret_cast<__half2 *>(Gs + r * Np + c) = __halves2half2(s0, s1);
+            }
         }
+        __syncthreads();
+        const long long r = r0 + 2 * tx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int cc = ty + 8 * j;
+            const int n = c0 + cc;
+            if (n < N && r < Bp) {
+                __half h0, l0, s0, h1, l1, s1;
+                split3(tile[2 * tx][cc] * gsc, h0, l0, s0);
+                split3(tile[2 * tx + 1][cc] * gsc, h1, l1, s1);
+                *reinterpret_cast<__half2 *>(GTh + (long long)n * Bp + r) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2 *>(GTl + (long long)n * Bp + r) = __halves2half2(l0, l1);
+                *reinterpret_cast<__half2 *>(GTs + (long long)n * Bp + r) = __halves2half2(s0, s1);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = s_part[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const long long r = r0 + ty + 8 * i;
+        if (tx == 0 && r < B) S[r] = v;
     }
 }
 
@@ -521,20 +534,21 @@ __global__ void finish_dx_kernel(float *dX, const float *x, const float *inv_n2,
 }
 
 // Assemble the READ_STATE cotangent of UT for the adjoint gate kernel:
-//   gUT[c][k_m].{re,im} = w_scale * ( c < F ? dWT[n][c] / gsc : pad * colsum[n] )   (n = 2m+ri), 0 elsewhere.
-__global__ void assemble_gut_kernel(const float *dWT, const float *colsum, const unsigned int *gmax_bits, int A, int F,
-                                    int N, int stride, float w_scale, float pad, float *gUT) {
-    const float inv_gsc = 1.f / g_scale_from_max(*gmax_bits);
+//   gUT[c][k_m].{re,im} = w_scale / gsc * ( c < F ? dWT[n][c] : pad * dWT[n][F] )   (n = 2m+ri), 0 elsewhere;
+// dWT[n][F] is the ones-column entry = sum_b G[b,n].
+__global__ void assemble_gut_kernel(const float *dWT, const unsigned int *gmax_bits, int A, int F, int Fx, int N,
+                                    int stride, float w_scale, float pad, float *gUT) {
+    const float k = w_scale / g_scale_from_max(*gmax_bits);
     const long long total = (long long)A * A * 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ri = (int)(i & 1);
         const long long ck = i >> 1;
-        const int c = (int)(ck / A), k = (int)(ck % A);
+        const int c = (int)(ck / A), kk = (int)(ck % A);
         float v = 0.f;
-        if (k % stride == 0) {
-            const int m = k / stride;
+        if (kk % stride == 0) {
+            const int m = kk / stride;
             const int n = 2 * m + ri;
-            if (n < N) v = w_scale * (c < F ? dWT[(long long)n * F + c] * inv_gsc : pad * colsum[n]);
+            if (n < N) v = k * (c < F ? dWT[(long long)n * Fx + c] : pad * dWT[(long long)n * Fx + F]);
         }
         gUT[i] = v;
     }
@@ -642,7 +656,8 @@ GemmShape gemm_shape(const GateParams &gp, int n_qubits) {
     GemmShape g;
     g.A = 1 << n_qubits;
     g.F = gp.n_features;
-    g.Kp = (g.F + 7) & ~7;
+    g.Fx = g.F < g.A ? g.F + 1 : g.F;        // features + the ones column (pad-row column sums)
+    g.Kp = (g.Fx + 7) & ~7;
     g.n_out = gp.read_count;
     g.N = 2 * g.n_out;
     g.Np = (g.N + 7) & ~7;
@@ -706,8 +721,7 @@ size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
     b += al((size_t)B * 4) + al(256);                 // S, gmax
     b += 3 * al((size_t)B * g.Np * 2);                // G splits row-major
     b += 3 * al((size_t)g.N * Bp * 2);                // G splits transposed
-    b += al((size_t)g.N * g.F * 4);                   // dWT
-    b += al((size_t)g.N * 4);                         // colsum
+    b += al((size_t)g.N * g.Fx * 4);                  // dWT (+ ones column)
     b += al((size_t)g.A * g.A * 8);                   // gUT
     return b;
 }
@@ -789,8 +803,7 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     __half *Gs[3], *GT[3];
     for (int i = 0; i < 3; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
     for (int i = 0; i < 3; ++i) { GT[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)g.N * Bp * 2); }
-    float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.F * 4);
-    float *colsum = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * 4);
+    float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.Fx * 4);
     float *gUT = reinterpret_cast<float *>(p8);
     *gut_out = gUT;
 
@@ -798,17 +811,14 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
     // (1) scale bound, then one fused pass: G splits (row-major + transposed), S, colsum
     if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(S, 0, (size_t)B * 4, s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(colsum, 0, (size_t)g.N * 4, s)) != cudaSuccess) return (int)e;
     const int warps = 8;
     g_bound_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale,
                                                                             g.w_scale, gmax);
     count_launch();
     dim3 tb(32, 8);
-    dim3 tg((g.Np + 31) / 32, (unsigned)((Bp + 31) / 32));
-    grad_y_fused_kernel<<<tg, tb, 0, s>>>(w.Y, grad_out, w.inv_n2, B, g.N, g.Np, Bp, g.n_out, eff_scale, gp.clamp,
-                                          gp.clamp_lo, gp.clamp_hi, gmax, Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2], S,
-                                          g.F < g.A ? colsum : nullptr);
+    grad_y_fused_kernel<<<(unsigned)((Bp + 63) / 64), tb, 0, s>>>(w.Y, grad_out, w.inv_n2, B, g.N, g.Np, Bp, g.n_out,
+                                                                 eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax,
+                                                                 Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2], S);
     count_launch();
     GemmParams p;
     int rc;
@@ -823,21 +833,21 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         count_launch();
     }
     // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]  (split-K over the batch, fp32 atomics)
-    if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.F * 4, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.Fx * 4, s)) != cudaSuccess) return (int)e;
     {
         memset(&p, 0, sizeof(p));
-        p.epi = EPI_STORE; p.out = dWT; p.ldo = g.F; p.out_scale = 1.f;
+        p.epi = EPI_STORE; p.out = dWT; p.ldo = g.Fx; p.out_scale = 1.f;
         Operand3 GTo{GT[0], GT[1], GT[2]}, XTo{w.XT[0], w.XT[1], w.XT[2]};
-        const int bn = pick_bn(g.F);
-        const int tiles = ((g.N + BM - 1) / BM) * ((g.F + bn - 1) / bn);
+        const int bn = pick_bn(g.Fx);
+        const int tiles = ((g.N + BM - 1) / BM) * ((g.Fx + bn - 1) / bn);
         long long kt = (long long)n_seg * ((Bp + BK - 1) / BK);
         int splits = (int)((2 * 148 + tiles - 1) / tiles);
         if (splits > kt) splits = (int)kt;
         if (splits < 1) splits = 1;
-        rc = run_gemm(GTo, g.N, Bp, XTo, g.F, Bp, g.N, g.F, (int)Bp, n_seg, splits, p, s);
+        rc = run_gemm(GTo, g.N, Bp, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
         if (rc != QIDDM_OK) return rc;
     }
-    assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, colsum, gmax, g.A, g.F, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
+    assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, gmax, g.A, g.F, g.Fx, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
     count_launch();
     e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;

@@ -49,7 +49,7 @@ void timing_end(cudaStream_t s);
 
 // qiddm_gemm.cu — unitary-collapse path (amplitude families)
 struct GemmShape {
-    int A, F, Kp, n_out, N, Np, stride;
+    int A, F, Fx, Kp, n_out, N, Np, stride;
     float w_scale;
 };
 GemmShape gemm_shape(const GateParams &gp, int n_qubits);
