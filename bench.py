@@ -282,7 +282,8 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     fp32_peak = 148 * 128 * 2 * (float(peaks.get("sm_max_mhz", 1965.0)) * 1e6) / 1e12
-    shares = {k: v["ms"] / ms for k, v in kinds.items() if v["launches"]}
+    MAIN = ("gate_forward", "gate_backward", "gemm")
+    shares = {k: v["ms"] / ms for k, v in kinds.items() if v["launches"] and k in MAIN}
     dom = max(shares, key=shares.get)
     kd = kinds[dom]
     per_launch_ms = kd["ms"] / kd["launches"]
@@ -307,7 +308,7 @@ def run_b200(args):
                     "note": "the gate path is FP32-FMA/shared-memory bound, not HBM bound (SURVEY.md 8d)",
                     "fp32": {"achieved_tflops": tf, "peak_tflops_nominal": fp32_peak, "frac": tf / fp32_peak}}
     roofline["kernel_shares_of_step"] = shares
-    roofline["kernel_ms_per_step"] = {k: v["ms"] / K for k, v in kinds.items() if v["launches"]}
+    roofline["kernel_ms_per_step"] = {k: round(v["ms"] / K, 4) for k, v in kinds.items() if v["launches"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

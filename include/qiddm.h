@@ -146,8 +146,11 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
 
 /* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
  * launching stream around each main kernel.  collect() synchronises on them and returns, per kind
- * (0 gate forward, 1 gate adjoint backward, 2 tcgen05 GEMM, 3 other), the summed milliseconds, the
- * summed algorithmic work (flops) and the launch count, then clears the record.  Arrays of 4. */
+ * (0 gate forward, 1 gate adjoint backward, 2 tcgen05 GEMM (all), 3 other, 4/5/6 GEMM forward / dX / dW,
+ * 7 prep_x, 8 transpose_x, 9 g_bound, 10 grad_y, 11 finish_dx, 12 assemble, 13 build_w), the summed
+ * milliseconds, the summed algorithmic work (flops) and the launch count, then clears the record.
+ * Arrays of QIDDM_TIMING_KINDS = 16. */
+#define QIDDM_TIMING_KINDS 16
 void qiddm_timing_enable(int enable);
 int  qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *launches_by_kind);
 

@@ -129,7 +129,8 @@ def launch_count() -> int:
     return int(load_library().qiddm_launch_count())
 
 
-TIMING_KINDS = ("gate_forward", "gate_backward", "gemm", "other")
+TIMING_KINDS = ("gate_forward", "gate_backward", "gemm", "other", "gemm_forward", "gemm_dx", "gemm_dw", "prep_x",
+                "transpose_x", "g_bound", "grad_y", "finish_dx", "assemble", "build_w", "k14", "k15")
 
 
 def timing_enable(on: bool) -> None:
@@ -138,7 +139,7 @@ def timing_enable(on: bool) -> None:
 
 def timing_collect() -> dict:
     """{kind: {"ms": .., "work": .., "launches": ..}} since the last collect (synchronises)."""
-    ms, wk, n = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int64 * 4)()
+    ms, wk, n = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int64 * 16)()
     check(load_library().qiddm_timing_collect(ms, wk, n), "qiddm_timing_collect")
     return {k: {"ms": ms[i], "work": wk[i], "launches": int(n[i])} for i, k in enumerate(TIMING_KINDS)}
 

@@ -696,8 +696,10 @@ int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapse
     if (e != cudaSuccess) return (int)e;
     const int cmax = g.A > g.Kp ? g.A : g.Kp;
     dim3 grid((cmax + 255) / 256, g.N);
+    timing_begin(TK_BUILD_W, 0.0, s);
     build_w_kernel<<<grid, 256, 0, s>>>(v.UT, g.A, g.F, g.Kp, g.N, g.Np, g.stride, g.w_scale, gp.pad_value, v.Wn[0],
                                         v.Wn[1], v.Wn[2], v.Wt[0], v.Wt[1], v.Wt[2], v.bias);
+    timing_end(s);
     count_launch();
     e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
@@ -760,13 +762,17 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     SavedView w = saved_view(g, B, keep ? saved : ws, keep);
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
+    timing_begin(TK_PREP_X, 0.0, s);
     prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(gp, x, B, g.F, g.Kp, g.A - g.F, w.X[0],
                                                                            w.X[1], w.X[2], w.inv_n2, keep || n_seg > 1);
+    timing_end(s);
     count_launch();
     if (keep) {
         dim3 tb(32, 8);
         dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
+        timing_begin(TK_TRANSPOSE_X, 0.0, s);
         transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], w.X[2], B, g.Kp, Bp, w.XT[0], w.XT[1], w.XT[2]);
+        timing_end(s);
         count_launch();
     }
     GemmParams p;
@@ -779,6 +785,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
     p.n_out = g.n_out;
     Operand3 A{w.X[0], w.X[1], w.X[2]}, Bm{v.Wn[0], v.Wn[1], v.Wn[2]};
+    timing_set_gemm_kind(TK_GEMM_FWD);
     return run_gemm(A, B, g.Kp, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
 }
 
@@ -812,13 +819,17 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     // (1) scale bound, then one fused pass: G splits (row-major + transposed), S, colsum
     if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
     const int warps = 8;
+    timing_begin(TK_G_BOUND, 0.0, s);
     g_bound_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale,
                                                                             g.w_scale, gmax);
+    timing_end(s);
     count_launch();
     dim3 tb(32, 8);
+    timing_begin(TK_GRAD_Y, 0.0, s);
     grad_y_fused_kernel<<<(unsigned)((Bp + 63) / 64), tb, 0, s>>>(w.Y, grad_out, w.inv_n2, B, g.N, g.Np, Bp, g.n_out,
                                                                  eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax,
                                                                  Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2], S);
+    timing_end(s);
     count_launch();
     GemmParams p;
     int rc;
@@ -827,9 +838,12 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
         Operand3 Go{Gs[0], Gs[1], Gs[2]}, Wt{v.Wt[0], v.Wt[1], v.Wt[2]};
+        timing_set_gemm_kind(TK_GEMM_DX);
         rc = run_gemm(Go, B, g.Np, Wt, g.F, g.Np, (int)B, g.F, g.N, n_seg, 1, p, s);
         if (rc != QIDDM_OK) return rc;
+        timing_begin(TK_FINISH_DX, 0.0, s);
         finish_dx_kernel<<<1184, 256, 0, s>>>(grad_in, x, w.inv_n2, S, gmax, B, g.F, gp.add_offset);
+        timing_end(s);
         count_launch();
     }
     // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]  (split-K over the batch, fp32 atomics)
@@ -844,10 +858,13 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         int splits = (int)((2 * 148 + tiles - 1) / tiles);
         if (splits > kt) splits = (int)kt;
         if (splits < 1) splits = 1;
+        timing_set_gemm_kind(TK_GEMM_DW);
         rc = run_gemm(GTo, g.N, Bp, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
         if (rc != QIDDM_OK) return rc;
     }
+    timing_begin(TK_ASSEMBLE, 0.0, s);
     assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, gmax, g.A, g.F, g.Fx, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
+    timing_end(s);
     count_launch();
     e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;

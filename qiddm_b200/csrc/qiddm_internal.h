@@ -43,9 +43,12 @@ void count_launch(int n = 1);
 
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream around
 // the launches of one kind; off by default.
-enum { TK_GATE_FWD = 0, TK_GATE_BWD = 1, TK_GEMM = 2, TK_OTHER = 3, TK_COUNT = 4 };
+enum { TK_GATE_FWD = 0, TK_GATE_BWD = 1, TK_GEMM = 2, TK_OTHER = 3, TK_GEMM_FWD = 4, TK_GEMM_DX = 5, TK_GEMM_DW = 6,
+       TK_PREP_X = 7, TK_TRANSPOSE_X = 8, TK_G_BOUND = 9, TK_GRAD_Y = 10, TK_FINISH_DX = 11, TK_ASSEMBLE = 12,
+       TK_BUILD_W = 13, TK_COUNT = 16 };
 void timing_begin(int kind, double work, cudaStream_t s);   // work = algorithmic flops (or bytes) of the launch
 void timing_end(cudaStream_t s);
+void timing_set_gemm_kind(int kind);
 
 // qiddm_gemm.cu — unitary-collapse path (amplitude families)
 struct GemmShape {
