@@ -10,12 +10,15 @@
 //
 // Precision: "x3" mode splits every fp32 operand into fp16 hi + lo (22 mantissa bits) and runs the
 // three cross terms (hi*hi, lo*hi, hi*lo) as three K-segments of the same accumulator — fp32-grade
-// results at 3x the executed flops; "x1" runs hi*hi only (about 1e-3 relative).  Scaled copies keep the
-// lo terms in fp16's normal range: lo' = lo * 2^11 is paired with hi_small = hi * 2^-11.
+// results at 3x the executed flops; "x1" runs hi*hi only (about 3e-4 relative).  Per-step ("activation")
+// operands X and G carry two arrays (hi, lo' = lo * 2^11, kept in fp16's normal range); the static
+// ("weight-side") operands W and X^T carry three (hi, hi * 2^-11 to pair with lo', and the plain lo, whose
+// subnormal rounding is an absolute 2^-25 on O(1) values).
 //
-// Backward (same GEMM kernel, plain fp32 epilogue): recompute Y, form G = dL/dY elementwise, then
-//   dX = G W^T  and  dW^T = G^T X  (split-K, fp32 atomics), and push dW back through the circuit with
-// the adjoint gate kernel run on the 2^n basis columns (READ_STATE cotangent).
+// Backward (same GEMM kernel): the forward keeps Y; G = dL/dY is formed in one streaming pass; then
+//   dX = G W^T (normalisation term fused in the epilogue) and dW^T = G^T X, where G is consumed row-major
+// as an MN-major UMMA operand (no transposed copy; split-K over the batch, fp32 atomics); dW is pushed
+// back through the circuit with the adjoint gate kernel run on the 2^n basis columns (READ_STATE cotangent).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -102,17 +105,30 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
     return d;
 }
 
+// MN-major, SWIZZLE_128B: each K row is 128 B of 64 contiguous M elements; 8 K rows form a 1024-B atom
+// (SBO); the next 64 M elements start LBO = 8192 B later (second TMA box of the 128-row tile).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 // GEMM: D[M,N] (+)= sum_seg A_seg[M,K] * B_seg[N,K]^T     (fp16 in, fp32 accumulate)
 // ------------------------------------------------------------------------------------------
-enum { EPI_STORE = 0, EPI_PROBS = 1 };
+enum { EPI_STORE = 0, EPI_PROBS = 1, EPI_DX = 2 };
 
 struct GemmParams {
-    alignas(64) CUtensorMap a_map[3];
-    alignas(64) CUtensorMap b_map[3];
-    int n_seg;
+    alignas(64) CUtensorMap a_map[2];   // activation side: hi, lo * 2^11
+    alignas(64) CUtensorMap b_map[3];   // weight side: hi, hi * 2^-11, lo
+    int n_seg;            // 1: (a0,b0);  3: (a0,b0), (a1,b1), (a0,b2)
+    int a_mn;             // A is MN-major: its tensor map is over the row-major (K rows, M cols) array
     int M, N, K;          // K per segment, elements
     int bn;               // BLOCK_N: multiple of 16, <= 256
     int stages;
@@ -128,7 +144,20 @@ struct GemmParams {
     int clamp;
     int n_out;               // number of (re,im) pairs that are real outputs
     float *y_out;            // optional (EPI_PROBS): Y + bias stored as fp32 (M, N) for the backward pass
+    // EPI_DX: out = acc / gsc - 2 (x + add_offset) inv_n2[row] S[row]
+    const float *dx_x, *dx_S;
+    const unsigned int *gmax_bits;
+    float add_offset;
 };
+
+// power-of-two scale that maps the bound on max |G| into [2^13, 2^14)
+__device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
+    const float mx = __uint_as_float(bits);
+    if (!(mx > 0.f)) return 1.f;
+    int e;
+    frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 14 - e);
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -190,7 +219,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), stage_bytes);
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    tma_load_2d(sa, &p.a_map[seg], full_bar(stage), kb * BK, tm * BM);
+                    const CUtensorMap *am = &p.a_map[seg == 1 ? 1 : 0];
+                    if (p.a_mn) {   // two (64 M) x (64 K) boxes from the row-major (K, M) array
+                        tma_load_2d(sa, am, full_bar(stage), tm * BM, kb * BK);
+                        tma_load_2d(sa + a_bytes / 2, am, full_bar(stage), tm * BM + 64, kb * BK);
+                    } else {
+                        tma_load_2d(sa, am, full_bar(stage), kb * BK, tm * BM);
+                    }
                     tma_load_2d(sa + a_bytes, &p.b_map[seg], full_bar(stage), kb * BK, tn * p.bn);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -200,7 +235,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+                                   (p.a_mn ? (1u << 15) : 0u);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x) {
@@ -214,12 +250,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t adesc = p.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + a_bytes);
+                    // K advance per MMA (16 elements): K-major +32 B inside the swizzle row (+2 in 16-B units);
+                    // MN-major +16 K rows = two 1024-B atoms (+128)
+                    const uint64_t a_step = p.a_mn ? 128 : 2;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 elements = 32 B along K inside the 128-B swizzle row: +2 in 16-B units
-                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(empty_bar(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -242,6 +280,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             const int n0 = tn * p.bn;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS;
             const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
+            float dx_a = 0.f, dx_b = 0.f;
+            if (p.epi == EPI_DX && row < p.M) {
+                dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
+                dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+            }
             for (int c0 = 0; c0 < p.bn; c0 += 16) {
                 float v[16];
                 tc_ld16(taddr + c0, v);
@@ -286,6 +329,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                         for (int j = 0; j < 8; ++j)
                             if (m0 + j < p.n_out) dst[j] = o[j];
                     }
+                } else if (p.epi == EPI_DX) {
+                    float *dst = p.out + (long long)row * p.ldo + col;
+                    const float *xs = p.dx_x + (long long)row * p.ldo + col;
+                    if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xs) + j);
+                            reinterpret_cast<float4 *>(dst)[j] =
+                                make_float4(v[4 * j] * dx_a + dx_b * (xv.x + p.add_offset),
+                                            v[4 * j + 1] * dx_a + dx_b * (xv.y + p.add_offset),
+                                            v[4 * j + 2] * dx_a + dx_b * (xv.z + p.add_offset),
+                                            v[4 * j + 3] * dx_a + dx_b * (xv.w + p.add_offset));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col + j < p.N) dst[j] = v[j] * dx_a + dx_b * (__ldg(xs + j) + p.add_offset);
+                    }
                 } else {
                     float *dst = p.out + (long long)row * p.ldo + col;
                     if (p.k_splits > 1) {
@@ -323,49 +384,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------
 // elementwise helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split3(float v, __half &hi, __half &lo, __half &hs) {
+// activation-side split: hi + lo * 2^11
+__device__ __forceinline__ void split_act(float v, __half &hi, __half &lo_s) {
+    hi = __float2half_rn(v);
+    lo_s = __float2half_rn((v - __half2float(hi)) * LO_SCALE);
+}
+// weight-side split: hi, hi * 2^-11 (pairs with the activation's lo * 2^11), plain lo
+__device__ __forceinline__ void split_wgt(float v, __half &hi, __half &hs, __half &lo) {
     hi = __float2half_rn(v);
     const float h = __half2float(hi);
-    lo = __float2half_rn((v - h) * LO_SCALE);
     hs = __float2half_rn(h * LO_INV);
+    lo = __float2half_rn(v - h);
 }
 
-// x (B,F) fp32 [+ fused unfold] -> Xh/Xl/Xs (B,Kp) fp16 and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).
-// One warp per row.
-__global__ void prep_x_kernel(const GateParams gp, const float *x, long long B, int F, int Kp, int n_pad,
-                              __half *Xh, __half *Xl, __half *Xs, float *inv_n2, int want_split) {
+// x (B,F) fp32 -> Xh/Xl (B,Kp) fp16 (hi, lo*2^11) and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).  One warp per row.
+// Column F (when the state has constant pad rows) is a column of ones: it meets zero weights in the forward
+// and dX GEMMs and yields sum_b G[b,n] (the pad rows of dW) in the dW GEMM.
+__global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_pad, float add_offset, float pad,
+                              __half *Xh, __half *Xl, float *inv_n2, int want_lo) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
     float ss = 0.f;
     for (int c = lane; c < Kp; c += 32) {
         float f = 0.f;
-        if (c < F) f = __ldg(x + row * F + c) + gp.add_offset;
-        __half hi, lo, hs;
-        // column F (when the state has constant pad rows) is a column of ones: it meets zero weights in
-        // the forward / dX GEMMs and yields sum_b G[b,n] (the pad rows of dW) in the dW GEMM
-        split3((c == F && n_pad > 0) ? 1.f : f, hi, lo, hs);
+        if (c < F) f = __ldg(x + row * F + c) + add_offset;
+        __half hi, lo;
+        split_act((c == F && n_pad > 0) ? 1.f : f, hi, lo);
         Xh[row * Kp + c] = hi;
-        if (want_split) {
-            Xl[row * Kp + c] = lo;
-            Xs[row * Kp + c] = hs;
-        }
+        if (want_lo) Xl[row * Kp + c] = lo;
         ss += f * f;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if (lane == 0) {
-        ss += (float)n_pad * gp.pad_value * gp.pad_value;
+        ss += (float)n_pad * pad * pad;
         inv_n2[row] = ss > 0.f ? 1.0f / ss : 0.f;
     }
 }
 
-// From UT (row c = U|c>, complex fp32) build the GEMM weight operands (scaled by w_scale):
-//   Wn[n][c] (N x Kp), Wt[c][n] (F x Np), with n = 2m + {re,im}, value = part(UT[c][m*stride]);
-//   bias[n] = pad * sum_{c >= F} value.   One thread per (n, c).
+// From UT (row c = U|c>, complex fp32) build the weight-side GEMM operands (scaled by w_scale):
+//   Wn[n][c] (N x Kp), Wt[c][n] (F x Np), n = 2m + {re,im}, value = part(UT[c][m*stride]);
+//   bias[n] = pad * sum_{c >= F} value.
 __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, int Np, int stride, float w_scale,
-                               float pad, __half *Wn_h, __half *Wn_l, __half *Wn_s, __half *Wt_h, __half *Wt_l,
-                               __half *Wt_s, float *bias) {
+                               float pad, __half *Wn_h, __half *Wn_s, __half *Wn_l, __half *Wt_h, __half *Wt_s,
+                               __half *Wt_l, float *bias) {
     const int n = blockIdx.y;
     const int m = n >> 1, ri = n & 1;
     float bsum = 0.f;
@@ -376,20 +439,19 @@ __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, in
             v = (ri ? u.y : u.x) * w_scale;
         }
         if (c < Kp) {
-            __half hi, lo, hs;
-            split3(c < F ? v : 0.f, hi, lo, hs);
+            __half hi, hs, lo;
+            split_wgt(c < F ? v : 0.f, hi, hs, lo);
             Wn_h[(long long)n * Kp + c] = hi;
-            Wn_l[(long long)n * Kp + c] = lo;
             Wn_s[(long long)n * Kp + c] = hs;
+            Wn_l[(long long)n * Kp + c] = lo;
             if (c < F) {
                 Wt_h[(long long)c * Np + n] = hi;
-                Wt_l[(long long)c * Np + n] = lo;
                 Wt_s[(long long)c * Np + n] = hs;
+                Wt_l[(long long)c * Np + n] = lo;
             }
         }
         if (c >= F && c < A) bsum += v;
     }
-    // block reduce of bsum -> bias[n] (bias zeroed by the caller)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
     if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(bias + n, bsum * pad);
@@ -412,93 +474,46 @@ __global__ void g_bound_kernel(const float *go, const float *inv_n2, long long B
     }
 }
 
-// power-of-two scale that maps the bound on max |G| into [2^13, 2^14)
-__device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
-    const float mx = __uint_as_float(bits);
-    if (!(mx > 0.f)) return 1.f;
-    int e;
-    frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
-    return ldexpf(1.f, 14 - e);
-}
-
-// One pass over Y (= X W' + bias', saved by the forward GEMM) and grad_out:
+// One streaming pass over Y (= X W' + bias', saved by the forward GEMM) and grad_out, one warp per row:
 //   out = scale inv_n2 |Y|^2, mask = !clamp || lo <= out <= hi,  G[2m+ri] = 2 g mask scale inv_n2 Y[2m+ri]
-// written as scaled fp16 splits row-major (B,Np) AND transposed (N,Bp) through a 64x64 smem tile, plus
-// S[b] = sum_m g mask out (normalisation term of dX).  One block owns 64 rows and walks all columns, so S
-// needs no atomics; every global access is a 128-byte warp transaction (float2 / half2 per thread).
-__global__ void __launch_bounds__(256) grad_y_fused_kernel(
-    const float *Y, const float *go, const float *inv_n2, long long B, int N, int Np, long long Bp, int n_out,
-    float scale, int clamp, float lo, float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl, __half *Gs,
-    __half *GTh, __half *GTl, __half *GTs, float *S) {
-    __shared__ float tile[64][65];
+// written as scaled fp16 (hi, lo*2^11) row-major (B,Np); S[b] = sum_m g mask out (normalisation term of dX).
+__global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float *go, const float *inv_n2, long long B,
+                                                     int N, int Np, int n_out, float scale, int clamp, float lo,
+                                                     float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl,
+                                                     float *S, int want_lo) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= B) return;
     const float gsc = g_scale_from_max(*gmax_bits);
-    const int tx = threadIdx.x, ty = threadIdx.y;     // 32 x 8
-    const long long r0 = (long long)blockIdx.x * 64;
-    float s_part[8], in2[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        s_part[i] = 0.f;
-        const long long r = r0 + ty + 8 * i;
-        in2[i] = r < B ? inv_n2[r] : 0.f;
-    }
-    for (int c0 = 0; c0 < Np; c0 += 64) {
-        const int c = c0 + 2 * tx;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long r = r0 + ty + 8 * i;
-            float gre = 0.f, gim = 0.f;
-            if (r < B && c < N) {
-                const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + c);
-                const float outv = scale * in2[i] * (y.x * y.x + y.y * y.y);
-                const bool pass = !clamp || (outv >= lo && outv <= hi);
-                const float g = pass ? __ldg(go + r * n_out + (c >> 1)) : 0.f;
-                const float coef = 2.f * g * scale * in2[i];
-                gre = coef * y.x;
-                gim = coef * y.y;
-                s_part[i] += g * outv;
-            }
-            tile[ty + 8 * i][2 * tx] = gre;
-            tile[ty + 8 * i][2 * tx + 1] = gim;
-            if (r < B && c < Np) {
-                __half h0, l0, s0, h1, l1, s1;
-                split3(gre * gsc, h0, l0, s0);
-                split3(gim * gsc, h1, l1, s1);
-                *reinterpret_cast<__half2 *>(Gh + r * Np + c) = __halves2half2(h0, h1);
-                *reinterpret_cast<__half2 *>(Gl + r * Np + c) = __halves2half2(l0, l1);
-                *reinterpret_cast<__half2 *>(Gs + r * Np + c) = __halves2half2(s0, s1);
-            }
+    const float in2 = inv_n2[r];
+    float s_part = 0.f;
+    for (int m = lane; 2 * m < Np; m += 32) {
+        float gre = 0.f, gim = 0.f;
+        if (m < n_out) {
+            const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + 2 * m);
+            const float outv = scale * in2 * (y.x * y.x + y.y * y.y);
+            const bool pass = !clamp || (outv >= lo && outv <= hi);
+            const float g = pass ? __ldg(go + r * n_out + m) : 0.f;
+            const float coef = 2.f * g * scale * in2 * gsc;
+            gre = coef * y.x;
+            gim = coef * y.y;
+            s_part += g * outv;
         }
-        __syncthreads();
-        const long long r = r0 + 2 * tx;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int cc = ty + 8 * j;
-            const int n = c0 + cc;
-            if (n < N && r < Bp) {
-                __half h0, l0, s0, h1, l1, s1;
-                split3(tile[2 * tx][cc] * gsc, h0, l0, s0);
-                split3(tile[2 * tx + 1][cc] * gsc, h1, l1, s1);
-                *reinterpret_cast<__half2 *>(GTh + (long long)n * Bp + r) = __halves2half2(h0, h1);
-                *reinterpret_cast<__half2 *>(GTl + (long long)n * Bp + r) = __halves2half2(l0, l1);
-                *reinterpret_cast<__half2 *>(GTs + (long long)n * Bp + r) = __halves2half2(s0, s1);
-            }
-        }
-        __syncthreads();
+        __half h0, l0, h1, l1;
+        split_act(gre, h0, l0);
+        split_act(gim, h1, l1);
+        *reinterpret_cast<__half2 *>(Gh + r * Np + 2 * m) = __halves2half2(h0, h1);
+        if (want_lo) *reinterpret_cast<__half2 *>(Gl + r * Np + 2 * m) = __halves2half2(l0, l1);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float v = s_part[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const long long r = r0 + ty + 8 * i;
-        if (tx == 0 && r < B) S[r] = v;
-    }
+    for (int o = 16; o > 0; o >>= 1) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
+    if (lane == 0) S[r] = s_part;
 }
 
-// X splits (B,Kp) -> transposed (Kp,Bp)
-__global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, const __half *Xs, long long B, int Kp,
-                                   long long Bp, __half *XTh, __half *XTl, __half *XTs) {
-    __shared__ __half th[32][34], tl[32][34], ts[32][34];
+// X (B,Kp) activation splits (hi, lo*2^11) -> transposed weight-side splits (Kp,Bp): hi, hi*2^-11, lo
+__global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, long long B, int Kp, long long Bp, __half *XTh,
+                                   __half *XTs, __half *XTl) {
+    __shared__ __half th[32][34], tl[32][34];
     const long long r0 = (long long)blockIdx.y * 32;
     const int c0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -507,29 +522,17 @@ __global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, const __h
         const bool ok = r < B && c < Kp;
         th[i][threadIdx.x] = ok ? Xh[r * Kp + c] : __float2half(0.f);
         tl[i][threadIdx.x] = ok ? Xl[r * Kp + c] : __float2half(0.f);
-        ts[i][threadIdx.x] = ok ? Xs[r * Kp + c] : __float2half(0.f);
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int c = c0 + i;
         const long long r = r0 + threadIdx.x;
         if (c < Kp && r < Bp) {
+            const float h = __half2float(th[threadIdx.x][i]);
             XTh[(long long)c * Bp + r] = th[threadIdx.x][i];
-            XTl[(long long)c * Bp + r] = tl[threadIdx.x][i];
-            XTs[(long long)c * Bp + r] = ts[threadIdx.x][i];
+            XTs[(long long)c * Bp + r] = __float2half_rn(h * LO_INV);
+            XTl[(long long)c * Bp + r] = __float2half_rn(__half2float(tl[threadIdx.x][i]) * LO_INV);
         }
-    }
-}
-
-// dX[b,c] = dXraw[b,c] / gsc - 2 f[b,c] inv_n2[b] S[b]      (f = x + offset), in place on dX
-__global__ void finish_dx_kernel(float *dX, const float *x, const float *inv_n2, const float *S,
-                                 const unsigned int *gmax_bits, long long B, int F, float add_offset) {
-    const float inv_gsc = 1.f / g_scale_from_max(*gmax_bits);
-    const long long n = B * F;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / F;
-        const float f = x[i] + add_offset;
-        dX[i] = dX[i] * inv_gsc - 2.f * f * inv_n2[b] * S[b];
     }
 }
 
@@ -590,36 +593,37 @@ int make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, 
 }
 
 int pick_bn(int N) {
-    // largest multiple of 16 <= 256 that tiles N with the least padding
+    // multiple of 16 <= 256 that tiles N with the least padding (small tiles pay more per-tile overhead)
     int best = 16;
     double best_cost = 1e30;
     for (int bn = 256; bn >= 16; bn -= 16) {
         const int tiles = (N + bn - 1) / bn;
-        const double waste = (double)tiles * bn / N;               // padded work
-        const double cost = waste * (1.0 + 24.0 / bn);              // small tiles pay more per-tile overhead
+        const double waste = (double)tiles * bn / N;
+        const double cost = waste * (1.0 + 24.0 / bn);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
 }
 
-struct Operand3 {
-    const __half *h, *l, *s;
-};
+struct ActOperand { const __half *h, *l; };          // hi, lo * 2^11
+struct WgtOperand { const __half *h, *s, *l; };      // hi, hi * 2^-11, lo
 
-// D[M,N] = sum over (hi,hi) [, (lo',hi_small), (hi_small, lo')] of A * B^T
-int run_gemm(const Operand3 &A, long long a_rows, long long a_pitch, const Operand3 &Bm, long long b_rows,
-             long long b_pitch, int M, int N, int K, int n_seg, int k_splits, GemmParams &p, cudaStream_t s) {
+// D[M,N] = A B^T over the precision segments.  a_mn: A is given as the row-major (K, M) array (MN-major operand).
+int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long a_pitch, bool a_mn,
+             const WgtOperand &Bm, long long b_rows, long long b_pitch, int M, int N, int K, int n_seg, int k_splits,
+             GemmParams &p, cudaStream_t s) {
     p.M = M; p.N = N; p.K = K;
     p.n_seg = n_seg;
+    p.a_mn = a_mn ? 1 : 0;
     p.bn = pick_bn(N);
     p.k_splits = k_splits;
-    const __half *as[3] = {A.h, A.l, A.s};
+    const __half *as[2] = {A.h, A.l};
     const __half *bs[3] = {Bm.h, Bm.s, Bm.l};
-    for (int i = 0; i < n_seg; ++i) {
-        int rc;
-        if ((rc = make_map(&p.a_map[i], as[i], a_rows, K, a_pitch, BM)) != QIDDM_OK) return rc;
+    int rc;
+    for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
+        if ((rc = make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, a_mn ? 64 : BM)) != QIDDM_OK) return rc;
+    for (int i = 0; i < n_seg; ++i)
         if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, p.bn)) != QIDDM_OK) return rc;
-    }
     const int stage_bytes = BM * BK * 2 + p.bn * BK * 2;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -650,7 +654,7 @@ inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-// layout of the collapsed operator and of the per-call workspace
+// layout of the collapsed operator, the saved forward state and the per-call workspace
 // ------------------------------------------------------------------------------------------
 GemmShape gemm_shape(const GateParams &gp, int n_qubits) {
     GemmShape g;
@@ -669,8 +673,8 @@ GemmShape gemm_shape(const GateParams &gp, int n_qubits) {
 size_t gemm_collapsed_bytes(const GemmShape &g) {
     size_t b = 0;
     b += al((size_t)g.A * g.A * 8);                  // UT
-    b += 3 * al((size_t)g.N * g.Kp * 2);             // Wn h/l/s
-    b += 3 * al((size_t)g.F * g.Np * 2);             // Wt h/l/s
+    b += 3 * al((size_t)g.N * g.Kp * 2);             // Wn h/s/l
+    b += 3 * al((size_t)g.F * g.Np * 2);             // Wt h/s/l
     b += al((size_t)g.N * 4);                        // bias
     return b;
 }
@@ -709,20 +713,18 @@ float *gemm_collapsed_ut(const GemmShape &g, void *collapsed) { return reinterpr
 
 size_t gemm_saved_bytes(const GemmShape &g, long long B) {
     const long long Bp = (B + 7) & ~7LL;
-    return 3 * al((size_t)B * g.Kp * 2) + 3 * al((size_t)g.Kp * Bp * 2) + al((size_t)B * 4) +
+    return 2 * al((size_t)B * g.Kp * 2) + 3 * al((size_t)g.Kp * Bp * 2) + al((size_t)B * 4) +
            al((size_t)B * g.N * 4);
 }
 
 size_t gemm_forward_ws_bytes(const GemmShape &g, long long B) {
-    return 3 * al((size_t)B * g.Kp * 2) + al((size_t)B * 4);
+    return 2 * al((size_t)B * g.Kp * 2) + al((size_t)B * 4);
 }
 
 size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
-    const long long Bp = (B + 7) & ~7LL;
     size_t b = gemm_saved_bytes(g, B);                // used when the forward did not save
     b += al((size_t)B * 4) + al(256);                 // S, gmax
-    b += 3 * al((size_t)B * g.Np * 2);                // G splits row-major
-    b += 3 * al((size_t)g.N * Bp * 2);                // G splits transposed
+    b += 2 * al((size_t)B * g.Np * 2);                // G splits (row-major)
     b += al((size_t)g.N * g.Fx * 4);                  // dWT (+ ones column)
     b += al((size_t)g.A * g.A * 8);                   // gUT
     return b;
@@ -730,7 +732,7 @@ size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
 
 namespace {
 struct SavedView {
-    __half *X[3], *XT[3];
+    __half *X[2], *XT[3];
     float *inv_n2, *Y;
     char *end;
 };
@@ -739,11 +741,10 @@ SavedView saved_view(const GemmShape &g, long long B, void *buf, bool full) {
     SavedView w;
     const long long Bp = (B + 7) & ~7LL;
     char *p = reinterpret_cast<char *>(buf);
-    for (int i = 0; i < 3; ++i) { w.X[i] = reinterpret_cast<__half *>(p); p += al((size_t)B * g.Kp * 2); }
-    if (full) {
-        for (int i = 0; i < 3; ++i) { w.XT[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.Kp * Bp * 2); }
-    } else {
-        for (int i = 0; i < 3; ++i) w.XT[i] = nullptr;
+    for (int i = 0; i < 2; ++i) { w.X[i] = reinterpret_cast<__half *>(p); p += al((size_t)B * g.Kp * 2); }
+    for (int i = 0; i < 3; ++i) {
+        w.XT[i] = full ? reinterpret_cast<__half *>(p) : nullptr;
+        if (full) p += al((size_t)g.Kp * Bp * 2);
     }
     w.inv_n2 = reinterpret_cast<float *>(p); p += al((size_t)B * 4);
     w.Y = nullptr;
@@ -763,15 +764,15 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
     timing_begin(TK_PREP_X, 0.0, s);
-    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(gp, x, B, g.F, g.Kp, g.A - g.F, w.X[0],
-                                                                           w.X[1], w.X[2], w.inv_n2, keep || n_seg > 1);
+    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(
+        x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1);
     timing_end(s);
     count_launch();
     if (keep) {
         dim3 tb(32, 8);
         dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
         timing_begin(TK_TRANSPOSE_X, 0.0, s);
-        transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], w.X[2], B, g.Kp, Bp, w.XT[0], w.XT[1], w.XT[2]);
+        transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1], w.XT[2]);
         timing_end(s);
         count_launch();
     }
@@ -784,9 +785,10 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     p.post_scale = gp.post_scale / (g.w_scale * g.w_scale);
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
     p.n_out = g.n_out;
-    Operand3 A{w.X[0], w.X[1], w.X[2]}, Bm{v.Wn[0], v.Wn[1], v.Wn[2]};
+    ActOperand A{w.X[0], w.X[1]};
+    WgtOperand Bm{v.Wn[0], v.Wn[1], v.Wn[2]};
     timing_set_gemm_kind(TK_GEMM_FWD);
-    return run_gemm(A, B, g.Kp, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
+    return run_gemm(A, B, g.Kp, g.Kp, false, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
 }
 
 // Produces grad_in (B,F) (nullable) and the READ_STATE cotangent gUT (A x 2A fp32) for the adjoint gate kernel.
@@ -807,16 +809,15 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     SavedView w = saved_view(g, B, saved_buf, true);
     float *S = reinterpret_cast<float *>(p8); p8 += al((size_t)B * 4);
     unsigned int *gmax = reinterpret_cast<unsigned int *>(p8); p8 += al(256);
-    __half *Gs[3], *GT[3];
-    for (int i = 0; i < 3; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
-    for (int i = 0; i < 3; ++i) { GT[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)g.N * Bp * 2); }
+    __half *Gs[2];
+    for (int i = 0; i < 2; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
     float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.Fx * 4);
     float *gUT = reinterpret_cast<float *>(p8);
     *gut_out = gUT;
 
     cudaError_t e;
     const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
-    // (1) scale bound, then one fused pass: G splits (row-major + transposed), S, colsum
+    // (1) scale bound, then one streaming pass: G splits (row-major) and S
     if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
     const int warps = 8;
     timing_begin(TK_G_BOUND, 0.0, s);
@@ -824,34 +825,31 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
                                                                             g.w_scale, gmax);
     timing_end(s);
     count_launch();
-    dim3 tb(32, 8);
     timing_begin(TK_GRAD_Y, 0.0, s);
-    grad_y_fused_kernel<<<(unsigned)((Bp + 63) / 64), tb, 0, s>>>(w.Y, grad_out, w.inv_n2, B, g.N, g.Np, Bp, g.n_out,
-                                                                 eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax,
-                                                                 Gs[0], Gs[1], Gs[2], GT[0], GT[1], GT[2], S);
+    grad_y_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(
+        w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
+        Gs[1], S, n_seg > 1);
     timing_end(s);
     count_launch();
     GemmParams p;
     int rc;
-    // (2) dX = G W^T (scaled by gsc), then the normalisation term
+    ActOperand Go{Gs[0], Gs[1]};
+    // (2) dX = G W^T / gsc - 2 f inv_n2 S   (normalisation term fused in the epilogue)
     if (grad_in != nullptr) {
         memset(&p, 0, sizeof(p));
-        p.epi = EPI_STORE; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
-        Operand3 Go{Gs[0], Gs[1], Gs[2]}, Wt{v.Wt[0], v.Wt[1], v.Wt[2]};
+        p.epi = EPI_DX; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
+        p.row_scale = w.inv_n2; p.dx_S = S; p.dx_x = x; p.gmax_bits = gmax; p.add_offset = gp.add_offset;
+        WgtOperand Wt{v.Wt[0], v.Wt[1], v.Wt[2]};
         timing_set_gemm_kind(TK_GEMM_DX);
-        rc = run_gemm(Go, B, g.Np, Wt, g.F, g.Np, (int)B, g.F, g.N, n_seg, 1, p, s);
+        rc = run_gemm(Go, B, g.Np, g.Np, false, Wt, g.F, g.Np, (int)B, g.F, g.N, n_seg, 1, p, s);
         if (rc != QIDDM_OK) return rc;
-        timing_begin(TK_FINISH_DX, 0.0, s);
-        finish_dx_kernel<<<1184, 256, 0, s>>>(grad_in, x, w.inv_n2, S, gmax, B, g.F, gp.add_offset);
-        timing_end(s);
-        count_launch();
     }
-    // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]  (split-K over the batch, fp32 atomics)
+    // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]: G consumed row-major as an MN-major operand, split-K over the batch
     if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.Fx * 4, s)) != cudaSuccess) return (int)e;
     {
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = dWT; p.ldo = g.Fx; p.out_scale = 1.f;
-        Operand3 GTo{GT[0], GT[1], GT[2]}, XTo{w.XT[0], w.XT[1], w.XT[2]};
+        WgtOperand XTo{w.XT[0], w.XT[1], w.XT[2]};
         const int bn = pick_bn(g.Fx);
         const int tiles = ((g.N + BM - 1) / BM) * ((g.Fx + bn - 1) / bn);
         long long kt = (long long)n_seg * ((Bp + BK - 1) / BK);
@@ -859,7 +857,7 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         if (splits > kt) splits = (int)kt;
         if (splits < 1) splits = 1;
         timing_set_gemm_kind(TK_GEMM_DW);
-        rc = run_gemm(GTo, g.N, Bp, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
+        rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
         if (rc != QIDDM_OK) return rc;
     }
     timing_begin(TK_ASSEMBLE, 0.0, s);
