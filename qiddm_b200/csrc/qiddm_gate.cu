@@ -22,6 +22,7 @@
 // partials and turned into angle gradients (incl. the tanh / pi*tanh re-map chain rule) in
 // double precision by finalize_grads_kernel (deterministic across CTAs).
 #include <math_constants.h>
+#include <cstdlib>
 #include "qiddm_internal.h"
 
 namespace qiddm {
@@ -40,11 +41,27 @@ struct Cfg {
     static constexpr int LO_LAST = NQ - RB;
 };
 
-__host__ __device__ constexpr int rb_forward(int nq) {
+// Register-tile width (log2 amplitudes per thread).  Candidates compiled per qubit count:
+// min(nq,3), min(nq,4), min(nq,5) (subject to 2^(nq-rb) <= 256 threads per instance); the defaults below were
+// picked from B200 measurements and can be overridden with QIDDM_RB_FWD / QIDDM_RB_BWD for tuning.
+inline bool rb_valid(int nq, int rb) {
+    if (rb < 1 || rb > 5 || rb > nq) return false;
+    if (rb < 3 && rb != nq) return false;
+    return (nq - rb) <= 8;
+}
+inline int rb_default(int nq, bool bwd) {
+    if (bwd) return nq <= 4 ? nq : nq <= 6 ? 3 : nq <= 8 ? 4 : nq == 9 ? 3 : 4;
     return nq <= 5 ? nq : nq == 6 ? 3 : nq <= 8 ? 4 : nq <= 10 ? 5 : 4;
 }
-__host__ __device__ constexpr int rb_backward(int nq) {
-    return nq <= 4 ? nq : nq <= 6 ? 3 : nq <= 8 ? 4 : nq == 9 ? 3 : 4;
+inline int rb_choose(int nq, bool bwd) {
+    static int env_f = -2, env_b = -2;
+    int &e = bwd ? env_b : env_f;
+    if (e == -2) {
+        const char *v = getenv(bwd ? "QIDDM_RB_BWD" : "QIDDM_RB_FWD");
+        e = v ? atoi(v) : -1;
+    }
+    if (e > 0 && rb_valid(nq, e)) return e;
+    return rb_default(nq, bwd);
 }
 
 struct Mat {
@@ -107,14 +124,22 @@ __device__ __forceinline__ float cz_sign(int k, int ring) {
     return (__popc(k & rot) & 1) ? -1.0f : 1.0f;
 }
 
-template <int G>
-__device__ __forceinline__ void group_sync() {
-    if (G <= 32) __syncwarp(); else __syncthreads();
+// Barrier over the G threads that simulate one instance: warp-level for G <= 32, a named barrier per
+// instance slot when several multi-warp groups share the CTA, the CTA barrier when one group fills it.
+template <int G, int T>
+__device__ __forceinline__ void group_sync(int slot) {
+    if (G <= 32) {
+        __syncwarp();
+    } else if (G == T) {
+        __syncthreads();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(G) : "memory");
+    }
 }
 
 // Sum over the G threads of a group.  G <= 32: xor shuffles.  G > 32: the group spans whole
 // warps; `red` has one slot per warp of the CTA and is reused, so callers sync around it.
-template <int G>
+template <int G, int T>
 __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
     if (G <= 32) {
 #pragma unroll
@@ -123,11 +148,12 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid) {
     } else {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncthreads();
+        const int slot = tid / G;
+        group_sync<G, T>(slot);
         if ((tid & 31) == 0) red[tid >> 5] = v;
-        __syncthreads();
+        group_sync<G, T>(slot);
         float s = 0.f;
-        const int w0 = (tid / G) * (G / 32);
+        const int w0 = slot * (G / 32);
 #pragma unroll
         for (int i = 0; i < G / 32; ++i) s += red[w0 + i];
         return s;
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 vals[i] = v;
                 ss += v * v;
             }
-            ss = group_sum<G>(ss, red, tid);
+            ss = group_sum<G, T>(ss, red, tid);
             inv_norm = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
 #pragma unroll
             for (int i = 0; i < R; ++i) psi[swz<RB>(g + i * G)] = make_float2(vals[i] * inv_norm, 0.f);
@@ -299,7 +325,7 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 ep[j] = make_float2(c, s);
             }
         }
-        group_sync<G>();
+        group_sync<G, T>(slot);
 
         // ---------------------------------------------------------------- forward sweep
         for (int blk = 0; blk < p.n_blocks; ++blk) {
@@ -308,18 +334,18 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 const int ring = NQ > 1 ? (layer % NRING) + 1 : 0;
                 const bool encl = (p.enc != QIDDM_ENC_NONE) && layer == 0;
                 float2 s[R];
-#pragma unroll
+#pragma unroll 1
                 for (int v = 0; v < NV; ++v) {
                     const int lo = (v * RB < LO_LAST) ? v * RB : LO_LAST;
-                    const int new_lo = v * RB;
-                    const int new_hi = ((v + 1) * RB < NQ) ? (v + 1) * RB : NQ;
+                    const int q_lo = v * RB - lo;                                        // first new local bit
+                    const int q_hi = (((v + 1) * RB < NQ) ? (v + 1) * RB : NQ) - lo;     // one past the last
+                    const int kbase = amp_index<NQ, RB>(g, 0, lo);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) s[r] = psi[swz<RB>(amp_index<NQ, RB>(g, r, lo))];
+                    for (int r = 0; r < R; ++r) s[r] = psi[swz<RB>(kbase | (r << lo))];
 #pragma unroll
                     for (int q = 0; q < RB; ++q) {
-                        const int pos = lo + q;
-                        if (pos < new_lo || pos >= new_hi) continue;
-                        const int wire = NQ - 1 - pos;
+                        if (q < q_lo || q >= q_hi) continue;
+                        const int wire = NQ - 1 - (lo + q);
                         Mat m = load_mat(gm + (gate_base + wire) * 8);
                         if (encl) m = fold_enc(m, ep[wire], p.enc);
 #pragma unroll
@@ -330,7 +356,7 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                     }
                     if (v == NV - 1 && NQ > 1) {
                         if (p.imprimitive == QIDDM_IMP_CNOT) {
-                            if (G > 1) group_sync<G>();  // every tile is in registers before the scatter
+                            if (G > 1) group_sync<G, T>(slot);  // every tile is in registers before the scatter
                             const int fk = ring_f<NQ>(k_thread_last, ring);
                             const unsigned short *ft = ftab + (ring - 1) * R;
 #pragma unroll
@@ -338,16 +364,16 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                         } else {
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
-                                const int k = amp_index<NQ, RB>(g, r, lo);
+                                const int k = kbase | (r << lo);
                                 const float sg = cz_sign<NQ>(k, ring);
                                 psi[swz<RB>(k)] = make_float2(s[r].x * sg, s[r].y * sg);
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int r = 0; r < R; ++r) psi[swz<RB>(amp_index<NQ, RB>(g, r, lo))] = s[r];
+                        for (int r = 0; r < R; ++r) psi[swz<RB>(kbase | (r << lo))] = s[r];
                     }
-                    group_sync<G>();
+                    group_sync<G, T>(slot);
                 }
             }
         }
@@ -375,14 +401,14 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 }
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
-                    const float t = group_sum<G>(ez[j], red, tid);
+                    const float t = group_sum<G, T>(ez[j], red, tid);
                     if (g == 0 && active) p.out[geo.out_base + j] = p.post_scale * t;
                 }
             } else {
                 for (int k = g; k < A; k += G)
                     if (active) reinterpret_cast<float2 *>(p.out + geo.out_base)[k] = psi[swz<RB>(k)];
             }
-            group_sync<G>();
+            group_sync<G, T>(slot);
             continue;
         }
 
@@ -419,7 +445,7 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 }
                 lam[swz<RB>(k)] = l;
             }
-            group_sync<G>();
+            group_sync<G, T>(slot);
 
             float ga[NQ];  // per-instance d/d(alpha_wire), partial over this thread's amplitudes
 #pragma unroll
@@ -431,12 +457,13 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                     const int ring = NQ > 1 ? (layer % NRING) + 1 : 0;
                     const bool encl = (p.enc != QIDDM_ENC_NONE) && layer == 0;
                     float2 s[R], l[R];
-#pragma unroll
+#pragma unroll 1
                     for (int vv = 0; vv < NV; ++vv) {
                         const int v = NV - 1 - vv;
                         const int lo = (v * RB < LO_LAST) ? v * RB : LO_LAST;
-                        const int new_lo = v * RB;
-                        const int new_hi = ((v + 1) * RB < NQ) ? (v + 1) * RB : NQ;
+                        const int q_lo = v * RB - lo;
+                        const int q_hi = (((v + 1) * RB < NQ) ? (v + 1) * RB : NQ) - lo;
+                        const int kbase = amp_index<NQ, RB>(g, 0, lo);
                         if (vv == 0 && NQ > 1) {
                             if (p.imprimitive == QIDDM_IMP_CNOT) {
                                 // pre-ring amplitude k sits at post-ring index f(k)
@@ -448,11 +475,11 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                                     s[r] = psi[a];
                                     l[r] = lam[a];
                                 }
-                                if (G > 1) group_sync<G>();
+                                if (G > 1) group_sync<G, T>(slot);
                             } else {
 #pragma unroll
                                 for (int r = 0; r < R; ++r) {
-                                    const int k = amp_index<NQ, RB>(g, r, lo);
+                                    const int k = kbase | (r << lo);
                                     const float sg = cz_sign<NQ>(k, ring);
                                     const int a = swz<RB>(k);
                                     s[r] = make_float2(psi[a].x * sg, psi[a].y * sg);
@@ -462,16 +489,15 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                         } else {
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
-                                const int a = swz<RB>(amp_index<NQ, RB>(g, r, lo));
+                                const int a = swz<RB>(kbase | (r << lo));
                                 s[r] = psi[a];
                                 l[r] = lam[a];
                             }
                         }
 #pragma unroll
                         for (int q = 0; q < RB; ++q) {
-                            const int pos = lo + q;
-                            if (pos < new_lo || pos >= new_hi) continue;
-                            const int wire = NQ - 1 - pos;
+                            if (q < q_lo || q >= q_hi) continue;
+                            const int wire = NQ - 1 - (lo + q);
                             const Mat ub = load_mat(gm + (gate_base + wire) * 8);
                             float2 cs = make_float2(1.f, 0.f);
                             Mat u = ub;
@@ -496,10 +522,11 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                             if (encl) {
                                 const float c = cs.x, sn = cs.y;
                                 float Mb[8];
+                                float dalpha;
                                 if (p.enc == QIDDM_ENC_RZ) {
                                     // d/dalpha = Im(M00 U'00) - Im(M01 U'01) + Im(M10 U'10) - Im(M11 U'11)
-                                    ga[wire] += (M[0] * u.i00 + M[1] * u.r00) - (M[2] * u.i01 + M[3] * u.r01) +
-                                                (M[4] * u.i10 + M[5] * u.r10) - (M[6] * u.i11 + M[7] * u.r11);
+                                    dalpha = (M[0] * u.i00 + M[1] * u.r00) - (M[2] * u.i01 + M[3] * u.r01) +
+                                             (M[4] * u.i10 + M[5] * u.r10) - (M[6] * u.i11 + M[7] * u.r11);
                                     // M_base = M' E^T, E = diag((c,-s),(c,s))
                                     Mb[0] = M[0] * c + M[1] * sn;  Mb[1] = M[1] * c - M[0] * sn;
                                     Mb[2] = M[2] * c - M[3] * sn;  Mb[3] = M[3] * c + M[2] * sn;
@@ -511,14 +538,17 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                                     const float t1r = -ub.r00 * c - ub.r01 * sn, t1i = -ub.i00 * c - ub.i01 * sn;
                                     const float t2r = -ub.r10 * sn + ub.r11 * c, t2i = -ub.i10 * sn + ub.i11 * c;
                                     const float t3r = -ub.r10 * c - ub.r11 * sn, t3i = -ub.i10 * c - ub.i11 * sn;
-                                    ga[wire] += (M[0] * t0r - M[1] * t0i) + (M[2] * t1r - M[3] * t1i) +
-                                                (M[4] * t2r - M[5] * t2i) + (M[6] * t3r - M[7] * t3i);
+                                    dalpha = (M[0] * t0r - M[1] * t0i) + (M[2] * t1r - M[3] * t1i) +
+                                             (M[4] * t2r - M[5] * t2i) + (M[6] * t3r - M[7] * t3i);
                                     // M_base = M' E^T, E = [[c,-s],[s,c]]
                                     Mb[0] = M[0] * c - M[2] * sn;  Mb[1] = M[1] * c - M[3] * sn;
                                     Mb[2] = M[0] * sn + M[2] * c;  Mb[3] = M[1] * sn + M[3] * c;
                                     Mb[4] = M[4] * c - M[6] * sn;  Mb[5] = M[5] * c - M[7] * sn;
                                     Mb[6] = M[4] * sn + M[6] * c;  Mb[7] = M[5] * sn + M[7] * c;
                                 }
+                                // wire is a runtime value here: select the accumulator without dynamic indexing
+#pragma unroll
+                                for (int j = 0; j < NQ; ++j) ga[j] += (j == wire) ? dalpha : 0.f;
                                 warp_reduce8_add(Mb, acc_s + (gate_base + wire) * 8, lane);
                             } else {
                                 warp_reduce8_add(M, acc_s + (gate_base + wire) * 8, lane);
@@ -526,11 +556,11 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                         }
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const int a = swz<RB>(amp_index<NQ, RB>(g, r, lo));
+                            const int a = swz<RB>(kbase | (r << lo));
                             psi[a] = s[r];
                             lam[a] = l[r];
                         }
-                        group_sync<G>();
+                        group_sync<G, T>(slot);
                     }
                 }
             }
@@ -546,7 +576,7 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                         qv[i] = 2.f * lam[a].x;
                         dot += qv[i] * psi[a].x;
                     }
-                    dot = group_sum<G>(dot, red, tid);
+                    dot = group_sum<G, T>(dot, red, tid);
 #pragma unroll
                     for (int i = 0; i < R; ++i) {
                         const int k = g + i * G;
@@ -564,12 +594,12 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 if (p.enc != QIDDM_ENC_NONE) {
 #pragma unroll
                     for (int j = 0; j < NQ; ++j) {
-                        const float t = group_sum<G>(ga[j], red, tid);
+                        const float t = group_sum<G, T>(ga[j], red, tid);
                         if (g == 0 && active) p.grad_in[geo.in_base + j] = p.enc_scale * t;
                     }
                 }
             }
-            group_sync<G>();
+            group_sync<G, T>(slot);
         }
     }
 
@@ -597,9 +627,8 @@ size_t smem_bytes(const GateParams &p, bool bwd) {
     return (bytes + 15) & ~(size_t)15;
 }
 
-template <int NQ, bool BWD>
+template <int NQ, int RB, bool BWD>
 cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
-    constexpr int RB = BWD ? rb_backward(NQ) : rb_forward(NQ);
     using C = Cfg<NQ, RB>;
     auto kern = gate_kernel<NQ, RB, BWD>;
     li->block = C::T;
@@ -617,9 +646,8 @@ cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
     return cudaSuccess;
 }
 
-template <int NQ, bool BWD>
+template <int NQ, int RB, bool BWD>
 cudaError_t launch_t(const GateParams &p, const LaunchInfo &li, cudaStream_t s) {
-    constexpr int RB = BWD ? rb_backward(NQ) : rb_forward(NQ);
     // algorithmic flops: 14 * 2^n per Rot; the adjoint sweep costs 4x a forward
     const double work = (double)p.B * p.n_rot * 14.0 * (double)(1 << NQ) * (BWD ? 4.0 : 1.0);
     timing_begin(BWD ? TK_GATE_BWD : TK_GATE_FWD, work, s);
@@ -629,20 +657,32 @@ cudaError_t launch_t(const GateParams &p, const LaunchInfo &li, cudaStream_t s) 
     return cudaGetLastError();
 }
 
+#define QIDDM_RB_CASES(EXPR)                                             \
+    switch (rb) {                                                        \
+        case 3: { constexpr int RB = NQ < 3 ? NQ : 3; return EXPR; }     \
+        case 4: { constexpr int RB = NQ < 4 ? NQ : 4; return EXPR; }     \
+        case 5: { constexpr int RB = NQ < 5 ? NQ : 5; return EXPR; }     \
+        default: { constexpr int RB = NQ < 3 ? NQ : 3; return EXPR; }    \
+    }
+#define QIDDM_RB_CASES_BIG(EXPR)                                         \
+    switch (rb) {                                                        \
+        case 5: { constexpr int RB = 5; return EXPR; }                   \
+        default: { constexpr int RB = 4; return EXPR; }                  \
+    }
 #define QIDDM_DISPATCH_NQ(nq, EXPR)                                      \
     switch (nq) {                                                        \
-        case 1: { constexpr int NQ = 1; return EXPR; }                   \
-        case 2: { constexpr int NQ = 2; return EXPR; }                   \
-        case 3: { constexpr int NQ = 3; return EXPR; }                   \
-        case 4: { constexpr int NQ = 4; return EXPR; }                   \
-        case 5: { constexpr int NQ = 5; return EXPR; }                   \
-        case 6: { constexpr int NQ = 6; return EXPR; }                   \
-        case 7: { constexpr int NQ = 7; return EXPR; }                   \
-        case 8: { constexpr int NQ = 8; return EXPR; }                   \
-        case 9: { constexpr int NQ = 9; return EXPR; }                   \
-        case 10: { constexpr int NQ = 10; return EXPR; }                 \
-        case 11: { constexpr int NQ = 11; return EXPR; }                 \
-        case 12: { constexpr int NQ = 12; return EXPR; }                 \
+        case 1: { constexpr int NQ = 1; constexpr int RB = 1; return EXPR; } \
+        case 2: { constexpr int NQ = 2; constexpr int RB = 2; return EXPR; } \
+        case 3: { constexpr int NQ = 3; constexpr int RB = 3; return EXPR; } \
+        case 4: { constexpr int NQ = 4; QIDDM_RB_CASES(EXPR) }           \
+        case 5: { constexpr int NQ = 5; QIDDM_RB_CASES(EXPR) }           \
+        case 6: { constexpr int NQ = 6; QIDDM_RB_CASES(EXPR) }           \
+        case 7: { constexpr int NQ = 7; QIDDM_RB_CASES(EXPR) }           \
+        case 8: { constexpr int NQ = 8; QIDDM_RB_CASES(EXPR) }           \
+        case 9: { constexpr int NQ = 9; QIDDM_RB_CASES(EXPR) }           \
+        case 10: { constexpr int NQ = 10; QIDDM_RB_CASES(EXPR) }         \
+        case 11: { constexpr int NQ = 11; QIDDM_RB_CASES(EXPR) }         \
+        case 12: { constexpr int NQ = 12; QIDDM_RB_CASES_BIG(EXPR) }     \
         default: return cudaErrorInvalidValue;                           \
     }
 
@@ -726,17 +766,20 @@ __global__ void finalize_grads_kernel(const float *partials, int n_partials, con
 
 }  // namespace
 
-int gate_rb(int n_qubits, bool backward) { return backward ? rb_backward(n_qubits) : rb_forward(n_qubits); }
+int gate_rb(int n_qubits, bool backward) { return rb_choose(n_qubits, backward); }
 
 cudaError_t gate_launch_info(int n_qubits, bool backward, const GateParams &p, LaunchInfo *info) {
-    if (backward) { QIDDM_DISPATCH_NQ(n_qubits, (info_t<NQ, true>(p, info))) }
-    QIDDM_DISPATCH_NQ(n_qubits, (info_t<NQ, false>(p, info)))
+    const int rb = rb_choose(n_qubits, backward);
+    if (backward) { QIDDM_DISPATCH_NQ(n_qubits, (info_t<NQ, RB, true>(p, info))) }
+    QIDDM_DISPATCH_NQ(n_qubits, (info_t<NQ, RB, false>(p, info)))
 }
 cudaError_t launch_gate_forward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s) {
-    QIDDM_DISPATCH_NQ(n_qubits, (launch_t<NQ, false>(p, li, s)))
+    const int rb = rb_choose(n_qubits, false);
+    QIDDM_DISPATCH_NQ(n_qubits, (launch_t<NQ, RB, false>(p, li, s)))
 }
 cudaError_t launch_gate_backward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s) {
-    QIDDM_DISPATCH_NQ(n_qubits, (launch_t<NQ, true>(p, li, s)))
+    const int rb = rb_choose(n_qubits, true);
+    QIDDM_DISPATCH_NQ(n_qubits, (launch_t<NQ, RB, true>(p, li, s)))
 }
 cudaError_t launch_prepare_gates(const void *weights, int wdtype, int remap, int n_rot, float *gates, cudaStream_t s) {
     prepare_gates_kernel<<<(n_rot + 127) / 128, 128, 0, s>>>(weights, wdtype, remap, n_rot, gates);
