@@ -12,10 +12,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libqiddm_b200.so"
 SOURCES = ["qiddm_gate.cu", "qiddm_gemm.cu", "qiddm_api.cu"]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def find_nvcc() -> str:
@@ -41,11 +38,26 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{CSRC}", "-o", str(LIB_PATH),
-           *[str(s) for s in sources()]]
+    obj_dir = PKG / "build"
+    obj_dir.mkdir(exist_ok=True)
+    nvcc = find_nvcc()
+    inc = [f"-I{ROOT / 'include'}", f"-I{CSRC}"]
+    # one nvcc per translation unit, in parallel; then link
+    procs, objs = [], []
+    for src in sources():
+        obj = obj_dir / (src.stem + ".o")
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH), *[str(o) for o in objs]]
     if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+        print(" ".join(link))
+    subprocess.run(link, check=True)
     return LIB_PATH
 
 

@@ -117,7 +117,7 @@ GateParams make_params(const qiddm_plan *pl, const qiddm_unfold_desc *u, long lo
     p.clamp_lo = d.clamp_lo;
     p.clamp_hi = d.clamp_hi;
     p.n_rot = pl->n_rot;
-    p.gates_in_smem = (size_t)pl->n_rot * 32 <= 48 * 1024;
+    p.merge_post = (d.imprimitive == QIDDM_IMP_CZ && d.enc != QIDDM_ENC_RY) ? 1 : 0;
     p.B = B;
     if (u) {
         p.unfold = 1;
@@ -138,7 +138,9 @@ bool unfold_valid(const qiddm_plan *pl, const qiddm_unfold_desc *u) {
     return true;
 }
 
-size_t gates_bytes(const qiddm_plan *pl) { return align_up((size_t)pl->n_rot * 8 * sizeof(float)); }
+size_t gates_bytes(const qiddm_plan *pl) {
+    return align_up(gate_table_bytes(pl->d.n_qubits, pl->d.n_blocks * pl->d.layers_per_block));
+}
 
 int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
                  const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s) {
@@ -150,7 +152,8 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
     GateParams p = make_params(pl, u, B);
     float *gates = reinterpret_cast<float *>(ws);
     p.in = in; p.basis = basis; p.gates = gates; p.out = out;
-    cudaError_t e = launch_prepare_gates(weights, wdtype, pl->d.remap, pl->n_rot, gates, s);
+    cudaError_t e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, false,
+                                          pl->d.n_blocks * pl->d.layers_per_block, p.merge_post, gates, s);
     if (e != cudaSuccess) return (int)e;
     LaunchInfo li;
     if ((e = gate_launch_info(pl->d.n_qubits, false, p, &li)) != cudaSuccess) return (int)e;
@@ -181,12 +184,15 @@ int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float 
     if (u && grad_in) {
         if ((e = cudaMemsetAsync(grad_in, 0, (size_t)grad_in_elems * sizeof(float), s)) != cudaSuccess) return (int)e;
     }
-    if ((e = launch_prepare_gates(weights, wdtype, pl->d.remap, pl->n_rot, gates, s)) != cudaSuccess) return (int)e;
+    if ((e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, true,
+                                   pl->d.n_blocks * pl->d.layers_per_block, p.merge_post, gates, s)) != cudaSuccess)
+        return (int)e;
     LaunchInfo li;
     if ((e = gate_launch_info(pl->d.n_qubits, true, p, &li)) != cudaSuccess) return (int)e;
     if ((e = launch_gate_backward(pl->d.n_qubits, p, li, s)) != cudaSuccess) return (int)e;
     if (grad_weights) {
-        if ((e = launch_finalize_grads(partials, li.grid, weights, wdtype, pl->d.remap, pl->n_rot, grad_weights, s)) !=
+        if ((e = launch_finalize_grads(partials, li.grid, weights, wdtype, pl->d.remap, pl->d.n_qubits,
+                                       pl->d.n_blocks * pl->d.layers_per_block, p.merge_post, grad_weights, s)) !=
             cudaSuccess)
             return (int)e;
     }
@@ -221,8 +227,8 @@ int qiddm_plan_create(const qiddm_circuit_desc *desc, qiddm_plan **plan) {
     *plan = nullptr;
     if (!desc_valid(desc)) return QIDDM_EINVAL;
     const long long n_rot = (long long)desc->n_blocks * desc->layers_per_block * desc->n_qubits;
-    // the backward kernel keeps one 2x2 cotangent (8 floats) per Rot gate in shared memory
-    if (n_rot * 32 > 96 * 1024) return QIDDM_EUNSUPPORTED;
+    // the backward kernel keeps three angle-gradient sums per Rot gate in shared memory
+    if (n_rot * 12 > 96 * 1024) return QIDDM_EUNSUPPORTED;
     qiddm_plan *p = new (std::nothrow) qiddm_plan;
     if (!p) return QIDDM_ENOMEM;
     p->d = *desc;
@@ -244,7 +250,7 @@ size_t qiddm_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
         if (gate_launch_info(plan->d.n_qubits, true, p, &li) == cudaSuccess) grid = li.grid;
         else (void)cudaGetLastError();
     }
-    return gates_bytes(plan) + align_up((size_t)grid * plan->n_rot * 8 * sizeof(float));
+    return gates_bytes(plan) + align_up((size_t)grid * plan->n_rot * 3 * sizeof(float));
 }
 
 int qiddm_forward(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,

@@ -12,18 +12,18 @@ struct GateParams {
     int n_blocks, layers, init, n_features, enc, imprimitive, readout, read_count, read_stride, clamp;
     float pad_value, add_offset, enc_scale, post_scale, clamp_lo, clamp_hi;
     int n_rot;                 // n_blocks * layers * n_qubits
-    int gates_in_smem;         // 1: stage the 2x2 matrices in shared memory
+    int merge_post;            // 1: RZ(omega) phases of layer l are merged into layer l+1's RZ(phi) table (CZ entangler)
     // fused patch-unfold (QConv); unfold == 0 -> plain (B, n_in) rows
     int unfold, C, H, W, kh, kw, ph, pw, Hout, Wout;
     long long B;               // circuit instances
     const float *in;           // (B, n_in) features / angles, or NCHW image when unfold
     const int *basis;          // INIT_BASIS start states (may be null -> instance index)
-    const float *gates;        // [n_rot][8]: re00 im00 re01 im01 re10 im10 re11 im11
+    const float *gates;        // per-layer phase tables + rotation coefficients (prepare_tables_kernel)
     float *out;
     // backward only
     const float *grad_out;
     float *grad_in;            // nullable
-    float *partials;           // [grid][n_rot*8] per-CTA sums of the 2x2 gate cotangents
+    float *partials;           // [grid][n_rot*3] per-CTA sums of the angle gradients (phi, theta, omega)
 };
 
 struct LaunchInfo {
@@ -36,9 +36,11 @@ int gate_rb(int n_qubits, bool backward);
 cudaError_t gate_launch_info(int n_qubits, bool backward, const GateParams &p, LaunchInfo *info);
 cudaError_t launch_gate_forward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s);
 cudaError_t launch_gate_backward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s);
-cudaError_t launch_prepare_gates(const void *weights, int wdtype, int remap, int n_rot, float *gates, cudaStream_t s);
-cudaError_t launch_finalize_grads(const float *partials, int n_partials, const void *weights, int wdtype,
-                                  int remap, int n_rot, void *grad_weights, cudaStream_t s);
+size_t gate_table_bytes(int n_qubits, int n_layers);
+cudaError_t launch_prepare_tables(const void *weights, int wdtype, int remap, int n_qubits, bool backward,
+                                  int n_layers, int merge_post, float *tables, cudaStream_t s);
+cudaError_t launch_finalize_grads(const float *partials, int n_partials, const void *weights, int wdtype, int remap,
+                                  int n_qubits, int n_layers, int merge_post, void *grad_weights, cudaStream_t s);
 void count_launch(int n = 1);
 
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream around
