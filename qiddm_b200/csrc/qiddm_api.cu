@@ -152,8 +152,7 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
     GateParams p = make_params(pl, u, B);
     float *gates = reinterpret_cast<float *>(ws);
     p.in = in; p.basis = basis; p.gates = gates; p.out = out;
-    cudaError_t e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, false,
-                                          pl->d.n_blocks * pl->d.layers_per_block, p.merge_post, gates, s);
+    cudaError_t e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, false, p, gates, s);
     if (e != cudaSuccess) return (int)e;
     LaunchInfo li;
     if ((e = gate_launch_info(pl->d.n_qubits, false, p, &li)) != cudaSuccess) return (int)e;
@@ -184,16 +183,14 @@ int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float 
     if (u && grad_in) {
         if ((e = cudaMemsetAsync(grad_in, 0, (size_t)grad_in_elems * sizeof(float), s)) != cudaSuccess) return (int)e;
     }
-    if ((e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, true,
-                                   pl->d.n_blocks * pl->d.layers_per_block, p.merge_post, gates, s)) != cudaSuccess)
+    if ((e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, true, p, gates, s)) != cudaSuccess)
         return (int)e;
     LaunchInfo li;
     if ((e = gate_launch_info(pl->d.n_qubits, true, p, &li)) != cudaSuccess) return (int)e;
     if ((e = launch_gate_backward(pl->d.n_qubits, p, li, s)) != cudaSuccess) return (int)e;
     if (grad_weights) {
-        if ((e = launch_finalize_grads(partials, li.grid, weights, wdtype, pl->d.remap, pl->d.n_qubits,
-                                       pl->d.n_blocks * pl->d.layers_per_block, p.merge_post, grad_weights, s)) !=
-            cudaSuccess)
+        if ((e = launch_finalize_grads(partials, li.grid, weights, wdtype, pl->d.remap, pl->d.n_qubits, p, grad_weights,
+                                       s)) != cudaSuccess)
             return (int)e;
     }
     return QIDDM_OK;
@@ -250,7 +247,9 @@ size_t qiddm_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
         if (gate_launch_info(plan->d.n_qubits, true, p, &li) == cudaSuccess) grid = li.grid;
         else (void)cudaGetLastError();
     }
-    return gates_bytes(plan) + align_up((size_t)grid * plan->n_rot * 3 * sizeof(float));
+    return gates_bytes(plan) +
+           align_up((size_t)grid * gate_partial_floats(plan->d.n_qubits, plan->d.n_blocks * plan->d.layers_per_block) *
+                    sizeof(float));
 }
 
 int qiddm_forward(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,

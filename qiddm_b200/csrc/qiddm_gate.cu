@@ -48,7 +48,9 @@ struct Cfg {
     static constexpr int SPAN = A + (A >> RB);      // padded float2 slots of one state
     static constexpr int STRIDE = SPAN | 1;         // odd: spreads the instances of a CTA over the banks
     static constexpr int LO_LAST = NQ - RB;
-    static constexpr int TAB_LAYER = NV * 2 * R + NQ;   // float2 per layer: [view][pre|post][R], then (cos,sin)[wire]
+    static constexpr int NVF = NQ / RB;                 // full views; a partial last view follows when NQ % RB != 0
+    static constexpr int Q_TAIL = RB - NQ % RB;         // first owned local bit of the partial view
+    static constexpr int TAB_LAYER = NV * 2 * R + ((NQ + 1) & ~1);   // float2 per layer: [view][pre|post][R], (cos,sin)[wire]
 };
 
 // Register-tile width (log2 amplitudes per thread).  Valid widths keep every view's low bit at 0 or
@@ -63,7 +65,7 @@ inline bool rb_valid(int nq, int rb) {
 inline int rb_default(int nq, bool bwd) {
     if (nq <= 5) return nq;
     if (nq <= 7) return 3;
-    if (bwd) return nq <= 9 ? 4 : (nq <= 11 ? 4 : 4);
+    if (bwd) return nq <= 9 ? 4 : 5;
     return nq <= 9 ? 4 : 5;
 }
 inline int rb_choose(int nq, bool bwd) {
@@ -250,25 +252,176 @@ struct View {
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// View cores: everything that happens to a register tile between its load and its store.  Q_LO is the
+// first local bit the view owns (0 for a full view; the only partial view is the last one when
+// NQ % RB != 0), so the set of active local bits is known at compile time.
+// ---------------------------------------------------------------------------------------------
+enum { ENCL_NONE = 0, ENCL_RZ = 1, ENCL_RY = 2 };
+
+template <int RB, int Q>
+__device__ __forceinline__ void ry_all(float2 cs, float2 (&s)[1 << RB]) {
+#pragma unroll
+    for (int j = 0; j < (1 << RB) / 2; ++j) {
+        const int r0 = ((j >> Q) << (Q + 1)) | (j & ((1 << Q) - 1));
+        ry_pair(cs, s[r0], s[r0 | (1 << Q)]);
+    }
+}
+// theta gradient from the post-rotation states, then RY^T on both
+template <int RB, int Q>
+__device__ __forceinline__ float ry_all_bwd(float2 cs, float2 (&s)[1 << RB], float2 (&l)[1 << RB]) {
+    float gt = 0.f;
+#pragma unroll
+    for (int j = 0; j < (1 << RB) / 2; ++j) {
+        const int r0 = ((j >> Q) << (Q + 1)) | (j & ((1 << Q) - 1));
+        const int r1 = r0 | (1 << Q);
+        gt += l[r1].x * s[r0].x + l[r1].y * s[r0].y - l[r0].x * s[r1].x - l[r0].y * s[r1].y;
+        ry_pair_t(cs, s[r0], s[r1]);
+        ry_pair_t(cs, l[r0], l[r1]);
+    }
+    return gt;
+}
+// s[r] *= table[r] (CONJ: conj(table[r])); two entries per 16-byte uniform load
+template <int RB, bool CONJ, bool GLOBAL>
+__device__ __forceinline__ void diag_mul(float2 (&s)[1 << RB], const float2 *t) {
+    if ((1 << RB) >= 2) {
+#pragma unroll
+        for (int j = 0; j < (1 << RB) / 2; ++j) {
+            const float4 e = GLOBAL ? __ldg(reinterpret_cast<const float4 *>(t) + j) : reinterpret_cast<const float4 *>(t)[j];
+            s[2 * j] = CONJ ? cmul_conj(s[2 * j], make_float2(e.x, e.y)) : cmul(s[2 * j], make_float2(e.x, e.y));
+            s[2 * j + 1] = CONJ ? cmul_conj(s[2 * j + 1], make_float2(e.z, e.w)) : cmul(s[2 * j + 1], make_float2(e.z, e.w));
+        }
+    }
+}
+template <int RB, bool GLOBAL>
+__device__ __forceinline__ void diag_mul2_conj(float2 (&s)[1 << RB], float2 (&l)[1 << RB], const float2 *t) {
+#pragma unroll
+    for (int j = 0; j < (1 << RB) / 2; ++j) {
+        const float4 e = GLOBAL ? __ldg(reinterpret_cast<const float4 *>(t) + j) : reinterpret_cast<const float4 *>(t)[j];
+        const float2 e0 = make_float2(e.x, e.y), e1 = make_float2(e.z, e.w);
+        s[2 * j] = cmul_conj(s[2 * j], e0);
+        l[2 * j] = cmul_conj(l[2 * j], e0);
+        s[2 * j + 1] = cmul_conj(s[2 * j + 1], e1);
+        l[2 * j + 1] = cmul_conj(l[2 * j + 1], e1);
+    }
+}
+
+// forward: [RY(s a)] -> pre phases -> [RZ(s a) phases] -> RY(theta) per owned wire -> [post phases]
+template <int NQ, int RB, int Q_LO>
+__device__ __forceinline__ void view_fwd(float2 (&s)[1 << RB], const float2 *tv, const float2 *cst, int lo,
+                                         bool has_post, int encl, const float2 *ev, const float2 *ep) {
+    constexpr int R = 1 << RB;
+    if (encl == ENCL_RY) {
+        if (Q_LO <= 0 && RB > 0) ry_all<RB, 0>(ep[NQ - 1 - lo], s);
+        if (Q_LO <= 1 && RB > 1) ry_all<RB, (RB > 1 ? 1 : 0)>(ep[NQ - 2 - lo], s);
+        if (Q_LO <= 2 && RB > 2) ry_all<RB, (RB > 2 ? 2 : 0)>(ep[NQ - 3 - lo], s);
+        if (Q_LO <= 3 && RB > 3) ry_all<RB, (RB > 3 ? 3 : 0)>(ep[NQ - 4 - lo], s);
+        if (Q_LO <= 4 && RB > 4) ry_all<RB, (RB > 4 ? 4 : 0)>(ep[NQ - 5 - lo], s);
+    }
+    diag_mul<RB, false, true>(s, tv);
+    if (encl == ENCL_RZ) diag_mul<RB, false, false>(s, ev);
+    if (Q_LO <= 0 && RB > 0) ry_all<RB, 0>(__ldg(cst + (NQ - 1 - lo)), s);
+    if (Q_LO <= 1 && RB > 1) ry_all<RB, (RB > 1 ? 1 : 0)>(__ldg(cst + (NQ - 2 - lo)), s);
+    if (Q_LO <= 2 && RB > 2) ry_all<RB, (RB > 2 ? 2 : 0)>(__ldg(cst + (NQ - 3 - lo)), s);
+    if (Q_LO <= 3 && RB > 3) ry_all<RB, (RB > 3 ? 3 : 0)>(__ldg(cst + (NQ - 4 - lo)), s);
+    if (Q_LO <= 4 && RB > 4) ry_all<RB, (RB > 4 ? 4 : 0)>(__ldg(cst + (NQ - 5 - lo)), s);
+    if (has_post) diag_mul<RB, false, true>(s, tv + R);
+}
+
+// backward: inverse of view_fwd on psi (s) and lambda (l); gv[q*3 + {0,1,2}] = this thread's partial
+// d/dphi, d/dtheta, d/domega of the wire at local bit q; ga[] += d/d(s a_wire) on re-upload layers.
+template <int NQ, int RB, int Q_LO>
+__device__ __forceinline__ void view_bwd(float2 (&s)[1 << RB], float2 (&l)[1 << RB], float (&gv)[16],
+                                         float (&ga)[NQ], const float2 *tv, const float2 *cst, int lo,
+                                         bool has_post, int encl, const float2 *ev, const float2 *ep) {
+    constexpr int R = 1 << RB;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gv[i] = 0.f;
+    if (has_post) {
+        float t[R], S[RB];
+#pragma unroll
+        for (int r = 0; r < R; ++r) t[r] = l[r].x * s[r].y - l[r].y * s[r].x;   // Im(conj(l) s)
+        signed_sums<RB>(t, S);
+#pragma unroll
+        for (int q = Q_LO; q < RB; ++q) gv[q * 3 + 2] = S[q];
+        diag_mul2_conj<RB, true>(s, l, tv + R);
+    }
+    if (Q_LO <= 4 && RB > 4) gv[4 * 3 + 1] = ry_all_bwd<RB, (RB > 4 ? 4 : 0)>(__ldg(cst + (NQ - 5 - lo)), s, l);
+    if (Q_LO <= 3 && RB > 3) gv[3 * 3 + 1] = ry_all_bwd<RB, (RB > 3 ? 3 : 0)>(__ldg(cst + (NQ - 4 - lo)), s, l);
+    if (Q_LO <= 2 && RB > 2) gv[2 * 3 + 1] = ry_all_bwd<RB, (RB > 2 ? 2 : 0)>(__ldg(cst + (NQ - 3 - lo)), s, l);
+    if (Q_LO <= 1 && RB > 1) gv[1 * 3 + 1] = ry_all_bwd<RB, (RB > 1 ? 1 : 0)>(__ldg(cst + (NQ - 2 - lo)), s, l);
+    if (Q_LO <= 0 && RB > 0) gv[0 * 3 + 1] = ry_all_bwd<RB, 0>(__ldg(cst + (NQ - 1 - lo)), s, l);
+    {
+        float t[R], S[RB];
+#pragma unroll
+        for (int r = 0; r < R; ++r) t[r] = l[r].x * s[r].y - l[r].y * s[r].x;
+        signed_sums<RB>(t, S);
+#pragma unroll
+        for (int q = Q_LO; q < RB; ++q) gv[q * 3] = S[q];
+        if (encl == ENCL_RZ) {
+#pragma unroll
+            for (int q = Q_LO; q < RB; ++q) {
+                const int wire = NQ - 1 - (lo + q);
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) ga[j] += (j == wire) ? S[q] : 0.f;
+            }
+            diag_mul2_conj<RB, false>(s, l, ev);
+        }
+        diag_mul2_conj<RB, true>(s, l, tv);
+    }
+    if (encl == ENCL_RY) {
+        float ge[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) ge[q] = 0.f;
+        if (Q_LO <= 4 && RB > 4) ge[(RB > 4 ? 4 : 0)] = ry_all_bwd<RB, (RB > 4 ? 4 : 0)>(ep[NQ - 5 - lo], s, l);
+        if (Q_LO <= 3 && RB > 3) ge[(RB > 3 ? 3 : 0)] = ry_all_bwd<RB, (RB > 3 ? 3 : 0)>(ep[NQ - 4 - lo], s, l);
+        if (Q_LO <= 2 && RB > 2) ge[(RB > 2 ? 2 : 0)] = ry_all_bwd<RB, (RB > 2 ? 2 : 0)>(ep[NQ - 3 - lo], s, l);
+        if (Q_LO <= 1 && RB > 1) ge[(RB > 1 ? 1 : 0)] = ry_all_bwd<RB, (RB > 1 ? 1 : 0)>(ep[NQ - 2 - lo], s, l);
+        if (Q_LO <= 0 && RB > 0) ge[0] = ry_all_bwd<RB, 0>(ep[NQ - 1 - lo], s, l);
+#pragma unroll
+        for (int q = Q_LO; q < RB; ++q) {
+            const int wire = NQ - 1 - (lo + q);
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) ga[j] += (j == wire) ? ge[q] : 0.f;
+        }
+    }
+}
+
+// resident CTAs per SM the register allocation aims for (more warps hide the shared-memory and table-load latency)
 template <int NQ, int RB, bool BWD>
-__global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p) {
+constexpr int min_blocks() {
+    constexpr int T = Cfg<NQ, RB>::T;
+    constexpr int want_regs = BWD ? (RB >= 5 ? 255 : RB == 4 ? 168 : 128) : (RB >= 5 ? 128 : RB == 4 ? 96 : 64);
+    constexpr int b = 65536 / (T * want_regs);
+    return b < 1 ? 1 : b;
+}
+
+// RES ("resident" schedule; NQ == 2 RB, diagonal entangler): a tile stays in registers across a layer
+// boundary -- RY(l-1) on its wires, the whole boundary diagonal (own wires from a table, the other half's
+// wires as one per-thread scalar, CZ signs, re-upload phases), RY(l) -- so the state crosses shared memory
+// once per layer instead of twice and only one phase table is read per layer.
+template <int NQ, int RB, bool BWD, bool RES>
+__global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gate_kernel(const GateParams p) {
     using C = Cfg<NQ, RB>;
     constexpr int A = C::A, R = C::R, G = C::G, NV = C::NV, T = C::T, CPB = C::CPB, STRIDE = C::STRIDE;
-    constexpr int LO_LAST = C::LO_LAST, TAB_LAYER = C::TAB_LAYER;
+    constexpr int LO_LAST = C::LO_LAST, TAB_LAYER = C::TAB_LAYER, NVF = C::NVF, Q_TAIL = C::Q_TAIL;
     constexpr int NRING = NQ > 1 ? NQ - 1 : 1;
+    constexpr int TAB_RES = 2 * R + ((NQ + 1) & ~1);   // RES: float2 per boundary: local[R], scalar[G = R], (cos,sin)[wire]
 
     extern __shared__ float4 smem_f4[];
     float *sm = reinterpret_cast<float *>(smem_f4);
-    // carve-up (float offsets; float2 regions start at even offsets)
-    const int n_acc = (p.n_rot * 3 + 1) & ~1;
+    // carve-up (float offsets; the per-instance phase tables are read as float4, so they come 16-byte aligned)
+    const int n_grad = RES ? (p.n_rot + NQ) * 2 : p.n_rot * 3;   // angle-gradient sums kept per CTA
+    const int n_acc = (n_grad + 3) & ~3;
     float *acc_s = sm;                                               // [n_acc] (BWD)
-    float2 *psi_all = reinterpret_cast<float2 *>(acc_s + (BWD ? n_acc : 0));
+    float2 *et_all = reinterpret_cast<float2 *>(acc_s + (BWD ? n_acc : 0));   // [CPB][NV][R] RZ re-upload phase tables
+    float2 *psi_all = et_all + (p.enc == QIDDM_ENC_RZ ? CPB * NV * R : 0);
     float2 *lam_all = psi_all + CPB * STRIDE;
     float2 *ep_all = BWD ? lam_all + CPB * STRIDE : lam_all;         // [CPB][NQ] (cos, sin)(s a_j / 2)
-    float2 *et_all = ep_all + CPB * NQ;                              // [CPB][NV][R] RZ re-upload phase tables
-    float *red = reinterpret_cast<float *>(et_all + (p.enc == QIDDM_ENC_RZ ? CPB * NV * R : 0));   // [T/32]
-    unsigned int *czw = reinterpret_cast<unsigned int *>(red + T / 32);                          // [NRING][G]
-    int *foff = reinterpret_cast<int *>(czw + (p.imprimitive == QIDDM_IMP_CZ ? NRING * G : 0));   // [2][n_features] (unfold)
+    float *red = reinterpret_cast<float *>(ep_all + CPB * NQ);       // [T/32]
+    unsigned int *czw = reinterpret_cast<unsigned int *>(red + T / 32);                          // [NRING][G] (RES: [2][NRING][G])
+    int *foff = reinterpret_cast<int *>(czw + (p.imprimitive == QIDDM_IMP_CZ ? (RES ? 2 : 1) * NRING * G : 0));   // [2][n_features] (unfold)
     int *fyx = foff + p.n_features;
     unsigned short *ftab = reinterpret_cast<unsigned short *>(foff + (p.unfold ? 2 * p.n_features : 0));
 
@@ -287,11 +440,15 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 ftab[i] = (unsigned short)ring_f<NQ>(r << LO_LAST, ring);
             }
         } else {
-            // bit r of czw[ring-1][g]: parity of the CZ ring on amplitude g | r << LO_LAST (last view's tile)
-            for (int i = tid; i < NRING * G; i += T) {
-                const int ring = i / G + 1, gg = i % G;
+            // bit r of czw[ring-1][g]: parity of the CZ ring on amplitude g | r << LO_LAST (last view's tile);
+            // RES: czw[v][ring-1][g] for the tiles of view 0 (g << RB | r) and view 1 (r << RB | g)
+            for (int i = tid; i < (RES ? 2 : 1) * NRING * G; i += T) {
+                const int v = i / (NRING * G), ring = (i / G) % NRING + 1, gg = i % G;
                 unsigned int w = 0;
-                for (int r = 0; r < R; ++r) w |= (unsigned int)cz_parity<NQ>(gg | (r << LO_LAST), ring) << r;
+                for (int r = 0; r < R; ++r) {
+                    const int k = RES ? (v == 0 ? ((gg << RB) | r) : ((r << RB) | gg)) : (gg | (r << LO_LAST));
+                    w |= (unsigned int)cz_parity<NQ>(k, ring) << r;
+                }
                 czw[i] = w;
             }
         }
@@ -373,54 +530,77 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
         group_sync<G, T>(slot);
 
         // ---------------------------------------------------------------- forward sweep
+        const int enc_mode = p.enc == QIDDM_ENC_RZ ? ENCL_RZ : (p.enc == QIDDM_ENC_RY ? ENCL_RY : ENCL_NONE);
+        const bool apply_last = p.readout == QIDDM_READ_STATE;   // a trailing diagonal only matters for a state readout
+        if constexpr (RES) {
+#pragma unroll 1
+            for (int j = 0; j <= n_layers; ++j) {
+                const int v = j & 1;
+                float2 *pp = psi + (v == 0 ? slot_of<RB>(g << RB) : g);
+                const int stride = v == 0 ? 1 : R + 1;
+                const int w0 = NQ - 1 - v * RB;                       // wire of local bit 0 in this view
+                const float2 *tb = tab + (size_t)j * TAB_RES;
+                float2 s[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s[r] = pp[r * stride];
+                if (j > 0) {
+                    const float2 *cst = tb - TAB_RES + 2 * R;
+                    if (RB > 0) ry_all<RB, 0>(__ldg(cst + w0), s);
+                    if (RB > 1) ry_all<RB, (RB > 1 ? 1 : 0)>(__ldg(cst + w0 - 1), s);
+                    if (RB > 2) ry_all<RB, (RB > 2 ? 2 : 0)>(__ldg(cst + w0 - 2), s);
+                    if (RB > 3) ry_all<RB, (RB > 3 ? 3 : 0)>(__ldg(cst + w0 - 3), s);
+                    if (RB > 4) ry_all<RB, (RB > 4 ? 4 : 0)>(__ldg(cst + w0 - 4), s);
+                }
+                if (j < n_layers || apply_last) {
+                    diag_mul<RB, false, true>(s, tb);
+                    float2 x = __ldg(tb + R + g);
+                    if (enc_mode == ENCL_RZ && j < n_layers && j % p.layers == 0) {
+                        diag_mul<RB, false, false>(s, et + v * R);
+                        x = cmul(x, et[(1 - v) * R + g]);
+                    }
+                    if (j > 0 && NQ > 1) {
+                        const unsigned int w = czw[(v * NRING + ((j - 1) % p.layers) % NRING) * G + g];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const unsigned int sg = (w << (31 - r)) & 0x80000000u;
+                            const float2 y = cmul(s[r], x);
+                            s[r] = make_float2(__uint_as_float(__float_as_uint(y.x) ^ sg), __uint_as_float(__float_as_uint(y.y) ^ sg));
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) s[r] = cmul(s[r], x);
+                    }
+                }
+                if (j < n_layers) {
+                    const float2 *cst = tb + 2 * R;
+                    if (RB > 0) ry_all<RB, 0>(__ldg(cst + w0), s);
+                    if (RB > 1) ry_all<RB, (RB > 1 ? 1 : 0)>(__ldg(cst + w0 - 1), s);
+                    if (RB > 2) ry_all<RB, (RB > 2 ? 2 : 0)>(__ldg(cst + w0 - 2), s);
+                    if (RB > 3) ry_all<RB, (RB > 3 ? 3 : 0)>(__ldg(cst + w0 - 3), s);
+                    if (RB > 4) ry_all<RB, (RB > 4 ? 4 : 0)>(__ldg(cst + w0 - 4), s);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) pp[r * stride] = s[r];
+                group_sync<G, T>(slot);
+            }
+        } else {
 #pragma unroll 1
         for (int li = 0; li < n_layers; ++li) {
             const int layer = li % p.layers;
             const int ring = NQ > 1 ? (layer % NRING) + 1 : 0;
-            const bool encl = (p.enc != QIDDM_ENC_NONE) && layer == 0;
+            const int encl = layer == 0 ? enc_mode : ENCL_NONE;
             const bool has_post = post_all || li == n_layers - 1;
             const float2 *tl = tab + (size_t)li * TAB_LAYER;
+            const float2 *cst = tl + NV * 2 * R;
 #pragma unroll 1
             for (int v = 0; v < NV; ++v) {
                 const View<NQ, RB> vw(v, g);
-                const float2 *tv = tl + v * 2 * R;
                 float2 *pp = psi + vw.base;
                 float2 s[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) s[r] = pp[r * vw.stride];
-                if (encl && p.enc == QIDDM_ENC_RY) {
-#pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        if (q < vw.q_lo || q >= vw.q_hi) continue;
-                        const float2 cs = ep[NQ - 1 - (vw.lo + q)];
-#pragma unroll
-                        for (int j = 0; j < R / 2; ++j) {
-                            const int r0 = ((j >> q) << (q + 1)) | (j & ((1 << q) - 1));
-                            ry_pair(cs, s[r0], s[r0 | (1 << q)]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) s[r] = cmul(s[r], __ldg(tv + r));
-                if (encl && p.enc == QIDDM_ENC_RZ) {
-                    const float2 *ev = et + v * R;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) s[r] = cmul(s[r], ev[r]);
-                }
-#pragma unroll
-                for (int q = 0; q < RB; ++q) {
-                    if (q < vw.q_lo || q >= vw.q_hi) continue;
-                    const float2 cs = __ldg(tl + NV * 2 * R + (NQ - 1 - (vw.lo + q)));
-#pragma unroll
-                    for (int j = 0; j < R / 2; ++j) {
-                        const int r0 = ((j >> q) << (q + 1)) | (j & ((1 << q) - 1));
-                        ry_pair(cs, s[r0], s[r0 | (1 << q)]);
-                    }
-                }
-                if (has_post) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) s[r] = cmul(s[r], __ldg(tv + R + r));
-                }
+                if (NVF == NV || v < NVF) view_fwd<NQ, RB, 0>(s, tl + v * 2 * R, cst, vw.lo, has_post, encl, et + v * R, ep);
+                else view_fwd<NQ, RB, (NVF == NV ? 0 : Q_TAIL)>(s, tl + v * 2 * R, cst, vw.lo, has_post, encl, et + v * R, ep);
                 if (v == NV - 1 && NQ > 1) {
                     if (p.imprimitive == QIDDM_IMP_CNOT) {
                         if (G > 1) group_sync<G, T>(slot);  // every tile is in registers before the scatter
@@ -443,6 +623,7 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                 }
                 group_sync<G, T>(slot);
             }
+        }
         }
 
         // ---------------------------------------------------------------- readout
@@ -518,17 +699,128 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
 #pragma unroll
             for (int j = 0; j < NQ; ++j) ga[j] = 0.f;
 
+            if constexpr (RES) {
+                // per-lane destination of a reduce-scattered gradient: lane 2i holds value i = kind * RB + q
+                auto push = [&](float (&gv)[16], int v, int jt, int ja) {   // jt: layer of the theta values, ja: boundary of the alphas (-1: none)
+                    warp_reduce_scatter16(gv, lane);
+                    if ((lane & 1) == 0) {
+                        const int i = lane >> 1, kind = i / RB, q = i - kind * RB;
+                        const int wire = NQ - 1 - (v * RB + q);
+                        if (kind == 0 && jt >= 0) atomicAdd(acc_s + (jt * NQ + wire) * 2 + 1, gv[0]);
+                        if (kind == 1 && ja >= 0) atomicAdd(acc_s + (ja * NQ + wire) * 2, gv[0]);
+                    }
+                };
+                auto alpha_sums = [&](float2 (&s)[R], float2 (&l)[R], float (&gv)[16], int v, bool enc_b) {
+                    float t[R], S[RB];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) t[r] = l[r].x * s[r].y - l[r].y * s[r].x;   // Im(conj(l) s)
+                    signed_sums<RB>(t, S);
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) gv[RB + q] = S[q];
+                    if (enc_b) {
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) {
+                            const int wire = NQ - 1 - (v * RB + q);
+#pragma unroll
+                            for (int jj = 0; jj < NQ; ++jj) ga[jj] += (jj == wire) ? S[q] : 0.f;
+                        }
+                    }
+                };
+                if (apply_last) {
+                    // the trailing diagonal's phases on the wires that are thread bits in residency n_layers
+                    const int v = (n_layers + 1) & 1;
+                    const float2 *pp = psi + (v == 0 ? slot_of<RB>(g << RB) : g), *lp = lam + (v == 0 ? slot_of<RB>(g << RB) : g);
+                    const int stride = v == 0 ? 1 : R + 1;
+                    float2 s[R], l[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        s[r] = pp[r * stride];
+                        l[r] = lp[r * stride];
+                    }
+                    float gv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) gv[i] = 0.f;
+                    alpha_sums(s, l, gv, v, false);
+                    push(gv, v, -1, n_layers);
+                }
+#pragma unroll 1
+                for (int j = n_layers; j >= 0; --j) {
+                    const int v = j & 1;
+                    float2 *pp = psi + (v == 0 ? slot_of<RB>(g << RB) : g), *lp = lam + (v == 0 ? slot_of<RB>(g << RB) : g);
+                    const int stride = v == 0 ? 1 : R + 1;
+                    const int w0 = NQ - 1 - v * RB;
+                    const float2 *tb = tab + (size_t)j * TAB_RES;
+                    float2 s[R], l[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        s[r] = pp[r * stride];
+                        l[r] = lp[r * stride];
+                    }
+                    float gv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) gv[i] = 0.f;
+                    if (j < n_layers) {
+                        const float2 *cst = tb + 2 * R;
+                        if (RB > 4) gv[(RB > 4 ? 4 : 0)] = ry_all_bwd<RB, (RB > 4 ? 4 : 0)>(__ldg(cst + w0 - 4), s, l);
+                        if (RB > 3) gv[(RB > 3 ? 3 : 0)] = ry_all_bwd<RB, (RB > 3 ? 3 : 0)>(__ldg(cst + w0 - 3), s, l);
+                        if (RB > 2) gv[(RB > 2 ? 2 : 0)] = ry_all_bwd<RB, (RB > 2 ? 2 : 0)>(__ldg(cst + w0 - 2), s, l);
+                        if (RB > 1) gv[(RB > 1 ? 1 : 0)] = ry_all_bwd<RB, (RB > 1 ? 1 : 0)>(__ldg(cst + w0 - 1), s, l);
+                        if (RB > 0) gv[0] = ry_all_bwd<RB, 0>(__ldg(cst + w0), s, l);
+                    }
+                    const bool has_diag = j < n_layers || apply_last;
+                    if (has_diag) {
+                        const bool enc_b = enc_mode == ENCL_RZ && j < n_layers && j % p.layers == 0;
+                        alpha_sums(s, l, gv, v, enc_b);
+                        float2 x = __ldg(tb + R + g);
+                        if (enc_b) {
+                            diag_mul2_conj<RB, false>(s, l, et + v * R);
+                            x = cmul(x, et[(1 - v) * R + g]);
+                        }
+                        unsigned int w = 0;
+                        if (j > 0 && NQ > 1) w = czw[(v * NRING + ((j - 1) % p.layers) % NRING) * G + g];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const unsigned int sg = (w << (31 - r)) & 0x80000000u;
+                            const float2 ys = cmul_conj(s[r], x), yl = cmul_conj(l[r], x);
+                            s[r] = make_float2(__uint_as_float(__float_as_uint(ys.x) ^ sg), __uint_as_float(__float_as_uint(ys.y) ^ sg));
+                            l[r] = make_float2(__uint_as_float(__float_as_uint(yl.x) ^ sg), __uint_as_float(__float_as_uint(yl.y) ^ sg));
+                        }
+                        diag_mul2_conj<RB, true>(s, l, tb);
+                    }
+                    push(gv, v, j < n_layers ? j : -1, has_diag ? j : -1);
+                    if (j > 0) {
+                        const float2 *cst = tb - TAB_RES + 2 * R;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) gv[i] = 0.f;
+                        if (RB > 4) gv[(RB > 4 ? 4 : 0)] = ry_all_bwd<RB, (RB > 4 ? 4 : 0)>(__ldg(cst + w0 - 4), s, l);
+                        if (RB > 3) gv[(RB > 3 ? 3 : 0)] = ry_all_bwd<RB, (RB > 3 ? 3 : 0)>(__ldg(cst + w0 - 3), s, l);
+                        if (RB > 2) gv[(RB > 2 ? 2 : 0)] = ry_all_bwd<RB, (RB > 2 ? 2 : 0)>(__ldg(cst + w0 - 2), s, l);
+                        if (RB > 1) gv[(RB > 1 ? 1 : 0)] = ry_all_bwd<RB, (RB > 1 ? 1 : 0)>(__ldg(cst + w0 - 1), s, l);
+                        if (RB > 0) gv[0] = ry_all_bwd<RB, 0>(__ldg(cst + w0), s, l);
+                        // the boundary j-1 phases of this view's wires were applied as a per-thread scalar in
+                        // residency j-1: Im(lambda^H Z_w psi) is unchanged by gates on other wires, so take it here
+                        alpha_sums(s, l, gv, v, enc_mode == ENCL_RZ && (j - 1) % p.layers == 0);
+                        push(gv, v, j - 1, j - 1);
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        pp[r * stride] = s[r];
+                        lp[r * stride] = l[r];
+                    }
+                    group_sync<G, T>(slot);
+                }
+            } else {
 #pragma unroll 1
             for (int li = n_layers - 1; li >= 0; --li) {
                 const int layer = li % p.layers;
                 const int ring = NQ > 1 ? (layer % NRING) + 1 : 0;
-                const bool encl = (p.enc != QIDDM_ENC_NONE) && layer == 0;
+                const int encl = layer == 0 ? enc_mode : ENCL_NONE;
                 const bool has_post = post_all || li == n_layers - 1;
                 const float2 *tl = tab + (size_t)li * TAB_LAYER;
+                const float2 *cst = tl + NV * 2 * R;
 #pragma unroll 1
                 for (int v = NV - 1; v >= 0; --v) {
                     const View<NQ, RB> vw(v, g);
-                    const float2 *tv = tl + v * 2 * R;
                     float2 *pp = psi + vw.base, *lp = lam + vw.base;
                     float2 s[R], l[R];
                     if (v == NV - 1 && NQ > 1) {
@@ -563,86 +855,8 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                         }
                     }
                     float gv[16];   // [q*3 + {phi, theta, omega}] partial angle gradients of this view
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) gv[i] = 0.f;
-                    if (has_post) {
-                        float t[R], S[RB];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) t[r] = l[r].x * s[r].y - l[r].y * s[r].x;   // Im(conj(l) s)
-                        signed_sums<RB>(t, S);
-#pragma unroll
-                        for (int q = 0; q < RB; ++q) gv[q * 3 + 2] = S[q];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const float2 ph = __ldg(tv + R + r);
-                            s[r] = cmul_conj(s[r], ph);
-                            l[r] = cmul_conj(l[r], ph);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        if (q < vw.q_lo || q >= vw.q_hi) continue;
-                        const float2 cs = __ldg(tl + NV * 2 * R + (NQ - 1 - (vw.lo + q)));
-                        float gt = 0.f;
-#pragma unroll
-                        for (int j = 0; j < R / 2; ++j) {
-                            const int r0 = ((j >> q) << (q + 1)) | (j & ((1 << q) - 1));
-                            const int r1 = r0 | (1 << q);
-                            gt += l[r1].x * s[r0].x + l[r1].y * s[r0].y - l[r0].x * s[r1].x - l[r0].y * s[r1].y;
-                            ry_pair_t(cs, s[r0], s[r1]);
-                            ry_pair_t(cs, l[r0], l[r1]);
-                        }
-                        gv[q * 3 + 1] = gt;
-                    }
-                    {
-                        float t[R], S[RB];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) t[r] = l[r].x * s[r].y - l[r].y * s[r].x;
-                        signed_sums<RB>(t, S);
-#pragma unroll
-                        for (int q = 0; q < RB; ++q) gv[q * 3] = S[q];
-                        if (encl && p.enc == QIDDM_ENC_RZ) {
-#pragma unroll
-                            for (int q = 0; q < RB; ++q) {
-                                if (q < vw.q_lo || q >= vw.q_hi) continue;
-                                const int wire = NQ - 1 - (vw.lo + q);
-#pragma unroll
-                                for (int j = 0; j < NQ; ++j) ga[j] += (j == wire) ? S[q] : 0.f;
-                            }
-                            const float2 *ev = et + v * R;
-#pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                const float2 ph = ev[r];
-                                s[r] = cmul_conj(s[r], ph);
-                                l[r] = cmul_conj(l[r], ph);
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const float2 ph = __ldg(tv + r);
-                            s[r] = cmul_conj(s[r], ph);
-                            l[r] = cmul_conj(l[r], ph);
-                        }
-                    }
-                    if (encl && p.enc == QIDDM_ENC_RY) {
-#pragma unroll
-                        for (int q = 0; q < RB; ++q) {
-                            if (q < vw.q_lo || q >= vw.q_hi) continue;
-                            const int wire = NQ - 1 - (vw.lo + q);
-                            const float2 cs = ep[wire];
-                            float gt = 0.f;
-#pragma unroll
-                            for (int j = 0; j < R / 2; ++j) {
-                                const int r0 = ((j >> q) << (q + 1)) | (j & ((1 << q) - 1));
-                                const int r1 = r0 | (1 << q);
-                                gt += l[r1].x * s[r0].x + l[r1].y * s[r0].y - l[r0].x * s[r1].x - l[r0].y * s[r1].y;
-                                ry_pair_t(cs, s[r0], s[r1]);
-                                ry_pair_t(cs, l[r0], l[r1]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < NQ; ++j) ga[j] += (j == wire) ? gt : 0.f;
-                        }
-                    }
+                    if (NVF == NV || v < NVF) view_bwd<NQ, RB, 0>(s, l, gv, ga, tl + v * 2 * R, cst, vw.lo, has_post, encl, et + v * R, ep);
+                    else view_bwd<NQ, RB, (NVF == NV ? 0 : Q_TAIL)>(s, l, gv, ga, tl + v * 2 * R, cst, vw.lo, has_post, encl, et + v * R, ep);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         pp[r * vw.stride] = s[r];
@@ -652,11 +866,12 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
                     warp_reduce_scatter16(gv, lane);
                     if ((lane & 1) == 0) {
                         const int i = lane >> 1, q = i / 3, kind = i - 3 * q;
-                        if (q < RB && q >= vw.q_lo && q < vw.q_hi && (kind != 2 || has_post))
+                        if (q < RB && q >= vw.q_lo && (kind != 2 || has_post))
                             atomicAdd(acc_s + (li * NQ + (NQ - 1 - (vw.lo + q))) * 3 + kind, gv[0]);
                     }
                     group_sync<G, T>(slot);
                 }
+            }
             }
 
             // ------------------------------------------------------------ input gradients
@@ -699,34 +914,40 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T) gate_kernel(const GateParams p
 
     if (BWD) {
         __syncthreads();
-        float *dst = p.partials + (long long)blockIdx.x * (p.n_rot * 3);
-        for (int i = tid; i < p.n_rot * 3; i += T) dst[i] = acc_s[i];
+        float *dst = p.partials + (long long)blockIdx.x * n_grad;
+        for (int i = tid; i < n_grad; i += T) dst[i] = acc_s[i];
     }
 }
 
+// the resident schedule needs two views of equal width and an all-diagonal layer boundary
 template <int NQ, int RB>
-size_t smem_bytes(const GateParams &p, bool bwd) {
+constexpr bool can_resident() { return NQ == 2 * RB; }
+inline bool wants_resident(int nq, int rb, const GateParams &p) { return nq == 2 * rb && p.merge_post != 0; }
+
+template <int NQ, int RB>
+size_t smem_bytes(const GateParams &p, bool bwd, bool res) {
     using C = Cfg<NQ, RB>;
     constexpr int NRING = NQ > 1 ? NQ - 1 : 1;
     size_t floats = 0;
-    if (bwd) floats += ((size_t)p.n_rot * 3 + 1) & ~(size_t)1;
+    const size_t n_grad = res ? ((size_t)p.n_rot + NQ) * 2 : (size_t)p.n_rot * 3;
+    if (bwd) floats += (n_grad + 3) & ~(size_t)3;
     floats += 2 * (size_t)C::CPB * C::STRIDE;                        // psi
     if (bwd) floats += 2 * (size_t)C::CPB * C::STRIDE;               // lambda
     floats += 2 * (size_t)C::CPB * NQ;                               // (cos, sin) of the re-upload angles
     if (p.enc == QIDDM_ENC_RZ) floats += 2 * (size_t)C::CPB * C::NV * C::R;
     floats += C::T / 32;                                             // red
-    if (p.imprimitive == QIDDM_IMP_CZ) floats += (size_t)NRING * C::G;
+    if (p.imprimitive == QIDDM_IMP_CZ) floats += (size_t)(res ? 2 : 1) * NRING * C::G;
     if (p.unfold) floats += 2 * (size_t)p.n_features;
     size_t bytes = floats * 4 + (p.imprimitive == QIDDM_IMP_CNOT ? (size_t)NRING * C::R * 2 : 0);
     return (bytes + 15) & ~(size_t)15;
 }
 
-template <int NQ, int RB, bool BWD>
-cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
+template <int NQ, int RB, bool BWD, bool RES>
+cudaError_t info_k(const GateParams &p, LaunchInfo *li) {
     using C = Cfg<NQ, RB>;
-    auto kern = gate_kernel<NQ, RB, BWD>;
+    auto kern = gate_kernel<NQ, RB, BWD, RES>;
     li->block = C::T;
-    li->smem = smem_bytes<NQ, RB>(p, BWD);
+    li->smem = smem_bytes<NQ, RB>(p, BWD, RES);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li->smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
@@ -739,13 +960,27 @@ cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
     li->grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
     return cudaSuccess;
 }
+template <int NQ, int RB, bool BWD>
+cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
+    if constexpr (can_resident<NQ, RB>()) {
+        if (wants_resident(NQ, RB, p)) return info_k<NQ, RB, BWD, true>(p, li);
+    }
+    return info_k<NQ, RB, BWD, false>(p, li);
+}
 
 template <int NQ, int RB, bool BWD>
 cudaError_t launch_t(const GateParams &p, const LaunchInfo &li, cudaStream_t s) {
     // algorithmic flops: 14 * 2^n per Rot; the adjoint sweep costs 4x a forward
     const double work = (double)p.B * p.n_rot * 14.0 * (double)(1 << NQ) * (BWD ? 4.0 : 1.0);
     timing_begin(BWD ? TK_GATE_BWD : TK_GATE_FWD, work, s);
-    gate_kernel<NQ, RB, BWD><<<li.grid, li.block, li.smem, s>>>(p);
+    bool done = false;
+    if constexpr (can_resident<NQ, RB>()) {
+        if (wants_resident(NQ, RB, p)) {
+            gate_kernel<NQ, RB, BWD, true><<<li.grid, li.block, li.smem, s>>>(p);
+            done = true;
+        }
+    }
+    if (!done) gate_kernel<NQ, RB, BWD, false><<<li.grid, li.block, li.smem, s>>>(p);
     timing_end(s);
     count_launch();
     return cudaGetLastError();
@@ -802,7 +1037,7 @@ __device__ __forceinline__ double remap_grad(double w, int remap) {
 __global__ void prepare_tables_kernel(const void *weights, int wdtype, int remap, int nq, int rb, int n_layers,
                                       int merge_post, float2 *tab) {
     const int R = 1 << rb, NV = (nq + rb - 1) / rb, lo_last = nq - rb;
-    const int tab_layer = NV * 2 * R + nq;
+    const int tab_layer = NV * 2 * R + ((nq + 1) & ~1);
     const long long total = (long long)n_layers * tab_layer;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int li = (int)(i / tab_layer);
@@ -810,8 +1045,8 @@ __global__ void prepare_tables_kernel(const void *weights, int wdtype, int remap
         float2 o;
         if (e >= NV * 2 * R) {
             const int wire = e - NV * 2 * R;
-            double s, c;
-            sincos(0.5 * remap_fn(load_w(weights, wdtype, (li * nq + wire) * 3 + 1), remap), &s, &c);
+            double s = 0.0, c = 1.0;
+            if (wire < nq) sincos(0.5 * remap_fn(load_w(weights, wdtype, (li * nq + wire) * 3 + 1), remap), &s, &c);
             o = make_float2((float)c, (float)s);
         } else {
             const int v = e / (2 * R), post = (e / R) & 1, r = e % R;
@@ -838,6 +1073,43 @@ __global__ void prepare_tables_kernel(const void *weights, int wdtype, int remap
     }
 }
 
+// Resident schedule (nq = 2 rb): boundary j = 0..n_layers carries alpha_{j,w} = phi^j_w + omega^{j-1}_w.  Residency j
+// works in view v = j & 1 (local bits [v rb, v rb + rb)):  local[r] = phases of the view's own wires, scalar[g] =
+// phases of the other half's wires (g = the thread's index), then (cos,sin)(theta^j_w / 2) per wire.
+__global__ void prepare_tables_res_kernel(const void *weights, int wdtype, int remap, int nq, int rb, int n_layers,
+                                          float2 *tab) {
+    const int R = 1 << rb;
+    const int tab_b = 2 * R + ((nq + 1) & ~1);
+    const long long total = (long long)(n_layers + 1) * tab_b;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i / tab_b);
+        const int e = (int)(i - (long long)j * tab_b);
+        float2 o;
+        if (e >= 2 * R) {
+            const int wire = e - 2 * R;
+            double s = 0.0, c = 1.0;
+            if (wire < nq && j < n_layers)
+                sincos(0.5 * remap_fn(load_w(weights, wdtype, (j * nq + wire) * 3 + 1), remap), &s, &c);
+            o = make_float2((float)c, (float)s);
+        } else {
+            const int v = j & 1;
+            const int half = (e < R) ? v : 1 - v;     // which half of the wires this entry covers
+            const int idx = e % R;
+            double ang = 0.0;
+            for (int q = 0; q < rb; ++q) {
+                const int wire = nq - 1 - (half * rb + q);
+                const double sgn = ((idx >> q) & 1) ? 0.5 : -0.5;
+                if (j < n_layers) ang += sgn * remap_fn(load_w(weights, wdtype, (j * nq + wire) * 3 + 0), remap);
+                if (j > 0) ang += sgn * remap_fn(load_w(weights, wdtype, ((j - 1) * nq + wire) * 3 + 2), remap);
+            }
+            double s, c;
+            sincos(ang, &s, &c);
+            o = make_float2((float)c, (float)s);
+        }
+        tab[i] = o;
+    }
+}
+
 // partials[b][(li*nq + wire)*3 + {0: d/dphi (+ d/domega of layer li-1 when merged), 1: d/dtheta, 2: d/domega}]
 __global__ void finalize_grads_kernel(const float *partials, int n_partials, const void *weights, int wdtype,
                                       int remap, int nq, int n_layers, int merge_post, void *grad_weights) {
@@ -854,20 +1126,42 @@ __global__ void finalize_grads_kernel(const float *partials, int n_partials, con
     else reinterpret_cast<float *>(grad_weights)[i] = (float)gval;
 }
 
+// resident schedule: partials[b][(j*nq + wire)*2 + {0: d/dalpha_j, 1: d/dtheta_j}], j = 0..n_layers
+__global__ void finalize_grads_res_kernel(const float *partials, int n_partials, const void *weights, int wdtype,
+                                          int remap, int nq, int n_layers, void *grad_weights) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (li*nq + wire)*3 + kind
+    const int n = n_layers * nq * 3;
+    if (i >= n) return;
+    const int kind = i % 3, gate = i / 3;
+    const int src = kind == 0 ? gate * 2 : (kind == 1 ? gate * 2 + 1 : (gate + nq) * 2);
+    const size_t stride = (size_t)(n_layers + 1) * nq * 2;
+    double acc = 0.0;
+    for (int b = 0; b < n_partials; ++b) acc += (double)partials[(size_t)b * stride + src];
+    const double gval = acc * remap_grad(load_w(weights, wdtype, i), remap);
+    if (wdtype == QIDDM_DTYPE_F64) reinterpret_cast<double *>(grad_weights)[i] = gval;
+    else reinterpret_cast<float *>(grad_weights)[i] = (float)gval;
+}
+
 }  // namespace
 
 int gate_rb(int n_qubits, bool backward) { return rb_choose(n_qubits, backward); }
 
 size_t gate_table_bytes(int n_qubits, int n_layers) {
-    // upper bound over the register-tile widths: NV * 2 * R + n float2 per layer (NV <= 4, R <= 32)
+    // upper bound over the register-tile widths and schedules: NV * 2 * R + n float2 per layer (NV <= 4, R <= 32),
+    // one extra boundary for the resident schedule
     size_t per_layer = 0;
     for (int rb = 1; rb <= 5; ++rb) {
         if (!rb_valid(n_qubits, rb)) continue;
         const size_t nv = (n_qubits + rb - 1) / rb;
-        const size_t t = nv * 2 * ((size_t)1 << rb) + n_qubits;
+        const size_t t = nv * 2 * ((size_t)1 << rb) + ((n_qubits + 1) & ~1);
         if (t > per_layer) per_layer = t;
     }
-    return (size_t)n_layers * per_layer * sizeof(float2);
+    return (size_t)(n_layers + 1) * per_layer * sizeof(float2);
+}
+
+size_t gate_partial_floats(int n_qubits, int n_layers) {
+    const size_t a = (size_t)n_layers * n_qubits * 3, b = (size_t)(n_layers + 1) * n_qubits * 2;
+    return a > b ? a : b;
 }
 
 cudaError_t gate_launch_info(int n_qubits, bool backward, const GateParams &p, LaunchInfo *info) {
@@ -884,21 +1178,34 @@ cudaError_t launch_gate_backward(int n_qubits, const GateParams &p, const Launch
     QIDDM_DISPATCH_NQ(n_qubits, (launch_t<NQ, RB, true>(p, li, s)))
 }
 cudaError_t launch_prepare_tables(const void *weights, int wdtype, int remap, int n_qubits, bool backward,
-                                  int n_layers, int merge_post, float *tables, cudaStream_t s) {
+                                  const GateParams &p, float *tables, cudaStream_t s) {
     const int rb = rb_choose(n_qubits, backward);
+    const int n_layers = p.n_blocks * p.layers;
     const int R = 1 << rb, NV = (n_qubits + rb - 1) / rb;
-    const long long total = (long long)n_layers * (NV * 2 * R + n_qubits);
+    const bool res = wants_resident(n_qubits, rb, p);
+    const long long total = res ? (long long)(n_layers + 1) * (2 * R + ((n_qubits + 1) & ~1))
+                                : (long long)n_layers * (NV * 2 * R + ((n_qubits + 1) & ~1));
     const int blocks = (int)((total + 255) / 256);
-    prepare_tables_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, s>>>(
-        weights, wdtype, remap, n_qubits, rb, n_layers, merge_post, reinterpret_cast<float2 *>(tables));
+    const int grid = blocks < 1184 ? blocks : 1184;
+    if (res)
+        prepare_tables_res_kernel<<<grid, 256, 0, s>>>(weights, wdtype, remap, n_qubits, rb, n_layers,
+                                                       reinterpret_cast<float2 *>(tables));
+    else
+        prepare_tables_kernel<<<grid, 256, 0, s>>>(weights, wdtype, remap, n_qubits, rb, n_layers, p.merge_post,
+                                                   reinterpret_cast<float2 *>(tables));
     count_launch();
     return cudaGetLastError();
 }
 cudaError_t launch_finalize_grads(const float *partials, int n_partials, const void *weights, int wdtype, int remap,
-                                  int n_qubits, int n_layers, int merge_post, void *grad_weights, cudaStream_t s) {
+                                  int n_qubits, const GateParams &p, void *grad_weights, cudaStream_t s) {
+    const int n_layers = p.n_blocks * p.layers;
     const int n = n_layers * n_qubits * 3;
-    finalize_grads_kernel<<<(n + 127) / 128, 128, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
-                                                         n_layers, merge_post, grad_weights);
+    if (wants_resident(n_qubits, rb_choose(n_qubits, true), p))
+        finalize_grads_res_kernel<<<(n + 127) / 128, 128, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
+                                                                 n_layers, grad_weights);
+    else
+        finalize_grads_kernel<<<(n + 127) / 128, 128, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
+                                                             n_layers, p.merge_post, grad_weights);
     count_launch();
     return cudaGetLastError();
 }

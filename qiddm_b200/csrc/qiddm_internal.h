@@ -37,10 +37,11 @@ cudaError_t gate_launch_info(int n_qubits, bool backward, const GateParams &p, L
 cudaError_t launch_gate_forward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s);
 cudaError_t launch_gate_backward(int n_qubits, const GateParams &p, const LaunchInfo &li, cudaStream_t s);
 size_t gate_table_bytes(int n_qubits, int n_layers);
+size_t gate_partial_floats(int n_qubits, int n_layers);      // per-CTA angle-gradient sums (upper bound over schedules)
 cudaError_t launch_prepare_tables(const void *weights, int wdtype, int remap, int n_qubits, bool backward,
-                                  int n_layers, int merge_post, float *tables, cudaStream_t s);
+                                  const GateParams &p, float *tables, cudaStream_t s);
 cudaError_t launch_finalize_grads(const float *partials, int n_partials, const void *weights, int wdtype, int remap,
-                                  int n_qubits, int n_layers, int merge_post, void *grad_weights, cudaStream_t s);
+                                  int n_qubits, const GateParams &p, void *grad_weights, cudaStream_t s);
 void count_launch(int n = 1);
 
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream around
