@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include <cstring>
 #include "qiddm_internal.h"
 
@@ -117,6 +118,44 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
     return d;
 }
 
+// ---- CTA-pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory that signals an mbarrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -157,6 +196,101 @@ __device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
     int e;
     frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
     return ldexpf(1.f, 14 - e);
+}
+
+// Epilogue of one accumulator tile for one warp: TMEM lanes [q*32, q*32+32) -> registers -> global.
+__device__ __forceinline__ void epilogue_tile(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane) {
+    {
+            const int row = row0 + q * 32 + lane;
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+            const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
+            float dx_a = 0.f, dx_b = 0.f;
+            if (p.epi == EPI_DX && row < p.M) {
+                dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
+                dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+            }
+            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                float v[16];
+                tc_ld16(taddr + c0, v);
+                const int col = n0 + c0;
+                if (row >= p.M || col >= p.N) continue;
+                if (p.epi == EPI_PROBS) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float re = v[2 * j], im = v[2 * j + 1];
+                        if (p.bias != nullptr && col + 2 * j + 1 < p.N) {
+                            re += __ldg(p.bias + col + 2 * j);
+                            im += __ldg(p.bias + col + 2 * j + 1);
+                        }
+                        v[2 * j] = re;
+                        v[2 * j + 1] = im;
+                        float pr = (re * re + im * im) * rs;
+                        if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
+                        o[j] = pr;
+                    }
+                    if (p.y_out != nullptr) {
+                        float *yd = p.y_out + (long long)row * p.N + col;
+                        if (col + 16 <= p.N && ((p.N & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<float4 *>(yd)[j] =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (col + j < p.N) yd[j] = v[j];
+                        }
+                    }
+                    if (p.out == nullptr) continue;
+                    const int m0 = col >> 1;
+                    float *dst = p.out + (long long)row * p.ldo + m0;
+                    if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
+                        reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (m0 + j < p.n_out) dst[j] = o[j];
+                    }
+                } else if (p.epi == EPI_DX) {
+                    float *dst = p.out + (long long)row * p.ldo + col;
+                    const float *xs = p.dx_x + (long long)row * p.ldo + col;
+                    if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xs) + j);
+                            reinterpret_cast<float4 *>(dst)[j] =
+                                make_float4(v[4 * j] * dx_a + dx_b * (xv.x + p.add_offset),
+                                            v[4 * j + 1] * dx_a + dx_b * (xv.y + p.add_offset),
+                                            v[4 * j + 2] * dx_a + dx_b * (xv.z + p.add_offset),
+                                            v[4 * j + 3] * dx_a + dx_b * (xv.w + p.add_offset));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col + j < p.N) dst[j] = v[j] * dx_a + dx_b * (__ldg(xs + j) + p.add_offset);
+                    }
+                } else {
+                    float *dst = p.out + (long long)row * p.ldo + col;
+                    if (p.k_splits > 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
+                    } else if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<float4 *>(dst)[j] =
+                                make_float4(v[4 * j] * p.out_scale, v[4 * j + 1] * p.out_scale,
+                                            v[4 * j + 2] * p.out_scale, v[4 * j + 3] * p.out_scale);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (col + j < p.N) dst[j] = v[j] * p.out_scale;
+                    }
+                }
+            }
+    }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -276,96 +410,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int row = tm * BM + q * 32 + lane;
-            const int n0 = tn * p.bn;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS;
-            const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
-            float dx_a = 0.f, dx_b = 0.f;
-            if (p.epi == EPI_DX && row < p.M) {
-                dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
-                dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
-            }
-            for (int c0 = 0; c0 < p.bn; c0 += 16) {
-                float v[16];
-                tc_ld16(taddr + c0, v);
-                const int col = n0 + c0;
-                if (row >= p.M || col >= p.N) continue;
-                if (p.epi == EPI_PROBS) {
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float re = v[2 * j], im = v[2 * j + 1];
-                        if (p.bias != nullptr && col + 2 * j + 1 < p.N) {
-                            re += __ldg(p.bias + col + 2 * j);
-                            im += __ldg(p.bias + col + 2 * j + 1);
-                        }
-                        v[2 * j] = re;
-                        v[2 * j + 1] = im;
-                        float pr = (re * re + im * im) * rs;
-                        if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
-                        o[j] = pr;
-                    }
-                    if (p.y_out != nullptr) {
-                        float *yd = p.y_out + (long long)row * p.N + col;
-                        if (col + 16 <= p.N && ((p.N & 3) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                reinterpret_cast<float4 *>(yd)[j] =
-                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (col + j < p.N) yd[j] = v[j];
-                        }
-                    }
-                    if (p.out == nullptr) continue;
-                    const int m0 = col >> 1;
-                    float *dst = p.out + (long long)row * p.ldo + m0;
-                    if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
-                        reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (m0 + j < p.n_out) dst[j] = o[j];
-                    }
-                } else if (p.epi == EPI_DX) {
-                    float *dst = p.out + (long long)row * p.ldo + col;
-                    const float *xs = p.dx_x + (long long)row * p.ldo + col;
-                    if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xs) + j);
-                            reinterpret_cast<float4 *>(dst)[j] =
-                                make_float4(v[4 * j] * dx_a + dx_b * (xv.x + p.add_offset),
-                                            v[4 * j + 1] * dx_a + dx_b * (xv.y + p.add_offset),
-                                            v[4 * j + 2] * dx_a + dx_b * (xv.z + p.add_offset),
-                                            v[4 * j + 3] * dx_a + dx_b * (xv.w + p.add_offset));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) dst[j] = v[j] * dx_a + dx_b * (__ldg(xs + j) + p.add_offset);
-                    }
-                } else {
-                    float *dst = p.out + (long long)row * p.ldo + col;
-                    if (p.k_splits > 1) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
-                    } else if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<float4 *>(dst)[j] =
-                                make_float4(v[4 * j] * p.out_scale, v[4 * j + 1] * p.out_scale,
-                                            v[4 * j + 2] * p.out_scale, v[4 * j + 3] * p.out_scale);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) dst[j] = v[j] * p.out_scale;
-                    }
-                }
-            }
+            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * BM, tn * p.bn, q, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -378,6 +423,214 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05.mma.cta_group::2, UMMA M = 256): the two CTAs of a cluster own the two
+// 128-row halves of a 256 x bn tile.  Each loads its own A rows and HALF of the B tile; the tensor cores
+// of the pair read both halves, so B crosses L2 -> SM once per pair.  In x3 mode one pipeline stage holds
+// A hi, A lo and the three B splits of a k-block (A hi is used by two of the three products), i.e.
+// 2 x 16 KB + 3 x bn/2 x 128 B per CTA for three 128 x bn x 64 products: 25 KB per product instead of
+// 44 KB, which is what the L2 -> SM throughput (~42 B/cycle/SM) sustains at the tensor peak.
+// Barriers: full[s] lives in the leader (rank 0) and collects both CTAs' TMA bytes; empty[s] and tfull[a]
+// are signalled in both CTAs by multicast commits; tempty[a] lives in the leader and counts the epilogue
+// warps of both CTAs.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int NSEG, bool AMN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr uint32_t N_A = NSEG > 1 ? 2 : 1;
+    constexpr uint32_t a_bytes = BM * BK * 2;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)(p.bn / 2) * BK * 2;          // this CTA's half of the B tile
+    const uint32_t stage_bytes = N_A * a_bytes + (uint32_t)NSEG * b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);      // the leader's arrive(expect_tx) for the bytes of both CTAs
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 8);    // 4 epilogue warps in each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);       // 256-row tiles
+    const int tiles_n = (p.N + p.bn - 1) / p.bn;
+    const int KB = (p.K + BK - 1) / BK;
+    const long long total = (long long)tiles_m * tiles_n * p.k_splits;
+    const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; one elected lane issues) =====================
+        const bool issuer = elect_one();
+        const uint32_t fb0 = mapa_rank(full_bar(0), 0);      // the leader's full barriers (shared::cluster address)
+        int stage = 0;
+        uint32_t phase = 0;
+        constexpr int PFD = 6;                               // L2 prefetch distance of the A operand, in k-blocks
+        for (long long w = pair; w < total; w += n_pairs) {
+            const int split = (int)(w % p.k_splits);
+            const long long tile = w / p.k_splits;
+            const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
+            const int m0 = tm * 2 * BM + (int)rank * BM;
+            const int nb0 = tn * p.bn + (int)rank * (p.bn / 2);
+            const int kb0 = (int)((long long)split * KB / p.k_splits);
+            const int kb1 = (int)((long long)(split + 1) * KB / p.k_splits);
+            // where this pair's next work item starts (for prefetching across the tile boundary)
+            const long long wn = w + n_pairs;
+            int nm0 = -1, nkb0 = 0;
+            if (wn < total) {
+                const int nsplit = (int)(wn % p.k_splits);
+                nm0 = (int)((wn / p.k_splits) / tiles_n) * 2 * BM + (int)rank * BM;
+                nkb0 = (int)((long long)nsplit * KB / p.k_splits);
+            }
+            if (w == pair && issuer) {
+                for (int i = 0; i < PFD && kb0 + i < kb1; ++i)
+                    for (uint32_t a = 0; a < N_A; ++a) {
+                        if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], m0, (kb0 + i) * BK); tma_prefetch_l2_2d(&p.a_map[a], m0 + 64, (kb0 + i) * BK); }
+                        else tma_prefetch_l2_2d(&p.a_map[a], (kb0 + i) * BK, m0);
+                    }
+            }
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                if (issuer) {
+                    const uint32_t fb = fb0 + 8u * stage;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * stage_bytes);
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+                    for (uint32_t i = 0; i < N_A; ++i) {
+                        const uint32_t dst = sa + i * a_bytes;
+                        if (AMN) {   // two (64 M) x (64 K) boxes from the row-major (K, M) array
+                            tma_load_2d_pair(dst, &p.a_map[i], fb, m0, kb * BK);
+                            tma_load_2d_pair(dst + a_bytes / 2, &p.a_map[i], fb, m0 + 64, kb * BK);
+                        } else {
+                            tma_load_2d_pair(dst, &p.a_map[i], fb, kb * BK, m0);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NSEG; ++i)
+                        tma_load_2d_pair(sa + N_A * a_bytes + i * b_bytes, &p.b_map[i], fb, kb * BK, nb0);
+                    // pull the A tile PFD k-blocks ahead (possibly in this pair's next tile) into L2
+                    int pk = kb + PFD, pm = m0;
+                    if (pk >= kb1) { pk = nkb0 + (pk - kb1); pm = nm0; }
+                    if (pm >= 0 && pk < KB) {
+#pragma unroll
+                        for (uint32_t a = 0; a < N_A; ++a) {
+                            if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], pm, pk * BK); tma_prefetch_l2_2d(&p.a_map[a], pm + 64, pk * BK); }
+                            else tma_prefetch_l2_2d(&p.a_map[a], pk * BK, pm);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only; the whole warp runs the loop so descriptors stay
+        // warp-uniform, one elected lane issues) =====================
+        if (leader) {
+            const bool issuer = elect_one();
+            // instruction descriptor: D=f32, A=B=f16, N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24) |
+                                   (AMN ? (1u << 15) : 0u);
+            constexpr uint64_t a_step = AMN ? 128 : 2;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long long w = pair; w < total; w += n_pairs) {
+                const int split = (int)(w % p.k_splits);
+                const int kb0 = (int)((long long)split * KB / p.k_splits);
+                const int kb1 = (int)((long long)(split + 1) * KB / p.k_splits);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint64_t ad0 = AMN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+                    const uint64_t ad1 = AMN ? make_smem_desc_mn(sa + a_bytes) : make_smem_desc(sa + a_bytes);
+                    const uint64_t bd0 = make_smem_desc(sa + N_A * a_bytes);
+                    const uint64_t bstep = (uint64_t)(b_bytes >> 4);
+                    if (issuer) {
+#pragma unroll
+                        for (int seg = 0; seg < NSEG; ++seg) {
+                            const uint64_t adesc = seg == 1 ? ad1 : ad0;
+                            const uint64_t bdesc = bd0 + bstep * seg;
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc,
+                                                (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u);
+                        }
+                        tc_commit_pair(empty_bar(stage));
+                        if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int q = warp & 3;
+        const uint32_t te0 = mapa_rank(tempty_bar(0), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long w = pair; w < total; w += n_pairs) {
+            const long long tile = w / p.k_splits;
+            const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(te0 + 8u * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();       // the peer's shared memory and barriers stay valid until both CTAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -608,6 +861,15 @@ int pick_bn(int N) {
 struct ActOperand { const __half *h, *l; };          // hi, lo * 2^11
 struct WgtOperand { const __half *h, *s, *l; };      // hi, hi * 2^-11, lo
 
+bool use_pair_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("QIDDM_GEMM_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // D[M,N] = A B^T over the precision segments.  a_mn: A is given as the row-major (K, M) array (MN-major operand).
 int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long a_pitch, bool a_mn,
              const WgtOperand &Bm, long long b_rows, long long b_pitch, int M, int N, int K, int n_seg, int k_splits,
@@ -617,35 +879,71 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
     p.a_mn = a_mn ? 1 : 0;
     p.bn = pick_bn(N);
     p.k_splits = k_splits;
+    const bool pair = use_pair_kernel();
     const __half *as[2] = {A.h, A.l};
     const __half *bs[3] = {Bm.h, Bm.s, Bm.l};
     int rc;
     for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
         if ((rc = make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, a_mn ? 64 : BM)) != QIDDM_OK) return rc;
     for (int i = 0; i < n_seg; ++i)
-        if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, p.bn)) != QIDDM_OK) return rc;
-    const int stage_bytes = BM * BK * 2 + p.bn * BK * 2;
-    int stages = (200 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+        if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, pair ? p.bn / 2 : p.bn)) != QIDDM_OK) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.bn - 1) / p.bn) * k_splits;
-    const int grid = (int)(tiles < sms ? tiles : sms);
     timing_begin(TK_GEMM, 2.0 * (double)M * (double)N * (double)K, s);   // single-pass (algorithmic) flops
-    gemm_kernel<<<grid, GEMM_THREADS, smem, s>>>(p);
+    cudaError_t e;
+    if (pair) {
+        const int stage_bytes = (n_seg > 1 ? 2 : 1) * BM * BK * 2 + n_seg * (p.bn / 2) * BK * 2;
+        int stages = (226 * 1024 - 1024 - 256) / stage_bytes;
+        if (stages > 8) stages = 8;
+        if (stages < 2) stages = 2;
+        p.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+        void (*kern)(const GemmParams) = n_seg > 1 ? (a_mn ? gemm_pair_kernel<3, true> : gemm_pair_kernel<3, false>)
+                                                   : (a_mn ? gemm_pair_kernel<1, true> : gemm_pair_kernel<1, false>);
+        static bool attr_set2[4] = {false, false, false, false};
+        const int ki = (n_seg > 1 ? 2 : 0) + (a_mn ? 1 : 0);
+        if (!attr_set2[ki]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_set2[ki] = true;
+        }
+        const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + p.bn - 1) / p.bn) * k_splits;
+        const int pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, p);
+    } else {
+        const int stage_bytes = BM * BK * 2 + p.bn * BK * 2;
+        int stages = (200 * 1024) / stage_bytes;
+        if (stages > 8) stages = 8;
+        if (stages < 2) stages = 2;
+        p.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.bn - 1) / p.bn) * k_splits;
+        const int grid = (int)(tiles < sms ? tiles : sms);
+        gemm_kernel<<<grid, GEMM_THREADS, smem, s>>>(p);
+        e = cudaGetLastError();
+    }
     timing_end(s);
     count_launch();
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
 }
 
@@ -851,9 +1149,11 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         p.epi = EPI_STORE; p.out = dWT; p.ldo = g.Fx; p.out_scale = 1.f;
         WgtOperand XTo{w.XT[0], w.XT[1], w.XT[2]};
         const int bn = pick_bn(g.Fx);
-        const int tiles = ((g.N + BM - 1) / BM) * ((g.Fx + bn - 1) / bn);
-        long long kt = (long long)n_seg * ((Bp + BK - 1) / BK);
-        int splits = (int)((2 * 148 + tiles - 1) / tiles);
+        const bool pair = use_pair_kernel();
+        const int bm = pair ? 2 * BM : BM;
+        const int tiles = ((g.N + bm - 1) / bm) * ((g.Fx + bn - 1) / bn);
+        long long kt = pair ? (Bp + BK - 1) / BK : (long long)n_seg * ((Bp + BK - 1) / BK);
+        int splits = (int)(((pair ? 148 : 2 * 148) + tiles - 1) / tiles);
         if (splits > kt) splits = (int)kt;
         if (splits < 1) splits = 1;
         timing_set_gemm_kind(TK_GEMM_DW);
