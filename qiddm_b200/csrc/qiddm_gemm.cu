@@ -35,6 +35,7 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
+constexpr int PAIR_THREADS = 384;   // CTA-pair kernel: 4 role warps + 8 epilogue warps
 constexpr int ACC_COLS = 256;    // TMEM columns per accumulator stage (2 stages = 512 columns)
 constexpr float LO_SCALE = 2048.f;          // 2^11
 constexpr float LO_INV = 1.f / 2048.f;
@@ -83,16 +84,20 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// 16 consecutive fp32 columns of this thread's TMEM lane; the registers are valid after tc_ld_wait()
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// waits for every outstanding tcgen05.ld of this thread; the operands tie the consumers of `r` to the wait
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups of 1024 B).
@@ -187,6 +192,7 @@ struct GemmParams {
     const float *dx_x, *dx_S;
     const unsigned int *gmax_bits;
     float add_offset;
+    int dbg_pfd, dbg_nostore;   // tuning knobs (QIDDM_GEMM_PFD, QIDDM_GEMM_NOSTORE)
 };
 
 // power-of-two scale that maps the bound on max |G| into [2^13, 2^14)
@@ -198,98 +204,109 @@ __device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
     return ldexpf(1.f, 14 - e);
 }
 
-// Epilogue of one accumulator tile for one warp: TMEM lanes [q*32, q*32+32) -> registers -> global.
-__device__ __forceinline__ void epilogue_tile(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane) {
-    {
-            const int row = row0 + q * 32 + lane;
-            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-            const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
-            float dx_a = 0.f, dx_b = 0.f;
-            if (p.epi == EPI_DX && row < p.M) {
-                dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
-                dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+// Epilogue of one accumulator tile for one warp: TMEM lanes [q*32, q*32+32), columns [cbeg, cend) -> registers ->
+// global.  The TMEM load of chunk i+1 is in flight while chunk i is processed.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32_t (&r)[16], int row, int col, float rs,
+                                               float dx_a, float dx_b) {
+    if (row >= p.M || col >= p.N || p.dbg_nostore) return;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    if (p.epi == EPI_PROBS) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float re = v[2 * j], im = v[2 * j + 1];
+            if (p.bias != nullptr && col + 2 * j + 1 < p.N) {
+                re += __ldg(p.bias + col + 2 * j);
+                im += __ldg(p.bias + col + 2 * j + 1);
             }
-            for (int c0 = 0; c0 < p.bn; c0 += 16) {
-                float v[16];
-                tc_ld16(taddr + c0, v);
-                const int col = n0 + c0;
-                if (row >= p.M || col >= p.N) continue;
-                if (p.epi == EPI_PROBS) {
-                    float o[8];
+            v[2 * j] = re;
+            v[2 * j + 1] = im;
+            float pr = (re * re + im * im) * rs;
+            if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
+            o[j] = pr;
+        }
+        if (p.y_out != nullptr) {
+            float *yd = p.y_out + (long long)row * p.N + col;
+            if (col + 16 <= p.N && ((p.N & 3) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float re = v[2 * j], im = v[2 * j + 1];
-                        if (p.bias != nullptr && col + 2 * j + 1 < p.N) {
-                            re += __ldg(p.bias + col + 2 * j);
-                            im += __ldg(p.bias + col + 2 * j + 1);
-                        }
-                        v[2 * j] = re;
-                        v[2 * j + 1] = im;
-                        float pr = (re * re + im * im) * rs;
-                        if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
-                        o[j] = pr;
-                    }
-                    if (p.y_out != nullptr) {
-                        float *yd = p.y_out + (long long)row * p.N + col;
-                        if (col + 16 <= p.N && ((p.N & 3) == 0)) {
+                for (int j = 0; j < 4; ++j)
+                    reinterpret_cast<float4 *>(yd)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                reinterpret_cast<float4 *>(yd)[j] =
-                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (col + j < p.N) yd[j] = v[j];
-                        }
-                    }
-                    if (p.out == nullptr) continue;
-                    const int m0 = col >> 1;
-                    float *dst = p.out + (long long)row * p.ldo + m0;
-                    if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
-                        reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (m0 + j < p.n_out) dst[j] = o[j];
-                    }
-                } else if (p.epi == EPI_DX) {
-                    float *dst = p.out + (long long)row * p.ldo + col;
-                    const float *xs = p.dx_x + (long long)row * p.ldo + col;
-                    if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xs) + j);
-                            reinterpret_cast<float4 *>(dst)[j] =
-                                make_float4(v[4 * j] * dx_a + dx_b * (xv.x + p.add_offset),
-                                            v[4 * j + 1] * dx_a + dx_b * (xv.y + p.add_offset),
-                                            v[4 * j + 2] * dx_a + dx_b * (xv.z + p.add_offset),
-                                            v[4 * j + 3] * dx_a + dx_b * (xv.w + p.add_offset));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) dst[j] = v[j] * dx_a + dx_b * (__ldg(xs + j) + p.add_offset);
-                    }
-                } else {
-                    float *dst = p.out + (long long)row * p.ldo + col;
-                    if (p.k_splits > 1) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
-                    } else if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<float4 *>(dst)[j] =
-                                make_float4(v[4 * j] * p.out_scale, v[4 * j + 1] * p.out_scale,
-                                            v[4 * j + 2] * p.out_scale, v[4 * j + 3] * p.out_scale);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) dst[j] = v[j] * p.out_scale;
-                    }
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (col + j < p.N) yd[j] = v[j];
             }
+        }
+        if (p.out == nullptr) return;
+        const int m0 = col >> 1;
+        float *dst = p.out + (long long)row * p.ldo + m0;
+        if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
+            reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (m0 + j < p.n_out) dst[j] = o[j];
+        }
+    } else if (p.epi == EPI_DX) {
+        float *dst = p.out + (long long)row * p.ldo + col;
+        const float *xs = p.dx_x + (long long)row * p.ldo + col;
+        if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
+            float4 xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xv[j] = __ldg(reinterpret_cast<const float4 *>(xs) + j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4 *>(dst)[j] =
+                    make_float4(v[4 * j] * dx_a + dx_b * (xv[j].x + p.add_offset), v[4 * j + 1] * dx_a + dx_b * (xv[j].y + p.add_offset),
+                                v[4 * j + 2] * dx_a + dx_b * (xv[j].z + p.add_offset), v[4 * j + 3] * dx_a + dx_b * (xv[j].w + p.add_offset));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col + j < p.N) dst[j] = v[j] * dx_a + dx_b * (__ldg(xs + j) + p.add_offset);
+        }
+    } else {
+        float *dst = p.out + (long long)row * p.ldo + col;
+        if (p.k_splits > 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
+        } else if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4 *>(dst)[j] = make_float4(v[4 * j] * p.out_scale, v[4 * j + 1] * p.out_scale,
+                                                                 v[4 * j + 2] * p.out_scale, v[4 * j + 3] * p.out_scale);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col + j < p.N) dst[j] = v[j] * p.out_scale;
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_tile(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane,
+                                              int cbeg, int cend) {
+    const int row = row0 + q * 32 + lane;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
+    float dx_a = 0.f, dx_b = 0.f;
+    if (p.epi == EPI_DX && row < p.M) {
+        dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
+        dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+    }
+    uint32_t ra[16], rb[16];
+    if (cbeg < cend) tc_ld16_issue(taddr + cbeg, ra);
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        tc_ld_wait(ra);
+        if (c0 + 16 < cend) tc_ld16_issue(taddr + c0 + 16, rb);
+        epilogue_chunk(p, ra, row, n0 + c0, rs, dx_a, dx_b);
+        if (c0 + 16 < cend) {
+            tc_ld_wait(rb);
+            if (c0 + 32 < cend) tc_ld16_issue(taddr + c0 + 32, ra);
+            epilogue_chunk(p, rb, row, n0 + c0 + 16, rs, dx_a, dx_b);
+        }
     }
 }
 
@@ -410,7 +427,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * BM, tn * p.bn, q, lane);
+            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * BM, tn * p.bn, q, lane, 0, p.bn);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -452,7 +469,7 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c
 }
 
 template <int NSEG, bool AMN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr uint32_t N_A = NSEG > 1 ? 2 : 1;
     constexpr uint32_t a_bytes = BM * BK * 2;
@@ -477,7 +494,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 8);    // 4 epilogue warps in each CTA
+            mbar_init(tempty_bar(s), 16);   // 8 epilogue warps in each CTA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
         const uint32_t fb0 = mapa_rank(full_bar(0), 0);      // the leader's full barriers (shared::cluster address)
         int stage = 0;
         uint32_t phase = 0;
-        constexpr int PFD = 6;                               // L2 prefetch distance of the A operand, in k-blocks
+        const int PFD = p.dbg_pfd;                           // L2 prefetch distance of the A operand, in k-blocks (0: off)
         for (long long w = pair; w < total; w += n_pairs) {
             const int split = (int)(w % p.k_splits);
             const long long tile = w / p.k_splits;
@@ -550,7 +567,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
                     // pull the A tile PFD k-blocks ahead (possibly in this pair's next tile) into L2
                     int pk = kb + PFD, pm = m0;
                     if (pk >= kb1) { pk = nkb0 + (pk - kb1); pm = nm0; }
-                    if (pm >= 0 && pk < KB) {
+                    if (PFD > 0 && pm >= 0 && pk < KB) {
 #pragma unroll
                         for (uint32_t a = 0; a < N_A; ++a) {
                             if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], pm, pk * BK); tma_prefetch_l2_2d(&p.a_map[a], pm + 64, pk * BK); }
@@ -609,7 +626,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
         }
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
-        const int q = warp & 3;
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;             // which half of the tile's columns (in 16-column chunks)
+        const int chunks = p.bn / 16;
+        const int cbeg = half == 0 ? 0 : ((chunks + 1) / 2) * 16, cend = half == 0 ? ((chunks + 1) / 2) * 16 : p.bn;
         const uint32_t te0 = mapa_rank(tempty_bar(0), 0);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -618,7 +638,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
             const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane);
+            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, cbeg, cend);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(te0 + 8u * acc);
@@ -708,6 +728,18 @@ __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, in
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
     if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(bias + n, bsum * pad);
+}
+
+// The constant pad rows of the state contribute bias[n] = pad * sum_{c >= F} W'[n][c] to every row of Y.  X carries a
+// column of ones at index F, so the bias becomes that column's weight: no bias add in the GEMM epilogue.
+__global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half *Wn_h, __half *Wn_s, __half *Wn_l) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    __half hi, hs, lo;
+    split_wgt(bias[n], hi, hs, lo);
+    Wn_h[(long long)n * Kp + F] = hi;
+    Wn_s[(long long)n * Kp + F] = hs;
+    Wn_l[(long long)n * Kp + F] = lo;
 }
 
 // Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
@@ -880,6 +912,12 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
     p.bn = pick_bn(N);
     p.k_splits = k_splits;
     const bool pair = use_pair_kernel();
+    {
+        static int pfd = -1, nost = -1;
+        if (pfd < 0) { const char *e = getenv("QIDDM_GEMM_PFD"); pfd = e ? atoi(e) : 0; }
+        if (nost < 0) { const char *e = getenv("QIDDM_GEMM_NOSTORE"); nost = e ? atoi(e) : 0; }
+        p.dbg_pfd = pfd; p.dbg_nostore = nost;
+    }
     const __half *as[2] = {A.h, A.l};
     const __half *bs[3] = {Bm.h, Bm.s, Bm.l};
     int rc;
@@ -912,7 +950,7 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         const int pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.blockDim = dim3(PAIR_THREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
@@ -1001,6 +1039,10 @@ int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapse
     timing_begin(TK_BUILD_W, 0.0, s);
     build_w_kernel<<<grid, 256, 0, s>>>(v.UT, g.A, g.F, g.Kp, g.N, g.Np, g.stride, g.w_scale, gp.pad_value, v.Wn[0],
                                         v.Wn[1], v.Wn[2], v.Wt[0], v.Wt[1], v.Wt[2], v.bias);
+    if (g.Fx > g.F) {
+        fold_bias_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(v.bias, g.N, g.Kp, g.F, v.Wn[0], v.Wn[1], v.Wn[2]);
+        count_launch();
+    }
     timing_end(s);
     count_launch();
     e = cudaGetLastError();
@@ -1079,7 +1121,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     p.epi = EPI_PROBS;
     p.out = out; p.ldo = g.n_out; p.out_scale = 1.f;
     p.y_out = w.Y;
-    p.bias = v.bias; p.row_scale = w.inv_n2;
+    p.bias = nullptr; p.row_scale = w.inv_n2;      // the bias rides in the ones column of X (fold_bias_kernel)
     p.post_scale = gp.post_scale / (g.w_scale * g.w_scale);
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
     p.n_out = g.n_out;
