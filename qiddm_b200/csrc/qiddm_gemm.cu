@@ -35,10 +35,9 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
-constexpr int PAIR_THREADS = 384;   // CTA-pair kernel: 4 role warps + 8 epilogue warps
+constexpr int PAIR_THREADS = 256;   // CTA-pair kernel: 4 role warps + 4 epilogue warps
+constexpr int EPI_STAGE_BYTES = 3072;   // per epilogue warp and buffer: 32 x 64 B (Y / dX chunk) + 32 x 32 B (probabilities)
 constexpr int ACC_COLS = 256;    // TMEM columns per accumulator stage (2 stages = 512 columns)
-constexpr float LO_SCALE = 2048.f;          // 2^11
-constexpr float LO_INV = 1.f / 2048.f;
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -111,6 +110,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
     return d;
 }
 
+// K-major, SWIZZLE_64B (32 fp16 per row; 8-row groups of 512 B)
+__device__ __forceinline__ uint64_t make_smem_desc_k32(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+    return d;
+}
+
 // MN-major, SWIZZLE_128B: each K row is 128 B of 64 contiguous M elements; 8 K rows form a 1024-B atom
 // (SBO); the next 64 M elements start LBO = 8192 B later (second TMA box of the 128-row tile).
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
@@ -169,9 +179,9 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
 enum { EPI_STORE = 0, EPI_PROBS = 1, EPI_DX = 2 };
 
 struct GemmParams {
-    alignas(64) CUtensorMap a_map[2];   // activation side: hi, lo * 2^11
-    alignas(64) CUtensorMap b_map[3];   // weight side: hi, hi * 2^-11, lo
-    int n_seg;            // 1: (a0,b0);  3: (a0,b0), (a1,b1), (a0,b2)
+    alignas(64) CUtensorMap a_map[2];   // activation side: hi, lo
+    alignas(64) CUtensorMap b_map[2];   // weight side: hi, lo
+    int n_seg;            // 1: (a0,b0);  3: (a0,b0), (a1,b0), (a0,b1)
     int a_mn;             // A is MN-major: its tensor map is over the row-major (K rows, M cols) array
     int M, N, K;          // K per segment, elements
     int bn;               // BLOCK_N: multiple of 16, <= 256
@@ -193,6 +203,10 @@ struct GemmParams {
     const unsigned int *gmax_bits;
     float add_offset;
     int dbg_pfd, dbg_nostore;   // tuning knobs (QIDDM_GEMM_PFD, QIDDM_GEMM_NOSTORE)
+    // pair kernel: epilogue through shared memory + TMA stores (fp32 boxes of 32 rows)
+    int tma_epi;
+    alignas(64) CUtensorMap y_map;      // EPI_PROBS: Y (M, N), box 16 x 32, SWIZZLE_64B
+    alignas(64) CUtensorMap o_map;      // EPI_PROBS: out (M, n_out), box 8 x 32; EPI_DX: dX (M, N), box 16 x 32, SWIZZLE_64B
 };
 
 // power-of-two scale that maps the bound on max |G| into [2^13, 2^14)
@@ -352,7 +366,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     const int tiles_n = (p.N + p.bn - 1) / p.bn;
     const int KB = (p.K + BK - 1) / BK;
     const int KT = p.n_seg * KB;
-    const long long total = (long long)tiles_m * tiles_n * p.k_splits;
+    const long long tiles_mn = (long long)tiles_m * tiles_n;
+    const long long total = tiles_mn * p.k_splits;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -360,8 +375,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-                const int split = (int)(w % p.k_splits);
-                const long long tile = w / p.k_splits;
+                const int split = (int)(w / tiles_mn);
+                const long long tile = w % tiles_mn;
                 const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
                 const int it0 = (int)((long long)split * KT / p.k_splits);
                 const int it1 = (int)((long long)(split + 1) * KT / p.k_splits);
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                     } else {
                         tma_load_2d(sa, am, full_bar(stage), kb * BK, tm * BM);
                     }
-                    tma_load_2d(sa + a_bytes, &p.b_map[seg], full_bar(stage), kb * BK, tn * p.bn);
+                    tma_load_2d(sa + a_bytes, &p.b_map[seg == 2 ? 1 : 0], full_bar(stage), kb * BK, tn * p.bn);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -391,7 +406,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-                const int split = (int)(w % p.k_splits);
+                const int split = (int)(w / tiles_mn);
                 const int it0 = (int)((long long)split * KT / p.k_splits);
                 const int it1 = (int)((long long)(split + 1) * KT / p.k_splits);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-            const long long tile = w / p.k_splits;
+            const long long tile = w % tiles_mn;
             const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -468,20 +483,121 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int NSEG, bool AMN>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Epilogue of one accumulator tile for one warp through shared memory: each lane writes its row of a 16-column chunk
+// (64-byte-swizzled) into the warp's staging buffer, one lane hands the 32-row box to the TMA (coalesced, clipped at the
+// matrix edges, asynchronous).  Two buffers alternate, so a chunk is staged while the previous one drains.
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane,
+                                                  uint32_t stage0, int &buf) {
+    const int rbase = row0 + q * 32;
+    const int row = rbase + lane;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const bool row_ok = row < p.M;
+    const float rs = (p.epi == EPI_PROBS && row_ok) ? p.row_scale[row] * p.post_scale : 0.f;
+    float dx_a = 0.f, dx_b = 0.f;
+    if (p.epi == EPI_DX && row_ok) {
+        dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
+        dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+    }
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);       // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+    auto chunk = [&](const uint32_t (&r)[16], int c0) {
+        const int col = n0 + c0;
+        if (col >= p.N || rbase >= p.M) return;             // warp-uniform
+        const uint32_t sb = stage0 + (uint32_t)buf * EPI_STAGE_BYTES;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer used two chunks ago is free
+        __syncwarp();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        const uint32_t yrow = sb + (uint32_t)lane * 64u;
+        if (p.epi == EPI_PROBS) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float pr = (v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1]) * rs;
+                if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
+                o[j] = pr;
+            }
+            if (p.y_out != nullptr) {
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                    st_shared_f4(yrow + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.out != nullptr) {
+                const uint32_t orow = sb + 2048u + (uint32_t)lane * 32u;
+                st_shared_f4(orow, o[0], o[1], o[2], o[3]);
+                st_shared_f4(orow + 16u, o[4], o[5], o[6], o[7]);
+            }
+        } else {   // EPI_DX
+            const float *xs = p.dx_x + (long long)row * p.ldo + col;
+            float x[16];
+            if (row_ok && col + 16 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(xs) + j);
+                    x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = (row_ok && col + j < p.N) ? __ldg(xs + j) : 0.f;
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                st_shared_f4(yrow + ((j ^ sw) << 4), v[4 * j] * dx_a + dx_b * (x[4 * j] + p.add_offset),
+                             v[4 * j + 1] * dx_a + dx_b * (x[4 * j + 1] + p.add_offset),
+                             v[4 * j + 2] * dx_a + dx_b * (x[4 * j + 2] + p.add_offset),
+                             v[4 * j + 3] * dx_a + dx_b * (x[4 * j + 3] + p.add_offset));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            if (p.epi == EPI_PROBS) {
+                if (p.y_out != nullptr) tma_store_2d(&p.y_map, sb, col, rbase);
+                if (p.out != nullptr) tma_store_2d(&p.o_map, sb + 2048u, col >> 1, rbase);
+            } else {
+                tma_store_2d(&p.o_map, sb, col, rbase);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        buf ^= 1;
+    };
+    uint32_t ra[16], rb[16];
+    tc_ld16_issue(taddr, ra);
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        tc_ld_wait(ra);
+        if (c0 + 16 < p.bn) tc_ld16_issue(taddr + c0 + 16, rb);
+        chunk(ra, c0);
+        if (c0 + 16 < p.bn) {
+            tc_ld_wait(rb);
+            if (c0 + 32 < p.bn) tc_ld16_issue(taddr + c0 + 32, ra);
+            chunk(rb, c0 + 16);
+        }
+    }
+}
+
+template <int NSEG, bool AMN, int BKT>
 __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr uint32_t N_A = NSEG > 1 ? 2 : 1;
-    constexpr uint32_t a_bytes = BM * BK * 2;
+    static_assert(BKT == 64 || (BKT == 32 && !AMN), "K-major tiles: 64 or 32 fp16 per row; MN-major: 64");
+    constexpr uint32_t N_A = NSEG > 1 ? 2 : 1, N_B = NSEG > 1 ? 2 : 1;   // hi (and lo) tiles of each operand per stage
+    constexpr uint32_t a_bytes = BM * BKT * 2;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)(p.bn / 2) * BK * 2;          // this CTA's half of the B tile
-    const uint32_t stage_bytes = N_A * a_bytes + (uint32_t)NSEG * b_bytes;
+    const uint32_t b_bytes = (uint32_t)(p.bn / 2) * BKT * 2;         // this CTA's half of the B tile
+    const uint32_t stage_bytes = N_A * a_bytes + N_B * b_bytes;
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+    const uint32_t epi_base = (tmem_slot + 4u + 511u) & ~511u;      // staging of the TMA-store epilogue (tma_epi)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -494,7 +610,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 16);   // 8 epilogue warps in each CTA
+            mbar_init(tempty_bar(s), 8);    // 4 epilogue warps in each CTA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -511,8 +627,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
 
     const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);       // 256-row tiles
     const int tiles_n = (p.N + p.bn - 1) / p.bn;
-    const int KB = (p.K + BK - 1) / BK;
-    const long long total = (long long)tiles_m * tiles_n * p.k_splits;
+    const int KB = (p.K + BKT - 1) / BKT;
+    const long long tiles_mn = (long long)tiles_m * tiles_n;
+    const long long total = tiles_mn * p.k_splits;
     const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (warp == 0) {
@@ -523,8 +640,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
         uint32_t phase = 0;
         const int PFD = p.dbg_pfd;                           // L2 prefetch distance of the A operand, in k-blocks (0: off)
         for (long long w = pair; w < total; w += n_pairs) {
-            const int split = (int)(w % p.k_splits);
-            const long long tile = w / p.k_splits;
+            const int split = (int)(w / tiles_mn);
+            const long long tile = w % tiles_mn;
             const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
             const int m0 = tm * 2 * BM + (int)rank * BM;
             const int nb0 = tn * p.bn + (int)rank * (p.bn / 2);
@@ -534,15 +651,15 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             const long long wn = w + n_pairs;
             int nm0 = -1, nkb0 = 0;
             if (wn < total) {
-                const int nsplit = (int)(wn % p.k_splits);
-                nm0 = (int)((wn / p.k_splits) / tiles_n) * 2 * BM + (int)rank * BM;
+                const int nsplit = (int)(wn / tiles_mn);
+                nm0 = (int)((wn % tiles_mn) / tiles_n) * 2 * BM + (int)rank * BM;
                 nkb0 = (int)((long long)nsplit * KB / p.k_splits);
             }
             if (w == pair && issuer) {
                 for (int i = 0; i < PFD && kb0 + i < kb1; ++i)
                     for (uint32_t a = 0; a < N_A; ++a) {
-                        if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], m0, (kb0 + i) * BK); tma_prefetch_l2_2d(&p.a_map[a], m0 + 64, (kb0 + i) * BK); }
-                        else tma_prefetch_l2_2d(&p.a_map[a], (kb0 + i) * BK, m0);
+                        if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], m0, (kb0 + i) * BKT); tma_prefetch_l2_2d(&p.a_map[a], m0 + 64, (kb0 + i) * BKT); }
+                        else tma_prefetch_l2_2d(&p.a_map[a], (kb0 + i) * BKT, m0);
                     }
             }
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -555,23 +672,23 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     for (uint32_t i = 0; i < N_A; ++i) {
                         const uint32_t dst = sa + i * a_bytes;
                         if (AMN) {   // two (64 M) x (64 K) boxes from the row-major (K, M) array
-                            tma_load_2d_pair(dst, &p.a_map[i], fb, m0, kb * BK);
-                            tma_load_2d_pair(dst + a_bytes / 2, &p.a_map[i], fb, m0 + 64, kb * BK);
+                            tma_load_2d_pair(dst, &p.a_map[i], fb, m0, kb * BKT);
+                            tma_load_2d_pair(dst + a_bytes / 2, &p.a_map[i], fb, m0 + 64, kb * BKT);
                         } else {
-                            tma_load_2d_pair(dst, &p.a_map[i], fb, kb * BK, m0);
+                            tma_load_2d_pair(dst, &p.a_map[i], fb, kb * BKT, m0);
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < NSEG; ++i)
-                        tma_load_2d_pair(sa + N_A * a_bytes + i * b_bytes, &p.b_map[i], fb, kb * BK, nb0);
+                    for (uint32_t i = 0; i < N_B; ++i)
+                        tma_load_2d_pair(sa + N_A * a_bytes + i * b_bytes, &p.b_map[i], fb, kb * BKT, nb0);
                     // pull the A tile PFD k-blocks ahead (possibly in this pair's next tile) into L2
                     int pk = kb + PFD, pm = m0;
                     if (pk >= kb1) { pk = nkb0 + (pk - kb1); pm = nm0; }
                     if (PFD > 0 && pm >= 0 && pk < KB) {
 #pragma unroll
                         for (uint32_t a = 0; a < N_A; ++a) {
-                            if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], pm, pk * BK); tma_prefetch_l2_2d(&p.a_map[a], pm + 64, pk * BK); }
-                            else tma_prefetch_l2_2d(&p.a_map[a], pk * BK, pm);
+                            if (AMN) { tma_prefetch_l2_2d(&p.a_map[a], pm, pk * BKT); tma_prefetch_l2_2d(&p.a_map[a], pm + 64, pk * BKT); }
+                            else tma_prefetch_l2_2d(&p.a_map[a], pk * BKT, pm);
                         }
                     }
                 }
@@ -591,7 +708,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (long long w = pair; w < total; w += n_pairs) {
-                const int split = (int)(w % p.k_splits);
+                const int split = (int)(w / tiles_mn);
                 const int kb0 = (int)((long long)split * KB / p.k_splits);
                 const int kb1 = (int)((long long)(split + 1) * KB / p.k_splits);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -601,17 +718,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    const uint64_t ad0 = AMN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
-                    const uint64_t ad1 = AMN ? make_smem_desc_mn(sa + a_bytes) : make_smem_desc(sa + a_bytes);
-                    const uint64_t bd0 = make_smem_desc(sa + N_A * a_bytes);
+                    const uint64_t ad0 = AMN ? make_smem_desc_mn(sa) : (BKT == 64 ? make_smem_desc(sa) : make_smem_desc_k32(sa));
+                    const uint64_t ad1 = AMN ? make_smem_desc_mn(sa + a_bytes)
+                                             : (BKT == 64 ? make_smem_desc(sa + a_bytes) : make_smem_desc_k32(sa + a_bytes));
+                    const uint64_t bd0 = BKT == 64 ? make_smem_desc(sa + N_A * a_bytes) : make_smem_desc_k32(sa + N_A * a_bytes);
                     const uint64_t bstep = (uint64_t)(b_bytes >> 4);
                     if (issuer) {
 #pragma unroll
                         for (int seg = 0; seg < NSEG; ++seg) {
                             const uint64_t adesc = seg == 1 ? ad1 : ad0;
-                            const uint64_t bdesc = bd0 + bstep * seg;
+                            const uint64_t bdesc = seg == 2 ? bd0 + bstep : bd0;
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k)
+                            for (int k = 0; k < BKT / UMMA_K; ++k)
                                 tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc,
                                                 (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u);
                         }
@@ -627,23 +745,25 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        const int half = (warp - 4) >> 2;             // which half of the tile's columns (in 16-column chunks)
-        const int chunks = p.bn / 16;
-        const int cbeg = half == 0 ? 0 : ((chunks + 1) / 2) * 16, cend = half == 0 ? ((chunks + 1) / 2) * 16 : p.bn;
         const uint32_t te0 = mapa_rank(tempty_bar(0), 0);
-        int acc = 0;
+        const uint32_t stage0 = epi_base + (uint32_t)q * 2u * EPI_STAGE_BYTES;
+        int acc = 0, buf = 0;
         uint32_t acc_phase = 0;
         for (long long w = pair; w < total; w += n_pairs) {
-            const long long tile = w / p.k_splits;
+            const long long tile = w % tiles_mn;
             const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, cbeg, cend);
+            if (p.tma_epi)
+                epilogue_tile_tma(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, buf);
+            else
+                epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, 0, p.bn);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(te0 + 8u * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_epi && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -657,17 +777,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
 // ------------------------------------------------------------------------------------------
 // elementwise helpers
 // ------------------------------------------------------------------------------------------
-// activation-side split: hi + lo * 2^11
-__device__ __forceinline__ void split_act(float v, __half &hi, __half &lo_s) {
+// fp32 -> fp16 hi + fp16 lo (22 mantissa bits; the tensor cores take fp16 subnormals, so lo needs no scaling --
+// measured: 7e-6 rel-to-max on the n = 10, K = 784 layer with inputs down to 2^-17)
+__device__ __forceinline__ void split_act(float v, __half &hi, __half &lo) {
     hi = __float2half_rn(v);
-    lo_s = __float2half_rn((v - __half2float(hi)) * LO_SCALE);
-}
-// weight-side split: hi, hi * 2^-11 (pairs with the activation's lo * 2^11), plain lo
-__device__ __forceinline__ void split_wgt(float v, __half &hi, __half &hs, __half &lo) {
-    hi = __float2half_rn(v);
-    const float h = __half2float(hi);
-    hs = __float2half_rn(h * LO_INV);
-    lo = __float2half_rn(v - h);
+    lo = __float2half_rn(v - __half2float(hi));
 }
 
 // x (B,F) fp32 -> Xh/Xl (B,Kp) fp16 (hi, lo*2^11) and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).  One warp per row.
@@ -700,7 +814,7 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
 //   Wn[n][c] (N x Kp), Wt[c][n] (F x Np), n = 2m + {re,im}, value = part(UT[c][m*stride]);
 //   bias[n] = pad * sum_{c >= F} value.
 __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, int Np, int stride, float w_scale,
-                               float pad, __half *Wn_h, __half *Wn_s, __half *Wn_l, __half *Wt_h, __half *Wt_s,
+                               float pad, __half *Wn_h, __half *Wn_l, __half *Wt_h,
                                __half *Wt_l, float *bias) {
     const int n = blockIdx.y;
     const int m = n >> 1, ri = n & 1;
@@ -712,14 +826,12 @@ __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, in
             v = (ri ? u.y : u.x) * w_scale;
         }
         if (c < Kp) {
-            __half hi, hs, lo;
-            split_wgt(c < F ? v : 0.f, hi, hs, lo);
+            __half hi, lo;
+            split_act(c < F ? v : 0.f, hi, lo);
             Wn_h[(long long)n * Kp + c] = hi;
-            Wn_s[(long long)n * Kp + c] = hs;
             Wn_l[(long long)n * Kp + c] = lo;
             if (c < F) {
                 Wt_h[(long long)c * Np + n] = hi;
-                Wt_s[(long long)c * Np + n] = hs;
                 Wt_l[(long long)c * Np + n] = lo;
             }
         }
@@ -732,13 +844,12 @@ __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, in
 
 // The constant pad rows of the state contribute bias[n] = pad * sum_{c >= F} W'[n][c] to every row of Y.  X carries a
 // column of ones at index F, so the bias becomes that column's weight: no bias add in the GEMM epilogue.
-__global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half *Wn_h, __half *Wn_s, __half *Wn_l) {
+__global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half *Wn_h, __half *Wn_l) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    __half hi, hs, lo;
-    split_wgt(bias[n], hi, hs, lo);
+    __half hi, lo;
+    split_act(bias[n], hi, lo);
     Wn_h[(long long)n * Kp + F] = hi;
-    Wn_s[(long long)n * Kp + F] = hs;
     Wn_l[(long long)n * Kp + F] = lo;
 }
 
@@ -797,7 +908,7 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
 
 // X (B,Kp) activation splits (hi, lo*2^11) -> transposed weight-side splits (Kp,Bp): hi, hi*2^-11, lo
 __global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, long long B, int Kp, long long Bp, __half *XTh,
-                                   __half *XTs, __half *XTl) {
+                                   __half *XTl) {
     __shared__ __half th[32][34], tl[32][34];
     const long long r0 = (long long)blockIdx.y * 32;
     const int c0 = blockIdx.x * 32;
@@ -813,10 +924,8 @@ __global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, long long
         const int c = c0 + i;
         const long long r = r0 + threadIdx.x;
         if (c < Kp && r < Bp) {
-            const float h = __half2float(th[threadIdx.x][i]);
             XTh[(long long)c * Bp + r] = th[threadIdx.x][i];
-            XTs[(long long)c * Bp + r] = __float2half_rn(h * LO_INV);
-            XTl[(long long)c * Bp + r] = __float2half_rn(__half2float(tl[threadIdx.x][i]) * LO_INV);
+            XTl[(long long)c * Bp + r] = tl[threadIdx.x][i];
         }
     }
 }
@@ -863,18 +972,24 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D fp16 row-major (rows x cols, pitch elements) tensor map with a (64 x box_rows) SWIZZLE_128B box.
-int make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long pitch, int box_rows) {
+// 2-D row-major (rows x cols, pitch elements) tensor map with a (box_cols x box_rows) box.
+int make_map_ex(CUtensorMap *map, CUtensorMapDataType dt, int elt_bytes, const void *ptr, long long rows, long long cols,
+                long long pitch, int box_cols, int box_rows, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return QIDDM_EUNSUPPORTED;
+    if (((uintptr_t)ptr & 15) != 0 || ((pitch * elt_bytes) & 15) != 0) return QIDDM_EINVAL;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * elt_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? QIDDM_OK : QIDDM_EINVAL;
+}
+// fp16 operand map: rows of `bk` K elements (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
+int make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long pitch, int box_rows, int bk = BK) {
+    return make_map_ex(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, rows, cols, pitch, bk, box_rows,
+                       bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int pick_bn(int N) {
@@ -890,8 +1005,8 @@ int pick_bn(int N) {
     return best;
 }
 
-struct ActOperand { const __half *h, *l; };          // hi, lo * 2^11
-struct WgtOperand { const __half *h, *s, *l; };      // hi, hi * 2^-11, lo
+struct ActOperand { const __half *h, *l; };          // hi, lo
+struct WgtOperand { const __half *h, *l; };          // hi, lo
 
 bool use_pair_kernel() {
     static int v = -1;
@@ -918,29 +1033,52 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         if (nost < 0) { const char *e = getenv("QIDDM_GEMM_NOSTORE"); nost = e ? atoi(e) : 0; }
         p.dbg_pfd = pfd; p.dbg_nostore = nost;
     }
+    static int bk32 = -1;
+    if (bk32 < 0) { const char *e = getenv("QIDDM_GEMM_BK32"); bk32 = e ? atoi(e) : 0; }
+    const int bkt = (pair && !a_mn && bk32) ? 32 : BK;       // optional 32-wide k-blocks (finer stages; measured slower)
     const __half *as[2] = {A.h, A.l};
-    const __half *bs[3] = {Bm.h, Bm.s, Bm.l};
+    const __half *bs[2] = {Bm.h, Bm.l};
     int rc;
     for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
-        if ((rc = make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, a_mn ? 64 : BM)) != QIDDM_OK) return rc;
-    for (int i = 0; i < n_seg; ++i)
-        if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, pair ? p.bn / 2 : p.bn)) != QIDDM_OK) return rc;
+        if ((rc = make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, a_mn ? 64 : BM, bkt)) != QIDDM_OK) return rc;
+    for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
+        if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, pair ? p.bn / 2 : p.bn, bkt)) != QIDDM_OK) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     timing_begin(TK_GEMM, 2.0 * (double)M * (double)N * (double)K, s);   // single-pass (algorithmic) flops
     cudaError_t e;
     if (pair) {
-        const int stage_bytes = (n_seg > 1 ? 2 : 1) * BM * BK * 2 + n_seg * (p.bn / 2) * BK * 2;
-        int stages = (226 * 1024 - 1024 - 256) / stage_bytes;
+        // epilogue through shared memory + TMA stores when the outputs are TMA-addressable
+        p.tma_epi = 0;
+        static int tma_epi_on = -1;
+        if (tma_epi_on < 0) { const char *ev = getenv("QIDDM_GEMM_TMA_EPI"); tma_epi_on = ev ? atoi(ev) : 1; }
+        if (tma_epi_on && k_splits == 1 && (p.epi == EPI_PROBS || p.epi == EPI_DX)) {
+            bool ok = true;
+            if (p.epi == EPI_PROBS) {
+                if (p.y_out) ok = ok && make_map_ex(&p.y_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.y_out, M, N, N, 16, 32,
+                                                    CU_TENSOR_MAP_SWIZZLE_64B) == QIDDM_OK;
+                if (p.out) ok = ok && make_map_ex(&p.o_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, M, p.n_out, p.ldo, 8, 32,
+                                                  CU_TENSOR_MAP_SWIZZLE_NONE) == QIDDM_OK;
+            } else {
+                ok = make_map_ex(&p.o_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, M, N, p.ldo, 16, 32,
+                                 CU_TENSOR_MAP_SWIZZLE_64B) == QIDDM_OK;
+            }
+            p.tma_epi = ok ? 1 : 0;
+        }
+        const int epi_bytes = p.tma_epi ? 4 * 2 * EPI_STAGE_BYTES + 512 : 0;
+        const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + (p.bn / 2) * bkt * 2);
+        int stages = (226 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes;
         if (stages > 8) stages = 8;
         if (stages < 2) stages = 2;
         p.stages = stages;
-        const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-        void (*kern)(const GemmParams) = n_seg > 1 ? (a_mn ? gemm_pair_kernel<3, true> : gemm_pair_kernel<3, false>)
-                                                   : (a_mn ? gemm_pair_kernel<1, true> : gemm_pair_kernel<1, false>);
-        static bool attr_set2[4] = {false, false, false, false};
-        const int ki = (n_seg > 1 ? 2 : 0) + (a_mn ? 1 : 0);
+        const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
+        void (*kern)(const GemmParams);
+        if (a_mn) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64> : gemm_pair_kernel<1, true, 64>;
+        else if (bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, false, 32> : gemm_pair_kernel<1, false, 32>;
+        else kern = n_seg > 1 ? gemm_pair_kernel<3, false, 64> : gemm_pair_kernel<1, false, 64>;
+        static bool attr_set2[6] = {false, false, false, false, false, false};
+        const int ki = (n_seg > 1 ? 3 : 0) + (a_mn ? 2 : (bkt == 32 ? 1 : 0));
         if (!attr_set2[ki]) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;
@@ -1009,23 +1147,23 @@ GemmShape gemm_shape(const GateParams &gp, int n_qubits) {
 size_t gemm_collapsed_bytes(const GemmShape &g) {
     size_t b = 0;
     b += al((size_t)g.A * g.A * 8);                  // UT
-    b += 3 * al((size_t)g.N * g.Kp * 2);             // Wn h/s/l
-    b += 3 * al((size_t)g.F * g.Np * 2);             // Wt h/s/l
+    b += 2 * al((size_t)g.N * g.Kp * 2);             // Wn hi/lo
+    b += 2 * al((size_t)g.F * g.Np * 2);             // Wt hi/lo
     b += al((size_t)g.N * 4);                        // bias
     return b;
 }
 
 struct CollapsedView {
     float2 *UT;
-    __half *Wn[3], *Wt[3];
+    __half *Wn[2], *Wt[2];
     float *bias;
 };
 static CollapsedView collapsed_view(const GemmShape &g, void *buf) {
     CollapsedView v;
     char *p = reinterpret_cast<char *>(buf);
     v.UT = reinterpret_cast<float2 *>(p); p += al((size_t)g.A * g.A * 8);
-    for (int i = 0; i < 3; ++i) { v.Wn[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.N * g.Kp * 2); }
-    for (int i = 0; i < 3; ++i) { v.Wt[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.F * g.Np * 2); }
+    for (int i = 0; i < 2; ++i) { v.Wn[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.N * g.Kp * 2); }
+    for (int i = 0; i < 2; ++i) { v.Wt[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.F * g.Np * 2); }
     v.bias = reinterpret_cast<float *>(p);
     return v;
 }
@@ -1038,9 +1176,9 @@ int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapse
     dim3 grid((cmax + 255) / 256, g.N);
     timing_begin(TK_BUILD_W, 0.0, s);
     build_w_kernel<<<grid, 256, 0, s>>>(v.UT, g.A, g.F, g.Kp, g.N, g.Np, g.stride, g.w_scale, gp.pad_value, v.Wn[0],
-                                        v.Wn[1], v.Wn[2], v.Wt[0], v.Wt[1], v.Wt[2], v.bias);
+                                        v.Wn[1], v.Wt[0], v.Wt[1], v.bias);
     if (g.Fx > g.F) {
-        fold_bias_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(v.bias, g.N, g.Kp, g.F, v.Wn[0], v.Wn[1], v.Wn[2]);
+        fold_bias_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(v.bias, g.N, g.Kp, g.F, v.Wn[0], v.Wn[1]);
         count_launch();
     }
     timing_end(s);
@@ -1053,7 +1191,7 @@ float *gemm_collapsed_ut(const GemmShape &g, void *collapsed) { return reinterpr
 
 size_t gemm_saved_bytes(const GemmShape &g, long long B) {
     const long long Bp = (B + 7) & ~7LL;
-    return 2 * al((size_t)B * g.Kp * 2) + 3 * al((size_t)g.Kp * Bp * 2) + al((size_t)B * 4) +
+    return 2 * al((size_t)B * g.Kp * 2) + 2 * al((size_t)g.Kp * Bp * 2) + al((size_t)B * 4) +
            al((size_t)B * g.N * 4);
 }
 
@@ -1072,7 +1210,7 @@ size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
 
 namespace {
 struct SavedView {
-    __half *X[2], *XT[3];
+    __half *X[2], *XT[2];
     float *inv_n2, *Y;
     char *end;
 };
@@ -1082,7 +1220,7 @@ SavedView saved_view(const GemmShape &g, long long B, void *buf, bool full) {
     const long long Bp = (B + 7) & ~7LL;
     char *p = reinterpret_cast<char *>(buf);
     for (int i = 0; i < 2; ++i) { w.X[i] = reinterpret_cast<__half *>(p); p += al((size_t)B * g.Kp * 2); }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 2; ++i) {
         w.XT[i] = full ? reinterpret_cast<__half *>(p) : nullptr;
         if (full) p += al((size_t)g.Kp * Bp * 2);
     }
@@ -1112,7 +1250,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
         dim3 tb(32, 8);
         dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
         timing_begin(TK_TRANSPOSE_X, 0.0, s);
-        transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1], w.XT[2]);
+        transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1]);
         timing_end(s);
         count_launch();
     }
@@ -1126,7 +1264,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
     p.n_out = g.n_out;
     ActOperand A{w.X[0], w.X[1]};
-    WgtOperand Bm{v.Wn[0], v.Wn[1], v.Wn[2]};
+    WgtOperand Bm{v.Wn[0], v.Wn[1]};
     timing_set_gemm_kind(TK_GEMM_FWD);
     return run_gemm(A, B, g.Kp, g.Kp, false, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg, 1, p, s);
 }
@@ -1179,7 +1317,7 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         memset(&p, 0, sizeof(p));
         p.epi = EPI_DX; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
         p.row_scale = w.inv_n2; p.dx_S = S; p.dx_x = x; p.gmax_bits = gmax; p.add_offset = gp.add_offset;
-        WgtOperand Wt{v.Wt[0], v.Wt[1], v.Wt[2]};
+        WgtOperand Wt{v.Wt[0], v.Wt[1]};
         timing_set_gemm_kind(TK_GEMM_DX);
         rc = run_gemm(Go, B, g.Np, g.Np, false, Wt, g.F, g.Np, (int)B, g.F, g.N, n_seg, 1, p, s);
         if (rc != QIDDM_OK) return rc;
@@ -1189,15 +1327,23 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     {
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = dWT; p.ldo = g.Fx; p.out_scale = 1.f;
-        WgtOperand XTo{w.XT[0], w.XT[1], w.XT[2]};
+        WgtOperand XTo{w.XT[0], w.XT[1]};
         const int bn = pick_bn(g.Fx);
         const bool pair = use_pair_kernel();
         const int bm = pair ? 2 * BM : BM;
         const int tiles = ((g.N + bm - 1) / bm) * ((g.Fx + bn - 1) / bn);
-        long long kt = pair ? (Bp + BK - 1) / BK : (long long)n_seg * ((Bp + BK - 1) / BK);
-        int splits = (int)(((pair ? 148 : 2 * 148) + tiles - 1) / tiles);
-        if (splits > kt) splits = (int)kt;
-        if (splits < 1) splits = 1;
+        const long long kt = pair ? (Bp + BK - 1) / BK : (long long)n_seg * ((Bp + BK - 1) / BK);
+        // split-K over the batch: fill whole waves of the persistent grid (items = tiles * splits close to a multiple of the
+        // number of CTAs / pairs), with a small price per split for its fp32 atomics
+        const int workers = pair ? 74 : 148;
+        int splits = 1;
+        double best = 1e30;
+        for (int sp = 1; sp <= 64 && sp <= kt; ++sp) {
+            const long long items = (long long)tiles * sp;
+            const long long waves = (items + workers - 1) / workers;
+            const double cost = (double)(waves * workers) / (double)items + 0.004 * sp + (items < workers ? 10.0 : 0.0);
+            if (cost < best) { best = cost; splits = sp; }
+        }
         timing_set_gemm_kind(TK_GEMM_DW);
         rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
         if (rc != QIDDM_OK) return rc;

@@ -1,28 +1,30 @@
-"""Diagnostic: where does the x3 GEMM path's forward error come from? (gate path vs GEMM vs U build)"""
-import sys, dataclasses, torch
-sys.path.insert(0, ".")
+#!/usr/bin/env python
+"""Measured GEMM-path accuracy vs the complex128 oracle (rel-to-max), for tuning the fp16 split scheme."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+import torch
 from oracle import qiddm_oracle as O
 from qiddm_b200 import _lib as L
-from qiddm_b200.functional import run_stage, build_unitary
-sys.path.insert(0, "tests")
-from test_gpu_gemm_path import _spec
+from qiddm_b200.functional import run_stage
 
-def rel(a, b):
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return ((a - b).abs().max() / b.abs().max()).item()
+def rel(a, b): return ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
 
-for depth in (4, 20, 60):
-    d = O.desc_qdense(depth, 784, O.REMAP_TANH)
-    d = dataclasses.replace(d, clamp=False)
-    g = torch.Generator().manual_seed(1)
-    W = torch.randn(1, depth, 10, 3, generator=g, dtype=torch.float64) * 0.4
-    x = torch.rand(257, 784, generator=g, dtype=torch.float64)
-    ref = O.run_stage(d, x, W)
-    gate = run_stage(_spec(d, L.PATH_GATE), x.cuda(), W.cuda())
-    gemm3 = run_stage(_spec(d, L.PATH_GEMM, 3), x.cuda(), W.cuda())
-    gemm1 = run_stage(_spec(d, L.PATH_GEMM, 1), x.cuda(), W.cuda())
-    U = build_unitary(_spec(d, L.PATH_GATE), W.cuda())
-    Uref = O.circuit_unitary(d, W)
-    eU = (U.cpu().to(torch.complex128) - Uref).abs().max().item() / Uref.abs().max().item()
-    print(f"depth {depth}: gate {rel(gate, ref):.2e}  gemm_x3 {rel(gemm3, ref):.2e}  gemm_x1 {rel(gemm1, ref):.2e}  "
-          f"U build {eU:.2e}  gemm3 vs gate {rel(gemm3, gate):.2e}  max ref {ref.max().item():.3f}")
+for (n, F, K, depth, small) in [(10, 784, 784, 60, False), (10, 784, 784, 60, True), (8, 200, 200, 10, False), (7, 72, 8, 3, True)]:
+    g = torch.Generator().manual_seed(n)
+    d = O.StageDesc(n_qubits=n, layers_per_block=depth, init=O.INIT_AMPLITUDE, n_features=F, pad_value=0.1,
+                    imprimitive=O.IMP_CNOT, remap=O.REMAP_TANH, readout=O.READ_PROBS, read_count=K, post_scale=float(K))
+    W = torch.randn(1, depth, n, 3, generator=g, dtype=torch.float64) * 0.4
+    x = torch.rand(300, F, generator=g, dtype=torch.float64) * (0.05 if small else 1.0)
+    Wr, xr = W.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ref = O.run_stage(d, xr, Wr, batch=300)
+    go = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * go).sum().backward()
+    spec = L.StageSpec(n_qubits=n, layers_per_block=depth, init=L.INIT_AMPLITUDE, n_features=F, pad_value=0.1,
+                       imprimitive=L.IMP_CNOT, remap=L.REMAP_TANH, readout=L.READ_PROBS, read_count=K,
+                       post_scale=float(K), path=L.PATH_GEMM, gemm_precision=3)
+    Wd, xd = W.cuda().requires_grad_(True), x.cuda().requires_grad_(True)
+    out = run_stage(spec, xd, Wd)
+    (out * go.cuda()).sum().backward()
+    print(f"n={n} F={F} K={K} depth={depth} small_inputs={small}: out {rel(out, ref.detach()):.2e}  dW {rel(Wd.grad, Wr.grad):.2e}  dX {rel(xd.grad, xr.grad):.2e}")
