@@ -855,77 +855,140 @@ __global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half
 
 // Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
 // |G[b,n]| = 2 |g| scale inv_n2 |Y'| <= 2 max_m|g[b,m]| * scale * sqrt(inv_n2[b]) * w_scale.
-__global__ void g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out, float scale,
-                               float w_scale, unsigned int *gmax_bits) {
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out,
+                                                      float scale, float w_scale, unsigned int *gmax_bits) {
     const int lane = threadIdx.x & 31;
-    if (row >= B) return;
-    float mx = 0.f;
-    for (int m = lane; m < n_out; m += 32) mx = fmaxf(mx, fabsf(__ldg(go + row * n_out + m)));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) {
-        const float bound = 2.f * mx * scale * sqrtf(inv_n2[row]) * w_scale;
-        if (bound > 0.f && bound < 3.0e38f) atomicMax(gmax_bits, __float_as_uint(bound));
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const bool vec = (n_out & 3) == 0 && ((uintptr_t)go & 15) == 0;
+    float best = 0.f;
+    for (long long row = warp0; row < B; row += nwarps) {
+        const float *g = go + row * n_out;
+        float mx = 0.f;
+        if (vec) {
+            for (int i = lane; i < (n_out >> 2); i += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            }
+        } else {
+            for (int m = lane; m < n_out; m += 32) mx = fmaxf(mx, fabsf(__ldg(g + m)));
+        }
+        best = fmaxf(best, 2.f * mx * scale * sqrtf(inv_n2[row]) * w_scale);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0 && best > 0.f && best < 3.0e38f) atomicMax(gmax_bits, __float_as_uint(best));
 }
 
 // One streaming pass over Y (= X W' + bias', saved by the forward GEMM) and grad_out, one warp per row:
 //   out = scale inv_n2 |Y|^2, mask = !clamp || lo <= out <= hi,  G[2m+ri] = 2 g mask scale inv_n2 Y[2m+ri]
-// written as scaled fp16 (hi, lo*2^11) row-major (B,Np); S[b] = sum_m g mask out (normalisation term of dX).
+// written as scaled fp16 (hi, lo) row-major (B,Np); S[b] = sum_m g mask out (normalisation term of dX).
 __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float *go, const float *inv_n2, long long B,
                                                      int N, int Np, int n_out, float scale, int clamp, float lo,
                                                      float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl,
                                                      float *S, int want_lo) {
-    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= B) return;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const float gsc = g_scale_from_max(*gmax_bits);
-    const float in2 = inv_n2[r];
-    float s_part = 0.f;
-    for (int m = lane; 2 * m < Np; m += 32) {
-        float gre = 0.f, gim = 0.f;
-        if (m < n_out) {
-            const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + 2 * m);
-            const float outv = scale * in2 * (y.x * y.x + y.y * y.y);
-            const bool pass = !clamp || (outv >= lo && outv <= hi);
-            const float g = pass ? __ldg(go + r * n_out + m) : 0.f;
-            const float coef = 2.f * g * scale * in2 * gsc;
-            gre = coef * y.x;
-            gim = coef * y.y;
-            s_part += g * outv;
-        }
-        __half h0, l0, h1, l1;
-        split_act(gre, h0, l0);
-        split_act(gim, h1, l1);
-        *reinterpret_cast<__half2 *>(Gh + r * Np + 2 * m) = __halves2half2(h0, h1);
-        if (want_lo) *reinterpret_cast<__half2 *>(Gl + r * Np + 2 * m) = __halves2half2(l0, l1);
-    }
+    // 4 outputs (8 columns of Y / G) per lane and iteration when everything is 16-byte aligned
+    const bool vec = (n_out & 3) == 0 && Np == N && (((uintptr_t)Y | (uintptr_t)go | (uintptr_t)Gh | (uintptr_t)Gl) & 15) == 0;
+    for (long long r = warp0; r < B; r += nwarps) {
+        const float in2 = inv_n2[r];
+        const float k0 = scale * in2, k1 = 2.f * scale * in2 * gsc;
+        float s_part = 0.f;
+        if (vec) {
+            const float4 *y4 = reinterpret_cast<const float4 *>(Y + r * N);
+            const float4 *g4 = reinterpret_cast<const float4 *>(go + r * n_out);
+            uint4 *gh4 = reinterpret_cast<uint4 *>(Gh + r * Np), *gl4 = reinterpret_cast<uint4 *>(Gl + r * Np);
+            for (int i = lane; i < (n_out >> 2); i += 32) {
+                const float4 ya = __ldg(y4 + 2 * i), yb = __ldg(y4 + 2 * i + 1), gg = __ldg(g4 + i);
+                const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
+                __half2 hh[4], ll[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
-    if (lane == 0) S[r] = s_part;
+                for (int j = 0; j < 4; ++j) {
+                    const float re = yv[2 * j], im = yv[2 * j + 1];
+                    const float outv = k0 * (re * re + im * im);
+                    const bool pass = !clamp || (outv >= lo && outv <= hi);
+                    const float g = pass ? gv[j] : 0.f;
+                    const float coef = k1 * g;
+                    s_part += g * outv;
+                    __half h0, l0, h1, l1;
+                    split_act(coef * re, h0, l0);
+                    split_act(coef * im, h1, l1);
+                    hh[j] = __halves2half2(h0, h1);
+                    ll[j] = __halves2half2(l0, l1);
+                }
+                gh4[i] = make_uint4(*reinterpret_cast<unsigned int *>(&hh[0]), *reinterpret_cast<unsigned int *>(&hh[1]),
+                                    *reinterpret_cast<unsigned int *>(&hh[2]), *reinterpret_cast<unsigned int *>(&hh[3]));
+                if (want_lo)
+                    gl4[i] = make_uint4(*reinterpret_cast<unsigned int *>(&ll[0]), *reinterpret_cast<unsigned int *>(&ll[1]),
+                                        *reinterpret_cast<unsigned int *>(&ll[2]), *reinterpret_cast<unsigned int *>(&ll[3]));
+            }
+        } else {
+            for (int m = lane; 2 * m < Np; m += 32) {
+                float gre = 0.f, gim = 0.f;
+                if (m < n_out) {
+                    const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + 2 * m);
+                    const float outv = k0 * (y.x * y.x + y.y * y.y);
+                    const bool pass = !clamp || (outv >= lo && outv <= hi);
+                    const float g = pass ? __ldg(go + r * n_out + m) : 0.f;
+                    gre = k1 * g * y.x;
+                    gim = k1 * g * y.y;
+                    s_part += g * outv;
+                }
+                __half h0, l0, h1, l1;
+                split_act(gre, h0, l0);
+                split_act(gim, h1, l1);
+                *reinterpret_cast<__half2 *>(Gh + r * Np + 2 * m) = __halves2half2(h0, h1);
+                if (want_lo) *reinterpret_cast<__half2 *>(Gl + r * Np + 2 * m) = __halves2half2(l0, l1);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
+        if (lane == 0) S[r] = s_part;
+    }
 }
 
 // X (B,Kp) activation splits (hi, lo*2^11) -> transposed weight-side splits (Kp,Bp): hi, hi*2^-11, lo
-__global__ void transpose_x_kernel(const __half *Xh, const __half *Xl, long long B, int Kp, long long Bp, __half *XTh,
-                                   __half *XTl) {
-    __shared__ __half th[32][34], tl[32][34];
-    const long long r0 = (long long)blockIdx.y * 32;
-    const int c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const long long r = r0 + i;
-        const int c = c0 + threadIdx.x;
-        const bool ok = r < B && c < Kp;
-        th[i][threadIdx.x] = ok ? Xh[r * Kp + c] : __float2half(0.f);
-        tl[i][threadIdx.x] = ok ? Xl[r * Kp + c] : __float2half(0.f);
+__global__ void __launch_bounds__(256) transpose_x_kernel(const __half *Xh, const __half *Xl, long long B, int Kp, long long Bp,
+                                                          __half *XTh, __half *XTl) {
+    // 64 x 64 tiles, 16-byte global accesses on both sides (Kp and Bp are multiples of 8)
+    __shared__ __half th[64][72], tl[64][72];
+    const long long r0 = (long long)blockIdx.y * 64;
+    const int c0 = blockIdx.x * 64;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + i * 256;            // 512 16-byte pieces per array: row = idx / 8, piece = idx % 8
+        const int rr = idx >> 3, pc = idx & 7;
+        const long long r = r0 + rr;
+        const int c = c0 + pc * 8;
+        uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+        if (r < B && c < Kp) {
+            vh = *reinterpret_cast<const uint4 *>(Xh + r * Kp + c);
+            vl = *reinterpret_cast<const uint4 *>(Xl + r * Kp + c);
+        }
+        *reinterpret_cast<uint4 *>(&th[rr][pc * 8]) = vh;
+        *reinterpret_cast<uint4 *>(&tl[rr][pc * 8]) = vl;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i;
-        const long long r = r0 + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = t + i * 256;            // output row (feature) = idx / 8, piece of 8 batch rows = idx % 8
+        const int cc = idx >> 3, pr = idx & 7;
+        const int c = c0 + cc;
+        const long long r = r0 + pr * 8;
         if (c < Kp && r < Bp) {
-            XTh[(long long)c * Bp + r] = th[threadIdx.x][i];
-            XTl[(long long)c * Bp + r] = tl[threadIdx.x][i];
+            __half oh[8], ol[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                oh[j] = th[pr * 8 + j][cc];
+                ol[j] = tl[pr * 8 + j][cc];
+            }
+            *reinterpret_cast<uint4 *>(XTh + (long long)c * Bp + r) = *reinterpret_cast<const uint4 *>(oh);
+            *reinterpret_cast<uint4 *>(XTl + (long long)c * Bp + r) = *reinterpret_cast<const uint4 *>(ol);
         }
     }
 }
@@ -1247,8 +1310,8 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     timing_end(s);
     count_launch();
     if (keep) {
-        dim3 tb(32, 8);
-        dim3 xg((g.Kp + 31) / 32, (unsigned)((Bp + 31) / 32));
+        dim3 tb(256);
+        dim3 xg((g.Kp + 63) / 64, (unsigned)((Bp + 63) / 64));
         timing_begin(TK_TRANSPOSE_X, 0.0, s);
         transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1]);
         timing_end(s);
@@ -1299,12 +1362,12 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
     const int warps = 8;
     timing_begin(TK_G_BOUND, 0.0, s);
-    g_bound_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale,
-                                                                            g.w_scale, gmax);
+    const unsigned ew_grid = (unsigned)((B + warps - 1) / warps < 148 * 8 ? (B + warps - 1) / warps : 148 * 8);
+    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax);
     timing_end(s);
     count_launch();
     timing_begin(TK_GRAD_Y, 0.0, s);
-    grad_y_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(
+    grad_y_kernel<<<ew_grid, warps * 32, 0, s>>>(
         w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
         Gs[1], S, n_seg > 1);
     timing_end(s);
