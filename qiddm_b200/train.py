@@ -73,6 +73,50 @@ def allreduce_gradients(bucket: FlatGradBucket, weights: Optional[float] = None)
     bucket.unpack()
 
 
+class DevicePrefetcher:
+    """Double-buffered host -> device input pipeline (the reference's `batch[0].to(dev)`, src/mnist_exm.py:178,
+    taken off the critical path): batch i+1 is copied from pinned host memory on a side stream while batch i is
+    being simulated.  `next(host_batch)` returns the device copy of the batch submitted by the PREVIOUS call
+    (None on the first call) and starts the copy of `host_batch`."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self.pending = None
+
+    def next(self, host_batch: Optional[torch.Tensor]):
+        cur = torch.cuda.current_stream(self.device)
+        out = None
+        if self.pending is not None:
+            j = self.pending
+            cur.wait_event(self.ready[j])          # the compute stream consumes buffer j from here on
+            out = self.bufs[j]
+        if host_batch is not None:
+            j = self.i & 1
+            self.i += 1
+            if self.bufs[j] is None or self.bufs[j].shape != host_batch.shape or self.bufs[j].dtype != host_batch.dtype:
+                self.bufs[j] = torch.empty(host_batch.shape, dtype=host_batch.dtype, device=self.device)
+            else:
+                self.stream.wait_event(self.free[j])   # the step that last read buffer j has been enqueued and finished
+            with torch.cuda.stream(self.stream):
+                self.bufs[j].copy_(host_batch, non_blocking=True)
+                self.ready[j].record(self.stream)
+            self.pending = j
+        else:
+            self.pending = None
+        return out
+
+    def release(self, batch: torch.Tensor) -> None:
+        """Call after the work that reads `batch` has been enqueued on the current stream."""
+        for j in range(2):
+            if self.bufs[j] is batch:
+                self.free[j].record(torch.cuda.current_stream(self.device))
+
+
 class DataParallelTrainer:
     """opt.zero_grad(); diff(x=x_local, T=tau); all-reduce; opt.step()  — the loop body of
     src/mnist_exm.py:175-182 with the batch sharded over ranks."""

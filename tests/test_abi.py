@@ -72,7 +72,7 @@ def test_plan_lifecycle_and_unsupported_depth(lib):
     assert p.handle.value
     del p
     with pytest.raises(L.QiddmError):
-        L.Plan(L.StageSpec(n_qubits=12, layers_per_block=400, readout=L.READ_EXPVAL_Z))
+        L.Plan(L.StageSpec(n_qubits=12, layers_per_block=800, readout=L.READ_EXPVAL_Z))
 
 
 def test_product_path_has_no_cpu_fallback():
