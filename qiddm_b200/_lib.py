@@ -48,7 +48,8 @@ EXPORTS = [
     "qiddm_qconv_forward", "qiddm_qconv_backward", "qiddm_build_unitary", "qiddm_launch_count",
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
-    "qiddm_timing_collect",
+    "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
+    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward",
 ]
 
 _lib = None
@@ -109,6 +110,14 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_gemm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_gemm_saved_bytes.restype = C.c_size_t
         lib.qiddm_gemm_saved_bytes.argtypes = [vp, i64]
+        for f in (lib.qiddm_qconv_gemm_saved_bytes, lib.qiddm_qconv_gemm_workspace_bytes):
+            f.restype = C.c_size_t
+            f.argtypes = [vp, C.POINTER(UnfoldDesc), i64]
+        lib.qiddm_qconv_gemm_forward.restype = i32
+        lib.qiddm_qconv_gemm_forward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_qconv_gemm_backward.restype = i32
+        lib.qiddm_qconv_gemm_backward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, vp, vp, vp, i64,
+                                                  i32, vp]
         lib.qiddm_timing_enable.restype = None
         lib.qiddm_timing_enable.argtypes = [i32]
         lib.qiddm_timing_collect.restype = i32
@@ -405,6 +414,55 @@ class Plan:
                                                _ptr(saved), _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
                                                self.spec.gemm_precision, self._stream(dev)), "qiddm_gemm_backward")
         return grad_in, grad_w
+
+    # ------------------------------------------------------------------ QConv on the unitary-collapse path
+    @staticmethod
+    def _out_hw(img: torch.Tensor, unfold: UnfoldDesc):
+        return (img.shape[2] + 2 * unfold.pad_h - unfold.kernel_h + 1,
+                img.shape[3] + 2 * unfold.pad_w - unfold.kernel_w + 1)
+
+    def qconv_gemm_forward(self, img: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc, save: bool = False):
+        """(N,C,H,W) -> (N,read_count,H_out,W_out); with `save` also returns the operand splits + Y for the backward."""
+        _require_cuda(img, "input")
+        col = self.gemm_prepare(weights)
+        dev = col.device
+        img = img.to(torch.float32).contiguous()
+        n = img.shape[0]
+        ho, wo = self._out_hw(img, unfold)
+        out = torch.empty((n, self.spec.read_count, ho, wo), dtype=torch.float32, device=dev)
+        saved = None
+        with torch.cuda.device(dev):
+            if save:
+                saved = torch.empty(int(self.lib.qiddm_qconv_gemm_saved_bytes(self.handle, C.byref(unfold), n)),
+                                    dtype=torch.uint8, device=dev)
+                ws = torch.empty(256, dtype=torch.uint8, device=dev)
+            else:
+                ws = torch.empty(int(self.lib.qiddm_qconv_gemm_saved_bytes(self.handle, C.byref(unfold), n)),
+                                 dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_qconv_gemm_forward(self.handle, _ptr(col), C.byref(unfold), _ptr(img), _ptr(out),
+                                                    _ptr(saved), _ptr(ws), n, self.spec.gemm_precision,
+                                                    self._stream(dev)), "qiddm_qconv_gemm_forward")
+        return (out, saved) if save else out
+
+    def qconv_gemm_backward(self, img: torch.Tensor, weights: torch.Tensor, grad_out: torch.Tensor, unfold: UnfoldDesc,
+                            need_grad_in: bool = True, need_grad_w: bool = True,
+                            saved: Optional[torch.Tensor] = None):
+        w = self._check_weights(weights)
+        col = self.gemm_prepare(weights)
+        dev = col.device
+        img = img.to(torch.float32).contiguous()
+        go = grad_out.to(torch.float32).contiguous()
+        n = img.shape[0]
+        grad_img = torch.empty_like(img) if need_grad_in else None
+        grad_w = torch.empty_like(w) if need_grad_w else None
+        with torch.cuda.device(dev):
+            ws = torch.empty(int(self.lib.qiddm_qconv_gemm_workspace_bytes(self.handle, C.byref(unfold), n)),
+                             dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_qconv_gemm_backward(self.handle, _ptr(col), C.byref(unfold), _ptr(img), _ptr(w),
+                                                     _wdtype(w), _ptr(go), _ptr(saved), _ptr(grad_img), _ptr(grad_w),
+                                                     _ptr(ws), n, self.spec.gemm_precision, self._stream(dev)),
+                  "qiddm_qconv_gemm_backward")
+        return grad_img, grad_w
 
     def build_unitary(self, weights: torch.Tensor) -> torch.Tensor:
         """Returns U as a (2^n, 2^n) complex64 tensor (the library writes U^T, row c = U|c>)."""

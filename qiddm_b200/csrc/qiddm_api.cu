@@ -397,6 +397,71 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
                          t.dim, 0, s);
 }
 
+// ---- QConv on the unitary-collapse path: the same GEMMs with the patch-unfold fused into the operand preparation,
+// probabilities written straight to NCHW, grad_out read from NCHW and the col2im of dX in one gather kernel.
+static long long unfold_patches(const qiddm_unfold_desc *u) {
+    return (long long)(u->height + 2 * u->pad_h - u->kernel_h + 1) * (u->width + 2 * u->pad_w - u->kernel_w + 1);
+}
+
+size_t qiddm_qconv_gemm_saved_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images) {
+    if (!plan || !gemm_eligible(plan) || !unfold_valid(plan, unfold) || n_images < 0) return 0;
+    return qiddm_gemm_saved_bytes(plan, n_images * unfold_patches(unfold));
+}
+
+size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images) {
+    if (!plan || !gemm_eligible(plan) || !unfold_valid(plan, unfold) || n_images < 0) return 0;
+    const long long B = n_images > 0 ? n_images * unfold_patches(unfold) : 1;
+    GateParams gp = make_params(plan, nullptr, 1);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    return gemm_backward_ws_bytes(g, B, true) + basis_ws_bytes(plan) + 256;
+}
+
+int qiddm_qconv_gemm_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
+                             const float *img, float *out, void *saved, void *workspace, int64_t n_images,
+                             int precision, qiddm_stream_t stream) {
+    if (!plan || !collapsed || !workspace || n_images < 0) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    if (!unfold_valid(plan, unfold) || (precision != 1 && precision != 3)) return QIDDM_EINVAL;
+    if (n_images == 0) return QIDDM_OK;
+    if (!img || !out) return QIDDM_EINVAL;
+    const long long B = n_images * unfold_patches(unfold);
+    if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, unfold, B);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    return gemm_forward(g, gp, collapsed, img, out, saved, workspace, B, precision, (cudaStream_t)stream);
+}
+
+int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
+                              const float *img, const void *weights, int weights_dtype, const float *grad_out,
+                              const void *saved, float *grad_img, void *grad_weights, void *workspace,
+                              int64_t n_images, int precision, qiddm_stream_t stream) {
+    if (!plan || !collapsed || !workspace || !weights || n_images < 0) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    if (!unfold_valid(plan, unfold) || (precision != 1 && precision != 3)) return QIDDM_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_images == 0) {
+        if (grad_weights) {
+            const size_t esz = weights_dtype == QIDDM_DTYPE_F64 ? 8 : 4;
+            cudaError_t e = cudaMemsetAsync(grad_weights, 0, (size_t)plan->n_rot * 3 * esz, s);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return QIDDM_OK;
+    }
+    if (!img || !grad_out) return QIDDM_EINVAL;
+    const long long B = n_images * unfold_patches(unfold);
+    if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, unfold, B);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    float *gut = nullptr;
+    int rc = gemm_backward(g, gp, collapsed, img, grad_out, saved, grad_img, &gut, workspace, B, precision, s);
+    if (rc != QIDDM_OK) return rc;
+    if (!grad_weights) return QIDDM_OK;
+    qiddm_plan t = basis_plan(plan);
+    char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, B, true));
+    return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
+                         t.dim, 0, s);
+}
+
 void qiddm_timing_enable(int enable) {
     std::lock_guard<std::mutex> lk(qiddm::g_tmutex);
     qiddm::g_timing = enable != 0;

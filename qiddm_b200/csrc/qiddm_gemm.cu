@@ -203,6 +203,7 @@ struct GemmParams {
     const unsigned int *gmax_bits;
     float add_offset;
     int dbg_pfd, dbg_nostore;   // tuning knobs (QIDDM_GEMM_PFD, QIDDM_GEMM_NOSTORE)
+    int out_P;               // EPI_PROBS, QConv: > 0 -> row = (image b, patch r), out[(b * n_out + m) * out_P + r] (NCHW)
     // pair kernel: epilogue through shared memory + TMA stores (fp32 boxes of 32 rows)
     int tma_epi;
     alignas(64) CUtensorMap y_map;      // EPI_PROBS: Y (M, N), box 16 x 32, SWIZZLE_64B
@@ -255,6 +256,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
         }
         if (p.out == nullptr) return;
         const int m0 = col >> 1;
+        if (p.out_P > 0) {      // QConv: consecutive rows (patches) of one image are consecutive addresses per channel
+            const int b = row / p.out_P, r = row - b * p.out_P;
+            float *dst = p.out + ((long long)b * p.n_out + m0) * p.out_P + r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (m0 + j < p.n_out) dst[(long long)j * p.out_P] = o[j];
+            return;
+        }
         float *dst = p.out + (long long)row * p.ldo + m0;
         if (m0 + 8 <= p.n_out && ((p.ldo & 3) == 0)) {
             reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -266,6 +275,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
         }
     } else if (p.epi == EPI_DX) {
         float *dst = p.out + (long long)row * p.ldo + col;
+        if (p.dx_x == nullptr) {       // QConv: plain rows; the normalisation term is added by fold_rows_kernel
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col + j < p.N) dst[j] = v[j] * dx_a;
+            return;
+        }
         const float *xs = p.dx_x + (long long)row * p.ldo + col;
         if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
             float4 xv[4];
@@ -308,7 +323,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams &p, uint32_t tmem
     float dx_a = 0.f, dx_b = 0.f;
     if (p.epi == EPI_DX && row < p.M) {
         dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
-        dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+        dx_b = p.dx_x != nullptr ? -2.f * p.row_scale[row] * p.dx_S[row] : 0.f;
     }
     uint32_t ra[16], rb[16];
     if (cbeg < cend) tc_ld16_issue(taddr + cbeg, ra);
@@ -504,7 +519,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
     float dx_a = 0.f, dx_b = 0.f;
     if (p.epi == EPI_DX && row_ok) {
         dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
-        dx_b = -2.f * p.row_scale[row] * p.dx_S[row];
+        dx_b = p.dx_x != nullptr ? -2.f * p.row_scale[row] * p.dx_S[row] : 0.f;
     }
     const uint32_t sw = (uint32_t)((lane >> 1) & 3);       // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
     auto chunk = [&](const uint32_t (&r)[16], int c0) {
@@ -538,7 +553,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
         } else {   // EPI_DX
             const float *xs = p.dx_x + (long long)row * p.ldo + col;
             float x[16];
-            if (row_ok && col + 16 <= p.N) {
+            if (p.dx_x == nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            } else if (row_ok && col + 16 <= p.N) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 t = __ldg(reinterpret_cast<const float4 *>(xs) + j);
@@ -787,15 +805,29 @@ __device__ __forceinline__ void split_act(float v, __half &hi, __half &lo) {
 // x (B,F) fp32 -> Xh/Xl (B,Kp) fp16 (hi, lo*2^11) and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).  One warp per row.
 // Column F (when the state has constant pad rows) is a column of ones: it meets zero weights in the forward
 // and dX GEMMs and yields sum_b G[b,n] (the pad rows of dW) in the dW GEMM.
+struct UnfoldGeom {      // fused patch-unfold (QConv, nn/qconv.py:76-77): row = (image, y, x), feature = (ch, ky, kx)
+    int on, C, H, W, kh, kw, ph, pw, Hout, Wout;
+};
+__device__ __forceinline__ float load_feature(const float *x, long long row, int F, int c, const UnfoldGeom &u) {
+    if (!u.on) return __ldg(x + row * F + c);
+    const int P = u.Hout * u.Wout, kk = u.kh * u.kw;
+    const int b = (int)(row / P), r = (int)(row - (long long)b * P);
+    const int y = r / u.Wout, xx = r - y * u.Wout;
+    const int ch = c / kk, q = c - ch * kk;
+    const int ky = q / u.kw, kx = q - ky * u.kw;
+    const int iy = y + ky - u.ph, ix = xx + kx - u.pw;
+    if (iy < 0 || iy >= u.H || ix < 0 || ix >= u.W) return 0.f;        // zero padding of torch.nn.Unfold
+    return __ldg(x + (((long long)b * u.C + ch) * u.H + iy) * u.W + ix);
+}
 __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_pad, float add_offset, float pad,
-                              __half *Xh, __half *Xl, float *inv_n2, int want_lo) {
+                              __half *Xh, __half *Xl, float *inv_n2, int want_lo, const UnfoldGeom u) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
     float ss = 0.f;
     for (int c = lane; c < Kp; c += 32) {
         float f = 0.f;
-        if (c < F) f = __ldg(x + row * F + c) + add_offset;
+        if (c < F) f = load_feature(x, row, F, c, u) + add_offset;
         __half hi, lo;
         split_act((c == F && n_pad > 0) ? 1.f : f, hi, lo);
         Xh[row * Kp + c] = hi;
@@ -807,6 +839,36 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
     if (lane == 0) {
         ss += (float)n_pad * pad * pad;
         inv_n2[row] = ss > 0.f ? 1.0f / ss : 0.f;
+    }
+}
+
+// QConv col2im of the dX rows with the normalisation term of the amplitude embedding, gather form (one thread per
+// image element, no atomics):  grad_img[b,ch,iy,ix] = sum_{(ky,kx): patch p=(b, iy-ky+ph, ix-kx+pw) exists}
+//     dXrows[p][(ch,ky,kx)] - 2 (img + add_offset) inv_n2[p] S[p]
+__global__ void __launch_bounds__(256) fold_rows_kernel(const float *dx_rows, int ldx, const float *img, const float *inv_n2,
+                                                        const float *S, long long n_elems, float add_offset,
+                                                        const UnfoldGeom u, float *grad_img) {
+    const int P = u.Hout * u.Wout, kk = u.kh * u.kw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % u.W);
+        long long t = i / u.W;
+        const int iy = (int)(t % u.H);
+        t /= u.H;
+        const int ch = (int)(t % u.C);
+        const long long b = t / u.C;
+        const float f = __ldg(img + i) + add_offset;
+        float acc = 0.f;
+        for (int ky = 0; ky < u.kh; ++ky) {
+            const int y = iy - ky + u.ph;
+            if (y < 0 || y >= u.Hout) continue;
+            for (int kx = 0; kx < u.kw; ++kx) {
+                const int xx = ix - kx + u.pw;
+                if (xx < 0 || xx >= u.Wout) continue;
+                const long long pr = b * P + (long long)y * u.Wout + xx;
+                acc += __ldg(dx_rows + pr * ldx + ch * kk + ky * u.kw + kx) - 2.f * f * __ldg(inv_n2 + pr) * __ldg(S + pr);
+            }
+        }
+        grad_img[i] = acc;
     }
 }
 
@@ -856,16 +918,19 @@ __global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half
 // Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
 // |G[b,n]| = 2 |g| scale inv_n2 |Y'| <= 2 max_m|g[b,m]| * scale * sqrt(inv_n2[b]) * w_scale.
 __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out,
-                                                      float scale, float w_scale, unsigned int *gmax_bits) {
+                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const bool vec = (n_out & 3) == 0 && ((uintptr_t)go & 15) == 0;
+    const bool vec = go_P == 0 && (n_out & 3) == 0 && ((uintptr_t)go & 15) == 0;
     float best = 0.f;
     for (long long row = warp0; row < B; row += nwarps) {
         const float *g = go + row * n_out;
         float mx = 0.f;
-        if (vec) {
+        if (go_P > 0) {        // QConv: grad_out is NCHW, element (row, m) at ((b * n_out + m) * P + r)
+            const long long b = row / go_P, r = row - b * go_P;
+            for (int m = lane; m < n_out; m += 32) mx = fmaxf(mx, fabsf(__ldg(go + (b * n_out + m) * go_P + r)));
+        } else if (vec) {
             for (int i = lane; i < (n_out >> 2); i += 32) {
                 const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
                 mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
@@ -886,13 +951,14 @@ __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const flo
 __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float *go, const float *inv_n2, long long B,
                                                      int N, int Np, int n_out, float scale, int clamp, float lo,
                                                      float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl,
-                                                     float *S, int want_lo) {
+                                                     float *S, int want_lo, int go_P) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const float gsc = g_scale_from_max(*gmax_bits);
     // 4 outputs (8 columns of Y / G) per lane and iteration when everything is 16-byte aligned
-    const bool vec = (n_out & 3) == 0 && Np == N && (((uintptr_t)Y | (uintptr_t)go | (uintptr_t)Gh | (uintptr_t)Gl) & 15) == 0;
+    const bool vec = go_P == 0 && (n_out & 3) == 0 && Np == N &&
+                     (((uintptr_t)Y | (uintptr_t)go | (uintptr_t)Gh | (uintptr_t)Gl) & 15) == 0;
     for (long long r = warp0; r < B; r += nwarps) {
         const float in2 = inv_n2[r];
         const float k0 = scale * in2, k1 = 2.f * scale * in2 * gsc;
@@ -933,7 +999,8 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
                     const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + 2 * m);
                     const float outv = k0 * (y.x * y.x + y.y * y.y);
                     const bool pass = !clamp || (outv >= lo && outv <= hi);
-                    const float g = pass ? __ldg(go + r * n_out + m) : 0.f;
+                    const long long gi = go_P > 0 ? ((r / go_P) * n_out + m) * go_P + (r % go_P) : r * n_out + m;
+                    const float g = pass ? __ldg(go + gi) : 0.f;
                     gre = k1 * g * y.x;
                     gim = k1 * g * y.y;
                     s_part += g * outv;
@@ -1116,7 +1183,7 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         p.tma_epi = 0;
         static int tma_epi_on = -1;
         if (tma_epi_on < 0) { const char *ev = getenv("QIDDM_GEMM_TMA_EPI"); tma_epi_on = ev ? atoi(ev) : 1; }
-        if (tma_epi_on && k_splits == 1 && (p.epi == EPI_PROBS || p.epi == EPI_DX)) {
+        if (tma_epi_on && k_splits == 1 && p.out_P == 0 && (p.epi == EPI_PROBS || p.epi == EPI_DX)) {
             bool ok = true;
             if (p.epi == EPI_PROBS) {
                 if (p.y_out) ok = ok && make_map_ex(&p.y_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.y_out, M, N, N, 16, 32,
@@ -1262,8 +1329,16 @@ size_t gemm_forward_ws_bytes(const GemmShape &g, long long B) {
     return 2 * al((size_t)B * g.Kp * 2) + al((size_t)B * 4);
 }
 
-size_t gemm_backward_ws_bytes(const GemmShape &g, long long B) {
+static UnfoldGeom unfold_geom(const GateParams &gp) {
+    UnfoldGeom u;
+    u.on = gp.unfold; u.C = gp.C; u.H = gp.H; u.W = gp.W; u.kh = gp.kh; u.kw = gp.kw; u.ph = gp.ph; u.pw = gp.pw;
+    u.Hout = gp.Hout; u.Wout = gp.Wout;
+    return u;
+}
+
+size_t gemm_backward_ws_bytes(const GemmShape &g, long long B, bool unfold) {
     size_t b = gemm_saved_bytes(g, B);                // used when the forward did not save
+    if (unfold) b += al((size_t)B * g.F * 4);         // dX rows before the col2im
     b += al((size_t)B * 4) + al(256);                 // S, gmax
     b += 2 * al((size_t)B * g.Np * 2);                // G splits (row-major)
     b += al((size_t)g.N * g.Fx * 4);                  // dWT (+ ones column)
@@ -1306,7 +1381,8 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     const int warps = 8;
     timing_begin(TK_PREP_X, 0.0, s);
     prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(
-        x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1);
+        x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
+        unfold_geom(gp));
     timing_end(s);
     count_launch();
     if (keep) {
@@ -1326,6 +1402,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     p.post_scale = gp.post_scale / (g.w_scale * g.w_scale);
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
     p.n_out = g.n_out;
+    p.out_P = gp.unfold ? gp.Hout * gp.Wout : 0;    // QConv: probabilities go straight to the NCHW output
     ActOperand A{w.X[0], w.X[1]};
     WgtOperand Bm{v.Wn[0], v.Wn[1]};
     timing_set_gemm_kind(TK_GEMM_FWD);
@@ -1353,8 +1430,10 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     __half *Gs[2];
     for (int i = 0; i < 2; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
     float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.Fx * 4);
-    float *gUT = reinterpret_cast<float *>(p8);
+    float *gUT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.A * g.A * 8);
     *gut_out = gUT;
+    float *dx_rows = reinterpret_cast<float *>(p8);   // QConv only (gemm_backward_ws_bytes(.., unfold = true))
+    const int go_P = gp.unfold ? gp.Hout * gp.Wout : 0;
 
     cudaError_t e;
     const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
@@ -1363,13 +1442,13 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     const int warps = 8;
     timing_begin(TK_G_BOUND, 0.0, s);
     const unsigned ew_grid = (unsigned)((B + warps - 1) / warps < 148 * 8 ? (B + warps - 1) / warps : 148 * 8);
-    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax);
+    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax, go_P);
     timing_end(s);
     count_launch();
     timing_begin(TK_GRAD_Y, 0.0, s);
     grad_y_kernel<<<ew_grid, warps * 32, 0, s>>>(
         w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
-        Gs[1], S, n_seg > 1);
+        Gs[1], S, n_seg > 1, go_P);
     timing_end(s);
     count_launch();
     GemmParams p;
@@ -1378,12 +1457,22 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     // (2) dX = G W^T / gsc - 2 f inv_n2 S   (normalisation term fused in the epilogue)
     if (grad_in != nullptr) {
         memset(&p, 0, sizeof(p));
-        p.epi = EPI_DX; p.out = grad_in; p.ldo = g.F; p.out_scale = 1.f;
-        p.row_scale = w.inv_n2; p.dx_S = S; p.dx_x = x; p.gmax_bits = gmax; p.add_offset = gp.add_offset;
+        p.epi = EPI_DX; p.out = gp.unfold ? dx_rows : grad_in; p.ldo = g.F; p.out_scale = 1.f;
+        p.row_scale = w.inv_n2; p.dx_S = S; p.dx_x = gp.unfold ? nullptr : x; p.gmax_bits = gmax;
+        p.add_offset = gp.add_offset;
         WgtOperand Wt{v.Wt[0], v.Wt[1]};
         timing_set_gemm_kind(TK_GEMM_DX);
         rc = run_gemm(Go, B, g.Np, g.Np, false, Wt, g.F, g.Np, (int)B, g.F, g.N, n_seg, 1, p, s);
         if (rc != QIDDM_OK) return rc;
+        if (gp.unfold) {     // col2im + normalisation term: image gradient in NCHW
+            const long long n_elems = (B / go_P) * gp.C * gp.H * gp.W;
+            const unsigned fg = (unsigned)((n_elems + 255) / 256 < 148 * 16 ? (n_elems + 255) / 256 : 148 * 16);
+            timing_begin(TK_FINISH_DX, 0.0, s);
+            fold_rows_kernel<<<fg, 256, 0, s>>>(dx_rows, g.F, x, w.inv_n2, S, n_elems, gp.add_offset, unfold_geom(gp),
+                                                grad_in);
+            timing_end(s);
+            count_launch();
+        }
     }
     // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]: G consumed row-major as an MN-major operand, split-K over the batch
     if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.Fx * 4, s)) != cudaSuccess) return (int)e;

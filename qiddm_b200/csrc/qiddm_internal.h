@@ -64,7 +64,7 @@ float *gemm_collapsed_ut(const GemmShape &g, void *collapsed);
 int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapsed, cudaStream_t s);
 size_t gemm_saved_bytes(const GemmShape &g, long long B);
 size_t gemm_forward_ws_bytes(const GemmShape &g, long long B);
-size_t gemm_backward_ws_bytes(const GemmShape &g, long long B);
+size_t gemm_backward_ws_bytes(const GemmShape &g, long long B, bool unfold = false);
 int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x, float *out,
                  void *saved, void *ws, long long B, int n_seg, cudaStream_t s);
 int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,

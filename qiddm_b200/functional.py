@@ -57,16 +57,32 @@ class _QConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan: Plan, img: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc):
         ctx.plan, ctx.unfold = plan, unfold
-        out = plan.qconv_forward(img.detach(), weights.detach(), unfold)
+        ho = img.shape[2] + 2 * unfold.pad_h - unfold.kernel_h + 1
+        wo = img.shape[3] + 2 * unfold.pad_w - unfold.kernel_w + 1
+        ctx.gemm = plan.use_gemm(img.shape[0] * ho * wo)       # circuit instances = patches
+        ctx.gemm_saved = None
+        if ctx.gemm:
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                out, ctx.gemm_saved = plan.qconv_gemm_forward(img.detach(), weights, unfold, save=True)
+            else:
+                out = plan.qconv_gemm_forward(img.detach(), weights, unfold)
+        else:
+            out = plan.qconv_forward(img.detach(), weights.detach(), unfold)
         ctx.save_for_backward(img, weights)
         return out.to(img.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
         img, weights = ctx.saved_tensors
-        gi, gw = ctx.plan.qconv_backward(img, weights, grad_out, ctx.unfold,
-                                         need_grad_in=ctx.needs_input_grad[1],
-                                         need_grad_w=ctx.needs_input_grad[2])
+        if ctx.gemm:
+            gi, gw = ctx.plan.qconv_gemm_backward(img, weights, grad_out, ctx.unfold,
+                                                  need_grad_in=ctx.needs_input_grad[1],
+                                                  need_grad_w=ctx.needs_input_grad[2], saved=ctx.gemm_saved)
+            ctx.gemm_saved = None
+        else:
+            gi, gw = ctx.plan.qconv_backward(img, weights, grad_out, ctx.unfold,
+                                             need_grad_in=ctx.needs_input_grad[1],
+                                             need_grad_w=ctx.needs_input_grad[2])
         if gi is not None:
             gi = gi.to(img.dtype)
         return None, gi, (gw.view_as(weights) if gw is not None else None), None

@@ -3,8 +3,10 @@
 Forward semantics = the INTENDED forward of `_QConv2d_FAST` (the reference lost the
 `x = self.qnode(x)` line between `:78` and `:79`): unfold -> +0.1 -> AmplitudeEmbedding(pad_with=0.5,
 normalize) -> StronglyEntanglingLayers(pi*tanh(W)) -> probs -> *2^n/2 -> clamp(0,1) -> [::2] ->
-[:out_channels].  Patch-unfold, post-processing and the NCHW re-layout are fused into one sm_100a
-kernel (qiddm_qconv_forward); backward is the adjoint kernel with a fused col2im."""
+[:out_channels].  Two B200 paths behind the same module (chosen per call from the patch count, `self.path`):
+gate by gate (qiddm_qconv_forward: unfold, post-processing and NCHW re-layout fused into the gate kernel, adjoint
+backward with fused col2im) or unitary collapse (qiddm_qconv_gemm_forward: the SEL block collapsed once per
+weight version, every patch one row of a tcgen05 GEMM with the unfold fused into the operand preparation)."""
 from __future__ import annotations
 
 import math
@@ -36,6 +38,7 @@ class _QConv2d_FAST(torch.nn.Module):
         weights = torch.rand((qdepth, self.wires, 3), dtype=torch.double) * math.pi - math.pi / 2
         self.weights = torch.nn.Parameter(weights)
         self.qdev = "qiddm_b200:sm_100a"
+        self.path = L.PATH_AUTO        # AUTO: unitary-collapse tcgen05 GEMM once patches >= 2 * 2**wires, else gate by gate
         self.qnode = self._circuit
         self.sample_qnode = None
         self.sample_matrix = None
@@ -47,7 +50,8 @@ class _QConv2d_FAST(torch.nn.Module):
             n_features=self.kernel_size[0] * self.kernel_size[1] * self.in_channels, pad_value=0.5,
             add_offset=0.0 if full else 0.1, imprimitive=L.IMP_CNOT, remap=L.REMAP_PI_TANH,
             readout=L.READ_PROBS, read_count=(1 << n) if full else self.out_channels,
-            read_stride=1 if full else 2, post_scale=1.0 if full else 0.5 * (1 << n), clamp=not full)
+            read_stride=1 if full else 2, post_scale=1.0 if full else 0.5 * (1 << n), clamp=not full,
+            path=L.PATH_GATE if full else self.path)
 
     def _circuit(self, features):
         """(P, F) patch rows -> un-scaled probs (P, 2**wires): what the reference QNode returns (:51-56)."""

@@ -128,6 +128,42 @@ def test_qconv2d_fused_unfold_matches_oracle(cfg):
     assert rel_to_max(xd.grad, xr.grad) <= GTOL
 
 
+@pytest.mark.parametrize("cfg", [(1, 8, 3, 1, 14, 14), (8, 8, 3, 1, 9, 10), (16, 8, 1, 0, 7, 7), (8, 16, 3, 1, 8, 9),
+                                 (32, 32, 3, 1, 7, 7), (8, 1, 1, 0, 12, 12), (3, 5, (3, 2), (1, 0), 9, 11)])
+def test_qconv2d_unitary_collapse_path_matches_oracle_and_gate_path(cfg):
+    """QConv2d on the tcgen05 GEMM path (fused unfold, NCHW epilogue, gather col2im) vs the oracle and vs the
+    gate-by-gate path.  GEMM-path bounds: 1e-5 outputs, 1e-4 gradients (rel-to-max)."""
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import nn
+    cin, cout, k, pad, H, Wd = cfg
+    torch.manual_seed(11)
+    m = nn.QConv2d(cin, cout, kernel_size=k, padding=pad, qdepth=3).cuda()
+    x = torch.rand(5, cin, H, Wd, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    Wr = m.weights.detach().cpu().clone().requires_grad_(True)
+    ref = O.qconv_forward(xr, Wr, cout, m.kernel_size, m.padding)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    res = {}
+    for name, path in (("gemm", L.PATH_GEMM), ("gate", L.PATH_GATE)):
+        m.path = path
+        m.weights.grad = None
+        xd = x.cuda().requires_grad_(True)
+        n0 = L.launch_count()
+        out = m(xd)
+        assert L.launch_count() > n0
+        (out * g.cuda()).sum().backward()
+        res[name] = (out.detach(), m.weights.grad.clone(), xd.grad.clone())
+        assert rel_to_max(out, ref) <= TOL, name
+        assert rel_to_max(m.weights.grad, Wr.grad) <= 1e-4, name
+        assert rel_to_max(xd.grad, xr.grad) <= 1e-4, name
+    assert rel_to_max(res["gemm"][0], res["gate"][0]) <= 2e-5
+    # inference forward (no saved state) gives the same result
+    m.path = L.PATH_GEMM
+    with torch.no_grad():
+        assert rel_to_max(m(x.cuda()), res["gemm"][0]) <= 1e-6
+
+
 def test_unet_undirected_quantum_runs_and_trains():
     """UNetUndirected(3, 8, qdepth) with QConv2d children (nn/unet.py:119-160): shapes + finite grads."""
     from qiddm_b200 import nn
