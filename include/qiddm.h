@@ -169,6 +169,17 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
 void qiddm_timing_enable(int enable);
 int  qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *launches_by_kind);
 
+/* On-device PCA support (replaces the sklearn `PCA.fit_transform` host round trip of nn/qdense.py:456, :1429):
+ * eigen-decomposition of a symmetric m x m float64 matrix (the Gram matrix of the centred batch rows), one CTA, parallel
+ * cyclic Jacobi.  evals[m] in DESCENDING order, evecs (m x m row-major) column j = eigenvector of evals[j].
+ * m <= qiddm_sym_eigh_max_dim(); asynchronous on `stream`, no status read-back (CUDA-graph capturable). */
+int qiddm_sym_eigh_max_dim(void);
+int qiddm_sym_eigh_f64(const double *a, int m, double *evals, double *evecs, qiddm_stream_t stream);
+
+/* Id of the CUDA-graph capture `stream` is currently part of, 0 when it is not capturing (lets the host side keep
+ * per-capture caches of the collapsed operator). */
+int64_t qiddm_stream_capture_id(qiddm_stream_t stream);
+
 /* Kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
 int64_t qiddm_launch_count(void);
 

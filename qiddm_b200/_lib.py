@@ -49,7 +49,8 @@ EXPORTS = [
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
-    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward",
+    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id",
+    "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64",
 ]
 
 _lib = None
@@ -96,6 +97,11 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_build_unitary.restype = i32
         lib.qiddm_build_unitary.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.qiddm_launch_count.restype = i64
+        lib.qiddm_sym_eigh_max_dim.restype = i32
+        lib.qiddm_sym_eigh_f64.restype = i32
+        lib.qiddm_sym_eigh_f64.argtypes = [vp, i32, vp, vp, vp]
+        lib.qiddm_stream_capture_id.restype = i64
+        lib.qiddm_stream_capture_id.argtypes = [vp]
         lib.qiddm_gemm_supported.restype = i32
         lib.qiddm_gemm_supported.argtypes = [vp]
         lib.qiddm_gemm_collapsed_bytes.restype = C.c_size_t
@@ -151,6 +157,25 @@ def timing_collect() -> dict:
     ms, wk, n = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int64 * 16)()
     check(load_library().qiddm_timing_collect(ms, wk, n), "qiddm_timing_collect")
     return {k: {"ms": ms[i], "work": wk[i], "launches": int(n[i])} for i, k in enumerate(TIMING_KINDS)}
+
+
+def sym_eigh(a: torch.Tensor):
+    """Eigen-decomposition of a symmetric float64 CUDA matrix by the library's single-CTA Jacobi kernel:
+    (evals descending (m,), evecs (m, m) with matching columns).  Asynchronous, CUDA-graph capturable."""
+    _require_cuda(a, "matrix")
+    lib = load_library()
+    m = a.shape[0]
+    if a.dim() != 2 or a.shape[1] != m or a.dtype != torch.float64:
+        raise QiddmError("sym_eigh needs a square float64 matrix")
+    if m > lib.qiddm_sym_eigh_max_dim():
+        raise QiddmError(f"sym_eigh supports m <= {lib.qiddm_sym_eigh_max_dim()}, got {m}")
+    a = a.contiguous()
+    evals = torch.empty(m, dtype=torch.float64, device=a.device)
+    evecs = torch.empty((m, m), dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.qiddm_sym_eigh_f64(_ptr(a), m, _ptr(evals), _ptr(evecs),
+                                     C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)), "qiddm_sym_eigh_f64")
+    return evals, evecs
 
 
 @dataclass(frozen=True)
@@ -360,15 +385,24 @@ class Plan:
         base = weights._base if weights._base is not None else weights
         key = (weights.storage_offset(), weights.numel(), weights._version, w.data_ptr())
         cached = getattr(self, "_collapsed", None)
+        # under CUDA-graph capture the collapse must be part of the graph (replays do not bump `_version`), and the
+        # buffer belongs to the graph's pool: neither read nor update the eager cache
+        dev = w.device
+        capture = int(self.lib.qiddm_stream_capture_id(self._stream(dev)))
+        if capture:
+            key = key + (capture,)
+            cached = getattr(self, "_collapsed_capture", None)
         if cached is not None and cached[0] is base and cached[1] == key:
             return cached[2]
-        dev = w.device
         buf = torch.empty(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
         ws = self._workspace(self.spec.dim, dev)
         with torch.cuda.device(dev):
             check(self.lib.qiddm_gemm_prepare(self.handle, _ptr(w), _wdtype(w), _ptr(buf), _ptr(ws),
                                               self._stream(dev)), "qiddm_gemm_prepare")
-        self._collapsed = (base, key, buf)
+        if capture:
+            self._collapsed_capture = (base, key, buf)
+        else:
+            self._collapsed = (base, key, buf)
         return buf
 
     def _gemm_ws(self, batch, dev):

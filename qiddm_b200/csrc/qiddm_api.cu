@@ -495,6 +495,26 @@ int qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *laun
     return rc;
 }
 
+int qiddm_sym_eigh_max_dim(void) {
+    int m = 1;
+    while (qiddm::eigh_smem_bytes(m + 1) <= 227 * 1024) ++m;
+    return m;
+}
+
+int qiddm_sym_eigh_f64(const double *a, int m, double *evals, double *evecs, qiddm_stream_t stream) {
+    return qiddm::sym_eigh_f64(a, m, evals, evecs, (cudaStream_t)stream);
+}
+
+int64_t qiddm_stream_capture_id(qiddm_stream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo((cudaStream_t)stream, &st, &id) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return st == cudaStreamCaptureStatusActive ? (int64_t)id : 0;
+}
+
 int64_t qiddm_launch_count(void) { return (int64_t)qiddm::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -71,4 +71,8 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
                   const float *grad_out, const void *saved, float *grad_in, float **gut_out, void *ws, long long B,
                   int n_seg, cudaStream_t s);
 
+// qiddm_pca.cu — single-CTA Jacobi eigensolver (float64) for the on-device PCA-in-forward
+size_t eigh_smem_bytes(int m);
+int sym_eigh_f64(const double *A, int m, double *evals, double *evecs, cudaStream_t s);
+
 }  // namespace qiddm

@@ -18,6 +18,7 @@ Deliberate deviations:
 from __future__ import annotations
 
 import math
+import os
 import pickle
 
 import einops
@@ -26,19 +27,34 @@ import torch.nn as nn
 
 from .. import _lib as L
 from ..functional import run_stage
+from ..pca import DevicePCA
 
 QDEV_NAME = "qiddm_b200:sm_100a"
 
 
-def _pca_fit_transform(pca, x: torch.Tensor):
-    """The reference re-fits sklearn PCA on every forward call on the current batch
-    (nn/qdense.py:456, :1429).  Kept verbatim: host round-trip, outside the kernel."""
-    return pca.fit_transform(x.detach().cpu().numpy())
+# The reference re-fits sklearn PCA on every forward call on the current batch through a numpy round trip
+# (nn/qdense.py:456, :1429).  Default here: the same per-call PCA ON THE DEVICE (qiddm_b200.pca.DevicePCA,
+# exact solver + U-based sign convention of the reference's scikit-learn 1.1.3, CUDA-graph capturable).
+# QIDDM_PCA=host (or `module.pca = sklearn.decomposition.PCA(k)`) keeps the host sklearn round trip.
+PCA_ON_DEVICE = os.environ.get("QIDDM_PCA", "device").lower() != "host"
 
 
 def _make_pca(n_components):
+    if PCA_ON_DEVICE:
+        return DevicePCA(n_components)
     from sklearn.decomposition import PCA
     return PCA(n_components=n_components)
+
+
+def _pca_call(pca, method: str, x: torch.Tensor) -> torch.Tensor:
+    """pca.<method>(x) as a float64 tensor on x.device (no gradient flows through the PCA, as in the reference)."""
+    if isinstance(pca, DevicePCA):
+        return getattr(pca, method)(x.detach())
+    return torch.as_tensor(getattr(pca, method)(x.detach().cpu().numpy()), dtype=torch.float64).to(x.device)
+
+
+def _pca_fit_transform(pca, x: torch.Tensor) -> torch.Tensor:
+    return _pca_call(pca, "fit_transform", x)
 
 
 def _check_noise(add_noise, allow_phase: bool):
@@ -298,7 +314,7 @@ class _DifferNBase(nn.Module):
         if self._reduce == "pca":
             flat = x.reshape(b, -1)
             a = _pca_fit_transform(self.pca, flat)
-            return torch.tensor(a, dtype=torch.float32).to(W.device)
+            return a.to(torch.float32).to(W.device)
         if self._reduce == "conv":
             a = self.conv_layer(x)
             return a.view(b, n, -1).mean(dim=2)
@@ -452,7 +468,7 @@ class _QIDDM_A_differN(_SaveLoadMixin, _DifferNBase):
     def _angles(self, x):
         b = x.shape[0]
         a = _pca_fit_transform(self.pca, x.reshape(b, -1))
-        return torch.tensor(a).to(x.device).to(x.dtype)
+        return a.to(x.device).to(x.dtype)
 
     def __repr__(self):
         return f"QIDDM(qlayer={self.spectrum_layer}, features={self.hidden_features}, N={self.N})"
@@ -508,7 +524,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
         if self._reduce == "pca":
             ref = self.linear_up.weight if hasattr(self, "linear_up") else self.weights1
             a = _pca_fit_transform(self.pca, x.reshape(b, -1))
-            return torch.tensor(a).to(ref.device).to(ref.dtype)
+            return a.to(ref.device).to(ref.dtype)
         if self._reduce == "conv":
             return self.conv_layer(x).view(b, self.hidden_features, -1).mean(dim=2)
         return self.linear_down(x.reshape(b, -1).to(self.linear_down.weight.dtype))
@@ -528,8 +544,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
         if self._restore == "linear":
             out = self.linear_up(a.to(self.linear_up.weight.dtype))
         else:
-            out = torch.tensor(self.pca.inverse_transform(a.detach().cpu().numpy()), device=x.device, dtype=x.dtype,
-                               requires_grad=True)
+            out = _pca_call(self.pca, "inverse_transform", a).to(x.dtype).requires_grad_(True)
         return out.view(b, c, w, h)
 
     def __repr__(self):
@@ -691,15 +706,13 @@ class QIDDM_PP_old(nn.Module):
         x = x.view(b, -1)
         if self.pca is None:
             self.pca = _make_pca(2 * self.hidden_features)
-            self.pca.fit(x.detach().cpu().numpy())
-        a = torch.tensor(self.pca.transform(x.detach().cpu().numpy()), device=x.device, dtype=x.dtype,
-                         requires_grad=True)
+            _pca_call(self.pca, "fit_transform", x)
+        a = _pca_call(self.pca, "transform", x).to(x.dtype).requires_grad_(True)
         a = self.linear_down(self.batch_norm(a))
         for n in range(self.N):
             a = self._circuit(a, self.weights1[n]).detach().to(x.dtype)
         a = self.linear_up(a).view(b, -1)
-        out = torch.tensor(self.pca.inverse_transform(a.detach().cpu().numpy()), device=x.device, dtype=x.dtype,
-                           requires_grad=True)
+        out = _pca_call(self.pca, "inverse_transform", a).to(x.dtype).requires_grad_(True)
         return out.view(b, c, w, h)
 
     def __repr__(self):

@@ -8,6 +8,7 @@ packed into ONE flat bucket (circuit weights <= 2.2 k + classical <= 30 k floats
 (NCCL over NVLink on GPUs, gloo on CPU for tests) and averaged.  No collective touches the data path."""
 from __future__ import annotations
 
+import copy
 from typing import Iterable, List, Optional
 
 import torch
@@ -149,3 +150,109 @@ class DataParallelTrainer:
         allreduce_gradients(self.bucket, weights=w)
         self.opt.step()
         return loss.detach()
+
+
+class GraphedTrainStep:
+    """The loop body of src/mnist_exm.py:175-182 (`opt.zero_grad(); diff(x=x, T=tau); opt.step()`) captured ONCE in a
+    CUDA graph and replayed per batch: at the reference batch sizes (batch 1, tau 10 -> 10 circuit
+    instances) the step is ~100 dependent kernel launches, so launch latency, not arithmetic, bounds it.
+
+    * inputs are copied into a static device buffer; the noise ladder's RNG draw, the net, the MSE, the backward
+      (incl. the adjoint gate kernels / the unitary-collapse GEMMs), the optional flat-bucket all-reduce and Adam
+      (`capturable=True`) all live inside the graph;
+    * models with a host round trip in forward (sklearn PCA) cannot be captured: use `pca_on_device`.
+    """
+
+    def __init__(self, diff: torch.nn.Module, optimizer: torch.optim.Optimizer, tau: int, example_x: torch.Tensor,
+                 warmup: int = 3, allreduce: bool = False):
+        if not example_x.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors (no CPU path)")
+        for gparam in optimizer.param_groups:
+            if not gparam.get("capturable", False):
+                raise RuntimeError("the optimizer must be built with capturable=True to live inside a CUDA graph")
+        self.diff, self.opt, self.tau = diff, optimizer, tau
+        self.x = example_x.clone()
+        self.bucket = FlatGradBucket(diff.parameters()) if allreduce else None
+        self.graph = torch.cuda.CUDAGraph()
+        diff.train()
+        # warm-up steps (lazy initialisation of cuBLAS / allocator pools / optimizer state) must not count as training:
+        # parameters, buffers and optimizer state are restored afterwards, so the first replay is the first step
+        model_state = copy.deepcopy(diff.state_dict())
+        opt_state = copy.deepcopy(optimizer.state_dict())
+        side = torch.cuda.Stream(example_x.device)
+        side.wait_stream(torch.cuda.current_stream(example_x.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._body()
+        torch.cuda.current_stream(example_x.device).wait_stream(side)
+        torch.cuda.synchronize(example_x.device)
+        had_state = len(opt_state["state"]) > 0
+        with torch.no_grad():
+            diff.load_state_dict(model_state)              # in place: the parameter tensors stay the same objects
+            if had_state:
+                optimizer.load_state_dict(opt_state)
+            else:                                          # fresh optimizer: zero the lazily created moments / step
+                for st in optimizer.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self._params = [p for p in diff.parameters()]
+
+    def _body(self):
+        self.opt.zero_grad(set_to_none=True)
+        (loss,) = self.diff(x=self.x, T=self.tau)
+        if self.bucket is not None:
+            allreduce_gradients(self.bucket)
+        self.opt.step()
+        return loss.detach()
+
+    def step(self, x: torch.Tensor) -> torch.Tensor:
+        """Copies `x` (same shape as the example; host or device) into the static buffer and replays the graph.
+        Returns the (device-resident) loss of this step."""
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        for p in self._params:        # the replay updated the weights in place: invalidate version-keyed caches
+            torch.autograd.graph.increment_version(p)
+        return self.loss
+
+
+class GraphedSampler:
+    """`Diffusion.sample` (src/models.py:106-147) as replays of one captured block of `unroll` fixed-point
+    iterations on a static buffer: the 1000-iteration sampler of config 4 is 1000 dependent tiny forward passes."""
+
+    def __init__(self, diff: torch.nn.Module, example_x: torch.Tensor, unroll: int = 10, noise_factor: float = 1.0):
+        self.diff, self.unroll, self.noise_factor = diff, unroll, noise_factor
+        self.x = example_x.clone()
+        self.graph = torch.cuda.CUDAGraph()
+        diff.eval()
+        side = torch.cuda.Stream(example_x.device)
+        side.wait_stream(torch.cuda.current_stream(example_x.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            self._iterate(self.x.clone(), 2)
+        torch.cuda.current_stream(example_x.device).wait_stream(side)
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.x.copy_(self._iterate(self.x, unroll))
+
+    def _iterate(self, x, k):
+        for _ in range(k):
+            pred = self.diff.net(x)
+            if self.diff.prediction_goal == "data":
+                x = pred
+            else:
+                x = torch.clamp(x - (pred - 0.5) * 0.1 * self.noise_factor, 0, 1)
+        return x
+
+    def sample(self, n_iters: int, first_x: torch.Tensor) -> torch.Tensor:
+        """Last iterate after `n_iters` iterations (the `only_last=True` result of Diffusion.sample)."""
+        self.x.copy_(first_x)
+        blocks, rest = divmod(n_iters, self.unroll)
+        for _ in range(blocks):
+            self.graph.replay()
+        x = self.x
+        if rest:
+            with torch.no_grad():
+                x = self._iterate(x.clone(), rest)
+        return x.clone()

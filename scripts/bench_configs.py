@@ -118,16 +118,22 @@ def sweep(quick):
 # ----------------------------------------------------------------------------------------------
 # training-step helpers
 # ----------------------------------------------------------------------------------------------
-def train_step_rate(net, shape, imgs, tau, lr, goal="data", dtype=torch.float64, iters=5, warmup=3):
+def train_step_rate(net, shape, imgs, tau, lr, goal="data", dtype=torch.float64, iters=5, warmup=3, graphed=False):
     diff = models.Diffusion(net, noise.add_normal_noise_multiple, goal, shape, torch.nn.MSELoss()).to(DEV, dtype)
     diff.train()
-    opt = torch.optim.Adam(diff.parameters(), lr=lr)
+    opt = torch.optim.Adam(diff.parameters(), lr=lr, capturable=graphed)
     x = torch.rand(imgs, shape[0] * shape[1], device=DEV, dtype=dtype)
+    if graphed:
+        from qiddm_b200.train import GraphedTrainStep
+        gs = GraphedTrainStep(diff, opt, tau, x)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        diff(x=x, T=tau)
-        opt.step()
+        def step():
+            gs.step(x)
+    else:
+        def step():
+            opt.zero_grad(set_to_none=True)
+            diff(x=x, T=tau)
+            opt.step()
 
     ms, ker, launches = timed(step, warmup, iters)
     return diff, ms, ker, launches
@@ -146,15 +152,17 @@ def config1(cpu):
     """src/mnist_exm.py defaults: QIDDM_LL_noise(784,6,14,2), QNN_noise(784,8,14); batch 1 image, tau 10."""
     from oracle import qiddm_oracle as O
     for name, args, lr in (("QIDDM_LL_noise", (784, 6, 14, 2), 0.0255), ("QNN_noise", (784, 8, 14), 0.01011)):
-        for imgs in (1, 8, 512, 8192):
+        for imgs, graphed in ((1, False), (1, True), (8, False), (8, True), (512, False), (512, True), (8192, False)):
             torch.manual_seed(42)
             net = getattr(qnn, name)(*args)
             stages = args[3] if name == "QIDDM_LL_noise" else 1
-            _, ms, ker, launches = train_step_rate(net, (28, 28), imgs, 10, lr, iters=20 if imgs <= 8 else 5)
-            rec = dict(what="config1", model=f"{name}{args}", images_per_step=imgs, tau=10, ms_per_step=round(ms, 4),
+            _, ms, ker, launches = train_step_rate(net, (28, 28), imgs, 10, lr, iters=20 if imgs <= 8 else 5,
+                                                   graphed=graphed)
+            rec = dict(what="config1", model=f"{name}{args}", images_per_step=imgs, tau=10, cuda_graph=graphed,
+                       ms_per_step=round(ms, 4),
                        train_samples_per_s=round(imgs / ms * 1e3, 1),
                        circuit_evals_per_s=round(imgs * 10 * stages / ms * 1e3), lib_launches_per_step=launches, kernels=ker)
-            if cpu and imgs == 1:
+            if cpu and imgs == 1 and not graphed:
                 ps = {k: v.detach().cpu().double().clone().requires_grad_(True) for k, v in net.named_parameters()}
                 data = torch.rand(1, 784, dtype=torch.float64)
                 eps = torch.normal(0.5, 0.2, size=(1, 784)).double()
@@ -197,22 +205,29 @@ def config4(quick):
     """src/emnist_exm.py: QIDDM_PL_noise(784,8,6,2) training + Diffusion.sample(n_iters=1000) on 10 images."""
     torch.manual_seed(0)
     net = qnn.QIDDM_PL_noise(784, 8, 6, 2)
-    for imgs in (1, 64):
-        diff, ms, ker, launches = train_step_rate(net, (28, 28), imgs, 10, 0.0255, goal="noise", iters=5)
-        emit(what="config4_train", model="QIDDM_PL_noise(784,8,6,2)", images_per_step=imgs, tau=10,
+    from qiddm_b200.nn import qdense as qd
+    from qiddm_b200.train import GraphedSampler
+    for imgs, graphed in ((1, False), (1, True), (8, True), (64, False)):
+        diff, ms, ker, launches = train_step_rate(net, (28, 28), imgs, 10, 0.0255, goal="noise", iters=10, graphed=graphed)
+        emit(what="config4_train", model="QIDDM_PL_noise(784,8,6,2)", images_per_step=imgs, tau=10, cuda_graph=graphed,
              ms_per_step=round(ms, 3), train_samples_per_s=round(imgs / ms * 1e3, 1), lib_launches_per_step=launches,
-             kernels=ker, note="sklearn PCA re-fit on the host every forward (reference H5)")
+             kernels=ker, pca="device (Gram + Jacobi eigh kernel)" if qd.PCA_ON_DEVICE else "host sklearn")
     diff.eval()
     n_iters = 100 if quick else 1000
-    for nimg in (10, 4096):
+    for nimg, graphed in ((10, False), (10, True), (64, True), (4096, False)):
         first = torch.rand(nimg, 1, 28, 28, device=DEV, dtype=torch.float64) * 0.75 + 0.5
+        gs = GraphedSampler(diff, first, unroll=10) if graphed else None
         torch.cuda.synchronize()
         t = time.perf_counter()
-        diff.sample(n_iters=n_iters, first_x=first, only_last=True)
+        if graphed:
+            gs.sample(n_iters, first)
+        else:
+            diff.sample(n_iters=n_iters, first_x=first, only_last=True)
         torch.cuda.synchronize()
         s = time.perf_counter() - t
-        emit(what="config4_sample", model="QIDDM_PL_noise(784,8,6,2)", images=nimg, n_iters=n_iters, seconds=round(s, 3),
-             sampler_iters_per_s=round(n_iters / s, 1), circuit_evals_per_s=round(nimg * 2 * n_iters / s))
+        emit(what="config4_sample", model="QIDDM_PL_noise(784,8,6,2)", images=nimg, n_iters=n_iters, cuda_graph=graphed,
+             seconds=round(s, 3), sampler_iters_per_s=round(n_iters / s, 1),
+             circuit_evals_per_s=round(nimg * 2 * n_iters / s))
 
 
 def config5(quick):
