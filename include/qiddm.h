@@ -169,6 +169,27 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
 void qiddm_timing_enable(int enable);
 int  qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *launches_by_kind);
 
+/* UNet glue around QConv2d (reference nn/unet.py:28-116: torch.nn.Upsample(scale_factor=2, mode="bilinear") and
+ * torch.nn.BatchNorm2d in float64).  dtype = QIDDM_DTYPE_F32 / F64 for all tensors of a call; NCHW, contiguous.
+ * Bilinear resize with align_corners = False: in (planes, h_in, w_in) -> out (planes, h_out, w_out), planes = N * C,
+ * scale_* = the source step per output pixel (1 / scale_factor when a scale factor was given, else in / out); backward
+ * is the exact transpose in gather form (grad_in OVERWRITTEN).
+ * BatchNorm2d with batch statistics: y = (x - mean_c) * rstd_c * gamma_c + beta_c over (n, hw) per channel; save_mean /
+ * save_rstd (float64[c]) are kept for the backward; running_* (nullable, tensor dtype) are updated with `momentum` and the
+ * unbiased variance as torch does; gamma / beta nullable.  backward: grad_x nullable, grad_gamma / grad_beta nullable,
+ * OVERWRITTEN.  Deterministic (two-stage reductions, no atomics).  workspace: qiddm_batchnorm_workspace_bytes(c). */
+int qiddm_upsample_bilinear_forward(const void *in, void *out, int dtype, int64_t planes, int h_in, int w_in, int h_out,
+                                    int w_out, double scale_h, double scale_w, qiddm_stream_t stream);
+int qiddm_upsample_bilinear_backward(const void *grad_out, void *grad_in, int dtype, int64_t planes, int h_in, int w_in,
+                                     int h_out, int w_out, double scale_h, double scale_w, qiddm_stream_t stream);
+size_t qiddm_batchnorm_workspace_bytes(int channels);
+int qiddm_batchnorm_forward(const void *x, void *y, int dtype, int n, int c, int hw, const void *gamma, const void *beta,
+                            double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum,
+                            double eps, void *workspace, qiddm_stream_t stream);
+int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int n, int c, int hw, const void *gamma,
+                             const double *save_mean, const double *save_rstd, void *grad_gamma, void *grad_beta,
+                             void *workspace, qiddm_stream_t stream);
+
 /* On-device PCA support (replaces the sklearn `PCA.fit_transform` host round trip of nn/qdense.py:456, :1429):
  * eigen-decomposition of a symmetric m x m float64 matrix (the Gram matrix of the centred batch rows), one CTA, parallel
  * cyclic Jacobi.  evals[m] in DESCENDING order, evecs (m x m row-major) column j = eigenvector of evals[j].

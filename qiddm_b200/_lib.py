@@ -50,7 +50,9 @@ EXPORTS = [
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
     "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id",
-    "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64",
+    "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_upsample_bilinear_forward",
+    "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
+    "qiddm_batchnorm_backward",
 ]
 
 _lib = None
@@ -97,6 +99,16 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_build_unitary.restype = i32
         lib.qiddm_build_unitary.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.qiddm_launch_count.restype = i64
+        f64 = C.c_double
+        for f in (lib.qiddm_upsample_bilinear_forward, lib.qiddm_upsample_bilinear_backward):
+            f.restype = i32
+            f.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, f64, f64, vp]
+        lib.qiddm_batchnorm_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_batchnorm_workspace_bytes.argtypes = [i32]
+        lib.qiddm_batchnorm_forward.restype = i32
+        lib.qiddm_batchnorm_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp]
+        lib.qiddm_batchnorm_backward.restype = i32
+        lib.qiddm_batchnorm_backward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.qiddm_sym_eigh_max_dim.restype = i32
         lib.qiddm_sym_eigh_f64.restype = i32
         lib.qiddm_sym_eigh_f64.argtypes = [vp, i32, vp, vp, vp]

@@ -495,6 +495,29 @@ int qiddm_timing_collect(double *ms_by_kind, double *work_by_kind, int64_t *laun
     return rc;
 }
 
+int qiddm_upsample_bilinear_forward(const void *in, void *out, int dtype, int64_t planes, int h_in, int w_in, int h_out,
+                                    int w_out, double scale_h, double scale_w, qiddm_stream_t stream) {
+    return qiddm::upsample_bilinear(in, out, dtype, false, planes, h_in, w_in, h_out, w_out, scale_h, scale_w, (cudaStream_t)stream);
+}
+int qiddm_upsample_bilinear_backward(const void *grad_out, void *grad_in, int dtype, int64_t planes, int h_in, int w_in,
+                                     int h_out, int w_out, double scale_h, double scale_w, qiddm_stream_t stream) {
+    return qiddm::upsample_bilinear(grad_out, grad_in, dtype, true, planes, h_in, w_in, h_out, w_out, scale_h, scale_w,
+                                    (cudaStream_t)stream);
+}
+size_t qiddm_batchnorm_workspace_bytes(int channels) { return channels > 0 ? qiddm::batchnorm_ws_bytes(channels) : 0; }
+int qiddm_batchnorm_forward(const void *x, void *y, int dtype, int n, int c, int hw, const void *gamma, const void *beta,
+                            double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum,
+                            double eps, void *workspace, qiddm_stream_t stream) {
+    return qiddm::batchnorm_forward(x, y, dtype, n, c, hw, gamma, beta, save_mean, save_rstd, running_mean, running_var, momentum,
+                                    eps, workspace, (cudaStream_t)stream);
+}
+int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int n, int c, int hw, const void *gamma,
+                             const double *save_mean, const double *save_rstd, void *grad_gamma, void *grad_beta,
+                             void *workspace, qiddm_stream_t stream) {
+    return qiddm::batchnorm_backward(x, grad_y, grad_x, dtype, n, c, hw, gamma, save_mean, save_rstd, grad_gamma, grad_beta,
+                                     workspace, (cudaStream_t)stream);
+}
+
 int qiddm_sym_eigh_max_dim(void) {
     int m = 1;
     while (qiddm::eigh_smem_bytes(m + 1) <= 227 * 1024) ++m;

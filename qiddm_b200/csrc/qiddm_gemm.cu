@@ -808,31 +808,58 @@ __device__ __forceinline__ void split_act(float v, __half &hi, __half &lo) {
 struct UnfoldGeom {      // fused patch-unfold (QConv, nn/qconv.py:76-77): row = (image, y, x), feature = (ch, ky, kx)
     int on, C, H, W, kh, kw, ph, pw, Hout, Wout;
 };
-__device__ __forceinline__ float load_feature(const float *x, long long row, int F, int c, const UnfoldGeom &u) {
-    if (!u.on) return __ldg(x + row * F + c);
-    const int P = u.Hout * u.Wout, kk = u.kh * u.kw;
-    const int b = (int)(row / P), r = (int)(row - (long long)b * P);
-    const int y = r / u.Wout, xx = r - y * u.Wout;
-    const int ch = c / kk, q = c - ch * kk;
-    const int ky = q / u.kw, kx = q - ky * u.kw;
-    const int iy = y + ky - u.ph, ix = xx + kx - u.pw;
-    if (iy < 0 || iy >= u.H || ix < 0 || ix >= u.W) return 0.f;        // zero padding of torch.nn.Unfold
-    return __ldg(x + (((long long)b * u.C + ch) * u.H + iy) * u.W + ix);
-}
 __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_pad, float add_offset, float pad,
                               __half *Xh, __half *Xl, float *inv_n2, int want_lo, const UnfoldGeom u) {
+    // QConv: per-CTA feature table (offset inside the image relative to the patch origin, packed (dy, dx) for the
+    // bounds test), so the per-element work is one table read instead of three integer divisions
+    extern __shared__ int ftab[];          // [2 * F] when u.on
+    if (u.on) {
+        const int kk = u.kh * u.kw;
+        for (int c = threadIdx.x; c < F; c += blockDim.x) {
+            const int ch = c / kk, q = c - ch * kk;
+            const int ky = q / u.kw, kx = q - ky * u.kw;
+            ftab[c] = (ch * u.H + (ky - u.ph)) * u.W + (kx - u.pw);
+            ftab[F + c] = ((ky - u.ph) << 16) | ((kx - u.pw) & 0xffff);
+        }
+        __syncthreads();
+    }
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
+    long long base = row * F;
+    int py = 0, px = 0;
+    if (u.on) {
+        const int P = u.Hout * u.Wout;
+        const long long b = row / P;
+        const int r = (int)(row - b * P);
+        py = r / u.Wout;
+        px = r - py * u.Wout;
+        base = b * u.C * u.H * u.W + (long long)py * u.W + px;
+    }
     float ss = 0.f;
-    for (int c = lane; c < Kp; c += 32) {
-        float f = 0.f;
-        if (c < F) f = load_feature(x, row, F, c, u) + add_offset;
-        __half hi, lo;
-        split_act((c == F && n_pad > 0) ? 1.f : f, hi, lo);
-        Xh[row * Kp + c] = hi;
-        if (want_lo) Xl[row * Kp + c] = lo;
-        ss += f * f;
+    // two consecutive features per lane: one 4-byte store per array
+    for (int c = 2 * lane; c < Kp; c += 64) {
+        float f[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int cc = c + j;
+            if (cc < F) {
+                if (u.on) {
+                    const int yx = ftab[F + cc];
+                    const int iy = py + (yx >> 16), ix = px + (int)(short)(yx & 0xffff);
+                    const bool in = iy >= 0 && iy < u.H && ix >= 0 && ix < u.W;       // zero padding of torch.nn.Unfold
+                    f[j] = (in ? __ldg(x + base + ftab[cc]) : 0.f) + add_offset;
+                } else {
+                    f[j] = __ldg(x + base + cc) + add_offset;
+                }
+            }
+        }
+        __half h0, l0, h1, l1;
+        split_act((c == F && n_pad > 0) ? 1.f : f[0], h0, l0);
+        split_act((c + 1 == F && n_pad > 0) ? 1.f : f[1], h1, l1);
+        *reinterpret_cast<__half2 *>(Xh + row * Kp + c) = __halves2half2(h0, h1);       // Kp is a multiple of 8
+        if (want_lo) *reinterpret_cast<__half2 *>(Xl + row * Kp + c) = __halves2half2(l0, l1);
+        ss += f[0] * f[0] + f[1] * f[1];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -918,27 +945,32 @@ __global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half
 // Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
 // |G[b,n]| = 2 |g| scale inv_n2 |Y'| <= 2 max_m|g[b,m]| * scale * sqrt(inv_n2[b]) * w_scale.
 __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out,
-                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P) {
-    const int lane = threadIdx.x & 31;
+                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P, int gw) {
+    // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp (small QConv rows keep the lanes busy)
+    const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const bool vec = go_P == 0 && (n_out & 3) == 0 && ((uintptr_t)go & 15) == 0;
+    const bool vec = gw == 32 && go_P == 0 && (n_out & 3) == 0 && ((uintptr_t)go & 15) == 0;
     float best = 0.f;
-    for (long long row = warp0; row < B; row += nwarps) {
-        const float *g = go + row * n_out;
+    for (long long rbase = warp0 * rpw; rbase < B; rbase += nwarps * rpw) {
+        const long long row = rbase + lane / gw;
+        const bool active = row < B;
         float mx = 0.f;
-        if (go_P > 0) {        // QConv: grad_out is NCHW, element (row, m) at ((b * n_out + m) * P + r)
+        if (!active) {
+        } else if (go_P > 0) {        // QConv: grad_out is NCHW, element (row, m) at ((b * n_out + m) * P + r)
             const long long b = row / go_P, r = row - b * go_P;
-            for (int m = lane; m < n_out; m += 32) mx = fmaxf(mx, fabsf(__ldg(go + (b * n_out + m) * go_P + r)));
+            for (int m = sub; m < n_out; m += gw) mx = fmaxf(mx, fabsf(__ldg(go + (b * n_out + m) * go_P + r)));
         } else if (vec) {
+            const float *g = go + row * n_out;
             for (int i = lane; i < (n_out >> 2); i += 32) {
                 const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
                 mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
             }
         } else {
-            for (int m = lane; m < n_out; m += 32) mx = fmaxf(mx, fabsf(__ldg(g + m)));
+            const float *g = go + row * n_out;
+            for (int m = sub; m < n_out; m += gw) mx = fmaxf(mx, fabsf(__ldg(g + m)));
         }
-        best = fmaxf(best, 2.f * mx * scale * sqrtf(inv_n2[row]) * w_scale);
+        if (active) best = fmaxf(best, 2.f * mx * scale * sqrtf(inv_n2[row]) * w_scale);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -951,16 +983,19 @@ __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const flo
 __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float *go, const float *inv_n2, long long B,
                                                      int N, int Np, int n_out, float scale, int clamp, float lo,
                                                      float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl,
-                                                     float *S, int want_lo, int go_P) {
-    const int lane = threadIdx.x & 31;
+                                                     float *S, int want_lo, int go_P, int gw) {
+    // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp
+    const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const float gsc = g_scale_from_max(*gmax_bits);
     // 4 outputs (8 columns of Y / G) per lane and iteration when everything is 16-byte aligned
-    const bool vec = go_P == 0 && (n_out & 3) == 0 && Np == N &&
+    const bool vec = gw == 32 && go_P == 0 && (n_out & 3) == 0 && Np == N &&
                      (((uintptr_t)Y | (uintptr_t)go | (uintptr_t)Gh | (uintptr_t)Gl) & 15) == 0;
-    for (long long r = warp0; r < B; r += nwarps) {
-        const float in2 = inv_n2[r];
+    for (long long rbase = warp0 * rpw; rbase < B; rbase += nwarps * rpw) {
+        const long long r = rbase + lane / gw;
+        const bool active = r < B;
+        const float in2 = active ? inv_n2[r] : 0.f;
         const float k0 = scale * in2, k1 = 2.f * scale * in2 * gsc;
         float s_part = 0.f;
         if (vec) {
@@ -992,8 +1027,8 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
                     gl4[i] = make_uint4(*reinterpret_cast<unsigned int *>(&ll[0]), *reinterpret_cast<unsigned int *>(&ll[1]),
                                         *reinterpret_cast<unsigned int *>(&ll[2]), *reinterpret_cast<unsigned int *>(&ll[3]));
             }
-        } else {
-            for (int m = lane; 2 * m < Np; m += 32) {
+        } else if (active) {
+            for (int m = sub; 2 * m < Np; m += gw) {
                 float gre = 0.f, gim = 0.f;
                 if (m < n_out) {
                     const float2 y = *reinterpret_cast<const float2 *>(Y + r * N + 2 * m);
@@ -1013,8 +1048,9 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
-        if (lane == 0) S[r] = s_part;
+        for (int o = 16; o > 0; o >>= 1)
+            if (o < gw) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
+        if (sub == 0 && active) S[r] = s_part;
     }
 }
 
@@ -1380,7 +1416,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
     timing_begin(TK_PREP_X, 0.0, s);
-    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, s>>>(
+    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
         x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
         unfold_geom(gp));
     timing_end(s);
@@ -1441,14 +1477,17 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
     const int warps = 8;
     timing_begin(TK_G_BOUND, 0.0, s);
-    const unsigned ew_grid = (unsigned)((B + warps - 1) / warps < 148 * 8 ? (B + warps - 1) / warps : 148 * 8);
-    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax, go_P);
+    int gw = 32;                                       // lanes per row: smallest power of two >= Np / 2
+    while (gw > 1 && gw / 2 >= g.Np / 2) gw >>= 1;
+    const long long row_warps = (B * gw + 31) / 32;
+    const unsigned ew_grid = (unsigned)((row_warps + warps - 1) / warps < 148 * 8 ? (row_warps + warps - 1) / warps : 148 * 8);
+    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax, go_P, gw);
     timing_end(s);
     count_launch();
     timing_begin(TK_GRAD_Y, 0.0, s);
     grad_y_kernel<<<ew_grid, warps * 32, 0, s>>>(
         w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
-        Gs[1], S, n_seg > 1, go_P);
+        Gs[1], S, n_seg > 1, go_P, gw);
     timing_end(s);
     count_launch();
     GemmParams p;

@@ -1,0 +1,313 @@
+// UNet glue around QConv2d on the device (reference nn/unet.py:28-116 runs these in float64 through
+// torch.nn.Upsample(scale_factor=2, mode="bilinear") and torch.nn.BatchNorm2d): HBM-bound kernels in the tensors' own
+// dtype (float64 like the reference, or float32), statistics accumulated in float64, deterministic two-stage
+// reductions (no atomics).  After QConv moved to the tcgen05 path these two ops were 65 % of the UNet training step
+// (library float64 kernels at 1-3 % of the HBM roofline).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "qiddm_internal.h"
+
+namespace qiddm {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// bilinear interpolation, align_corners = False (torch: src = max((dst + 0.5) * scale - 0.5, 0), i1 = min(i0 + 1, in - 1))
+// ------------------------------------------------------------------------------------------------------------------
+struct Lerp {
+    int i0, i1;
+    double l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_of(int dst, double scale, int in_size) {
+    double src = ((double)dst + 0.5) * scale - 0.5;
+    if (src < 0.0) src = 0.0;
+    Lerp r;
+    r.i0 = (int)src;
+    if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+    r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+    r.l1 = src - (double)r.i0;
+    r.l0 = 1.0 - r.l1;
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const T *in, T *out, long long planes, int Hin, int Win, int Hout,
+                                                           int Wout, double sh, double sw) {
+    const long long total = planes * Hout * Wout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wout);
+        const long long t = i / Wout;
+        const int oy = (int)(t % Hout);
+        const long long pl = t / Hout;
+        const Lerp y = lerp_of(oy, sh, Hin), x = lerp_of(ox, sw, Win);
+        const T *p = in + pl * Hin * Win;
+        const double v = y.l0 * (x.l0 * (double)p[y.i0 * Win + x.i0] + x.l1 * (double)p[y.i0 * Win + x.i1]) +
+                         y.l1 * (x.l0 * (double)p[y.i1 * Win + x.i0] + x.l1 * (double)p[y.i1 * Win + x.i1]);
+        out[i] = (T)v;
+    }
+}
+
+// gather form of the transpose: every input pixel sums the output pixels that read it (deterministic, no atomics)
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const T *gout, T *gin, long long planes, int Hin, int Win, int Hout,
+                                                           int Wout, double sh, double sw) {
+    const long long total = planes * Hin * Win;
+    // output rows that can touch input row iy: (iy - 1) / sh - 1 .. (iy + 1) / sh + 1
+    const double ish = 1.0 / sh, isw = 1.0 / sw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % Win);
+        const long long t = i / Win;
+        const int iy = (int)(t % Hin);
+        const long long pl = t / Hin;
+        const T *g = gout + pl * Hout * Wout;
+        int oy0 = (int)(((double)iy - 1.0) * ish) - 1, oy1 = (int)(((double)iy + 1.0) * ish) + 1;
+        int ox0 = (int)(((double)ix - 1.0) * isw) - 1, ox1 = (int)(((double)ix + 1.0) * isw) + 1;
+        if (oy0 < 0) oy0 = 0;
+        if (ox0 < 0) ox0 = 0;
+        if (oy1 > Hout - 1) oy1 = Hout - 1;
+        if (ox1 > Wout - 1) ox1 = Wout - 1;
+        double acc = 0.0;
+        for (int oy = oy0; oy <= oy1; ++oy) {
+            const Lerp y = lerp_of(oy, sh, Hin);
+            const double wy = (y.i0 == iy ? y.l0 : 0.0) + (y.i1 == iy ? y.l1 : 0.0);
+            if (wy == 0.0) continue;
+            for (int ox = ox0; ox <= ox1; ++ox) {
+                const Lerp x = lerp_of(ox, sw, Win);
+                const double wx = (x.i0 == ix ? x.l0 : 0.0) + (x.i1 == ix ? x.l1 : 0.0);
+                if (wx != 0.0) acc += wy * wx * (double)g[oy * Wout + ox];
+            }
+        }
+        gin[i] = (T)acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BatchNorm2d (NCHW), training statistics over (N, H, W) per channel
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BN_SPLITS = 32;      // partial sums per channel (grid.y)
+constexpr int BN_THREADS = 256;
+
+__device__ __forceinline__ void block_reduce2(double &a, double &b, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[2 * w] = a; red[2 * w + 1] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = l < (BN_THREADS >> 5) ? red[2 * l] : 0.0;
+        b = l < (BN_THREADS >> 5) ? red[2 * l + 1] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+    }
+}
+
+// partial[c][split] = (sum x, sum x^2) over this split's share of (n, hw)
+// (I = unsigned when every index fits 32 bits: the per-element div/mod is the instruction cost of these kernels)
+template <typename T, typename I>
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *x, int N, int C, int HW, double *partial) {
+    __shared__ double red[2 * (BN_THREADS >> 5)];
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const I M = (I)N * (I)HW;
+    double s = 0.0, q = 0.0;
+    for (I i = (I)sp * BN_THREADS + threadIdx.x; i < M; i += (I)BN_SPLITS * BN_THREADS) {
+        const I n = i / (I)HW;
+        const I hw = i - n * (I)HW;
+        const double v = (double)x[(n * (I)C + (I)c) * (I)HW + hw];
+        s += v;
+        q += v * v;
+    }
+    block_reduce2(s, q, red);
+    if (threadIdx.x == 0) {
+        partial[(c * BN_SPLITS + sp) * 2] = s;
+        partial[(c * BN_SPLITS + sp) * 2 + 1] = q;
+    }
+}
+
+// mean / rstd per channel (+ running statistics with the unbiased variance, as torch does)
+template <typename T>
+__global__ void bn_finalize_kernel(const double *partial, int C, long long M, double eps, double momentum, double *save_mean,
+                                   double *save_rstd, T *running_mean, T *running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < BN_SPLITS; ++i) {
+        s += partial[(c * BN_SPLITS + i) * 2];
+        q += partial[(c * BN_SPLITS + i) * 2 + 1];
+    }
+    const double mean = s / (double)M;
+    double var = q / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    save_mean[c] = mean;
+    save_rstd[c] = 1.0 / sqrt(var + eps);
+    if (running_mean != nullptr) {
+        const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (T)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+        running_var[c] = (T)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+    }
+}
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T *x, T *y, long long total_, int C, int HW, const double *mean,
+                                                       const double *rstd, const T *gamma, const T *beta) {
+    const I total = (I)total_;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const int c = (int)((i / (I)HW) % (I)C);
+        const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+        y[i] = (T)(((double)x[i] - mean[c]) * rstd[c] * g + b);
+    }
+}
+
+// partial[c][split] = (sum dy, sum dy * xhat)
+template <typename T, typename I>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *x, const T *dy, int N, int C, int HW,
+                                                                   const double *mean, const double *rstd, double *partial) {
+    __shared__ double red[2 * (BN_THREADS >> 5)];
+    const int c = blockIdx.x, sp = blockIdx.y;
+    const I M = (I)N * (I)HW;
+    const double mu = mean[c], rs = rstd[c];
+    double s = 0.0, q = 0.0;
+    for (I i = (I)sp * BN_THREADS + threadIdx.x; i < M; i += (I)BN_SPLITS * BN_THREADS) {
+        const I n = i / (I)HW;
+        const I hw = i - n * (I)HW;
+        const I idx = (n * (I)C + (I)c) * (I)HW + hw;
+        const double g = (double)dy[idx];
+        s += g;
+        q += g * ((double)x[idx] - mu) * rs;
+    }
+    block_reduce2(s, q, red);
+    if (threadIdx.x == 0) {
+        partial[(c * BN_SPLITS + sp) * 2] = s;
+        partial[(c * BN_SPLITS + sp) * 2 + 1] = q;
+    }
+}
+
+template <typename T>
+__global__ void bn_bwd_finalize_kernel(const double *partial, int C, double *sums, T *dgamma, T *dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < BN_SPLITS; ++i) {
+        s += partial[(c * BN_SPLITS + i) * 2];
+        q += partial[(c * BN_SPLITS + i) * 2 + 1];
+    }
+    sums[2 * c] = s;
+    sums[2 * c + 1] = q;
+    if (dbeta) dbeta[c] = (T)s;
+    if (dgamma) dgamma[c] = (T)q;
+}
+
+// dx = gamma rstd (dy - sum_dy / M - xhat sum_dy_xhat / M)
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *x, const T *dy, T *dx, long long total_, int C, int HW,
+                                                           double inv_m, const double *mean, const double *rstd,
+                                                           const T *gamma, const double *sums) {
+    const I total = (I)total_;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const int c = (int)((i / (I)HW) % (I)C);
+        const double g = gamma ? (double)gamma[c] : 1.0;
+        const double xh = ((double)x[i] - mean[c]) * rstd[c];
+        dx[i] = (T)(g * rstd[c] * ((double)dy[i] - sums[2 * c] * inv_m - xh * sums[2 * c + 1] * inv_m));
+    }
+}
+
+inline unsigned ew_grid(long long total) {
+    const long long b = (total + 255) / 256;
+    return (unsigned)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
+}
+
+template <typename T>
+int upsample_impl(const void *in, void *out, bool backward, long long planes, int Hin, int Win, int Hout, int Wout, double sh,
+                  double sw, cudaStream_t s) {
+    if (backward)   // `in` = grad_out (planes, Hout, Wout), `out` = grad_in (planes, Hin, Win)
+        upsample_bwd_kernel<T><<<ew_grid(planes * Hin * Win), 256, 0, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out),
+                                                                          planes, Hin, Win, Hout, Wout, sh, sw);
+    else
+        upsample_fwd_kernel<T><<<ew_grid(planes * Hout * Wout), 256, 0, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out),
+                                                                            planes, Hin, Win, Hout, Wout, sh, sw);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+template <typename T, typename I>
+int bn_fwd_impl(const void *x, void *y, int N, int C, int HW, const void *gamma, const void *beta, double *save_mean,
+                double *save_rstd, void *running_mean, void *running_var, double momentum, double eps, double *ws,
+                cudaStream_t s) {
+    const long long M = (long long)N * HW, total = M * C;
+    bn_stats_kernel<T, I><<<dim3(C, BN_SPLITS), BN_THREADS, 0, s>>>(reinterpret_cast<const T *>(x), N, C, HW, ws);
+    bn_finalize_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(ws, C, M, eps, momentum, save_mean, save_rstd,
+                                                         reinterpret_cast<T *>(running_mean), reinterpret_cast<T *>(running_var));
+    bn_apply_kernel<T, I><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<T *>(y), total, C, HW,
+                                                     save_mean, save_rstd, reinterpret_cast<const T *>(gamma),
+                                                     reinterpret_cast<const T *>(beta));
+    count_launch(3);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+template <typename T, typename I>
+int bn_bwd_impl(const void *x, const void *dy, void *dx, int N, int C, int HW, const void *gamma, const double *save_mean,
+                const double *save_rstd, void *dgamma, void *dbeta, double *ws, cudaStream_t s) {
+    const long long M = (long long)N * HW, total = M * C;
+    double *sums = ws + (size_t)C * BN_SPLITS * 2;
+    bn_bwd_reduce_kernel<T, I><<<dim3(C, BN_SPLITS), BN_THREADS, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<const T *>(dy),
+                                                                      N, C, HW, save_mean, save_rstd, ws);
+    bn_bwd_finalize_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(ws, C, sums, reinterpret_cast<T *>(dgamma), reinterpret_cast<T *>(dbeta));
+    int launches = 2;
+    if (dx != nullptr) {
+        bn_bwd_apply_kernel<T, I><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<const T *>(dy),
+                                                             reinterpret_cast<T *>(dx), total, C, HW, 1.0 / (double)M, save_mean,
+                                                             save_rstd, reinterpret_cast<const T *>(gamma), sums);
+        ++launches;
+    }
+    count_launch(launches);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+}  // namespace
+
+size_t batchnorm_ws_bytes(int C) { return ((size_t)C * BN_SPLITS * 2 + (size_t)C * 2) * sizeof(double); }
+
+int upsample_bilinear(const void *in, void *out, int dtype, bool backward, long long planes, int Hin, int Win, int Hout, int Wout,
+                      double scale_h, double scale_w, cudaStream_t s) {
+    if (!in || !out || planes < 0 || Hin < 1 || Win < 1 || Hout < 1 || Wout < 1) return QIDDM_EINVAL;
+    if (planes == 0) return QIDDM_OK;
+    if (dtype == QIDDM_DTYPE_F64) return upsample_impl<double>(in, out, backward, planes, Hin, Win, Hout, Wout, scale_h, scale_w, s);
+    if (dtype == QIDDM_DTYPE_F32) return upsample_impl<float>(in, out, backward, planes, Hin, Win, Hout, Wout, scale_h, scale_w, s);
+    return QIDDM_EINVAL;
+}
+
+int batchnorm_forward(const void *x, void *y, int dtype, int N, int C, int HW, const void *gamma, const void *beta,
+                      double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum, double eps,
+                      void *ws, cudaStream_t s) {
+    if (!x || !y || !save_mean || !save_rstd || !ws || N < 1 || C < 1 || HW < 1) return QIDDM_EINVAL;
+    if ((running_mean == nullptr) != (running_var == nullptr)) return QIDDM_EINVAL;
+    const bool small = (long long)N * C * HW < (1LL << 31);
+    double *w = reinterpret_cast<double *>(ws);
+#define QIDDM_BN_FWD(T, I) bn_fwd_impl<T, I>(x, y, N, C, HW, gamma, beta, save_mean, save_rstd, running_mean, running_var, momentum, eps, w, s)
+    if (dtype == QIDDM_DTYPE_F64) return small ? QIDDM_BN_FWD(double, unsigned) : QIDDM_BN_FWD(double, long long);
+    if (dtype == QIDDM_DTYPE_F32) return small ? QIDDM_BN_FWD(float, unsigned) : QIDDM_BN_FWD(float, long long);
+#undef QIDDM_BN_FWD
+    return QIDDM_EINVAL;
+}
+
+int batchnorm_backward(const void *x, const void *dy, void *dx, int dtype, int N, int C, int HW, const void *gamma,
+                       const double *save_mean, const double *save_rstd, void *dgamma, void *dbeta, void *ws, cudaStream_t s) {
+    if (!x || !dy || !save_mean || !save_rstd || !ws || N < 1 || C < 1 || HW < 1) return QIDDM_EINVAL;
+    const bool small = (long long)N * C * HW < (1LL << 31);
+    double *w = reinterpret_cast<double *>(ws);
+#define QIDDM_BN_BWD(T, I) bn_bwd_impl<T, I>(x, dy, dx, N, C, HW, gamma, save_mean, save_rstd, dgamma, dbeta, w, s)
+    if (dtype == QIDDM_DTYPE_F64) return small ? QIDDM_BN_BWD(double, unsigned) : QIDDM_BN_BWD(double, long long);
+    if (dtype == QIDDM_DTYPE_F32) return small ? QIDDM_BN_BWD(float, unsigned) : QIDDM_BN_BWD(float, long long);
+#undef QIDDM_BN_BWD
+    return QIDDM_EINVAL;
+}
+
+}  // namespace qiddm

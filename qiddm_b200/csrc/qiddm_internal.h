@@ -75,4 +75,14 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
 size_t eigh_smem_bytes(int m);
 int sym_eigh_f64(const double *A, int m, double *evals, double *evecs, cudaStream_t s);
 
+// qiddm_glue.cu — UNet glue around QConv2d: bilinear resize (align_corners = False) and BatchNorm2d (NCHW)
+size_t batchnorm_ws_bytes(int C);
+int upsample_bilinear(const void *in, void *out, int dtype, bool backward, long long planes, int Hin, int Win, int Hout, int Wout,
+                      double scale_h, double scale_w, cudaStream_t s);
+int batchnorm_forward(const void *x, void *y, int dtype, int N, int C, int HW, const void *gamma, const void *beta,
+                      double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum, double eps,
+                      void *ws, cudaStream_t s);
+int batchnorm_backward(const void *x, const void *dy, void *dx, int dtype, int N, int C, int HW, const void *gamma,
+                       const double *save_mean, const double *save_rstd, void *dgamma, void *dbeta, void *ws, cudaStream_t s);
+
 }  // namespace qiddm

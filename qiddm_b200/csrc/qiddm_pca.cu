@@ -19,8 +19,9 @@ constexpr int EIGH_THREADS = 512;
 __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double *A_in, int m, double *evals, double *evecs,
                                                                    int max_sweeps) {
     extern __shared__ double sm[];
-    double *A = sm, *V = sm + (size_t)m * m;
-    double *cs = V + (size_t)m * m;            // [2 * half]
+    const int ld = m | 1;                      // odd row stride (in doubles): rows start in different banks
+    double *A = sm, *V = sm + (size_t)m * ld;
+    double *cs = V + (size_t)m * ld;           // [2 * half]
     const int me = (m + 1) & ~1, half = me / 2;
     double *red = cs + 2 * half;               // [EIGH_THREADS / 32 + 2]
     int *pq = reinterpret_cast<int *>(red + EIGH_THREADS / 32 + 2);   // [2 * half]
@@ -28,8 +29,8 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
 
     for (int i = tid; i < m * m; i += nt) {
         const int r = i / m, c = i - r * m;
-        A[i] = 0.5 * (A_in[i] + A_in[c * m + r]);       // symmetrise the input
-        V[i] = r == c ? 1.0 : 0.0;
+        A[r * ld + c] = 0.5 * (A_in[i] + A_in[c * m + r]);       // symmetrise the input
+        V[r * ld + c] = r == c ? 1.0 : 0.0;
     }
     __syncthreads();
 
@@ -45,7 +46,10 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
     };
 
     double fro = 0.0;
-    for (int i = tid; i < m * m; i += nt) fro += A[i] * A[i];
+    for (int i = tid; i < m * m; i += nt) {
+        const double v = A[(i / m) * ld + (i % m)];
+        fro += v * v;
+    }
     fro = block_sum(fro);
 
     double prev_off = 1e300;
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
         double off = 0.0;
         for (int i = tid; i < m * m; i += nt) {
             const int r = i / m, c = i - r * m;
-            if (r != c) off += A[i] * A[i];
+            if (r != c) off += A[r * ld + c] * A[r * ld + c];
         }
         off = block_sum(off);
         // |off|_F <= 1e-13 |A|_F, or already below 1e-10 |A|_F without further progress (rounding floor ~ m * eps)
@@ -69,9 +73,9 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
                 if (p > q) { const int t = p; p = q; q = t; }
                 double c = 1.0, s = 0.0;
                 if (q < m) {
-                    const double apq = A[p * m + q];
+                    const double apq = A[p * ld + q];
                     if (fabs(apq) > 1e-300) {
-                        const double tau = (A[q * m + q] - A[p * m + p]) / (2.0 * apq);
+                        const double tau = (A[q * ld + q] - A[p * ld + p]) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                         c = 1.0 / sqrt(1.0 + t * t);
                         s = t * c;
@@ -89,25 +93,25 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
                 const int ka = i / half, kb = i - ka * half;
                 const int pa = pq[2 * ka], qa = pq[2 * ka + 1], pb = pq[2 * kb], qb = pq[2 * kb + 1];
                 const double ca = cs[2 * ka], sa = cs[2 * ka + 1], cb = cs[2 * kb], sb = cs[2 * kb + 1];
-                const double b11 = A[pa * m + pb];
-                const double b12 = qb >= 0 ? A[pa * m + qb] : 0.0;
-                const double b21 = qa >= 0 ? A[qa * m + pb] : 0.0;
-                const double b22 = (qa >= 0 && qb >= 0) ? A[qa * m + qb] : 0.0;
+                const double b11 = A[pa * ld + pb];
+                const double b12 = qb >= 0 ? A[pa * ld + qb] : 0.0;
+                const double b21 = qa >= 0 ? A[qa * ld + pb] : 0.0;
+                const double b22 = (qa >= 0 && qb >= 0) ? A[qa * ld + qb] : 0.0;
                 const double t11 = cb * b11 - sb * b12, t12 = sb * b11 + cb * b12;
                 const double t21 = cb * b21 - sb * b22, t22 = sb * b21 + cb * b22;
-                A[pa * m + pb] = ca * t11 - sa * t21;
-                if (qb >= 0) A[pa * m + qb] = ca * t12 - sa * t22;
-                if (qa >= 0) A[qa * m + pb] = sa * t11 + ca * t21;
-                if (qa >= 0 && qb >= 0) A[qa * m + qb] = sa * t12 + ca * t22;
+                A[pa * ld + pb] = ca * t11 - sa * t21;
+                if (qb >= 0) A[pa * ld + qb] = ca * t12 - sa * t22;
+                if (qa >= 0) A[qa * ld + pb] = sa * t11 + ca * t21;
+                if (qa >= 0 && qb >= 0) A[qa * ld + qb] = sa * t12 + ca * t22;
             }
-            for (int i = tid; i < half * m; i += nt) {
-                const int k = i / m, r = i - k * m;
+            for (int i = tid; i < half * m; i += nt) {       // consecutive threads: same row, different column pairs
+                const int r = i / half, k = i - r * half;
                 const int p = pq[2 * k], q = pq[2 * k + 1];
                 if (q < 0) continue;
                 const double c = cs[2 * k], s = cs[2 * k + 1];
-                const double vp = V[r * m + p], vq = V[r * m + q];
-                V[r * m + p] = c * vp - s * vq;
-                V[r * m + q] = s * vp + c * vq;
+                const double vp = V[r * ld + p], vq = V[r * ld + q];
+                V[r * ld + p] = c * vp - s * vq;
+                V[r * ld + q] = s * vp + c * vq;
             }
             __syncthreads();
         }
@@ -115,10 +119,10 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
 
     // descending order by rank counting (ties broken by index), then scatter
     for (int j = tid; j < m; j += nt) {
-        const double lj = A[j * m + j];
+        const double lj = A[j * ld + j];
         int rank = 0;
         for (int i = 0; i < m; ++i) {
-            const double li = A[i * m + i];
+            const double li = A[i * ld + i];
             if (li > lj || (li == lj && i < j)) ++rank;
         }
         evals[rank] = lj;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
     __syncthreads();
     for (int i = tid; i < m * m; i += nt) {
         const int r = i / m, c = i - r * m;
-        evecs[r * m + pq[c]] = V[i];
+        evecs[r * m + pq[c]] = V[r * ld + c];
     }
 }
 
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double 
 
 size_t eigh_smem_bytes(int m) {
     const int me = (m + 1) & ~1, half = me / 2;
-    return (size_t)(2 * m * m + 2 * half + EIGH_THREADS / 32 + 2) * sizeof(double) + (size_t)2 * half * sizeof(int) + 16;
+    return (size_t)(2 * m * (m | 1) + 2 * half + EIGH_THREADS / 32 + 2) * sizeof(double) + (size_t)2 * half * sizeof(int) + 16;
 }
 
 int sym_eigh_f64(const double *A, int m, double *evals, double *evecs, cudaStream_t s) {

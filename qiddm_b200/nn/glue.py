@@ -1,0 +1,141 @@
+"""Device-side UNet glue around QConv2d: drop-in `BatchNorm2d` and `Upsample` whose CUDA path runs
+the library's own HBM-bound kernels (qiddm_batchnorm_*, qiddm_upsample_bilinear_*) in the tensors' dtype (float64
+like the reference `nn/unet.py:28-116`, or float32).  Same constructor arguments, parameters, buffers and
+`state_dict` keys as the torch modules they subclass; CPU tensors (the classical `qdepth=0` UNet in host tests) go
+through the torch implementation of the parent class."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+_DT = {torch.float32: L.DTYPE_F32, torch.float64: L.DTYPE_F64}
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _BatchNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps):
+        lib = L.load_library()
+        x = x.contiguous()
+        n, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (n * c)
+        y = torch.empty_like(x)
+        mean = torch.empty(c, dtype=torch.float64, device=x.device)
+        rstd = torch.empty(c, dtype=torch.float64, device=x.device)
+        ws = torch.empty(int(lib.qiddm_batchnorm_workspace_bytes(c)), dtype=torch.uint8, device=x.device)
+        g = gamma.detach().to(x.dtype).contiguous() if gamma is not None else None
+        b = beta.detach().to(x.dtype).contiguous() if beta is not None else None
+        rm = rv = None
+        if running_mean is not None:
+            if running_mean.dtype != x.dtype or not running_mean.is_contiguous():
+                raise L.QiddmError("BatchNorm2d: running statistics must be contiguous and have the input's dtype")
+            rm, rv = running_mean, running_var
+        with torch.cuda.device(x.device):
+            L.check(lib.qiddm_batchnorm_forward(L._ptr(x), L._ptr(y), _DT[x.dtype], n, c, hw, L._ptr(g), L._ptr(b),
+                                                L._ptr(mean), L._ptr(rstd), L._ptr(rm), L._ptr(rv), float(momentum),
+                                                float(eps), L._ptr(ws), _stream(x.device)), "qiddm_batchnorm_forward")
+        ctx.save_for_backward(x, g, mean, rstd)
+        ctx.has_affine = gamma is not None
+        ctx.param_dtype = gamma.dtype if gamma is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load_library()
+        x, g, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (n * c)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dgamma = torch.empty(c, dtype=x.dtype, device=x.device) if ctx.has_affine else None
+        dbeta = torch.empty(c, dtype=x.dtype, device=x.device) if ctx.has_affine else None
+        ws = torch.empty(int(lib.qiddm_batchnorm_workspace_bytes(c)), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.qiddm_batchnorm_backward(L._ptr(x), L._ptr(dy), L._ptr(dx), _DT[x.dtype], n, c, hw, L._ptr(g),
+                                                 L._ptr(mean), L._ptr(rstd), L._ptr(dgamma), L._ptr(dbeta), L._ptr(ws),
+                                                 _stream(x.device)), "qiddm_batchnorm_backward")
+        if ctx.has_affine:
+            dgamma, dbeta = dgamma.to(ctx.param_dtype), dbeta.to(ctx.param_dtype)
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+class BatchNorm2d(torch.nn.BatchNorm2d):
+    """torch.nn.BatchNorm2d (nn/unet.py:43-45, :95, :106) with the batch-statistics path on the library's kernels."""
+
+    def forward(self, x):
+        if not x.is_cuda or x.dtype not in _DT or x.dim() != 4 or x.numel() == 0:
+            return super().forward(x)
+        use_batch_stats = self.training or self.running_mean is None
+        if not use_batch_stats:           # eval: running statistics, plain elementwise math (differentiable)
+            scale = torch.rsqrt(self.running_var.to(x.dtype) + self.eps)
+            shift = -self.running_mean.to(x.dtype) * scale
+            if self.affine:
+                scale = scale * self.weight.to(x.dtype)
+                shift = shift * self.weight.to(x.dtype) + self.bias.to(x.dtype)
+            return x * scale[None, :, None, None] + shift[None, :, None, None]
+        factor = 0.0
+        rm = rv = None
+        if self.training and self.track_running_stats and self.running_mean is not None:
+            # momentum None = cumulative moving average; reading the counter would sync, so only the (default)
+            # exponential average takes the library path
+            if self.momentum is None or self.running_mean.dtype != x.dtype:
+                return super().forward(x)
+            self.num_batches_tracked.add_(1)
+            factor = self.momentum
+            rm, rv = self.running_mean, self.running_var
+        return _BatchNormFunction.apply(x, self.weight if self.affine else None, self.bias if self.affine else None,
+                                        rm, rv, factor, self.eps)
+
+
+class _UpsampleFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h_out, w_out, scale_h, scale_w):
+        lib = L.load_library()
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        out = torch.empty((n, c, h_out, w_out), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.qiddm_upsample_bilinear_forward(L._ptr(x), L._ptr(out), _DT[x.dtype], n * c, h, w, h_out, w_out,
+                                                        scale_h, scale_w, _stream(x.device)),
+                    "qiddm_upsample_bilinear_forward")
+        ctx.geom = (n, c, h, w, h_out, w_out, scale_h, scale_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load_library()
+        n, c, h, w, h_out, w_out, scale_h, scale_w = ctx.geom
+        g = g.contiguous()
+        gin = torch.empty((n, c, h, w), dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            L.check(lib.qiddm_upsample_bilinear_backward(L._ptr(g), L._ptr(gin), _DT[g.dtype], n * c, h, w, h_out, w_out,
+                                                         scale_h, scale_w, _stream(g.device)),
+                    "qiddm_upsample_bilinear_backward")
+        return gin, None, None, None, None
+
+
+class Upsample(torch.nn.Upsample):
+    """torch.nn.Upsample(scale_factor=2, mode="bilinear") of nn/unet.py:38 on the library's kernel
+    (align_corners = False, the torch default the reference relies on)."""
+
+    def forward(self, x):
+        ok = (x.is_cuda and x.dtype in _DT and x.dim() == 4 and self.mode == "bilinear" and not self.align_corners
+              and x.numel() > 0 and not getattr(self, "recompute_scale_factor", None))
+        if not ok:
+            return super().forward(x)
+        h, w = x.shape[2], x.shape[3]
+        if self.size is not None:
+            h_out, w_out = (self.size, self.size) if isinstance(self.size, int) else tuple(self.size)
+            sh, sw = h / h_out, w / w_out
+        else:
+            sf = self.scale_factor
+            fh, fw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
+            h_out, w_out = int(h * fh), int(w * fw)       # floor, as torch computes the output size
+            sh, sw = 1.0 / fh, 1.0 / fw                   # the given scale factor drives the source coordinates
+        return _UpsampleFunction.apply(x, h_out, w_out, float(sh), float(sw))

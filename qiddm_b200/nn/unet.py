@@ -1,7 +1,9 @@
-"""UNet callers of QConv2d (reference `nn/unet.py:9-190`).  Pure torch glue in float64 like the
-reference; only the Conv2d factory's quantum branch changes (B200 QConv2d)."""
+"""UNet callers of QConv2d (reference `nn/unet.py:9-190`).  Float64 glue like the reference; the Conv2d factory's
+quantum branch is the B200 QConv2d, and BatchNorm2d / the bilinear Upsample run the library's own kernels on CUDA
+(qiddm_b200.nn.glue: same parameters and state_dict keys as the torch modules)."""
 import torch
 
+from .glue import BatchNorm2d, Upsample
 from .qconv import QConv2d
 from .utils import autopad, get_label_embedding
 
@@ -21,17 +23,17 @@ class UpBlock(torch.nn.Module):
         super().__init__()
         self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
         self.up_conv = torch.nn.Sequential(
-            torch.nn.Upsample(scale_factor=2, mode="bilinear"),
+            Upsample(scale_factor=2, mode="bilinear"),
             Conv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=1, padding=0, qdepth=qdepth),
         ).double()
         self.net = torch.nn.Sequential(
             Conv2d(in_channels=2 * out_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1,
                    qdepth=qdepth),
             torch.nn.ReLU(),
-            torch.nn.BatchNorm2d(out_channels, dtype=torch.double),
+            BatchNorm2d(out_channels, dtype=torch.double),
             Conv2d(in_channels=out_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1,
                    qdepth=qdepth),
-            torch.nn.BatchNorm2d(out_channels, dtype=torch.double),
+            BatchNorm2d(out_channels, dtype=torch.double),
             torch.nn.ReLU(),
         ).double()
 
@@ -51,11 +53,11 @@ class DownBlock(torch.nn.Module):
         self.net = torch.nn.Sequential(
             Conv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size, qdepth=qdepth,
                    padding=1),
-            torch.nn.BatchNorm2d(out_channels, dtype=torch.double),
+            BatchNorm2d(out_channels, dtype=torch.double),
             torch.nn.ReLU(),
             Conv2d(in_channels=out_channels, out_channels=out_channels, kernel_size=kernel_size, qdepth=qdepth,
                    padding=1),
-            torch.nn.BatchNorm2d(out_channels, dtype=torch.double),
+            BatchNorm2d(out_channels, dtype=torch.double),
             torch.nn.ReLU(),
         ).double()
         if self.pooling:

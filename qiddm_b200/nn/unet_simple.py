@@ -1,6 +1,7 @@
 """One-QConv-per-block UNet variant (reference `nn/unet_simple.py:6-94`)."""
 import torch
 
+from .glue import BatchNorm2d, Upsample
 from .qconv import QConv2d
 from .unet import DownBlock, UNetUndirected, UpBlock, get_label_embedding
 
@@ -11,7 +12,7 @@ class DownBlockS(DownBlock):
         self.net = torch.nn.Sequential(
             QConv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size, qdepth=qdepth,
                     padding=1),
-            torch.nn.BatchNorm2d(out_channels),
+            BatchNorm2d(out_channels),
         )
 
 
@@ -21,10 +22,10 @@ class UpBlockS(UpBlock):
         self.net = torch.nn.Sequential(
             QConv2d(in_channels=2 * out_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1,
                     qdepth=qdepth),
-            torch.nn.BatchNorm2d(out_channels),
+            BatchNorm2d(out_channels),
         )
         self.up_conv = torch.nn.Sequential(
-            torch.nn.Upsample(scale_factor=2, mode="bilinear"),
+            Upsample(scale_factor=2, mode="bilinear"),
             QConv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=1, padding=0, qdepth=qdepth),
         )
 

@@ -1,0 +1,97 @@
+"""UNet glue kernels (qiddm_b200.nn.glue: BatchNorm2d, bilinear Upsample) against the torch modules they replace
+(reference nn/unet.py:28-116 uses torch.nn.BatchNorm2d / torch.nn.Upsample in float64)."""
+import pytest
+import torch
+
+from conftest import rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("shape", [(10, 8, 28, 28), (3, 16, 7, 7), (1, 5, 1, 3), (640, 32, 7, 7)])
+def test_batchnorm2d_matches_torch(dtype, tol, shape):
+    from qiddm_b200 import _lib as L
+    from qiddm_b200.nn.glue import BatchNorm2d
+    torch.manual_seed(0)
+    c = shape[1]
+    ref = torch.nn.BatchNorm2d(c, dtype=dtype).cuda()
+    our = BatchNorm2d(c, dtype=dtype).cuda()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.uniform_(-0.5, 0.5)
+    our.load_state_dict(ref.state_dict())
+    for it in range(2):                                   # two steps: running statistics accumulate
+        x = torch.rand(shape, dtype=dtype, device="cuda") * 2 + it
+        g = torch.randn(shape, dtype=dtype, device="cuda")
+        xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        n0 = L.launch_count()
+        yr, yo = ref(xr), our(xo)
+        assert L.launch_count() > n0
+        (yr * g).sum().backward()
+        (yo * g).sum().backward()
+        assert rel_to_max(yo, yr) <= tol
+        assert rel_to_max(xo.grad, xr.grad) <= tol * 50
+        assert rel_to_max(our.weight.grad, ref.weight.grad) <= tol * 50
+        assert rel_to_max(our.bias.grad, ref.bias.grad) <= tol * 50
+        ref.zero_grad(); our.zero_grad()
+    assert rel_to_max(our.running_mean, ref.running_mean) <= tol
+    assert rel_to_max(our.running_var, ref.running_var) <= tol * 10
+    assert int(our.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+    ref.eval(); our.eval()
+    x = torch.rand(shape, dtype=dtype, device="cuda")
+    assert rel_to_max(our(x), ref(x)) <= max(tol, 1e-6 if dtype == torch.float32 else 0)
+    assert set(our.state_dict()) == set(ref.state_dict())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-13), (torch.float32, 1e-6)])
+@pytest.mark.parametrize("cfg", [((4, 3, 7, 7), dict(scale_factor=2)), ((2, 5, 14, 13), dict(scale_factor=2)),
+                                 ((2, 2, 1, 1), dict(scale_factor=2)), ((3, 2, 5, 6), dict(scale_factor=3)),
+                                 ((2, 3, 6, 9), dict(size=(11, 7))), ((2, 2, 8, 8), dict(scale_factor=1.5))])
+def test_bilinear_upsample_matches_torch(dtype, tol, cfg):
+    from qiddm_b200 import _lib as L
+    from qiddm_b200.nn.glue import Upsample
+    shape, kw = cfg
+    torch.manual_seed(1)
+    ref, our = torch.nn.Upsample(mode="bilinear", **kw), Upsample(mode="bilinear", **kw)
+    x = torch.rand(shape, dtype=dtype, device="cuda")
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    n0 = L.launch_count()
+    yr, yo = ref(xr), our(xo)
+    assert L.launch_count() > n0 and yo.shape == yr.shape
+    g = torch.randn_like(yr)
+    (yr * g).sum().backward()
+    (yo * g).sum().backward()
+    assert rel_to_max(yo, yr) <= tol
+    assert rel_to_max(xo.grad, xr.grad) <= tol * 10
+
+
+def test_unet_with_library_glue_equals_torch_glue():
+    """UNetUndirected (QConv2d children) with the library BatchNorm2d / Upsample vs the same net run with the torch
+    modules (identical weights): outputs and gradients agree to float64 round-off of the glue."""
+    from qiddm_b200 import nn
+    torch.manual_seed(6)
+    net = nn.UNetUndirected(depth=3, start_channels=4, qdepth=2).cuda()
+    x = torch.rand(4, 1, 12, 12, dtype=torch.float64, device="cuda")
+    y = net(x)
+    y.square().mean().backward()
+    grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+
+    def to_torch(m):
+        for name, child in list(m.named_children()):
+            if isinstance(child, nn.glue.BatchNorm2d):
+                t = torch.nn.BatchNorm2d(child.num_features, dtype=torch.double).cuda()
+                t.load_state_dict(child.state_dict())
+                t.running_mean.zero_(); t.running_var.fill_(1.0)
+                setattr(m, name, t)
+            elif isinstance(child, nn.glue.Upsample):
+                setattr(m, name, torch.nn.Upsample(scale_factor=2, mode="bilinear"))
+            else:
+                to_torch(child)
+    to_torch(net)
+    y2 = net(x)
+    y2.square().mean().backward()
+    assert rel_to_max(y, y2) <= 1e-9
+    for k, p in net.named_parameters():
+        assert rel_to_max(grads[k], p.grad, floor=1e-12) <= 1e-5, k      # fp32 QConv children amplify glue round-off
