@@ -381,13 +381,23 @@ class Plan:
         return bool(self.lib.qiddm_gemm_supported(self.handle))
 
     def use_gemm(self, batch: int) -> bool:
-        """PATH_AUTO rule: the collapse costs about 2^n gate-path instances per optimizer step, so it
-        pays once the batch is a few times 2^n (SURVEY.md 8d break-even)."""
+        """PATH_AUTO rule, a cost model fitted to the B200 sweep (profiles/r1_configs.md): per instance the gate path
+        costs ~77 flop per Rot and amplitude (forward + adjoint backward) at ~28 TFLOP/s effective; the collapse path
+        costs three fp16x3 GEMMs at ~1.25 PFLOP/s plus its streaming operand traffic, and per optimizer step the
+        collapse itself (gate kernels on the 2^n basis columns, forward + adjoint) plus ~0.12 ms of small launches."""
         if self.spec.path == PATH_GATE or not self.gemm_supported():
             return False
         if self.spec.path == PATH_GEMM:
             return True
-        return batch >= 2 * self.spec.dim
+        a, f, n_out = self.spec.dim, self.spec.n_features, self.spec.read_count
+        if batch < 2 * a:
+            return False
+        n_rot = self.spec.n_blocks * self.spec.layers_per_block * self.spec.n_qubits
+        kp = (f + 1 + 7) // 8 * 8
+        t_gate = 77.0 * n_rot * a / 28e12 + 1e-9
+        t_gemm = 18.0 * kp * (2 * n_out) / 1.25e15 + (24.0 * f + 20.0 * 2 * n_out) / 5e12 + 1e-9
+        t_collapse = a * t_gate + 1.2e-4
+        return batch * t_gemm + t_collapse < batch * t_gate
 
     def gemm_prepare(self, weights: torch.Tensor) -> torch.Tensor:
         """Collapsed operator (U^T + fp16 GEMM operands) for the current weights; cached per weights version."""

@@ -809,7 +809,7 @@ struct UnfoldGeom {      // fused patch-unfold (QConv, nn/qconv.py:76-77): row =
     int on, C, H, W, kh, kw, ph, pw, Hout, Wout;
 };
 __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_pad, float add_offset, float pad,
-                              __half *Xh, __half *Xl, float *inv_n2, int want_lo, const UnfoldGeom u) {
+                              __half *Xh, __half *Xl, float *inv_n2, int want_lo, const UnfoldGeom u, int gw) {
     // QConv: per-CTA feature table (offset inside the image relative to the patch origin, packed (dy, dx) for the
     // bounds test), so the per-element work is one table read instead of three integer divisions
     extern __shared__ int ftab[];          // [2 * F] when u.on
@@ -823,12 +823,13 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
         }
         __syncthreads();
     }
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= B) return;
+    // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp: short QConv rows keep the lanes busy
+    const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / gw;
+    const bool active = row < B;
     long long base = row * F;
     int py = 0, px = 0;
-    if (u.on) {
+    if (u.on && active) {
         const int P = u.Hout * u.Wout;
         const long long b = row / P;
         const int r = (int)(row - b * P);
@@ -838,7 +839,7 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
     }
     float ss = 0.f;
     // two consecutive features per lane: one 4-byte store per array
-    for (int c = 2 * lane; c < Kp; c += 64) {
+    for (int c = 2 * sub; c < Kp && active; c += 2 * gw) {
         float f[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -862,10 +863,93 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
         ss += f[0] * f[0] + f[1] * f[1];
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) {
+    for (int o = 16; o > 0; o >>= 1)
+        if (o < gw) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (sub == 0 && active) {
         ss += (float)n_pad * pad * pad;
         inv_n2[row] = ss > 0.f ? 1.0f / ss : 0.f;
+    }
+}
+
+// Training forward, dense rows: prep_x and transpose_x in one pass (x is read once): a CTA owns 64 rows and walks the
+// column tiles; it writes the row-major splits X (B,Kp), stages each 64 x 64 tile in shared memory for the transposed
+// splits XT (Kp,Bp), and keeps the row sums of squares in registers (deterministic: 8 lanes per row, shuffle-reduced).
+__global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long B, int F, int Kp, long long Bp, int n_pad,
+                                                      float add_offset, float pad, __half *Xh, __half *Xl, __half *XTh,
+                                                      __half *XTl, float *inv_n2) {
+    __shared__ __half th[64][72], tl[64][72];
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int t = threadIdx.x;
+    const bool vec = (F & 3) == 0 && ((uintptr_t)x & 15) == 0;
+    float ss[2] = {0.f, 0.f};
+    for (int c0 = 0; c0 < Kp; c0 += 64) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = t + i * 256;            // row = idx / 8, 8-column piece = idx % 8
+            const int rr = idx >> 3, pc = idx & 7;
+            const long long r = r0 + rr;
+            const int c = c0 + pc * 8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            if (r < B && c < F) {
+                const float *src = x + r * F + c;
+                if (vec && c + 8 <= F) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+                    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += add_offset;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c + j < F) f[j] = __ldg(src + j) + add_offset;
+                }
+            }
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ss[i] += f[j] * f[j];
+                const bool one = (c + j == F) && n_pad > 0 && r < B;      // the ones column (pad-row column sums)
+                split_act(one ? 1.f : f[j], hi[j], lo[j]);
+            }
+            if (r < B && c < Kp) {
+                *reinterpret_cast<uint4 *>(Xh + r * Kp + c) = *reinterpret_cast<const uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(Xl + r * Kp + c) = *reinterpret_cast<const uint4 *>(lo);
+            }
+            *reinterpret_cast<uint4 *>(&th[rr][pc * 8]) = *reinterpret_cast<const uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(&tl[rr][pc * 8]) = *reinterpret_cast<const uint4 *>(lo);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = t + i * 256;            // output row (feature) = idx / 8, piece of 8 batch rows = idx % 8
+            const int cc = idx >> 3, pr = idx & 7;
+            const int c = c0 + cc;
+            const long long r = r0 + pr * 8;
+            if (c < Kp && r < Bp) {
+                __half oh[8], ol[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    oh[j] = th[pr * 8 + j][cc];
+                    ol[j] = tl[pr * 8 + j][cc];
+                }
+                *reinterpret_cast<uint4 *>(XTh + (long long)c * Bp + r) = *reinterpret_cast<const uint4 *>(oh);
+                *reinterpret_cast<uint4 *>(XTl + (long long)c * Bp + r) = *reinterpret_cast<const uint4 *>(ol);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float v = ss[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        const long long r = r0 + ((t + i * 256) >> 3);
+        if ((t & 7) == 0 && r < B) {
+            v += (float)n_pad * pad * pad;
+            inv_n2[r] = v > 0.f ? 1.0f / v : 0.f;
+        }
     }
 }
 
@@ -1415,19 +1499,31 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     SavedView w = saved_view(g, B, keep ? saved : ws, keep);
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
-    timing_begin(TK_PREP_X, 0.0, s);
-    prep_x_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
-        x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
-        unfold_geom(gp));
-    timing_end(s);
-    count_launch();
-    if (keep) {
-        dim3 tb(256);
-        dim3 xg((g.Kp + 63) / 64, (unsigned)((Bp + 63) / 64));
-        timing_begin(TK_TRANSPOSE_X, 0.0, s);
-        transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1]);
+    if (keep && !gp.unfold) {
+        // training forward on dense rows: X, X^T and the norms in one pass over x
+        timing_begin(TK_PREP_X, 0.0, s);
+        prep_xt_kernel<<<(unsigned)((Bp + 63) / 64), 256, 0, s>>>(x, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value,
+                                                                 w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2);
         timing_end(s);
         count_launch();
+    } else {
+        int gw = 32;                                   // lanes per row: smallest power of two >= Kp / 2
+        while (gw > 1 && gw / 2 >= g.Kp / 2) gw >>= 1;
+        const long long row_warps = (B * gw + 31) / 32;
+        timing_begin(TK_PREP_X, 0.0, s);
+        prep_x_kernel<<<(unsigned)((row_warps + warps - 1) / warps), warps * 32, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
+            x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
+            unfold_geom(gp), gw);
+        timing_end(s);
+        count_launch();
+        if (keep) {
+            dim3 tb(256);
+            dim3 xg((g.Kp + 63) / 64, (unsigned)((Bp + 63) / 64));
+            timing_begin(TK_TRANSPOSE_X, 0.0, s);
+            transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1]);
+            timing_end(s);
+            count_launch();
+        }
     }
     GemmParams p;
     memset(&p, 0, sizeof(p));

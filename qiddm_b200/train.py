@@ -168,7 +168,7 @@ class GraphedTrainStep:
         if not example_x.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (no CPU path)")
         for gparam in optimizer.param_groups:
-            if not gparam.get("capturable", False):
+            if "capturable" in gparam and not gparam["capturable"]:
                 raise RuntimeError("the optimizer must be built with capturable=True to live inside a CUDA graph")
         self.diff, self.opt, self.tau = diff, optimizer, tau
         self.x = example_x.clone()

@@ -183,18 +183,19 @@ def config1(cpu):
             emit(**rec)
 
 
-def unet_rate(tag, side, imgs_list, qdepth=3, simple=False):
+def unet_rate(tag, side, imgs_list, qdepth=3, simple=False, graphed=False):
     for imgs in imgs_list:
         torch.manual_seed(0)
         net = (qnn.UNetUndirectedS if simple else qnn.UNetUndirected)(3, 8, qdepth)
         try:
-            _, ms, ker, launches = train_step_rate(net, (side, side), imgs, 10, 1e-3, iters=3, warmup=2)
+            _, ms, ker, launches = train_step_rate(net, (side, side), imgs, 10, 1e-3, iters=3, warmup=2, graphed=graphed)
         except torch.OutOfMemoryError:
             emit(what=tag, images_per_step=imgs, error="oom")
             continue
         patches = 5782 if side == 28 else None
         emit(what=tag, model=f"{'UNetUndirectedS' if simple else 'UNetUndirected'}(3,8,{qdepth}) {side}x{side}",
-             images_per_step=imgs, tau=10, ms_per_step=round(ms, 3), train_samples_per_s=round(imgs / ms * 1e3, 1),
+             images_per_step=imgs, tau=10, cuda_graph=graphed, ms_per_step=round(ms, 3),
+             train_samples_per_s=round(imgs / ms * 1e3, 1),
              circuit_evals_per_s=(round(imgs * 10 * patches / ms * 1e3) if patches else None),
              lib_launches_per_step=launches, kernels=ker)
         del net
@@ -259,7 +260,8 @@ def main():
         elif w == "config1":
             config1(a.cpu)
         elif w == "config3":
-            unet_rate("config3_unet28", 28, (8, 64) if a.quick else (8, 64, 256))
+            unet_rate("config3_unet28", 28, (8, 64) if a.quick else (1, 8, 64, 256))
+            unet_rate("config3_unet28", 28, (8, 64) if a.quick else (1, 8, 64), graphed=True)
             unet_rate("config3_unet28_simple", 28, (64,), simple=True)
         elif w == "config4":
             config4(a.quick)

@@ -75,12 +75,14 @@ def test_gemm_equals_gate_path_and_auto_dispatch():
     d = O.desc_qdense(8, 256, O.REMAP_PI_TANH)
     g = torch.Generator().manual_seed(4)
     W = (torch.randn(1, 8, 8, 3, generator=g, dtype=torch.float64) * 0.4).cuda()
-    x = torch.rand(1000, 256, generator=g, dtype=torch.float64).cuda()
+    x = torch.rand(20000, 256, generator=g, dtype=torch.float64).cuda()
     a = run_stage(_spec(d, L.PATH_GATE), x, W)
     b = run_stage(_spec(d, L.PATH_GEMM), x, W)
     c = run_stage(_spec(d, L.PATH_AUTO), x, W)
     assert rel_to_max(b, a) <= 1e-5
-    assert torch.equal(b, c)                      # B = 1000 >= 2 * 256 -> AUTO picks the GEMM path
+    assert L.Plan.get(_spec(d, L.PATH_AUTO)).use_gemm(20000)
+    assert torch.equal(b, c)                      # cost model: 20000 instances of an 8-layer n = 8 circuit -> GEMM path
+    assert not L.Plan.get(_spec(d, L.PATH_AUTO)).use_gemm(100)
     small = run_stage(_spec(d, L.PATH_AUTO), x[:100], W)
     assert torch.equal(small, run_stage(_spec(d, L.PATH_GATE), x[:100], W))
 

@@ -34,7 +34,9 @@ def test_graphed_train_step_equals_eager_steps(model):
     # eager reference
     d0 = _diff(factories[model], goal, eps)
     d0.train()
-    o0 = torch.optim.Adam(d0.parameters(), lr=1e-2, capturable=True)
+    # SGD for the strict parameter comparison: Adam's g / (|g| + eps) turns round-off on analytically-zero gradients
+    # (e.g. the last RZ before a probability readout) into +-lr steps; Adam itself is covered below
+    o0 = torch.optim.SGD(d0.parameters(), lr=0.05)
     losses0 = []
     for x in batches:
         o0.zero_grad(set_to_none=True)
@@ -43,13 +45,39 @@ def test_graphed_train_step_equals_eager_steps(model):
         losses0.append(l.item())
     # graphed
     d1 = _diff(factories[model], goal, eps)
-    o1 = torch.optim.Adam(d1.parameters(), lr=1e-2, capturable=True)
+    o1 = torch.optim.SGD(d1.parameters(), lr=0.05)
     g = GraphedTrainStep(d1, o1, tau, batches[0])
     losses1 = [g.step(x).item() for x in batches]
     for a, b in zip(losses0, losses1):
         assert abs(a - b) <= 1e-5 * abs(a), (losses0, losses1)
     for (n0, p0), (_, p1) in zip(d0.named_parameters(), d1.named_parameters()):
-        assert rel_to_max(p1, p0) <= 1e-4, n0
+        assert rel_to_max(p1, p0) <= 1e-5, n0
+
+
+def test_graphed_train_step_with_capturable_adam_trains():
+    """The reference optimizer (Adam, src/mnist_exm.py:170) inside the graph: same loss trajectory as eager Adam."""
+    from qiddm_b200 import nn
+    from qiddm_b200.train import GraphedTrainStep
+    imgs, tau = 2, 5
+    eps = torch.normal(0.5, 0.2, size=(imgs, 64), generator=torch.Generator().manual_seed(1)).double().cuda()
+    x = torch.rand(imgs, 64, dtype=torch.float64, generator=torch.Generator().manual_seed(2)).cuda()
+    d0 = _diff(lambda: nn.QIDDM_LL_noise(64, 4, 3, 2), "data", eps)
+    d0.train()
+    o0 = torch.optim.Adam(d0.parameters(), lr=1e-2, capturable=True)
+    l0 = []
+    for _ in range(12):
+        o0.zero_grad(set_to_none=True)
+        (l,) = d0(x=x, T=tau)
+        o0.step()
+        l0.append(l.item())
+    d1 = _diff(lambda: nn.QIDDM_LL_noise(64, 4, 3, 2), "data", eps)
+    g = GraphedTrainStep(d1, torch.optim.Adam(d1.parameters(), lr=1e-2, capturable=True), tau, x)
+    l1 = [g.step(x).item() for _ in range(12)]
+    assert l1[-1] < l1[0]
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-3 * abs(a), (l0, l1)
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(d1, torch.optim.Adam(d1.parameters(), lr=1e-2), tau, x)
 
 
 def test_graphed_sampler_equals_diffusion_sample():
