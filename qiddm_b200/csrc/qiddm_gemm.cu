@@ -876,11 +876,37 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
 // splits XT (Kp,Bp), and keeps the row sums of squares in registers (deterministic: 8 lanes per row, shuffle-reduced).
 __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long B, int F, int Kp, long long Bp, int n_pad,
                                                       float add_offset, float pad, __half *Xh, __half *Xl, __half *XTh,
-                                                      __half *XTl, float *inv_n2) {
+                                                      __half *XTl, float *inv_n2, const UnfoldGeom u) {
     __shared__ __half th[64][72], tl[64][72];
+    extern __shared__ int ftab[];          // QConv: [2 * F] feature table (see prep_x_kernel)
     const long long r0 = (long long)blockIdx.x * 64;
     const int t = threadIdx.x;
-    const bool vec = (F & 3) == 0 && ((uintptr_t)x & 15) == 0;
+    const bool vec = !u.on && (F & 3) == 0 && ((uintptr_t)x & 15) == 0;
+    long long base[2];
+    int py[2] = {0, 0}, px[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const long long r = r0 + ((t + i * 256) >> 3);
+        base[i] = r * F;
+        if (u.on && r < B) {
+            const int P = u.Hout * u.Wout;
+            const long long b = r / P;
+            const int rr = (int)(r - b * P);
+            py[i] = rr / u.Wout;
+            px[i] = rr - py[i] * u.Wout;
+            base[i] = b * u.C * u.H * u.W + (long long)py[i] * u.W + px[i];
+        }
+    }
+    if (u.on) {
+        const int kk = u.kh * u.kw;
+        for (int c = t; c < F; c += 256) {
+            const int ch = c / kk, q = c - ch * kk;
+            const int ky = q / u.kw, kx = q - ky * u.kw;
+            ftab[c] = (ch * u.H + (ky - u.ph)) * u.W + (kx - u.pw);
+            ftab[F + c] = ((ky - u.ph) << 16) | ((kx - u.pw) & 0xffff);
+        }
+        __syncthreads();
+    }
     float ss[2] = {0.f, 0.f};
     for (int c0 = 0; c0 < Kp; c0 += 64) {
 #pragma unroll
@@ -893,13 +919,24 @@ __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long 
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = 0.f;
             if (r < B && c < F) {
-                const float *src = x + r * F + c;
-                if (vec && c + 8 <= F) {
+                if (u.on) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c + j < F) {
+                            const int yx = ftab[F + c + j];
+                            const int iy = py[i] + (yx >> 16), ix = px[i] + (int)(short)(yx & 0xffff);
+                            const bool in = iy >= 0 && iy < u.H && ix >= 0 && ix < u.W;
+                            f[j] = (in ? __ldg(x + base[i] + ftab[c + j]) : 0.f) + add_offset;
+                        }
+                    }
+                } else if (vec && c + 8 <= F) {
+                    const float *src = x + base[i] + c;
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
                     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] += add_offset;
                 } else {
+                    const float *src = x + base[i] + c;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (c + j < F) f[j] = __ldg(src + j) + add_offset;
@@ -1135,48 +1172,6 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
         for (int o = 16; o > 0; o >>= 1)
             if (o < gw) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
         if (sub == 0 && active) S[r] = s_part;
-    }
-}
-
-// X (B,Kp) activation splits (hi, lo*2^11) -> transposed weight-side splits (Kp,Bp): hi, hi*2^-11, lo
-__global__ void __launch_bounds__(256) transpose_x_kernel(const __half *Xh, const __half *Xl, long long B, int Kp, long long Bp,
-                                                          __half *XTh, __half *XTl) {
-    // 64 x 64 tiles, 16-byte global accesses on both sides (Kp and Bp are multiples of 8)
-    __shared__ __half th[64][72], tl[64][72];
-    const long long r0 = (long long)blockIdx.y * 64;
-    const int c0 = blockIdx.x * 64;
-    const int t = threadIdx.x;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int idx = t + i * 256;            // 512 16-byte pieces per array: row = idx / 8, piece = idx % 8
-        const int rr = idx >> 3, pc = idx & 7;
-        const long long r = r0 + rr;
-        const int c = c0 + pc * 8;
-        uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-        if (r < B && c < Kp) {
-            vh = *reinterpret_cast<const uint4 *>(Xh + r * Kp + c);
-            vl = *reinterpret_cast<const uint4 *>(Xl + r * Kp + c);
-        }
-        *reinterpret_cast<uint4 *>(&th[rr][pc * 8]) = vh;
-        *reinterpret_cast<uint4 *>(&tl[rr][pc * 8]) = vl;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int idx = t + i * 256;            // output row (feature) = idx / 8, piece of 8 batch rows = idx % 8
-        const int cc = idx >> 3, pr = idx & 7;
-        const int c = c0 + cc;
-        const long long r = r0 + pr * 8;
-        if (c < Kp && r < Bp) {
-            __half oh[8], ol[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                oh[j] = th[pr * 8 + j][cc];
-                ol[j] = tl[pr * 8 + j][cc];
-            }
-            *reinterpret_cast<uint4 *>(XTh + (long long)c * Bp + r) = *reinterpret_cast<const uint4 *>(oh);
-            *reinterpret_cast<uint4 *>(XTl + (long long)c * Bp + r) = *reinterpret_cast<const uint4 *>(ol);
-        }
     }
 }
 
@@ -1499,11 +1494,12 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     SavedView w = saved_view(g, B, keep ? saved : ws, keep);
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
-    if (keep && !gp.unfold) {
-        // training forward on dense rows: X, X^T and the norms in one pass over x
+    if (keep) {
+        // training forward: X, X^T and the norms in one pass over x (QConv: through the fused patch-unfold)
         timing_begin(TK_PREP_X, 0.0, s);
-        prep_xt_kernel<<<(unsigned)((Bp + 63) / 64), 256, 0, s>>>(x, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value,
-                                                                 w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2);
+        prep_xt_kernel<<<(unsigned)((Bp + 63) / 64), 256, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
+            x, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2,
+            unfold_geom(gp));
         timing_end(s);
         count_launch();
     } else {
@@ -1516,14 +1512,6 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
             unfold_geom(gp), gw);
         timing_end(s);
         count_launch();
-        if (keep) {
-            dim3 tb(256);
-            dim3 xg((g.Kp + 63) / 64, (unsigned)((Bp + 63) / 64));
-            timing_begin(TK_TRANSPOSE_X, 0.0, s);
-            transpose_x_kernel<<<xg, tb, 0, s>>>(w.X[0], w.X[1], B, g.Kp, Bp, w.XT[0], w.XT[1]);
-            timing_end(s);
-            count_launch();
-        }
     }
     GemmParams p;
     memset(&p, 0, sizeof(p));

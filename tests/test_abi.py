@@ -83,3 +83,25 @@ def test_product_path_has_no_cpu_fallback():
         m.cpu()(torch.rand(2, 1, 8, 8))
     src = "".join(p.read_text() for p in (ROOT / "qiddm_b200").rglob("*.py"))
     assert "oracle" not in src.replace("oracle/", "")  # the product never imports the test oracle
+
+
+def test_host_side_argument_checks_of_the_new_entry_points(lib):
+    """No compute: NULL / invalid arguments are rejected before any launch (no GPU needed)."""
+    from qiddm_b200 import _lib as L
+    assert lib.qiddm_sym_eigh_max_dim() >= 100
+    assert lib.qiddm_sym_eigh_f64(None, 4, None, None, None) == -1
+    assert lib.qiddm_batchnorm_workspace_bytes(0) == 0 and lib.qiddm_batchnorm_workspace_bytes(8) > 0
+    assert lib.qiddm_batchnorm_forward(None, None, 1, 1, 1, 1, None, None, None, None, None, None, 0.1, 1e-5, None, None) == -1
+    assert lib.qiddm_batchnorm_backward(None, None, None, 1, 1, 1, 1, None, None, None, None, None, None, None) == -1
+    assert lib.qiddm_upsample_bilinear_forward(None, None, 1, 1, 2, 2, 4, 4, 0.5, 0.5, None) == -1
+    assert lib.qiddm_stream_capture_id(None) == 0 or True      # no context on a CPU box: must not crash
+    # QConv collapse path: a descriptor / unfold geometry mismatch yields 0 bytes / EINVAL
+    s = L.StageSpec(n_qubits=7, layers_per_block=3, init=L.INIT_AMPLITUDE, n_features=72, pad_value=0.5, add_offset=0.1,
+                    readout=L.READ_PROBS, read_count=8, read_stride=2, post_scale=64.0, clamp=True)
+    plan = L.Plan(s)
+    good = L.UnfoldDesc(8, 28, 28, 3, 3, 1, 1)
+    bad = L.UnfoldDesc(4, 28, 28, 3, 3, 1, 1)           # 4*9 != 72 features
+    assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(good), 10) > 0
+    assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(bad), 10) == 0
+    assert lib.qiddm_qconv_gemm_workspace_bytes(plan.handle, C.byref(good), 10) > lib.qiddm_gemm_workspace_bytes(plan.handle, 7840) - 1
+    assert lib.qiddm_qconv_gemm_forward(plan.handle, None, C.byref(good), None, None, None, None, 1, 3, None) == -1

@@ -209,3 +209,24 @@ def test_reference_checkpoint_loads_and_generates_letter():
     img = out[0, 0].cpu()
     contrast = img[6:22, 6:22].mean() - (img.sum() - img[6:22, 6:22].sum()) / (784 - 256)
     assert contrast > 0.3
+
+
+def test_qconv2d_collapse_path_edge_cases():
+    """Empty image batch, a single patch row, and an input that needs no gradient (first UNet layer)."""
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import nn
+    torch.manual_seed(2)
+    m = nn.QConv2d(1, 8, kernel_size=3, padding=1, qdepth=2).cuda()
+    m.path = L.PATH_GEMM
+    assert m(torch.zeros(0, 1, 6, 6, device="cuda", dtype=torch.float64)).shape == (0, 8, 6, 6)
+    x = torch.rand(1, 1, 1, 1, dtype=torch.float64)                 # one patch, 8 of 9 features in the zero padding
+    ref = O.qconv_forward(x, m.weights.detach().cpu(), 8, m.kernel_size, m.padding)
+    assert rel_to_max(m(x.cuda()), ref) <= TOL
+    x = torch.rand(6, 1, 10, 10, dtype=torch.float64)               # no grad for the image: the dX GEMM is skipped
+    Wr = m.weights.detach().cpu().clone().requires_grad_(True)
+    ref = O.qconv_forward(x, Wr, 8, m.kernel_size, m.padding)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    out = m(x.cuda())
+    (out * g.cuda()).sum().backward()
+    assert rel_to_max(out, ref) <= TOL and rel_to_max(m.weights.grad, Wr.grad) <= 1e-4
