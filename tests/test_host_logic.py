@@ -137,3 +137,41 @@ def test_shard_batch_covers_everything_once():
         parts = [shard_batch(x, r, world) for r in range(world)]
         assert torch.equal(torch.cat(parts), x)
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_path_dispatch_cost_model_against_the_measured_sweep():
+    """Plan.use_gemm (gate-by-gate vs unitary collapse) replayed against the committed B200 sweep
+    (profiles/r1_configs.jsonl, scripts/bench_configs.py): wrong on few points, and never expensively."""
+    import json
+    from pathlib import Path
+    from qiddm_b200 import _lib as L
+
+    class FakePlan(L.Plan):                     # the rule only needs the descriptor
+        def __init__(self, spec):
+            self.spec = spec
+
+        def gemm_supported(self):
+            return True
+
+    rows = [json.loads(l) for l in (Path(__file__).resolve().parent.parent / "profiles" / "r1_configs.jsonl").open()]
+    pts = {}
+    for r in rows:
+        if r["what"] == "sweep" and r["family"] == "qdense":
+            pts.setdefault((r["n"], r["depth"], r["batch"]), {})[r["path"]] = r["fwd_bwd_ms"]
+    both = {k: v for k, v in pts.items() if len(v) == 2}
+    assert len(both) >= 100
+    wrong, worst = 0, 1.0
+    for (n, depth, batch), v in both.items():
+        feats = 784 if n == 10 else 1 << n
+        spec = L.StageSpec(n_qubits=n, layers_per_block=depth, init=L.INIT_AMPLITUDE, n_features=feats, read_count=feats)
+        pick = "gemm" if FakePlan(spec).use_gemm(batch) else "gate"
+        best = min(v, key=v.get)
+        if pick != best:
+            wrong += 1
+            worst = max(worst, v[pick] / v[best])
+    assert wrong <= 0.1 * len(both) and worst <= 1.3, (wrong, worst)
+    # forced paths and the re-upload families
+    spec = L.StageSpec(n_qubits=10, layers_per_block=60, init=L.INIT_AMPLITUDE, n_features=784, read_count=784, path=L.PATH_GATE)
+    assert not FakePlan(spec).use_gemm(1 << 20)
+    spec = L.StageSpec(n_qubits=10, layers_per_block=60, init=L.INIT_AMPLITUDE, n_features=784, read_count=784, path=L.PATH_GEMM)
+    assert FakePlan(spec).use_gemm(1)
