@@ -297,7 +297,11 @@ def run_b200(args):
         achieved = kd["work"] / (kd["ms"] * 1e-3) / 1e12
         roofline = {"kernel": "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::f16 + TMA, fused |Y|^2 readout epilogue)",
                     "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tc_peak, "traffic": None,
+                    "frac": achieved / tc_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's three GEMM launches, from
+                    # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv)
+                    "traffic": 3.41e9 if (B == 262144 and args.precision == 3 and world == 1) else None,
+                    "traffic_unit": "bytes/launch (algorithmic operand bytes: 3.2e9)",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
                     "ms_per_launch": per_launch_ms, "launches": kd["launches"],
                     "algorithmic_flops": "2*M*N*K per GEMM (single pass); precision %d executes %dx that"

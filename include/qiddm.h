@@ -146,17 +146,18 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
 
 /* QConv on the unitary-collapse path (replaces torch.nn.Unfold + einops + the missing QNode call of
  * nn/qconv.py:76-86 and, in eval mode, the QubitUnitary path of nn/qconv.py:92-126): `collapsed` comes from
- * qiddm_gemm_prepare; img (n_images, C, H, W) fp32 and out / grad_out (n_images, read_count, H_out, W_out) fp32 are
- * NCHW; the patch-unfold is fused into the operand preparation and the col2im of the image gradient runs as one
+ * qiddm_gemm_prepare; img (n_images, C, H, W) and out / grad_out (n_images, read_count, H_out, W_out) are NCHW tensors
+ * of io_dtype (QIDDM_DTYPE_F32, or QIDDM_DTYPE_F64 as the reference's float64 UNet passes them — read and written in
+ * place of a cast; the simulation itself is fp32); the patch-unfold is fused into the operand preparation and the col2im of the image gradient runs as one
  * gather kernel (grad_img is OVERWRITTEN; may be NULL). */
 size_t qiddm_qconv_gemm_saved_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images);
 size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images);
 int qiddm_qconv_gemm_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
-                             const float *img, float *out, void *saved, void *workspace, int64_t n_images,
+                             int io_dtype, const void *img, void *out, void *saved, void *workspace, int64_t n_images,
                              int precision, qiddm_stream_t stream);
 int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
-                              const float *img, const void *weights, int weights_dtype, const float *grad_out,
-                              const void *saved, float *grad_img, void *grad_weights, void *workspace,
+                              int io_dtype, const void *img, const void *weights, int weights_dtype, const void *grad_out,
+                              const void *saved, void *grad_img, void *grad_weights, void *workspace,
                               int64_t n_images, int precision, qiddm_stream_t stream);
 
 /* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the

@@ -132,10 +132,10 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
             f.restype = C.c_size_t
             f.argtypes = [vp, C.POINTER(UnfoldDesc), i64]
         lib.qiddm_qconv_gemm_forward.restype = i32
-        lib.qiddm_qconv_gemm_forward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), vp, vp, vp, vp, i64, i32, vp]
+        lib.qiddm_qconv_gemm_forward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), i32, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_qconv_gemm_backward.restype = i32
-        lib.qiddm_qconv_gemm_backward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, vp, vp, vp, i64,
-                                                  i32, vp]
+        lib.qiddm_qconv_gemm_backward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), i32, vp, vp, i32, vp, vp, vp, vp, vp,
+                                                  i64, i32, vp]
         lib.qiddm_timing_enable.restype = None
         lib.qiddm_timing_enable.argtypes = [i32]
         lib.qiddm_timing_collect.restype = i32
@@ -486,10 +486,12 @@ class Plan:
         _require_cuda(img, "input")
         col = self.gemm_prepare(weights)
         dev = col.device
-        img = img.to(torch.float32).contiguous()
+        # float64 images (the reference's UNet) are read and written in place of a cast; the simulation is fp32
+        io = torch.float64 if img.dtype == torch.float64 else torch.float32
+        img = img.to(io).contiguous()
         n = img.shape[0]
         ho, wo = self._out_hw(img, unfold)
-        out = torch.empty((n, self.spec.read_count, ho, wo), dtype=torch.float32, device=dev)
+        out = torch.empty((n, self.spec.read_count, ho, wo), dtype=io, device=dev)
         saved = None
         with torch.cuda.device(dev):
             if save:
@@ -499,7 +501,8 @@ class Plan:
             else:
                 ws = torch.empty(int(self.lib.qiddm_qconv_gemm_saved_bytes(self.handle, C.byref(unfold), n)),
                                  dtype=torch.uint8, device=dev)
-            check(self.lib.qiddm_qconv_gemm_forward(self.handle, _ptr(col), C.byref(unfold), _ptr(img), _ptr(out),
+            check(self.lib.qiddm_qconv_gemm_forward(self.handle, _ptr(col), C.byref(unfold),
+                                                    DTYPE_F64 if io == torch.float64 else DTYPE_F32, _ptr(img), _ptr(out),
                                                     _ptr(saved), _ptr(ws), n, self.spec.gemm_precision,
                                                     self._stream(dev)), "qiddm_qconv_gemm_forward")
         return (out, saved) if save else out
@@ -510,15 +513,17 @@ class Plan:
         w = self._check_weights(weights)
         col = self.gemm_prepare(weights)
         dev = col.device
-        img = img.to(torch.float32).contiguous()
-        go = grad_out.to(torch.float32).contiguous()
+        io = torch.float64 if img.dtype == torch.float64 else torch.float32
+        img = img.to(io).contiguous()
+        go = grad_out.to(io).contiguous()
         n = img.shape[0]
         grad_img = torch.empty_like(img) if need_grad_in else None
         grad_w = torch.empty_like(w) if need_grad_w else None
         with torch.cuda.device(dev):
             ws = torch.empty(int(self.lib.qiddm_qconv_gemm_workspace_bytes(self.handle, C.byref(unfold), n)),
                              dtype=torch.uint8, device=dev)
-            check(self.lib.qiddm_qconv_gemm_backward(self.handle, _ptr(col), C.byref(unfold), _ptr(img), _ptr(w),
+            check(self.lib.qiddm_qconv_gemm_backward(self.handle, _ptr(col), C.byref(unfold),
+                                                     DTYPE_F64 if io == torch.float64 else DTYPE_F32, _ptr(img), _ptr(w),
                                                      _wdtype(w), _ptr(go), _ptr(saved), _ptr(grad_img), _ptr(grad_w),
                                                      _ptr(ws), n, self.spec.gemm_precision, self._stream(dev)),
                   "qiddm_qconv_gemm_backward")

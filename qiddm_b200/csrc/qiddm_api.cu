@@ -417,27 +417,31 @@ size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfo
 }
 
 int qiddm_qconv_gemm_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
-                             const float *img, float *out, void *saved, void *workspace, int64_t n_images,
+                             int io_dtype, const void *img, void *out, void *saved, void *workspace, int64_t n_images,
                              int precision, qiddm_stream_t stream) {
     if (!plan || !collapsed || !workspace || n_images < 0) return QIDDM_EINVAL;
     if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
     if (!unfold_valid(plan, unfold) || (precision != 1 && precision != 3)) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     if (n_images == 0) return QIDDM_OK;
     if (!img || !out) return QIDDM_EINVAL;
     const long long B = n_images * unfold_patches(unfold);
     if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
     GateParams gp = make_params(plan, unfold, B);
+    gp.io64 = io_dtype == QIDDM_DTYPE_F64 ? 1 : 0;
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
-    return gemm_forward(g, gp, collapsed, img, out, saved, workspace, B, precision, (cudaStream_t)stream);
+    return gemm_forward(g, gp, collapsed, reinterpret_cast<const float *>(img), reinterpret_cast<float *>(out), saved, workspace,
+                        B, precision, (cudaStream_t)stream);
 }
 
 int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
-                              const float *img, const void *weights, int weights_dtype, const float *grad_out,
-                              const void *saved, float *grad_img, void *grad_weights, void *workspace,
+                              int io_dtype, const void *img, const void *weights, int weights_dtype, const void *grad_out,
+                              const void *saved, void *grad_img, void *grad_weights, void *workspace,
                               int64_t n_images, int precision, qiddm_stream_t stream) {
     if (!plan || !collapsed || !workspace || !weights || n_images < 0) return QIDDM_EINVAL;
     if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
     if (!unfold_valid(plan, unfold) || (precision != 1 && precision != 3)) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     if (n_images == 0) {
         if (grad_weights) {
@@ -451,9 +455,11 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
     const long long B = n_images * unfold_patches(unfold);
     if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
     GateParams gp = make_params(plan, unfold, B);
+    gp.io64 = io_dtype == QIDDM_DTYPE_F64 ? 1 : 0;
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
     float *gut = nullptr;
-    int rc = gemm_backward(g, gp, collapsed, img, grad_out, saved, grad_img, &gut, workspace, B, precision, s);
+    int rc = gemm_backward(g, gp, collapsed, reinterpret_cast<const float *>(img), reinterpret_cast<const float *>(grad_out), saved,
+                           reinterpret_cast<float *>(grad_img), &gut, workspace, B, precision, s);
     if (rc != QIDDM_OK) return rc;
     if (!grad_weights) return QIDDM_OK;
     qiddm_plan t = basis_plan(plan);

@@ -203,6 +203,7 @@ struct GemmParams {
     const unsigned int *gmax_bits;
     float add_offset;
     int dbg_pfd, dbg_nostore;   // tuning knobs (QIDDM_GEMM_PFD, QIDDM_GEMM_NOSTORE)
+    int out_f64;             // EPI_PROBS, QConv: `out` is a float64 tensor
     int out_P;               // EPI_PROBS, QConv: > 0 -> row = (image b, patch r), out[(b * n_out + m) * out_P + r] (NCHW)
     // pair kernel: epilogue through shared memory + TMA stores (fp32 boxes of 32 rows)
     int tma_epi;
@@ -258,10 +259,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
         const int m0 = col >> 1;
         if (p.out_P > 0) {      // QConv: consecutive rows (patches) of one image are consecutive addresses per channel
             const int b = row / p.out_P, r = row - b * p.out_P;
-            float *dst = p.out + ((long long)b * p.n_out + m0) * p.out_P + r;
+            const long long o0 = ((long long)b * p.n_out + m0) * p.out_P + r;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (m0 + j < p.n_out) dst[(long long)j * p.out_P] = o[j];
+            for (int j = 0; j < 8; ++j) {
+                if (m0 + j >= p.n_out) break;
+                if (p.out_f64) reinterpret_cast<double *>(p.out)[o0 + (long long)j * p.out_P] = (double)o[j];
+                else p.out[o0 + (long long)j * p.out_P] = o[j];
+            }
             return;
         }
         float *dst = p.out + (long long)row * p.ldo + m0;
@@ -274,13 +278,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
                 if (m0 + j < p.n_out) dst[j] = o[j];
         }
     } else if (p.epi == EPI_DX) {
-        float *dst = p.out + (long long)row * p.ldo + col;
-        if (p.dx_x == nullptr) {       // QConv: plain rows; the normalisation term is added by fold_rows_kernel
+        if (p.dx_x == nullptr) {       // QConv: dX stored TRANSPOSED (feature-major, ld = ldo): consecutive rows (patches) are
+                                       // consecutive addresses, for this store and for fold_rows_kernel's gather
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (col + j < p.N) dst[j] = v[j] * dx_a;
+                if (col + j < p.N) p.out[(long long)(col + j) * p.ldo + row] = v[j] * dx_a;
             return;
         }
+        float *dst = p.out + (long long)row * p.ldo + col;
         const float *xs = p.dx_x + (long long)row * p.ldo + col;
         if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
             float4 xv[4];
@@ -550,13 +555,14 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
                 st_shared_f4(orow, o[0], o[1], o[2], o[3]);
                 st_shared_f4(orow + 16u, o[4], o[5], o[6], o[7]);
             }
+        } else if (p.dx_x == nullptr) {   // EPI_DX, QConv: feature-major dX -> stage [feature][patch] (16 x 32 floats)
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + (j * 32u + (uint32_t)lane) * 4u), "f"(v[j] * dx_a) : "memory");
         } else {   // EPI_DX
             const float *xs = p.dx_x + (long long)row * p.ldo + col;
             float x[16];
-            if (p.dx_x == nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            } else if (row_ok && col + 16 <= p.N) {
+            if (row_ok && col + 16 <= p.N) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 t = __ldg(reinterpret_cast<const float4 *>(xs) + j);
@@ -579,6 +585,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
             if (p.epi == EPI_PROBS) {
                 if (p.y_out != nullptr) tma_store_2d(&p.y_map, sb, col, rbase);
                 if (p.out != nullptr) tma_store_2d(&p.o_map, sb + 2048u, col >> 1, rbase);
+            } else if (p.dx_x == nullptr) {
+                tma_store_2d(&p.o_map, sb, rbase, col);     // (patch, feature) coordinates of the feature-major dX
             } else {
                 tma_store_2d(&p.o_map, sb, col, rbase);
             }
@@ -805,11 +813,15 @@ __device__ __forceinline__ void split_act(float v, __half &hi, __half &lo) {
 // x (B,F) fp32 -> Xh/Xl (B,Kp) fp16 (hi, lo*2^11) and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).  One warp per row.
 // Column F (when the state has constant pad rows) is a column of ones: it meets zero weights in the forward
 // and dX GEMMs and yields sum_b G[b,n] (the pad rows of dW) in the dW GEMM.
+__device__ __forceinline__ float ld_io(const void *p, long long i, int io64) {
+    return io64 ? (float)__ldg(reinterpret_cast<const double *>(p) + i) : __ldg(reinterpret_cast<const float *>(p) + i);
+}
+
 struct UnfoldGeom {      // fused patch-unfold (QConv, nn/qconv.py:76-77): row = (image, y, x), feature = (ch, ky, kx)
     int on, C, H, W, kh, kw, ph, pw, Hout, Wout;
 };
 __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_pad, float add_offset, float pad,
-                              __half *Xh, __half *Xl, float *inv_n2, int want_lo, const UnfoldGeom u, int gw) {
+                              __half *Xh, __half *Xl, float *inv_n2, int want_lo, const UnfoldGeom u, int gw, int io64) {
     // QConv: per-CTA feature table (offset inside the image relative to the patch origin, packed (dy, dx) for the
     // bounds test), so the per-element work is one table read instead of three integer divisions
     extern __shared__ int ftab[];          // [2 * F] when u.on
@@ -849,7 +861,7 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
                     const int yx = ftab[F + cc];
                     const int iy = py + (yx >> 16), ix = px + (int)(short)(yx & 0xffff);
                     const bool in = iy >= 0 && iy < u.H && ix >= 0 && ix < u.W;       // zero padding of torch.nn.Unfold
-                    f[j] = (in ? __ldg(x + base + ftab[cc]) : 0.f) + add_offset;
+                    f[j] = (in ? ld_io(x, base + ftab[cc], io64) : 0.f) + add_offset;
                 } else {
                     f[j] = __ldg(x + base + cc) + add_offset;
                 }
@@ -871,42 +883,16 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
     }
 }
 
-// Training forward, dense rows: prep_x and transpose_x in one pass (x is read once): a CTA owns 64 rows and walks the
-// column tiles; it writes the row-major splits X (B,Kp), stages each 64 x 64 tile in shared memory for the transposed
-// splits XT (Kp,Bp), and keeps the row sums of squares in registers (deterministic: 8 lanes per row, shuffle-reduced).
+// Training forward, dense rows: operand splits and their transposes in one pass (x is read once): a CTA owns 64 rows and
+// walks the column tiles; it writes the row-major splits X (B,Kp), stages each 64 x 64 tile in shared memory for the
+// transposed splits XT (Kp,Bp), and keeps the row sums of squares in registers (deterministic: 8 lanes per row).
 __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long B, int F, int Kp, long long Bp, int n_pad,
                                                       float add_offset, float pad, __half *Xh, __half *Xl, __half *XTh,
-                                                      __half *XTl, float *inv_n2, const UnfoldGeom u) {
+                                                      __half *XTl, float *inv_n2) {
     __shared__ __half th[64][72], tl[64][72];
-    extern __shared__ int ftab[];          // QConv: [2 * F] feature table (see prep_x_kernel)
     const long long r0 = (long long)blockIdx.x * 64;
     const int t = threadIdx.x;
-    const bool vec = !u.on && (F & 3) == 0 && ((uintptr_t)x & 15) == 0;
-    long long base[2];
-    int py[2] = {0, 0}, px[2] = {0, 0};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const long long r = r0 + ((t + i * 256) >> 3);
-        base[i] = r * F;
-        if (u.on && r < B) {
-            const int P = u.Hout * u.Wout;
-            const long long b = r / P;
-            const int rr = (int)(r - b * P);
-            py[i] = rr / u.Wout;
-            px[i] = rr - py[i] * u.Wout;
-            base[i] = b * u.C * u.H * u.W + (long long)py[i] * u.W + px[i];
-        }
-    }
-    if (u.on) {
-        const int kk = u.kh * u.kw;
-        for (int c = t; c < F; c += 256) {
-            const int ch = c / kk, q = c - ch * kk;
-            const int ky = q / u.kw, kx = q - ky * u.kw;
-            ftab[c] = (ch * u.H + (ky - u.ph)) * u.W + (kx - u.pw);
-            ftab[F + c] = ((ky - u.ph) << 16) | ((kx - u.pw) & 0xffff);
-        }
-        __syncthreads();
-    }
+    const bool vec = (F & 3) == 0 && ((uintptr_t)x & 15) == 0;
     float ss[2] = {0.f, 0.f};
     for (int c0 = 0; c0 < Kp; c0 += 64) {
 #pragma unroll
@@ -919,24 +905,13 @@ __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long 
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = 0.f;
             if (r < B && c < F) {
-                if (u.on) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (c + j < F) {
-                            const int yx = ftab[F + c + j];
-                            const int iy = py[i] + (yx >> 16), ix = px[i] + (int)(short)(yx & 0xffff);
-                            const bool in = iy >= 0 && iy < u.H && ix >= 0 && ix < u.W;
-                            f[j] = (in ? __ldg(x + base[i] + ftab[c + j]) : 0.f) + add_offset;
-                        }
-                    }
-                } else if (vec && c + 8 <= F) {
-                    const float *src = x + base[i] + c;
+                const float *src = x + r * F + c;
+                if (vec && c + 8 <= F) {
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
                     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] += add_offset;
                 } else {
-                    const float *src = x + base[i] + c;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (c + j < F) f[j] = __ldg(src + j) + add_offset;
@@ -990,13 +965,108 @@ __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long 
     }
 }
 
-// QConv col2im of the dX rows with the normalisation term of the amplitude embedding, gather form (one thread per
-// image element, no atomics):  grad_img[b,ch,iy,ix] = sum_{(ky,kx): patch p=(b, iy-ky+ph, ix-kx+pw) exists}
-//     dXrows[p][(ch,ky,kx)] - 2 (img + add_offset) inv_n2[p] S[p]
-__global__ void __launch_bounds__(256) fold_rows_kernel(const float *dx_rows, int ldx, const float *img, const float *inv_n2,
-                                                        const float *S, long long n_elems, float add_offset,
-                                                        const UnfoldGeom u, float *grad_img) {
-    const int P = u.Hout * u.Wout, kk = u.kh * u.kw;
+// Training forward, QConv: the same outputs straight from the NCHW image (patch-unfold fused).  A CTA owns 64 consecutive
+// patches; a thread keeps ONE patch and walks the features, so for a given feature the 32 lanes of a warp read 32
+// neighbouring pixels (coalesced).  The 64 x 64 (feature, patch) tile goes through shared memory once: XT rows are
+// written as 128-byte runs of patches, X rows as 16-byte pieces of features.
+__global__ void __launch_bounds__(256) prep_xt_unfold_kernel(const void *img, int io64, long long B, int F, int Kp, long long Bp,
+                                                             int n_pad, float add_offset, float pad, __half *Xh, __half *Xl,
+                                                             __half *XTh, __half *XTl, float *inv_n2, const UnfoldGeom u) {
+    __shared__ __half th[64][66], tl[64][66];     // [feature of the tile][patch]; 33-word rows: conflict-free both ways
+    __shared__ float ssum[4][64];
+    extern __shared__ int ftab[];                 // [2 * F] feature table (see prep_x_kernel)
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int t = threadIdx.x, rr = t & 63, cg = t >> 6;
+    const long long r = r0 + rr;
+    const bool rowok = r < B;
+    long long base = 0;
+    int py = 0, px = 0;
+    if (rowok) {
+        const int P = u.Hout * u.Wout;
+        const long long b = r / P;
+        const int q = (int)(r - b * P);
+        py = q / u.Wout;
+        px = q - py * u.Wout;
+        base = b * u.C * u.H * u.W + (long long)py * u.W + px;
+    }
+    {
+        const int kk = u.kh * u.kw;
+        for (int c = t; c < F; c += 256) {
+            const int ch = c / kk, q = c - ch * kk;
+            const int ky = q / u.kw, kx = q - ky * u.kw;
+            ftab[c] = (ch * u.H + (ky - u.ph)) * u.W + (kx - u.pw);
+            ftab[F + c] = ((ky - u.ph) << 16) | ((kx - u.pw) & 0xffff);
+        }
+    }
+    __syncthreads();
+    float ss = 0.f;
+    for (int c0 = 0; c0 < Kp; c0 += 64) {
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const int cc = cg + 4 * k, c = c0 + cc;
+            float f = 0.f;
+            if (rowok && c < F) {
+                const int yx = ftab[F + c];
+                const int iy = py + (yx >> 16), ix = px + (int)(short)(yx & 0xffff);
+                const bool in = iy >= 0 && iy < u.H && ix >= 0 && ix < u.W;       // zero padding of torch.nn.Unfold
+                f = (in ? ld_io(img, base + ftab[c], io64) : 0.f) + add_offset;
+            }
+            ss += f * f;
+            __half hi, lo;
+            split_act((c == F && n_pad > 0 && rowok) ? 1.f : f, hi, lo);
+            th[cc][rr] = hi;
+            tl[cc][rr] = lo;
+        }
+        __syncthreads();
+        {   // XT: feature rows of 64 patches = 32 half2 per row
+            const int lane = t & 31, w = t >> 5;
+            const long long r2 = r0 + 2 * lane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int cc = w + 8 * k, c = c0 + cc;
+                if (c < Kp && r2 < Bp) {
+                    *reinterpret_cast<__half2 *>(XTh + (long long)c * Bp + r2) = *reinterpret_cast<const __half2 *>(&th[cc][2 * lane]);
+                    *reinterpret_cast<__half2 *>(XTl + (long long)c * Bp + r2) = *reinterpret_cast<const __half2 *>(&tl[cc][2 * lane]);
+                }
+            }
+        }
+        {   // X: patch rows; 4 threads per row, two 8-feature pieces each
+            const int row = t >> 2, q = t & 3;
+            const long long rx = r0 + row;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc0 = q * 16 + h * 8, c = c0 + cc0;
+                if (rx < B && c < Kp) {
+                    __half oh[8], ol[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        oh[j] = th[cc0 + j][row];
+                        ol[j] = tl[cc0 + j][row];
+                    }
+                    *reinterpret_cast<uint4 *>(Xh + rx * Kp + c) = *reinterpret_cast<const uint4 *>(oh);
+                    *reinterpret_cast<uint4 *>(Xl + rx * Kp + c) = *reinterpret_cast<const uint4 *>(ol);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    ssum[cg][rr] = ss;
+    __syncthreads();
+    if (t < 64 && r0 + t < B) {
+        const float v = ssum[0][t] + ssum[1][t] + ssum[2][t] + ssum[3][t] + (float)n_pad * pad * pad;
+        inv_n2[r0 + t] = v > 0.f ? 1.0f / v : 0.f;
+    }
+}
+
+// QConv col2im of dX (stored feature-major: dxT[f][patch], ld = ldt) with the normalisation term of the amplitude
+// embedding, gather form (one thread per image element, no atomics; neighbouring pixels read neighbouring patches):
+//   grad_img[b,ch,iy,ix] = sum_{(ky,kx): patch p=(b, iy-ky+ph, ix-kx+pw) exists} dxT[(ch,ky,kx)][p] - 2 (img + add_offset) inv_n2[p] S[p]
+template <int KH, int KW>      // > 0: compile-time window (fully unrolled gather, loads in flight together); 0: runtime
+__global__ void __launch_bounds__(256) fold_rows_kernel(const float *dxT, long long ldt, const void *img, int io64,
+                                                        const float *inv_n2, const float *S, long long n_elems, float add_offset,
+                                                        const UnfoldGeom u, void *grad_img) {
+    const int kh = KH > 0 ? KH : u.kh, kw = KW > 0 ? KW : u.kw;
+    const int P = u.Hout * u.Wout, kk = kh * kw;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long long)gridDim.x * blockDim.x) {
         const int ix = (int)(i % u.W);
         long long t = i / u.W;
@@ -1004,19 +1074,24 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const float *dx_rows, in
         t /= u.H;
         const int ch = (int)(t % u.C);
         const long long b = t / u.C;
-        const float f = __ldg(img + i) + add_offset;
+        const float f2 = -2.f * (ld_io(img, i, io64) + add_offset);
+        const float *dch = dxT + (long long)ch * kk * ldt + b * P;
         float acc = 0.f;
-        for (int ky = 0; ky < u.kh; ++ky) {
+#pragma unroll
+        for (int ky = 0; ky < kh; ++ky) {
             const int y = iy - ky + u.ph;
-            if (y < 0 || y >= u.Hout) continue;
-            for (int kx = 0; kx < u.kw; ++kx) {
+#pragma unroll
+            for (int kx = 0; kx < kw; ++kx) {
                 const int xx = ix - kx + u.pw;
-                if (xx < 0 || xx >= u.Wout) continue;
-                const long long pr = b * P + (long long)y * u.Wout + xx;
-                acc += __ldg(dx_rows + pr * ldx + ch * kk + ky * u.kw + kx) - 2.f * f * __ldg(inv_n2 + pr) * __ldg(S + pr);
+                const bool ok = y >= 0 && y < u.Hout && xx >= 0 && xx < u.Wout;
+                const int pr = ok ? y * u.Wout + xx : 0;
+                const float d = __ldg(dch + (long long)(ky * kw + kx) * ldt + pr);
+                const float ns = __ldg(inv_n2 + b * P + pr) * __ldg(S + b * P + pr);
+                if (ok) acc += d + f2 * ns;
             }
         }
-        grad_img[i] = acc;
+        if (io64) reinterpret_cast<double *>(grad_img)[i] = (double)acc;
+        else reinterpret_cast<float *>(grad_img)[i] = acc;
     }
 }
 
@@ -1066,7 +1141,7 @@ __global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half
 // Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
 // |G[b,n]| = 2 |g| scale inv_n2 |Y'| <= 2 max_m|g[b,m]| * scale * sqrt(inv_n2[b]) * w_scale.
 __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out,
-                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P, int gw) {
+                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P, int gw, int go_f64) {
     // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp (small QConv rows keep the lanes busy)
     const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1080,7 +1155,7 @@ __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const flo
         if (!active) {
         } else if (go_P > 0) {        // QConv: grad_out is NCHW, element (row, m) at ((b * n_out + m) * P + r)
             const long long b = row / go_P, r = row - b * go_P;
-            for (int m = sub; m < n_out; m += gw) mx = fmaxf(mx, fabsf(__ldg(go + (b * n_out + m) * go_P + r)));
+            for (int m = sub; m < n_out; m += gw) mx = fmaxf(mx, fabsf(ld_io(go, (b * n_out + m) * go_P + r, go_f64)));
         } else if (vec) {
             const float *g = go + row * n_out;
             for (int i = lane; i < (n_out >> 2); i += 32) {
@@ -1104,7 +1179,7 @@ __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const flo
 __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float *go, const float *inv_n2, long long B,
                                                      int N, int Np, int n_out, float scale, int clamp, float lo,
                                                      float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl,
-                                                     float *S, int want_lo, int go_P, int gw) {
+                                                     float *S, int want_lo, int go_P, int gw, int go_f64) {
     // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp
     const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1156,7 +1231,7 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
                     const float outv = k0 * (y.x * y.x + y.y * y.y);
                     const bool pass = !clamp || (outv >= lo && outv <= hi);
                     const long long gi = go_P > 0 ? ((r / go_P) * n_out + m) * go_P + (r % go_P) : r * n_out + m;
-                    const float g = pass ? __ldg(go + gi) : 0.f;
+                    const float g = pass ? (go_P > 0 ? ld_io(go, gi, go_f64) : __ldg(go + gi)) : 0.f;
                     gre = k1 * g * y.x;
                     gim = k1 * g * y.y;
                     s_part += g * outv;
@@ -1298,7 +1373,11 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         p.tma_epi = 0;
         static int tma_epi_on = -1;
         if (tma_epi_on < 0) { const char *ev = getenv("QIDDM_GEMM_TMA_EPI"); tma_epi_on = ev ? atoi(ev) : 1; }
-        if (tma_epi_on && k_splits == 1 && p.out_P == 0 && (p.epi == EPI_PROBS || p.epi == EPI_DX)) {
+        if (tma_epi_on && k_splits == 1 && p.epi == EPI_DX && p.dx_x == nullptr) {
+            // QConv dX, feature-major (N rows of ldo patches): boxes of 32 patches x 16 features
+            p.tma_epi = make_map_ex(&p.o_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, N, p.ldo, p.ldo, 32, 16,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE) == QIDDM_OK ? 1 : 0;
+        } else if (tma_epi_on && k_splits == 1 && p.out_P == 0 && (p.epi == EPI_PROBS || p.epi == EPI_DX)) {
             bool ok = true;
             if (p.epi == EPI_PROBS) {
                 if (p.y_out) ok = ok && make_map_ex(&p.y_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.y_out, M, N, N, 16, 32,
@@ -1453,7 +1532,7 @@ static UnfoldGeom unfold_geom(const GateParams &gp) {
 
 size_t gemm_backward_ws_bytes(const GemmShape &g, long long B, bool unfold) {
     size_t b = gemm_saved_bytes(g, B);                // used when the forward did not save
-    if (unfold) b += al((size_t)B * g.F * 4);         // dX rows before the col2im
+    if (unfold) b += al((size_t)((B + 7) & ~7LL) * g.F * 4);   // dX (feature-major) before the col2im
     b += al((size_t)B * 4) + al(256);                 // S, gmax
     b += 2 * al((size_t)B * g.Np * 2);                // G splits (row-major)
     b += al((size_t)g.N * g.Fx * 4);                  // dWT (+ ones column)
@@ -1494,12 +1573,19 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     SavedView w = saved_view(g, B, keep ? saved : ws, keep);
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
-    if (keep) {
-        // training forward: X, X^T and the norms in one pass over x (QConv: through the fused patch-unfold)
+    if (keep && gp.unfold) {
+        // training forward, QConv: X, X^T and the norms straight from the NCHW image
         timing_begin(TK_PREP_X, 0.0, s);
-        prep_xt_kernel<<<(unsigned)((Bp + 63) / 64), 256, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
-            x, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2,
+        prep_xt_unfold_kernel<<<(unsigned)((Bp + 63) / 64), 256, 2 * g.F * sizeof(int), s>>>(
+            x, gp.io64, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2,
             unfold_geom(gp));
+        timing_end(s);
+        count_launch();
+    } else if (keep) {
+        // training forward, dense rows: X, X^T and the norms in one pass over x
+        timing_begin(TK_PREP_X, 0.0, s);
+        prep_xt_kernel<<<(unsigned)((Bp + 63) / 64), 256, 0, s>>>(x, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value,
+                                                                 w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2);
         timing_end(s);
         count_launch();
     } else {
@@ -1509,7 +1595,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
         timing_begin(TK_PREP_X, 0.0, s);
         prep_x_kernel<<<(unsigned)((row_warps + warps - 1) / warps), warps * 32, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
             x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
-            unfold_geom(gp), gw);
+            unfold_geom(gp), gw, gp.unfold ? gp.io64 : 0);
         timing_end(s);
         count_launch();
     }
@@ -1523,6 +1609,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
     p.n_out = g.n_out;
     p.out_P = gp.unfold ? gp.Hout * gp.Wout : 0;    // QConv: probabilities go straight to the NCHW output
+    p.out_f64 = gp.unfold ? gp.io64 : 0;
     ActOperand A{w.X[0], w.X[1]};
     WgtOperand Bm{v.Wn[0], v.Wn[1]};
     timing_set_gemm_kind(TK_GEMM_FWD);
@@ -1565,13 +1652,14 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     while (gw > 1 && gw / 2 >= g.Np / 2) gw >>= 1;
     const long long row_warps = (B * gw + 31) / 32;
     const unsigned ew_grid = (unsigned)((row_warps + warps - 1) / warps < 148 * 8 ? (row_warps + warps - 1) / warps : 148 * 8);
-    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax, go_P, gw);
+    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax, go_P, gw,
+                                                  gp.unfold ? gp.io64 : 0);
     timing_end(s);
     count_launch();
     timing_begin(TK_GRAD_Y, 0.0, s);
     grad_y_kernel<<<ew_grid, warps * 32, 0, s>>>(
         w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
-        Gs[1], S, n_seg > 1, go_P, gw);
+        Gs[1], S, n_seg > 1, go_P, gw, gp.unfold ? gp.io64 : 0);
     timing_end(s);
     count_launch();
     GemmParams p;
@@ -1580,7 +1668,7 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     // (2) dX = G W^T / gsc - 2 f inv_n2 S   (normalisation term fused in the epilogue)
     if (grad_in != nullptr) {
         memset(&p, 0, sizeof(p));
-        p.epi = EPI_DX; p.out = gp.unfold ? dx_rows : grad_in; p.ldo = g.F; p.out_scale = 1.f;
+        p.epi = EPI_DX; p.out = gp.unfold ? dx_rows : grad_in; p.ldo = gp.unfold ? Bp : g.F; p.out_scale = 1.f;
         p.row_scale = w.inv_n2; p.dx_S = S; p.dx_x = gp.unfold ? nullptr : x; p.gmax_bits = gmax;
         p.add_offset = gp.add_offset;
         WgtOperand Wt{v.Wt[0], v.Wt[1]};
@@ -1591,8 +1679,15 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
             const long long n_elems = (B / go_P) * gp.C * gp.H * gp.W;
             const unsigned fg = (unsigned)((n_elems + 255) / 256 < 148 * 16 ? (n_elems + 255) / 256 : 148 * 16);
             timing_begin(TK_FINISH_DX, 0.0, s);
-            fold_rows_kernel<<<fg, 256, 0, s>>>(dx_rows, g.F, x, w.inv_n2, S, n_elems, gp.add_offset, unfold_geom(gp),
-                                                grad_in);
+            if (gp.kh == 3 && gp.kw == 3)
+                fold_rows_kernel<3, 3><<<fg, 256, 0, s>>>(dx_rows, Bp, x, gp.io64, w.inv_n2, S, n_elems, gp.add_offset,
+                                                          unfold_geom(gp), grad_in);
+            else if (gp.kh == 1 && gp.kw == 1)
+                fold_rows_kernel<1, 1><<<fg, 256, 0, s>>>(dx_rows, Bp, x, gp.io64, w.inv_n2, S, n_elems, gp.add_offset,
+                                                          unfold_geom(gp), grad_in);
+            else
+                fold_rows_kernel<0, 0><<<fg, 256, 0, s>>>(dx_rows, Bp, x, gp.io64, w.inv_n2, S, n_elems, gp.add_offset,
+                                                          unfold_geom(gp), grad_in);
             timing_end(s);
             count_launch();
         }

@@ -15,6 +15,7 @@ struct GateParams {
     int merge_post;            // 1: RZ(omega) phases of layer l are merged into layer l+1's RZ(phi) table (CZ entangler)
     // fused patch-unfold (QConv); unfold == 0 -> plain (B, n_in) rows
     int unfold, C, H, W, kh, kw, ph, pw, Hout, Wout;
+    int io64;                  // QConv collapse path: image / output / gradient tensors are float64 (else float32)
     long long B;               // circuit instances
     const float *in;           // (B, n_in) features / angles, or NCHW image when unfold
     const int *basis;          // INIT_BASIS start states (may be null -> instance index)

@@ -104,4 +104,4 @@ def test_host_side_argument_checks_of_the_new_entry_points(lib):
     assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(good), 10) > 0
     assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(bad), 10) == 0
     assert lib.qiddm_qconv_gemm_workspace_bytes(plan.handle, C.byref(good), 10) > lib.qiddm_gemm_workspace_bytes(plan.handle, 7840) - 1
-    assert lib.qiddm_qconv_gemm_forward(plan.handle, None, C.byref(good), None, None, None, None, 1, 3, None) == -1
+    assert lib.qiddm_qconv_gemm_forward(plan.handle, None, C.byref(good), 0, None, None, None, None, 1, 3, None) == -1
