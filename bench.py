@@ -301,7 +301,7 @@ def run_b200(args):
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's three GEMM launches, from
                     # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv)
                     "traffic": 3.41e9 if (B == 262144 and args.precision == 3 and world == 1) else None,
-                    "traffic_unit": "bytes/launch (algorithmic operand bytes: 3.2e9)",
+                    "traffic_unit": "bytes/launch (algorithmic operand + result bytes: 3.0e9)",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
                     "ms_per_launch": per_launch_ms, "launches": kd["launches"],
                     "algorithmic_flops": "2*M*N*K per GEMM (single pass); precision %d executes %dx that"
