@@ -46,7 +46,10 @@ struct Cfg {
     static constexpr int T = G > 128 ? G : 128;
     static constexpr int CPB = T / G;
     static constexpr int SPAN = A + (A >> RB);      // padded float2 slots of one state
-    static constexpr int STRIDE = SPAN | 1;         // odd: spreads the instances of a CTA over the banks
+    // distance between the states of a CTA's instances.  A warp holds 32 / G instances; when G <= 8 their tiles must
+    // interleave over the 16 float2 bank pairs: stride = G (mod 16) makes the 32 lanes cover every bank pair exactly twice
+    // (n = 6, RB = 3: 72 instead of 73 -- ncu showed 49 % conflicted shared wavefronts with the odd stride).  Otherwise odd.
+    static constexpr int STRIDE = (G >= 2 && G <= 8) ? SPAN + ((G - SPAN % 16) + 16) % 16 : (SPAN | 1);
     static constexpr int LO_LAST = NQ - RB;
     static constexpr int NVF = NQ / RB;                 // full views; a partial last view follows when NQ % RB != 0
     static constexpr int Q_TAIL = RB - NQ % RB;         // first owned local bit of the partial view

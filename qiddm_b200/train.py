@@ -158,8 +158,9 @@ class GraphedTrainStep:
     instances) the step is ~100 dependent kernel launches, so launch latency, not arithmetic, bounds it.
 
     * inputs are copied into a static device buffer; the noise ladder's RNG draw, the net, the MSE, the backward
-      (incl. the adjoint gate kernels / the unitary-collapse GEMMs), the optional flat-bucket all-reduce and Adam
-      (`capturable=True`) all live inside the graph;
+      (incl. the adjoint gate kernels / the unitary-collapse GEMMs) and Adam (`capturable=True`) live inside the graph;
+      with `allreduce=True` under torch.distributed the step is two graphs around ONE eager NCCL all-reduce of the flat
+      gradient bucket;
     * models with a host round trip in forward (sklearn PCA) cannot be captured: use `pca_on_device`.
     """
 
@@ -197,8 +198,24 @@ class GraphedTrainStep:
                         if torch.is_tensor(v):
                             v.zero_()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.loss = self._body()
+        self.world = dist.get_world_size() if (allreduce and dist.is_available() and dist.is_initialized()) else 1
+        if self.bucket is None or not (dist.is_available() and dist.is_initialized()):
+            with torch.cuda.graph(self.graph):
+                self.loss = self._body()
+            self.graph_tail = None
+        else:
+            # data parallel: the collective stays OUTSIDE the captures (graph 1: zero_grad .. backward .. pack the flat
+            # bucket; eager NCCL all-reduce of the bucket; graph 2: unpack + optimizer) -- two replays and one NCCL call
+            # per step, no dependence on capturing the process group's streams
+            with torch.cuda.graph(self.graph):
+                self.opt.zero_grad(set_to_none=True)
+                (loss,) = self.diff(x=self.x, T=self.tau)
+                self.loss = loss.detach()
+                self.flat = self.bucket.pack()
+            self.graph_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_tail, pool=self.graph.pool()):
+                self.bucket.unpack()
+                self.opt.step()
         self._params = [p for p in diff.parameters()]
 
     def _body(self):
@@ -210,10 +227,14 @@ class GraphedTrainStep:
         return loss.detach()
 
     def step(self, x: torch.Tensor) -> torch.Tensor:
-        """Copies `x` (same shape as the example; host or device) into the static buffer and replays the graph.
+        """Copies `x` (same shape as the example; host or device) into the static buffer and replays the graph(s).
         Returns the (device-resident) loss of this step."""
         self.x.copy_(x, non_blocking=True)
         self.graph.replay()
+        if self.graph_tail is not None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world)
+            self.graph_tail.replay()
         for p in self._params:        # the replay updated the weights in place: invalidate version-keyed caches
             torch.autograd.graph.increment_version(p)
         return self.loss

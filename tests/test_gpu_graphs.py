@@ -116,3 +116,33 @@ def test_collapsed_operator_inside_a_graph_follows_the_weights():
     with torch.no_grad():
         ref = m(x)
     assert rel_to_max(y, ref) <= 1e-6
+
+
+def test_graphed_data_parallel_step_two_graphs_around_the_collective():
+    """allreduce=True under torch.distributed: graph 1 (.. backward, pack) -> eager all-reduce of the flat bucket ->
+    graph 2 (unpack, optimizer).  Single-rank NCCL group here (the 2-GPU run is scripts/bench_dp.py); the step must equal
+    the plain graphed step."""
+    import os
+    import torch.distributed as dist
+    from qiddm_b200 import nn
+    from qiddm_b200.train import GraphedTrainStep
+    imgs, tau = 2, 5
+    eps = torch.normal(0.5, 0.2, size=(imgs, 64), generator=torch.Generator().manual_seed(1)).double().cuda()
+    xs = [torch.rand(imgs, 64, dtype=torch.float64, generator=torch.Generator().manual_seed(20 + i)).cuda() for i in range(3)]
+    d0 = _diff(lambda: nn.QIDDM_LL_noise(64, 4, 3, 2), "data", eps)
+    g0 = GraphedTrainStep(d0, torch.optim.SGD(d0.parameters(), lr=0.05), tau, xs[0])
+    l0 = [g0.step(x).item() for x in xs]
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        d1 = _diff(lambda: nn.QIDDM_LL_noise(64, 4, 3, 2), "data", eps)
+        g1 = GraphedTrainStep(d1, torch.optim.SGD(d1.parameters(), lr=0.05), tau, xs[0], allreduce=True)
+        assert g1.graph_tail is not None
+        l1 = [g1.step(x).item() for x in xs]
+    finally:
+        dist.destroy_process_group()
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-6 * abs(a)
+    for (n0, p0), (_, p1) in zip(d0.named_parameters(), d1.named_parameters()):
+        assert rel_to_max(p1, p0) <= 1e-6, n0
