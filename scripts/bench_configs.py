@@ -152,14 +152,16 @@ def config1(cpu):
     """src/mnist_exm.py defaults: QIDDM_LL_noise(784,6,14,2), QNN_noise(784,8,14); batch 1 image, tau 10."""
     from oracle import qiddm_oracle as O
     for name, args, lr in (("QIDDM_LL_noise", (784, 6, 14, 2), 0.0255), ("QNN_noise", (784, 8, 14), 0.01011)):
-        for imgs, graphed in ((1, False), (1, True), (8, False), (8, True), (512, False), (512, True), (8192, False)):
+        for imgs, graphed, dt in ((1, False, torch.float64), (1, True, torch.float64), (8, False, torch.float64),
+                                  (8, True, torch.float64), (512, False, torch.float64), (512, True, torch.float64),
+                                  (8192, False, torch.float64), (8192, True, torch.float64), (8192, True, torch.float32)):
             torch.manual_seed(42)
             net = getattr(qnn, name)(*args)
             stages = args[3] if name == "QIDDM_LL_noise" else 1
             _, ms, ker, launches = train_step_rate(net, (28, 28), imgs, 10, lr, iters=20 if imgs <= 8 else 5,
-                                                   graphed=graphed)
+                                                   graphed=graphed, dtype=dt)
             rec = dict(what="config1", model=f"{name}{args}", images_per_step=imgs, tau=10, cuda_graph=graphed,
-                       ms_per_step=round(ms, 4),
+                       module_dtype=str(dt).replace("torch.", ""), ms_per_step=round(ms, 4),
                        train_samples_per_s=round(imgs / ms * 1e3, 1),
                        circuit_evals_per_s=round(imgs * 10 * stages / ms * 1e3), lib_launches_per_step=launches, kernels=ker)
             if cpu and imgs == 1 and not graphed:
@@ -183,19 +185,20 @@ def config1(cpu):
             emit(**rec)
 
 
-def unet_rate(tag, side, imgs_list, qdepth=3, simple=False, graphed=False):
+def unet_rate(tag, side, imgs_list, qdepth=3, simple=False, graphed=False, dtype=torch.float64):
     for imgs in imgs_list:
         torch.manual_seed(0)
         net = (qnn.UNetUndirectedS if simple else qnn.UNetUndirected)(3, 8, qdepth)
         try:
-            _, ms, ker, launches = train_step_rate(net, (side, side), imgs, 10, 1e-3, iters=3, warmup=2, graphed=graphed)
+            _, ms, ker, launches = train_step_rate(net, (side, side), imgs, 10, 1e-3, iters=3, warmup=2, graphed=graphed,
+                                                   dtype=dtype)
         except torch.OutOfMemoryError:
             emit(what=tag, images_per_step=imgs, error="oom")
             continue
         patches = 5782 if side == 28 else None
         emit(what=tag, model=f"{'UNetUndirectedS' if simple else 'UNetUndirected'}(3,8,{qdepth}) {side}x{side}",
-             images_per_step=imgs, tau=10, cuda_graph=graphed, ms_per_step=round(ms, 3),
-             train_samples_per_s=round(imgs / ms * 1e3, 1),
+             images_per_step=imgs, tau=10, cuda_graph=graphed, module_dtype=str(dtype).replace("torch.", ""),
+             ms_per_step=round(ms, 3), train_samples_per_s=round(imgs / ms * 1e3, 1),
              circuit_evals_per_s=(round(imgs * 10 * patches / ms * 1e3) if patches else None),
              lib_launches_per_step=launches, kernels=ker)
         del net
@@ -244,6 +247,7 @@ def config5(quick):
     emit(what="config5_pl64", model="QIDDM_PL_noise(4096,8,6,2)", images_per_step=64, tau=10, ms_per_step=round(ms, 3),
          train_samples_per_s=round(64 / ms * 1e3, 1), lib_launches_per_step=launches, kernels=ker)
     unet_rate("config5_unet64", 64, (8,) if quick else (8, 32))
+    unet_rate("config5_unet64", 64, (8,) if quick else (8, 32), graphed=True)
 
 
 def main():
@@ -261,7 +265,7 @@ def main():
             config1(a.cpu)
         elif w == "config3":
             unet_rate("config3_unet28", 28, (8, 64) if a.quick else (1, 8, 64, 256))
-            unet_rate("config3_unet28", 28, (8, 64) if a.quick else (1, 8, 64), graphed=True)
+            unet_rate("config3_unet28", 28, (8, 64) if a.quick else (1, 8, 64, 256), graphed=True)
             unet_rate("config3_unet28_simple", 28, (64,), simple=True)
         elif w == "config4":
             config4(a.quick)

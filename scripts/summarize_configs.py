@@ -32,7 +32,8 @@ def table(title, what, cols):
 
 
 step_cols = [("model", lambda r: r.get("model")), ("images/step", lambda r: r.get("images_per_step")),
-             ("graph", lambda r: "yes" if r.get("cuda_graph") else "no"), ("ms/step", lambda r: r.get("ms_per_step")),
+             ("graph", lambda r: "yes" if r.get("cuda_graph") else "no"), ("dtype", lambda r: r.get("module_dtype", "float64")),
+             ("ms/step", lambda r: r.get("ms_per_step")),
              ("train samples/s", lambda r: r.get("train_samples_per_s")),
              ("circuit evals/s", lambda r: r.get("circuit_evals_per_s")),
              ("gate fwd+bwd ms", lambda r: round(r.get("kernels", {}).get("gate_forward", 0) + r.get("kernels", {}).get("gate_backward", 0), 3) or None),
@@ -42,13 +43,13 @@ table("Config 1 — `src/mnist_exm.py` training step (tau = 10, Adam, float64 mo
 table("Config 3 — `UNetUndirected(3,8,3)` QConv-UNet training step, 28x28 (5 782 circuits per image-forward)", "config3_unet28", step_cols[:-1])
 table("Config 3 — `UNetUndirectedS(3,8,3)`", "config3_unet28_simple", step_cols[:-1])
 table("Config 4 — `QIDDM_PL_noise(784,8,6,2)` training step (goal noise, PCA re-fit per forward)", "config4_train",
-      step_cols[:5] + [("pca", lambda r: r.get("pca"))])
+      step_cols[:6] + [("pca", lambda r: r.get("pca"))])
 table("Config 4 — `Diffusion.sample` fixed-point sampler", "config4_sample",
       [("model", lambda r: r["model"]), ("images", lambda r: r["images"]), ("iterations", lambda r: r["n_iters"]),
        ("graph", lambda r: "yes" if r.get("cuda_graph") else "no"), ("seconds", lambda r: r["seconds"]),
        ("iterations/s", lambda r: r["sampler_iters_per_s"]), ("circuit evals/s", lambda r: r["circuit_evals_per_s"])])
 table("Config 5 — 64x64: `QDenseUndirected_old(60,64)` (n = 12)", "config5_qdense64", step_cols[:-1])
-table("Config 5 — 64x64: `QIDDM_PL_noise(4096,8,6,2)`", "config5_pl64", step_cols[:5])
+table("Config 5 — 64x64: `QIDDM_PL_noise(4096,8,6,2)`", "config5_pl64", step_cols[:6])
 table("Config 5 — 64x64: `UNetUndirected(3,8,3)`", "config5_unet64", step_cols[:-1])
 
 sw = [r for r in rows if r["what"] == "sweep"]
