@@ -100,3 +100,47 @@ def test_collapsed_operator_cache_follows_weight_updates():
     b = run_stage(spec, x, W).detach()
     ref = O.run_stage(d, x.cpu(), W.detach().cpu())
     assert rel_to_max(b, ref) <= 1e-5 and rel_to_max(a, ref) > 1e-3
+
+
+def test_full_size_properties_of_the_bench_workload():
+    """BASELINE config 2 / bench.py size (n = 10, 60 layers, 262 144 instances) through size-independent properties:
+    probabilities of every instance sum to 1, sampled rows equal the oracle, identical rows give identical results,
+    and the backward is linear in the upstream gradient."""
+    from qiddm_b200 import _lib as L
+    from qiddm_b200.functional import run_stage
+    B = 262144
+    d = O.desc_qdense(60, 784, O.REMAP_TANH)
+    full = O.StageDesc(**{**d.__dict__, "read_count": 1024, "post_scale": 1.0, "clamp": False})
+    g = torch.Generator().manual_seed(99)
+    W = (torch.randn(1, 60, 10, 3, generator=g, dtype=torch.float64) * 0.4)
+    x = torch.rand(B, 784, generator=g, dtype=torch.float32)
+    x[B - 1] = x[0]                                              # a duplicated instance far away in the batch
+    xd, Wd = x.cuda(), W.cuda()
+    n0 = L.launch_count()
+    p = run_stage(_spec(full, L.PATH_GEMM), xd, Wd)              # (B, 1024) un-scaled probabilities
+    assert L.launch_count() > n0 and p.shape == (B, 1024)
+    s = p.sum(dim=1)
+    assert (s - 1).abs().max().item() <= 3e-5
+    assert p.min().item() >= 0
+    assert torch.equal(p[0], p[B - 1])
+    idx = torch.tensor([0, 1, 777, 65535, 131072, 200001, B - 2])
+    ref = O.run_stage(full, x[idx].double(), W)
+    assert rel_to_max(p[idx.cuda()], ref) <= 1e-5
+    del p
+    # the clamped module readout at full size equals the gate path on a slice
+    out = run_stage(_spec(d, L.PATH_GEMM), xd, Wd)
+    sl = slice(100000, 100512)
+    assert rel_to_max(out[sl], run_stage(_spec(d, L.PATH_GATE), xd[sl], Wd)) <= 2e-5
+    # backward linearity in grad_out (weights gradient), B = 65 536
+    xs = xd[:65536].clone()
+    g1 = torch.randn(65536, 784, generator=g).cuda() / 65536
+    g2 = torch.randn(65536, 784, generator=g).cuda() / 65536
+
+    def wgrad(go):
+        Wp = Wd.clone().requires_grad_(True)
+        o = run_stage(_spec(d, L.PATH_GEMM), xs, Wp)
+        (o * go).sum().backward()
+        return Wp.grad
+
+    a, b, c = wgrad(g1), wgrad(g2), wgrad(g1 + g2)
+    assert rel_to_max(a + b, c) <= 2e-4
