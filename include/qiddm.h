@@ -197,6 +197,10 @@ int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, in
  * m <= qiddm_sym_eigh_max_dim(); asynchronous on `stream`, no status read-back (CUDA-graph capturable). */
 int qiddm_sym_eigh_max_dim(void);
 int qiddm_sym_eigh_f64(const double *a, int m, double *evals, double *evecs, qiddm_stream_t stream);
+/* `count` independent matrices, contiguous (count, m, m) -> evals (count, m), evecs (count, m, m); one CTA each.  Used for
+ * per-group PCA: a batch of N images x tau noise levels keeps the reference's batch-1 semantics (one PCA per image's
+ * tau-ladder, nn/qdense.py:1429 with src/mnist_exm.py:144) as N groups of tau rows in one launch. */
+int qiddm_sym_eigh_f64_batched(const double *a, int m, int64_t count, double *evals, double *evecs, qiddm_stream_t stream);
 
 /* Id of the CUDA-graph capture `stream` is currently part of, 0 when it is not capturing (lets the host side keep
  * per-capture caches of the collapsed operator). */

@@ -50,7 +50,7 @@ EXPORTS = [
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
     "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id",
-    "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_upsample_bilinear_forward",
+    "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward",
 ]
@@ -112,6 +112,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_sym_eigh_max_dim.restype = i32
         lib.qiddm_sym_eigh_f64.restype = i32
         lib.qiddm_sym_eigh_f64.argtypes = [vp, i32, vp, vp, vp]
+        lib.qiddm_sym_eigh_f64_batched.restype = i32
+        lib.qiddm_sym_eigh_f64_batched.argtypes = [vp, i32, i64, vp, vp, vp]
         lib.qiddm_stream_capture_id.restype = i64
         lib.qiddm_stream_capture_id.argtypes = [vp]
         lib.qiddm_gemm_supported.restype = i32
@@ -172,21 +174,23 @@ def timing_collect() -> dict:
 
 
 def sym_eigh(a: torch.Tensor):
-    """Eigen-decomposition of a symmetric float64 CUDA matrix by the library's single-CTA Jacobi kernel:
-    (evals descending (m,), evecs (m, m) with matching columns).  Asynchronous, CUDA-graph capturable."""
+    """Eigen-decomposition of symmetric float64 CUDA matrices (..., m, m) by the library's Jacobi kernel (one CTA per
+    matrix): (evals descending (..., m), evecs (..., m, m) with matching columns).  Asynchronous, CUDA-graph capturable."""
     _require_cuda(a, "matrix")
     lib = load_library()
-    m = a.shape[0]
-    if a.dim() != 2 or a.shape[1] != m or a.dtype != torch.float64:
-        raise QiddmError("sym_eigh needs a square float64 matrix")
+    if a.dim() < 2 or a.shape[-1] != a.shape[-2] or a.dtype != torch.float64:
+        raise QiddmError("sym_eigh needs square float64 matrices")
+    m = a.shape[-1]
     if m > lib.qiddm_sym_eigh_max_dim():
         raise QiddmError(f"sym_eigh supports m <= {lib.qiddm_sym_eigh_max_dim()}, got {m}")
     a = a.contiguous()
-    evals = torch.empty(m, dtype=torch.float64, device=a.device)
-    evecs = torch.empty((m, m), dtype=torch.float64, device=a.device)
+    count = a.numel() // (m * m)
+    evals = torch.empty(a.shape[:-1], dtype=torch.float64, device=a.device)
+    evecs = torch.empty(a.shape, dtype=torch.float64, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib.qiddm_sym_eigh_f64(_ptr(a), m, _ptr(evals), _ptr(evecs),
-                                     C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)), "qiddm_sym_eigh_f64")
+        check(lib.qiddm_sym_eigh_f64_batched(_ptr(a), m, count, _ptr(evals), _ptr(evecs),
+                                             C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)),
+              "qiddm_sym_eigh_f64_batched")
     return evals, evecs
 
 

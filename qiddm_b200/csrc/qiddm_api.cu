@@ -531,7 +531,11 @@ int qiddm_sym_eigh_max_dim(void) {
 }
 
 int qiddm_sym_eigh_f64(const double *a, int m, double *evals, double *evecs, qiddm_stream_t stream) {
-    return qiddm::sym_eigh_f64(a, m, evals, evecs, (cudaStream_t)stream);
+    return qiddm::sym_eigh_f64(a, m, 1, evals, evecs, (cudaStream_t)stream);
+}
+
+int qiddm_sym_eigh_f64_batched(const double *a, int m, int64_t count, double *evals, double *evecs, qiddm_stream_t stream) {
+    return qiddm::sym_eigh_f64(a, m, count, evals, evecs, (cudaStream_t)stream);
 }
 
 int64_t qiddm_stream_capture_id(qiddm_stream_t stream) {

@@ -74,7 +74,7 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
 
 // qiddm_pca.cu — single-CTA Jacobi eigensolver (float64) for the on-device PCA-in-forward
 size_t eigh_smem_bytes(int m);
-int sym_eigh_f64(const double *A, int m, double *evals, double *evecs, cudaStream_t s);
+int sym_eigh_f64(const double *A, int m, long long count, double *evals, double *evecs, cudaStream_t s);
 
 // qiddm_glue.cu — UNet glue around QConv2d: bilinear resize (align_corners = False) and BatchNorm2d (NCHW)
 size_t batchnorm_ws_bytes(int C);

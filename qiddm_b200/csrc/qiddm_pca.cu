@@ -16,8 +16,12 @@ constexpr int EIGH_THREADS = 512;
 
 // A (m x m, symmetric, row-major) -> eigenvalues in DESCENDING order and the matching eigenvectors as the columns of
 // V (row-major m x m).  Shared memory: A, V (m*m doubles each), c/s per pair, diag + rank scratch.
-__global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double *A_in, int m, double *evals, double *evecs,
-                                                                   int max_sweeps) {
+__global__ void __launch_bounds__(EIGH_THREADS) jacobi_eigh_kernel(const double *A_batch, int m, double *evals_batch,
+                                                                   double *evecs_batch, int max_sweeps) {
+    // one CTA per matrix of the batch (per-group PCA: one group = the tau-ladder of one image)
+    const double *A_in = A_batch + (size_t)blockIdx.x * m * m;
+    double *evals = evals_batch + (size_t)blockIdx.x * m;
+    double *evecs = evecs_batch + (size_t)blockIdx.x * m * m;
     extern __shared__ double sm[];
     const int ld = m | 1;                      // odd row stride (in doubles): rows start in different banks
     double *A = sm, *V = sm + (size_t)m * ld;
@@ -142,8 +146,9 @@ size_t eigh_smem_bytes(int m) {
     return (size_t)(2 * m * (m | 1) + 2 * half + EIGH_THREADS / 32 + 2) * sizeof(double) + (size_t)2 * half * sizeof(int) + 16;
 }
 
-int sym_eigh_f64(const double *A, int m, double *evals, double *evecs, cudaStream_t s) {
-    if (!A || !evals || !evecs || m < 1) return QIDDM_EINVAL;
+int sym_eigh_f64(const double *A, int m, long long count, double *evals, double *evecs, cudaStream_t s) {
+    if (!A || !evals || !evecs || m < 1 || count < 0 || count > 0x7fffffffLL) return QIDDM_EINVAL;
+    if (count == 0) return QIDDM_OK;
     const size_t smem = eigh_smem_bytes(m);
     if (smem > 227 * 1024) return QIDDM_EUNSUPPORTED;
     static bool attr_set = false;
@@ -152,7 +157,10 @@ int sym_eigh_f64(const double *A, int m, double *evals, double *evecs, cudaStrea
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    jacobi_eigh_kernel<<<1, EIGH_THREADS, smem, s>>>(A, m, evals, evecs, 40);
+    // threads ~ the m/2 x m/2 block updates of a round: small matrices (m = tau = 10) use two warps, large ones all 16
+    const int work = ((m + 1) / 2) * m;
+    const int threads = work <= 64 ? 64 : (work <= 256 ? 128 : (work <= 1024 ? 256 : EIGH_THREADS));
+    jacobi_eigh_kernel<<<(unsigned)count, threads, smem, s>>>(A, m, evals, evecs, 40);
     count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;

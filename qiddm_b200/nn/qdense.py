@@ -46,15 +46,28 @@ def _make_pca(n_components):
     return PCA(n_components=n_components)
 
 
-def _pca_call(pca, method: str, x: torch.Tensor) -> torch.Tensor:
-    """pca.<method>(x) as a float64 tensor on x.device (no gradient flows through the PCA, as in the reference)."""
+def _pca_call(pca, method: str, x: torch.Tensor, group=None) -> torch.Tensor:
+    """pca.<method>(x) as a float64 tensor on x.device (no gradient flows through the PCA, as in the reference).
+
+    `group` (module attribute `pca_group`, default None = one PCA over the whole batch, what the reference does for the
+    batch it is given): rows are split into consecutive groups of that many rows with ONE PCA PER GROUP, solved together
+    on the device.  With group = tau this keeps the reference's default batch-size-1 semantics (src/mnist_exm.py:144:
+    each step's PCA sees the tau-ladder of one image) for a batch of many images -- which is what lets the training
+    step and the sampler scale over images without changing the PCA basis of any of them."""
     if isinstance(pca, DevicePCA):
+        if group and x.shape[0] > group:
+            if x.shape[0] % group:
+                raise ValueError(f"pca_group={group} does not divide the batch of {x.shape[0]} rows")
+            out = getattr(pca, method)(x.detach().reshape(x.shape[0] // group, group, -1))
+            return out.reshape(x.shape[0], -1)
         return getattr(pca, method)(x.detach())
+    if group and x.shape[0] > group:
+        raise ValueError("pca_group needs the on-device PCA (QIDDM_PCA=device)")
     return torch.as_tensor(getattr(pca, method)(x.detach().cpu().numpy()), dtype=torch.float64).to(x.device)
 
 
-def _pca_fit_transform(pca, x: torch.Tensor) -> torch.Tensor:
-    return _pca_call(pca, "fit_transform", x)
+def _pca_fit_transform(pca, x: torch.Tensor, group=None) -> torch.Tensor:
+    return _pca_call(pca, "fit_transform", x, group)
 
 
 def _check_noise(add_noise, allow_phase: bool):
@@ -313,7 +326,7 @@ class _DifferNBase(nn.Module):
         W = getattr(self, self._weight_name)
         if self._reduce == "pca":
             flat = x.reshape(b, -1)
-            a = _pca_fit_transform(self.pca, flat)
+            a = _pca_fit_transform(self.pca, flat, getattr(self, "pca_group", None))
             return a.to(torch.float32).to(W.device)
         if self._reduce == "conv":
             a = self.conv_layer(x)
@@ -467,7 +480,7 @@ class _QIDDM_A_differN(_SaveLoadMixin, _DifferNBase):
 
     def _angles(self, x):
         b = x.shape[0]
-        a = _pca_fit_transform(self.pca, x.reshape(b, -1))
+        a = _pca_fit_transform(self.pca, x.reshape(b, -1), getattr(self, "pca_group", None))
         return a.to(x.device).to(x.dtype)
 
     def __repr__(self):
@@ -523,7 +536,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
         b = x.shape[0]
         if self._reduce == "pca":
             ref = self.linear_up.weight if hasattr(self, "linear_up") else self.weights1
-            a = _pca_fit_transform(self.pca, x.reshape(b, -1))
+            a = _pca_fit_transform(self.pca, x.reshape(b, -1), getattr(self, "pca_group", None))
             return a.to(ref.device).to(ref.dtype)
         if self._reduce == "conv":
             return self.conv_layer(x).view(b, self.hidden_features, -1).mean(dim=2)
@@ -544,7 +557,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
         if self._restore == "linear":
             out = self.linear_up(a.to(self.linear_up.weight.dtype))
         else:
-            out = _pca_call(self.pca, "inverse_transform", a).to(x.dtype).requires_grad_(True)
+            out = _pca_call(self.pca, "inverse_transform", a, getattr(self, "pca_group", None)).to(x.dtype).requires_grad_(True)
         return out.view(b, c, w, h)
 
     def __repr__(self):

@@ -28,43 +28,49 @@ class DevicePCA:
 
     @staticmethod
     def _eigh_desc(a: torch.Tensor):
-        if a.is_cuda and a.shape[0] <= L.load_library().qiddm_sym_eigh_max_dim():
+        if a.is_cuda and a.shape[-1] <= L.load_library().qiddm_sym_eigh_max_dim():
             return L.sym_eigh(a)
         lam, vec = torch.linalg.eigh(a)                       # ascending
-        return lam.flip(0), vec.flip(1)
+        return lam.flip(-1), vec.flip(-1)
+
+    @staticmethod
+    def _u_based_signs(u: torch.Tensor) -> torch.Tensor:
+        """(..., m, k) -> (..., 1, k): sign of the entry of largest magnitude in every column (svd_flip, U-based)."""
+        idx = u.abs().argmax(dim=-2, keepdim=True)
+        signs = torch.sign(u.gather(-2, idx))
+        return torch.where(signs == 0, torch.ones_like(signs), signs)
 
     def fit_transform(self, x: torch.Tensor) -> torch.Tensor:
-        """(m, P) -> (m, k) float64 scores on x.device."""
+        """(m, P) -> (m, k) float64 scores on x.device.  A 3-D input (G, m, P) is G independent PCAs (one per group, e.g.
+        one per image's tau-ladder: the reference's batch-1 semantics for a batch of G images) solved in one launch."""
         x = x.detach().to(torch.float64)
-        m, p = x.shape
+        m, p = x.shape[-2], x.shape[-1]
         k = self.n_components
         if k > min(m, p):
             raise ValueError(f"n_components={k} must be between 0 and min(n_samples, n_features)={min(m, p)}")
-        self.mean_ = x.mean(dim=0)
+        self.mean_ = x.mean(dim=-2, keepdim=True)
         xc = x - self.mean_
+        xt = xc.transpose(-1, -2)
         if m <= p:
-            lam, u = self._eigh_desc(xc @ xc.T)               # Gram matrix of the centred rows
-            s = lam[:k].clamp_min(0).sqrt()
-            u = u[:, :k]
-            idx = u.abs().argmax(dim=0)
-            signs = torch.sign(u.gather(0, idx[None, :]))[0]
-            signs = torch.where(signs == 0, torch.ones_like(signs), signs)
-            u = u * signs
+            lam, u = self._eigh_desc(xc @ xt)                 # Gram matrix of the centred rows
+            s = lam[..., :k].clamp_min(0).sqrt().unsqueeze(-2)        # (..., 1, k)
+            u = u[..., :, :k]
+            u = u * self._u_based_signs(u)
             scores = u * s
             # V_k^T = S^-1 U^T Xc; a rank-deficient tail (k >= m: the centred batch has rank m - 1) gets a zero axis
-            inv_s = torch.where(s > 1e-12 * s[0], 1.0 / s.clamp_min(1e-300), torch.zeros_like(s))
-            self.components_ = (u * inv_s).T @ xc
+            inv_s = torch.where(s > 1e-12 * s[..., :1], 1.0 / s.clamp_min(1e-300), torch.zeros_like(s))
+            self.components_ = (u * inv_s).transpose(-1, -2) @ xc
         else:
-            lam, v = self._eigh_desc(xc.T @ xc)               # covariance (un-normalised)
-            s = lam[:k].clamp_min(0).sqrt()
-            v = v[:, :k]
+            lam, v = self._eigh_desc(xt @ xc)                 # covariance (un-normalised)
+            s = lam[..., :k].clamp_min(0).sqrt().unsqueeze(-2)
+            v = v[..., :, :k]
             scores = xc @ v
-            idx = scores.abs().argmax(dim=0)                  # argmax |U| = argmax |U S| per column
-            signs = torch.sign(scores.gather(0, idx[None, :]))[0]
-            signs = torch.where(signs == 0, torch.ones_like(signs), signs)
+            signs = self._u_based_signs(scores)               # argmax |U| = argmax |U S| per column
             scores = scores * signs
-            self.components_ = (v * signs).T
-        self.singular_values_ = s
+            self.components_ = (v * signs).transpose(-1, -2)
+        self.singular_values_ = s.squeeze(-2)
+        if x.dim() == 2:
+            self.mean_ = self.mean_.squeeze(0)
         return scores
 
     def fit(self, x: torch.Tensor) -> "DevicePCA":
@@ -74,7 +80,7 @@ class DevicePCA:
     def transform(self, x: torch.Tensor) -> torch.Tensor:
         """(m, P) -> (m, k): (x - mean_) @ components_.T with the fitted basis."""
         x = x.detach().to(torch.float64)
-        return (x - self.mean_.to(x.device)) @ self.components_.to(x.device).T
+        return (x - self.mean_.to(x.device)) @ self.components_.to(x.device).transpose(-1, -2)
 
     def inverse_transform(self, scores: torch.Tensor) -> torch.Tensor:
         """(m, k) -> (m, P): scores @ components_ + mean_ (sklearn `PCA.inverse_transform`, whiten=False)."""

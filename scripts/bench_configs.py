@@ -211,14 +211,19 @@ def config4(quick):
     net = qnn.QIDDM_PL_noise(784, 8, 6, 2)
     from qiddm_b200.nn import qdense as qd
     from qiddm_b200.train import GraphedSampler
-    for imgs, graphed in ((1, False), (1, True), (8, True), (64, False)):
+    for imgs, graphed, group in ((1, False, None), (1, True, None), (8, True, None), (64, False, None), (64, True, 10),
+                                 (1024, True, 10), (8192, True, 10)):
+        net.pca_group = group
         diff, ms, ker, launches = train_step_rate(net, (28, 28), imgs, 10, 0.0255, goal="noise", iters=10, graphed=graphed)
         emit(what="config4_train", model="QIDDM_PL_noise(784,8,6,2)", images_per_step=imgs, tau=10, cuda_graph=graphed,
              ms_per_step=round(ms, 3), train_samples_per_s=round(imgs / ms * 1e3, 1), lib_launches_per_step=launches,
-             kernels=ker, pca="device (Gram + Jacobi eigh kernel)" if qd.PCA_ON_DEVICE else "host sklearn")
+             kernels=ker, pca=("device, one PCA per image (pca_group = tau)" if group else
+                               "device, one PCA over the batch" if qd.PCA_ON_DEVICE else "host sklearn"))
     diff.eval()
     n_iters = 100 if quick else 1000
-    for nimg, graphed in ((10, False), (10, True), (64, True), (4096, False)):
+    for nimg, graphed, group in ((10, False, None), (10, True, None), (64, True, None), (4096, False, None),
+                                 (4000, True, 10), (40000, True, 10)):
+        net.pca_group = group
         first = torch.rand(nimg, 1, 28, 28, device=DEV, dtype=torch.float64) * 0.75 + 0.5
         gs = GraphedSampler(diff, first, unroll=10) if graphed else None
         torch.cuda.synchronize()
@@ -230,8 +235,8 @@ def config4(quick):
         torch.cuda.synchronize()
         s = time.perf_counter() - t
         emit(what="config4_sample", model="QIDDM_PL_noise(784,8,6,2)", images=nimg, n_iters=n_iters, cuda_graph=graphed,
-             seconds=round(s, 3), sampler_iters_per_s=round(n_iters / s, 1),
-             circuit_evals_per_s=round(nimg * 2 * n_iters / s))
+             pca_group=group, seconds=round(s, 3), sampler_iters_per_s=round(n_iters / s, 1),
+             image_iterations_per_s=round(nimg * n_iters / s), circuit_evals_per_s=round(nimg * 2 * n_iters / s))
 
 
 def config5(quick):

@@ -46,7 +46,8 @@ table("Config 4 — `QIDDM_PL_noise(784,8,6,2)` training step (goal noise, PCA r
       step_cols[:6] + [("pca", lambda r: r.get("pca"))])
 table("Config 4 — `Diffusion.sample` fixed-point sampler", "config4_sample",
       [("model", lambda r: r["model"]), ("images", lambda r: r["images"]), ("iterations", lambda r: r["n_iters"]),
-       ("graph", lambda r: "yes" if r.get("cuda_graph") else "no"), ("seconds", lambda r: r["seconds"]),
+       ("graph", lambda r: "yes" if r.get("cuda_graph") else "no"), ("pca group", lambda r: r.get("pca_group")),
+       ("seconds", lambda r: r["seconds"]),
        ("iterations/s", lambda r: r["sampler_iters_per_s"]), ("circuit evals/s", lambda r: r["circuit_evals_per_s"])])
 table("Config 5 — 64x64: `QDenseUndirected_old(60,64)` (n = 12)", "config5_qdense64", step_cols[:-1])
 table("Config 5 — 64x64: `QIDDM_PL_noise(4096,8,6,2)`", "config5_pl64", step_cols[:6])

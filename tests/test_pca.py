@@ -62,3 +62,53 @@ def test_device_pca_on_gpu_equals_cpu_math():
     a = DevicePCA(8).fit_transform(x)
     b = DevicePCA(8).fit_transform(x.cuda()).cpu()
     assert (a - b).abs().max() <= 1e-9 * a.abs().max()
+
+
+def test_grouped_pca_equals_one_pca_per_group():
+    """3-D input = independent PCAs per group (the reference's batch-1 semantics for a batch of images)."""
+    torch.manual_seed(3)
+    x = torch.rand(6, 10, 64, dtype=torch.float64)
+    pca = DevicePCA(8)
+    got = pca.fit_transform(x)
+    inv = pca.inverse_transform(got)
+    for g in range(6):
+        one = DevicePCA(8)
+        ref = one.fit_transform(x[g])
+        assert (got[g] - ref).abs().max() <= 1e-10 * ref.abs().max()
+        assert (inv[g] - one.inverse_transform(ref)).abs().max() <= 1e-10
+
+
+def test_module_pca_group_matches_per_image_forward():
+    """QIDDM_PL-style reduction with pca_group = tau on a batch of images == the per-image calls of the reference."""
+    from qiddm_b200.nn import qdense
+    torch.manual_seed(4)
+    x = torch.rand(30, 64, dtype=torch.float64)                 # 3 images x tau = 10 rows
+    pca = DevicePCA(4)
+    grouped = qdense._pca_fit_transform(pca, x, 10)
+    for i in range(3):
+        ref = DevicePCA(4).fit_transform(x[10 * i:10 * i + 10])
+        assert (grouped[10 * i:10 * i + 10] - ref).abs().max() <= 1e-10 * ref.abs().max()
+    with pytest.raises(ValueError):
+        qdense._pca_fit_transform(pca, x[:25], 10)
+
+
+@pytest.mark.gpu
+def test_batched_jacobi_kernel_and_grouped_module_on_gpu():
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import nn
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn(37, 10, 40, generator=g, dtype=torch.float64)
+    a = (a @ a.transpose(1, 2)).cuda()
+    lam, vec = L.sym_eigh(a)
+    ref = torch.linalg.eigvalsh(a.cpu()).flip(-1)
+    assert (lam.cpu() - ref).abs().max() <= 1e-12 * ref.abs().max()
+    assert ((a @ vec) - vec * lam.unsqueeze(1)).abs().max().item() <= 1e-10 * ref.abs().max().item()
+    # a PL model on 4 images x tau rows with pca_group = tau equals 4 separate forwards
+    torch.manual_seed(0)
+    m = nn.QIDDM_PL_noise(64, 4, 3, 2).to("cuda", torch.float64)
+    m.pca_group = 5
+    x = torch.rand(20, 1, 8, 8, dtype=torch.float64, device="cuda")
+    with torch.no_grad():
+        whole = m(x)
+        parts = torch.cat([m(x[5 * i:5 * i + 5]) for i in range(4)])
+    assert (whole - parts).abs().max().item() <= 1e-6 * parts.abs().max().item()
