@@ -391,6 +391,40 @@ def extras(dev):
     out["qiddm_ll_train_samples_per_s"] = imgs / (ms * 1e-3)
     out["qiddm_ll_train_circuit_evals_per_s"] = imgs * 10 * 2 / (ms * 1e-3)
     out["qiddm_ll_config"] = "QIDDM_LL_noise(784,6,14,2), 4096 images/step, tau=10, Adam, float64 module I/O"
+    del diff, opt, data
+
+    # the other BASELINE configs through CUDA-graph steps (qiddm_b200.train.GraphedTrainStep), float64 modules, tau = 10
+    from qiddm_b200.train import GraphedTrainStep
+
+    def graphed_rate(net, imgs, side, goal, iters=10):
+        d = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (side, side), torch.nn.MSELoss()).to(dev, torch.float64)
+        o = torch.optim.Adam(d.parameters(), lr=1e-3, capturable=True)
+        xs = torch.rand(imgs, side * side, device=dev, dtype=torch.float64)
+        g = GraphedTrainStep(d, o, 10, xs)
+        for _ in range(2):
+            g.step(xs)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(iters):
+            g.step(xs)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    torch.manual_seed(0)
+    ms = graphed_rate(qnn.QIDDM_LL_noise(784, 6, 14, 2), 1, 28, "data", iters=50)
+    out["config1_reference_batch_ms_per_step_graphed"] = ms           # src/mnist_exm.py defaults: 1 image x tau 10
+    ms = graphed_rate(qnn.UNetUndirected(3, 8, 3), 64, 28, "data", iters=5)
+    out["config3_qconv_unet_train_samples_per_s"] = 64 / (ms * 1e-3)
+    out["config3_qconv_unet_circuit_evals_per_s"] = 64 * 10 * 5782 / (ms * 1e-3)
+    pl = qnn.QIDDM_PL_noise(784, 8, 6, 2)
+    pl.pca_group = 10                                                  # one PCA per image's tau-ladder (reference batch-1 semantics)
+    ms = graphed_rate(pl, 1024, 28, "noise", iters=10)
+    out["config4_qiddm_pl_train_samples_per_s"] = 1024 / (ms * 1e-3)
+    out["configs_note"] = ("graphed steps, one B200: config 1 = QIDDM_LL_noise(784,6,14,2) at the reference batch (1 image); "
+                           "config 3 = UNetUndirected(3,8,3), 64 images/step, QConv on the tcgen05 path; config 4 = "
+                           "QIDDM_PL_noise(784,8,6,2), 1024 images/step, per-image on-device PCA; more in profiles/r1_configs.md")
     return out
 
 
