@@ -54,6 +54,8 @@ def workload_config(batch, n_gpus):
     return {"workload": f"QDenseUndirected_old_noise({QDEPTH},{SIDE}) fwd+bwd, n={NQ} qubits, 600 Rot + 600 CNOT, "
                         f"synthetic MNIST-shaped 28x28", "instances_per_gpu": batch, "global_instances": batch * n_gpus,
             "parallelism": f"dp{n_gpus} (instances sharded, weight-grad all-reduce only)",
+            "step": "device-resident step = forward + backward for BOTH the input and the weight gradients; the e2e "
+                    "Diffusion step (first layer: the noisy images need no gradient) skips the dX GEMM, as the reference does",
             "l2": "inputs+grads per step (>=2x%.0f MB) exceed the 126 MB L2" % (batch * PIXELS * 4 / 1e6)}
 
 

@@ -191,6 +191,18 @@ int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, in
                              const double *save_mean, const double *save_rstd, void *grad_gamma, void *grad_beta,
                              void *workspace, qiddm_stream_t stream);
 
+/* Diffusion-step glue.  qiddm_noise_ladder = src/noise.py:105-126 (`add_normal_noise_multiple`) fused with the slicing of
+ * src/models.py:50-63: for x, eps (batch, pixels) (eps float32 as the reference draws it) and the level weights w[tau]
+ * (tensor dtype), level_t = clamp(x (1 - w_t) + eps w_t, 0, 1); writes noisy[(b, t)] = level_{t+1} and clean[(b, t)] =
+ * level_t for t < tau - 1, both (batch * (tau - 1), pixels).  qiddm_mse_loss_grad = MSELoss + `.mean().backward()` seed
+ * (src/models.py:65-67, :95-99): d = scale * pred + shift - target (+ target_add when non-NULL); loss[0] = mean(d^2),
+ * grad = 2 scale d / n (deterministic two-stage sum).  workspace: qiddm_mse_workspace_bytes(). */
+int qiddm_noise_ladder(const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels, int tau,
+                       void *noisy, void *clean, qiddm_stream_t stream);
+size_t qiddm_mse_workspace_bytes(void);
+int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target_add, int dtype, double scale, double shift,
+                        int64_t n, void *grad, void *loss, void *workspace, qiddm_stream_t stream);
+
 /* On-device PCA support (replaces the sklearn `PCA.fit_transform` host round trip of nn/qdense.py:456, :1429):
  * eigen-decomposition of a symmetric m x m float64 matrix (the Gram matrix of the centred batch rows), one CTA, parallel
  * cyclic Jacobi.  evals[m] in DESCENDING order, evecs (m x m row-major) column j = eigenvector of evals[j].

@@ -52,7 +52,7 @@ EXPORTS = [
     "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id",
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
-    "qiddm_batchnorm_backward",
+    "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
 ]
 
 _lib = None
@@ -109,6 +109,11 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_batchnorm_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp]
         lib.qiddm_batchnorm_backward.restype = i32
         lib.qiddm_batchnorm_backward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.qiddm_noise_ladder.restype = i32
+        lib.qiddm_noise_ladder.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]
+        lib.qiddm_mse_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_mse_loss_grad.restype = i32
+        lib.qiddm_mse_loss_grad.argtypes = [vp, vp, vp, i32, f64, f64, i64, vp, vp, vp, vp]
         lib.qiddm_sym_eigh_max_dim.restype = i32
         lib.qiddm_sym_eigh_f64.restype = i32
         lib.qiddm_sym_eigh_f64.argtypes = [vp, i32, vp, vp, vp]

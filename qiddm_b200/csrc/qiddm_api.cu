@@ -524,6 +524,16 @@ int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, in
                                      workspace, (cudaStream_t)stream);
 }
 
+int qiddm_noise_ladder(const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels, int tau,
+                       void *noisy, void *clean, qiddm_stream_t stream) {
+    return qiddm::noise_ladder(x, eps, w, dtype, batch, pixels, tau, noisy, clean, (cudaStream_t)stream);
+}
+size_t qiddm_mse_workspace_bytes(void) { return qiddm::mse_ws_bytes(); }
+int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target_add, int dtype, double scale, double shift,
+                        int64_t n, void *grad, void *loss, void *workspace, qiddm_stream_t stream) {
+    return qiddm::mse_loss_grad(pred, target, target_add, dtype, scale, shift, n, grad, loss, workspace, (cudaStream_t)stream);
+}
+
 int qiddm_sym_eigh_max_dim(void) {
     int m = 1;
     while (qiddm::eigh_smem_bytes(m + 1) <= 227 * 1024) ++m;

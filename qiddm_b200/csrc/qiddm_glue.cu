@@ -216,6 +216,67 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *x, const T *
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// diffusion-step glue (src/noise.py:105-126 + src/models.py:46-67): the noise ladder written directly as the (noisy, clean)
+// pair the training step consumes, and the MSE loss with its gradient in one pass
+// ------------------------------------------------------------------------------------------------------------------
+// level(b, t, p) = clamp(x (1 - w_t) + eps w_t, 0, 1);  noisy[(b, t)] = level(b, t + 1), clean[(b, t)] = level(b, t), t < T
+template <typename T>
+__global__ void __launch_bounds__(256) noise_ladder_kernel(const T *x, const float *eps, const T *w, long long n_bp, int P, int tau,
+                                                           T *noisy, T *clean) {
+    const int steps = tau - 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bp; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / P;
+        const int p = (int)(i - b * P);
+        const T xv = x[i], ev = (T)eps[i];
+        T prev = (T)0;
+        for (int t = 0; t < tau; ++t) {
+            const T wt = w[t];
+            T v = xv * ((T)1 - wt) + ev * wt;
+            v = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+            if (t > 0) {
+                const long long o = (b * steps + (t - 1)) * P + p;
+                noisy[o] = v;
+                clean[o] = prev;
+            }
+            prev = v;
+        }
+    }
+}
+
+constexpr int MSE_BLOCKS = 148 * 8;
+// d = a r + b - t1 + (t2 ? t2 : 0);  partial[block] = sum d^2;  grad = 2 a d / n
+template <typename T>
+__global__ void __launch_bounds__(256) mse_grad_kernel(const T *r, const T *t1, const T *t2, double a, double b, long long n,
+                                                       T *grad, double *partial) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    const double k = 2.0 * a / (double)n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double d = a * (double)r[i] + b - (double)t1[i];
+        if (t2 != nullptr) d += (double)t2[i];
+        acc += d * d;
+        grad[i] = (T)(k * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        partial[blockIdx.x] = s;
+    }
+}
+template <typename T>
+__global__ void mse_finalize_kernel(const double *partial, int n_partial, long long n, T *loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n_partial; ++i) s += partial[i];
+        loss[0] = (T)(s / (double)n);
+    }
+}
+
 inline unsigned ew_grid(long long total) {
     const long long b = (total + 255) / 256;
     return (unsigned)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
@@ -271,7 +332,47 @@ int bn_bwd_impl(const void *x, const void *dy, void *dx, int N, int C, int HW, c
     return e == cudaSuccess ? QIDDM_OK : (int)e;
 }
 
+template <typename T>
+int ladder_impl(const void *x, const float *eps, const void *w, long long batch, int P, int tau, void *noisy, void *clean,
+                cudaStream_t s) {
+    noise_ladder_kernel<T><<<ew_grid(batch * P), 256, 0, s>>>(reinterpret_cast<const T *>(x), eps, reinterpret_cast<const T *>(w),
+                                                              batch * P, P, tau, reinterpret_cast<T *>(noisy), reinterpret_cast<T *>(clean));
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+template <typename T>
+int mse_impl(const void *r, const void *t1, const void *t2, double a, double b, long long n, void *grad, void *loss, double *ws,
+             cudaStream_t s) {
+    const int blocks = (int)((n + 255) / 256 < MSE_BLOCKS ? (n + 255) / 256 : MSE_BLOCKS);
+    mse_grad_kernel<T><<<blocks, 256, 0, s>>>(reinterpret_cast<const T *>(r), reinterpret_cast<const T *>(t1),
+                                              reinterpret_cast<const T *>(t2), a, b, n, reinterpret_cast<T *>(grad), ws);
+    mse_finalize_kernel<T><<<1, 32, 0, s>>>(ws, blocks, n, reinterpret_cast<T *>(loss));
+    count_launch(2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
 }  // namespace
+
+size_t mse_ws_bytes() { return (size_t)MSE_BLOCKS * sizeof(double); }
+
+int noise_ladder(const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau, void *noisy,
+                 void *clean, cudaStream_t s) {
+    if (!x || !eps || !w || !noisy || !clean || batch < 0 || P < 1 || tau < 2) return QIDDM_EINVAL;
+    if (batch == 0) return QIDDM_OK;
+    if (dtype == QIDDM_DTYPE_F64) return ladder_impl<double>(x, eps, w, batch, P, tau, noisy, clean, s);
+    if (dtype == QIDDM_DTYPE_F32) return ladder_impl<float>(x, eps, w, batch, P, tau, noisy, clean, s);
+    return QIDDM_EINVAL;
+}
+
+int mse_loss_grad(const void *r, const void *t1, const void *t2, int dtype, double a, double b, long long n, void *grad,
+                  void *loss, void *ws, cudaStream_t s) {
+    if (!r || !t1 || !grad || !loss || !ws || n < 1) return QIDDM_EINVAL;
+    if (dtype == QIDDM_DTYPE_F64) return mse_impl<double>(r, t1, t2, a, b, n, grad, loss, reinterpret_cast<double *>(ws), s);
+    if (dtype == QIDDM_DTYPE_F32) return mse_impl<float>(r, t1, t2, a, b, n, grad, loss, reinterpret_cast<double *>(ws), s);
+    return QIDDM_EINVAL;
+}
 
 size_t batchnorm_ws_bytes(int C) { return ((size_t)C * BN_SPLITS * 2 + (size_t)C * 2) * sizeof(double); }
 

@@ -16,3 +16,58 @@ def add_normal_noise_multiple(data: torch.Tensor, tau: int, decay_mod: float = 1
     w = (w / w.max()).to(data.dtype)[None, :, None]                      # (1, tau, 1)
     noisy = data[:, None, :] * (1 - w) + eps.to(data.device)[:, None, :] * w
     return noisy.clamp(0, 1).reshape(batch * tau, pixels)
+
+
+def _level_weights(tau: int, decay_mod: float, device, dtype) -> torch.Tensor:
+    w = torch.linspace(0, 1, tau, device=device) ** decay_mod
+    return (w / w.max()).to(dtype)
+
+
+def ladder_pair(data: torch.Tensor, T: int, decay_mod: float = 3.0, eps: torch.Tensor = None):
+    """(noisy, clean) of the training step in one kernel launch (qiddm_noise_ladder): the tau = T + 1 level ladder of
+    `add_normal_noise_multiple` (src/noise.py:105-126) written directly as noisy = levels 1..T and clean = levels 0..T-1,
+    each ((batch T), pixels) batch-major -- what src/models.py:46-63 slices out of the full ladder.  CUDA tensors only."""
+    import ctypes as C
+    from . import _lib as L
+    if not data.is_cuda:
+        raise L.QiddmError("ladder_pair needs CUDA tensors; use add_normal_noise_multiple on the host")
+    if data.dim() == 1:
+        data = data.unsqueeze(0)
+    data = data.contiguous()
+    batch, pixels = data.shape
+    if eps is None:
+        eps = torch.normal(mean=0.5, std=0.2, size=(batch, pixels), device=data.device)      # float32 draw, as the reference
+    eps = eps.to(device=data.device, dtype=torch.float32).contiguous()
+    dt = {torch.float32: L.DTYPE_F32, torch.float64: L.DTYPE_F64}[data.dtype]
+    w = _level_weights(T + 1, decay_mod, data.device, data.dtype)
+    noisy = torch.empty((batch * T, pixels), dtype=data.dtype, device=data.device)
+    clean = torch.empty_like(noisy)
+    with torch.cuda.device(data.device):
+        L.check(L.load_library().qiddm_noise_ladder(L._ptr(data), L._ptr(eps), L._ptr(w), dt, batch, pixels, T + 1,
+                                                    L._ptr(noisy), L._ptr(clean),
+                                                    C.c_void_p(torch.cuda.current_stream(data.device).cuda_stream)),
+                "qiddm_noise_ladder")
+    return noisy, clean
+
+
+def mse_loss_and_grad(pred: torch.Tensor, target: torch.Tensor, target_add: torch.Tensor = None, scale: float = 1.0,
+                      shift: float = 0.0):
+    """loss = mean((scale * pred + shift - target + target_add)^2) and d loss / d pred in one pass (qiddm_mse_loss_grad):
+    the MSELoss + `.mean().backward()` seed of src/models.py:65-67 (goal "data") and :95-99 (goal "noise": scale 0.1,
+    shift -0.05, target = noisy, target_add = clean).  Returns (loss 0-d tensor, grad like pred)."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load_library()
+    pred_c = pred.detach().contiguous()
+    dt = {torch.float32: L.DTYPE_F32, torch.float64: L.DTYPE_F64}[pred_c.dtype]
+    t1 = target.detach().to(pred_c.dtype).contiguous()
+    t2 = target_add.detach().to(pred_c.dtype).contiguous() if target_add is not None else None
+    grad = torch.empty_like(pred_c)
+    loss = torch.empty((), dtype=pred_c.dtype, device=pred_c.device)
+    ws = torch.empty(int(lib.qiddm_mse_workspace_bytes()), dtype=torch.uint8, device=pred_c.device)
+    with torch.cuda.device(pred_c.device):
+        L.check(lib.qiddm_mse_loss_grad(L._ptr(pred_c), L._ptr(t1), L._ptr(t2), dt, float(scale), float(shift), pred_c.numel(),
+                                        L._ptr(grad), L._ptr(loss), L._ptr(ws),
+                                        C.c_void_p(torch.cuda.current_stream(pred_c.device).cuda_stream)),
+                "qiddm_mse_loss_grad")
+    return loss, grad

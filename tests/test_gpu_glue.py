@@ -95,3 +95,64 @@ def test_unet_with_library_glue_equals_torch_glue():
     assert rel_to_max(y, y2) <= 1e-9
     for k, p in net.named_parameters():
         assert rel_to_max(grads[k], p.grad, floor=1e-12) <= 1e-5, k      # fp32 QConv children amplify glue round-off
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-15), (torch.float32, 1e-6)])
+def test_fused_noise_ladder_pair_matches_the_reference_schedule(dtype, tol):
+    """noise.ladder_pair (one kernel) == slicing add_normal_noise_multiple's ladder as src/models.py:46-63 does."""
+    from qiddm_b200 import noise
+    torch.manual_seed(0)
+    x = torch.rand(7, 50, dtype=dtype, device="cuda")
+    eps = torch.normal(0.5, 0.2, size=(7, 50), device="cuda")
+    T = 10
+    whole = noise.add_normal_noise_multiple(x, tau=T + 1, decay_mod=3.0, eps=eps).reshape(7, T + 1, 50)
+    noisy, clean = noise.ladder_pair(x, T, 3.0, eps=eps)
+    assert noisy.shape == (70, 50) and noisy.dtype == dtype
+    assert (noisy - whole[:, 1:].reshape(70, 50)).abs().max().item() <= tol
+    assert (clean - whole[:, :-1].reshape(70, 50)).abs().max().item() <= tol
+    assert torch.equal(clean.reshape(7, T, 50)[:, 0], x.clamp(0, 1))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-13), (torch.float32, 1e-5)])
+def test_fused_mse_loss_and_grad_matches_torch(dtype, tol):
+    from qiddm_b200 import noise
+    torch.manual_seed(1)
+    p = torch.rand(33, 1, 9, 9, dtype=dtype, device="cuda", requires_grad=True)
+    a, b = torch.rand_like(p), torch.rand_like(p)
+    ref = torch.nn.MSELoss()(p, a)
+    ref.backward()
+    loss, grad = noise.mse_loss_and_grad(p, a)
+    assert abs(loss.item() - ref.item()) <= tol * ref.item() and rel_to_max(grad, p.grad) <= tol
+    p.grad = None
+    ref = torch.nn.MSELoss()((p - 0.5) * 0.1, a - b)          # goal "noise" (src/models.py:95-96)
+    ref.backward()
+    loss, grad = noise.mse_loss_and_grad(p, a, b, scale=0.1, shift=-0.05)
+    assert abs(loss.item() - ref.item()) <= tol * ref.item() and rel_to_max(grad, p.grad) <= tol
+
+
+def test_diffusion_step_fused_glue_equals_torch_glue():
+    """Diffusion.forward with the fused ladder + MSE kernels vs the same step through the torch ops (custom add_noise /
+    verbose path), both goals: same loss and parameter gradients."""
+    from qiddm_b200 import models, nn, noise
+    for goal in ("data", "noise"):
+        torch.manual_seed(3)
+        net = nn.QIDDM_LL_noise(64, 4, 3, 2)
+        d = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (8, 8), torch.nn.MSELoss()).to("cuda", torch.float64)
+        d.train()
+        x = torch.rand(3, 64, dtype=torch.float64, device="cuda")
+        torch.manual_seed(11)
+        (l1,) = d(x=x, T=5)
+        g1 = {k: p.grad.clone() for k, p in net.named_parameters()}
+        net.zero_grad()
+        d.add_noise = lambda data, tau, decay_mod: noise.add_normal_noise_multiple(data, tau, decay_mod)   # torch ladder
+        d.loss = _TorchMSE()                                                                              # torch loss path
+        torch.manual_seed(11)
+        (l3,) = d(x=x, T=5)
+        assert abs(l1.item() - l3.item()) <= 1e-9 * abs(l3.item())
+        for k, p in net.named_parameters():
+            assert rel_to_max(g1[k], p.grad, floor=1e-12) <= 1e-6, (goal, k)
+
+
+class _TorchMSE(torch.nn.Module):          # not `type(...) is MSELoss` -> Diffusion keeps the torch loss path
+    def forward(self, a, b):
+        return torch.nn.functional.mse_loss(a, b)
