@@ -89,15 +89,19 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(
     return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 // RY(theta) on an amplitude pair, cs = (cos, sin)(theta/2)
+// The real 2 x 2 rotation acts on (re, im) pairs, so it maps one-to-one onto the packed fp32 instructions of sm_100
+// (fma.rn.f32x2 / mul.rn.f32x2): same FMA-pipe time, half the issued instructions (the forward kernels are issue-bound).
 __device__ __forceinline__ void ry_pair(float2 cs, float2 &x0, float2 &x1) {
     const float2 a = x0, b = x1;
-    x0 = make_float2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
-    x1 = make_float2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
+    const float2 c2 = make_float2(cs.x, cs.x), s2 = make_float2(cs.y, cs.y), ns2 = make_float2(-cs.y, -cs.y);
+    x0 = __ffma2_rn(c2, a, __fmul2_rn(ns2, b));
+    x1 = __ffma2_rn(s2, a, __fmul2_rn(c2, b));
 }
 __device__ __forceinline__ void ry_pair_t(float2 cs, float2 &x0, float2 &x1) {   // RY(theta)^T
     const float2 a = x0, b = x1;
-    x0 = make_float2(cs.x * a.x + cs.y * b.x, cs.x * a.y + cs.y * b.y);
-    x1 = make_float2(cs.x * b.x - cs.y * a.x, cs.x * b.y - cs.y * a.y);
+    const float2 c2 = make_float2(cs.x, cs.x), s2 = make_float2(cs.y, cs.y), ns2 = make_float2(-cs.y, -cs.y);
+    x0 = __ffma2_rn(c2, a, __fmul2_rn(s2, b));
+    x1 = __ffma2_rn(c2, b, __fmul2_rn(ns2, a));
 }
 
 template <int NQ>
