@@ -278,16 +278,18 @@ __device__ __forceinline__ void ry_all(float2 cs, float2 (&s)[1 << RB]) {
 // theta gradient from the post-rotation states, then RY^T on both
 template <int RB, int Q>
 __device__ __forceinline__ float ry_all_bwd(float2 cs, float2 (&s)[1 << RB], float2 (&l)[1 << RB]) {
-    float gt = 0.f;
+    // Re(conj(l1) s0) - Re(conj(l0) s1) summed over the tile: two packed accumulators (re and im products side by side)
+    float2 gp = make_float2(0.f, 0.f), gn = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < (1 << RB) / 2; ++j) {
         const int r0 = ((j >> Q) << (Q + 1)) | (j & ((1 << Q) - 1));
         const int r1 = r0 | (1 << Q);
-        gt += l[r1].x * s[r0].x + l[r1].y * s[r0].y - l[r0].x * s[r1].x - l[r0].y * s[r1].y;
+        gp = __ffma2_rn(l[r1], s[r0], gp);
+        gn = __ffma2_rn(l[r0], s[r1], gn);
         ry_pair_t(cs, s[r0], s[r1]);
         ry_pair_t(cs, l[r0], l[r1]);
     }
-    return gt;
+    return (gp.x + gp.y) - (gn.x + gn.y);
 }
 // s[r] *= table[r] (CONJ: conj(table[r])); two entries per 16-byte uniform load
 template <int RB, bool CONJ, bool GLOBAL>
