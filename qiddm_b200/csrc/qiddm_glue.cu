@@ -269,12 +269,12 @@ __global__ void __launch_bounds__(256) mse_grad_kernel(const T *r, const T *t1, 
     }
 }
 template <typename T>
-__global__ void mse_finalize_kernel(const double *partial, int n_partial, long long n, T *loss) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n_partial; ++i) s += partial[i];
-        loss[0] = (T)(s / (double)n);
-    }
+__global__ void mse_finalize_kernel(const double *partial, int n_partial, long long n, T *loss) {   // one warp, fixed order
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) loss[0] = (T)(s / (double)n);
 }
 
 inline unsigned ew_grid(long long total) {
