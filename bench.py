@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=262144, help="circuit instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=524288, help="circuit instances per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--path", default="auto", choices=["auto", "gate", "gemm"],
@@ -302,8 +302,8 @@ def run_b200(args):
                     "frac": achieved / tc_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's three GEMM launches, from
                     # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv)
-                    "traffic": 3.41e9 if (B == 262144 and args.precision == 3 and world == 1) else None,
-                    "traffic_unit": "bytes/launch (algorithmic operand + result bytes: 3.0e9)",
+                    "traffic": 7.03e9 if (B == 524288 and args.precision == 3) else None,
+                    "traffic_unit": "bytes/launch (algorithmic operand + result bytes: 6.04e9)",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
                     "ms_per_launch": per_launch_ms, "launches": kd["launches"],
                     "algorithmic_flops": "2*M*N*K per GEMM (single pass); precision %d executes %dx that"
