@@ -889,7 +889,7 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
 __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long B, int F, int Kp, long long Bp, int n_pad,
                                                       float add_offset, float pad, __half *Xh, __half *Xl, __half *XTh,
                                                       __half *XTl, float *inv_n2) {
-    __shared__ __half th[64][72], tl[64][72];
+    __shared__ __half th[64][66], tl[64][66];      // 33-word rows: the transposed 2-byte reads spread over the banks
     const long long r0 = (long long)blockIdx.x * 64;
     const int t = threadIdx.x;
     const bool vec = (F & 3) == 0 && ((uintptr_t)x & 15) == 0;
@@ -928,8 +928,11 @@ __global__ void __launch_bounds__(256) prep_xt_kernel(const float *x, long long 
                 *reinterpret_cast<uint4 *>(Xh + r * Kp + c) = *reinterpret_cast<const uint4 *>(hi);
                 *reinterpret_cast<uint4 *>(Xl + r * Kp + c) = *reinterpret_cast<const uint4 *>(lo);
             }
-            *reinterpret_cast<uint4 *>(&th[rr][pc * 8]) = *reinterpret_cast<const uint4 *>(hi);
-            *reinterpret_cast<uint4 *>(&tl[rr][pc * 8]) = *reinterpret_cast<const uint4 *>(lo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<__half2 *>(&th[rr][pc * 8 + 2 * j]) = __halves2half2(hi[2 * j], hi[2 * j + 1]);
+                *reinterpret_cast<__half2 *>(&tl[rr][pc * 8 + 2 * j]) = __halves2half2(lo[2 * j], lo[2 * j + 1]);
+            }
         }
         __syncthreads();
 #pragma unroll
