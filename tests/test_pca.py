@@ -112,3 +112,16 @@ def test_batched_jacobi_kernel_and_grouped_module_on_gpu():
         whole = m(x)
         parts = torch.cat([m(x[5 * i:5 * i + 5]) for i in range(4)])
     assert (whole - parts).abs().max().item() <= 1e-6 * parts.abs().max().item()
+
+
+def test_host_sklearn_pca_still_plugs_in():
+    """`module.pca = sklearn.decomposition.PCA(k)` (or QIDDM_PCA=host) keeps the reference's host round trip."""
+    from sklearn.decomposition import PCA
+    from qiddm_b200.nn import qdense
+    x = torch.rand(10, 64, dtype=torch.float64)
+    a = qdense._pca_fit_transform(PCA(n_components=4), x)
+    b = qdense._pca_fit_transform(DevicePCA(4), x)
+    assert a.shape == b.shape == (10, 4) and a.dtype == torch.float64
+    assert (a.abs() - b.abs()).abs().max() <= 1e-9 * b.abs().max()          # same scores up to the sign convention
+    with pytest.raises(ValueError):
+        qdense._pca_fit_transform(PCA(n_components=4), torch.rand(20, 64, dtype=torch.float64), 10)
