@@ -29,6 +29,7 @@
 // (at most 15) partial sums are reduced over the warp with a reduce-scatter and added to per-CTA
 // accumulators in shared memory; per-CTA partials are summed in double precision by
 // finalize_grads_kernel (incl. the tanh / pi*tanh re-map chain rule).
+#include <atomic>
 #include <math_constants.h>
 #include <cstdlib>
 #include "qiddm_internal.h"
@@ -957,13 +958,29 @@ cudaError_t info_k(const GateParams &p, LaunchInfo *li) {
     auto kern = gate_kernel<NQ, RB, BWD, RES>;
     li->block = C::T;
     li->smem = smem_bytes<NQ, RB>(p, BWD, RES);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li->smem);
-    if (e != cudaSuccess) return e;
+    // the attribute / occupancy queries cost ~10 us of host time per launch: remembered per kernel instantiation, thread
+    // and device for the last shared-memory size (a module calls the same circuit over and over)
+    thread_local size_t c_smem = ~(size_t)0;
+    thread_local int c_dev = -1, c_sms = 0, c_per_sm = 0;
+    cudaError_t e;
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, li->smem)) != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (c_smem == li->smem && c_dev == dev) {
+        sms = c_sms; per_sm = c_per_sm;
+    } else {
+        // the opt-in shared-memory limit of a function is process-wide per device: only ever raise it
+        static std::atomic<int> attr_max[64];
+        const int di = dev & 63;
+        if ((int)li->smem > attr_max[di].load(std::memory_order_relaxed)) {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li->smem)) != cudaSuccess) return e;
+            int cur = attr_max[di].load(std::memory_order_relaxed);
+            while ((int)li->smem > cur && !attr_max[di].compare_exchange_weak(cur, (int)li->smem)) {}
+        }
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, li->smem)) != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        c_smem = li->smem; c_dev = dev; c_sms = sms; c_per_sm = per_sm;
+    }
     const long long need = (p.B + C::CPB - 1) / C::CPB;
     const long long cap = (long long)sms * per_sm;
     li->grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
