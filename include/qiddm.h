@@ -203,6 +203,15 @@ size_t qiddm_mse_workspace_bytes(void);
 int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target_add, int dtype, double scale, double shift,
                         int64_t n, void *grad, void *loss, void *workspace, qiddm_stream_t stream);
 
+/* Noise channels right before a probability readout (the `add_noise` branch of nn/qdense.py:98-104, :174-180, :431-439,
+ * run on `default.mixed` by src/mnist_noise.py:211-229): the same single-qubit channel on every wire immediately before
+ * probs() acts on the probability vector as p' = (M x ... x M) p with one 2 x 2 column-stochastic M = [[m00, m01], [m10,
+ * m11]] per wire -- AmplitudeDamping(g): [[1, g], [0, 1 - g]]; DepolarizingChannel(q): [[1 - 2q/3, 2q/3], [2q/3, 1 - 2q/3]];
+ * PhaseShift / PhaseDamping: identity.  probs_in / probs_out (batch, 2^n), tensor dtype; the backward is the same call
+ * with M transposed.  probs_in == probs_out is allowed. */
+int qiddm_readout_channel(const void *probs_in, void *probs_out, int dtype, int64_t batch, int n_qubits, double m00, double m01,
+                          double m10, double m11, qiddm_stream_t stream);
+
 /* On-device PCA support (replaces the sklearn `PCA.fit_transform` host round trip of nn/qdense.py:456, :1429):
  * eigen-decomposition of a symmetric m x m float64 matrix (the Gram matrix of the centred batch rows), one CTA, parallel
  * cyclic Jacobi.  evals[m] in DESCENDING order, evecs (m x m row-major) column j = eigenvector of evals[j].

@@ -447,3 +447,71 @@ def sample(net_fn, first_x: torch.Tensor, n_iters: int, goal: str = "data", nois
             else:
                 x = torch.clamp(x - (pred - 0.5) * 0.1 * noise_factor, 0, 1)
     return x
+
+
+# --------------------------------------------------------------------------------------
+# noise channels of the `*_noise` probability models (nn/qdense.py:98-104, :174-180, :431-439 on default.mixed)
+# Kraus operators as documented for PennyLane 0.29 (qml.PhaseDamping, qml.AmplitudeDamping, qml.DepolarizingChannel,
+# qml.PhaseShift); PennyLane itself is not installable here, so this part of the oracle is "parity unpinned".
+NOISE_PHASE, NOISE_AMPLITUDE_DAMPING, NOISE_DEPOLARIZING = 1, 2, 3
+
+
+def kraus_operators(kind: int, param: float, phase_shift: bool = False):
+    z = torch.zeros((), dtype=CDTYPE)
+    one = torch.ones((), dtype=CDTYPE)
+    if kind == NOISE_PHASE:
+        if phase_shift:                                      # qml.PhaseShift(phi) = diag(1, e^{i phi}) (a unitary)
+            return [torch.stack([torch.stack([one, z]), torch.stack([z, torch.exp(1j * torch.tensor(param, dtype=RDTYPE)).to(CDTYPE)])])]
+        g = torch.tensor(param, dtype=RDTYPE)                # qml.PhaseDamping(g)
+        return [torch.diag(torch.stack([one, torch.sqrt(1 - g).to(CDTYPE)])),
+                torch.diag(torch.stack([z, torch.sqrt(g).to(CDTYPE)]))]
+    if kind == NOISE_AMPLITUDE_DAMPING:                      # qml.AmplitudeDamping(g)
+        g = torch.tensor(param, dtype=RDTYPE)
+        k0 = torch.diag(torch.stack([one, torch.sqrt(1 - g).to(CDTYPE)]))
+        k1 = torch.zeros(2, 2, dtype=CDTYPE)
+        k1[0, 1] = torch.sqrt(g)
+        return [k0, k1]
+    if kind == NOISE_DEPOLARIZING:                           # qml.DepolarizingChannel(p): sqrt(1-p) I, sqrt(p/3) X, Y, Z
+        p = torch.tensor(param, dtype=RDTYPE)
+        eye = torch.eye(2, dtype=CDTYPE)
+        x = torch.tensor([[0, 1], [1, 0]], dtype=CDTYPE)
+        y = torch.tensor([[0, -1j], [1j, 0]], dtype=CDTYPE)
+        zz = torch.tensor([[1, 0], [0, -1]], dtype=CDTYPE)
+        return [torch.sqrt(1 - p) * eye, torch.sqrt(p / 3) * x, torch.sqrt(p / 3) * y, torch.sqrt(p / 3) * zz]
+    raise ValueError(kind)
+
+
+def density_matrix_readout(state: torch.Tensor, n: int, kind: int, param: float, phase_shift: bool = False) -> torch.Tensor:
+    """What default.mixed computes: rho = |psi><psi|, the channel on every wire (Kraus sum), then the diagonal.
+    state (B, 2**n) complex -> (B, 2**n) probabilities.  Exponential in n: small cases only."""
+    B, A = state.shape
+    rho = state[:, :, None] * state.conj()[:, None, :]                  # (B, A, A)
+    ks = kraus_operators(kind, param, phase_shift)
+    for wire in range(n):
+        shape = (B,) + (2,) * (2 * n)
+        r = rho.reshape(shape)
+        row_ax, col_ax = 1 + wire, 1 + n + wire
+        acc = torch.zeros_like(r)
+        for k in ks:
+            t = torch.movedim(torch.tensordot(k, torch.movedim(r, row_ax, 0), dims=([1], [0])), 0, row_ax)            # K rho
+            t = torch.movedim(torch.tensordot(k.conj(), torch.movedim(t, col_ax, 0), dims=([1], [0])), 0, col_ax)    # .. K^dagger
+            acc = acc + t
+        rho = acc.reshape(B, A, A)
+    return torch.diagonal(rho, dim1=1, dim2=2).real
+
+
+def readout_channel_probs(p: torch.Tensor, n: int, kind: int, param: float) -> torch.Tensor:
+    """The same thing as a classical map on the probabilities (what the CUDA path implements): per wire
+    AmplitudeDamping (p0, p1) -> (p0 + g p1, (1 - g) p1); Depolarizing: bit flip with probability 2p/3; phase: identity."""
+    if kind == NOISE_PHASE:
+        return p
+    if kind == NOISE_AMPLITUDE_DAMPING:
+        m = torch.tensor([[1.0, param], [0.0, 1.0 - param]], dtype=p.dtype)
+    else:
+        q = 2.0 * param / 3.0
+        m = torch.tensor([[1.0 - q, q], [q, 1.0 - q]], dtype=p.dtype)
+    B = p.shape[0]
+    t = p.reshape((B,) + (2,) * n)
+    for wire in range(n):
+        t = torch.movedim(torch.tensordot(m, torch.movedim(t, 1 + wire, 0), dims=([1], [0])), 0, 1 + wire)
+    return t.reshape(B, -1)

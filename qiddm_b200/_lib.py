@@ -53,6 +53,7 @@ EXPORTS = [
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
+    "qiddm_readout_channel",
 ]
 
 _lib = None
@@ -114,6 +115,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_mse_workspace_bytes.restype = C.c_size_t
         lib.qiddm_mse_loss_grad.restype = i32
         lib.qiddm_mse_loss_grad.argtypes = [vp, vp, vp, i32, f64, f64, i64, vp, vp, vp, vp]
+        lib.qiddm_readout_channel.restype = i32
+        lib.qiddm_readout_channel.argtypes = [vp, vp, i32, i64, i32, f64, f64, f64, f64, vp]
         lib.qiddm_sym_eigh_max_dim.restype = i32
         lib.qiddm_sym_eigh_f64.restype = i32
         lib.qiddm_sym_eigh_f64.argtypes = [vp, i32, vp, vp, vp]

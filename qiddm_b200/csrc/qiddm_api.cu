@@ -534,6 +534,11 @@ int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target
     return qiddm::mse_loss_grad(pred, target, target_add, dtype, scale, shift, n, grad, loss, workspace, (cudaStream_t)stream);
 }
 
+int qiddm_readout_channel(const void *probs_in, void *probs_out, int dtype, int64_t batch, int n_qubits, double m00, double m01,
+                          double m10, double m11, qiddm_stream_t stream) {
+    return qiddm::prob_channel(probs_in, probs_out, dtype, batch, n_qubits, m00, m01, m10, m11, (cudaStream_t)stream);
+}
+
 int qiddm_sym_eigh_max_dim(void) {
     int m = 1;
     while (qiddm::eigh_smem_bytes(m + 1) <= 227 * 1024) ++m;

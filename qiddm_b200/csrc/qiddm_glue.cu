@@ -277,6 +277,36 @@ __global__ void mse_finalize_kernel(const double *partial, int n_partial, long l
     if (threadIdx.x == 0) loss[0] = (T)(s / (double)n);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Noise channels right before a computational-basis readout (nn/qdense.py:98-104, :174-180, :431-439 on default.mixed;
+// src/mnist_noise.py:211-229).  A single-qubit channel applied to every wire immediately before probs() only moves
+// population: PhaseShift / PhaseDamping are diagonal (no effect), AmplitudeDamping(g) maps (p0, p1) -> (p0 + g p1,
+// (1 - g) p1), DepolarizingChannel(q) (Kraus sqrt(1-q) I, sqrt(q/3) X, Y, Z) flips the bit with probability 2q/3.  So
+// the density-matrix simulation reduces EXACTLY to one 2 x 2 column-stochastic matrix M per wire acting on the
+// probability vector: p' = (M x ... x M) p, n butterfly stages in shared memory, one CTA per instance.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) prob_channel_kernel(const T *p_in, T *p_out, int n, double m00, double m01, double m10,
+                                                           double m11) {
+    extern __shared__ double ch_sm[];
+    const int A = 1 << n;
+    const T *src = p_in + (size_t)blockIdx.x * A;
+    for (int k = threadIdx.x; k < A; k += blockDim.x) ch_sm[k] = (double)src[k];
+    __syncthreads();
+    for (int b = 0; b < n; ++b) {
+        for (int i = threadIdx.x; i < A / 2; i += blockDim.x) {
+            const int lo = i & ((1 << b) - 1);
+            const int k0 = ((i >> b) << (b + 1)) | lo, k1 = k0 | (1 << b);
+            const double a = ch_sm[k0], c = ch_sm[k1];
+            ch_sm[k0] = m00 * a + m01 * c;
+            ch_sm[k1] = m10 * a + m11 * c;
+        }
+        __syncthreads();
+    }
+    T *dst = p_out + (size_t)blockIdx.x * A;
+    for (int k = threadIdx.x; k < A; k += blockDim.x) dst[k] = (T)ch_sm[k];
+}
+
 inline unsigned ew_grid(long long total) {
     const long long b = (total + 255) / 256;
     return (unsigned)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
@@ -354,6 +384,25 @@ int mse_impl(const void *r, const void *t1, const void *t2, double a, double b, 
 }
 
 }  // namespace
+
+int prob_channel(const void *p_in, void *p_out, int dtype, long long batch, int n, double m00, double m01, double m10, double m11,
+                 cudaStream_t s) {
+    if (!p_in || !p_out || batch < 0 || n < 1 || n > QIDDM_MAX_QUBITS || batch > 0x7fffffffLL) return QIDDM_EINVAL;
+    if (batch == 0) return QIDDM_OK;
+    const size_t smem = ((size_t)1 << n) * sizeof(double);
+    const int threads = (1 << n) / 2 < 256 ? ((1 << n) / 2 < 32 ? 32 : (1 << n) / 2) : 256;
+    if (dtype == QIDDM_DTYPE_F64)
+        prob_channel_kernel<double><<<(unsigned)batch, threads, smem, s>>>(reinterpret_cast<const double *>(p_in),
+                                                                            reinterpret_cast<double *>(p_out), n, m00, m01, m10, m11);
+    else if (dtype == QIDDM_DTYPE_F32)
+        prob_channel_kernel<float><<<(unsigned)batch, threads, smem, s>>>(reinterpret_cast<const float *>(p_in),
+                                                                           reinterpret_cast<float *>(p_out), n, m00, m01, m10, m11);
+    else
+        return QIDDM_EINVAL;
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
 
 size_t mse_ws_bytes() { return (size_t)MSE_BLOCKS * sizeof(double); }
 

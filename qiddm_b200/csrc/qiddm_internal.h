@@ -79,6 +79,8 @@ int sym_eigh_f64(const double *A, int m, long long count, double *evals, double 
 // qiddm_glue.cu — UNet glue around QConv2d: bilinear resize (align_corners = False) and BatchNorm2d (NCHW)
 size_t batchnorm_ws_bytes(int C);
 size_t mse_ws_bytes();
+int prob_channel(const void *p_in, void *p_out, int dtype, long long batch, int n, double m00, double m01, double m10, double m11,
+                 cudaStream_t s);
 int noise_ladder(const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau, void *noisy,
                  void *clean, cudaStream_t s);
 int mse_loss_grad(const void *r, const void *t1, const void *t2, int dtype, double a, double b, long long n, void *grad,

@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from ..channels import apply_readout_channel, channel_matrix
 from ..functional import run_stage
 from ..pca import DevicePCA
 
@@ -70,14 +71,17 @@ def _pca_fit_transform(pca, x: torch.Tensor, group=None) -> torch.Tensor:
     return _pca_call(pca, "fit_transform", x, group)
 
 
-def _check_noise(add_noise, allow_phase: bool):
+def _check_noise(add_noise, allow_phase: bool, readout_channels: bool = False):
     if add_noise in (0, None):
         return
     if add_noise == 1 and allow_phase:
-        return  # PhaseShift on every wire right before probs(): diagonal, no effect on probabilities
+        return  # PhaseShift / PhaseDamping on every wire right before probs(): diagonal, no effect on probabilities
+    if add_noise in (1, 2, 3) and readout_channels:
+        return  # channels right before probs(): exact classical map on the probabilities (qiddm_b200.channels)
     raise NotImplementedError(
-        f"add_noise={add_noise}: density-matrix noise channels (default.mixed) are out of scope of the "
-        "B200 state-vector path (SURVEY.md §8f-4)")
+        f"add_noise={add_noise}: this class applies its noise channels in the middle of the circuit (after every "
+        "re-upload gate), which needs a density-matrix simulation (default.mixed) -- out of scope of the B200 "
+        "state-vector path (SURVEY.md 8f-4); channels right before a probability readout are supported")
 
 
 def _shape2(shape):
@@ -129,10 +133,20 @@ class _AmplitudeDense(nn.Module):
         s = L.StageSpec(**{**s.__dict__, "read_count": s.dim, "post_scale": 1.0, "clamp": False})
         return run_stage(s, inp, self.weights)
 
+    _noise_params = {2: 0.1, 3: 0.02}      # AmplitudeDamping(0.1), DepolarizingChannel(0.02): nn/qdense.py:101-104
+
     def forward(self, x):
         x = einops.rearrange(x, "b 1 w h -> b (w h)")
-        # qnode + _post_process fused in the kernel epilogue (slice, scale by pixels, clamp)
-        x = run_stage(self._spec(), x, self.weights)
+        noise = getattr(self, "add_noise", 0)
+        if channel_matrix(noise, self._noise_params.get(noise, 0.0)) is not None:
+            # channels on every wire right before probs() (read at call time: src/mnist_noise.py:218 sets it on the
+            # trained net): full probabilities -> exact readout channel -> _post_process
+            _check_noise(noise, True, readout_channels=True)
+            p = apply_readout_channel(self._circuit(x), self.wires, noise, self._noise_params[noise])
+            x = torch.clamp(p[:, :self.pixels] * self.pixels, 0, 1)
+        else:
+            # qnode + _post_process fused in the kernel epilogue (slice, scale by pixels, clamp)
+            x = run_stage(self._spec(), x, self.weights)
         return einops.rearrange(x, "b (w h) -> b 1 w h", w=self.width, h=self.height)
 
 
@@ -157,7 +171,7 @@ class QDenseUndirected_old_noise(_AmplitudeDense):
 
     def __init__(self, qdepth, shape, add_noise=0, device_type="default.qubit.torch") -> None:
         super().__init__()
-        _check_noise(add_noise, allow_phase=True)
+        _check_noise(add_noise, allow_phase=True, readout_channels=True)
         self.add_noise = add_noise
         self.device_type = device_type
         self._setup(qdepth, shape)
@@ -177,7 +191,7 @@ class QNN_A(nn.Module):
 
     def __init__(self, qdepth, shape, add_noise=0, device_type="default.qubit.torch", diff_method="backprop") -> None:
         super().__init__()
-        _check_noise(add_noise, allow_phase=False)
+        _check_noise(add_noise, allow_phase=True, readout_channels=True)
         self.qdepth = qdepth
         self.add_noise = add_noise
         self.device_type = device_type
@@ -199,10 +213,18 @@ class QNN_A(nn.Module):
     def _circuit(self, inp):
         return run_stage(self._spec(full=True), inp, self.weights)
 
+    _noise_params = {2: 0.05, 3: 0.02}     # PhaseDamping: no effect; AmplitudeDamping(0.05); Depolarizing(0.02): :175-180
+
     def forward(self, x):
         x = einops.rearrange(x, "b 1 w h -> b (w h)")
         x = self.linear_down(x)
-        x = run_stage(self._spec(), x, self.weights)
+        noise = self.add_noise
+        if channel_matrix(noise, self._noise_params.get(noise, 0.0)) is not None:
+            _check_noise(noise, True, readout_channels=True)
+            p = apply_readout_channel(self._circuit(x), self.wires, noise, self._noise_params[noise])
+            x = torch.clamp(p[:, :self.pixels] * self.pixels, 0, 1)
+        else:
+            x = run_stage(self._spec(), x, self.weights)
         return einops.rearrange(x, "b (w h) -> b 1 w h", w=self.width, h=self.height)
 
     def __repr__(self):
@@ -336,9 +358,21 @@ class _DifferNBase(nn.Module):
     def _chain(self, a):
         W = getattr(self, self._weight_name)
         n = self._n
+        noise = getattr(self, "add_noise", 0)
+        noisy = getattr(self, "_readout_noise", False) and channel_matrix(noise, self._noise_params.get(noise, 0.0)) is not None
         for k in range(self.N):
             w = W if self._shared_weights else W[k]
-            a = run_stage(self._stage_spec(last=(k == self.N - 1)), a[:, :n].contiguous(), w)
+            last = k == self.N - 1
+            if noisy:
+                # every stage is one QNode whose channels sit right before probs() (nn/qdense.py:431-441): full
+                # probabilities -> exact readout channel -> the stage's usual slice (next angles / final image)
+                p = apply_readout_channel(self._circuit(a, w), n, noise, self._noise_params[noise])
+                if last or self._post_each_stage:
+                    a = torch.clamp(p[:, :(self.pixels if last else n)] * self.pixels, 0, 1)
+                else:
+                    a = p[:, :n]
+            else:
+                a = run_stage(self._stage_spec(last=last), a[:, :n].contiguous(), w)
             if self.detach_quantum:
                 a = a.detach()
         return a
@@ -352,9 +386,12 @@ class _DifferNBase(nn.Module):
 class differN_noise(_DifferNBase):
     """nn/qdense.py:389-478."""
 
+    _readout_noise = True
+    _noise_params = {2: 0.1, 3: 0.02}      # PhaseShift: no effect; AmplitudeDamping(0.1); Depolarizing(0.02): :431-439
+
     def __init__(self, shape, spectrum_layer, N, add_noise=0) -> None:
         super().__init__()
-        _check_noise(add_noise, allow_phase=True)
+        _check_noise(add_noise, allow_phase=True, readout_channels=True)
         self.add_noise = add_noise
         self.wires = self._setup(shape, spectrum_layer, N)
         self.pca = _make_pca(self.wires)

@@ -80,8 +80,9 @@ def test_qconv_wire_count_rule_and_noise_guard():
     with pytest.raises(NotImplementedError):
         nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=2)
     with pytest.raises(NotImplementedError):
-        nn.QDenseUndirected_old_noise(4, 8, add_noise=3)
+        nn.QDenseUndirected_old_noise(4, 8, add_noise=4)
     nn.QDenseUndirected_old_noise(4, 8, add_noise=1)       # PhaseShift before probs: a no-op
+    nn.QDenseUndirected_old_noise(4, 8, add_noise=3)       # channels right before probs(): exact readout map (channels.py)
 
 
 def test_noise_ladder_matches_oracle_and_reference_layout():

@@ -1,0 +1,101 @@
+"""Readout noise channels (add_noise of QDenseUndirected_old_noise / QNN_A / differN_noise, nn/qdense.py:98-104, :174-180,
+:431-439): the classical probability map the CUDA path implements equals the density-matrix (Kraus)
+simulation default.mixed performs, and the modules equal the oracle pipeline."""
+import pytest
+import torch
+
+from conftest import rel_to_max
+from oracle import qiddm_oracle as O
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+@pytest.mark.parametrize("kind,param,ps", [(1, 0.05, True), (1, 0.05, False), (2, 0.1, False), (2, 0.05, False), (3, 0.02, False)])
+def test_channel_before_measurement_is_a_classical_map(n, kind, param, ps):
+    g = torch.Generator().manual_seed(n * 10 + kind)
+    psi = torch.randn(4, 1 << n, generator=g, dtype=torch.float64) + 1j * torch.randn(4, 1 << n, generator=g, dtype=torch.float64)
+    psi = psi / psi.abs().pow(2).sum(1, keepdim=True).sqrt()
+    dm = O.density_matrix_readout(psi, n, kind, param, phase_shift=ps)
+    cl = O.readout_channel_probs(psi.abs() ** 2, n, kind, param)
+    assert (dm - cl).abs().max() <= 1e-14
+    assert (dm.sum(1) - 1).abs().max() <= 1e-14            # trace preserving
+
+
+def test_mid_circuit_noise_classes_still_refuse():
+    from qiddm_b200 import nn
+    for make in (lambda: nn.QNN_noise(64, 4, 2, add_noise=2), lambda: nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=3),
+                 lambda: nn.differN_noise_befor(8, 2, 2, add_noise=2)):
+        with pytest.raises(NotImplementedError):
+            make()
+    assert nn.QDenseUndirected_old_noise(2, 8, add_noise=3).add_noise == 3
+    assert nn.differN_noise(8, 2, 2, add_noise=2).add_noise == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("n,kind,param", [(1, 2, 0.1), (4, 2, 0.05), (6, 3, 0.02), (10, 2, 0.1), (12, 3, 0.02)])
+def test_readout_channel_kernel_and_its_transpose(dtype, n, kind, param):
+    from qiddm_b200 import _lib as L
+    from qiddm_b200.channels import apply_readout_channel
+    g = torch.Generator().manual_seed(n + kind)
+    p = torch.rand(5, 1 << n, generator=g, dtype=torch.float64)
+    p = p / p.sum(1, keepdim=True)
+    pr = p.clone().requires_grad_(True)
+    ref = O.readout_channel_probs(pr, n, kind, param)
+    go = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * go).sum().backward()
+    pd = p.to(dtype).cuda().requires_grad_(True)
+    n0 = L.launch_count()
+    out = apply_readout_channel(pd, n, kind, param)
+    (out * go.to(dtype).cuda()).sum().backward()
+    assert L.launch_count() - n0 == 2
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    assert rel_to_max(out, ref) <= tol and rel_to_max(pd.grad, pr.grad) <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("noise", [1, 2, 3])
+def test_qdense_noise_module_matches_the_density_matrix_oracle(noise):
+    """QDenseUndirected_old_noise(add_noise) == AmplitudeEmbedding -> SEL(tanh W) -> channels (Kraus, density matrix) ->
+    probs -> _post_process, incl. the weight gradient through the channel."""
+    from qiddm_b200 import nn
+    torch.manual_seed(2)
+    m = nn.QDenseUndirected_old_noise(3, 4, add_noise=noise).to("cuda", torch.float64)      # 4x4 image, n = 4
+    x = torch.rand(6, 1, 4, 4, dtype=torch.float64)
+    W = m.weights.detach().cpu().clone().requires_grad_(True)
+    d = O.desc_qdense(3, 16, O.REMAP_TANH)
+    full = O.StageDesc(**{**d.__dict__, "readout": O.READ_STATE, "clamp": False, "post_scale": 1.0})
+    st = O.run_stage(full, x.reshape(6, 16), W.reshape(1, 3, 4, 3))
+    psi = torch.view_as_complex(st.reshape(6, 16, 2).contiguous())
+    param = {1: 0.05, 2: 0.1, 3: 0.02}[noise]
+    probs = O.density_matrix_readout(psi, 4, noise, param, phase_shift=(noise == 1))
+    ref = torch.clamp(probs[:, :16] * 16, 0, 1).reshape(6, 1, 4, 4)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    out = m(x.cuda())
+    (out * g.cuda()).sum().backward()
+    assert rel_to_max(out, ref) <= 1e-5
+    assert rel_to_max(m.weights.grad, W.grad) <= 1e-4
+    # src/mnist_noise.py:218 flips add_noise on a trained net at test time
+    m.add_noise = 0
+    clean = m(x.cuda())
+    assert (noise == 1) == (rel_to_max(clean, out) <= 1e-6)
+
+
+@pytest.mark.gpu
+def test_differn_noise_chain_with_readout_channels():
+    from qiddm_b200 import nn
+    torch.manual_seed(4)
+    m = nn.differN_noise(4, 2, 2, add_noise=3).cuda()                 # 4x4 image, n = 4, L = 2, N = 2
+    ang = torch.rand(5, 4, dtype=torch.float64)
+    W = m.weights.detach().cpu().double()
+    a = ang
+    for k in range(2):
+        d = O.desc_reupload(4, 2, 2, readout=O.READ_STATE)
+        st = O.run_stage(d, a[:, :4], W[k])
+        psi = torch.view_as_complex(st.reshape(5, 16, 2).contiguous())
+        a = O.density_matrix_readout(psi, 4, 3, 0.02)
+    ref = torch.clamp(a[:, :16] * 16, 0, 1)
+    out = m._chain(ang.float().cuda())
+    assert rel_to_max(out, ref) <= 1e-5
+    whole = m(torch.rand(8, 1, 4, 4).cuda())                          # with the PCA in front
+    assert whole.shape == (8, 1, 4, 4)
