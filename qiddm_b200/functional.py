@@ -14,8 +14,10 @@ from ._lib import Plan, StageSpec, UnfoldDesc
 
 class _StageFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan: Plan, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int]):
+    def forward(ctx, plan: Plan, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int],
+                basis: Optional[torch.Tensor] = None):
         ctx.plan = plan
+        ctx.basis = basis
         ctx.x_dtype = x.dtype if x is not None else None
         ctx.gemm = x is not None and plan.use_gemm(x.shape[0])
         ctx.gemm_saved = None
@@ -25,7 +27,7 @@ class _StageFunction(torch.autograd.Function):
             else:
                 out = plan.gemm_forward(x.detach(), weights)
         else:
-            out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch)
+            out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch, basis=basis)
         ctx.save_for_backward(x if x is not None else torch.empty(0), weights)
         ctx.has_x = x is not None
         return out.to(x.dtype if x is not None else weights.dtype)
@@ -41,16 +43,17 @@ class _StageFunction(torch.autograd.Function):
                                             saved=ctx.gemm_saved)
             ctx.gemm_saved = None
         else:
-            gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w)
+            gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w, basis=ctx.basis)
         if gi is not None:
             gi = gi.to(ctx.x_dtype)
-        return None, gi, (gw.view_as(weights) if gw is not None else None), None
+        return None, gi, (gw.view_as(weights) if gw is not None else None), None, None
 
 
 def run_stage(spec: StageSpec, x: Optional[torch.Tensor], weights: torch.Tensor,
-              batch: Optional[int] = None) -> torch.Tensor:
-    """One QNode-equivalent evaluation: (B, n_in) -> (B, n_out), differentiable in x and weights."""
-    return _StageFunction.apply(Plan.get(spec), x, weights, batch)
+              batch: Optional[int] = None, basis: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One QNode-equivalent evaluation: (B, n_in) -> (B, n_out), differentiable in x and weights.
+    `basis` (int32, (B,)): start states of an INIT_BASIS descriptor."""
+    return _StageFunction.apply(Plan.get(spec), x, weights, batch, basis)
 
 
 class _QConvFunction(torch.autograd.Function):

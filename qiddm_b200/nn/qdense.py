@@ -257,11 +257,34 @@ class _QNNBase(_SaveLoadMixin, nn.Module):
         w = self.weights if weights is None else weights
         return run_stage(_reupload_spec(self.hidden_features, 1, self.qdepth), inputs.reshape(-1, self.hidden_features), w)
 
+    def _noisy_expvals(self, batch: int):
+        """QNN_noise with add_noise = 3 (nn/qdense.py:252-263: a channel on every wire right after its RZ, BEFORE the
+        entangling layers).  The state in front of the channels is |0..0> up to a phase, so PhaseDamping and
+        AmplitudeDamping leave it alone (K1|0> = 0) and DepolarizingChannel(p) turns each wire into the classical
+        mixture (1 - 2p/3)|0><0| + (2p/3)|1><1|: the exact density-matrix result is the mixture over the 2^n basis
+        inputs of the noiseless circuit, <Z_i> = sum_s P(s) <s|U^dagger Z_i U|s> -- 2^n state-vector runs, independent
+        of the sample (RZ on a basis state is a phase), computed once per call."""
+        n = self.hidden_features
+        q = 2.0 * self._depolarizing_p / 3.0
+        dev = self.weights.device
+        idx = torch.arange(1 << n, device=dev, dtype=torch.int32)
+        spec = L.StageSpec(n_qubits=n, n_blocks=1, layers_per_block=self.qdepth, init=L.INIT_BASIS, imprimitive=L.IMP_CZ,
+                           readout=L.READ_EXPVAL_Z)
+        vals = run_stage(spec, None, self.weights, batch=1 << n, basis=idx).to(self.weights.dtype)      # (2^n, n)
+        ones = torch.zeros(1 << n, device=dev, dtype=torch.int64)
+        for j in range(n):
+            ones += (idx.long() >> j) & 1
+        prob = (q ** ones.to(vals.dtype)) * ((1.0 - q) ** (n - ones).to(vals.dtype))                      # P(s)
+        return (prob[:, None] * vals).sum(dim=0, keepdim=True).expand(batch, n)
+
     def forward(self, x):
         b, c, w, h = x.shape
         x = x.view(b, -1).to(self.linear_down.weight.dtype)
         x_reduced = self.linear_down(x)
-        x_reduced = self._circuit(x_reduced)
+        if getattr(self, "add_noise", 0) == 3:
+            x_reduced = self._noisy_expvals(b) + 0.0 * x_reduced.sum()       # keeps linear_down in the graph (zero gradient)
+        else:
+            x_reduced = self._circuit(x_reduced)       # add_noise 1 / 2: the channels act on |0..0> and change nothing
         if self.detach_quantum:
             x_reduced = x_reduced.detach()
         x_restored = self.linear_up(x_reduced.to(self.linear_up.weight.dtype))
@@ -271,9 +294,12 @@ class _QNNBase(_SaveLoadMixin, nn.Module):
 class QNN_noise(_QNNBase):
     """nn/qdense.py:219-307."""
 
+    _depolarizing_p = 0.02          # qml.DepolarizingChannel(0.02), nn/qdense.py:261
+
     def __init__(self, input_dim, hidden_features, qdepth: int, add_noise=0) -> None:
         super().__init__()
-        _check_noise(add_noise, allow_phase=False)
+        # channels on the wires of |0..0> (right after the single RZ layer): exactly reducible, see _noisy_expvals
+        _check_noise(add_noise, allow_phase=True, readout_channels=True)
         self.add_noise = add_noise
         self._setup(input_dim, hidden_features, qdepth)
 

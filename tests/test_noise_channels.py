@@ -22,7 +22,7 @@ def test_channel_before_measurement_is_a_classical_map(n, kind, param, ps):
 
 def test_mid_circuit_noise_classes_still_refuse():
     from qiddm_b200 import nn
-    for make in (lambda: nn.QNN_noise(64, 4, 2, add_noise=2), lambda: nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=3),
+    for make in (lambda: nn.QIDDM_PL_noise(64, 4, 2, 2, add_noise=2), lambda: nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=3),
                  lambda: nn.differN_noise_befor(8, 2, 2, add_noise=2)):
         with pytest.raises(NotImplementedError):
             make()
@@ -99,3 +99,70 @@ def test_differn_noise_chain_with_readout_channels():
     assert rel_to_max(out, ref) <= 1e-5
     whole = m(torch.rand(8, 1, 4, 4).cuda())                          # with the PCA in front
     assert whole.shape == (8, 1, 4, 4)
+
+
+def _density_qnn(angles, W, n, kind, param):
+    """Density-matrix simulation of QNN_noise._circuit (nn/qdense.py:249-265): RZ(a_j) + channel on wire j, SEL(CZ), <Z_i>."""
+    B = angles.shape[0]
+    A = 1 << n
+    psi = torch.zeros(B, A, dtype=O.CDTYPE)
+    psi[:, 0] = 1.0
+    for j in range(n):
+        psi = O.apply_1q(psi, O.rz_matrix(angles[:, j]), j, n)
+    rho = psi[:, :, None] * psi.conj()[:, None, :]
+    ks = O.kraus_operators(kind, param)
+    for wire in range(n):
+        r = rho.reshape((B,) + (2,) * (2 * n))
+        acc = torch.zeros_like(r)
+        for k in ks:
+            t = torch.movedim(torch.tensordot(k, torch.movedim(r, 1 + wire, 0), dims=([1], [0])), 0, 1 + wire)
+            t = torch.movedim(torch.tensordot(k.conj(), torch.movedim(t, 1 + n + wire, 0), dims=([1], [0])), 0, 1 + n + wire)
+            acc = acc + t
+        rho = acc.reshape(B, A, A)
+    d = O.StageDesc(n_qubits=n, n_blocks=1, layers_per_block=W.shape[0], init=O.INIT_BASIS, imprimitive=O.IMP_CZ, readout=O.READ_STATE)
+    U = O.circuit_unitary(d, W.reshape(1, W.shape[0], n, 3))
+    rho = U[None] @ rho @ U.conj().T[None]
+    p = torch.diagonal(rho, dim1=1, dim2=2).real
+    k = torch.arange(A)
+    return torch.stack([(p * (1 - 2 * ((k >> (n - 1 - i)) & 1)).to(p.dtype)).sum(1) for i in range(n)], dim=1)
+
+
+def test_qnn_noise_reduction_matches_density_matrix_on_cpu():
+    """The reduction QNN_noise uses (mixture over basis inputs for Depolarizing; nothing for the dampings) == the Kraus
+    density-matrix simulation of the reference circuit."""
+    n, depth = 3, 2
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(depth, n, 3, generator=g, dtype=torch.float64) * 0.4
+    a = torch.randn(4, n, generator=g, dtype=torch.float64)
+    d = O.desc_reupload(n, 1, depth)
+    clean = O.run_stage(d, a, W.reshape(1, depth, n, 3))
+    for kind, param in ((1, 0.03), (2, 0.05)):
+        assert (_density_qnn(a, W, n, kind, param) - clean).abs().max() <= 1e-13
+    dm = _density_qnn(a, W, n, 3, 0.02)
+    db = O.StageDesc(n_qubits=n, n_blocks=1, layers_per_block=depth, init=O.INIT_BASIS, imprimitive=O.IMP_CZ, readout=O.READ_EXPVAL_Z)
+    vals = O.run_stage(db, None, W.reshape(1, depth, n, 3), basis_index=torch.arange(1 << n))
+    q = 2 * 0.02 / 3
+    ones = torch.tensor([bin(s).count("1") for s in range(1 << n)], dtype=torch.float64)
+    mix = ((q ** ones) * ((1 - q) ** (n - ones)))[:, None] * vals
+    assert (dm - mix.sum(0, keepdim=True)).abs().max() <= 1e-13
+
+
+@pytest.mark.gpu
+def test_qnn_noise_module_with_depolarizing_channel():
+    from qiddm_b200 import nn
+    torch.manual_seed(7)
+    m = nn.QNN_noise(64, 4, 3, add_noise=3)
+    x = torch.rand(5, 1, 8, 8, dtype=torch.float64, device=m.weights.device)
+    W = m.weights.detach().cpu().clone().requires_grad_(True)
+    dm = _density_qnn(torch.zeros(1, 4, dtype=torch.float64), W, 4, 3, 0.02)          # input-independent
+    ref = (dm @ m.linear_up.weight.detach().cpu().T + m.linear_up.bias.detach().cpu()).expand(5, 64).reshape(5, 1, 8, 8)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    out = m(x)
+    (out * g.to(out.device)).sum().backward()
+    assert rel_to_max(out, ref) <= 1e-5
+    assert rel_to_max(m.weights.grad, W.grad) <= 1e-4
+    m.add_noise = 2                                         # AmplitudeDamping on |0..0>: identical to the noiseless net
+    m2 = m(x)
+    m.add_noise = 0
+    assert rel_to_max(m2, m(x)) <= 1e-7
