@@ -1139,14 +1139,20 @@ __global__ void prepare_tables_res_kernel(const void *weights, int wdtype, int r
 // partials[b][(li*nq + wire)*3 + {0: d/dphi (+ d/domega of layer li-1 when merged), 1: d/dtheta, 2: d/domega}]
 __global__ void finalize_grads_kernel(const float *partials, int n_partials, const void *weights, int wdtype,
                                       int remap, int nq, int n_layers, int merge_post, void *grad_weights) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (li*nq + wire)*3 + kind
+    // one warp per output: the lanes sum interleaved subsets of the per-CTA partials in a fixed order (deterministic),
+    // then a shuffle tree -- the serial loop over up to ~2 400 partial buffers cost 25 us per launch
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (li*nq + wire)*3 + kind
+    const int lane = threadIdx.x & 31;
     const int n = n_layers * nq * 3;
     if (i >= n) return;
     const int kind = i % 3, gate = i / 3, li = gate / nq;
     int src = i;
     if (kind == 2 && merge_post && li < n_layers - 1) src = (gate + nq) * 3;    // merged into the next layer's phi table
     double acc = 0.0;
-    for (int b = 0; b < n_partials; ++b) acc += (double)partials[(size_t)b * n + src];
+    for (int b = lane; b < n_partials; b += 32) acc += (double)partials[(size_t)b * n + src];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
     const double gval = acc * remap_grad(load_w(weights, wdtype, i), remap);
     if (wdtype == QIDDM_DTYPE_F64) reinterpret_cast<double *>(grad_weights)[i] = gval;
     else reinterpret_cast<float *>(grad_weights)[i] = (float)gval;
@@ -1155,14 +1161,18 @@ __global__ void finalize_grads_kernel(const float *partials, int n_partials, con
 // resident schedule: partials[b][(j*nq + wire)*2 + {0: d/dalpha_j, 1: d/dtheta_j}], j = 0..n_layers
 __global__ void finalize_grads_res_kernel(const float *partials, int n_partials, const void *weights, int wdtype,
                                           int remap, int nq, int n_layers, void *grad_weights) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (li*nq + wire)*3 + kind
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (li*nq + wire)*3 + kind; one warp per output
+    const int lane = threadIdx.x & 31;
     const int n = n_layers * nq * 3;
     if (i >= n) return;
     const int kind = i % 3, gate = i / 3;
     const int src = kind == 0 ? gate * 2 : (kind == 1 ? gate * 2 + 1 : (gate + nq) * 2);
     const size_t stride = (size_t)(n_layers + 1) * nq * 2;
     double acc = 0.0;
-    for (int b = 0; b < n_partials; ++b) acc += (double)partials[(size_t)b * stride + src];
+    for (int b = lane; b < n_partials; b += 32) acc += (double)partials[(size_t)b * stride + src];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
     const double gval = acc * remap_grad(load_w(weights, wdtype, i), remap);
     if (wdtype == QIDDM_DTYPE_F64) reinterpret_cast<double *>(grad_weights)[i] = gval;
     else reinterpret_cast<float *>(grad_weights)[i] = (float)gval;
@@ -1227,10 +1237,10 @@ cudaError_t launch_finalize_grads(const float *partials, int n_partials, const v
     const int n_layers = p.n_blocks * p.layers;
     const int n = n_layers * n_qubits * 3;
     if (wants_resident(n_qubits, rb_choose(n_qubits, true), p))
-        finalize_grads_res_kernel<<<(n + 127) / 128, 128, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
+        finalize_grads_res_kernel<<<(n + 7) / 8, 256, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
                                                                  n_layers, grad_weights);
     else
-        finalize_grads_kernel<<<(n + 127) / 128, 128, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
+        finalize_grads_kernel<<<(n + 7) / 8, 256, 0, s>>>(partials, n_partials, weights, wdtype, remap, n_qubits,
                                                              n_layers, p.merge_post, grad_weights);
     count_launch();
     return cudaGetLastError();

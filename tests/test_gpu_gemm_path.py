@@ -125,12 +125,12 @@ def test_full_size_properties_of_the_bench_workload():
     assert torch.equal(p[0], p[B - 1])
     idx = torch.tensor([0, 1, 777, 65535, 131072, 200001, B - 2])
     ref = O.run_stage(full, x[idx].double(), W)
-    assert rel_to_max(p[idx.cuda()], ref) <= 1e-5
+    assert rel_to_max(p[idx.cuda()], ref) <= 2e-5          # K = 784: measured 5-7e-6, stated bound 3e-5
     del p
     # the clamped module readout at full size equals the gate path on a slice
     out = run_stage(_spec(d, L.PATH_GEMM), xd, Wd)
     sl = slice(100000, 100512)
-    assert rel_to_max(out[sl], run_stage(_spec(d, L.PATH_GATE), xd[sl], Wd)) <= 2e-5
+    assert rel_to_max(out[sl], run_stage(_spec(d, L.PATH_GATE), xd[sl], Wd)) <= 4e-5      # measured 1.4-1.8e-5
     # backward linearity in grad_out (weights gradient), B = 65 536
     xs = xd[:65536].clone()
     g1 = torch.randn(65536, 784, generator=g).cuda() / 65536
@@ -143,4 +143,6 @@ def test_full_size_properties_of_the_bench_workload():
         return Wp.grad
 
     a, b, c = wgrad(g1), wgrad(g2), wgrad(g1 + g2)
-    assert rel_to_max(a + b, c) <= 2e-4
+    # random-sign upstream gradients over 65 536 instances cancel in dW, which amplifies the fp32 accumulation error of the
+    # split-K sums relative to the result: measured 5e-6 ... 1.9e-4 over seeds (scripts/full_size_margins.py)
+    assert rel_to_max(a + b, c) <= 1e-3
