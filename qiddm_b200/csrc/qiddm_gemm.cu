@@ -183,6 +183,7 @@ struct GemmParams {
     alignas(64) CUtensorMap b_map[2];   // weight side: hi, lo
     int n_seg;            // 1: (a0,b0);  3: (a0,b0), (a1,b0), (a0,b1)
     int a_mn;             // A is MN-major: its tensor map is over the row-major (K rows, M cols) array
+    int b_mn;             // pair kernel, with a_mn: B is MN-major too, its map is over the row-major (K rows, N cols) array
     int M, N, K;          // K per segment, elements
     int bn;               // BLOCK_N: multiple of 16, <= 256
     int stages;
@@ -615,7 +616,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
     constexpr uint32_t N_A = NSEG > 1 ? 2 : 1, N_B = NSEG > 1 ? 2 : 1;   // hi (and lo) tiles of each operand per stage
     constexpr uint32_t a_bytes = BM * BKT * 2;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)(p.bn / 2) * BKT * 2;         // this CTA's half of the B tile
+    // this CTA's half of the B tile: K-major rows of BKT elements, or (MN-major) whole 64-column boxes of 64 K rows
+    const bool bmn = AMN && p.b_mn != 0;
+    const uint32_t b_boxes = (uint32_t)(p.bn / 2 + 63) / 64;
+    const uint32_t b_bytes = bmn ? b_boxes * 8192u : (uint32_t)(p.bn / 2) * BKT * 2;
     const uint32_t stage_bytes = N_A * a_bytes + N_B * b_bytes;
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -705,8 +709,15 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                         }
                     }
 #pragma unroll
-                    for (uint32_t i = 0; i < N_B; ++i)
-                        tma_load_2d_pair(sa + N_A * a_bytes + i * b_bytes, &p.b_map[i], fb, kb * BKT, nb0);
+                    for (uint32_t i = 0; i < N_B; ++i) {
+                        const uint32_t dst = sa + N_A * a_bytes + i * b_bytes;
+                        if (bmn) {   // (64 N) x (64 K) boxes from the row-major (K, N) array; columns past N/2 are not read
+                            for (uint32_t j = 0; j < b_boxes; ++j)
+                                tma_load_2d_pair(dst + j * 8192u, &p.b_map[i], fb, nb0 + 64 * (int)j, kb * BKT);
+                        } else {
+                            tma_load_2d_pair(dst, &p.b_map[i], fb, kb * BKT, nb0);
+                        }
+                    }
                     // pull the A tile PFD k-blocks ahead (possibly in this pair's next tile) into L2
                     int pk = kb + PFD, pm = m0;
                     if (pk >= kb1) { pk = nkb0 + (pk - kb1); pm = nm0; }
@@ -729,8 +740,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             const bool issuer = elect_one();
             // instruction descriptor: D=f32, A=B=f16, N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24) |
-                                   (AMN ? (1u << 15) : 0u);
+                                   (AMN ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
             constexpr uint64_t a_step = AMN ? 128 : 2;
+            const uint64_t b_step = bmn ? 128 : 2;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (long long w = pair; w < total; w += n_pairs) {
@@ -747,7 +759,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     const uint64_t ad0 = AMN ? make_smem_desc_mn(sa) : (BKT == 64 ? make_smem_desc(sa) : make_smem_desc_k32(sa));
                     const uint64_t ad1 = AMN ? make_smem_desc_mn(sa + a_bytes)
                                              : (BKT == 64 ? make_smem_desc(sa + a_bytes) : make_smem_desc_k32(sa + a_bytes));
-                    const uint64_t bd0 = BKT == 64 ? make_smem_desc(sa + N_A * a_bytes) : make_smem_desc_k32(sa + N_A * a_bytes);
+                    const uint64_t bd0 = bmn ? make_smem_desc_mn(sa + N_A * a_bytes)
+                                             : (BKT == 64 ? make_smem_desc(sa + N_A * a_bytes) : make_smem_desc_k32(sa + N_A * a_bytes));
                     const uint64_t bstep = (uint64_t)(b_bytes >> 4);
                     if (issuer) {
 #pragma unroll
@@ -756,7 +769,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                             const uint64_t bdesc = seg == 2 ? bd0 + bstep : bd0;
 #pragma unroll
                             for (int k = 0; k < BKT / UMMA_K; ++k)
-                                tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc,
+                                tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc,
                                                 (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u);
                         }
                         tc_commit_pair(empty_bar(stage));
@@ -1021,7 +1034,7 @@ __global__ void __launch_bounds__(256) prep_xt_unfold_kernel(const void *img, in
             tl[cc][rr] = lo;
         }
         __syncthreads();
-        {   // XT: feature rows of 64 patches = 32 half2 per row
+        if (XTh != nullptr) {   // XT: feature rows of 64 patches = 32 half2 per row
             const int lane = t & 31, w = t >> 5;
             const long long r2 = r0 + 2 * lane;
 #pragma unroll
@@ -1328,6 +1341,23 @@ int pick_bn(int N) {
     return best;
 }
 
+// B operand MN-major (64-column boxes): the tile that minimises padded MMA work and the operand bytes staged per column
+int pick_bn_mn(int N) {
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("QIDDM_GEMM_DW_BN"); forced = e ? atoi(e) : 0; }
+    if (forced >= 16 && forced <= 256 && forced % 16 == 0) return forced;
+    int best = 16;
+    double best_cost = 1e30;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+        const int tiles = (N + bn - 1) / bn;
+        const double waste = (double)tiles * bn / N;
+        const double kb_per_col = (32.0 + 16.0 * ((bn / 2 + 63) / 64)) / bn;      // A (256 rows) + B boxes, hi and lo, per stage
+        const double cost = waste * (1.0 + 24.0 / bn) + 0.25 * (kb_per_col / 0.325 - 1.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
 struct ActOperand { const __half *h, *l; };          // hi, lo
 struct WgtOperand { const __half *h, *l; };          // hi, lo
 
@@ -1340,14 +1370,28 @@ bool use_pair_kernel() {
     return v == 1;
 }
 
+// The transposed operand splits X^T (Kp, Bp) are only materialised for the cta_group::1 kernel (or QIDDM_GEMM_XT=1); the
+// pair kernel reads X row-major as an MN-major B operand in the dW GEMM.
+bool use_xt() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("QIDDM_GEMM_XT");
+        v = (!use_pair_kernel() || (e && e[0] == '1')) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 // D[M,N] = A B^T over the precision segments.  a_mn: A is given as the row-major (K, M) array (MN-major operand).
+// b_mn (pair kernel, with a_mn): B is given as the row-major (K, N) array of b_rows x b_cols elements.
 int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long a_pitch, bool a_mn,
              const WgtOperand &Bm, long long b_rows, long long b_pitch, int M, int N, int K, int n_seg, int k_splits,
-             GemmParams &p, cudaStream_t s) {
+             GemmParams &p, cudaStream_t s, bool b_mn = false, long long b_cols = 0) {
     p.M = M; p.N = N; p.K = K;
     p.n_seg = n_seg;
     p.a_mn = a_mn ? 1 : 0;
-    p.bn = pick_bn(N);
+    p.b_mn = b_mn ? 1 : 0;
+    p.bn = b_mn ? pick_bn_mn(N) : pick_bn(N);
+    if (b_mn && !(a_mn && use_pair_kernel())) return QIDDM_EINVAL;
     p.k_splits = k_splits;
     const bool pair = use_pair_kernel();
     {
@@ -1365,7 +1409,8 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
     for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
         if ((rc = make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, a_mn ? 64 : BM, bkt)) != QIDDM_OK) return rc;
     for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
-        if ((rc = make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, pair ? p.bn / 2 : p.bn, bkt)) != QIDDM_OK) return rc;
+        if ((rc = b_mn ? make_map(&p.b_map[i], bs[i], b_rows, b_cols, b_pitch, 64, 64)
+                       : make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, pair ? p.bn / 2 : p.bn, bkt)) != QIDDM_OK) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1394,7 +1439,8 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
             p.tma_epi = ok ? 1 : 0;
         }
         const int epi_bytes = p.tma_epi ? 4 * 2 * EPI_STAGE_BYTES + 512 : 0;
-        const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + (p.bn / 2) * bkt * 2);
+        const int b_tile_bytes = b_mn ? ((p.bn / 2 + 63) / 64) * 8192 : (p.bn / 2) * bkt * 2;
+        const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + b_tile_bytes);
         int stages = (226 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes;
         if (stages > 8) stages = 8;
         if (stages < 2) stages = 2;
@@ -1518,7 +1564,7 @@ float *gemm_collapsed_ut(const GemmShape &g, void *collapsed) { return reinterpr
 
 size_t gemm_saved_bytes(const GemmShape &g, long long B) {
     const long long Bp = (B + 7) & ~7LL;
-    return 2 * al((size_t)B * g.Kp * 2) + 2 * al((size_t)g.Kp * Bp * 2) + al((size_t)B * 4) +
+    return 2 * al((size_t)B * g.Kp * 2) + (use_xt() ? 2 * al((size_t)g.Kp * Bp * 2) : 0) + al((size_t)B * 4) +
            al((size_t)B * g.N * 4);
 }
 
@@ -1556,8 +1602,9 @@ SavedView saved_view(const GemmShape &g, long long B, void *buf, bool full) {
     char *p = reinterpret_cast<char *>(buf);
     for (int i = 0; i < 2; ++i) { w.X[i] = reinterpret_cast<__half *>(p); p += al((size_t)B * g.Kp * 2); }
     for (int i = 0; i < 2; ++i) {
-        w.XT[i] = full ? reinterpret_cast<__half *>(p) : nullptr;
-        if (full) p += al((size_t)g.Kp * Bp * 2);
+        const bool xt = full && use_xt();
+        w.XT[i] = xt ? reinterpret_cast<__half *>(p) : nullptr;
+        if (xt) p += al((size_t)g.Kp * Bp * 2);
     }
     w.inv_n2 = reinterpret_cast<float *>(p); p += al((size_t)B * 4);
     w.Y = nullptr;
@@ -1584,7 +1631,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
             unfold_geom(gp));
         timing_end(s);
         count_launch();
-    } else if (keep) {
+    } else if (keep && use_xt()) {
         // training forward, dense rows: X, X^T and the norms in one pass over x
         timing_begin(TK_PREP_X, 0.0, s);
         prep_xt_kernel<<<(unsigned)((Bp + 63) / 64), 256, 0, s>>>(x, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value,
@@ -1700,8 +1747,9 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     {
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = dWT; p.ldo = g.Fx; p.out_scale = 1.f;
-        WgtOperand XTo{w.XT[0], w.XT[1]};
-        const int bn = pick_bn(g.Fx);
+        const bool xt = use_xt();
+        WgtOperand XTo{xt ? w.XT[0] : w.X[0], xt ? w.XT[1] : w.X[1]};
+        const int bn = xt ? pick_bn(g.Fx) : pick_bn_mn(g.Fx);
         const bool pair = use_pair_kernel();
         const int bm = pair ? 2 * BM : BM;
         const int tiles = ((g.N + bm - 1) / bm) * ((g.Fx + bn - 1) / bn);
@@ -1718,7 +1766,8 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
             if (cost < best) { best = cost; splits = sp; }
         }
         timing_set_gemm_kind(TK_GEMM_DW);
-        rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
+        if (xt) rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
+        else rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, B, g.Kp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s, true, g.Kp);
         if (rc != QIDDM_OK) return rc;
     }
     timing_begin(TK_ASSEMBLE, 0.0, s);

@@ -30,6 +30,12 @@ class DevicePCA:
     def _eigh_desc(a: torch.Tensor):
         if a.is_cuda and a.shape[-1] <= L.load_library().qiddm_sym_eigh_max_dim():
             return L.sym_eigh(a)
+        if a.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise L.QiddmError(
+                f"DevicePCA: a {a.shape[-1]} x {a.shape[-1]} eigenproblem exceeds the capturable Jacobi kernel "
+                f"(<= {L.load_library().qiddm_sym_eigh_max_dim()}); torch.linalg.eigh synchronises and cannot be captured in a "
+                "CUDA graph.  Set module.pca_group = tau (one PCA per image's tau-ladder, the reference's batch-1 semantics) "
+                "or run the step eagerly.")
         lam, vec = torch.linalg.eigh(a)                       # ascending
         return lam.flip(-1), vec.flip(-1)
 

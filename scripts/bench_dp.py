@@ -34,6 +34,8 @@ side = 64 if a.model == "unet64" else 28
 net = {"unet": lambda: qnn.UNetUndirected(3, 8, 3), "unet64": lambda: qnn.UNetUndirected(3, 8, 3),
        "qiddm_ll": lambda: qnn.QIDDM_LL_noise(784, 6, 14, 2), "qiddm_pl": lambda: qnn.QIDDM_PL_noise(784, 8, 6, 2),
        "qdense": lambda: qnn.QDenseUndirected_old_noise(60, 28)}[a.model]()
+if a.model == "qiddm_pl":
+    net.pca_group = 10          # one PCA per image's tau-ladder (reference batch-1 semantics; whole-batch PCA is not capturable)
 diff = models.Diffusion(net, noise.add_normal_noise_multiple, "data", (side, side), torch.nn.MSELoss()).to(dev, torch.float64)
 opt = torch.optim.Adam(diff.parameters(), lr=1e-3, capturable=a.graph)
 trainer = DataParallelTrainer(diff, opt, tau=10)
