@@ -301,8 +301,9 @@ def run_b200(args):
                     "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                     "frac": achieved / tc_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's three GEMM launches, from
-                    # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv)
-                    "traffic": 7.03e9 if (B == 524288 and args.precision == 3) else None,
+                    # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv; 8.3-11.2e9
+                    # across the captures of the round: the dW launch's L2 re-reads vary with the box, profiles/r1_gemm_pair_summary.md)
+                    "traffic": 11.2e9 if (B == 524288 and args.precision == 3) else None,
                     "traffic_unit": "bytes/launch (algorithmic operand + result bytes: 6.04e9)",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
                     "ms_per_launch": per_launch_ms, "launches": kd["launches"],

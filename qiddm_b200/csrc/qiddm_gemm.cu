@@ -305,9 +305,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
     } else {
         float *dst = p.out + (long long)row * p.ldo + col;
         if (p.k_splits > 1) {
+            if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {     // 16-byte vector reductions: a quarter of the L2 atomic transactions
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j] * p.out_scale),
+                                 "f"(v[4 * j + 1] * p.out_scale), "f"(v[4 * j + 2] * p.out_scale), "f"(v[4 * j + 3] * p.out_scale)
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (col + j < p.N) atomicAdd(dst + j, v[j] * p.out_scale);
+            }
         } else if (col + 16 <= p.N && ((p.ldo & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -762,6 +770,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     const uint64_t bd0 = bmn ? make_smem_desc_mn(sa + N_A * a_bytes)
                                              : (BKT == 64 ? make_smem_desc(sa + N_A * a_bytes) : make_smem_desc_k32(sa + N_A * a_bytes));
                     const uint64_t bstep = (uint64_t)(b_bytes >> 4);
+                    // the last k-block of the operands only issues the 16-wide steps that hold data (the rest is zero fill)
+                    const int ksteps = kb == KB - 1 ? (p.K - kb * BKT + UMMA_K - 1) / UMMA_K : BKT / UMMA_K;
                     if (issuer) {
 #pragma unroll
                         for (int seg = 0; seg < NSEG; ++seg) {
@@ -769,8 +779,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                             const uint64_t bdesc = seg == 2 ? bd0 + bstep : bd0;
 #pragma unroll
                             for (int k = 0; k < BKT / UMMA_K; ++k)
-                                tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc,
-                                                (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u);
+                                if (k < ksteps)
+                                    tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc,
+                                                    (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u);
                         }
                         tc_commit_pair(empty_bar(stage));
                         if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc));
@@ -893,6 +904,45 @@ __global__ void prep_x_kernel(const float *x, long long B, int F, int Kp, int n_
     if (sub == 0 && active) {
         ss += (float)n_pad * pad * pad;
         inv_n2[row] = ss > 0.f ? 1.0f / ss : 0.f;
+    }
+}
+
+// Dense rows with 16-byte aligned fp32 features (F % 4 == 0): the same outputs as prep_x_kernel, one warp per row, a lane
+// takes 8 consecutive features per step (two 16-byte loads, one 16-byte store per split) - a pure streaming pass.
+__global__ void __launch_bounds__(256) prep_x_dense_kernel(const float *x, long long B, int F, int Kp, int n_pad, float add_offset,
+                                                           float pad, __half *Xh, __half *Xl, float *inv_n2, int want_lo) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = warp0; row < B; row += nwarps) {
+        const float *src = x + row * F;
+        float ss = 0.f;
+        for (int c = 8 * lane; c < Kp; c += 256) {
+            float f[8];
+            if (c + 8 <= F) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + c)), b = __ldg(reinterpret_cast<const float4 *>(src + c) + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += add_offset;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = c + j < F ? __ldg(src + c + j) + add_offset : 0.f;
+            }
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ss += f[j] * f[j];
+                split_act((c + j == F && n_pad > 0) ? 1.f : f[j], hi[j], lo[j]);
+            }
+            *reinterpret_cast<uint4 *>(Xh + row * Kp + c) = *reinterpret_cast<const uint4 *>(hi);       // Kp is a multiple of 8
+            if (want_lo) *reinterpret_cast<uint4 *>(Xl + row * Kp + c) = *reinterpret_cast<const uint4 *>(lo);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) {
+            ss += (float)n_pad * pad * pad;
+            inv_n2[row] = ss > 0.f ? 1.0f / ss : 0.f;
+        }
     }
 }
 
@@ -1269,7 +1319,7 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
 // Assemble the READ_STATE cotangent of UT for the adjoint gate kernel:
 //   gUT[c][k_m].{re,im} = w_scale / gsc * ( c < F ? dWT[n][c] : pad * dWT[n][F] )   (n = 2m+ri), 0 elsewhere;
 // dWT[n][F] is the ones-column entry = sum_b G[b,n].
-__global__ void assemble_gut_kernel(const float *dWT, const unsigned int *gmax_bits, int A, int F, int Fx, int N,
+__global__ void assemble_gut_kernel(const float *dWT, const unsigned int *gmax_bits, int A, int F, int ldw, int N,
                                     int stride, float w_scale, float pad, float *gUT) {
     const float k = w_scale / g_scale_from_max(*gmax_bits);
     const long long total = (long long)A * A * 2;
@@ -1281,7 +1331,7 @@ __global__ void assemble_gut_kernel(const float *dWT, const unsigned int *gmax_b
         if (kk % stride == 0) {
             const int m = kk / stride;
             const int n = 2 * m + ri;
-            if (n < N) v = k * (c < F ? dWT[(long long)n * Fx + c] : pad * dWT[(long long)n * Fx + F]);
+            if (n < N) v = k * (c < F ? dWT[(long long)n * ldw + c] : pad * dWT[(long long)n * ldw + F]);
         }
         gUT[i] = v;
     }
@@ -1584,7 +1634,7 @@ size_t gemm_backward_ws_bytes(const GemmShape &g, long long B, bool unfold) {
     if (unfold) b += al((size_t)((B + 7) & ~7LL) * g.F * 4);   // dX (feature-major) before the col2im
     b += al((size_t)B * 4) + al(256);                 // S, gmax
     b += 2 * al((size_t)B * g.Np * 2);                // G splits (row-major)
-    b += al((size_t)g.N * g.Fx * 4);                  // dWT (+ ones column)
+    b += al((size_t)g.N * ((g.Fx + 3) & ~3) * 4);     // dWT (+ ones column; rows padded to 16 bytes)
     b += al((size_t)g.A * g.A * 8);                   // gUT
     return b;
 }
@@ -1643,9 +1693,15 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
         while (gw > 1 && gw / 2 >= g.Kp / 2) gw >>= 1;
         const long long row_warps = (B * gw + 31) / 32;
         timing_begin(TK_PREP_X, 0.0, s);
-        prep_x_kernel<<<(unsigned)((row_warps + warps - 1) / warps), warps * 32, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
-            x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
-            unfold_geom(gp), gw, gp.unfold ? gp.io64 : 0);
+        if (!gp.unfold && (g.F & 3) == 0 && g.Kp >= 128 && ((uintptr_t)x & 15) == 0) {
+            const long long blocks = (B + warps - 1) / warps;
+            prep_x_dense_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), warps * 32, 0, s>>>(
+                x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1);
+        } else {
+            prep_x_kernel<<<(unsigned)((row_warps + warps - 1) / warps), warps * 32, gp.unfold ? 2 * g.F * sizeof(int) : 0, s>>>(
+                x, B, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.inv_n2, keep || n_seg > 1,
+                unfold_geom(gp), gw, gp.unfold ? gp.io64 : 0);
+        }
         timing_end(s);
         count_launch();
     }
@@ -1686,7 +1742,8 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     unsigned int *gmax = reinterpret_cast<unsigned int *>(p8); p8 += al(256);
     __half *Gs[2];
     for (int i = 0; i < 2; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
-    float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * g.Fx * 4);
+    const int ldw = (g.Fx + 3) & ~3;                  // 16-byte rows: vector reductions in the split-K epilogue
+    float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * ldw * 4);
     float *gUT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.A * g.A * 8);
     *gut_out = gUT;
     float *dx_rows = reinterpret_cast<float *>(p8);   // QConv only (gemm_backward_ws_bytes(.., unfold = true))
@@ -1743,10 +1800,10 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         }
     }
     // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]: G consumed row-major as an MN-major operand, split-K over the batch
-    if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * g.Fx * 4, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * ldw * 4, s)) != cudaSuccess) return (int)e;
     {
         memset(&p, 0, sizeof(p));
-        p.epi = EPI_STORE; p.out = dWT; p.ldo = g.Fx; p.out_scale = 1.f;
+        p.epi = EPI_STORE; p.out = dWT; p.ldo = ldw; p.out_scale = 1.f;
         const bool xt = use_xt();
         WgtOperand XTo{xt ? w.XT[0] : w.X[0], xt ? w.XT[1] : w.X[1]};
         const int bn = xt ? pick_bn(g.Fx) : pick_bn_mn(g.Fx);
@@ -1765,13 +1822,18 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
             const double cost = (double)(waves * workers) / (double)items + 0.004 * sp + (items < workers ? 10.0 : 0.0);
             if (cost < best) { best = cost; splits = sp; }
         }
+        {
+            static int forced = -1;
+            if (forced < 0) { const char *ev = getenv("QIDDM_GEMM_DW_SPLITS"); forced = ev ? atoi(ev) : 0; }
+            if (forced > 0 && forced <= kt) splits = forced;
+        }
         timing_set_gemm_kind(TK_GEMM_DW);
         if (xt) rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, g.Fx, Bp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s);
         else rc = run_gemm(Go, B, g.Np, g.Np, true, XTo, B, g.Kp, g.N, g.Fx, (int)Bp, n_seg, splits, p, s, true, g.Kp);
         if (rc != QIDDM_OK) return rc;
     }
     timing_begin(TK_ASSEMBLE, 0.0, s);
-    assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, gmax, g.A, g.F, g.Fx, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
+    assemble_gut_kernel<<<1184, 256, 0, s>>>(dWT, gmax, g.A, g.F, ldw, g.N, g.stride, g.w_scale, gp.pad_value, gUT);
     timing_end(s);
     count_launch();
     e = cudaGetLastError();
