@@ -85,6 +85,11 @@ def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
     per = t_probe / 16
     per_step = max(target_seconds / max(steps + warmup, 1), 0.5)
     b = int(min(4096, max(16, per_step / per)))
+    for _ in range(4):                       # small batches under-use the cores: refine the estimate at the sample's own size
+        t_b = run(b)
+        if t_b >= 0.6 * per_step or b >= 4096:
+            break
+        b = int(min(4096, max(b + 1, b * per_step / t_b)))
     for _ in range(warmup):
         run(b)
     times = [run(b) for _ in range(max(steps, 1))]
