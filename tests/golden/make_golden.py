@@ -4,6 +4,8 @@
 * f1_qdense_label14.pt / f1_differn_label14.pt — weights trained by the REAL PennyLane stack, taken
   verbatim from the reference artefact results/emnist.zip (fixture F1), plus the oracle's
   sampler output / stage outputs for them.
+* f1_expval_label14.pt — the same for the <Z> families: QIDDM_PL_noise(784,8,6,2) (a4) and QNN(784,8,6) (a5) checkpoints of
+  label 14 with the oracle's chain / layer outputs on seeded inputs (`python make_golden.py f1_expval` writes only this one).
 * f2_state_dict_contract.json — key names / shapes / dtypes of every shipped checkpoint family (F2).
 * stage_vectors.pt — oracle outputs and gradients for seeded inputs of each circuit family.
 """
@@ -27,8 +29,31 @@ def load_ck(z, name):
     return torch.load(io.BytesIO(z.read(name)), weights_only=False, map_location="cpu")
 
 
+def f1_expval(z):
+    """F1 a4 / a5: checkpoints trained through lightning.qubit + expval(PauliZ): weights verbatim + oracle outputs."""
+    src_pl = "emnist14/noise_0/QIDDM_PL_noise=8_L=6_N=2_noise_14.pt"
+    sd = load_ck(z, src_pl)["model_state_dict"]
+    torch.manual_seed(2)
+    ang = torch.randn(4, 8, dtype=torch.float64)
+    chain = O.qiddm_expval_chain(ang, sd["net.weights1"].double())
+    pl = {"weights1": sd["net.weights1"], "linear_up.weight": sd["net.linear_up.weight"], "linear_up.bias": sd["net.linear_up.bias"],
+          "angles": ang, "chain_out": chain,
+          "image_out": chain @ sd["net.linear_up.weight"].double().T + sd["net.linear_up.bias"].double(), "source": "results/emnist.zip:" + src_pl}
+    src_qnn = "emnist14/noise_0/QNN_linear_features=8_qdepth=6_add_noise=0_noise_14.pt"
+    sd = load_ck(z, src_qnn)["model_state_dict"]
+    x = torch.rand(2, 1, 28, 28, dtype=torch.float64)
+    out = O.qnn_forward(x, sd["net.weights"].double(), sd["net.linear_down.weight"], sd["net.linear_down.bias"],
+                        sd["net.linear_up.weight"], sd["net.linear_up.bias"])
+    qnn = {**{k[4:]: v for k, v in sd.items()}, "x": x, "out": out, "source": "results/emnist.zip:" + src_qnn}
+    torch.save({"qiddm_pl": pl, "qnn": qnn}, OUT / "f1_expval_label14.pt")
+
+
 def main():
     z = zipfile.ZipFile(REF / "results/emnist.zip")
+    if sys.argv[1:] == ["f1_expval"]:
+        f1_expval(z)
+        return
+    f1_expval(z)
     # ---- F1 a1: QDenseUndirected_old_noise(60, 28), label 14 ("O")
     ck = load_ck(z, "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")
     W = ck["model_state_dict"]["net.weights"]
