@@ -6,6 +6,8 @@
   sampler output / stage outputs for them.
 * f1_expval_label14.pt — the same for the <Z> families: QIDDM_PL_noise(784,8,6,2) (a4) and QNN(784,8,6) (a5) checkpoints of
   label 14 with the oracle's chain / layer outputs on seeded inputs (`python make_golden.py f1_expval` writes only this one).
+* f1_unet_label14.pt — the classical UNetUndirected(3, 8, qdepth=0) checkpoint of label 14 (row a7: the UNet glue around the
+  convolutions) + 20 sampler iterations of the product module on the CPU (`python make_golden.py f1_unet`).
 * f2_state_dict_contract.json — key names / shapes / dtypes of every shipped checkpoint family (F2).
 * stage_vectors.pt — oracle outputs and gradients for seeded inputs of each circuit family.
 """
@@ -48,12 +50,30 @@ def f1_expval(z):
     torch.save({"qiddm_pl": pl, "qnn": qnn}, OUT / "f1_expval_label14.pt")
 
 
+def f1_unet(z):
+    """F1 a7: weights of the reference's classical UNet (torch.nn.Conv2d children) verbatim + the sampler's output."""
+    from qiddm_b200 import nn as qnn
+    src = "emnist14/noise_0/unet_undirected_d3_s8_d0_noise_14.pt"
+    sd = {k[4:]: v for k, v in load_ck(z, src)["model_state_dict"].items()}
+    net = qnn.UNetUndirected(3, 8, 0)
+    net.load_state_dict(sd)
+    net.eval()
+    torch.manual_seed(0)
+    x0 = torch.rand(2, 1, 28, 28, dtype=torch.float64) * 0.75 + 0.5
+    smp = O.sample(lambda v: net(v), x0, 20, goal="noise")
+    torch.save({"state_dict": sd, "first_x": x0, "sample": smp, "source": "results/emnist.zip:" + src}, OUT / "f1_unet_label14.pt")
+
+
 def main():
     z = zipfile.ZipFile(REF / "results/emnist.zip")
     if sys.argv[1:] == ["f1_expval"]:
         f1_expval(z)
         return
+    if sys.argv[1:] == ["f1_unet"]:
+        f1_unet(z)
+        return
     f1_expval(z)
+    f1_unet(z)
     # ---- F1 a1: QDenseUndirected_old_noise(60, 28), label 14 ("O")
     ck = load_ck(z, "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")
     W = ck["model_state_dict"]["net.weights"]

@@ -119,6 +119,41 @@ def test_diffusion_wrapper_with_a_classical_net_on_cpu():
     assert last.shape == (3, 1, 8, 8) and last.min() >= 0 and last.max() <= 1
 
 
+def test_f1_reference_unet_checkpoint_draws_its_letter_only_with_the_reference_wiring():
+    """Row a7 pinned by fixture F1: the reference's trained classical UNet (results/emnist.zip, label 14, weights verbatim
+    in tests/golden/f1_unet_label14.pt) loaded into the product `UNetUndirected(3, 8, qdepth=0)` draws its letter through
+    `Diffusion.sample` (centre brighter than border by > 0.35); with the skip concatenation swapped ([down, up] instead of
+    [up, down], nn/unet.py:73) the letter is gone."""
+    from conftest import GOLDEN
+    from qiddm_b200 import models, noise, nn
+    import qiddm_b200.nn.unet as U
+    gold = torch.load(GOLDEN / "f1_unet_label14.pt", weights_only=True)
+    net = nn.UNetUndirected(3, 8, 0)
+    net.load_state_dict(gold["state_dict"])
+    diff = models.Diffusion(net, noise.add_normal_noise_multiple, "noise", (28, 28), torch.nn.MSELoss()).double()
+    diff.eval()
+
+    def contrast(img):
+        return (img[6:22, 6:22].mean() - (img.sum() - img[6:22, 6:22].sum()) / (784 - 256)).item()
+
+    out = diff.sample(20, first_x=gold["first_x"], only_last=True)
+    assert torch.allclose(out, gold["sample"], atol=1e-8)
+    assert min(contrast(out[i, 0]) for i in range(out.shape[0])) > 0.35
+
+    def swapped(self, from_down, from_up):
+        from_up = self.up_conv(from_up)
+        from_down, from_up = U.autopad(from_down.double(), from_up.double())
+        return self.net(torch.cat([from_down, from_up], dim=1).double())
+
+    orig = U.UpBlock.forward
+    U.UpBlock.forward = swapped
+    try:
+        bad = diff.sample(100, first_x=gold["first_x"], only_last=True)
+    finally:
+        U.UpBlock.forward = orig
+    assert max(abs(contrast(bad[i, 0])) for i in range(bad.shape[0])) < 0.2
+
+
 def test_unet_glue_helpers():
     from qiddm_b200.nn import autocrop, autopad, get_label_embedding
     big, small = torch.zeros(1, 1, 7, 7), torch.ones(1, 1, 4, 5)
