@@ -16,8 +16,8 @@
 // subnormal rounding is an absolute 2^-25 on O(1) values).
 //
 // Backward (same GEMM kernel): the forward keeps Y; G = dL/dY is formed in one streaming pass; then
-//   dX = G W^T (normalisation term fused in the epilogue) and dW^T = G^T X, where G is consumed row-major
-// as an MN-major UMMA operand (no transposed copy; split-K over the batch, fp32 atomics); dW is pushed
+//   dX = G W^T (normalisation term fused in the epilogue) and dW^T = G^T X, where G and X are both consumed
+// row-major as MN-major UMMA operands (no transposed copies; split-K over the batch, 16-byte fp32 reductions); dW is pushed
 // back through the circuit with the adjoint gate kernel run on the 2^n basis columns (READ_STATE cotangent).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -1664,8 +1664,8 @@ SavedView saved_view(const GemmShape &g, long long B, void *buf, bool full) {
 }
 }  // namespace
 
-// Forward.  `out` may be null (backward re-materialisation).  `saved` (gemm_saved_bytes) non-null: the X / X^T
-// splits, 1/|f|^2 and Y are kept there for the backward pass; null: they live in `ws` and only `out` is produced.
+// Forward.  `out` may be null (backward re-materialisation).  `saved` (gemm_saved_bytes) non-null: the X (with use_xt(): and
+// X^T) splits, 1/|f|^2 and Y are kept there for the backward pass; null: they live in `ws` and only `out` is produced.
 int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x, float *out,
                  void *saved, void *ws, long long B, int n_seg, cudaStream_t s) {
     CollapsedView v = collapsed_view(g, const_cast<void *>(collapsed));
@@ -1674,7 +1674,7 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
     const long long Bp = (B + 7) & ~7LL;
     const int warps = 8;
     if (keep && gp.unfold) {
-        // training forward, QConv: X, X^T and the norms straight from the NCHW image
+        // training forward, QConv: X (X^T only when use_xt()) and the norms straight from the NCHW image
         timing_begin(TK_PREP_X, 0.0, s);
         prep_xt_unfold_kernel<<<(unsigned)((Bp + 63) / 64), 256, 2 * g.F * sizeof(int), s>>>(
             x, gp.io64, B, g.F, g.Kp, Bp, g.A - g.F, gp.add_offset, gp.pad_value, w.X[0], w.X[1], w.XT[0], w.XT[1], w.inv_n2,
