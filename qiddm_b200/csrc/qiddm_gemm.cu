@@ -1736,6 +1736,14 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         int rc0 = gemm_forward(g, gp, collapsed, x, nullptr, saved_buf, nullptr, B, n_seg, s);
         if (rc0 != QIDDM_OK) return rc0;
     }
+    {
+        // EXPERIMENTAL, off by default (QIDDM_GEMM_BWD_X1=1): single-pass gradient GEMMs behind the fp32-grade forward.  CPU
+        // emulation (scripts/emulate_split_accuracy.py): weight-gradient error 3.3e-4 rel-to-max instead of 7e-8, dX + dW at a
+        // third of the MMA work.  Not yet parity-tested on the GPU.
+        static int bwd_x1 = -1;
+        if (bwd_x1 < 0) { const char *ev = getenv("QIDDM_GEMM_BWD_X1"); bwd_x1 = ev ? atoi(ev) : 0; }
+        if (bwd_x1) n_seg = 1;
+    }
     p8 += gemm_saved_bytes(g, B);
     SavedView w = saved_view(g, B, saved_buf, true);
     float *S = reinterpret_cast<float *>(p8); p8 += al((size_t)B * 4);
