@@ -176,6 +176,20 @@ def test_f1_expval_checkpoints_pin_the_sign_of_pauli_z():
     assert abs(_letter_contrast(O.sample(pl_net(-1.0), x0, 20, goal="noise")[0, 0])) < 0.1
 
 
+@pytest.mark.skipif(not REF_ZIP.exists(), reason="reference artefacts not mounted (GPU box)")
+def test_f4_reference_checkpoints_show_the_cut_circuit_gradient():
+    """Fixture F4: the shipped QIDDM_PL_noise checkpoints of different labels carry bit-identical circuit
+    weights (the reference detaches the QNode output, so `weights1` never trains) while their `linear_up` differs - the
+    behaviour `detach_quantum=True` reproduces in the product modules."""
+    z = zipfile.ZipFile(REF_ZIP)
+    sds = [torch.load(io.BytesIO(z.read(n)), weights_only=False, map_location="cpu")["model_state_dict"]
+           for n in sorted(z.namelist()) if "QIDDM_PL_noise=8_L=6_N=2" in n and n.endswith(".pt")]
+    assert len(sds) >= 5
+    same = [sd for sd in sds if torch.equal(sd["net.weights1"], sds[0]["net.weights1"])]
+    assert len(same) >= 5
+    assert not torch.equal(same[0]["net.linear_up.weight"], same[1]["net.linear_up.weight"])
+
+
 def test_noise_ladder_and_training_targets():
     """src/noise.py:105-126 + src/models.py:46-63 layout: '(batch tau) pixels', w_0 = 0, w_last = 1."""
     x = torch.rand(3, 16, dtype=torch.float64)
