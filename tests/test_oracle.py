@@ -185,7 +185,7 @@ def test_f4_reference_checkpoints_show_the_cut_circuit_gradient():
     sds = [torch.load(io.BytesIO(z.read(n)), weights_only=False, map_location="cpu")["model_state_dict"]
            for n in sorted(z.namelist()) if "QIDDM_PL_noise=8_L=6_N=2" in n and n.endswith(".pt")]
     assert len(sds) >= 5
-    same = [sd for sd in sds if torch.equal(sd["net.weights1"], sds[0]["net.weights1"])]
+    same = max(([sd for sd in sds if torch.equal(sd["net.weights1"], ref["net.weights1"])] for ref in sds), key=len)
     assert len(same) >= 5
     assert not torch.equal(same[0]["net.linear_up.weight"], same[1]["net.linear_up.weight"])
 
