@@ -281,6 +281,9 @@ def run_b200(args):
     e2e_val = imgs * TAU * world / (ms_e / ke * 1e-3)
     # clocks sampled over both timed regions (device-resident steps and the end-to-end steps)
     clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
+    if clocks is not None and "sw_power_cap" in (clocks.get("reasons") or []):
+        # nvidia-smi's polled clocks.sm does not resolve the cap: ncu reports 1.17-1.43 GHz inside the GEMM launches
+        clocks["note"] = "power cap active: ncu shows 1.17-1.43 GHz SM clock inside the GEMM launches (profiles/r1_gemm_pair_summary.md)"
 
     if rank != 0:
         if world > 1:
