@@ -3,7 +3,8 @@
 in the two modes SURVEY.md §8(d) names: (a) the whole (batch tau) ladder as ONE batched circuit call with autograd through
 the circuit, and (b) the reference's own shape of the computation — a Python loop of B = 1 circuit calls per sample and
 chained stage (nn/qdense.py:1631-1635: `for i in range(b)` x N QNode calls), forward only through the circuit (the
-reference detaches it), gradients for the classical layers only.  Needs no GPU; prints one JSON line per model.
+reference detaches it), gradients for the classical layers only; and (c) the same loop on the C restatement (oracle/statevec_oracle.c: one state vector,
+gates applied in place one after the other, like lightning.qubit, the reference's device for these classes).  Needs no GPU; prints one JSON line per model.
   python scripts/cpu_baseline_config1.py [--repeat 3]"""
 import argparse
 import json
@@ -15,6 +16,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 
+from oracle import c_oracle as C
 from oracle import qiddm_oracle as O
 
 ap = argparse.ArgumentParser()
@@ -70,10 +72,25 @@ for name, n, shape_w in (("QIDDM_LL_noise(784,6,14,2)", 6, (2, 14, 2, 6, 3)), ("
             O.diffusion_loss(f, data, eps, 10, (28, 28), "data").backward()
         return run
 
-    tb, tl = best(step(batched), a.repeat), best(step(looped), a.repeat)
+    def looped_c(v):                        # the same loop on the gate-by-gate C restatement (lightning.qubit-like), 1 thread per call
+        ang = (v.reshape(v.shape[0], -1) @ p["wd"].T + p["bd"]).detach()
+        rows = []
+        for i in range(ang.shape[0]):
+            z = ang[i:i + 1]
+            if ll:
+                for k in range(shape_w[0]):
+                    z = C.run_stage(O.desc_reupload(n, shape_w[1], shape_w[2]), z, p["w"].detach()[k], threads=1)
+            else:
+                z = C.run_stage(O.desc_reupload(n, 1, shape_w[0]), z, p["w"].detach()[None], threads=1)
+            rows.append(z)
+        return (torch.cat(rows) @ p["wu"].T + p["bu"]).reshape(-1, 1, 28, 28)
+
+    tb, tl, tc = best(step(batched), a.repeat), best(step(looped), a.repeat), best(step(looped_c), a.repeat)
     stages = 2 if ll else 1
     print(json.dumps({"what": "config1_cpu_baseline", "model": name, "images_per_step": 1, "tau": 10, "cores": os.cpu_count(),
                       "dtype": "complex128", "batched_autograd_ms_per_step": round(tb * 1e3, 1),
                       "per_sample_loop_forward_only_ms_per_step": round(tl * 1e3, 1),
+                      "per_sample_loop_c_gate_by_gate_ms_per_step": round(tc * 1e3, 2),
                       "circuit_evals_per_s_batched": round(10 * stages / tb, 1),
+                      "circuit_evals_per_s_loop_c": round(10 * stages / tc, 1),
                       "circuit_evals_per_s_loop": round(10 * stages / tl, 1), "host": "build container (no GPU)"}))

@@ -1,0 +1,57 @@
+"""The C restatement (oracle/statevec_oracle.c, gate by gate in place like lightning.qubit) against the torch
+restatement (oracle/qiddm_oracle.py, batched tensor ops like default.qubit.torch) and the committed golden vectors:
+two independent implementations of the conventions of SURVEY.md §8c must agree to 1e-12.  CPU only."""
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import c_oracle as C
+from oracle import qiddm_oracle as O
+
+
+def test_c_oracle_reproduces_every_golden_stage_vector():
+    vec = torch.load(GOLDEN / "stage_vectors.pt", weights_only=False)
+    assert len(vec) >= 10
+    for name, v in vec.items():
+        d = O.StageDesc(**v["desc"])
+        out = C.run_stage(d, v["x"], v["weights"])
+        assert torch.allclose(out, v["out"], atol=1e-12), name
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7])
+@pytest.mark.parametrize("imp", [O.IMP_CNOT, O.IMP_CZ])
+def test_c_oracle_full_state_matches_torch_oracle(n, imp):
+    """Full state (not only probabilities): ring order, CNOT direction, wire order and the Rot decomposition."""
+    g = torch.Generator().manual_seed(10 * n + imp)
+    d = O.StageDesc(n_qubits=n, n_blocks=3, layers_per_block=max(2, n), enc=O.ENC_RZ, enc_scale=0.7, imprimitive=imp,
+                    remap=O.REMAP_PI_TANH, readout=O.READ_STATE)
+    W = torch.randn(3, max(2, n), n, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(4, n, generator=g, dtype=torch.float64)
+    assert torch.allclose(C.run_stage(d, x, W), O.run_stage(d, x, W), atol=1e-12)
+    d.enc = O.ENC_RY
+    assert torch.allclose(C.run_stage(d, x, W), O.run_stage(d, x, W), atol=1e-12)
+
+
+def test_c_oracle_unitary_columns_and_reference_checkpoint():
+    """Basis-state columns (the collapse of nn/qconv.py:92-126) and the F1 checkpoint forward."""
+    d = O.desc_qconv(2, 4, (3, 3), 3)
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(1, 3, d.n_qubits, 3, generator=g, dtype=torch.float64)
+    db = O.StageDesc(**{**d.__dict__, "init": O.INIT_BASIS, "readout": O.READ_STATE})
+    idx = torch.arange(d.dim)
+    assert torch.allclose(C.run_stage(db, None, W, basis_index=idx), O.run_stage(db, None, W, basis_index=idx), atol=1e-12)
+    gold = torch.load(GOLDEN / "f1_qdense_label14.pt", weights_only=True)
+    dq = O.desc_qdense(60, 784, O.REMAP_TANH)
+    out = C.run_stage(dq, gold["first_x"].reshape(1, 784), gold["weights"][None])
+    assert torch.allclose(out.reshape(gold["one_forward"].shape), gold["one_forward"], atol=1e-12)
+    pl = torch.load(GOLDEN / "f1_expval_label14.pt", weights_only=True)["qiddm_pl"]
+    a = pl["angles"]
+    for k in range(2):
+        a = C.run_stage(O.desc_reupload(8, 6, 2), a, pl["weights1"][k])
+    assert torch.allclose(a, pl["chain_out"], atol=1e-12)
+
+
+def test_c_oracle_rejects_bad_descriptors():
+    d = O.StageDesc(n_qubits=3, init=O.INIT_AMPLITUDE, n_features=9, readout=O.READ_PROBS, read_count=4)
+    with pytest.raises(ValueError):
+        C.run_stage(d, torch.rand(2, 9, dtype=torch.float64), torch.zeros(1, 1, 3, 3, dtype=torch.float64))
