@@ -94,9 +94,21 @@ def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
         run(b)
     times = [run(b) for _ in range(max(steps, 1))]
     t = sum(times) / len(times)
-    return {"value": b / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{b} instances/step x {len(times)} step(s) of the same circuit, complex128 torch oracle "
-                      f"(per-gate ops on a (B,2^n) tensor + autograd, mirrors default.qubit.torch), {t:.2f} s/step"}, t
+    cb = {"value": b / t, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"{b} instances/step x {len(times)} step(s) of the same circuit, complex128 torch oracle "
+                    f"(per-gate ops on a (B,2^n) tensor + autograd, mirrors default.qubit.torch), {t:.2f} s/step"}
+    try:    # for scale: the forward alone on the gate-by-gate C restatement (lightning.qubit-like), OpenMP over the instances
+        from oracle import c_oracle as C
+        d = O.desc_qdense(QDEPTH, PIXELS, O.REMAP_TANH)
+        xc = torch.rand(32 * cores, PIXELS, generator=g, dtype=torch.float64)
+        C.run_stage(d, xc[:cores], W.detach()[None])
+        t0 = time.perf_counter()
+        C.run_stage(d, xc, W.detach()[None])
+        cb["c_forward_only"] = {"value": xc.shape[0] / (time.perf_counter() - t0), "unit": "circuit-evals/s (forward only)",
+                                "cores": cores, "sample": f"{xc.shape[0]} instances, oracle/statevec_oracle.c"}
+    except Exception as e:
+        cb["c_forward_only"] = {"unavailable": str(e)[:120]}
+    return cb, t
 
 
 def run_reference(args):
