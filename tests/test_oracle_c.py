@@ -55,3 +55,36 @@ def test_c_oracle_rejects_bad_descriptors():
     d = O.StageDesc(n_qubits=3, init=O.INIT_AMPLITUDE, n_features=9, readout=O.READ_PROBS, read_count=4)
     with pytest.raises(ValueError):
         C.run_stage(d, torch.rand(2, 9, dtype=torch.float64), torch.zeros(1, 1, 3, 3, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("family", ["amplitude_probs", "reupload_expval", "ry_probs_chain"])
+def test_autograd_gradients_of_the_torch_oracle_match_central_differences_of_the_c_forward(family):
+    """Gradients without autograd: d/d(weights, inputs) of a random linear functional of the stage output, by central
+    differences on the C forward (h = 1e-5), against the torch oracle's autograd (the golden gradients' source)."""
+    g = torch.Generator().manual_seed({"amplitude_probs": 1, "reupload_expval": 2, "ry_probs_chain": 3}[family])
+    if family == "amplitude_probs":
+        d = O.StageDesc(n_qubits=4, layers_per_block=3, init=O.INIT_AMPLITUDE, n_features=11, pad_value=0.3, add_offset=0.1,
+                        imprimitive=O.IMP_CNOT, remap=O.REMAP_TANH, readout=O.READ_PROBS, read_count=6, read_stride=2,
+                        post_scale=8.0)
+        x = torch.rand(2, 11, generator=g, dtype=torch.float64)
+    elif family == "reupload_expval":
+        d = O.desc_reupload(3, 3, 2)
+        x = torch.randn(2, 3, generator=g, dtype=torch.float64)
+    else:
+        d = O.desc_reupload(4, 2, 2, enc=O.ENC_RY, readout=O.READ_PROBS, read_count=4)
+        x = torch.randn(2, 4, generator=g, dtype=torch.float64)
+    W = torch.randn(d.n_blocks, d.layers_per_block, d.n_qubits, 3, generator=g, dtype=torch.float64) * 0.5
+    c = torch.randn(2, d.n_out, generator=g, dtype=torch.float64)
+    Wr, xr = W.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (O.run_stage(d, xr, Wr) * c).sum().backward()
+    f = lambda xv, wv: (C.run_stage(d, xv, wv) * c).sum().item()
+    h = 1e-5
+    for t, grad, is_w in ((W, Wr.grad, True), (x, xr.grad, False)):
+        flat = t.reshape(-1)
+        for i in range(0, flat.numel(), max(1, flat.numel() // 12)):     # a dozen coordinates of each
+            tp, tm = flat.clone(), flat.clone()
+            tp[i] += h
+            tm[i] -= h
+            fd = ((f(x, tp.reshape(t.shape)) - f(x, tm.reshape(t.shape))) if is_w
+                  else (f(tp.reshape(t.shape), W) - f(tm.reshape(t.shape), W))) / (2 * h)
+            assert abs(fd - grad.reshape(-1)[i].item()) < 1e-8 * max(1.0, abs(fd)) + 1e-9, (family, is_w, i)
