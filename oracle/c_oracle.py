@@ -49,7 +49,34 @@ def _load():
         _lib.qc_forward.restype = ctypes.c_int
         _lib.qc_forward.argtypes = [ctypes.POINTER(_Desc), ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_long]
+        _lib.qc_backward.restype = ctypes.c_int
+        _lib.qc_backward.argtypes = [ctypes.POINTER(_Desc), ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
     return _lib
+
+
+def _c_desc(desc: O.StageDesc) -> _Desc:
+    return _Desc(desc.n_qubits, desc.n_blocks, desc.layers_per_block, desc.init, desc.n_features, desc.pad_value,
+                 desc.add_offset, desc.enc, desc.enc_scale, desc.imprimitive, desc.remap, desc.readout, desc.read_count,
+                 desc.read_stride, desc.post_scale, int(bool(desc.clamp)), desc.clamp_lo, desc.clamp_hi)
+
+
+def stage_grads(desc: O.StageDesc, x: Optional[torch.Tensor], weights: torch.Tensor, grad_out: torch.Tensor,
+                batch: Optional[int] = None):
+    """Adjoint-method gradients of sum(out * grad_out): (grad_weights like `weights`, grad_x like `x` or None)."""
+    lib = _load()
+    d = _c_desc(desc)
+    w = weights.detach().to(torch.float64).reshape(desc.n_blocks, desc.layers_per_block, desc.n_qubits, 3).contiguous()
+    xs = x.detach().to(torch.float64).contiguous() if x is not None else None
+    go = grad_out.detach().to(torch.float64).contiguous()
+    B = xs.shape[0] if xs is not None else int(batch)
+    gw = torch.empty_like(w)
+    gx = torch.zeros_like(xs) if xs is not None else None
+    rc = lib.qc_backward(ctypes.byref(d), xs.data_ptr() if xs is not None else None, xs.shape[1] if xs is not None else 0,
+                         None, w.data_ptr(), go.data_ptr(), gx.data_ptr() if gx is not None else None, gw.data_ptr(), B)
+    if rc != 0:
+        raise ValueError(f"qc_backward: invalid descriptor (rc={rc})")
+    return gw.reshape(weights.shape), gx
 
 
 def run_stage(desc: O.StageDesc, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int] = None,

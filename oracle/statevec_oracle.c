@@ -4,8 +4,10 @@
  * the product (qiddm_b200/) never does.  Where oracle/qiddm_oracle.py mirrors PennyLane's `default.qubit.torch` (batched tensor
  * ops, precomputed ring permutations, autograd), this file mirrors `lightning.qubit`, the device the reference's QIDDM_LL / PL /
  * QNN classes run on (nn/qdense.py:1372-1373, :1568-1569): one complex128 state vector per circuit instance, every gate
- * applied in place, one after the other, in the order the QNode tape lists them — forward only, as the reference never
- * differentiates through these circuits.  The two restatements share no code, so their agreement (tests/
+ * applied in place, one after the other, in the order the QNode tape lists them.  qc_forward is what the reference runs (it
+ * never differentiates through these circuits); qc_backward adds the adjoint method on the same gate list (what
+ * lightning.qubit's diff_method="adjoint" does, and what the CUDA gate kernel does on the device), as a check of the torch
+ * oracle's autograd gradients that shares nothing with autograd.  The two restatements share no code, so their agreement (tests/
  * test_oracle_c.py, 1e-12) checks the ring composition order, the CNOT direction and the wire order a second time.
  *
  * Conventions (PennyLane 0.29 documentation — PennyLane itself is not installable here):
@@ -164,4 +166,118 @@ int qc_forward(const qc_desc *d, const double *x, long x_stride, const long *bas
         free(s);
     }
     return rc;
+}
+
+/* ---- adjoint-method backward (gradient of L = sum(out * grad_out) w.r.t. the raw weights and the inputs) ----------------
+ * With psi the final state and lambda = dL/d(conj psi), walking the gate list in reverse: for a rotation R_P(a) = exp(-i a P / 2)
+ * (P = Z or Y) applied at some point, dL/da = Im <lambda_post | P | psi_post>; then both vectors are taken back through R_P(a)^+.
+ * CNOT / CZ are their own inverses.  Amplitude embedding: psi0 = v / |v| is real, dL/dpsi0 = 2 Re(lambda0), projected through
+ * the normalisation. */
+static double rot_grad_z(const cplx *lam, const cplx *psi, int n, int wire) {
+    const long A = 1L << n;
+    double acc = 0;
+    for (long k = 0; k < A; ++k) {
+        const double v = cimag(conj(lam[k]) * psi[k]);
+        acc += ((k >> (n - 1 - wire)) & 1) ? -v : v;
+    }
+    return acc;
+}
+
+static double rot_grad_y(const cplx *lam, const cplx *psi, int n, int wire) {       /* Y|0> = i|1>, Y|1> = -i|0> */
+    const long A = 1L << n, st = 1L << (n - 1 - wire);
+    double acc = 0;
+    for (long k = 0; k < A; ++k)
+        if (!(k & st)) acc += cimag(conj(lam[k]) * (-I * psi[k | st]) + conj(lam[k | st]) * (I * psi[k]));
+    return acc;
+}
+
+static double remap_dw(double w, int remap) {
+    if (remap == 1) { const double t = tanh(w); return 1 - t * t; }
+    if (remap == 2) { const double t = tanh(w); return M_PI * (1 - t * t); }
+    return 1;
+}
+
+/* grad_x: (B, x_stride) or NULL; grad_w: (n_blocks, layers_per_block, n, 3), ACCUMULATED over the rows (zeroed here). */
+int qc_backward(const qc_desc *d, const double *x, long x_stride, const long *basis_index, const double *weights,
+                const double *grad_out, double *grad_x, double *grad_w, long B) {
+    const int n = d->n_qubits;
+    if (d->readout == 2) return -1;                  /* state read-out: not needed by the tests */
+    const long A = 1L << n;
+    const long n_out = d->readout == 1 ? n : d->read_count;
+    const long n_w = (long)d->n_blocks * d->layers_per_block * n * 3;
+    double *fwd = (double *)malloc((size_t)(B * n_out) * sizeof(double));
+    qc_desc ds = *d;
+    ds.readout = 2;                                   /* final state of every row */
+    double *st_all = (double *)malloc((size_t)(B * 2 * A) * sizeof(double));
+    if (!fwd || !st_all) { free(fwd); free(st_all); return -1; }
+    int rc = qc_forward(&ds, x, x_stride, basis_index, weights, st_all, B);
+    if (rc == 0) rc = qc_forward(d, x, x_stride, basis_index, weights, fwd, B);
+    if (rc != 0) { free(fwd); free(st_all); return rc; }
+    memset(grad_w, 0, (size_t)n_w * sizeof(double));
+    if (grad_x) memset(grad_x, 0, (size_t)(B * x_stride) * sizeof(double));
+    for (long b = 0; b < B; ++b) {                    /* serial over rows: grad_w accumulates deterministically */
+        cplx *psi = (cplx *)malloc((size_t)A * sizeof(cplx)), *lam = (cplx *)calloc((size_t)A, sizeof(cplx));
+        for (long k = 0; k < A; ++k) psi[k] = st_all[(b * A + k) * 2] + I * st_all[(b * A + k) * 2 + 1];
+        for (long m = 0; m < n_out; ++m) {            /* seed: out = clamp(post_scale * q), q = |psi_k|^2 or <Z_j> */
+            const double raw = fwd[b * n_out + m];
+            double g = grad_out[b * n_out + m] * d->post_scale;
+            if (d->clamp && (raw <= d->clamp_lo || raw >= d->clamp_hi)) {
+                /* torch.clamp passes the gradient only strictly inside (and at exact equality with a bound it does too:
+                 * recompute the unclamped value to decide) */
+                double q = 0;
+                if (d->readout == 0) { const cplx v = psi[m * d->read_stride]; q = creal(v) * creal(v) + cimag(v) * cimag(v); }
+                else for (long k = 0; k < A; ++k) { const double p = creal(psi[k]) * creal(psi[k]) + cimag(psi[k]) * cimag(psi[k]); q += ((k >> (n - 1 - m)) & 1) ? -p : p; }
+                const double u = q * d->post_scale;
+                if (u < d->clamp_lo || u > d->clamp_hi) g = 0;
+            }
+            if (d->readout == 0) lam[m * d->read_stride] += g * psi[m * d->read_stride];
+            else for (long k = 0; k < A; ++k) lam[k] += (((k >> (n - 1 - m)) & 1) ? -g : g) * psi[k];
+        }
+        for (int blk = d->n_blocks - 1; blk >= 0; --blk) {
+            for (int l = d->layers_per_block - 1; l >= 0; --l) {
+                const long wo = ((long)(blk * d->layers_per_block + l) * n) * 3;
+                if (n > 1) {
+                    const int r = (l % (n - 1)) + 1;
+                    for (int i = n - 1; i >= 0; --i) {
+                        if (d->imprimitive == 0) { apply_cnot(psi, n, i, (i + r) % n); apply_cnot(lam, n, i, (i + r) % n); }
+                        else { apply_cz(psi, n, i, (i + r) % n); apply_cz(lam, n, i, (i + r) % n); }
+                    }
+                }
+                for (int i = n - 1; i >= 0; --i) {
+                    const double *w = weights + wo + 3 * i;
+                    const double ang[3] = {remap_w(w[0], d->remap), remap_w(w[1], d->remap), remap_w(w[2], d->remap)};
+                    /* Rot = RZ(omega) RY(theta) RZ(phi): undo omega, theta, phi in this order */
+                    grad_w[wo + 3 * i + 2] += rot_grad_z(lam, psi, n, i) * remap_dw(w[2], d->remap);
+                    apply_rz(psi, n, i, -ang[2]); apply_rz(lam, n, i, -ang[2]);
+                    grad_w[wo + 3 * i + 1] += rot_grad_y(lam, psi, n, i) * remap_dw(w[1], d->remap);
+                    apply_ry(psi, n, i, -ang[1]); apply_ry(lam, n, i, -ang[1]);
+                    grad_w[wo + 3 * i + 0] += rot_grad_z(lam, psi, n, i) * remap_dw(w[0], d->remap);
+                    apply_rz(psi, n, i, -ang[0]); apply_rz(lam, n, i, -ang[0]);
+                }
+            }
+            if (d->enc != 0)
+                for (int j = n - 1; j >= 0; --j) {
+                    const double a = x[b * x_stride + j] * d->enc_scale;
+                    const double gr = d->enc == 1 ? rot_grad_z(lam, psi, n, j) : rot_grad_y(lam, psi, n, j);
+                    if (grad_x) grad_x[b * x_stride + j] += gr * d->enc_scale;
+                    if (d->enc == 1) { apply_rz(psi, n, j, -a); apply_rz(lam, n, j, -a); }
+                    else { apply_ry(psi, n, j, -a); apply_ry(lam, n, j, -a); }
+                }
+        }
+        if (d->init == 1 && grad_x) {
+            double nrm = 0, dot = 0;
+            for (long k = 0; k < A; ++k) {
+                const double v = k < d->n_features ? x[b * x_stride + k] + d->add_offset : d->pad_value;
+                nrm += v * v;
+            }
+            nrm = sqrt(nrm);
+            for (long k = 0; k < A; ++k) dot += creal(psi[k]) * 2 * creal(lam[k]);       /* psi is psi0 (real) again */
+            for (long k = 0; k < d->n_features; ++k) grad_x[b * x_stride + k] = (2 * creal(lam[k]) - creal(psi[k]) * dot) / nrm;
+        }
+        free(psi);
+        free(lam);
+    }
+    free(fwd);
+    free(st_all);
+    return 0;
 }

@@ -88,3 +88,13 @@ def test_autograd_gradients_of_the_torch_oracle_match_central_differences_of_the
             fd = ((f(x, tp.reshape(t.shape)) - f(x, tm.reshape(t.shape))) if is_w
                   else (f(tp.reshape(t.shape), W) - f(tm.reshape(t.shape), W))) / (2 * h)
             assert abs(fd - grad.reshape(-1)[i].item()) < 1e-8 * max(1.0, abs(fd)) + 1e-9, (family, is_w, i)
+
+
+def test_c_adjoint_gradients_reproduce_the_golden_autograd_gradients():
+    """The adjoint method in C (no autograd anywhere) against the golden gradients the torch oracle's autograd produced."""
+    vec = torch.load(GOLDEN / "stage_vectors.pt", weights_only=False)
+    for name, v in vec.items():
+        d = O.StageDesc(**v["desc"])
+        gw, gx = C.stage_grads(d, v["x"], v["weights"], v["grad_out"])
+        assert torch.allclose(gw, v["grad_w"], atol=1e-10), name
+        assert torch.allclose(gx, v["grad_x"], atol=1e-10), name
