@@ -106,6 +106,12 @@ def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
         C.run_stage(d, xc, W.detach()[None])
         cb["c_forward_only"] = {"value": xc.shape[0] / (time.perf_counter() - t0), "unit": "circuit-evals/s (forward only)",
                                 "cores": cores, "sample": f"{xc.shape[0]} instances, oracle/statevec_oracle.c"}
+        goc = torch.randn(xc.shape[0], PIXELS, generator=g, dtype=torch.float64)
+        t0 = time.perf_counter()
+        C.stage_grads(d, xc, W.detach()[None], goc)
+        cb["c_fwd_bwd"] = {"value": xc.shape[0] / (time.perf_counter() - t0), "unit": UNIT, "cores": cores,
+                           "sample": f"{xc.shape[0]} instances, forward + adjoint-method backward in C (OpenMP over the "
+                                     f"instances): what an optimised CPU simulator reaches; the reference's path is the torch one"}
     except Exception as e:
         cb["c_forward_only"] = {"unavailable": str(e)[:120]}
     return cb, t

@@ -21,6 +21,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 typedef double complex cplx;
 
@@ -215,7 +218,21 @@ int qc_backward(const qc_desc *d, const double *x, long x_stride, const long *ba
     if (rc != 0) { free(fwd); free(st_all); return rc; }
     memset(grad_w, 0, (size_t)n_w * sizeof(double));
     if (grad_x) memset(grad_x, 0, (size_t)(B * x_stride) * sizeof(double));
-    for (long b = 0; b < B; ++b) {                    /* serial over rows: grad_w accumulates deterministically */
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    double *gw_all = (double *)calloc((size_t)nt * n_w, sizeof(double));   /* per-thread partial sums, added in thread order */
+    if (!gw_all) { free(fwd); free(st_all); return -1; }
+#pragma omp parallel num_threads(nt)
+    {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    double *grad_w = gw_all + (long)tid * n_w;        /* shadows the output: this thread's partial sum */
+#pragma omp for schedule(static)
+    for (long b = 0; b < B; ++b) {
         cplx *psi = (cplx *)malloc((size_t)A * sizeof(cplx)), *lam = (cplx *)calloc((size_t)A, sizeof(cplx));
         for (long k = 0; k < A; ++k) psi[k] = st_all[(b * A + k) * 2] + I * st_all[(b * A + k) * 2 + 1];
         for (long m = 0; m < n_out; ++m) {            /* seed: out = clamp(post_scale * q), q = |psi_k|^2 or <Z_j> */
@@ -277,6 +294,10 @@ int qc_backward(const qc_desc *d, const double *x, long x_stride, const long *ba
         free(psi);
         free(lam);
     }
+    }
+    for (int t = 0; t < nt; ++t)
+        for (long i = 0; i < n_w; ++i) grad_w[i] += gw_all[(long)t * n_w + i];
+    free(gw_all);
     free(fwd);
     free(st_all);
     return 0;
