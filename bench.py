@@ -101,14 +101,14 @@ def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
         from oracle import c_oracle as C
         d = O.desc_qdense(QDEPTH, PIXELS, O.REMAP_TANH)
         xc = torch.rand(32 * cores, PIXELS, generator=g, dtype=torch.float64)
-        C.run_stage(d, xc[:cores], W.detach()[None])
+        C.run_stage(d, xc[:cores], W.detach()[None], threads=cores)
         t0 = time.perf_counter()
-        C.run_stage(d, xc, W.detach()[None])
+        C.run_stage(d, xc, W.detach()[None], threads=cores)
         cb["c_forward_only"] = {"value": xc.shape[0] / (time.perf_counter() - t0), "unit": "circuit-evals/s (forward only)",
                                 "cores": cores, "sample": f"{xc.shape[0]} instances, oracle/statevec_oracle.c"}
         goc = torch.randn(xc.shape[0], PIXELS, generator=g, dtype=torch.float64)
         t0 = time.perf_counter()
-        C.stage_grads(d, xc, W.detach()[None], goc)
+        C.stage_grads(d, xc, W.detach()[None], goc, threads=cores)
         cb["c_fwd_bwd"] = {"value": xc.shape[0] / (time.perf_counter() - t0), "unit": UNIT, "cores": cores,
                            "sample": f"{xc.shape[0]} instances, forward + adjoint-method backward in C (OpenMP over the "
                                      f"instances): what an optimised CPU simulator reaches; the reference's path is the torch one"}

@@ -5,7 +5,6 @@
 from __future__ import annotations
 
 import ctypes
-import os
 import shutil
 import subprocess
 from pathlib import Path
@@ -49,6 +48,8 @@ def _load():
         _lib.qc_forward.restype = ctypes.c_int
         _lib.qc_forward.argtypes = [ctypes.POINTER(_Desc), ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_long]
+        _lib.qc_set_threads.restype = None
+        _lib.qc_set_threads.argtypes = [ctypes.c_int]
         _lib.qc_backward.restype = ctypes.c_int
         _lib.qc_backward.argtypes = [ctypes.POINTER(_Desc), ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
@@ -62,7 +63,7 @@ def _c_desc(desc: O.StageDesc) -> _Desc:
 
 
 def stage_grads(desc: O.StageDesc, x: Optional[torch.Tensor], weights: torch.Tensor, grad_out: torch.Tensor,
-                batch: Optional[int] = None):
+                batch: Optional[int] = None, threads: Optional[int] = None):
     """Adjoint-method gradients of sum(out * grad_out): (grad_weights like `weights`, grad_x like `x` or None)."""
     lib = _load()
     d = _c_desc(desc)
@@ -72,6 +73,8 @@ def stage_grads(desc: O.StageDesc, x: Optional[torch.Tensor], weights: torch.Ten
     B = xs.shape[0] if xs is not None else int(batch)
     gw = torch.empty_like(w)
     gx = torch.zeros_like(xs) if xs is not None else None
+    if threads is not None:
+        lib.qc_set_threads(int(threads))
     rc = lib.qc_backward(ctypes.byref(d), xs.data_ptr() if xs is not None else None, xs.shape[1] if xs is not None else 0,
                          None, w.data_ptr(), go.data_ptr(), gx.data_ptr() if gx is not None else None, gw.data_ptr(), B)
     if rc != 0:
@@ -92,7 +95,7 @@ def run_stage(desc: O.StageDesc, x: Optional[torch.Tensor], weights: torch.Tenso
     B = xs.shape[0] if xs is not None else (bi.shape[0] if bi is not None else int(batch))
     out = torch.empty(B, desc.n_out, dtype=torch.float64)
     if threads is not None:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        lib.qc_set_threads(int(threads))
     rc = lib.qc_forward(ctypes.byref(d), xs.data_ptr() if xs is not None else None, xs.shape[1] if xs is not None else 0,
                         bi.data_ptr() if bi is not None else None, w.data_ptr(), out.data_ptr(), B)
     if rc != 0:

@@ -44,6 +44,15 @@ typedef struct {
     double clamp_lo, clamp_hi;
 } qc_desc;
 
+/* number of OpenMP threads of the calls that follow (0: leave the runtime's default) */
+void qc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static void apply_1q(cplx *s, int n, int wire, cplx m00, cplx m01, cplx m10, cplx m11) {
     const long A = 1L << n, st = 1L << (n - 1 - wire);
     for (long base = 0; base < A; base += 2 * st)
