@@ -14,17 +14,21 @@ NOT installable here (no network):
   ``RZ``, ``RY``, ``Rot``, ``CNOT``, ``CZ``, ``StronglyEntanglingLayers``, ``probs``,
   ``expval(PauliZ)``, device ``default.qubit.torch``;
 * PennyLane-Lightning 0.30.0 (``requirements.txt:47``): device ``lightning.qubit``;
-* qW-Map 0.1.2 (``requirements.txt:68``): ``qw_map.tanh`` (= pi*tanh, UNPINNED: package
-  source absent; rests on its public documentation only).
+* qW-Map 0.1.2 (``requirements.txt:68``): ``qw_map.tanh`` (= pi*tanh; package source absent, pinned by
+  fixture F3, see below).
 
 Parity status: the reference has no tests for this path.  The conventions restated
 here (wire 0 = MSB, ``Rot = RZ(omega) RY(theta) RZ(phi)``, SEL ranges, CNOT direction,
 CZ, RZ re-upload chaining, ``AmplitudeEmbedding(pad_with, normalize)``, probs order,
 ``torch.tanh`` remap) are pinned by fixture F1: checkpoints trained by the real
 PennyLane stack (``results/emnist.zip``) produce recognisable letters only under these
-conventions (``tests/test_oracle_f1.py``, golden vectors in ``tests/golden``).
-``qw_map.tanh``, ``AngleEmbedding(rotation="Y")`` and QConv's ``pad_with=0.5``/``[::2]``
-are "parity unpinned" (documentation only).
+conventions (``tests/test_oracle.py``, golden vectors in ``tests/golden``); the sign of the
+``expval(PauliZ)`` readout by the checkpoints of the <Z> families; ``qw_map.tanh = pi*tanh`` by
+fixture F3: the one shipped ``QDenseUndirected_old`` checkpoint with its recorded training losses
+and its 100 training images (``results_rebuttal_complex_dataset/logo2kplus.zip``) reproduces the
+recorded loss (19.3-19.8 per epoch) only with pi*tanh (19.5; tanh 22.6, identity 23.6).
+``AngleEmbedding(rotation="Y")`` and QConv's ``pad_with=0.5``/``[::2]`` stay "parity unpinned"
+(documentation only: no shipped artefact exercises them).
 
 Reference call sites each function follows are cited as ``nn/qdense.py:LINE`` etc.
 (paths relative to ``/root/reference``).

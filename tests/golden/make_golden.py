@@ -8,6 +8,9 @@
   label 14 with the oracle's chain / layer outputs on seeded inputs (`python make_golden.py f1_expval` writes only this one).
 * f1_unet_label14.pt — the classical UNetUndirected(3, 8, qdepth=0) checkpoint of label 14 (row a7: the UNet glue around the
   convolutions) + 20 sampler iterations of the product module on the CPU (`python make_golden.py f1_unet`).
+* f3_qw_map_logo_ascari.pt — fixture F3 turned into a pin of `qw_map.tanh`: the QDenseUndirected_old(60, 28) checkpoint of
+  results_rebuttal_complex_dataset/logo2kplus.zip (label "Ascari"), its recorded per-epoch training losses and the 100 training
+  images the reference saved next to it (8-bit PNGs) (`python make_golden.py f3_qw_map`).
 * f2_state_dict_contract.json — key names / shapes / dtypes of every shipped checkpoint family (F2).
 * stage_vectors.pt — oracle outputs and gradients for seeded inputs of each circuit family.
 """
@@ -64,7 +67,26 @@ def f1_unet(z):
     torch.save({"state_dict": sd, "first_x": x0, "sample": smp, "source": "results/emnist.zip:" + src}, OUT / "f1_unet_label14.pt")
 
 
+def f3_qw_map():
+    """The only shipped checkpoints of a class that calls qw_map.tanh (nn/qdense.py:45) + their training data."""
+    import numpy as np
+    from PIL import Image
+    z = zipfile.ZipFile(REF / "results_rebuttal_complex_dataset/logo2kplus.zip")
+    src = "logo2kplus/Ascari/QDenseUndirected_old60_w28_h28_0.pt"
+    ck = load_ck(z, src)
+    imgs = [np.asarray(Image.open(io.BytesIO(z.read(f"logo2kplus/Ascari/image_0/train_image_{i}.png"))).convert("L"))
+            for i in range(1, 101)]
+    torch.save({"weights": ck["model_state_dict"]["net.weights"], "loss_values": torch.tensor(ck["loss_values"]),
+                "epochs": ck["epochs"], "train_images_u8": torch.tensor(np.stack(imgs), dtype=torch.uint8),
+                "source": "results_rebuttal_complex_dataset/logo2kplus.zip:" + src + " + Ascari/image_0/train_image_*.png "
+                          "(plt.imsave(cmap='gray') of the training tensors, src/bloodmnist.py:266-268)"},
+               OUT / "f3_qw_map_logo_ascari.pt")
+
+
 def main():
+    if sys.argv[1:] == ["f3_qw_map"]:
+        f3_qw_map()
+        return
     z = zipfile.ZipFile(REF / "results/emnist.zip")
     if sys.argv[1:] == ["f1_expval"]:
         f1_expval(z)
@@ -74,6 +96,7 @@ def main():
         return
     f1_expval(z)
     f1_unet(z)
+    f3_qw_map()
     # ---- F1 a1: QDenseUndirected_old_noise(60, 28), label 14 ("O")
     ck = load_ck(z, "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")
     W = ck["model_state_dict"]["net.weights"]

@@ -190,6 +190,32 @@ def test_f4_reference_checkpoints_show_the_cut_circuit_gradient():
     assert not torch.equal(same[0]["net.linear_up.weight"], same[1]["net.linear_up.weight"])
 
 
+def test_f3_recorded_training_loss_pins_qw_map_tanh_as_pi_tanh():
+    """`QDenseUndirected_old` re-maps its weights with the un-vendored `qw_map.tanh` (nn/qdense.py:45; QConv2d does the same,
+    nn/qconv.py:55).  The reference ships one such checkpoint together with its recorded per-epoch training losses AND the
+    100 training images (results_rebuttal_complex_dataset/logo2kplus.zip, copied to tests/golden/f3_qw_map_logo_ascari.pt).
+    Re-evaluating the training loss of `src/bloodmnist.py:181-191` (batch 1, tau 10, goal "data": the epoch loss is the sum of
+    the per-image MSE) with the oracle reproduces the recorded final losses (19.26 ... 19.81) only with qw_map.tanh = pi * tanh
+    (19.5); torch.tanh (22.7) and the identity (23.0) stay at the level of the first, untrained epoch (22.0)."""
+    gold = torch.load(GOLDEN / "f3_qw_map_logo_ascari.pt", weights_only=True)
+    W = gold["weights"].double()
+    X = gold["train_images_u8"].double().reshape(100, 784) / 255
+    recorded = gold["loss_values"]
+    n_img = 40                                       # a subset keeps the CPU suite short; the loss is a per-image mean
+    g = torch.Generator().manual_seed(0)
+    eps = torch.normal(0.5, 0.2, size=(n_img, 784), generator=g).double()
+
+    def epoch_loss(remap):
+        with torch.no_grad():
+            per_image = O.diffusion_loss(lambda v: O.qdense_forward(v, W, remap), X[:n_img], eps, 10, (28, 28), goal="data")
+        return per_image.item() * 100                # 100 batches of one image per epoch
+
+    trained = recorded[-5:].mean().item()
+    assert abs(epoch_loss(O.REMAP_PI_TANH) - trained) < 0.03 * trained
+    assert epoch_loss(O.REMAP_TANH) > trained * 1.1
+    assert epoch_loss(O.REMAP_NONE) > trained * 1.1
+
+
 def test_noise_ladder_and_training_targets():
     """src/noise.py:105-126 + src/models.py:46-63 layout: '(batch tau) pixels', w_0 = 0, w_last = 1."""
     x = torch.rand(3, 16, dtype=torch.float64)
