@@ -11,6 +11,8 @@
 * f3_qw_map_logo_ascari.pt — fixture F3 turned into a pin of `qw_map.tanh`: the QDenseUndirected_old(60, 28) checkpoint of
   results_rebuttal_complex_dataset/logo2kplus.zip (label "Ascari"), its recorded per-epoch training losses and the 100 training
   images the reference saved next to it (8-bit PNGs) (`python make_golden.py f3_qw_map`).
+* f3_qiddm_pl_logo_sanyo.pt — the same kind of fixture for family a4: QIDDM_PL_noise(784,8,6,2), recorded losses, training
+  images (`python make_golden.py f3_qiddm_pl`).
 * f2_state_dict_contract.json — key names / shapes / dtypes of every shipped checkpoint family (F2).
 * stage_vectors.pt — oracle outputs and gradients for seeded inputs of each circuit family.
 """
@@ -83,9 +85,27 @@ def f3_qw_map():
                OUT / "f3_qw_map_logo_ascari.pt")
 
 
+def f3_qiddm_pl():
+    """QIDDM_PL_noise(784,8,6,2) checkpoint of logo2kplus "Sanyo" + recorded losses + its 100 training images (a4)."""
+    import numpy as np
+    from PIL import Image
+    z = zipfile.ZipFile(REF / "results_rebuttal_complex_dataset/logo2kplus.zip")
+    src = "logo2kplus/Sanyo/QIDDM_PL_noise=8_L=6_N=2_5.pt"
+    ck = load_ck(z, src)
+    imgs = [np.asarray(Image.open(io.BytesIO(z.read(f"logo2kplus/Sanyo/image_0/train_image_{i}.png"))).convert("L"))
+            for i in range(1, 101)]
+    torch.save({**ck["model_state_dict"], "loss_values": torch.tensor(ck["loss_values"]), "epochs": ck["epochs"],
+                "train_images_u8": torch.tensor(np.stack(imgs), dtype=torch.uint8),
+                "source": "results_rebuttal_complex_dataset/logo2kplus.zip:" + src + " + Sanyo/image_0/train_image_*.png"},
+               OUT / "f3_qiddm_pl_logo_sanyo.pt")
+
+
 def main():
     if sys.argv[1:] == ["f3_qw_map"]:
         f3_qw_map()
+        return
+    if sys.argv[1:] == ["f3_qiddm_pl"]:
+        f3_qiddm_pl()
         return
     z = zipfile.ZipFile(REF / "results/emnist.zip")
     if sys.argv[1:] == ["f1_expval"]:
@@ -97,6 +117,7 @@ def main():
     f1_expval(z)
     f1_unet(z)
     f3_qw_map()
+    f3_qiddm_pl()
     # ---- F1 a1: QDenseUndirected_old_noise(60, 28), label 14 ("O")
     ck = load_ck(z, "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")
     W = ck["model_state_dict"]["net.weights"]
