@@ -94,9 +94,15 @@ def f3_qiddm_pl():
     ck = load_ck(z, src)
     imgs = [np.asarray(Image.open(io.BytesIO(z.read(f"logo2kplus/Sanyo/image_0/train_image_{i}.png"))).convert("L"))
             for i in range(1, 101)]
+    # the reference's OWN sampler output for this checkpoint: image_{1..10}/step_{1..6}.png = first_x and 5 iterations of
+    # Diffusion.sample (goal "data"), clamped to [0, 1] and saved with plt.imsave(cmap="gray") (src/bloodmnist.py:231-278)
+    steps = [[np.asarray(Image.open(io.BytesIO(z.read(f"logo2kplus/Sanyo/image_{i}/step_{s}.png"))).convert("L"))
+              for i in range(1, 11)] for s in range(1, 7)]
     torch.save({**ck["model_state_dict"], "loss_values": torch.tensor(ck["loss_values"]), "epochs": ck["epochs"],
                 "train_images_u8": torch.tensor(np.stack(imgs), dtype=torch.uint8),
-                "source": "results_rebuttal_complex_dataset/logo2kplus.zip:" + src + " + Sanyo/image_0/train_image_*.png"},
+                "sample_steps_u8": torch.tensor(np.array(steps), dtype=torch.uint8),
+                "source": "results_rebuttal_complex_dataset/logo2kplus.zip:" + src + " + Sanyo/image_0/train_image_*.png"
+                          " + Sanyo/image_*/step_*.png"},
                OUT / "f3_qiddm_pl_logo_sanyo.pt")
 
 
