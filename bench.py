@@ -10,7 +10,12 @@ instance, fwd+bwd), whole job over all ranks.
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL): instances are sharded over ranks (weak
 scaling, no data-path collective); only the 1 800-float circuit-weight gradient is all-reduced per step.
-`--impl reference` times the CPU oracle port of the reference path on the host cores (rank 0 only).
+`--impl reference` times the CPU oracle port of the reference path on the host cores (rank 0 only): W warm-up + K timed
+steps, each a FIXED bounded sample (`config.sample_instances`) of the same workload.
+
+Besides the headline (`value`, `e2e`, `roofline` of the tcgen05 GEMM) the line carries `secondary`: the second half of
+BASELINE.json's metric, QIDDM train samples/s (configs 1 and 4) as CUDA-graph training steps, data-parallel over the ranks
+with the flat-bucket all-reduce, with the gate kernels' FP32 roofline (peak measured in-run by qiddm_probe_fp32_fma).
 """
 from __future__ import annotations
 
@@ -40,11 +45,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=524288, help="circuit instances per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-instances", type=int, default=1024,
+                    help="circuit instances per CPU sample step (cpu_baseline: best of 3; --impl reference: every step)")
     ap.add_argument("--path", default="auto", choices=["auto", "gate", "gemm"],
                     help="auto = library dispatch (unitary-collapse tcgen05 GEMM when batch >= 2 * 2^n)")
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
                     help="GEMM path: 3 = fp32-grade 3-term fp16 split (default), 1 = single fp16 pass")
+    ap.add_argument("--bwd-precision", type=int, default=0, choices=[0, 1, 3],
+                    help="GEMM path, dX / dW GEMMs: 0 = same as --precision; 1 behind --precision 3 = x3 forward, x1 gradients")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
@@ -53,6 +62,9 @@ def parse():
 def workload_config(batch, n_gpus):
     return {"workload": f"QDenseUndirected_old_noise({QDEPTH},{SIDE}) fwd+bwd, n={NQ} qubits, 600 Rot + 600 CNOT, "
                         f"synthetic MNIST-shaped 28x28", "instances_per_gpu": batch, "global_instances": batch * n_gpus,
+            "work_per_step": "value: forward + input gradient + weight gradient per instance; e2e and the CPU arms "
+                             "(cpu_baseline, --impl reference): forward + weight gradient (the layer is the first one of the "
+                             "Diffusion step, its input needs no gradient -- src/models.py:64-67)",
             "parallelism": f"dp{n_gpus} (instances sharded, weight-grad all-reduce only)",
             "step": "device-resident step = forward + backward for BOTH the input and the weight gradients; the e2e "
                     "Diffusion step (first layer: the noisy images need no gradient) skips the dX GEMM, as the reference does",
@@ -62,8 +74,19 @@ def workload_config(batch, n_gpus):
 # ----------------------------------------------------------------------------------------------
 # CPU oracle legs (the only places bench.py may execute oracle/)
 # ----------------------------------------------------------------------------------------------
-def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
-    """Times the complex128 oracle port of the reference path (fwd + autograd bwd) on the host cores."""
+def cpu_sample_size(requested: int, steps_total: int) -> int:
+    """Fixed sample per CPU step: `requested` (1024) instances, reduced only when W + K steps of it would not end within a few
+    minutes (~2 s per 1024 instances on 16 cores)."""
+    b = requested
+    if steps_total > 40:
+        b = max(128, (requested * 40 // steps_total) // 64 * 64)
+    return b
+
+
+def cpu_oracle_rate(sample_instances: int, steps: int = 3, warmup: int = 1, best: bool = True):
+    """Times the complex128 oracle port of the reference path (forward + autograd weight gradient) on the host cores:
+    `warmup` + `steps` steps of `sample_instances` instances each.  best=True -> rate of the fastest step (cpu_baseline),
+    else of the mean step (--impl reference, whose ms_per_step x steps must match the wall clock)."""
     import torch
     from oracle import qiddm_oracle as O
     cores = os.cpu_count() or 1
@@ -80,23 +103,18 @@ def cpu_oracle_rate(target_seconds: float, steps: int = 1, warmup: int = 0):
         W.grad = None
         return time.perf_counter() - t
 
-    run(4)                                   # warm the thread pool / allocator
-    t_probe = run(16)
-    per = t_probe / 16
-    per_step = max(target_seconds / max(steps + warmup, 1), 0.5)
-    b = int(min(4096, max(16, per_step / per)))
-    for _ in range(4):                       # small batches under-use the cores: refine the estimate at the sample's own size
-        t_b = run(b)
-        if t_b >= 0.6 * per_step or b >= 4096:
-            break
-        b = int(min(4096, max(b + 1, b * per_step / t_b)))
+    b = sample_instances
+    run(8)                                   # warm the thread pool / allocator
     for _ in range(warmup):
         run(b)
     times = [run(b) for _ in range(max(steps, 1))]
-    t = sum(times) / len(times)
+    t = min(times) if best else sum(times) / len(times)
     cb = {"value": b / t, "unit": UNIT, "cores": cores, "kind": "port",
-          "sample": f"{b} instances/step x {len(times)} step(s) of the same circuit, complex128 torch oracle "
-                    f"(per-gate ops on a (B,2^n) tensor + autograd, mirrors default.qubit.torch), {t:.2f} s/step"}
+          "sample": f"{b} instances/step x {len(times)} timed step(s) (+{warmup} warm-up) of the same circuit, forward + weight "
+                    f"gradient, complex128 torch oracle (per-gate ops on a (B,2^n) tensor + autograd, mirrors "
+                    f"default.qubit.torch); {'best' if best else 'mean'} step {t:.2f} s, all steps "
+                    f"{[round(v, 2) for v in times]} s",
+          "sample_instances": b, "steps_timed": len(times)}
     try:    # for scale: the forward alone on the gate-by-gate C restatement (lightning.qubit-like), OpenMP over the instances
         from oracle import c_oracle as C
         d = O.desc_qdense(QDEPTH, PIXELS, O.REMAP_TANH)
@@ -121,11 +139,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, t = cpu_oracle_rate(args.cpu_seconds * 2, steps=max(1, min(args.steps, 5)), warmup=min(args.warmup, 1))
+    K, Wm = max(args.steps, 1), max(args.warmup, 0)
+    b = cpu_sample_size(args.cpu_instances, K + Wm)
+    cb, t = cpu_oracle_rate(b, steps=K, warmup=Wm, best=False)
+    cfg = workload_config(args.batch, args.gpus)
+    cfg["sample_instances"] = b
+    cfg["sample_note"] = (f"each CPU step simulates a bounded sample of {b} instances of the workload (the rate is per "
+                          f"instance); instances_per_gpu / global_instances describe the GPU arm's step")
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "steps": K, "warmup": Wm, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.batch, args.gpus), "cpu_baseline": cb,
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "PennyLane/Lightning are not installable here (no network); this is the oracle port of the "
                     "reference's default.qubit.torch path on the host cores"}
@@ -194,9 +218,10 @@ def run_b200(args):
     torch.manual_seed(42 + rank)
     net = qnn.QDenseUndirected_old_noise(QDEPTH, SIDE).to(dev, torch.float64)
     if world > 1:
-        dist.broadcast(net.weights.data, 0)
+        dist.broadcast(net.weights.detach(), 0)      # detach() shares the version counter (cache invalidation)
     path_id = {"auto": L.PATH_AUTO, "gate": L.PATH_GATE, "gemm": L.PATH_GEMM}[args.path]
-    spec = dataclasses.replace(net._spec(), path=path_id, gemm_precision=args.precision)
+    spec = dataclasses.replace(net._spec(), path=path_id, gemm_precision=args.precision,
+                               gemm_bwd_precision=args.bwd_precision)
     net._spec = lambda: spec                                   # the module API (e2e) uses the same dispatch
     plan = Plan.get(spec)
     use_gemm = plan.use_gemm(B)
@@ -303,6 +328,26 @@ def run_b200(args):
         # nvidia-smi's polled clocks.sm does not resolve the cap: ncu reports 1.17-1.43 GHz inside the GEMM launches
         clocks["note"] = "power cap active: ncu shows 1.17-1.43 GHz SM clock inside the GEMM launches (profiles/r1_gemm_pair_summary.md)"
 
+    # --- sustained rate: the same device-resident step back to back for >= 3 s (the "sustained" tensor peak is a 4 s loop)
+    sustained = None
+    if world == 1 and not args.no_extras:
+        n_s = max(int(3000.0 / ms_step) + 1, K)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(n_s):
+            step_device()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_s = e0.elapsed_time(e1)
+        sustained = {"value": B * n_s / (ms_s * 1e-3), "unit": UNIT, "steps": n_s, "seconds": ms_s * 1e-3,
+                     "ms_per_step": ms_s / n_s}
+    del x, go
+
+    # --- the second half of BASELINE.json's metric: QIDDM train samples/s, data-parallel over the ranks (all ranks take part)
+    sec = None
+    if not args.no_secondary:
+        sec = secondary_train(dev, world, rank, max(5, min(K, 10)))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -321,21 +366,38 @@ def run_b200(args):
     dom = max(shares, key=shares.get)
     kd = kinds[dom]
     per_launch_ms = kd["ms"] / kd["launches"]
+    bwdp = args.bwd_precision or args.precision
     if dom == "gemm":
         achieved = kd["work"] / (kd["ms"] * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
+        # (profiles/r2_gemm_traffic.json, written by scripts/ncu_summary.py from the .ncu-rep): not measured in this run
+        traffic, traffic_src = None, "no ncu capture committed for this configuration"
+        tj = ROOT / "profiles" / "r2_gemm_traffic.json"
+        if tj.exists():
+            try:
+                td = json.loads(tj.read_text())
+                key = f"B{B}_p{args.precision}{bwdp}"
+                if key in td:
+                    traffic = float(td[key]["mean_bytes_per_launch"])
+                    traffic_src = f"ncu capture {td[key]['source']} (per-launch bytes of forward / dX / dW: {td[key]['per_launch']})"
+            except Exception as exc:      # a malformed side file must not kill the bench line
+                traffic_src = f"profiles/r2_gemm_traffic.json unreadable: {exc}"
+        exec_mult = (args.precision + 2 * bwdp) / 3.0
         roofline = {"kernel": "gemm_pair_kernel (tcgen05.mma.cta_group::2 kind::f16 + TMA, fused |Y|^2 readout epilogue)",
                     "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                     "frac": achieved / tc_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's three GEMM launches, from
                     # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv; 8.3-11.2e9
                     # across the captures of the round: the dW launch's L2 re-reads vary with the box, profiles/r1_gemm_pair_summary.md)
-                    "traffic": 11.2e9 if (B == 524288 and args.precision == 3) else None,
-                    "traffic_unit": "bytes/launch (algorithmic operand + result bytes: 6.04e9)",
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "traffic_unit": "DRAM bytes/launch, mean of the step's GEMM launches; the algorithm's own bytes per launch "
+                                    "(fp32 x / grad_out in, out / grad_in out, shared by the step's 3 launches): %.3g"
+                                    % (4.0 * B * PIXELS * 4 / 3),
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
                     "ms_per_launch": per_launch_ms, "launches": kd["launches"],
-                    "algorithmic_flops": "2*M*N*K per GEMM (single pass); precision %d executes %dx that"
-                                         % (args.precision, args.precision),
-                    "executed_tflops": achieved * args.precision, "share_of_step": shares[dom]}
+                    "algorithmic_flops": "2*M*N*K per GEMM (single pass); forward executes %dx, dX / dW %dx that"
+                                         % (args.precision, bwdp),
+                    "executed_tflops": achieved * exec_mult, "share_of_step": shares[dom]}
     else:
         alg_bytes = B * 4 * (PIXELS * 3) * K                 # x in, grad_out in, grad_in out (fp32) per launch
         achieved = alg_bytes / (kd["ms"] * 1e-3) / 1e9
@@ -351,24 +413,119 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("f32 (tcgen05 fp16 x%d split, fp32 accumulate)" % args.precision) if use_gemm else "f32",
+            "dtype": ("f32 (tcgen05 fp16 operands: x%d split forward, x%d split gradient GEMMs; fp32 accumulate)"
+                      % (args.precision, bwdp)) if use_gemm else "f32",
             "data": "synthetic", "config": workload_config(B, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": imgs * PIXELS * 4,
                     "d2h_bytes_per_step": res_h.numel() * 8, "ms_per_step": ms_e / ke,
                     "api": "qiddm_b200.models.Diffusion(QDenseUndirected_old_noise(60,28)).forward(x, T=10): "
                            f"{imgs} pinned host images/step -> {imgs * TAU} circuit instances, loss+grad to host; "
                            "H2D double-buffered on a copy stream (qiddm_b200.train.DevicePrefetcher), one copy per step"},
-            "path": ("gemm_x%d" % args.precision) if use_gemm else "gate",
+            "path": ("gemm_x%d_bwd_x%d" % (args.precision, bwdp)) if use_gemm else "gate",
             "gpu_launches": int(launches), "roofline": roofline}
 
+    if sec is not None:
+        line["secondary"] = sec
     if not args.no_extras:
-        line["extras"] = extras(dev)
+        line["extras"] = extras(dev) if world == 1 else {}
+        if sustained is not None:
+            line["extras"]["sustained_3s"] = sustained
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_oracle_rate(args.cpu_seconds)
+        cb, _ = cpu_oracle_rate(cpu_sample_size(args.cpu_instances, 4), steps=3, warmup=1, best=True)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_train(dev, world, rank, steps):
+    """QIDDM train samples/s (BASELINE.json metric, second half; configs 1 and 4) as the loop body of
+    src/mnist_exm.py:175-182 captured in CUDA graphs (qiddm_b200.train.GraphedTrainStep), weak-scaled over the ranks:
+    every rank trains on its own images, ONE flat-bucket NCCL all-reduce of all gradients per step.  The gate kernels'
+    roofline is FP32-FMA: algorithmic flops (14 * 2^n per Rot, adjoint = 4x forward) over the kernels'
+    own CUDA-event time from an eager pass, against the FP32 peak measured here by qiddm_probe_fp32_fma."""
+    import torch
+    import torch.distributed as dist
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import models, noise
+    from qiddm_b200 import nn as qnn
+    from qiddm_b200.train import DataParallelTrainer, GraphedTrainStep
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    fp32_peak = L.fp32_fma_peak_tflops(dev) if rank == 0 else None
+    cfgs = [("config1", "QIDDM_LL_noise(784,6,14,2)", lambda: qnn.QIDDM_LL_noise(784, 6, 14, 2), 4096, "data", None, 0.0255,
+             "src/mnist_exm.py:46,139"),
+            ("config4", "QIDDM_PL_noise(784,8,6,2)", lambda: qnn.QIDDM_PL_noise(784, 8, 6, 2), 1024, "noise", 10, 0.01,
+             "src/emnist_exm.py:45")]
+    out = {"metric": "qiddm_train_samples_per_sec", "unit": "train-samples/s", "n_gpus": world, "tau": 10,
+           "scaling": "weak", "fp32_peak_tflops_measured": fp32_peak,
+           "what": "whole-job images/s through Diffusion training steps (noise ladder -> net -> MSE -> adjoint backward -> "
+                   "flat-bucket all-reduce -> Adam), CUDA-graph replays, float64 module I/O, fp32 simulation"}
+    for key, name, make, imgs, goal, pca_group, lr, src in cfgs:
+        torch.manual_seed(0)
+        net = make()
+        if pca_group:
+            net.pca_group = pca_group        # one PCA per image's tau-ladder = the reference's batch-1 semantics (SURVEY H5)
+        diff = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (SIDE, SIDE), torch.nn.MSELoss()).to(dev, torch.float64)
+        opt = torch.optim.Adam(diff.parameters(), lr=lr, capturable=True)
+        trainer = DataParallelTrainer(diff, opt, tau=10)
+        trainer.broadcast_parameters()
+        torch.manual_seed(100 + rank)
+        x = torch.rand(imgs, PIXELS, device=dev, dtype=torch.float64)
+        trainer.step(x, already_sharded=True)                    # eager warm-up
+        L.timing_enable(True)
+        L.timing_collect()
+        n0 = L.launch_count()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(2):
+            trainer.step(x, already_sharded=True)
+        b.record()
+        torch.cuda.synchronize()
+        kinds = L.timing_collect()
+        L.timing_enable(False)
+        launches = (L.launch_count() - n0) // 2
+        eager_ms = a.elapsed_time(b) / 2
+        gs = GraphedTrainStep(diff, opt, 10, x, allreduce=world > 1)
+        for _ in range(3):
+            gs.step(x)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(steps):
+            gs.step(x)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        gf, gb = kinds["gate_forward"], kinds["gate_backward"]
+        roof = None
+        if rank == 0 and gf["launches"] and gb["launches"]:
+            tf_f = gf["work"] / (gf["ms"] * 1e-3) / 1e12
+            tf_b = gb["work"] / (gb["ms"] * 1e-3) / 1e12
+            tf_all = (gf["work"] + gb["work"]) / ((gf["ms"] + gb["ms"]) * 1e-3) / 1e12
+            roof = {"kernel": "gate_kernel (forward + adjoint backward)", "bound": "fp32", "unit": "TFLOP/s",
+                    "achieved": tf_all, "peak": fp32_peak, "frac": tf_all / fp32_peak if fp32_peak else None,
+                    "peak_source": "qiddm_probe_fp32_fma, this run (packed FFMA2 chains)",
+                    "forward": {"achieved": tf_f, "frac": tf_f / fp32_peak, "ms_per_step": gf["ms"] / 2},
+                    "backward": {"achieved": tf_b, "frac": tf_b / fp32_peak, "ms_per_step": gb["ms"] / 2,
+                                 "note": "algorithmic flops of the adjoint counted as 4x the forward (un-apply on psi, apply-dagger "
+                                         "on lambda, inner products)"},
+                    "share_of_eager_step": (gf["ms"] + gb["ms"]) / 2 / eager_ms}
+        out[key] = {"model": name, "reference": src, "goal": goal, "images_per_gpu": imgs, "value": imgs * world / (ms * 1e-3),
+                    "ms_per_step": ms, "steps": steps, "circuit_evals_per_s": imgs * world * 10 * 2 / (ms * 1e-3),
+                    "eager_ms_per_step": eager_ms, "gpu_launches_per_step": int(launches), "roofline": roof,
+                    "allreduce": "one flat fp64 bucket of all gradients per step (NCCL), between two graph replays" if world > 1 else None}
+        del gs, trainer, opt, diff, net, x
+        torch.cuda.empty_cache()
+    return out
 
 
 def extras(dev):

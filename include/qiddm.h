@@ -128,7 +128,9 @@ int qiddm_build_unitary(const qiddm_plan *plan, const void *weights, int weights
  * nn/qconv.py:92-126 to training.  `prepare` collapses the circuit for the current weights into
  * `collapsed` (qiddm_gemm_collapsed_bytes; call again whenever the weights change); forward/backward
  * then run every instance as one row of a tcgen05 GEMM.  precision: 3 = fp32-grade (3-term fp16 split),
- * 1 = single fp16 pass (about 1e-3 relative).  Workspace: qiddm_gemm_workspace_bytes(plan, batch). */
+ * 1 = single fp16 pass (about 1e-3 relative).  The backward takes its own precision: 1 behind a precision-3 forward runs
+ * the dX / dW GEMMs single-pass on the fp32-grade saved state (outputs unchanged, gradients to about 5e-4 of their
+ * maximum).  Workspace: qiddm_gemm_workspace_bytes(plan, batch). */
 int    qiddm_gemm_supported(const qiddm_plan *plan);
 size_t qiddm_gemm_collapsed_bytes(const qiddm_plan *plan);
 size_t qiddm_gemm_workspace_bytes(const qiddm_plan *plan, int64_t batch);
@@ -138,6 +140,8 @@ int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_
  * splits and Y there and the backward reuses them (no re-materialisation GEMM); pass NULL for inference, and
  * NULL to the backward to have it recompute them. */
 size_t qiddm_gemm_saved_bytes(const qiddm_plan *plan, int64_t batch);
+/* workspace of an inference forward (saved == NULL): the operand splits and norms live there */
+size_t qiddm_gemm_forward_workspace_bytes(const qiddm_plan *plan, int64_t batch);
 int qiddm_gemm_forward(const qiddm_plan *plan, const void *collapsed, const float *in, float *out, void *saved,
                        void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
 int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const float *in, const void *weights,
@@ -159,6 +163,16 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
                               int io_dtype, const void *img, const void *weights, int weights_dtype, const void *grad_out,
                               const void *saved, void *grad_img, void *grad_weights, void *workspace,
                               int64_t n_images, int precision, qiddm_stream_t stream);
+
+/* Compatibility: the forward `_QConv2d_FAST` LITERALLY executes (nn/qconv.py:71-90 -- the QNode call is missing there, SURVEY.md
+ * H1): out[b, j, y, x] = clamp((patch feature 2j + 0.1) * F * 0.5, 0, 1), F = C * kernel_h * kernel_w, feature = (ch, ky, kx)
+ * in torch.nn.Unfold order, zero padding; out_channels = min(module out_channels, ceil(F / 2)).  img / out / grad tensors
+ * NCHW of `dtype`; the backward OVERWRITES grad_img.  Every checkpoint the reference saved for a QConv network was trained
+ * through this map (its circuit weights never received a gradient). */
+int qiddm_qconv_reference_map_forward(const qiddm_unfold_desc *unfold, int dtype, const void *img, void *out, int out_channels,
+                                      int64_t n_images, qiddm_stream_t stream);
+int qiddm_qconv_reference_map_backward(const qiddm_unfold_desc *unfold, int dtype, const void *img, const void *grad_out,
+                                       void *grad_img, int out_channels, int64_t n_images, qiddm_stream_t stream);
 
 /* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
  * launching stream around each main kernel.  collect() synchronises on them and returns, per kind
@@ -226,6 +240,12 @@ int qiddm_sym_eigh_f64_batched(const double *a, int m, int64_t count, double *ev
 /* Id of the CUDA-graph capture `stream` is currently part of, 0 when it is not capturing (lets the host side keep
  * per-capture caches of the collapsed operator). */
 int64_t qiddm_stream_capture_id(qiddm_stream_t stream);
+
+/* Measurement support: one launch of a register-only packed-FMA loop (8 independent fma.rn.f32x2 chains per thread,
+ * 8 CTAs of 256 threads per SM, `iters` rounds of 64 flop per thread); *flops (host, nullable) = flops the launch executes.
+ * The caller times it with events on `stream`: the FP32-pipe roofline denominator of the gate kernels (SURVEY.md 8d:
+ * MEASURED_PEAKS.json holds no FP32 figure).  `sink` = any 4-byte device buffer (never written). */
+int qiddm_probe_fp32_fma(int iters, float *sink, double *flops, qiddm_stream_t stream);
 
 /* Kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
 int64_t qiddm_launch_count(void);

@@ -53,7 +53,8 @@ EXPORTS = [
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
-    "qiddm_readout_channel",
+    "qiddm_readout_channel", "qiddm_gemm_forward_workspace_bytes", "qiddm_probe_fp32_fma",
+    "qiddm_qconv_reference_map_forward", "qiddm_qconv_reference_map_backward",
 ]
 
 _lib = None
@@ -138,6 +139,14 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_gemm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_gemm_saved_bytes.restype = C.c_size_t
         lib.qiddm_gemm_saved_bytes.argtypes = [vp, i64]
+        lib.qiddm_gemm_forward_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_gemm_forward_workspace_bytes.argtypes = [vp, i64]
+        lib.qiddm_qconv_reference_map_forward.restype = i32
+        lib.qiddm_qconv_reference_map_forward.argtypes = [C.POINTER(UnfoldDesc), i32, vp, vp, i32, i64, vp]
+        lib.qiddm_qconv_reference_map_backward.restype = i32
+        lib.qiddm_qconv_reference_map_backward.argtypes = [C.POINTER(UnfoldDesc), i32, vp, vp, vp, i32, i64, vp]
+        lib.qiddm_probe_fp32_fma.restype = i32
+        lib.qiddm_probe_fp32_fma.argtypes = [i32, vp, C.POINTER(C.c_double), vp]
         for f in (lib.qiddm_qconv_gemm_saved_bytes, lib.qiddm_qconv_gemm_workspace_bytes):
             f.restype = C.c_size_t
             f.argtypes = [vp, C.POINTER(UnfoldDesc), i64]
@@ -179,6 +188,51 @@ def timing_collect() -> dict:
     ms, wk, n = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int64 * 16)()
     check(load_library().qiddm_timing_collect(ms, wk, n), "qiddm_timing_collect")
     return {k: {"ms": ms[i], "work": wk[i], "launches": int(n[i])} for i, k in enumerate(TIMING_KINDS)}
+
+
+def fp32_fma_peak_tflops(device=None, iters: int = 20000, repeats: int = 3) -> float:
+    """Measured FP32 FMA-pipe rate of this GPU (packed fma.rn.f32x2 chains, no memory traffic): the roofline denominator
+    of the gate-by-gate kernels (MEASURED_PEAKS.json holds HBM and tensor peaks only).  Best of `repeats`, CUDA events."""
+    lib = load_library()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    sink = torch.zeros(1, dtype=torch.float32, device=dev)
+    flops = C.c_double()
+    best = 0.0
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(lib.qiddm_probe_fp32_fma(iters // 10, _ptr(sink), C.byref(flops), st), "qiddm_probe_fp32_fma")
+        for _ in range(repeats):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(lib.qiddm_probe_fp32_fma(iters, _ptr(sink), C.byref(flops), st), "qiddm_probe_fp32_fma")
+            b.record()
+            b.synchronize()
+            best = max(best, flops.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+    return best
+
+
+def qconv_reference_map(img: torch.Tensor, unfold: UnfoldDesc, out_channels: int, grad_out: Optional[torch.Tensor] = None):
+    """The forward nn/qconv.py:71-90 literally executes (no circuit) or, with `grad_out`, its backward."""
+    _require_cuda(img, "input")
+    lib = load_library()
+    if img.dtype not in (torch.float32, torch.float64):
+        raise QiddmError("qconv_reference_map needs float32 / float64 images")
+    dt = DTYPE_F64 if img.dtype == torch.float64 else DTYPE_F32
+    img = img.contiguous()
+    n, c, h, w = img.shape
+    ho, wo = h + 2 * unfold.pad_h - unfold.kernel_h + 1, w + 2 * unfold.pad_w - unfold.kernel_w + 1
+    with torch.cuda.device(img.device):
+        st = C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)
+        if grad_out is None:
+            out = torch.empty((n, out_channels, ho, wo), dtype=img.dtype, device=img.device)
+            check(lib.qiddm_qconv_reference_map_forward(C.byref(unfold), dt, _ptr(img), _ptr(out), out_channels, n, st),
+                  "qiddm_qconv_reference_map_forward")
+            return out
+        go = grad_out.to(img.dtype).contiguous()
+        gi = torch.empty_like(img)
+        check(lib.qiddm_qconv_reference_map_backward(C.byref(unfold), dt, _ptr(img), _ptr(go), _ptr(gi), out_channels, n, st),
+              "qiddm_qconv_reference_map_backward")
+        return gi
 
 
 def sym_eigh(a: torch.Tensor):
@@ -225,12 +279,18 @@ class StageSpec:
     clamp_hi: float = 1.0
     path: int = PATH_AUTO
     gemm_precision: int = 3   # host-side only: 3 = fp32-grade 3-term fp16 split, 1 = single fp16 pass
+    gemm_bwd_precision: int = 0   # host-side only: precision of the dX / dW GEMMs; 0 = same as gemm_precision, 1 behind a
+                                  # precision-3 forward = "x3 forward, x1 gradients" (stated gradient bound: DESIGN.md 4.2)
 
     def to_c(self) -> CircuitDesc:
         return CircuitDesc(self.n_qubits, self.n_blocks, self.layers_per_block, self.init, self.n_features,
                            self.pad_value, self.add_offset, self.enc, self.enc_scale, self.imprimitive,
                            self.remap, self.readout, self.read_count, self.read_stride, self.post_scale,
                            int(self.clamp), self.clamp_lo, self.clamp_hi, self.path)
+
+    @property
+    def bwd_precision(self) -> int:
+        return self.gemm_bwd_precision or self.gemm_precision
 
     @property
     def dim(self) -> int:
@@ -415,33 +475,61 @@ class Plan:
         t_collapse = max(a * t_gate, n_layers * 3.5e-6) + 1.5e-4
         return batch * t_gemm + t_collapse < batch * t_gate
 
+    COLLAPSED_CACHE_ENTRIES = 8      # weight tensors per plan (layers that share a StageSpec share the plan, not U)
+
+    def invalidate(self) -> None:
+        """Drop every cached collapsed operator of this plan.  Needed after writes that do not bump the weights'
+        version counter (`p.data.copy_`, `dist.broadcast(p.data)`, ...): write through `p` under torch.no_grad(), call
+        torch.autograd.graph.increment_version(p), or call this."""
+        with self._cache_lock:
+            self._collapsed = {}
+            self._collapsed_capture = {}
+
+    @classmethod
+    def invalidate_all(cls) -> None:
+        with cls._cache_lock:
+            plans = list(cls._cache.values())
+        for p in plans:
+            p.invalidate()
+
     def gemm_prepare(self, weights: torch.Tensor) -> torch.Tensor:
-        """Collapsed operator (U^T + fp16 GEMM operands) for the current weights; cached per weights version."""
+        """Collapsed operator (U^T + fp16 GEMM operands) for the current weights; cached per weight tensor and version
+        (modules with equal StageSpecs share the Plan but not the operator: a UNet's same-shaped QConv layers keep one
+        entry each)."""
         w = self._check_weights(weights)
         # identity of the (base) tensor object + its version counter; the cache keeps a strong reference
         # to that object, so its address cannot be recycled by another tensor while the entry lives
         base = weights._base if weights._base is not None else weights
         key = (weights.storage_offset(), weights.numel(), weights._version, w.data_ptr())
-        cached = getattr(self, "_collapsed", None)
         # under CUDA-graph capture the collapse must be part of the graph (replays do not bump `_version`), and the
         # buffer belongs to the graph's pool: neither read nor update the eager cache
         dev = w.device
         capture = int(self.lib.qiddm_stream_capture_id(self._stream(dev)))
-        if capture:
-            key = key + (capture,)
-            cached = getattr(self, "_collapsed_capture", None)
-        if cached is not None and cached[0] is base and cached[1] == key:
-            return cached[2]
+        slot = (id(base), weights.storage_offset(), weights.numel())
+        with self._cache_lock:
+            if not isinstance(getattr(self, "_collapsed", None), dict):
+                self._collapsed, self._collapsed_capture = {}, {}
+            cache = self._collapsed_capture if capture else self._collapsed
+            if capture:
+                key = key + (capture,)
+            cached = cache.get(slot)
+            if cached is not None and cached[0] is base and cached[1] == key:
+                cache[slot] = cache.pop(slot)          # most recently used last
+                return cached[2]
         buf = torch.empty(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
         ws = self._workspace(self.spec.dim, dev)
         with torch.cuda.device(dev):
             check(self.lib.qiddm_gemm_prepare(self.handle, _ptr(w), _wdtype(w), _ptr(buf), _ptr(ws),
                                               self._stream(dev)), "qiddm_gemm_prepare")
-        if capture:
-            self._collapsed_capture = (base, key, buf)
-        else:
-            self._collapsed = (base, key, buf)
+        with self._cache_lock:
+            cache.pop(slot, None)
+            cache[slot] = (base, key, buf)
+            while len(cache) > self.COLLAPSED_CACHE_ENTRIES:
+                cache.pop(next(iter(cache)))
+        Plan.collapse_count += 1
         return buf
+
+    collapse_count = 0       # qiddm_gemm_prepare calls issued by this process (tests: one collapse per layer and step)
 
     def _gemm_ws(self, batch, dev):
         with torch.cuda.device(dev):
@@ -463,8 +551,8 @@ class Plan:
                                     device=dev)
                 ws = torch.empty(256, dtype=torch.uint8, device=dev)
             else:
-                kp = (self.spec.n_features + 1 + 7) // 8 * 8
-                ws = torch.empty(3 * (batch * kp * 2 + 256) + batch * 4 + 512, dtype=torch.uint8, device=dev)
+                ws = torch.empty(int(self.lib.qiddm_gemm_forward_workspace_bytes(self.handle, batch)), dtype=torch.uint8,
+                                 device=dev)
             check(self.lib.qiddm_gemm_forward(self.handle, _ptr(col), _ptr(x), _ptr(out), _ptr(saved), _ptr(ws),
                                               batch, self.spec.gemm_precision, self._stream(dev)),
                   "qiddm_gemm_forward")
@@ -484,7 +572,7 @@ class Plan:
         with torch.cuda.device(dev):
             check(self.lib.qiddm_gemm_backward(self.handle, _ptr(col), _ptr(x), _ptr(w), _wdtype(w), _ptr(go),
                                                _ptr(saved), _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
-                                               self.spec.gemm_precision, self._stream(dev)), "qiddm_gemm_backward")
+                                               self.spec.bwd_precision, self._stream(dev)), "qiddm_gemm_backward")
         return grad_in, grad_w
 
     # ------------------------------------------------------------------ QConv on the unitary-collapse path
@@ -537,7 +625,7 @@ class Plan:
             check(self.lib.qiddm_qconv_gemm_backward(self.handle, _ptr(col), C.byref(unfold),
                                                      DTYPE_F64 if io == torch.float64 else DTYPE_F32, _ptr(img), _ptr(w),
                                                      _wdtype(w), _ptr(go), _ptr(saved), _ptr(grad_img), _ptr(grad_w),
-                                                     _ptr(ws), n, self.spec.gemm_precision, self._stream(dev)),
+                                                     _ptr(ws), n, self.spec.bwd_precision, self._stream(dev)),
                   "qiddm_qconv_gemm_backward")
         return grad_img, grad_w
 

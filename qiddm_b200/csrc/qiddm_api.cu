@@ -348,6 +348,12 @@ int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_
     return gemm_build_operands(g, gp, collapsed, (cudaStream_t)stream);
 }
 
+size_t qiddm_gemm_forward_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
+    if (!plan || !gemm_eligible(plan) || batch < 0) return 0;
+    GateParams gp = make_params(plan, nullptr, 1);
+    return gemm_forward_ws_bytes(gemm_shape(gp, plan->d.n_qubits), batch > 0 ? batch : 1) + 256;
+}
+
 size_t qiddm_gemm_saved_bytes(const qiddm_plan *plan, int64_t batch) {
     if (!plan || !gemm_eligible(plan) || batch < 0) return 0;
     GateParams gp = make_params(plan, nullptr, 1);
@@ -561,6 +567,23 @@ int64_t qiddm_stream_capture_id(qiddm_stream_t stream) {
         return 0;
     }
     return st == cudaStreamCaptureStatusActive ? (int64_t)id : 0;
+}
+
+int qiddm_qconv_reference_map_forward(const qiddm_unfold_desc *u, int dtype, const void *img, void *out, int out_channels,
+                                      int64_t n_images, qiddm_stream_t stream) {
+    if (!u) return QIDDM_EINVAL;
+    return qiddm::qconv_reference_map(img, nullptr, out, dtype, false, n_images, u->channels, u->height, u->width, u->kernel_h,
+                                      u->kernel_w, u->pad_h, u->pad_w, out_channels, (cudaStream_t)stream);
+}
+int qiddm_qconv_reference_map_backward(const qiddm_unfold_desc *u, int dtype, const void *img, const void *grad_out,
+                                       void *grad_img, int out_channels, int64_t n_images, qiddm_stream_t stream) {
+    if (!u) return QIDDM_EINVAL;
+    return qiddm::qconv_reference_map(img, grad_out, grad_img, dtype, true, n_images, u->channels, u->height, u->width,
+                                      u->kernel_h, u->kernel_w, u->pad_h, u->pad_w, out_channels, (cudaStream_t)stream);
+}
+
+int qiddm_probe_fp32_fma(int iters, float *sink, double *flops, qiddm_stream_t stream) {
+    return qiddm::probe_fp32_fma(iters, sink, flops, (cudaStream_t)stream);
 }
 
 int64_t qiddm_launch_count(void) { return (int64_t)qiddm::g_launches.load(std::memory_order_relaxed); }

@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include "qiddm_internal.h"
@@ -1500,12 +1501,13 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         if (a_mn) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64> : gemm_pair_kernel<1, true, 64>;
         else if (bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, false, 32> : gemm_pair_kernel<1, false, 32>;
         else kern = n_seg > 1 ? gemm_pair_kernel<3, false, 64> : gemm_pair_kernel<1, false, 64>;
-        static bool attr_set2[6] = {false, false, false, false, false, false};
+        // the opt-in shared-memory limit of a function is per device: remembered per (device, instantiation)
+        static std::atomic<bool> attr_set2[64][6];
         const int ki = (n_seg > 1 ? 3 : 0) + (a_mn ? 2 : (bkt == 32 ? 1 : 0));
-        if (!attr_set2[ki]) {
+        if (!attr_set2[dev & 63][ki].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;
-            attr_set2[ki] = true;
+            attr_set2[dev & 63][ki].store(true, std::memory_order_release);
         }
         const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + p.bn - 1) / p.bn) * k_splits;
         const int pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
@@ -1529,11 +1531,11 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         if (stages < 2) stages = 2;
         p.stages = stages;
         const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<bool> attr_set[64];
+        if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;
-            attr_set = true;
+            attr_set[dev & 63].store(true, std::memory_order_release);
         }
         const long long tiles = (long long)((M + BM - 1) / BM) * ((N + p.bn - 1) / p.bn) * k_splits;
         const int grid = (int)(tiles < sms ? tiles : sms);
@@ -1736,14 +1738,8 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         int rc0 = gemm_forward(g, gp, collapsed, x, nullptr, saved_buf, nullptr, B, n_seg, s);
         if (rc0 != QIDDM_OK) return rc0;
     }
-    {
-        // EXPERIMENTAL, off by default (QIDDM_GEMM_BWD_X1=1): single-pass gradient GEMMs behind the fp32-grade forward.  CPU
-        // emulation (scripts/emulate_split_accuracy.py): weight-gradient error 3.3e-4 rel-to-max instead of 7e-8, dX + dW at a
-        // third of the MMA work.  Not yet parity-tested on the GPU.
-        static int bwd_x1 = -1;
-        if (bwd_x1 < 0) { const char *ev = getenv("QIDDM_GEMM_BWD_X1"); bwd_x1 = ev ? atoi(ev) : 0; }
-        if (bwd_x1) n_seg = 1;
-    }
+    // n_seg here may be 1 behind an n_seg = 3 forward ("x3 forward, x1 gradients": the saved Y and X splits are fp32-grade, only
+    // the dX / dW GEMMs run single-pass; stated gradient bound in DESIGN.md 4.2)
     p8 += gemm_saved_bytes(g, B);
     SavedView w = saved_view(g, B, saved_buf, true);
     float *S = reinterpret_cast<float *>(p8); p8 += al((size_t)B * 4);

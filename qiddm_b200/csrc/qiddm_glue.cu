@@ -307,6 +307,61 @@ __global__ void __launch_bounds__(256) prob_channel_kernel(const T *p_in, T *p_o
     for (int k = threadIdx.x; k < A; k += blockDim.x) dst[k] = (T)ch_sm[k];
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The forward the reference's `_QConv2d_FAST` ACTUALLY executes (nn/qconv.py:71-90; SURVEY.md H1: the QNode is never
+// called): unfold -> +0.1 -> * F * 0.5 -> clamp(0, 1) -> [:, ::2] -> [:, :out_channels], F = C kh kw.  Output channel j is
+// the patch feature 2j = (ch, ky, kx) -- one pixel per output element, so the map and its gradient are gathers.
+// ------------------------------------------------------------------------------------------------------------------
+struct RefMapGeom {
+    int C, H, W, kh, kw, ph, pw, Hout, Wout, n_ch_out;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) qconv_refmap_fwd_kernel(const T *img, T *out, long long total, RefMapGeom g) {
+    const int kk = g.kh * g.kw;
+    const T F = (T)(g.C * kk);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % g.Wout);
+        long long t = i / g.Wout;
+        const int y = (int)(t % g.Hout);
+        t /= g.Hout;
+        const int j = (int)(t % g.n_ch_out);
+        const long long b = t / g.n_ch_out;
+        const int f = 2 * j, ch = f / kk, r = f - ch * kk, ky = r / g.kw, kx = r - ky * g.kw;
+        const int iy = y + ky - g.ph, ix = x + kx - g.pw;
+        T v = (T)0;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = img[((b * g.C + ch) * g.H + iy) * g.W + ix];
+        v = (v + (T)0.1) * F * (T)0.5;
+        out[i] = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+    }
+}
+// grad_img[b,ch,iy,ix] = mask(pixel) * F/2 * sum over the retained features (ch,ky,kx) = 2j of grad_out[b,j,iy-ky+ph,ix-kx+pw]
+template <typename T>
+__global__ void __launch_bounds__(256) qconv_refmap_bwd_kernel(const T *img, const T *gout, T *gimg, long long total,
+                                                               RefMapGeom g) {
+    const int kk = g.kh * g.kw;
+    const T F = (T)(g.C * kk);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % g.W);
+        long long t = i / g.W;
+        const int iy = (int)(t % g.H);
+        t /= g.H;
+        const int ch = (int)(t % g.C);
+        const long long b = t / g.C;
+        T acc = (T)0;
+        for (int r = 0; r < kk; ++r) {
+            const int f = ch * kk + r;
+            if ((f & 1) || (f >> 1) >= g.n_ch_out) continue;
+            const int ky = r / g.kw, kx = r - ky * g.kw;
+            const int y = iy - ky + g.ph, x = ix - kx + g.pw;
+            if (y < 0 || y >= g.Hout || x < 0 || x >= g.Wout) continue;
+            acc += gout[((b * g.n_ch_out + (f >> 1)) * g.Hout + y) * g.Wout + x];
+        }
+        const T v = (img[i] + (T)0.1) * F * (T)0.5;
+        // zero-padding pixels feed outputs too, but carry no gradient to the image
+        gimg[i] = (v >= (T)0 && v <= (T)1) ? acc * F * (T)0.5 : (T)0;
+    }
+}
+
 inline unsigned ew_grid(long long total) {
     const long long b = (total + 255) / 256;
     return (unsigned)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
@@ -399,6 +454,67 @@ int prob_channel(const void *p_in, void *p_out, int dtype, long long batch, int 
                                                                            reinterpret_cast<float *>(p_out), n, m00, m01, m10, m11);
     else
         return QIDDM_EINVAL;
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+// FP32 FMA-pipe probe (the roofline denominator of the gate kernels, which MEASURED_PEAKS.json does not hold): every thread
+// runs 8 independent packed-FMA chains, `iters` rounds of 16 fma.rn.f32x2 = 64 flop per round; no memory traffic.
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float *sink, int iters, float a, float b) {
+    float2 x[8], y[8];
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = make_float2(threadIdx.x * 1e-3f + i, (float)i); y[i] = make_float2(i * 0.5f, 1.f); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i] = __ffma2_rn(a2, x[i], y[i]); y[i] = __ffma2_rn(b2, y[i], x[i]); }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y + y[i].x + y[i].y;
+    if (s == 1.2345e-30f) sink[0] = s;          // never true: keeps the chains alive without a store per thread
+}
+int probe_fp32_fma(int iters, float *sink, double *flops, cudaStream_t s) {
+    if (iters < 1 || !sink) return QIDDM_EINVAL;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return QIDDM_ENODEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 8;
+    fp32_probe_kernel<<<grid, 256, 0, s>>>(sink, iters, 0.999f, 1.001f);
+    count_launch();
+    if (flops) *flops = (double)grid * 256.0 * (double)iters * 64.0;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+int qconv_reference_map(const void *img, const void *grad_out, void *out, int dtype, bool backward, long long n_images, int C,
+                        int H, int W, int kh, int kw, int ph, int pw, int n_ch_out, cudaStream_t s) {
+    if (!img || !out || n_images < 0 || C < 1 || H < 1 || W < 1 || kh < 1 || kw < 1 || ph < 0 || pw < 0) return QIDDM_EINVAL;
+    if (backward && !grad_out) return QIDDM_EINVAL;
+    RefMapGeom g{C, H, W, kh, kw, ph, pw, H + 2 * ph - kh + 1, W + 2 * pw - kw + 1, n_ch_out};
+    if (g.Hout < 1 || g.Wout < 1 || n_ch_out < 1 || 2 * (n_ch_out - 1) >= C * kh * kw) return QIDDM_EINVAL;
+    if (n_images == 0) return QIDDM_OK;
+    const long long total = backward ? n_images * C * H * W : n_images * n_ch_out * g.Hout * g.Wout;
+    if (dtype == QIDDM_DTYPE_F64) {
+        if (backward)
+            qconv_refmap_bwd_kernel<double><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const double *>(img),
+                                                                          reinterpret_cast<const double *>(grad_out),
+                                                                          reinterpret_cast<double *>(out), total, g);
+        else
+            qconv_refmap_fwd_kernel<double><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const double *>(img),
+                                                                          reinterpret_cast<double *>(out), total, g);
+    } else if (dtype == QIDDM_DTYPE_F32) {
+        if (backward)
+            qconv_refmap_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float *>(img),
+                                                                         reinterpret_cast<const float *>(grad_out),
+                                                                         reinterpret_cast<float *>(out), total, g);
+        else
+            qconv_refmap_fwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float *>(img),
+                                                                         reinterpret_cast<float *>(out), total, g);
+    } else {
+        return QIDDM_EINVAL;
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;

@@ -79,6 +79,9 @@ int sym_eigh_f64(const double *A, int m, long long count, double *evals, double 
 // qiddm_glue.cu — UNet glue around QConv2d: bilinear resize (align_corners = False) and BatchNorm2d (NCHW)
 size_t batchnorm_ws_bytes(int C);
 size_t mse_ws_bytes();
+int qconv_reference_map(const void *img, const void *grad_out, void *out, int dtype, bool backward, long long n_images, int C,
+                        int H, int W, int kh, int kw, int ph, int pw, int n_ch_out, cudaStream_t s);
+int probe_fp32_fma(int iters, float *sink, double *flops, cudaStream_t s);
 int prob_channel(const void *p_in, void *p_out, int dtype, long long batch, int n, double m00, double m01, double m10, double m11,
                  cudaStream_t s);
 int noise_ladder(const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau, void *noisy,

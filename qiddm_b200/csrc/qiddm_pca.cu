@@ -6,6 +6,7 @@
 // and no status read-back, so the whole training / sampling step stays capturable in a CUDA graph.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <atomic>
 #include "qiddm_internal.h"
 
 namespace qiddm {
@@ -151,11 +152,14 @@ int sym_eigh_f64(const double *A, int m, long long count, double *evals, double 
     if (count == 0) return QIDDM_OK;
     const size_t smem = eigh_smem_bytes(m);
     if (smem > 227 * 1024) return QIDDM_EUNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in shared-memory limit of a function is per device
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return QIDDM_ENODEVICE;
+    if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set[dev & 63].store(true, std::memory_order_release);
     }
     // threads ~ the m/2 x m/2 block updates of a round: small matrices (m = tau = 10) use two warps, large ones all 16
     const int work = ((m + 1) / 2) * m;

@@ -98,5 +98,28 @@ def run_qconv(spec: StageSpec, img: torch.Tensor, weights: torch.Tensor, kernel_
     return _QConvFunction.apply(Plan.get(spec), img, weights, unfold)
 
 
+class _QConvReferenceMap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img: torch.Tensor, unfold: UnfoldDesc, out_channels: int):
+        from ._lib import qconv_reference_map
+        ctx.unfold, ctx.out_channels = unfold, out_channels
+        ctx.save_for_backward(img)
+        return qconv_reference_map(img.detach(), unfold, out_channels)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from ._lib import qconv_reference_map
+        (img,) = ctx.saved_tensors
+        return qconv_reference_map(img.detach(), ctx.unfold, ctx.out_channels, grad_out=grad_out), None, None
+
+
+def run_qconv_reference_map(img: torch.Tensor, kernel_size, padding, out_channels: int) -> torch.Tensor:
+    """What `_QConv2d_FAST.forward` literally computes in the reference (nn/qconv.py:71-90; the circuit is never called)."""
+    n, c, h, w = img.shape
+    unfold = UnfoldDesc(c, h, w, kernel_size[0], kernel_size[1], padding[0], padding[1])
+    n_ch = min(out_channels, (c * kernel_size[0] * kernel_size[1] + 1) // 2)
+    return _QConvReferenceMap.apply(img, unfold, n_ch)
+
+
 def build_unitary(spec: StageSpec, weights: torch.Tensor) -> torch.Tensor:
     return Plan.get(spec).build_unitary(weights.detach())

@@ -10,19 +10,27 @@ weight version, every patch one row of a tcgen05 GEMM with the unfold fused into
 from __future__ import annotations
 
 import math
+import os
 import warnings
 
 import torch
 
 from .. import _lib as L
-from ..functional import build_unitary, run_qconv, run_stage
+from ..functional import build_unitary, run_qconv, run_qconv_reference_map, run_stage
+
+# `reference_forward=True` (or QIDDM_QCONV_REFERENCE_FORWARD=1): reproduce what the reference's forward LITERALLY computes --
+# unfold -> +0.1 -> * F * 0.5 -> clamp -> [::2] -> [:out_channels], no circuit (nn/qconv.py:71-90) -- which is the map every
+# QConv checkpoint of the reference was trained through (its `weights` never received a gradient).  Default: the intended
+# circuit forward (H1).
+REFERENCE_FORWARD_DEFAULT = os.environ.get("QIDDM_QCONV_REFERENCE_FORWARD", "0").lower() in ("1", "true", "yes")
 
 
 class _QConv2d_FAST(torch.nn.Module):
     """Fastest version of QConv2d.  nn/qconv.py:8-126."""
 
-    def __init__(self, in_channels, out_channels, kernel_size=(3, 3), padding=1, qdepth=2):
+    def __init__(self, in_channels, out_channels, kernel_size=(3, 3), padding=1, qdepth=2, reference_forward=None):
         super().__init__()
+        self.reference_forward = REFERENCE_FORWARD_DEFAULT if reference_forward is None else bool(reference_forward)
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.kernel_size = kernel_size if isinstance(kernel_size, tuple) else (kernel_size, kernel_size)
@@ -60,7 +68,18 @@ class _QConv2d_FAST(torch.nn.Module):
     def forward(self, x):
         b, c, h_in, w_in = x.shape
         assert c == self.in_channels, f"Expected {self.in_channels} channels, got {c}"
+        if self.reference_forward:
+            return run_qconv_reference_map(x, self.kernel_size, self.padding, self.out_channels)
         return run_qconv(self._spec(), x, self.weights, self.kernel_size, self.padding)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        if prefix + "weights" in state_dict and not self.reference_forward:
+            warnings.warn(
+                "QConv2d: loading circuit weights into the circuit forward (H1).  Checkpoints written by the reference were "
+                "trained through its literal forward, which never calls the circuit (nn/qconv.py:71-90): their `weights` are "
+                "the untrained initial draw.  Pass reference_forward=True (or QIDDM_QCONV_REFERENCE_FORWARD=1) to reproduce "
+                "the reference's outputs for such a checkpoint.", stacklevel=2)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def __repr__(self):
         return (f"QConv2d({self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "

@@ -17,9 +17,10 @@ Deliberate deviations:
 """
 from __future__ import annotations
 
+import ast
 import math
+import operator
 import os
-import pickle
 
 import einops
 import torch
@@ -84,6 +85,31 @@ def _check_noise(add_noise, allow_phase: bool, readout_channels: bool = False):
         "state-vector path (SURVEY.md 8f-4); channels right before a probability readout are supported")
 
 
+# The reference cuts the gradient at every lightning.qubit result (`torch.tensor(qnode(...))`), so there only
+# `linear_up` trains.  Default here: the TRUE gradient (adjoint kernels; BASELINE.json north_star (d)).  QIDDM_REFERENCE_GRADIENTS=1
+# (or `module.detach_quantum = True`, or the class attribute) restores the reference's cut gradient for every class that
+# detaches upstream, for runs that must reproduce the recorded training curves with the reference's hyper-parameters.
+REFERENCE_GRADIENTS = os.environ.get("QIDDM_REFERENCE_GRADIENTS", "0").lower() in ("1", "true", "yes")
+
+_ARITH = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.FloorDiv: operator.floordiv,
+          ast.Pow: operator.pow}
+
+
+def _parse_int_expr(text: str) -> int:
+    """"28 * 28" -> 784 (nn/qdense.py:222-223 uses eval() on the driver's model_params string): integer arithmetic only."""
+    def ev(node):
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant) and isinstance(node.value, int):
+            return node.value
+        if isinstance(node, ast.BinOp) and type(node.op) in _ARITH:
+            return _ARITH[type(node.op)](ev(node.left), ev(node.right))
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, ast.USub):
+            return -ev(node.operand)
+        raise ValueError(f"input_dim {text!r}: only integer arithmetic (+ - * // **) is accepted")
+    return int(ev(ast.parse(text.strip(), mode="eval")))
+
+
 def _shape2(shape):
     return (shape, shape) if isinstance(shape, int) else tuple(shape)
 
@@ -102,7 +128,8 @@ class _SaveLoadMixin:
         torch.save({"model_state_dict": self.state_dict(), "loss_values": loss_values, "epochs": epochs}, path)
 
     def load_model(self, path):
-        checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+        # the reference's checkpoints hold a state_dict plus lists / ints: no pickled code is needed to read them
+        checkpoint = torch.load(path, map_location="cpu", weights_only=True)
         self.load_state_dict(checkpoint["model_state_dict"])
 
 
@@ -238,11 +265,11 @@ class QNN_A(nn.Module):
 # a5 — linear_down + RZ + SEL(CZ) + <Z> + linear_up       nn/qdense.py:219-386
 # ======================================================================================
 class _QNNBase(_SaveLoadMixin, nn.Module):
-    detach_quantum = False
+    detach_quantum = REFERENCE_GRADIENTS
 
     def _setup(self, input_dim, hidden_features, qdepth):
         if isinstance(input_dim, str):
-            input_dim = eval(input_dim)  # "28 * 28" -> 784, as nn/qdense.py:222-223
+            input_dim = _parse_int_expr(input_dim)  # "28 * 28" -> 784, as nn/qdense.py:222-223
         self.hidden_features = hidden_features
         self.qdepth = qdepth
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
@@ -335,7 +362,7 @@ class _DifferNBase(nn.Module):
     _post_each_stage = False   # per-sample variants post-process between stages (:813-817)
     _shared_weights = False    # QIDDM_A_sameN
     _weight_name = "weights"
-    detach_quantum = False
+    detach_quantum = False     # the batched default.qubit.torch classes train through the circuit in the reference too
 
     def _setup(self, shape, spectrum_layer, N):
         self.spectrum_layer = spectrum_layer
@@ -405,6 +432,8 @@ class _DifferNBase(nn.Module):
 
     def forward(self, x):
         b, c, w, h = x.shape
+        if not getattr(self, "_readout_noise", False):      # read per call: src/mnist_noise.py:218 flips it on a trained net
+            _check_noise(getattr(self, "add_noise", 0), allow_phase=False)
         probs = self._chain(self._angles(x))
         return einops.rearrange(probs, "b (w h) -> b 1 w h", w=self.width, h=self.height).to(x.dtype)
 
@@ -535,6 +564,7 @@ class _QIDDM_A_differN(_SaveLoadMixin, _DifferNBase):
     _enc_scale = math.pi * 0.5
     _post_each_stage = True
     _weight_name = "weights1"
+    detach_quantum = REFERENCE_GRADIENTS       # per-sample lightning.qubit classes: nn/qdense.py:2246, :2409
 
     def __init__(self, input_dim, spectrum_layer, N: int) -> None:
         super().__init__()
@@ -570,7 +600,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
     _layers = 2
     _bias = True
     _repr_name = "QIDDM"
-    detach_quantum = False
+    detach_quantum = REFERENCE_GRADIENTS
 
     def _setup(self, input_dim, hidden_features, spectrum_layer, N):
         self.hidden_features = hidden_features
@@ -608,8 +638,14 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
     def _between_stages(self, a):
         return a
 
+    def _check_noise_at_call(self):
+        """`add_noise` is flipped on trained nets at test time (src/mnist_noise.py:218): read it per call, never serve a
+        noiseless result for a noisy request."""
+        _check_noise(getattr(self, "add_noise", 0), allow_phase=False)
+
     def forward(self, x):
         b, c, w, h = x.shape
+        self._check_noise_at_call()
         a = self._reduce_input(x)
         for n in range(self.N):
             a = self._between_stages(a)
@@ -700,8 +736,9 @@ class QIDDM_CL_new(_QIDDMExpvalPlain):
 
 
 class QIDDM_CL_old(_QIDDMExpvalPlain):
-    """nn/qdense.py:1104-1173."""
+    """nn/qdense.py:1104-1173 (no re-wrap of the QNode result there: the gradient is not cut)."""
     _reduce = "conv"
+    detach_quantum = False
 
     def save_name(self) -> str:
         return f"QIDDM_CL_old_q={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
@@ -709,8 +746,9 @@ class QIDDM_CL_old(_QIDDMExpvalPlain):
 
 class QIDDM_PL_old(_QIDDMExpvalPlain):
     """nn/qdense.py:1176-1268 (the reference passes the whole batch flattened, which only runs at
-    batch 1; evaluated per sample here)."""
+    batch 1; evaluated per sample here; no re-wrap of the QNode result: the gradient is not cut)."""
     _reduce = "pca"
+    detach_quantum = False
 
     def save_name(self) -> str:
         return f"QIDDM_PL_old_q={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
@@ -743,6 +781,7 @@ class QIDDM_L_B(_QIDDMExpvalPlain):
     """BatchNorm1d before every stage, 3-layer SEL blocks.  nn/qdense.py:2077-2179 (the reference
     instantiates default.qubit.jax with interface torch — dead code)."""
     _layers, _repr_name = 3, "QIDDM_L_B"
+    detach_quantum = False          # backprop device in the reference: trains through the circuit
 
     def __init__(self, input_dim, hidden_features, spectrum_layer, N: int) -> None:
         super().__init__(input_dim, hidden_features, spectrum_layer, N)
@@ -798,16 +837,23 @@ class QIDDM_PP_old(nn.Module):
         return f"QIDDM_PP_features={self.hidden_features}_L={self.spectrum_layer}_N={self.N}"
 
     def save_model(self, path):
+        # the fitted PCA travels as plain tensors (mean_, components_, ...), not as a pickle (nn/qdense.py:1852-1870 pickles it)
         model_dict = {"model_state_dict": self.state_dict()}
         if self.pca is not None:
-            model_dict["pca_state"] = pickle.dumps(self.pca)
+            model_dict["pca_state"] = {k: torch.as_tensor(getattr(self.pca, k)).detach().cpu()
+                                       for k in ("mean_", "components_", "singular_values_", "explained_variance_")
+                                       if getattr(self.pca, k, None) is not None}
         torch.save(model_dict, path)
 
     def load_model(self, path):
-        checkpoint = torch.load(path, map_location="cpu", weights_only=False)
+        checkpoint = torch.load(path, map_location="cpu", weights_only=True)
         self.load_state_dict(checkpoint["model_state_dict"])
         if "pca_state" in checkpoint:
-            self.pca = pickle.loads(checkpoint["pca_state"])
+            state = checkpoint["pca_state"]
+            self.pca = _make_pca(2 * self.hidden_features)
+            dev = self.linear_down.weight.device
+            for k, v in state.items():
+                setattr(self.pca, k, v.to(dev) if isinstance(self.pca, DevicePCA) else v.numpy())
 
 
 __all__ = [

@@ -129,11 +129,13 @@ class DataParallelTrainer:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
 
     def broadcast_parameters(self, src: int = 0) -> None:
+        # through `p.detach()`, not `p.data`: the detached alias shares the version counter, so the in-place write
+        # invalidates version-keyed caches (the collapsed operator of the GEMM path)
         if self.world > 1:
             for p in self.diff.parameters():
-                dist.broadcast(p.data, src)
+                dist.broadcast(p.detach(), src)
             for b in self.diff.buffers():
-                dist.broadcast(b.data, src)
+                dist.broadcast(b.detach(), src)
 
     def step(self, x_global: torch.Tensor, already_sharded: bool = False) -> torch.Tensor:
         x = x_global if already_sharded else shard_batch(x_global, self.rank, self.world)

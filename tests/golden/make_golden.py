@@ -13,6 +13,10 @@
   images the reference saved next to it (8-bit PNGs) (`python make_golden.py f3_qw_map`).
 * f3_qiddm_pl_logo_sanyo.pt — the same kind of fixture for family a4: QIDDM_PL_noise(784,8,6,2), recorded losses, training
   images (`python make_golden.py f3_qiddm_pl`).
+* ref_qconv_literal_forward.pt — OUTPUTS OF THE REFERENCE'S OWN CODE: `/root/reference/nn/qconv.py::_QConv2d_FAST` imported with
+  stub `pennylane` / `qw_map` modules (its forward never calls the QNode, nn/qconv.py:71-90, so the stubs are never executed)
+  and run on seeded float64 images: forward outputs and autograd image gradients for five layer shapes
+  (`python make_golden.py ref_qconv`).  Pins the `reference_forward=True` mode of the product's QConv2d.
 * f2_state_dict_contract.json — key names / shapes / dtypes of every shipped checkpoint family (F2).
 * stage_vectors.pt — oracle outputs and gradients for seeded inputs of each circuit family.
 """
@@ -106,7 +110,45 @@ def f3_qiddm_pl():
                OUT / "f3_qiddm_pl_logo_sanyo.pt")
 
 
+def ref_qconv():
+    """Run the reference's literal `_QConv2d_FAST.forward` (torch + einops only; PennyLane is stubbed, never executed)."""
+    import importlib.util
+    import types
+    qml = types.ModuleType("pennylane")
+
+    class _SEL:
+        @staticmethod
+        def shape(n_layers, n_wires):
+            return (n_layers, n_wires, 3)
+
+    qml.StronglyEntanglingLayers = _SEL
+    qml.device = lambda *a, **k: object()
+    qml.QNode = lambda *a, **k: (lambda *aa, **kk: (_ for _ in ()).throw(RuntimeError("stub QNode executed")))
+    sys.modules.setdefault("pennylane", qml)
+    sys.modules.setdefault("qw_map", types.ModuleType("qw_map"))
+    spec = importlib.util.spec_from_file_location("ref_qconv", REF / "nn/qconv.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = {}
+    for i, (cin, cout, k, pad, hw) in enumerate([(1, 8, 3, 1, (7, 6)), (8, 8, 3, 1, (6, 6)), (4, 1, 1, 0, (5, 5)),
+                                                   (3, 4, (3, 2), (1, 0), (6, 7)), (16, 8, 3, 1, (4, 4))]):
+        g = torch.Generator().manual_seed(500 + i)
+        layer = mod._QConv2d_FAST(cin, cout, kernel_size=k, padding=pad, qdepth=2)
+        x = (torch.rand(2, cin, *hw, generator=g, dtype=torch.float64) * 0.4 - 0.1).requires_grad_(True)   # spans both clamp edges
+        out = layer(x)
+        go = torch.randn(out.shape, generator=g, dtype=torch.float64)
+        (out * go).sum().backward()
+        cases[f"in{cin}_out{cout}_k{k}_p{pad}"] = {"args": (cin, cout, k, pad), "x": x.detach().clone(), "out": out.detach(),
+                                                   "grad_out": go, "grad_x": x.grad.clone()}
+    torch.save({"cases": cases, "source": "/root/reference/nn/qconv.py::_QConv2d_FAST.forward (:71-90), pennylane/qw_map stubbed"},
+               OUT / "ref_qconv_literal_forward.pt")
+    print({k: tuple(v["out"].shape) for k, v in cases.items()})
+
+
 def main():
+    if sys.argv[1:] == ["ref_qconv"]:
+        ref_qconv()
+        return
     if sys.argv[1:] == ["f3_qw_map"]:
         f3_qw_map()
         return
@@ -124,6 +166,7 @@ def main():
     f1_unet(z)
     f3_qw_map()
     f3_qiddm_pl()
+    ref_qconv()
     # ---- F1 a1: QDenseUndirected_old_noise(60, 28), label 14 ("O")
     ck = load_ck(z, "emnist14/noise_0/QDenseUndirected_old_noise60_w28_h28_noise0_noise_14.pt")
     W = ck["model_state_dict"]["net.weights"]
