@@ -108,6 +108,16 @@ int qiddm_backward(const qiddm_plan *plan, const float *in, const int32_t *basis
                    int weights_dtype, const float *grad_out, float *grad_in, void *grad_weights,
                    void *workspace, int64_t batch, qiddm_stream_t stream);
 
+/* The same pair with the final states kept between them: `state` (qiddm_state_bytes(plan, batch) = batch * 2^n complex fp32)
+ * is WRITTEN by the forward and READ by the backward, whose adjoint sweep then starts from psi_final instead of recomputing
+ * the forward sweep (20-25 % of its time).  `state` may be NULL (= the plain calls). */
+size_t qiddm_state_bytes(const qiddm_plan *plan, int64_t batch);
+int qiddm_forward_save(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                       int weights_dtype, float *out, float *state, void *workspace, int64_t batch, qiddm_stream_t stream);
+int qiddm_backward_saved(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                         int weights_dtype, const float *grad_out, const float *state, float *grad_in, void *grad_weights,
+                         void *workspace, int64_t batch, qiddm_stream_t stream);
+
 /* QConv: same circuit with the patch-unfold fused.  img (n_images, C, H, W) fp32; out
  * (n_images, read_count, H_out, W_out) fp32; grad_img is OVERWRITTEN (col2im accumulated inside). */
 int qiddm_qconv_forward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, const float *img,

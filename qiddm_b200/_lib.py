@@ -4,6 +4,7 @@ or a non-CUDA tensor raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from pathlib import Path
@@ -55,6 +56,7 @@ EXPORTS = [
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
     "qiddm_readout_channel", "qiddm_gemm_forward_workspace_bytes", "qiddm_probe_fp32_fma",
     "qiddm_qconv_reference_map_forward", "qiddm_qconv_reference_map_backward",
+    "qiddm_state_bytes", "qiddm_forward_save", "qiddm_backward_saved",
 ]
 
 _lib = None
@@ -94,6 +96,12 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_forward.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp]
         lib.qiddm_backward.restype = i32
         lib.qiddm_backward.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp]
+        lib.qiddm_state_bytes.restype = C.c_size_t
+        lib.qiddm_state_bytes.argtypes = [vp, i64]
+        lib.qiddm_forward_save.restype = i32
+        lib.qiddm_forward_save.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
+        lib.qiddm_backward_saved.restype = i32
+        lib.qiddm_backward_saved.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i64, vp]
         lib.qiddm_qconv_forward.restype = i32
         lib.qiddm_qconv_forward.argtypes = [vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, i64, vp]
         lib.qiddm_qconv_backward.restype = i32
@@ -190,9 +198,11 @@ def timing_collect() -> dict:
     return {k: {"ms": ms[i], "work": wk[i], "launches": int(n[i])} for i, k in enumerate(TIMING_KINDS)}
 
 
-def fp32_fma_peak_tflops(device=None, iters: int = 20000, repeats: int = 3) -> float:
+def fp32_fma_peak_tflops(device=None, sustained: bool = False) -> float:
     """Measured FP32 FMA-pipe rate of this GPU (packed fma.rn.f32x2 chains, no memory traffic): the roofline denominator
-    of the gate-by-gate kernels (MEASURED_PEAKS.json holds HBM and tensor peaks only).  Best of `repeats`, CUDA events."""
+    of the gate-by-gate kernels (MEASURED_PEAKS.json holds HBM and tensor peaks only).  Default = burst: best of five
+    ~0.7 ms launches (the figure for a kernel timed alone; ~74 TFLOP/s = 148 SMs x 128 lanes x 2 x 1.965 GHz);
+    sustained=True: one ~50 ms launch, which runs into the 1 kW power cap (~57 TFLOP/s)."""
     lib = load_library()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     sink = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -200,11 +210,11 @@ def fp32_fma_peak_tflops(device=None, iters: int = 20000, repeats: int = 3) -> f
     best = 0.0
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        check(lib.qiddm_probe_fp32_fma(iters // 10, _ptr(sink), C.byref(flops), st), "qiddm_probe_fp32_fma")
-        for _ in range(repeats):
+        check(lib.qiddm_probe_fp32_fma(500, _ptr(sink), C.byref(flops), st), "qiddm_probe_fp32_fma")
+        for _ in range(1 if sustained else 5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            check(lib.qiddm_probe_fp32_fma(iters, _ptr(sink), C.byref(flops), st), "qiddm_probe_fp32_fma")
+            check(lib.qiddm_probe_fp32_fma(150000 if sustained else 2000, _ptr(sink), C.byref(flops), st), "qiddm_probe_fp32_fma")
             b.record()
             b.synchronize()
             best = max(best, flops.value / (a.elapsed_time(b) * 1e-3) / 1e12)
@@ -378,8 +388,17 @@ class Plan:
         return w.contiguous()
 
     # ------------------------------------------------------------------ dense rows
+    # psi_final kept between forward and backward when it is at most this many bytes (QIDDM_SAVE_STATE_MB, default 4096;
+    # 0 disables): the adjoint then skips its forward recomputation
+    SAVE_STATE_BYTES = int(float(os.environ.get("QIDDM_SAVE_STATE_MB", "4096")) * (1 << 20))
+
+    def state_bytes(self, batch: int) -> int:
+        return int(self.lib.qiddm_state_bytes(self.handle, batch))
+
     def forward(self, x: Optional[torch.Tensor], weights: torch.Tensor, batch: Optional[int] = None,
-                basis: Optional[torch.Tensor] = None) -> torch.Tensor:
+                basis: Optional[torch.Tensor] = None, save_state: bool = False):
+        """(B, n_out) outputs; with `save_state` also the (B, 2^n, 2) final states for `backward(state=...)` (None when they
+        would exceed SAVE_STATE_BYTES)."""
         w = self._check_weights(weights)
         dev = w.device
         if self.spec.n_in > 0:
@@ -392,14 +411,18 @@ class Plan:
             raise QiddmError("batch is required for circuits without inputs")
         out = torch.empty((batch, self.spec.n_out), dtype=torch.float32, device=dev)
         ws = self._workspace(batch, dev)
+        state = None
+        if save_state and 0 < self.state_bytes(batch) <= self.SAVE_STATE_BYTES:
+            state = torch.empty((batch, self.spec.dim, 2), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(self.lib.qiddm_forward(self.handle, _ptr(x) if self.spec.n_in else None, _ptr(basis), _ptr(w),
-                                         _wdtype(w), _ptr(out), _ptr(ws), batch, self._stream(dev)),
+            check(self.lib.qiddm_forward_save(self.handle, _ptr(x) if self.spec.n_in else None, _ptr(basis), _ptr(w),
+                                              _wdtype(w), _ptr(out), _ptr(state), _ptr(ws), batch, self._stream(dev)),
                   "qiddm_forward")
-        return out
+        return (out, state) if save_state else out
 
     def backward(self, x: Optional[torch.Tensor], weights: torch.Tensor, grad_out: torch.Tensor,
-                 need_grad_in: bool = True, need_grad_w: bool = True, basis: Optional[torch.Tensor] = None):
+                 need_grad_in: bool = True, need_grad_w: bool = True, basis: Optional[torch.Tensor] = None,
+                 state: Optional[torch.Tensor] = None):
         w = self._check_weights(weights)
         dev = w.device
         go = grad_out.to(torch.float32).contiguous()
@@ -411,9 +434,9 @@ class Plan:
         grad_w = torch.empty_like(w) if need_grad_w else None
         ws = self._workspace(batch, dev)
         with torch.cuda.device(dev):
-            check(self.lib.qiddm_backward(self.handle, _ptr(x) if self.spec.n_in else None, _ptr(basis), _ptr(w),
-                                          _wdtype(w), _ptr(go), _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
-                                          self._stream(dev)), "qiddm_backward")
+            check(self.lib.qiddm_backward_saved(self.handle, _ptr(x) if self.spec.n_in else None, _ptr(basis), _ptr(w),
+                                                _wdtype(w), _ptr(go), _ptr(state), _ptr(grad_in), _ptr(grad_w), _ptr(ws),
+                                                batch, self._stream(dev)), "qiddm_backward")
         return grad_in, grad_w
 
     # ------------------------------------------------------------------ fused-unfold QConv

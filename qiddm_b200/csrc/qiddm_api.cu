@@ -143,7 +143,7 @@ size_t gates_bytes(const qiddm_plan *pl) {
 }
 
 int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
-                 const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s) {
+                 const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s, float *state = nullptr) {
     if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     if (B == 0) return QIDDM_OK;
@@ -152,6 +152,7 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
     GateParams p = make_params(pl, u, B);
     float *gates = reinterpret_cast<float *>(ws);
     p.in = in; p.basis = basis; p.gates = gates; p.out = out;
+    p.state = (state != nullptr && gate_state_compatible(pl->d.n_qubits, p)) ? state : nullptr;
     cudaError_t e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, false, p, gates, s);
     if (e != cudaSuccess) return (int)e;
     LaunchInfo li;
@@ -162,7 +163,7 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
 
 int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
                   const void *weights, int wdtype, const float *grad_out, float *grad_in, void *grad_weights,
-                  void *ws, long long B, long long grad_in_elems, cudaStream_t s) {
+                  void *ws, long long B, long long grad_in_elems, cudaStream_t s, const float *state = nullptr) {
     if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     if (B > 0 && (!grad_out || (n_inputs(&pl->d) > 0 && !in))) return QIDDM_EINVAL;
@@ -172,6 +173,7 @@ int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float 
     float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + gates_bytes(pl));
     p.in = in; p.basis = basis; p.gates = gates; p.out = nullptr;
     p.grad_out = grad_out; p.grad_in = grad_in; p.partials = partials;
+    p.state = (state != nullptr && gate_state_compatible(pl->d.n_qubits, p)) ? const_cast<float *>(state) : nullptr;
     cudaError_t e;
     if (B == 0) {
         if (grad_weights) {
@@ -262,6 +264,23 @@ int qiddm_backward(const qiddm_plan *plan, const float *in, const int32_t *basis
                    int64_t batch, qiddm_stream_t stream) {
     return backward_impl(plan, nullptr, in, basis, weights, weights_dtype, grad_out, grad_in, grad_weights, workspace,
                          batch, 0, (cudaStream_t)stream);
+}
+
+size_t qiddm_state_bytes(const qiddm_plan *plan, int64_t batch) {
+    if (!plan || batch < 0) return 0;
+    return (size_t)batch * (size_t)plan->dim * 2 * sizeof(float);
+}
+
+int qiddm_forward_save(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                       int weights_dtype, float *out, float *state, void *workspace, int64_t batch, qiddm_stream_t stream) {
+    return forward_impl(plan, nullptr, in, basis, weights, weights_dtype, out, workspace, batch, (cudaStream_t)stream, state);
+}
+
+int qiddm_backward_saved(const qiddm_plan *plan, const float *in, const int32_t *basis, const void *weights,
+                         int weights_dtype, const float *grad_out, const float *state, float *grad_in, void *grad_weights,
+                         void *workspace, int64_t batch, qiddm_stream_t stream) {
+    return backward_impl(plan, nullptr, in, basis, weights, weights_dtype, grad_out, grad_in, grad_weights, workspace,
+                         batch, 0, (cudaStream_t)stream, state);
 }
 
 int qiddm_qconv_forward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, const float *img,
@@ -399,8 +418,9 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
     // adjoint sweep on the 2^n basis columns with the READ_STATE cotangent dL/dU^T
     qiddm_plan t = basis_plan(plan);
     char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, batch));
+    // psi_final of basis column c is row c of U^T, which the collapse already holds: the adjoint sweep starts from it
     return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
-                         t.dim, 0, s);
+                         t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
 }
 
 // ---- QConv on the unitary-collapse path: the same GEMMs with the patch-unfold fused into the operand preparation,
@@ -471,7 +491,7 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
     qiddm_plan t = basis_plan(plan);
     char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, B, true));
     return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
-                         t.dim, 0, s);
+                         t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
 }
 
 void qiddm_timing_enable(int enable) {

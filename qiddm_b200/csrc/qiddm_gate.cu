@@ -542,7 +542,16 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
         // ---------------------------------------------------------------- forward sweep
         const int enc_mode = p.enc == QIDDM_ENC_RZ ? ENCL_RZ : (p.enc == QIDDM_ENC_RY ? ENCL_RY : ENCL_NONE);
         const bool apply_last = p.readout == QIDDM_READ_STATE;   // a trailing diagonal only matters for a state readout
-        if constexpr (RES) {
+        if (BWD && p.state != nullptr) {
+            // adjoint with psi_final kept by the forward launch (same kernel family, same arithmetic): no recomputation
+            const float2 *src = reinterpret_cast<const float2 *>(p.state) + (active ? cid : 0) * A;
+#pragma unroll 4
+            for (int i = 0; i < R; ++i) {
+                const int k = g + i * G;
+                psi[slot_of<RB>(k)] = active ? __ldg(src + k) : make_float2(0.f, 0.f);
+            }
+            group_sync<G, T>(slot);
+        } else if constexpr (RES) {
 #pragma unroll 1
             for (int j = 0; j <= n_layers; ++j) {
                 const int v = j & 1;
@@ -637,6 +646,14 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
         }
 
         // ---------------------------------------------------------------- readout
+        if (!BWD && p.state != nullptr && active) {
+            float2 *dst = reinterpret_cast<float2 *>(p.state) + cid * A;
+#pragma unroll 4
+            for (int i = 0; i < R; ++i) {
+                const int k = g + i * G;
+                dst[k] = psi[slot_of<RB>(k)];
+            }
+        }
         if (!BWD) {
             if (p.readout == QIDDM_READ_PROBS) {
                 for (int m = g; m < p.read_count; m += G) {
@@ -1181,6 +1198,13 @@ __global__ void finalize_grads_res_kernel(const float *partials, int n_partials,
 }  // namespace
 
 int gate_rb(int n_qubits, bool backward) { return rb_choose(n_qubits, backward); }
+
+// The resident schedule leaves psi_final without the trailing diagonal (it only matters for a state readout), the plain
+// schedule applies it: a saved psi_final is only handed from the forward to the adjoint kernel when both run the same schedule.
+bool gate_state_compatible(int n_qubits, const GateParams &p) {
+    const int rf = rb_choose(n_qubits, false), rbw = rb_choose(n_qubits, true);
+    return wants_resident(n_qubits, rf, p) == wants_resident(n_qubits, rbw, p);
+}
 
 size_t gate_table_bytes(int n_qubits, int n_layers) {
     // upper bound over the register-tile widths and schedules: NV * 2 * R + n float2 per layer (NV <= 4, R <= 32),

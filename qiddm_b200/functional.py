@@ -21,11 +21,16 @@ class _StageFunction(torch.autograd.Function):
         ctx.x_dtype = x.dtype if x is not None else None
         ctx.gemm = x is not None and plan.use_gemm(x.shape[0])
         ctx.gemm_saved = None
+        ctx.gate_state = None
         if ctx.gemm:
             if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
                 out, ctx.gemm_saved = plan.gemm_forward(x.detach(), weights, save=True)
             else:
                 out = plan.gemm_forward(x.detach(), weights)
+        elif any(ctx.needs_input_grad[1:3]):
+            # training: psi_final travels to the backward (the adjoint kernel skips its forward recomputation)
+            out, ctx.gate_state = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch,
+                                               basis=basis, save_state=True)
         else:
             out = plan.forward(x.detach() if x is not None else None, weights.detach(), batch=batch, basis=basis)
         ctx.save_for_backward(x if x is not None else torch.empty(0), weights)
@@ -43,7 +48,9 @@ class _StageFunction(torch.autograd.Function):
                                             saved=ctx.gemm_saved)
             ctx.gemm_saved = None
         else:
-            gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w, basis=ctx.basis)
+            gi, gw = ctx.plan.backward(x, weights, grad_out, need_grad_in=need_x, need_grad_w=need_w, basis=ctx.basis,
+                                       state=ctx.gate_state)
+            ctx.gate_state = None
         if gi is not None:
             gi = gi.to(ctx.x_dtype)
         return None, gi, (gw.view_as(weights) if gw is not None else None), None, None
