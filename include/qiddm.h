@@ -39,7 +39,8 @@ enum { QIDDM_OK = 0, QIDDM_EINVAL = -1, QIDDM_EUNSUPPORTED = -2, QIDDM_ENOMEM = 
 /* initial state */
 enum { QIDDM_INIT_ZERO = 0,      /* |0...0>                                                            */
        QIDDM_INIT_AMPLITUDE = 1, /* AmplitudeEmbedding(features + add_offset, pad_with, normalize)     */
-       QIDDM_INIT_BASIS = 2 };   /* |basis[c]> (or |c> when basis == NULL): used to build unitaries    */
+       QIDDM_INIT_BASIS = 2,     /* |basis[c]> (or |c> when basis == NULL): used to build unitaries    */
+       QIDDM_INIT_STATE = 3 };   /* internal (density-matrix path): complex state vectors supplied by the library */
 /* per-block data gate that precedes each block's first Rot on every wire (re-upload encoding) */
 enum { QIDDM_ENC_NONE = 0, QIDDM_ENC_RZ = 1, QIDDM_ENC_RY = 2 };
 enum { QIDDM_IMP_CNOT = 0, QIDDM_IMP_CZ = 1 };
@@ -235,6 +236,19 @@ int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target
  * with M transposed.  probs_in == probs_out is allowed. */
 int qiddm_readout_channel(const void *probs_in, void *probs_out, int dtype, int64_t batch, int n_qubits, double m00, double m01,
                           double m10, double m11, qiddm_stream_t stream);
+
+/* Mid-circuit noise channels of the re-upload classes (the `add_noise` branches of nn/qdense.py:515-527, :1405-1417,
+ * :1599-1617, which src/mnist_noise.py:211-229 evaluates on `default.mixed` with the flag flipped on a TRAINED net: inference
+ * only, no backward).  Descriptor: QIDDM_INIT_ZERO, QIDDM_ENC_RZ, readout PROBS or EXPVAL_Z.  After the RZ(a_j) of every block
+ * each wire passes a single-qubit channel given in its generic form on the wire's 2 x 2 block: the populations mix as
+ * (rho00, rho11) -> [[m00, m01], [m10, m11]] (rho00, rho11), the coherences scale by f_off.  PhaseDamping(g): f_off =
+ * sqrt(1 - g), M = I; AmplitudeDamping(g): f_off = sqrt(1 - g), M = [[1, g], [0, 1 - g]]; DepolarizingChannel(p): f_off =
+ * 1 - 4p/3, M = [[1 - 2p/3, 2p/3], [2p/3, 1 - 2p/3]].  Full density-matrix simulation ((batch, 2^n, 2^n) complex fp32 in the
+ * workspace, the unitary layers through the gate kernels on its rows); in (batch, n) angles, out (batch, n_outputs). */
+size_t qiddm_noisy_workspace_bytes(const qiddm_plan *plan, int64_t batch);
+int qiddm_noisy_forward(const qiddm_plan *plan, const float *in, const void *weights, int weights_dtype, double f_off,
+                        double m00, double m01, double m10, double m11, float *out, void *workspace, int64_t batch,
+                        qiddm_stream_t stream);
 
 /* On-device PCA support (replaces the sklearn `PCA.fit_transform` host round trip of nn/qdense.py:456, :1429):
  * eigen-decomposition of a symmetric m x m float64 matrix (the Gram matrix of the centred batch rows), one CTA, parallel

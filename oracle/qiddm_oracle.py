@@ -519,3 +519,58 @@ def readout_channel_probs(p: torch.Tensor, n: int, kind: int, param: float) -> t
     for wire in range(n):
         t = torch.movedim(torch.tensordot(m, torch.movedim(t, 1 + wire, 0), dims=([1], [0])), 0, 1 + wire)
     return t.reshape(B, -1)
+
+
+# --------------------------------------------------------------------------------------
+# mid-circuit noise channels of the re-upload classes on `default.mixed` (nn/qdense.py:515-527, :1405-1417, :1599-1617;
+# src/mnist_noise.py:211-229).  Literal tape order on the full density matrix: per block, per wire j: RZ(a_j) then the channel's
+# Kraus sum on wire j; then StronglyEntanglingLayers (Rot on every wire, CZ ring).  Exponential in n: small cases only.
+# Same status as the readout channels above: Kraus operators as documented for PennyLane 0.29 -- "parity unpinned".
+def _embed_1q(mat: torch.Tensor, wire: int, n: int) -> torch.Tensor:
+    """Full 2**n x 2**n matrix of a 2 x 2 operator on ``wire`` (wire 0 = MSB)."""
+    full = torch.ones(1, 1, dtype=CDTYPE)
+    for i in range(n):
+        full = torch.kron(full, mat.to(CDTYPE) if i == wire else torch.eye(2, dtype=CDTYPE))
+    return full
+
+
+def noisy_reupload_stage(desc: StageDesc, angles: torch.Tensor, weights: torch.Tensor, kind: int, param: float) -> torch.Tensor:
+    """One QNode call of a re-upload class with `add_noise = kind` (1 PhaseDamping, 2 AmplitudeDamping, 3 DepolarizingChannel,
+    parameter ``param``) after every RZ(a_j).  angles (B, n), weights (L, D, n, 3) -> (B, n_out) float64."""
+    assert desc.init == INIT_ZERO and desc.enc == ENC_RZ
+    n, A = desc.n_qubits, desc.dim
+    B = angles.shape[0]
+    W = weights.to(RDTYPE).reshape(desc.n_blocks, desc.layers_per_block, n, 3)
+    ang = angles.to(RDTYPE)[:, :n] * desc.enc_scale
+    rho = torch.zeros(B, A, A, dtype=CDTYPE)
+    rho[:, 0, 0] = 1.0
+    kraus = [[_embed_1q(k, j, n) for k in kraus_operators(kind, param)] for j in range(n)]
+    k_idx = torch.arange(A)
+    ranges = sel_ranges(desc.layers_per_block, n)
+    for blk in range(desc.n_blocks):
+        for j in range(n):
+            sgn = (2 * _bit(k_idx, j, n) - 1).to(RDTYPE)                       # RZ(a) = diag(e^{-ia/2}, e^{+ia/2})
+            d = torch.exp(0.5j * (ang[:, j:j + 1] * sgn[None, :]).to(CDTYPE))  # (B, A)
+            rho = d[:, :, None] * rho * d.conj()[:, None, :]
+            rho = sum(k[None] @ rho @ k.conj().T[None] for k in kraus[j])
+        for l in range(desc.layers_per_block):
+            for i in range(n):
+                u = _embed_1q(rot_matrix(W[blk, l, i, 0], W[blk, l, i, 1], W[blk, l, i, 2]), i, n)
+                rho = u[None] @ rho @ u.conj().T[None]
+            if n > 1:
+                if desc.imprimitive == IMP_CZ:
+                    s = ring_cz_sign(n, ranges[l]).to(CDTYPE)
+                    rho = s[None, :, None] * rho * s[None, None, :]
+                else:
+                    src = ring_permutation(n, ranges[l])
+                    rho = rho[:, src][:, :, src]
+    p = torch.diagonal(rho, dim1=1, dim2=2).real
+    if desc.readout == READ_EXPVAL_Z:
+        signs = torch.stack([(1 - 2 * _bit(k_idx, j, n)).to(RDTYPE) for j in range(n)], dim=1)
+        out = p @ signs
+    else:
+        out = p[:, : desc.read_count * desc.read_stride: desc.read_stride]
+    out = out * desc.post_scale
+    if desc.clamp:
+        out = torch.clamp(out, desc.clamp_lo, desc.clamp_hi)
+    return out

@@ -57,6 +57,7 @@ EXPORTS = [
     "qiddm_readout_channel", "qiddm_gemm_forward_workspace_bytes", "qiddm_probe_fp32_fma",
     "qiddm_qconv_reference_map_forward", "qiddm_qconv_reference_map_backward",
     "qiddm_state_bytes", "qiddm_forward_save", "qiddm_backward_saved",
+    "qiddm_noisy_workspace_bytes", "qiddm_noisy_forward",
 ]
 
 _lib = None
@@ -102,6 +103,11 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_forward_save.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
         lib.qiddm_backward_saved.restype = i32
         lib.qiddm_backward_saved.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i64, vp]
+        lib.qiddm_noisy_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_noisy_workspace_bytes.argtypes = [vp, i64]
+        lib.qiddm_noisy_forward.restype = i32
+        lib.qiddm_noisy_forward.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp,
+                                            i64, vp]
         lib.qiddm_qconv_forward.restype = i32
         lib.qiddm_qconv_forward.argtypes = [vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, i64, vp]
         lib.qiddm_qconv_backward.restype = i32
@@ -439,6 +445,30 @@ class Plan:
                                                 batch, self._stream(dev)), "qiddm_backward")
         return grad_in, grad_w
 
+    # ------------------------------------------------------------------ mid-circuit noise channels (density matrix)
+    NOISY_MAX_BYTES = 64 << 30
+
+    def noisy_forward(self, x: torch.Tensor, weights: torch.Tensor, f_off: float, m) -> torch.Tensor:
+        """Re-upload stage with a single-qubit channel after every RZ(a_j) (qiddm_noisy_forward): inference only."""
+        w = self._check_weights(weights)
+        _require_cuda(x, "input")
+        dev = w.device
+        if x.dim() != 2 or x.shape[1] != self.spec.n_in:
+            raise QiddmError(f"input must be (B, {self.spec.n_in}), got {tuple(x.shape)}")
+        x = x.to(torch.float32).contiguous()
+        batch = x.shape[0]
+        out = torch.empty((batch, self.spec.n_out), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = int(self.lib.qiddm_noisy_workspace_bytes(self.handle, batch))
+            if nbytes == 0:
+                raise QiddmError("this circuit has no mid-circuit-noise path (needs |0..0> start, RZ re-upload, probs / <Z> readout)")
+            if nbytes > self.NOISY_MAX_BYTES:
+                raise QiddmError(f"density-matrix workspace of {nbytes >> 20} MiB: lower the batch ({batch} x 4^{self.spec.n_qubits} amplitudes)")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_noisy_forward(self.handle, _ptr(x), _ptr(w), _wdtype(w), float(f_off), *[float(v) for v in m],
+                                               _ptr(out), _ptr(ws), batch, self._stream(dev)), "qiddm_noisy_forward")
+        return out
+
     # ------------------------------------------------------------------ fused-unfold QConv
     def qconv_forward(self, img: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc) -> torch.Tensor:
         w = self._check_weights(weights)
@@ -539,7 +569,8 @@ class Plan:
             if cached is not None and cached[0] is base and cached[1] == key:
                 cache[slot] = cache.pop(slot)          # most recently used last
                 return cached[2]
-        buf = torch.empty(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
+        # zero-filled: the fp16 operand rows are padded to 16 bytes and the padding meets zero columns of the other operand
+        buf = torch.zeros(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
         ws = self._workspace(self.spec.dim, dev)
         with torch.cuda.device(dev):
             check(self.lib.qiddm_gemm_prepare(self.handle, _ptr(w), _wdtype(w), _ptr(buf), _ptr(ws),

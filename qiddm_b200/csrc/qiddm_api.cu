@@ -143,7 +143,8 @@ size_t gates_bytes(const qiddm_plan *pl) {
 }
 
 int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
-                 const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s, float *state = nullptr) {
+                 const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s, float *state = nullptr,
+                 const float *init_state = nullptr, int in_shift = 0) {
     if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     if (B == 0) return QIDDM_OK;
@@ -153,6 +154,8 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
     float *gates = reinterpret_cast<float *>(ws);
     p.in = in; p.basis = basis; p.gates = gates; p.out = out;
     p.state = (state != nullptr && gate_state_compatible(pl->d.n_qubits, p)) ? state : nullptr;
+    p.init_state = init_state; p.in_shift = in_shift;
+    if (pl->d.init == QIDDM_INIT_STATE && !init_state) return QIDDM_EINVAL;
     cudaError_t e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, false, p, gates, s);
     if (e != cudaSuccess) return (int)e;
     LaunchInfo li;
@@ -492,6 +495,67 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
     char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, B, true));
     return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
                          t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
+}
+
+// ----------------------------------------------------------------------------- mid-circuit noise (density matrix)
+static bool noisy_eligible(const qiddm_plan *pl) {
+    const qiddm_circuit_desc &d = pl->d;
+    return d.init == QIDDM_INIT_ZERO && d.enc == QIDDM_ENC_RZ &&
+           (d.readout == QIDDM_READ_PROBS || d.readout == QIDDM_READ_EXPVAL_Z);
+}
+static qiddm_plan noisy_block_plan(const qiddm_plan *pl) {
+    qiddm_plan t = *pl;
+    t.d.init = QIDDM_INIT_STATE;
+    t.d.n_blocks = 1;
+    t.d.readout = QIDDM_READ_STATE;
+    t.d.clamp = 0;
+    t.n_rot = pl->d.layers_per_block * pl->d.n_qubits;
+    return t;
+}
+
+size_t qiddm_noisy_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
+    if (!plan || !noisy_eligible(plan) || batch < 0) return 0;
+    qiddm_plan t = noisy_block_plan(plan);
+    const long long rows = (batch > 0 ? batch : 1) * (long long)plan->dim;
+    return 2 * dm_state_bytes(plan->d.n_qubits, batch > 0 ? batch : 1) + qiddm_workspace_bytes(&t, rows) + 256;
+}
+
+int qiddm_noisy_forward(const qiddm_plan *plan, const float *in, const void *weights, int weights_dtype, double f_off,
+                        double m00, double m01, double m10, double m11, float *out, void *workspace, int64_t batch,
+                        qiddm_stream_t stream) {
+    if (!plan || !weights || !workspace || batch < 0) return QIDDM_EINVAL;
+    if (!noisy_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    if (weights_dtype != QIDDM_DTYPE_F32 && weights_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    if (batch == 0) return QIDDM_OK;
+    if (!in || !out) return QIDDM_EINVAL;
+    const int n = plan->d.n_qubits;
+    if (batch > 65535 || (batch << n) > 0x7fffffffLL) return QIDDM_EUNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    char *p8 = reinterpret_cast<char *>(workspace);
+    float2 *tau = reinterpret_cast<float2 *>(p8); p8 += dm_state_bytes(n, batch);
+    float2 *tau2 = reinterpret_cast<float2 *>(p8); p8 += dm_state_bytes(n, batch);
+    void *gate_ws = p8;
+    qiddm_plan t = noisy_block_plan(plan);
+    const size_t esz = weights_dtype == QIDDM_DTYPE_F64 ? 8 : 4;
+    const size_t block_stride = (size_t)plan->d.layers_per_block * n * 3 * esz;
+    const long long rows = (long long)batch << n;
+    int rc = dm_init(tau, n, batch, s);
+    for (int i = 0; i < plan->d.n_blocks && rc == QIDDM_OK; ++i) {
+        const void *w_i = reinterpret_cast<const char *>(weights) + (size_t)i * block_stride;
+        // channels on every wire (RZ(a_j) commutes with them and rides in the unitary part)
+        if ((rc = dm_channel(tau, n, batch, (float)f_off, (float)m00, (float)m01, (float)m10, (float)m11, s)) != QIDDM_OK) break;
+        // (U rho)^T: U = SEL(W_i) RZ(a) on the rows of tau; then conj(U rho); then conj(U rho) U^T = (U rho U^dagger)^T
+        if ((rc = forward_impl(&t, nullptr, in, nullptr, w_i, weights_dtype, reinterpret_cast<float *>(tau2), gate_ws, rows, s,
+                               nullptr, reinterpret_cast<const float *>(tau), n)) != QIDDM_OK) break;
+        if ((rc = dm_transpose_conj(tau2, tau, n, batch, s)) != QIDDM_OK) break;
+        if ((rc = forward_impl(&t, nullptr, in, nullptr, w_i, weights_dtype, reinterpret_cast<float *>(tau2), gate_ws, rows, s,
+                               nullptr, reinterpret_cast<const float *>(tau), n)) != QIDDM_OK) break;
+        float2 *tmp = tau; tau = tau2; tau2 = tmp;
+    }
+    if (rc != QIDDM_OK) return rc;
+    const qiddm_circuit_desc &d = plan->d;
+    return dm_readout(tau, n, batch, d.readout, d.read_count, d.read_stride > 0 ? d.read_stride : 1, d.post_scale, d.clamp,
+                      d.clamp_lo, d.clamp_hi, out, s);
 }
 
 void qiddm_timing_enable(int enable) {

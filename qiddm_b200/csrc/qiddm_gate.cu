@@ -209,7 +209,7 @@ __device__ __forceinline__ InstanceGeom instance_geom(const GateParams &p, long 
         g.out_stride = P;
     } else {
         g.b = g.y = g.x = 0;
-        g.in_base = cid * n_in;
+        g.in_base = (cid >> p.in_shift) * n_in;
         g.out_base = cid * n_out;
         g.out_stride = 1;
     }
@@ -506,6 +506,13 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
             inv_norm = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
 #pragma unroll
             for (int i = 0; i < R; ++i) psi[slot_of<RB>(g + i * G)].x *= inv_norm;
+        } else if (p.init == QIDDM_INIT_STATE) {
+            const float2 *src = reinterpret_cast<const float2 *>(p.init_state) + (active ? cid : 0) * A;
+#pragma unroll 4
+            for (int i = 0; i < R; ++i) {
+                const int k = g + i * G;
+                psi[slot_of<RB>(k)] = active ? __ldg(src + k) : make_float2(0.f, 0.f);
+            }
         } else {
             int start = 0;
             if (p.init == QIDDM_INIT_BASIS) start = p.basis ? (active ? p.basis[cid] : 0) : (int)(cid & (A - 1));

@@ -1165,13 +1165,16 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const float *dxT, long l
 // From UT (row c = U|c>, complex fp32) build the weight-side GEMM operands (scaled by w_scale):
 //   Wn[n][c] (N x Kp), Wt[c][n] (F x Np), n = 2m + {re,im}, value = part(UT[c][m*stride]);
 //   bias[n] = pad * sum_{c >= F} value.
-__global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, int Np, int stride, float w_scale,
-                               float pad, __half *Wn_h, __half *Wn_l, __half *Wt_h,
-                               __half *Wt_l, float *bias) {
-    const int n = blockIdx.y;
+__global__ void __launch_bounds__(256) build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, int Np, int stride,
+                                                      float w_scale, float pad, __half *Wn_h, __half *Wn_l, __half *Wt_h,
+                                                      __half *Wt_l, float *bias) {
+    // one CTA per output column n: the pad-row sum is reduced in a fixed order (warp shuffles, then the 8 warp sums in
+    // sequence), so two collapses of the same weights give bit-identical operands (no float atomics)
+    __shared__ float wsum[8];
+    const int n = blockIdx.x;
     const int m = n >> 1, ri = n & 1;
     float bsum = 0.f;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < max(A, Kp); c += gridDim.x * blockDim.x) {
+    for (int c = threadIdx.x; c < max(A, Kp); c += blockDim.x) {
         float v = 0.f;
         if (c < A) {
             const float2 u = UT[(long long)c * A + (long long)m * stride];
@@ -1191,7 +1194,13 @@ __global__ void build_w_kernel(const float2 *UT, int A, int F, int Kp, int N, in
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-    if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(bias + n, bsum * pad);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = bsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+        bias[n] = t * pad;
+    }
 }
 
 // The constant pad rows of the state contribute bias[n] = pad * sum_{c >= F} W'[n][c] to every row of Y.  X carries a
@@ -1595,12 +1604,9 @@ static CollapsedView collapsed_view(const GemmShape &g, void *buf) {
 
 int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapsed, cudaStream_t s) {
     CollapsedView v = collapsed_view(g, collapsed);
-    cudaError_t e = cudaMemsetAsync(v.bias, 0, (size_t)g.N * 4, s);
-    if (e != cudaSuccess) return (int)e;
-    const int cmax = g.A > g.Kp ? g.A : g.Kp;
-    dim3 grid((cmax + 255) / 256, g.N);
+    cudaError_t e;
     timing_begin(TK_BUILD_W, 0.0, s);
-    build_w_kernel<<<grid, 256, 0, s>>>(v.UT, g.A, g.F, g.Kp, g.N, g.Np, g.stride, g.w_scale, gp.pad_value, v.Wn[0],
+    build_w_kernel<<<g.N, 256, 0, s>>>(v.UT, g.A, g.F, g.Kp, g.N, g.Np, g.stride, g.w_scale, gp.pad_value, v.Wn[0],
                                         v.Wn[1], v.Wt[0], v.Wt[1], v.bias);
     if (g.Fx > g.F) {
         fold_bias_kernel<<<(g.N + 127) / 128, 128, 0, s>>>(v.bias, g.N, g.Kp, g.F, v.Wn[0], v.Wn[1]);

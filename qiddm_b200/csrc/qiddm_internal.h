@@ -28,6 +28,10 @@ struct GateParams {
     // optional (B, 2^n) complex fp32 final states psi_final (before the readout): the forward kernel WRITES them, the adjoint
     // kernel READS them instead of recomputing the forward sweep (a fifth to a quarter of its time)
     float *state;
+    // QIDDM_INIT_STATE (density-matrix path): instance cid starts from init_state[cid] (2^n complex fp32); its re-upload
+    // angles are row (cid >> in_shift) of `in` (the 2^n columns of one density matrix share their sample's angles)
+    const float *init_state;
+    int in_shift;
 };
 
 struct LaunchInfo {
@@ -75,6 +79,14 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
 int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,
                   const float *grad_out, const void *saved, float *grad_in, float **gut_out, void *ws, long long B,
                   int n_seg, cudaStream_t s);
+
+// qiddm_dm.cu — density-matrix pieces for the mid-circuit noise channels (tau = rho^T, (B, 2^n, 2^n) complex fp32)
+size_t dm_state_bytes(int n_qubits, long long B);
+int dm_init(float2 *tau, int n, long long B, cudaStream_t s);
+int dm_channel(float2 *tau, int n, long long B, float f_off, float m00, float m01, float m10, float m11, cudaStream_t s);
+int dm_transpose_conj(const float2 *src, float2 *dst, int n, long long B, cudaStream_t s);
+int dm_readout(const float2 *tau, int n, long long B, int readout, int read_count, int read_stride, float post_scale, int clamp,
+               float lo, float hi, float *out, cudaStream_t s);
 
 // qiddm_pca.cu — single-CTA Jacobi eigensolver (float64) for the on-device PCA-in-forward
 size_t eigh_smem_bytes(int m);

@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
-from ..channels import apply_readout_channel, channel_matrix
+from ..channels import apply_readout_channel, channel_matrix, run_noisy_stage
 from ..functional import run_stage
 from ..pca import DevicePCA
 
@@ -416,7 +416,10 @@ class _DifferNBase(nn.Module):
         for k in range(self.N):
             w = W if self._shared_weights else W[k]
             last = k == self.N - 1
-            if noisy:
+            if getattr(self, "_mid_circuit_noise", None) and noise in (1, 2, 3):
+                # channels after every re-upload RZ (nn/qdense.py:515-527): density-matrix stage, inference only
+                a = run_noisy_stage(self._stage_spec(last=last), a[:, :n].contiguous(), w, noise, self._mid_circuit_noise)
+            elif noisy:
                 # every stage is one QNode whose channels sit right before probs() (nn/qdense.py:431-441): full
                 # probabilities -> exact readout channel -> the stage's usual slice (next angles / final image)
                 p = apply_readout_channel(self._circuit(a, w), n, noise, self._noise_params[noise])
@@ -432,8 +435,8 @@ class _DifferNBase(nn.Module):
 
     def forward(self, x):
         b, c, w, h = x.shape
-        if not getattr(self, "_readout_noise", False):      # read per call: src/mnist_noise.py:218 flips it on a trained net
-            _check_noise(getattr(self, "add_noise", 0), allow_phase=False)
+        if not getattr(self, "_readout_noise", False) and not getattr(self, "_mid_circuit_noise", None):
+            _check_noise(getattr(self, "add_noise", 0), allow_phase=False)      # read per call: src/mnist_noise.py:218 flips it
         probs = self._chain(self._angles(x))
         return einops.rearrange(probs, "b (w h) -> b 1 w h", w=self.width, h=self.height).to(x.dtype)
 
@@ -461,9 +464,12 @@ class differN_noise(_DifferNBase):
 class differN_noise_befor(_DifferNBase):
     """nn/qdense.py:481-562."""
 
+    _mid_circuit_noise = {1: 0.03, 2: 0.05, 3: 0.02}    # PhaseDamping / AmplitudeDamping / DepolarizingChannel, :520-526
+
     def __init__(self, shape, spectrum_layer, N, add_noise=0, device_type="default.qubit.torch") -> None:
         super().__init__()
-        _check_noise(add_noise, allow_phase=False)
+        if add_noise not in (0, None, 1, 2, 3):
+            raise NotImplementedError(f"add_noise={add_noise}")
         self.add_noise = add_noise
         self.device_type = device_type
         self.wires = self._setup(shape, spectrum_layer, N)
@@ -638,18 +644,31 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
     def _between_stages(self, a):
         return a
 
+    _mid_circuit_noise = None      # {1: PhaseDamping g, 2: AmplitudeDamping g, 3: Depolarizing p} of the *_noise classes
+
     def _check_noise_at_call(self):
         """`add_noise` is flipped on trained nets at test time (src/mnist_noise.py:218): read it per call, never serve a
-        noiseless result for a noisy request."""
-        _check_noise(getattr(self, "add_noise", 0), allow_phase=False)
+        noiseless result for a noisy request.  Returns the flag when the density-matrix path has to run."""
+        noise = getattr(self, "add_noise", 0)
+        if noise in (0, None):
+            return 0
+        if self._mid_circuit_noise and noise in (1, 2, 3) and self._enc == L.ENC_RZ:
+            return noise
+        _check_noise(noise, allow_phase=False)
+        return 0
 
     def forward(self, x):
         b, c, w, h = x.shape
-        self._check_noise_at_call()
+        noise = self._check_noise_at_call()
         a = self._reduce_input(x)
         for n in range(self.N):
             a = self._between_stages(a)
-            a = self._circuit(a, self.weights1[n])
+            if noise:
+                # channel after every re-upload RZ (nn/qdense.py:1599-1617): density-matrix stage, inference only
+                a = run_noisy_stage(self._spec(), a.reshape(-1, self.hidden_features), self.weights1[n], noise,
+                                    self._mid_circuit_noise)
+            else:
+                a = self._circuit(a, self.weights1[n])
             if self.detach_quantum:
                 a = a.detach()
         a = a.view(b, -1)
@@ -664,10 +683,16 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
 
 
 class _QIDDMExpvalNoise(_QIDDMExpval):
+    # PhaseDamping(0.03) / AmplitudeDamping(0.05) / DepolarizingChannel(0.9) after every RZ: nn/qdense.py:1412-1416, :1511-1515,
+    # :1608-1612, :1700-1704 (the RY-encoded QIDDM_PL_noise1, :606-610, has no density-matrix path: RY does not commute with
+    # the channels, NotImplementedError)
+    _mid_circuit_noise = {1: 0.03, 2: 0.05, 3: 0.9}
+
     def __init__(self, input_dim, hidden_features, spectrum_layer, N: int, add_noise=0,
                  device_type="lightning.qubit") -> None:
         super().__init__()
-        _check_noise(add_noise, allow_phase=False)
+        if add_noise not in (0, None, 1, 2, 3):
+            raise NotImplementedError(f"add_noise={add_noise}")
         self.add_noise = add_noise
         self.device_type = device_type
         self._setup(input_dim, hidden_features, spectrum_layer, N)

@@ -20,14 +20,108 @@ def test_channel_before_measurement_is_a_classical_map(n, kind, param, ps):
     assert (dm.sum(1) - 1).abs().max() <= 1e-14            # trace preserving
 
 
-def test_mid_circuit_noise_classes_still_refuse():
+def test_mid_circuit_noise_classes_construct_and_read_the_flag_at_call_time():
+    """`add_noise` is a constructor argument AND is flipped on trained nets at test time (src/mnist_noise.py:218).  The RZ
+    re-upload classes route it to the density-matrix path (inference only: refuses under autograd); the RY-encoded
+    QIDDM_PL_noise1 has no such path and refuses at call time -- never a silent noiseless result."""
     from qiddm_b200 import nn
     for make in (lambda: nn.QIDDM_PL_noise(64, 4, 2, 2, add_noise=2), lambda: nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=3),
                  lambda: nn.differN_noise_befor(8, 2, 2, add_noise=2)):
-        with pytest.raises(NotImplementedError):
-            make()
+        assert make().add_noise in (2, 3)
+    with pytest.raises(NotImplementedError):
+        nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=7)
+    m = nn.QIDDM_LL_noise(64, 4, 2, 2)
+    m.add_noise = 2                                         # flipped after construction, as mnist_noise.test() does
+    with pytest.raises(NotImplementedError, match="inference path"):
+        m(torch.rand(1, 1, 8, 8))                            # autograd enabled: there is no density-matrix backward
+    ry = nn.QIDDM_PL_noise1(64, 4, 2, 2)
+    ry.add_noise = 1
+    with pytest.raises(NotImplementedError):
+        ry(torch.rand(2, 1, 8, 8))
     assert nn.QDenseUndirected_old_noise(2, 8, add_noise=3).add_noise == 3
     assert nn.differN_noise(8, 2, 2, add_noise=2).add_noise == 2
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_mid_circuit_oracle_reduces_to_the_state_vector_stage_and_keeps_the_trace(kind):
+    """Zero-strength channels give the noiseless stage; any strength keeps Tr rho = 1; DepolarizingChannel(3/4) on every wire of
+    the last block's input is the fully mixed state only at p = 3/4 -- with p = 0.9 (the reference's value) <Z> stays non-trivial."""
+    g = torch.Generator().manual_seed(kind)
+    d = O.desc_reupload(4, 3, 2)
+    W = torch.randn(3, 2, 4, 3, generator=g, dtype=torch.float64) * 0.4
+    a = torch.randn(5, 4, generator=g, dtype=torch.float64)
+    assert (O.noisy_reupload_stage(d, a, W, kind, 0.0) - O.run_stage(d, a, W)).abs().max() <= 1e-13
+    dp = O.desc_reupload(4, 3, 2, readout=O.READ_PROBS, read_count=16)
+    p = O.noisy_reupload_stage(dp, a, W, kind, {1: 0.03, 2: 0.05, 3: 0.9}[kind])
+    assert (p.sum(1) - 1).abs().max() <= 1e-13 and p.min() >= -1e-15
+    assert (p - O.run_stage(dp, a, W)).abs().max() > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,L_,D,readout", [(4, 3, 2, "z"), (5, 2, 2, "z"), (6, 3, 2, "z"), (6, 2, 3, "p"), (3, 4, 2, "p")])
+@pytest.mark.parametrize("kind,param", [(1, 0.03), (2, 0.05), (3, 0.9), (3, 0.02)])
+def test_mid_circuit_noise_stage_matches_the_density_matrix_oracle(n, L_, D, readout, kind, param):
+    """qiddm_noisy_forward (class-wise channel butterflies + gate kernels on the rows of rho^T) against the literal Kraus
+    simulation, n = 3 ... 6 (both gate-kernel schedules: n = 6 with 3-bit tiles is the resident one)."""
+    from qiddm_b200 import _lib as L
+    from qiddm_b200.channels import run_noisy_stage
+    g = torch.Generator().manual_seed(100 * n + kind)
+    if readout == "z":
+        d = O.desc_reupload(n, L_, D)
+    else:
+        d = O.desc_reupload(n, L_, D, readout=O.READ_PROBS, read_count=(1 << n) - 1)
+        d.post_scale, d.clamp = float(1 << n), True
+    W = torch.randn(L_, D, n, 3, generator=g, dtype=torch.float64) * 0.4
+    a = torch.randn(7, n, generator=g, dtype=torch.float64)
+    ref = O.noisy_reupload_stage(d, a, W, kind, param)
+    spec = L.StageSpec(n_qubits=n, n_blocks=L_, layers_per_block=D, init=L.INIT_ZERO, enc=L.ENC_RZ, imprimitive=L.IMP_CZ,
+                       readout=L.READ_EXPVAL_Z if readout == "z" else L.READ_PROBS, read_count=d.read_count,
+                       post_scale=d.post_scale, clamp=d.clamp)
+    with torch.no_grad():
+        out = run_noisy_stage(spec, a.cuda(), W.cuda(), kind, {kind: param})
+    assert out.shape == ref.shape
+    assert rel_to_max(out, ref, floor=1e-3) <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("noise", [1, 2, 3])
+def test_qiddm_ll_noise_module_with_the_flag_flipped_at_test_time(noise):
+    """src/mnist_noise.py:211-229: a trained QIDDM_LL_noise gets `add_noise = k` and is sampled under no_grad on default.mixed."""
+    from qiddm_b200 import nn
+    torch.manual_seed(noise)
+    m = nn.QIDDM_LL_noise(64, 4, 3, 2).to("cuda", torch.float64)
+    x = torch.rand(3, 1, 8, 8, dtype=torch.float64)
+    ps = {k: v.detach().cpu() for k, v in m.named_parameters()}
+    clean = m(x.cuda()).detach()
+    m.add_noise = noise
+    with torch.no_grad():
+        out = m(x.cuda())
+    a = x.reshape(3, 64) @ ps["linear_down.weight"].T + ps["linear_down.bias"]
+    for k in range(2):
+        a = O.noisy_reupload_stage(O.desc_reupload(4, 3, 2), a, ps["weights1"][k], noise, {1: 0.03, 2: 0.05, 3: 0.9}[noise])
+    ref = (a @ ps["linear_up.weight"].T + ps["linear_up.bias"]).reshape(3, 1, 8, 8)
+    assert rel_to_max(out, ref) <= 2e-5
+    assert rel_to_max(out, clean) > 1e-3                    # the flag is honoured
+
+
+@pytest.mark.gpu
+def test_differn_noise_befor_chain_with_mid_circuit_channels():
+    """nn/qdense.py:481-562 with add_noise = 2: two chained stages, each a density-matrix run; the next stage's angles are the
+    first n probabilities."""
+    from qiddm_b200 import nn
+    torch.manual_seed(5)
+    m = nn.differN_noise_befor(4, 2, 2).cuda()              # 4 x 4 pixels -> 4 wires
+    a = torch.randn(5, m.wires, dtype=torch.float64)
+    W = m.weights.detach().cpu().double()
+    m.add_noise = 2
+    with torch.no_grad():
+        out = m._chain(a.cuda())
+    n = m.wires
+    d_mid = O.desc_reupload(n, 2, 2, readout=O.READ_PROBS, read_count=n)
+    d_last = O.desc_reupload(n, 2, 2, readout=O.READ_PROBS, read_count=16)
+    d_last.post_scale, d_last.clamp = 16.0, True
+    ref = O.noisy_reupload_stage(d_last, O.noisy_reupload_stage(d_mid, a, W[0], 2, 0.05), W[1], 2, 0.05)
+    assert rel_to_max(out, ref) <= 2e-5
 
 
 @pytest.mark.gpu
