@@ -442,7 +442,7 @@ def secondary_train(dev, world, rank, steps):
     """QIDDM train samples/s (BASELINE.json metric, second half; configs 1 and 4) as the loop body of
     src/mnist_exm.py:175-182 captured in CUDA graphs (qiddm_b200.train.GraphedTrainStep), weak-scaled over the ranks:
     every rank trains on its own images, ONE flat-bucket NCCL all-reduce of all gradients per step.  The gate kernels'
-    roofline is FP32-FMA: algorithmic flops (14 * 2^n per Rot, adjoint = 4x forward) over the kernels'
+    roofline is FP32-FMA: algorithmic flops (14 * 2^n per Rot, adjoint = 3x forward) over the kernels'
     own CUDA-event time from an eager pass, against the FP32 peak measured here by qiddm_probe_fp32_fma."""
     import torch
     import torch.distributed as dist
@@ -518,8 +518,8 @@ def secondary_train(dev, world, rank, steps):
                                    "a 50 ms launch of the same loop is power-capped at fp32_sustained_tflops_measured",
                     "forward": {"achieved": tf_f, "frac": tf_f / fp32_peak, "ms_per_step": gf["ms"] / 2},
                     "backward": {"achieved": tf_b, "frac": tf_b / fp32_peak, "ms_per_step": gb["ms"] / 2,
-                                 "note": "algorithmic flops of the adjoint counted as 4x the forward (un-apply on psi, apply-dagger "
-                                         "on lambda, inner products)"},
+                                 "note": "algorithmic flops of the adjoint counted as 3x the forward (un-apply on psi, apply-dagger "
+                                         "on lambda, inner products); psi_final comes from the forward launch, no recomputation"},
                     "share_of_eager_step": (gf["ms"] + gb["ms"]) / 2 / eager_ms}
         out[key] = {"model": name, "reference": src, "goal": goal, "images_per_gpu": imgs, "value": imgs * world / (ms * 1e-3),
                     "ms_per_step": ms, "steps": steps, "circuit_evals_per_s": imgs * world * 10 * 2 / (ms * 1e-3),

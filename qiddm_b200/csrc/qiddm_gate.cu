@@ -1020,8 +1020,9 @@ cudaError_t info_t(const GateParams &p, LaunchInfo *li) {
 
 template <int NQ, int RB, bool BWD>
 cudaError_t launch_t(const GateParams &p, const LaunchInfo &li, cudaStream_t s) {
-    // algorithmic flops: 14 * 2^n per Rot; the adjoint sweep costs 4x a forward
-    const double work = (double)p.B * p.n_rot * 14.0 * (double)(1 << NQ) * (BWD ? 4.0 : 1.0);
+    // algorithmic flops: 14 * 2^n per Rot; the adjoint costs 3x a forward (un-apply on psi, apply-dagger on
+    // lambda, the inner products) plus one more forward when psi_final has to be recomputed
+    const double work = (double)p.B * p.n_rot * 14.0 * (double)(1 << NQ) * (BWD ? (p.state != nullptr ? 3.0 : 4.0) : 1.0);
     timing_begin(BWD ? TK_GATE_BWD : TK_GATE_FWD, work, s);
     bool done = false;
     if constexpr (can_resident<NQ, RB>()) {

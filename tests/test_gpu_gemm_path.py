@@ -35,8 +35,28 @@ def _run(d, B, seed, precision, out_tol, grad_tol, wscale=0.4):
     Wd, xd = W.cuda().requires_grad_(True), x.cuda().requires_grad_(True)
     out = run_stage(_spec(d, L.PATH_GEMM, precision), xd, Wd)
     (out * go.cuda()).sum().backward()
-    e = (rel_to_max(out, ref), rel_to_max(Wd.grad, Wr.grad), rel_to_max(xd.grad, xr.grad))
-    assert e[0] <= out_tol, f"forward {e[0]:.3e}"
+    e0 = rel_to_max(out, ref)
+    assert e0 <= out_tol, f"forward {e0:.3e}"
+    if d.clamp:
+        o = out.detach().cpu()
+        agree = (((o >= d.clamp_hi) == (ref >= d.clamp_hi)) & ((o <= d.clamp_lo) == (ref <= d.clamp_lo))).all(dim=1)
+        assert agree.float().mean().item() >= 0.9
+        if not bool(agree.all()):          # weight gradient of the agreeing instances only: re-run both sides on them
+            return _run_rows(d, W, x[agree], go[agree], precision, grad_tol)
+    e = (e0, rel_to_max(Wd.grad, Wr.grad), rel_to_max(xd.grad, xr.grad))
+    assert e[1] <= grad_tol, f"weight grad {e[1]:.3e}"
+    assert e[2] <= grad_tol, f"input grad {e[2]:.3e}"
+    return e
+
+
+def _run_rows(d, W, x, go, precision, grad_tol):
+    from qiddm_b200 import _lib as L
+    from qiddm_b200.functional import run_stage
+    Wr, xr = W.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (O.run_stage(d, xr, Wr) * go).sum().backward()
+    Wd, xd = W.cuda().requires_grad_(True), x.cuda().requires_grad_(True)
+    (run_stage(_spec(d, L.PATH_GEMM, precision), xd, Wd) * go.cuda()).sum().backward()
+    e = (0.0, rel_to_max(Wd.grad, Wr.grad), rel_to_max(xd.grad, xr.grad))
     assert e[1] <= grad_tol, f"weight grad {e[1]:.3e}"
     assert e[2] <= grad_tol, f"input grad {e[2]:.3e}"
     return e
@@ -48,13 +68,13 @@ def test_gemm_path_matches_oracle_fp32_grade(n, F, K, stride):
     d = O.StageDesc(n_qubits=n, layers_per_block=4, init=O.INIT_AMPLITUDE, n_features=F, pad_value=0.3,
                     add_offset=0.1, imprimitive=O.IMP_CNOT, remap=O.REMAP_TANH, readout=O.READ_PROBS, read_count=K,
                     read_stride=stride, post_scale=float(2 ** n) / 2)
-    _run(d, B=300, seed=n, precision=3, out_tol=1e-5, grad_tol=1e-4)
+    _run(d, B=300, seed=n, precision=3, out_tol=1e-5, grad_tol=3e-5)
 
 
 def test_gemm_path_qdense_60x28_clamped_fp32_grade():
     """The bench circuit: QDenseUndirected_old_noise(60,28), clamp epilogue, 784 of 1024 amplitudes."""
     d = O.desc_qdense(60, 784, O.REMAP_TANH)
-    _run(d, B=257, seed=1, precision=3, out_tol=3e-5, grad_tol=1e-4)
+    _run(d, B=257, seed=1, precision=3, out_tol=3e-5, grad_tol=3e-5)
 
 
 def test_gemm_path_single_pass_fp16_looser_bound():
@@ -66,7 +86,7 @@ def test_gemm_path_single_pass_fp16_looser_bound():
 
 def test_gemm_path_qconv_rows():
     d = O.desc_qconv(8, 8, (3, 3), 3)
-    _run(d, B=500, seed=3, precision=3, out_tol=1e-5, grad_tol=1e-4, wscale=1.0)
+    _run(d, B=500, seed=3, precision=3, out_tol=1e-5, grad_tol=3e-5, wscale=1.0)
 
 
 def test_gemm_equals_gate_path_and_auto_dispatch():

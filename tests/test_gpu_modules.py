@@ -11,7 +11,7 @@ from oracle import qiddm_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-GTOL = 5e-5
+GTOL = 2e-5            # measured <= 8.5e-6 per family at BASELINE sizes (profiles/r2_parity_margins.md)
 
 
 def _to64(m):
@@ -100,7 +100,7 @@ def test_differn_chain_module_matches_oracle():
     g = torch.randn_like(ref)
     (ref * g).sum().backward()
     (out * g.cuda()).sum().backward()
-    assert rel_to_max(m.weights.grad, W.grad) <= 2e-4       # float32 parameters
+    assert rel_to_max(m.weights.grad, W.grad) <= 4e-5       # float32 parameters (gradient returned in fp32)
     full = m(torch.rand(9, 1, 8, 8).cuda())                  # with the sklearn PCA in the loop (H5)
     assert full.shape == (9, 1, 8, 8)
 
@@ -155,8 +155,8 @@ def test_qconv2d_unitary_collapse_path_matches_oracle_and_gate_path(cfg):
         (out * g.cuda()).sum().backward()
         res[name] = (out.detach(), m.weights.grad.clone(), xd.grad.clone())
         assert rel_to_max(out, ref) <= TOL, name
-        assert rel_to_max(m.weights.grad, Wr.grad) <= 1e-4, name
-        assert rel_to_max(xd.grad, xr.grad) <= 1e-4, name
+        assert rel_to_max(m.weights.grad, Wr.grad) <= 3e-5, name
+        assert rel_to_max(xd.grad, xr.grad) <= 3e-5, name
     assert rel_to_max(res["gemm"][0], res["gate"][0]) <= 2e-5
     # inference forward (no saved state) gives the same result
     m.path = L.PATH_GEMM
@@ -229,4 +229,4 @@ def test_qconv2d_collapse_path_edge_cases():
     (ref * g).sum().backward()
     out = m(x.cuda())
     (out * g.cuda()).sum().backward()
-    assert rel_to_max(out, ref) <= TOL and rel_to_max(m.weights.grad, Wr.grad) <= 1e-4
+    assert rel_to_max(out, ref) <= TOL and rel_to_max(m.weights.grad, Wr.grad) <= 3e-5

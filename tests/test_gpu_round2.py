@@ -157,7 +157,7 @@ def test_unet_undirected_3_8_3_forward_and_weight_gradients_match_oracle_composi
     (out * go.cuda()).sum().backward()
     assert out.shape == ref.shape == (2, 1, 28, 28)
     e_out = rel_to_max(out, ref)
-    assert e_out <= 6e-4, e_out
+    assert e_out <= 4e-4, e_out                 # measured 1.55e-4
     ref_grads = dict(twin.named_parameters())
     worst = ("", 0.0)
     for k, v in m.named_parameters():
@@ -168,7 +168,7 @@ def test_unet_undirected_3_8_3_forward_and_weight_gradients_match_oracle_composi
         e = rel_to_max(v.grad, rg, floor=1e-9)
         worst = max(worst, (k, e), key=lambda t: t[1])
     print(f"unet end-to-end: out {e_out:.2e}, worst parameter gradient {worst[0]} {worst[1]:.2e}")
-    assert worst[1] <= 5e-2, worst
+    assert worst[1] <= 2e-4, worst              # measured 5.7e-5 (up_blocks.0.net.3.weights)
 
 
 # ------------------------------------------------------------------------------------------------ product sampler vs reference images

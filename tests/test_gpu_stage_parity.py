@@ -1,7 +1,8 @@
 """GPU parity: CUDA gate-path kernels (through the C ABI) vs the complex128 oracle, forward and
 adjoint backward, for every circuit family of SURVEY.md §8a at sizes the oracle finishes in seconds.
-Tolerance: 1e-5 relative to the max-norm of the reference tensor for fp32 outputs (north_star), and
-5e-5 for gradients of 600-gate circuits (fp32 accumulation over the adjoint sweep; stated here)."""
+Tolerance: 1e-5 relative to the max-norm of the reference tensor for fp32 outputs (north_star) and 2e-5 for gradients:
+measured at the BASELINE sizes (profiles/r2_parity_margins.md, three seeds per family): outputs <= 6.3e-6 (1.2e-5 for the
+x784-scaled clamped differN readout), weight / input gradients <= 8.5e-6 on every gate-path family, n = 3 ... 12."""
 import math
 
 import pytest
@@ -13,7 +14,7 @@ from oracle import qiddm_oracle as O
 pytestmark = pytest.mark.gpu
 
 FWD_TOL = 1e-5
-GRAD_TOL = 5e-5
+GRAD_TOL = 2e-5
 
 
 def _spec_from_desc(d: O.StageDesc):
@@ -142,7 +143,7 @@ def test_persistent_grid_many_instances(cfg):
 
 
 def test_float32_weights():
-    _check(O.desc_reupload(6, 3, 2), B=10, seed=12, wdtype=torch.float32, grad_tol=1e-4)
+    _check(O.desc_reupload(6, 3, 2), B=10, seed=12, wdtype=torch.float32, grad_tol=4e-5)
 
 
 def test_empty_batch():
