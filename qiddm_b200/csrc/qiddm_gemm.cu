@@ -100,6 +100,26 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[16]) {
                  :: "memory");
 }
 
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups of 1024 B).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
     uint64_t d = 0;
@@ -149,14 +169,35 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrive on the leader's tempty barrier.  RELAXED: what the MMA issuer must observe is that this warp's tcgen05.ld of the
+// accumulator have completed, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync order before the arrive; a
+// release arrive compiles to MEMBAR.ALL.CTA and makes the warp wait for its global stores of the tile to drain first
+// (ncu: 8 % of the epilogue warps' time, and the accumulator stage stays blocked meanwhile).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into this CTA's shared memory that signals an mbarrier of either CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+// the same load with an L2 eviction-priority policy (createpolicy)
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1,
+                                                      uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -187,6 +228,7 @@ struct GemmParams {
     int b_mn;             // pair kernel, with a_mn: B is MN-major too, its map is over the row-major (K rows, N cols) array
     int M, N, K;          // K per segment, elements
     int bn;               // BLOCK_N: multiple of 16, <= 256
+    int bn_last;          // pair kernel: width of the LAST N tile (multiple of 16, <= bn): N = (tiles_n - 1) * bn + (<= bn_last)
     int stages;
     int k_splits;         // > 1: fp32 atomics into `out` (must be zeroed)
     int epi;
@@ -205,6 +247,8 @@ struct GemmParams {
     const unsigned int *gmax_bits;
     float add_offset;
     int dbg_pfd, dbg_nostore;   // tuning knobs (QIDDM_GEMM_PFD, QIDDM_GEMM_NOSTORE)
+    int l2_hints;               // bit 0: epilogue TMA stores evict_first; bit 1: weight-side (B) operand loads evict_last;
+                                // bit 2: activation-side (A) operand loads evict_first; bit 3: LSU epilogue stores st.global.cs
     int out_f64;             // EPI_PROBS, QConv: `out` is a float64 tensor
     int out_P;               // EPI_PROBS, QConv: > 0 -> row = (image b, patch r), out[(b * n_out + m) * out_P + r] (NCHW)
     // pair kernel: epilogue through shared memory + TMA stores (fp32 boxes of 32 rows)
@@ -517,6 +561,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *map, uint32_t src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -525,7 +573,7 @@ __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, fl
 // (64-byte-swizzled) into the warp's staging buffer, one lane hands the 32-row box to the TMA (coalesced, clipped at the
 // matrix edges, asynchronous).  Two buffers alternate, so a chunk is staged while the previous one drains.
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane,
-                                                  uint32_t stage0, int &buf) {
+                                                  uint32_t stage0, int &buf, int bn_t) {
     const int rbase = row0 + q * 32;
     const int row = rbase + lane;
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
@@ -592,7 +640,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            if (p.epi == EPI_PROBS) {
+            if (p.l2_hints & 1) {       // results are not re-read by this launch: first in line for eviction
+                const uint64_t pol = l2_policy_evict_first();
+                if (p.epi == EPI_PROBS) {
+                    if (p.y_out != nullptr) tma_store_2d_hint(&p.y_map, sb, col, rbase, pol);
+                    if (p.out != nullptr) tma_store_2d_hint(&p.o_map, sb + 2048u, col >> 1, rbase, pol);
+                } else if (p.dx_x == nullptr) {
+                    tma_store_2d_hint(&p.o_map, sb, rbase, col, pol);
+                } else {
+                    tma_store_2d_hint(&p.o_map, sb, col, rbase, pol);
+                }
+            } else if (p.epi == EPI_PROBS) {
                 if (p.y_out != nullptr) tma_store_2d(&p.y_map, sb, col, rbase);
                 if (p.out != nullptr) tma_store_2d(&p.o_map, sb + 2048u, col >> 1, rbase);
             } else if (p.dx_x == nullptr) {
@@ -606,14 +664,101 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
     };
     uint32_t ra[16], rb[16];
     tc_ld16_issue(taddr, ra);
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+    for (int c0 = 0; c0 < bn_t; c0 += 32) {
         tc_ld_wait(ra);
-        if (c0 + 16 < p.bn) tc_ld16_issue(taddr + c0 + 16, rb);
+        if (c0 + 16 < bn_t) tc_ld16_issue(taddr + c0 + 16, rb);
         chunk(ra, c0);
-        if (c0 + 16 < p.bn) {
+        if (c0 + 16 < bn_t) {
             tc_ld_wait(rb);
-            if (c0 + 32 < p.bn) tc_ld16_issue(taddr + c0 + 32, ra);
+            if (c0 + 32 < bn_t) tc_ld16_issue(taddr + c0 + 32, ra);
             chunk(rb, c0 + 16);
+        }
+    }
+}
+
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// EPI_PROBS epilogue through shared memory and plain global stores (tma_epi == 2).  The TMA-store epilogue shares the SM's
+// TMA unit with the operand loads: ncu shows its UTMASTG issue retried and every 16-column chunk waiting ~1.4 k cycles for
+// the store two chunks back to leave its staging buffer -- the forward GEMM ran at 67 % tensor activity and 25 % faster with
+// the stores removed, whether or not Y was written.  Here a lane stages its row of a 32-column chunk (128 B of Y, 64 B of
+// probabilities, 16-byte pieces XOR-swizzled: conflict-free both ways) and the warp writes the block back with 16-byte
+// stores, 8 lanes per 128-byte row segment: full-line, no asynchronous proxy, no fences, one __syncwarp each way.
+__device__ __forceinline__ void epilogue_tile_lsu(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane,
+                                                  uint32_t stage0, int bn_t) {
+    const int rbase = row0 + q * 32;
+    const int row = rbase + lane;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const float rs = row < p.M ? p.row_scale[row] * p.post_scale : 0.f;
+    const uint32_t ybase = stage0, obase = stage0 + 4096u;
+    uint32_t ra[32], rb[32];
+    auto chunk = [&](const uint32_t (&r)[32], int c0) {
+        const int col = n0 + c0;
+        if (col >= p.N || rbase >= p.M) return;             // warp-uniform
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float re = __uint_as_float(r[2 * j]), im = __uint_as_float(r[2 * j + 1]);
+            float pr = (re * re + im * im) * rs;
+            if (p.clamp) pr = fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi);
+            o[j] = pr;
+        }
+        __syncwarp();                                       // the previous chunk's block has been read back by every lane
+        if (p.y_out != nullptr) {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                st_shared_f4(ybase + (uint32_t)lane * 128u + ((j ^ ((uint32_t)lane & 7u)) << 4), __uint_as_float(r[4 * j]),
+                             __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        if (p.out != nullptr) {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                st_shared_f4(obase + (uint32_t)lane * 64u + ((j ^ (((uint32_t)lane >> 1) & 3u)) << 4), o[4 * j], o[4 * j + 1],
+                             o[4 * j + 2], o[4 * j + 3]);
+        }
+        __syncwarp();
+        if (p.y_out != nullptr) {
+            const uint32_t c = (uint32_t)lane & 7u;
+            const int gcol = col + 4 * (int)c;
+#pragma unroll
+            for (uint32_t it = 0; it < 8; ++it) {
+                const uint32_t r_ = it * 4u + ((uint32_t)lane >> 3);
+                const int grow = rbase + (int)r_;
+                const float4 v = ld_shared_f4(ybase + r_ * 128u + ((c ^ (r_ & 7u)) << 4));
+                if (grow < p.M && gcol < p.N && c0 + 4 * (int)c < bn_t) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.y_out + (long long)grow * p.N + gcol);
+                    if (p.l2_hints & 8) __stcs(dst, v); else *dst = v;      // streaming: Y is not read again before the backward
+                }
+            }
+        }
+        if (p.out != nullptr) {
+            const uint32_t c = (uint32_t)lane & 3u;
+            const int gcol = (col >> 1) + 4 * (int)c;
+#pragma unroll
+            for (uint32_t it = 0; it < 4; ++it) {
+                const uint32_t r_ = it * 8u + ((uint32_t)lane >> 2);
+                const int grow = rbase + (int)r_;
+                const float4 v = ld_shared_f4(obase + r_ * 64u + ((c ^ ((r_ >> 1) & 3u)) << 4));
+                if (grow < p.M && gcol < p.n_out && c0 + 8 * (int)c < bn_t) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + (long long)grow * p.ldo + gcol);
+                    if (p.l2_hints & 8) __stcs(dst, v); else *dst = v;
+                }
+            }
+        }
+    };
+    tc_ld32_issue(taddr, ra);
+    for (int c0 = 0; c0 < bn_t; c0 += 64) {
+        tc_ld_wait32(ra);
+        if (c0 + 32 < bn_t) tc_ld32_issue(taddr + c0 + 32, rb);
+        chunk(ra, c0);
+        if (c0 + 32 < bn_t) {
+            tc_ld_wait32(rb);
+            if (c0 + 64 < bn_t) tc_ld32_issue(taddr + c0 + 64, ra);
+            chunk(rb, c0 + 32);
         }
     }
 }
@@ -678,12 +823,14 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
         int stage = 0;
         uint32_t phase = 0;
         const int PFD = p.dbg_pfd;                           // L2 prefetch distance of the A operand, in k-blocks (0: off)
+        const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
         for (long long w = pair; w < total; w += n_pairs) {
             const int split = (int)(w / tiles_mn);
             const long long tile = w % tiles_mn;
-            const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
+            const int tm = (int)(tile / tiles_n), tn = (int)((tile % tiles_n + tm) % tiles_n);   // skewed by tm (see the MMA warp)
             const int m0 = tm * 2 * BM + (int)rank * BM;
-            const int nb0 = tn * p.bn + (int)rank * (p.bn / 2);
+            const int bn_t = tn == tiles_n - 1 ? p.bn_last : p.bn;      // the last N tile may be narrower (no padded MMA columns)
+            const int nb0 = tn * p.bn + (int)rank * (bn_t / 2);
             const int kb0 = (int)((long long)split * KB / p.k_splits);
             const int kb1 = (int)((long long)(split + 1) * KB / p.k_splits);
             // where this pair's next work item starts (for prefetching across the tile boundary)
@@ -713,6 +860,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                         if (AMN) {   // two (64 M) x (64 K) boxes from the row-major (K, M) array
                             tma_load_2d_pair(dst, &p.a_map[i], fb, m0, kb * BKT);
                             tma_load_2d_pair(dst + a_bytes / 2, &p.a_map[i], fb, m0 + 64, kb * BKT);
+                        } else if (p.l2_hints & 4) {
+                            tma_load_2d_pair_hint(dst, &p.a_map[i], fb, kb * BKT, m0, pol_first);
                         } else {
                             tma_load_2d_pair(dst, &p.a_map[i], fb, kb * BKT, m0);
                         }
@@ -723,6 +872,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                         if (bmn) {   // (64 N) x (64 K) boxes from the row-major (K, N) array; columns past N/2 are not read
                             for (uint32_t j = 0; j < b_boxes; ++j)
                                 tma_load_2d_pair(dst + j * 8192u, &p.b_map[i], fb, nb0 + 64 * (int)j, kb * BKT);
+                        } else if (p.l2_hints & 2) {
+                            tma_load_2d_pair_hint(dst, &p.b_map[i], fb, kb * BKT, nb0, pol_last);
                         } else {
                             tma_load_2d_pair(dst, &p.b_map[i], fb, kb * BKT, nb0);
                         }
@@ -748,8 +899,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
         if (leader) {
             const bool issuer = elect_one();
             // instruction descriptor: D=f32, A=B=f16, N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24) |
-                                   (AMN ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
+            const uint32_t idesc0 = (1u << 4) | ((uint32_t)((2 * BM) >> 4) << 24) | (AMN ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
             constexpr uint64_t a_step = AMN ? 128 : 2;
             const uint64_t b_step = bmn ? 128 : 2;
             int stage = 0, acc = 0;
@@ -758,6 +908,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                 const int split = (int)(w / tiles_mn);
                 const int kb0 = (int)((long long)split * KB / p.k_splits);
                 const int kb1 = (int)((long long)(split + 1) * KB / p.k_splits);
+                // N tile of item w, skewed by its M tile: with a narrower last N tile the items are not equally long, and the
+                // persistent round-robin (pair p takes w = p, p + n_pairs, ...) must not hand some pairs only the wide ones
+                const long long tile_w = w % tiles_mn;
+                const int bn_t = (int)((tile_w % tiles_n + tile_w / tiles_n) % tiles_n) == tiles_n - 1 ? p.bn_last : p.bn;
+                const uint32_t idesc = idesc0 | ((uint32_t)(bn_t >> 3) << 17);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
@@ -802,19 +957,22 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
         uint32_t acc_phase = 0;
         for (long long w = pair; w < total; w += n_pairs) {
             const long long tile = w % tiles_mn;
-            const int tm = (int)(tile / tiles_n), tn = (int)(tile % tiles_n);
+            const int tm = (int)(tile / tiles_n), tn = (int)((tile % tiles_n + tm) % tiles_n);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            if (p.tma_epi)
-                epilogue_tile_tma(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, buf);
+            const int bn_t = tn == tiles_n - 1 ? p.bn_last : p.bn;
+            if (p.tma_epi == 2)
+                epilogue_tile_lsu(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, bn_t);
+            else if (p.tma_epi)
+                epilogue_tile_tma(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, buf, bn_t);
             else
-                epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, 0, p.bn);
+                epilogue_tile(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, 0, bn_t);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(te0 + 8u * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (p.tma_epi && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (p.tma_epi == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -1390,6 +1548,9 @@ int make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, 
 
 int pick_bn(int N) {
     // multiple of 16 <= 256 that tiles N with the least padding (small tiles pay more per-tile overhead)
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("QIDDM_GEMM_BN"); forced = e ? atoi(e) : 0; }
+    if (forced >= 16 && forced <= 256 && forced % 16 == 0) return forced;
     int best = 16;
     double best_cost = 1e30;
     for (int bn = 256; bn >= 16; bn -= 16) {
@@ -1451,6 +1612,19 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
     p.a_mn = a_mn ? 1 : 0;
     p.b_mn = b_mn ? 1 : 0;
     p.bn = b_mn ? pick_bn_mn(N) : pick_bn(N);
+    {
+        // the last N tile only issues MMA columns that hold data (rounded up to the UMMA granularity of 16)
+        // measured (profiles/r2_gemm_summary.md): no gain on dX (its tiles are bound by the A-operand feed, which a narrower tile
+        // does not shrink) and the MN-major dW GEMM 12 % SLOWER -- off by default
+        static int vartail = -1;
+        if (vartail < 0) { const char *e = getenv("QIDDM_GEMM_VARTAIL"); vartail = e ? atoi(e) : 0; }
+        const int tiles_n = (N + p.bn - 1) / p.bn;
+        const int rest = N - (tiles_n - 1) * p.bn;
+        // rounded to 32: each CTA of the pair then holds a multiple of 16 columns of the B tile (176 = 2 x 88 columns ran the
+        // MN-major dW GEMM 15 % slower than the padded 208)
+        p.bn_last = vartail ? ((rest + 31) / 32) * 32 : p.bn;
+        if (p.bn_last > p.bn) p.bn_last = p.bn;
+    }
     if (b_mn && !(a_mn && use_pair_kernel())) return QIDDM_EINVAL;
     p.k_splits = k_splits;
     const bool pair = use_pair_kernel();
@@ -1459,6 +1633,9 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         if (pfd < 0) { const char *e = getenv("QIDDM_GEMM_PFD"); pfd = e ? atoi(e) : 0; }
         if (nost < 0) { const char *e = getenv("QIDDM_GEMM_NOSTORE"); nost = e ? atoi(e) : 0; }
         p.dbg_pfd = pfd; p.dbg_nostore = nost;
+        static int hints = -1;
+        if (hints < 0) { const char *e = getenv("QIDDM_GEMM_L2_HINTS"); hints = e ? atoi(e) : 0; }
+        p.l2_hints = hints;
     }
     static int bk32 = -1;
     if (bk32 < 0) { const char *e = getenv("QIDDM_GEMM_BK32"); bk32 = e ? atoi(e) : 0; }
@@ -1497,11 +1674,20 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
                                  CU_TENSOR_MAP_SWIZZLE_64B) == QIDDM_OK;
             }
             p.tma_epi = ok ? 1 : 0;
+            // readout epilogue: staged in shared memory, written back with plain 16-byte stores (see epilogue_tile_lsu)
+            static int lsu_epi = -1;
+            if (lsu_epi < 0) { const char *ev = getenv("QIDDM_GEMM_LSU_EPI"); lsu_epi = ev ? atoi(ev) : 1; }
+            if (lsu_epi && p.epi == EPI_PROBS && (N & 3) == 0 && (p.n_out & 3) == 0 && (p.ldo & 3) == 0 &&
+                (((uintptr_t)p.y_out | (uintptr_t)p.out) & 15) == 0)
+                p.tma_epi = 2;
         }
         const int epi_bytes = p.tma_epi ? 4 * 2 * EPI_STAGE_BYTES + 512 : 0;
         const int b_tile_bytes = b_mn ? ((p.bn / 2 + 63) / 64) * 8192 : (p.bn / 2) * bkt * 2;
         const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + b_tile_bytes);
         int stages = (226 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes;
+        static int max_stages = -1;
+        if (max_stages < 0) { const char *ev = getenv("QIDDM_GEMM_STAGES"); max_stages = ev ? atoi(ev) : 8; }
+        if (stages > max_stages && max_stages >= 2) stages = max_stages;
         if (stages > 8) stages = 8;
         if (stages < 2) stages = 2;
         p.stages = stages;

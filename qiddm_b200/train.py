@@ -24,53 +24,79 @@ def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 
 class FlatGradBucket:
-    """Flat view over the gradients of `params` (created lazily with the first gradients' dtype/device)."""
+    """All gradients of `params` in ONE flat buffer per (dtype, device): every `p.grad` is a VIEW into it (as DDP's
+    `gradient_as_bucket_view`), so autograd accumulates straight into the bucket, "packing" and "unpacking" move nothing,
+    zeroing is one memset per buffer and the all-reduce is one collective per buffer (one in practice: the QIDDM modules are
+    float64 after `.to(dtype=double)`; a float32 circuit-weight tensor next to float64 linears gives two)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        self.flat: Optional[torch.Tensor] = None
+        self.flats: List[torch.Tensor] = []
+        self._views: List[torch.Tensor] = []
 
     def _ensure(self):
-        if self.flat is None:
-            p0 = self.params[0]
-            n = sum(p.numel() for p in self.params)
-            self.flat = torch.zeros(n, dtype=torch.float32 if p0.dtype == torch.float32 else torch.float64,
-                                    device=p0.device)
+        if self._views:
+            return
+        groups = {}
+        for p in self.params:
+            groups.setdefault((p.dtype, p.device), []).append(p)
+        view_of = {}
+        for (dtype, device), ps in groups.items():
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=dtype, device=device)
+            self.flats.append(flat)
+            off = 0
+            for p in ps:
+                view_of[id(p)] = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self._views = [view_of[id(p)] for p in self.params]
+
+    @property
+    def flat(self) -> torch.Tensor:
+        """The flat buffer (the first one when parameters of several dtypes are present; see `flats`)."""
+        self._ensure()
+        return self.flats[0]
+
+    def zero(self):
+        """`opt.zero_grad()` for the bucket: one memset per buffer; every `p.grad` is (re)attached to its view."""
+        self._ensure()
+        for f in self.flats:
+            f.zero_()
+        for p, v in zip(self.params, self._views):
+            if p.grad is not v:
+                p.grad = v
 
     def pack(self):
+        """Make the buffers hold the current gradients.  Free when the gradients already are the views (after `zero()`);
+        gradients autograd created on its own (first step after `zero_grad(set_to_none=True)`) are copied in once."""
         self._ensure()
-        off = 0
-        for p in self.params:
-            n = p.numel()
+        for p, v in zip(self.params, self._views):
+            if p.grad is v:
+                continue
             if p.grad is None:
-                self.flat[off:off + n].zero_()
+                v.zero_()
             else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        return self.flat
+                v.copy_(p.grad)
+            p.grad = v
+        return self.flats[0]
 
     def unpack(self):
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.flat[off:off + n].view_as(p).to(p.dtype)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+        """The gradients are views of the buffers: nothing to move."""
+        for p, v in zip(self.params, self._views):
+            if p.grad is not v:
+                p.grad = v
 
 
 def allreduce_gradients(bucket: FlatGradBucket, weights: Optional[float] = None) -> None:
     """Sum the flat bucket over ranks and divide by the world size (or weight by local/global samples)."""
-    flat = bucket.pack()
+    bucket.pack()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        if weights is not None:
-            flat.mul_(weights)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        else:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            flat.div_(dist.get_world_size())
+        for flat in bucket.flats:
+            if weights is not None:
+                flat.mul_(weights)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.div_(dist.get_world_size())
     bucket.unpack()
 
 
@@ -140,7 +166,7 @@ class DataParallelTrainer:
     def step(self, x_global: torch.Tensor, already_sharded: bool = False) -> torch.Tensor:
         x = x_global if already_sharded else shard_batch(x_global, self.rank, self.world)
         self.diff.train()
-        self.opt.zero_grad(set_to_none=True)
+        self.bucket.zero()                        # gradients accumulate straight into the flat bucket
         n_global = x_global.shape[0] if not already_sharded else None
         if x.shape[0] > 0:
             (loss,) = self.diff(x=x, T=self.tau)
@@ -162,7 +188,7 @@ class GraphedTrainStep:
     * inputs are copied into a static device buffer; the noise ladder's RNG draw, the net, the MSE, the backward
       (incl. the adjoint gate kernels / the unitary-collapse GEMMs) and Adam (`capturable=True`) live inside the graph;
       with `allreduce=True` under torch.distributed the step is two graphs around ONE eager NCCL all-reduce of the flat
-      gradient bucket;
+      gradient bucket, which the gradients are views of (no pack / unpack kernels);
     * models with a host round trip in forward (sklearn PCA) cannot be captured: use `pca_on_device`.
     """
 
@@ -210,18 +236,22 @@ class GraphedTrainStep:
             # bucket; eager NCCL all-reduce of the bucket; graph 2: unpack + optimizer) -- two replays and one NCCL call
             # per step, no dependence on capturing the process group's streams
             with torch.cuda.graph(self.graph):
-                self.opt.zero_grad(set_to_none=True)
+                self.bucket.zero()
                 (loss,) = self.diff(x=self.x, T=self.tau)
                 self.loss = loss.detach()
-                self.flat = self.bucket.pack()
+                self.bucket.pack()
             self.graph_tail = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_tail, pool=self.graph.pool()):
-                self.bucket.unpack()
+                for f in self.bucket.flats:
+                    f.div_(self.world)
                 self.opt.step()
         self._params = [p for p in diff.parameters()]
 
     def _body(self):
-        self.opt.zero_grad(set_to_none=True)
+        if self.bucket is not None:
+            self.bucket.zero()
+        else:
+            self.opt.zero_grad(set_to_none=True)
         (loss,) = self.diff(x=self.x, T=self.tau)
         if self.bucket is not None:
             allreduce_gradients(self.bucket)
@@ -234,8 +264,8 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.graph.replay()
         if self.graph_tail is not None:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(self.world)
+            for f in self.bucket.flats:
+                dist.all_reduce(f, op=dist.ReduceOp.SUM)
             self.graph_tail.replay()
         for p in self._params:        # the replay updated the weights in place: invalidate version-keyed caches
             torch.autograd.graph.increment_version(p)

@@ -114,3 +114,24 @@ def test_flat_bucket_roundtrip():
     assert b.flat.numel() == 8
     for p, g in zip(lin.parameters(), g0):
         assert torch.equal(p.grad, g)
+
+
+def test_flat_bucket_gradients_are_views_of_the_bucket():
+    """After `zero()` every p.grad is a view of the flat buffer: autograd accumulates in place, nothing is packed or unpacked,
+    and parameters of two dtypes get one buffer each."""
+    from qiddm_b200.train import FlatGradBucket
+    lin64, lin32 = torch.nn.Linear(3, 2).double(), torch.nn.Linear(2, 2)
+    params = list(lin64.parameters()) + list(lin32.parameters())
+    b = FlatGradBucket(params)
+    b.zero()
+    assert len(b.flats) == 2 and b.flats[0].dtype == torch.float64 and b.flats[1].dtype == torch.float32
+    ptrs = [p.grad.data_ptr() for p in params]
+    for _ in range(2):                                   # the second backward ACCUMULATES into the same storage
+        lin32(lin64(torch.ones(1, 3, dtype=torch.float64)).float()).sum().backward()
+    assert [p.grad.data_ptr() for p in params] == ptrs
+    assert torch.equal(b.flats[0][:6].view(2, 3), lin64.weight.grad) and lin64.weight.grad.abs().sum() > 0
+    g = lin32.bias.grad.clone()
+    b.pack(), b.unpack()                                 # both free
+    assert torch.equal(lin32.bias.grad, g) and lin32.bias.grad.data_ptr() == ptrs[3]
+    b.zero()
+    assert all(float(f.abs().sum()) == 0 for f in b.flats) and [p.grad.data_ptr() for p in params] == ptrs

@@ -77,8 +77,9 @@ def test_qconv_wire_count_rule_and_noise_guard():
     cases = {(1, 8, 3): 4, (8, 8, 3): 7, (16, 16, 3): 8, (32, 32, 3): 9, (32, 16, 1): 5, (8, 1, 1): 3, (1, 1, 1): 1}
     for (cin, cout, k), wires in cases.items():
         assert nn.QConv2d(cin, cout, kernel_size=k, padding=k // 2).wires == wires
+    assert nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=2).add_noise == 2     # mid-circuit channels: density-matrix path (inference)
     with pytest.raises(NotImplementedError):
-        nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=2)
+        nn.QIDDM_LL_noise(64, 4, 2, 2, add_noise=4)
     with pytest.raises(NotImplementedError):
         nn.QDenseUndirected_old_noise(4, 8, add_noise=4)
     nn.QDenseUndirected_old_noise(4, 8, add_noise=1)       # PhaseShift before probs: a no-op
