@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--bwd-precision", type=int, default=0, choices=[0, 1, 3],
                     help="GEMM path, dX / dW GEMMs: 0 = same as --precision; 1 behind --precision 3 = x3 forward, x1 gradients")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--secondary", default="", help="comma list of the secondary configs to run (default: config1,config4,config3,config5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
@@ -346,7 +347,7 @@ def run_b200(args):
     # --- the second half of BASELINE.json's metric: QIDDM train samples/s, data-parallel over the ranks (all ranks take part)
     sec = None
     if not args.no_secondary:
-        sec = secondary_train(dev, world, rank, max(5, min(K, 10)))
+        sec = secondary_train(dev, world, rank, max(5, min(K, 10)), only=args.secondary.split(",") if args.secondary else None)
 
     if rank != 0:
         if world > 1:
@@ -438,7 +439,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def secondary_train(dev, world, rank, steps):
+def secondary_train(dev, world, rank, steps, only=None):
     """QIDDM train samples/s (BASELINE.json metric, second half; configs 1 and 4) as the loop body of
     src/mnist_exm.py:175-182 captured in CUDA graphs (qiddm_b200.train.GraphedTrainStep), weak-scaled over the ranks:
     every rank trains on its own images, ONE flat-bucket NCCL all-reduce of all gradients per step.  The gate kernels'
@@ -454,25 +455,32 @@ def secondary_train(dev, world, rank, steps):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     fp32_peak = L.fp32_fma_peak_tflops(dev) if rank == 0 else None                       # burst: the harder denominator
     fp32_sustained = L.fp32_fma_peak_tflops(dev, sustained=True) if rank == 0 else None
-    cfgs = [("config1", "QIDDM_LL_noise(784,6,14,2)", lambda: qnn.QIDDM_LL_noise(784, 6, 14, 2), 4096, "data", None, 0.0255,
+    # (key, model, constructor, images per GPU and step, goal, pca_group, lr, side, reference)
+    cfgs = [("config1", "QIDDM_LL_noise(784,6,14,2)", lambda: qnn.QIDDM_LL_noise(784, 6, 14, 2), 4096, "data", None, 0.0255, SIDE,
              "src/mnist_exm.py:46,139"),
-            ("config4", "QIDDM_PL_noise(784,8,6,2)", lambda: qnn.QIDDM_PL_noise(784, 8, 6, 2), 1024, "noise", 10, 0.01,
-             "src/emnist_exm.py:45")]
+            ("config4", "QIDDM_PL_noise(784,8,6,2)", lambda: qnn.QIDDM_PL_noise(784, 8, 6, 2), 1024, "noise", 10, 0.01, SIDE,
+             "src/emnist_exm.py:45"),
+            ("config3", "UNetUndirected(3,8,3) (QConv-UNet, 5 782 circuits per image-forward)", lambda: qnn.UNetUndirected(3, 8, 3),
+             64, "data", None, 1e-3, SIDE, "src/fashion_exm.py, nn/unet.py:119-160"),
+            ("config5", "QIDDM_PL_noise(4096,8,6,2) on 64x64", lambda: qnn.QIDDM_PL_noise(4096, 8, 6, 2), 256, "noise", 10, 0.01, 64,
+             "src/bloodmnist.py:47")]
+    if only:
+        cfgs = [c for c in cfgs if c[0] in only]
     out = {"metric": "qiddm_train_samples_per_sec", "unit": "train-samples/s", "n_gpus": world, "tau": 10,
            "scaling": "weak", "fp32_peak_tflops_measured": fp32_peak, "fp32_sustained_tflops_measured": fp32_sustained,
            "what": "whole-job images/s through Diffusion training steps (noise ladder -> net -> MSE -> adjoint backward -> "
                    "flat-bucket all-reduce -> Adam), CUDA-graph replays, float64 module I/O, fp32 simulation"}
-    for key, name, make, imgs, goal, pca_group, lr, src in cfgs:
+    for key, name, make, imgs, goal, pca_group, lr, side, src in cfgs:
         torch.manual_seed(0)
         net = make()
         if pca_group:
             net.pca_group = pca_group        # one PCA per image's tau-ladder = the reference's batch-1 semantics
-        diff = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (SIDE, SIDE), torch.nn.MSELoss()).to(dev, torch.float64)
+        diff = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (side, side), torch.nn.MSELoss()).to(dev, torch.float64)
         opt = torch.optim.Adam(diff.parameters(), lr=lr, capturable=True)
         trainer = DataParallelTrainer(diff, opt, tau=10)
         trainer.broadcast_parameters()
         torch.manual_seed(100 + rank)
-        x = torch.rand(imgs, PIXELS, device=dev, dtype=torch.float64)
+        x = torch.rand(imgs, side * side, device=dev, dtype=torch.float64)
         trainer.step(x, already_sharded=True)                    # eager warm-up
         L.timing_enable(True)
         L.timing_collect()
@@ -521,18 +529,21 @@ def secondary_train(dev, world, rank, steps):
                                  "note": "algorithmic flops of the adjoint counted as 3x the forward (un-apply on psi, apply-dagger "
                                          "on lambda, inner products); psi_final comes from the forward launch, no recomputation"},
                     "share_of_eager_step": (gf["ms"] + gb["ms"]) / 2 / eager_ms}
+        kshares = {k: round(v["ms"] / 2 / eager_ms, 4) for k, v in kinds.items() if v["launches"] and v["ms"] / 2 / eager_ms >= 0.01}
+        evals_per_image = {"config3": 10 * 5782}.get(key, 10 * 2)         # tau x (circuits per image-forward)
         out[key] = {"model": name, "reference": src, "goal": goal, "images_per_gpu": imgs, "value": imgs * world / (ms * 1e-3),
-                    "ms_per_step": ms, "steps": steps, "circuit_evals_per_s": imgs * world * 10 * 2 / (ms * 1e-3),
+                    "ms_per_step": ms, "steps": steps, "circuit_evals_per_s": imgs * world * evals_per_image / (ms * 1e-3),
+                    "kernel_shares_of_eager_step": kshares,
                     "eager_ms_per_step": eager_ms, "gpu_launches_per_step": int(launches), "roofline": roof,
-                    "allreduce": "one flat fp64 bucket of all gradients per step (NCCL), between two graph replays" if world > 1 else None}
+                    "allreduce": "one flat fp64 bucket of all gradients per step (NCCL; the gradients are views of the bucket), "
+                                 "between two graph replays" if world > 1 else None}
         del gs, trainer, opt, diff, net, x
         torch.cuda.empty_cache()
     return out
 
 
 def extras(dev):
-    """Secondary numbers (not the headline): forward-only rate, and QIDDM train samples/s on an
-    MNIST-shaped QIDDM_LL_noise(784,6,14,2) training step (src/mnist_exm.py:46, tau = 10)."""
+    """Side numbers (not the headline): forward-only rate of the bench layer and the config-1 step at the reference batch size."""
     import torch
     from qiddm_b200 import models, nn as qnn, noise
     from qiddm_b200._lib import Plan
@@ -552,35 +563,6 @@ def extras(dev):
     b.record()
     torch.cuda.synchronize()
     out["qdense_forward_only_evals_per_s"] = B * 5 / (a.elapsed_time(b) * 1e-3)
-    # QIDDM train samples/s
-    torch.manual_seed(0)
-    qn = qnn.QIDDM_LL_noise(784, 6, 14, 2)
-    diff = models.Diffusion(qn, noise.add_normal_noise_multiple, "data", (28, 28), torch.nn.MSELoss()).to(dev, torch.float64)
-    diff.train()
-    opt = torch.optim.Adam(diff.parameters(), lr=0.0255)
-    imgs = 4096
-    data = torch.rand(imgs, 784, device=dev, dtype=torch.float64)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        diff(x=data, T=10)
-        opt.step()
-
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    a, b = ev(), ev()
-    a.record()
-    for _ in range(5):
-        step()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 5
-    out["qiddm_ll_train_samples_per_s"] = imgs / (ms * 1e-3)
-    out["qiddm_ll_train_circuit_evals_per_s"] = imgs * 10 * 2 / (ms * 1e-3)
-    out["qiddm_ll_config"] = "QIDDM_LL_noise(784,6,14,2), 4096 images/step, tau=10, Adam, float64 module I/O"
-    del diff, opt, data
-
     # the other BASELINE configs through CUDA-graph steps (qiddm_b200.train.GraphedTrainStep), float64 modules, tau = 10
     from qiddm_b200.train import GraphedTrainStep
 
@@ -603,16 +585,8 @@ def extras(dev):
     torch.manual_seed(0)
     ms = graphed_rate(qnn.QIDDM_LL_noise(784, 6, 14, 2), 1, 28, "data", iters=50)
     out["config1_reference_batch_ms_per_step_graphed"] = ms           # src/mnist_exm.py defaults: 1 image x tau 10
-    ms = graphed_rate(qnn.UNetUndirected(3, 8, 3), 64, 28, "data", iters=5)
-    out["config3_qconv_unet_train_samples_per_s"] = 64 / (ms * 1e-3)
-    out["config3_qconv_unet_circuit_evals_per_s"] = 64 * 10 * 5782 / (ms * 1e-3)
-    pl = qnn.QIDDM_PL_noise(784, 8, 6, 2)
-    pl.pca_group = 10                                                  # one PCA per image's tau-ladder (reference batch-1 semantics)
-    ms = graphed_rate(pl, 1024, 28, "noise", iters=10)
-    out["config4_qiddm_pl_train_samples_per_s"] = 1024 / (ms * 1e-3)
-    out["configs_note"] = ("graphed steps, one B200: config 1 = QIDDM_LL_noise(784,6,14,2) at the reference batch (1 image); "
-                           "config 3 = UNetUndirected(3,8,3), 64 images/step, QConv on the tcgen05 path; config 4 = "
-                           "QIDDM_PL_noise(784,8,6,2), 1024 images/step, per-image on-device PCA; more in profiles/r1_configs.md")
+    out["configs_note"] = ("config 1 = QIDDM_LL_noise(784,6,14,2) at the REFERENCE batch (1 image x tau 10, src/mnist_exm.py:144), one graph "
+                           "replay per step; the throughput-sized configs 1 / 3 / 4 / 5 are in `secondary`")
     return out
 
 

@@ -99,9 +99,9 @@ def sweep(quick):
                         def fwd():
                             plan.forward(x, w)
 
-                        def both():
-                            plan.forward(x, w)
-                            plan.backward(x, w, go)
+                        def both():       # training pair: psi_final travels from the forward to the adjoint launch
+                            _, st = plan.forward(x, w, save_state=True)
+                            plan.backward(x, w, go, state=st)
                     it = 3 if B * n_rot * A > 2e11 else 5
                     f_ms, _, _ = timed(fwd, 2, it)
                     t_ms, ker, _ = timed(both, 2, it)
