@@ -506,12 +506,12 @@ class Plan:
         return bool(self.lib.qiddm_gemm_supported(self.handle))
 
     def use_gemm(self, batch: int) -> bool:
-        """PATH_AUTO rule, a cost model fitted to the B200 sweep (profiles/r1_configs.md): per instance the gate path
-        costs ~77 flop per Rot and amplitude (forward + adjoint backward) at ~28 TFLOP/s effective; the collapse path
-        costs three fp16x3 GEMMs at ~1.25 PFLOP/s plus its streaming operand traffic, and per optimizer step the
-        collapse itself (gate kernels on the 2^n basis columns, forward + adjoint) plus ~0.15 ms of small launches.
-        Against the committed sweep it picks the slower path on 6 of 144 points, never by more than 1.2x
-        (tests/test_host_logic.py::test_path_dispatch_cost_model_against_the_measured_sweep)."""
+        """PATH_AUTO rule, a cost model fitted to the B200 sweep (profiles/r2_configs_sweep.jsonl, gate path with the
+        psi_final hand-over): per instance the gate path costs ~70 flop per Rot and amplitude (forward + adjoint) at
+        ~28 TFLOP/s effective; the collapse path costs three fp16x3 GEMMs at ~1.5 PFLOP/s executed plus its streaming
+        operand traffic, and per optimizer step the collapse itself (gate kernels on the 2^n basis columns, forward +
+        adjoint) plus ~0.2 ms of small launches.  Against the 144 sweep points with both paths measured it picks the
+        slower one once, by 1 % (tests/test_host_logic.py::test_path_dispatch_cost_model_against_the_measured_sweep)."""
         if self.spec.path == PATH_GATE or not self.gemm_supported():
             return False
         if self.spec.path == PATH_GEMM:
@@ -522,10 +522,10 @@ class Plan:
         n_rot = self.spec.n_blocks * self.spec.layers_per_block * self.spec.n_qubits
         kp = (f + 1 + 7) // 8 * 8
         n_layers = self.spec.n_blocks * self.spec.layers_per_block
-        t_gate = 77.0 * (n_rot + 11) * a / 28e12              # + embedding / readout / recompute ~ 11 Rot-equivalents
-        t_gemm = 18.0 * kp * (2 * n_out) / 1.25e15 + (24.0 * f + 20.0 * 2 * n_out) / 5e12 + 1e-9
+        t_gate = 70.0 * (n_rot + 11) * a / 28e12              # + embedding / readout ~ 11 Rot-equivalents
+        t_gemm = 18.0 * kp * (2 * n_out) / 1.5e15 + (24.0 * f + 20.0 * 2 * n_out) / 5e12 + 1e-9
         # the collapse runs 2^n basis columns: throughput-bound for wide states, latency-bound (serial layers) otherwise
-        t_collapse = max(a * t_gate, n_layers * 3.5e-6) + 1.5e-4
+        t_collapse = max(a * t_gate, n_layers * 3.5e-6) + 2.0e-4
         return batch * t_gemm + t_collapse < batch * t_gate
 
     COLLAPSED_CACHE_ENTRIES = 8      # weight tensors per plan (layers that share a StageSpec share the plan, not U)
