@@ -216,6 +216,21 @@ int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, in
                              const double *save_mean, const double *save_rstd, void *grad_gamma, void *grad_beta,
                              void *workspace, qiddm_stream_t stream);
 
+/* The same BatchNorm2d with the neighbouring ReLU of the UNet blocks fused in (nn/unet.py:92-108: Conv -> BN -> ReLU; :55-63:
+ * Conv -> ReLU -> BN): relu_mode 0 = none, 1 = y = relu(bn(x)) (the backward masks grad_y where bn(x) <= 0, so it takes beta),
+ * 2 = y = bn(relu(x)) (statistics of relu(x); the backward zeroes grad_x where x <= 0).  One pass less over the activation in
+ * each direction per fused pair.  MaxPool2d(kernel, stride = kernel, no padding) of nn/unet.py:110 on (planes, h, w): the
+ * backward recomputes the window's first maximum instead of storing indices (grad_x OVERWRITTEN). */
+int qiddm_batchnorm_relu_forward(const void *x, void *y, int dtype, int n, int c, int hw, const void *gamma, const void *beta,
+                                 double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum,
+                                 double eps, int relu_mode, void *workspace, qiddm_stream_t stream);
+int qiddm_batchnorm_relu_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int n, int c, int hw,
+                                  const void *gamma, const void *beta, const double *save_mean, const double *save_rstd,
+                                  void *grad_gamma, void *grad_beta, int relu_mode, void *workspace, qiddm_stream_t stream);
+int qiddm_maxpool2d_forward(const void *x, void *y, int dtype, int64_t planes, int h, int w, int kernel, qiddm_stream_t stream);
+int qiddm_maxpool2d_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int64_t planes, int h, int w, int kernel,
+                             qiddm_stream_t stream);
+
 /* Diffusion-step glue.  qiddm_noise_ladder = src/noise.py:105-126 (`add_normal_noise_multiple`) fused with the slicing of
  * src/models.py:50-63: for x, eps (batch, pixels) (eps float32 as the reference draws it) and the level weights w[tau]
  * (tensor dtype), level_t = clamp(x (1 - w_t) + eps w_t, 0, 1); writes noisy[(b, t)] = level_{t+1} and clean[(b, t)] =

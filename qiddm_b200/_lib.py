@@ -58,6 +58,7 @@ EXPORTS = [
     "qiddm_qconv_reference_map_forward", "qiddm_qconv_reference_map_backward",
     "qiddm_state_bytes", "qiddm_forward_save", "qiddm_backward_saved",
     "qiddm_noisy_workspace_bytes", "qiddm_noisy_forward",
+    "qiddm_batchnorm_relu_forward", "qiddm_batchnorm_relu_backward", "qiddm_maxpool2d_forward", "qiddm_maxpool2d_backward",
 ]
 
 _lib = None
@@ -125,6 +126,14 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_batchnorm_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp]
         lib.qiddm_batchnorm_backward.restype = i32
         lib.qiddm_batchnorm_backward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.qiddm_batchnorm_relu_forward.restype = i32
+        lib.qiddm_batchnorm_relu_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, i32, vp, vp]
+        lib.qiddm_batchnorm_relu_backward.restype = i32
+        lib.qiddm_batchnorm_relu_backward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+        lib.qiddm_maxpool2d_forward.restype = i32
+        lib.qiddm_maxpool2d_forward.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp]
+        lib.qiddm_maxpool2d_backward.restype = i32
+        lib.qiddm_maxpool2d_backward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp]
         lib.qiddm_noise_ladder.restype = i32
         lib.qiddm_noise_ladder.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]
         lib.qiddm_mse_workspace_bytes.restype = C.c_size_t

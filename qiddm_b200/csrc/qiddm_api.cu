@@ -614,6 +614,26 @@ int qiddm_batchnorm_backward(const void *x, const void *grad_y, void *grad_x, in
                                      workspace, (cudaStream_t)stream);
 }
 
+int qiddm_batchnorm_relu_forward(const void *x, void *y, int dtype, int n, int c, int hw, const void *gamma, const void *beta,
+                                 double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum,
+                                 double eps, int relu_mode, void *workspace, qiddm_stream_t stream) {
+    return qiddm::batchnorm_forward(x, y, dtype, n, c, hw, gamma, beta, save_mean, save_rstd, running_mean, running_var, momentum,
+                                    eps, workspace, (cudaStream_t)stream, relu_mode);
+}
+int qiddm_batchnorm_relu_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int n, int c, int hw,
+                                  const void *gamma, const void *beta, const double *save_mean, const double *save_rstd,
+                                  void *grad_gamma, void *grad_beta, int relu_mode, void *workspace, qiddm_stream_t stream) {
+    return qiddm::batchnorm_backward(x, grad_y, grad_x, dtype, n, c, hw, gamma, save_mean, save_rstd, grad_gamma, grad_beta,
+                                     workspace, (cudaStream_t)stream, beta, relu_mode);
+}
+int qiddm_maxpool2d_forward(const void *x, void *y, int dtype, int64_t planes, int h, int w, int kernel, qiddm_stream_t stream) {
+    return qiddm::maxpool2d(x, nullptr, y, dtype, false, planes, h, w, kernel, (cudaStream_t)stream);
+}
+int qiddm_maxpool2d_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int64_t planes, int h, int w, int kernel,
+                             qiddm_stream_t stream) {
+    return qiddm::maxpool2d(x, grad_y, grad_x, dtype, true, planes, h, w, kernel, (cudaStream_t)stream);
+}
+
 int qiddm_noise_ladder(const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels, int tau,
                        void *noisy, void *clean, qiddm_stream_t stream) {
     return qiddm::noise_ladder(x, eps, w, dtype, batch, pixels, tau, noisy, clean, (cudaStream_t)stream);

@@ -110,7 +110,7 @@ __device__ __forceinline__ void block_reduce2(double &a, double &b, double *red)
 // partial[c][split] = (sum x, sum x^2) over this split's share of (n, hw)
 // (I = unsigned when every index fits 32 bits: the per-element div/mod is the instruction cost of these kernels)
 template <typename T, typename I>
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *x, int N, int C, int HW, double *partial) {
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *x, int N, int C, int HW, double *partial, int relu) {
     __shared__ double red[2 * (BN_THREADS >> 5)];
     const int c = blockIdx.x, sp = blockIdx.y;
     const I M = (I)N * (I)HW;
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *x, int N,
     for (I i = (I)sp * BN_THREADS + threadIdx.x; i < M; i += (I)BN_SPLITS * BN_THREADS) {
         const I n = i / (I)HW;
         const I hw = i - n * (I)HW;
-        const double v = (double)x[(n * (I)C + (I)c) * (I)HW + hw];
+        double v = (double)x[(n * (I)C + (I)c) * (I)HW + hw];
+        if (relu == 2 && !(v > 0.0)) v = 0.0;           // ReLU fused in front of the normalisation (nn/unet.py:59-61)
         s += v;
         q += v * v;
     }
@@ -154,31 +155,41 @@ __global__ void bn_finalize_kernel(const double *partial, int C, long long M, do
 
 template <typename T, typename I>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T *x, T *y, long long total_, int C, int HW, const double *mean,
-                                                       const double *rstd, const T *gamma, const T *beta) {
+                                                       const double *rstd, const T *gamma, const T *beta, int relu) {
     const I total = (I)total_;
     for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
         const int c = (int)((i / (I)HW) % (I)C);
         const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
-        y[i] = (T)(((double)x[i] - mean[c]) * rstd[c] * g + b);
+        double xin = (double)x[i];
+        if (relu == 2 && !(xin > 0.0)) xin = 0.0;
+        double v = (xin - mean[c]) * rstd[c] * g + b;
+        if (relu == 1 && !(v > 0.0)) v = 0.0;           // ReLU fused behind the normalisation (nn/unet.py:95-96, :106-107)
+        y[i] = (T)v;
     }
 }
 
 // partial[c][split] = (sum dy, sum dy * xhat)
 template <typename T, typename I>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *x, const T *dy, int N, int C, int HW,
-                                                                   const double *mean, const double *rstd, double *partial) {
+                                                                   const double *mean, const double *rstd, double *partial,
+                                                                   const T *gamma, const T *beta, int relu) {
     __shared__ double red[2 * (BN_THREADS >> 5)];
     const int c = blockIdx.x, sp = blockIdx.y;
     const I M = (I)N * (I)HW;
     const double mu = mean[c], rs = rstd[c];
+    const double gm = gamma ? (double)gamma[c] : 1.0, bt = beta ? (double)beta[c] : 0.0;
     double s = 0.0, q = 0.0;
     for (I i = (I)sp * BN_THREADS + threadIdx.x; i < M; i += (I)BN_SPLITS * BN_THREADS) {
         const I n = i / (I)HW;
         const I hw = i - n * (I)HW;
         const I idx = (n * (I)C + (I)c) * (I)HW + hw;
-        const double g = (double)dy[idx];
+        double xin = (double)x[idx];
+        if (relu == 2 && !(xin > 0.0)) xin = 0.0;
+        const double xh = (xin - mu) * rs;
+        double g = (double)dy[idx];
+        if (relu == 1 && !(xh * gm + bt > 0.0)) g = 0.0;     // threshold_backward of the fused trailing ReLU
         s += g;
-        q += g * ((double)x[idx] - mu) * rs;
+        q += g * xh;
     }
     block_reduce2(s, q, red);
     if (threadIdx.x == 0) {
@@ -206,13 +217,63 @@ __global__ void bn_bwd_finalize_kernel(const double *partial, int C, double *sum
 template <typename T, typename I>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *x, const T *dy, T *dx, long long total_, int C, int HW,
                                                            double inv_m, const double *mean, const double *rstd,
-                                                           const T *gamma, const double *sums) {
+                                                           const T *gamma, const double *sums, const T *beta, int relu) {
     const I total = (I)total_;
     for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
         const int c = (int)((i / (I)HW) % (I)C);
-        const double g = gamma ? (double)gamma[c] : 1.0;
-        const double xh = ((double)x[i] - mean[c]) * rstd[c];
-        dx[i] = (T)(g * rstd[c] * ((double)dy[i] - sums[2 * c] * inv_m - xh * sums[2 * c + 1] * inv_m));
+        const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+        const double xraw = (double)x[i];
+        const double xin = (relu == 2 && !(xraw > 0.0)) ? 0.0 : xraw;
+        const double xh = (xin - mean[c]) * rstd[c];
+        double gy = (double)dy[i];
+        if (relu == 1 && !(xh * g + b > 0.0)) gy = 0.0;
+        double v = g * rstd[c] * (gy - sums[2 * c] * inv_m - xh * sums[2 * c + 1] * inv_m);
+        if (relu == 2 && !(xraw > 0.0)) v = 0.0;              // threshold_backward of the fused leading ReLU
+        dx[i] = (T)v;
+    }
+}
+
+// MaxPool2d(kernel k, stride k) on (planes, H, W) -> (planes, H / k, W / k) (nn/unet.py:110: MaxPool2d(2, 2)); the backward
+// recomputes the window's first maximum (row-major scan, strict >, as torch's kernel) instead of storing indices
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T *x, T *y, long long total, int H, int W, int Ho, int Wo, int k) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        const long long t = i / Wo;
+        const int oy = (int)(t % Ho);
+        const long long pl = t / Ho;
+        const T *src = x + (pl * H + (long long)oy * k) * W + (long long)ox * k;
+        T m = src[0];
+        for (int dy = 0; dy < k; ++dy)
+            for (int dx = 0; dx < k; ++dx) {
+                const T v = src[(long long)dy * W + dx];
+                if (v > m) m = v;
+            }
+        y[i] = m;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *x, const T *gy, T *gx, long long total, int H, int W, int Ho,
+                                                          int Wo, int k) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % W);
+        const long long t = i / W;
+        const int iy = (int)(t % H);
+        const long long pl = t / H;
+        const int oy = iy / k, ox = ix / k;
+        T g = (T)0;
+        if (oy < Ho && ox < Wo) {
+            const T *src = x + (pl * H + (long long)oy * k) * W + (long long)ox * k;
+            T m = src[0];
+            int arg = 0;
+            for (int dy = 0; dy < k; ++dy)
+                for (int dx = 0; dx < k; ++dx) {
+                    const T v = src[(long long)dy * W + dx];
+                    if (v > m) { m = v; arg = dy * k + dx; }
+                }
+            if (arg == (iy - oy * k) * k + (ix - ox * k)) g = gy[(pl * Ho + oy) * Wo + ox];
+        }
+        gx[i] = g;
     }
 }
 
@@ -384,14 +445,14 @@ int upsample_impl(const void *in, void *out, bool backward, long long planes, in
 template <typename T, typename I>
 int bn_fwd_impl(const void *x, void *y, int N, int C, int HW, const void *gamma, const void *beta, double *save_mean,
                 double *save_rstd, void *running_mean, void *running_var, double momentum, double eps, double *ws,
-                cudaStream_t s) {
+                cudaStream_t s, int relu) {
     const long long M = (long long)N * HW, total = M * C;
-    bn_stats_kernel<T, I><<<dim3(C, BN_SPLITS), BN_THREADS, 0, s>>>(reinterpret_cast<const T *>(x), N, C, HW, ws);
+    bn_stats_kernel<T, I><<<dim3(C, BN_SPLITS), BN_THREADS, 0, s>>>(reinterpret_cast<const T *>(x), N, C, HW, ws, relu);
     bn_finalize_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(ws, C, M, eps, momentum, save_mean, save_rstd,
                                                          reinterpret_cast<T *>(running_mean), reinterpret_cast<T *>(running_var));
     bn_apply_kernel<T, I><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<T *>(y), total, C, HW,
                                                      save_mean, save_rstd, reinterpret_cast<const T *>(gamma),
-                                                     reinterpret_cast<const T *>(beta));
+                                                     reinterpret_cast<const T *>(beta), relu);
     count_launch(3);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
@@ -399,17 +460,19 @@ int bn_fwd_impl(const void *x, void *y, int N, int C, int HW, const void *gamma,
 
 template <typename T, typename I>
 int bn_bwd_impl(const void *x, const void *dy, void *dx, int N, int C, int HW, const void *gamma, const double *save_mean,
-                const double *save_rstd, void *dgamma, void *dbeta, double *ws, cudaStream_t s) {
+                const double *save_rstd, void *dgamma, void *dbeta, double *ws, cudaStream_t s, const void *beta, int relu) {
     const long long M = (long long)N * HW, total = M * C;
     double *sums = ws + (size_t)C * BN_SPLITS * 2;
     bn_bwd_reduce_kernel<T, I><<<dim3(C, BN_SPLITS), BN_THREADS, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<const T *>(dy),
-                                                                      N, C, HW, save_mean, save_rstd, ws);
+                                                                      N, C, HW, save_mean, save_rstd, ws,
+                                                                      reinterpret_cast<const T *>(gamma), reinterpret_cast<const T *>(beta), relu);
     bn_bwd_finalize_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(ws, C, sums, reinterpret_cast<T *>(dgamma), reinterpret_cast<T *>(dbeta));
     int launches = 2;
     if (dx != nullptr) {
         bn_bwd_apply_kernel<T, I><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<const T *>(dy),
                                                              reinterpret_cast<T *>(dx), total, C, HW, 1.0 / (double)M, save_mean,
-                                                             save_rstd, reinterpret_cast<const T *>(gamma), sums);
+                                                             save_rstd, reinterpret_cast<const T *>(gamma), sums,
+                                                             reinterpret_cast<const T *>(beta), relu);
         ++launches;
     }
     count_launch(launches);
@@ -552,12 +615,12 @@ int upsample_bilinear(const void *in, void *out, int dtype, bool backward, long 
 
 int batchnorm_forward(const void *x, void *y, int dtype, int N, int C, int HW, const void *gamma, const void *beta,
                       double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum, double eps,
-                      void *ws, cudaStream_t s) {
-    if (!x || !y || !save_mean || !save_rstd || !ws || N < 1 || C < 1 || HW < 1) return QIDDM_EINVAL;
+                      void *ws, cudaStream_t s, int relu) {
+    if (!x || !y || !save_mean || !save_rstd || !ws || N < 1 || C < 1 || HW < 1 || relu < 0 || relu > 2) return QIDDM_EINVAL;
     if ((running_mean == nullptr) != (running_var == nullptr)) return QIDDM_EINVAL;
     const bool small = (long long)N * C * HW < (1LL << 31);
     double *w = reinterpret_cast<double *>(ws);
-#define QIDDM_BN_FWD(T, I) bn_fwd_impl<T, I>(x, y, N, C, HW, gamma, beta, save_mean, save_rstd, running_mean, running_var, momentum, eps, w, s)
+#define QIDDM_BN_FWD(T, I) bn_fwd_impl<T, I>(x, y, N, C, HW, gamma, beta, save_mean, save_rstd, running_mean, running_var, momentum, eps, w, s, relu)
     if (dtype == QIDDM_DTYPE_F64) return small ? QIDDM_BN_FWD(double, unsigned) : QIDDM_BN_FWD(double, long long);
     if (dtype == QIDDM_DTYPE_F32) return small ? QIDDM_BN_FWD(float, unsigned) : QIDDM_BN_FWD(float, long long);
 #undef QIDDM_BN_FWD
@@ -565,15 +628,37 @@ int batchnorm_forward(const void *x, void *y, int dtype, int N, int C, int HW, c
 }
 
 int batchnorm_backward(const void *x, const void *dy, void *dx, int dtype, int N, int C, int HW, const void *gamma,
-                       const double *save_mean, const double *save_rstd, void *dgamma, void *dbeta, void *ws, cudaStream_t s) {
-    if (!x || !dy || !save_mean || !save_rstd || !ws || N < 1 || C < 1 || HW < 1) return QIDDM_EINVAL;
+                       const double *save_mean, const double *save_rstd, void *dgamma, void *dbeta, void *ws, cudaStream_t s,
+                       const void *beta, int relu) {
+    if (!x || !dy || !save_mean || !save_rstd || !ws || N < 1 || C < 1 || HW < 1 || relu < 0 || relu > 2) return QIDDM_EINVAL;
     const bool small = (long long)N * C * HW < (1LL << 31);
     double *w = reinterpret_cast<double *>(ws);
-#define QIDDM_BN_BWD(T, I) bn_bwd_impl<T, I>(x, dy, dx, N, C, HW, gamma, save_mean, save_rstd, dgamma, dbeta, w, s)
+#define QIDDM_BN_BWD(T, I) bn_bwd_impl<T, I>(x, dy, dx, N, C, HW, gamma, save_mean, save_rstd, dgamma, dbeta, w, s, beta, relu)
     if (dtype == QIDDM_DTYPE_F64) return small ? QIDDM_BN_BWD(double, unsigned) : QIDDM_BN_BWD(double, long long);
     if (dtype == QIDDM_DTYPE_F32) return small ? QIDDM_BN_BWD(float, unsigned) : QIDDM_BN_BWD(float, long long);
 #undef QIDDM_BN_BWD
     return QIDDM_EINVAL;
+}
+
+int maxpool2d(const void *x, const void *gy, void *out, int dtype, bool backward, long long planes, int H, int W, int k,
+              cudaStream_t s) {
+    if (!x || !out || planes < 0 || H < 1 || W < 1 || k < 1 || (backward && !gy)) return QIDDM_EINVAL;
+    const int Ho = H / k, Wo = W / k;
+    if (Ho < 1 || Wo < 1) return QIDDM_EINVAL;
+    if (planes == 0) return QIDDM_OK;
+    const long long total = backward ? planes * H * W : planes * Ho * Wo;
+    if (dtype == QIDDM_DTYPE_F64) {
+        if (backward) maxpool_bwd_kernel<double><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const double *>(x), reinterpret_cast<const double *>(gy), reinterpret_cast<double *>(out), total, H, W, Ho, Wo, k);
+        else maxpool_fwd_kernel<double><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const double *>(x), reinterpret_cast<double *>(out), total, H, W, Ho, Wo, k);
+    } else if (dtype == QIDDM_DTYPE_F32) {
+        if (backward) maxpool_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float *>(x), reinterpret_cast<const float *>(gy), reinterpret_cast<float *>(out), total, H, W, Ho, Wo, k);
+        else maxpool_fwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float *>(x), reinterpret_cast<float *>(out), total, H, W, Ho, Wo, k);
+    } else {
+        return QIDDM_EINVAL;
+    }
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
 }
 
 }  // namespace qiddm

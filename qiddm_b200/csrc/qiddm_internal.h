@@ -108,8 +108,11 @@ int upsample_bilinear(const void *in, void *out, int dtype, bool backward, long 
                       double scale_h, double scale_w, cudaStream_t s);
 int batchnorm_forward(const void *x, void *y, int dtype, int N, int C, int HW, const void *gamma, const void *beta,
                       double *save_mean, double *save_rstd, void *running_mean, void *running_var, double momentum, double eps,
-                      void *ws, cudaStream_t s);
+                      void *ws, cudaStream_t s, int relu = 0);
 int batchnorm_backward(const void *x, const void *dy, void *dx, int dtype, int N, int C, int HW, const void *gamma,
-                       const double *save_mean, const double *save_rstd, void *dgamma, void *dbeta, void *ws, cudaStream_t s);
+                       const double *save_mean, const double *save_rstd, void *dgamma, void *dbeta, void *ws, cudaStream_t s,
+                       const void *beta = nullptr, int relu = 0);
+int maxpool2d(const void *x, const void *gy, void *out, int dtype, bool backward, long long planes, int H, int W, int k,
+              cudaStream_t s);
 
 }  // namespace qiddm

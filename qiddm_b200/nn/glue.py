@@ -18,9 +18,12 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+RELU_NONE, RELU_POST, RELU_PRE = 0, 1, 2       # relu_mode of qiddm_batchnorm_relu_*
+
+
 class _BatchNormFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu_mode=RELU_NONE):
         lib = L.load_library()
         x = x.contiguous()
         n, c = x.shape[0], x.shape[1]
@@ -37,10 +40,12 @@ class _BatchNormFunction(torch.autograd.Function):
                 raise L.QiddmError("BatchNorm2d: running statistics must be contiguous and have the input's dtype")
             rm, rv = running_mean, running_var
         with torch.cuda.device(x.device):
-            L.check(lib.qiddm_batchnorm_forward(L._ptr(x), L._ptr(y), _DT[x.dtype], n, c, hw, L._ptr(g), L._ptr(b),
-                                                L._ptr(mean), L._ptr(rstd), L._ptr(rm), L._ptr(rv), float(momentum),
-                                                float(eps), L._ptr(ws), _stream(x.device)), "qiddm_batchnorm_forward")
-        ctx.save_for_backward(x, g, mean, rstd)
+            L.check(lib.qiddm_batchnorm_relu_forward(L._ptr(x), L._ptr(y), _DT[x.dtype], n, c, hw, L._ptr(g), L._ptr(b),
+                                                     L._ptr(mean), L._ptr(rstd), L._ptr(rm), L._ptr(rv), float(momentum),
+                                                     float(eps), int(relu_mode), L._ptr(ws), _stream(x.device)),
+                    "qiddm_batchnorm_relu_forward")
+        ctx.relu_mode = int(relu_mode)
+        ctx.save_for_backward(x, g, mean, rstd, b if relu_mode == RELU_POST else None)
         ctx.has_affine = gamma is not None
         ctx.param_dtype = gamma.dtype if gamma is not None else None
         return y
@@ -48,7 +53,7 @@ class _BatchNormFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         lib = L.load_library()
-        x, g, mean, rstd = ctx.saved_tensors
+        x, g, mean, rstd, b = ctx.saved_tensors
         dy = dy.contiguous()
         n, c = x.shape[0], x.shape[1]
         hw = x.numel() // (n * c)
@@ -57,40 +62,123 @@ class _BatchNormFunction(torch.autograd.Function):
         dbeta = torch.empty(c, dtype=x.dtype, device=x.device) if ctx.has_affine else None
         ws = torch.empty(int(lib.qiddm_batchnorm_workspace_bytes(c)), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
-            L.check(lib.qiddm_batchnorm_backward(L._ptr(x), L._ptr(dy), L._ptr(dx), _DT[x.dtype], n, c, hw, L._ptr(g),
-                                                 L._ptr(mean), L._ptr(rstd), L._ptr(dgamma), L._ptr(dbeta), L._ptr(ws),
-                                                 _stream(x.device)), "qiddm_batchnorm_backward")
+            L.check(lib.qiddm_batchnorm_relu_backward(L._ptr(x), L._ptr(dy), L._ptr(dx), _DT[x.dtype], n, c, hw, L._ptr(g),
+                                                      L._ptr(b), L._ptr(mean), L._ptr(rstd), L._ptr(dgamma), L._ptr(dbeta),
+                                                      ctx.relu_mode, L._ptr(ws), _stream(x.device)),
+                    "qiddm_batchnorm_relu_backward")
         if ctx.has_affine:
             dgamma, dbeta = dgamma.to(ctx.param_dtype), dbeta.to(ctx.param_dtype)
-        return dx, dgamma, dbeta, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 class BatchNorm2d(torch.nn.BatchNorm2d):
-    """torch.nn.BatchNorm2d (nn/unet.py:43-45, :95, :106) with the batch-statistics path on the library's kernels."""
+    """torch.nn.BatchNorm2d (nn/unet.py:43-45, :95, :106) with the batch-statistics path on the library's kernels.
+    `fuse_relu` ("post" | "pre" | None, set by `fuse_bn_relu`): the ReLU that follows / precedes this layer in the UNet
+    block is computed inside the BatchNorm kernels (the neighbouring `FusedReLU` module then passes its input through)."""
+
+    fuse_relu = None
+
+    def _torch_path(self, x):
+        if self.fuse_relu == "pre":
+            x = torch.relu(x)
+        y = super().forward(x)
+        return torch.relu(y) if self.fuse_relu == "post" else y
 
     def forward(self, x):
         if not x.is_cuda or x.dtype not in _DT or x.dim() != 4 or x.numel() == 0:
-            return super().forward(x)
+            return self._torch_path(x)
         use_batch_stats = self.training or self.running_mean is None
         if not use_batch_stats:           # eval: running statistics, plain elementwise math (differentiable)
+            if self.fuse_relu == "pre":
+                x = torch.relu(x)
             scale = torch.rsqrt(self.running_var.to(x.dtype) + self.eps)
             shift = -self.running_mean.to(x.dtype) * scale
             if self.affine:
                 scale = scale * self.weight.to(x.dtype)
                 shift = shift * self.weight.to(x.dtype) + self.bias.to(x.dtype)
-            return x * scale[None, :, None, None] + shift[None, :, None, None]
+            y = x * scale[None, :, None, None] + shift[None, :, None, None]
+            return torch.relu(y) if self.fuse_relu == "post" else y
         factor = 0.0
         rm = rv = None
         if self.training and self.track_running_stats and self.running_mean is not None:
             # momentum None = cumulative moving average; reading the counter would sync, so only the (default)
             # exponential average takes the library path
             if self.momentum is None or self.running_mean.dtype != x.dtype:
-                return super().forward(x)
+                return self._torch_path(x)
             self.num_batches_tracked.add_(1)
             factor = self.momentum
             rm, rv = self.running_mean, self.running_var
+        mode = {"post": RELU_POST, "pre": RELU_PRE}.get(self.fuse_relu, RELU_NONE)
         return _BatchNormFunction.apply(x, self.weight if self.affine else None, self.bias if self.affine else None,
-                                        rm, rv, factor, self.eps)
+                                        rm, rv, factor, self.eps, mode)
+
+
+class FusedReLU(torch.nn.ReLU):
+    """torch.nn.ReLU of the UNet blocks (nn/unet.py:44, :47, :96, :107).  `fused = True` (set by `fuse_bn_relu`): the
+    neighbouring BatchNorm2d computes it, this module passes its input through (no parameters: state_dict unchanged)."""
+
+    fused = False
+
+    def forward(self, x):
+        return x if self.fused else super().forward(x)
+
+
+def fuse_bn_relu(seq: torch.nn.Sequential) -> torch.nn.Sequential:
+    """Pair every FusedReLU of `seq` with the BatchNorm2d right behind it (Conv -> ReLU -> BN: "pre") or right in front of
+    it (Conv -> BN -> ReLU: "post")."""
+    mods = list(seq.children())
+    for i, m in enumerate(mods):
+        if not isinstance(m, FusedReLU) or m.fused:
+            continue
+        prev = mods[i - 1] if i > 0 else None
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if isinstance(prev, BatchNorm2d) and prev.fuse_relu is None:
+            prev.fuse_relu, m.fused = "post", True
+        elif isinstance(nxt, BatchNorm2d) and nxt.fuse_relu is None:
+            nxt.fuse_relu, m.fused = "pre", True
+    return seq
+
+
+class _MaxPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k):
+        lib = L.load_library()
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, h // k, w // k), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.qiddm_maxpool2d_forward(L._ptr(x), L._ptr(y), _DT[x.dtype], n * c, h, w, k, _stream(x.device)),
+                    "qiddm_maxpool2d_forward")
+        ctx.save_for_backward(x)
+        ctx.k = k
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load_library()
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        n, c, h, w = x.shape
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(lib.qiddm_maxpool2d_backward(L._ptr(x), L._ptr(gy), L._ptr(gx), _DT[x.dtype], n * c, h, w, ctx.k,
+                                                 _stream(x.device)), "qiddm_maxpool2d_backward")
+        return gx, None
+
+
+class MaxPool2d(torch.nn.MaxPool2d):
+    """torch.nn.MaxPool2d(kernel_size=2, stride=2) of nn/unet.py:110 on the library's kernel (indices recomputed in the
+    backward); any other configuration, and CPU tensors, go through torch."""
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else (self.kernel_size[0] if self.kernel_size[0] == self.kernel_size[1] else None)
+        st = self.stride if isinstance(self.stride, int) else (self.stride[0] if self.stride[0] == self.stride[1] else None)
+        ok = (x.is_cuda and x.dtype in _DT and x.dim() == 4 and x.numel() > 0 and k is not None and st == k
+              and self.padding in (0, (0, 0)) and self.dilation in (1, (1, 1)) and not self.ceil_mode and not self.return_indices
+              and x.shape[2] >= k and x.shape[3] >= k)
+        if not ok:
+            return super().forward(x)
+        return _MaxPoolFunction.apply(x, int(k))
 
 
 class _UpsampleFunction(torch.autograd.Function):

@@ -3,7 +3,7 @@ quantum branch is the B200 QConv2d, and BatchNorm2d / the bilinear Upsample run 
 (qiddm_b200.nn.glue: same parameters and state_dict keys as the torch modules)."""
 import torch
 
-from .glue import BatchNorm2d, Upsample
+from .glue import BatchNorm2d, FusedReLU, MaxPool2d, Upsample, fuse_bn_relu
 from .qconv import QConv2d
 from .utils import autopad, get_label_embedding
 
@@ -26,16 +26,16 @@ class UpBlock(torch.nn.Module):
             Upsample(scale_factor=2, mode="bilinear"),
             Conv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=1, padding=0, qdepth=qdepth),
         ).double()
-        self.net = torch.nn.Sequential(
+        self.net = fuse_bn_relu(torch.nn.Sequential(
             Conv2d(in_channels=2 * out_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1,
                    qdepth=qdepth),
-            torch.nn.ReLU(),
+            FusedReLU(),
             BatchNorm2d(out_channels, dtype=torch.double),
             Conv2d(in_channels=out_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1,
                    qdepth=qdepth),
             BatchNorm2d(out_channels, dtype=torch.double),
-            torch.nn.ReLU(),
-        ).double()
+            FusedReLU(),
+        )).double()
 
     def forward(self, from_down, from_up):
         from_up = self.up_conv(from_up)
@@ -50,18 +50,18 @@ class DownBlock(torch.nn.Module):
         super().__init__()
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.pooling = kernel_size, pooling
-        self.net = torch.nn.Sequential(
+        self.net = fuse_bn_relu(torch.nn.Sequential(
             Conv2d(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size, qdepth=qdepth,
                    padding=1),
             BatchNorm2d(out_channels, dtype=torch.double),
-            torch.nn.ReLU(),
+            FusedReLU(),
             Conv2d(in_channels=out_channels, out_channels=out_channels, kernel_size=kernel_size, qdepth=qdepth,
                    padding=1),
             BatchNorm2d(out_channels, dtype=torch.double),
-            torch.nn.ReLU(),
-        ).double()
+            FusedReLU(),
+        )).double()
         if self.pooling:
-            self.pooling_layer = torch.nn.MaxPool2d(kernel_size=2, stride=2)
+            self.pooling_layer = MaxPool2d(kernel_size=2, stride=2)
 
     def forward(self, x):
         x = self.net(x.double())

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/j_pytest.log 2>&1; tail -3 gpurun_out/j_pytest.log; grep -n "^FAILED\|^E  " gpurun_out/j_pytest.log | head
+timeout 300 python bench.py --no-cpu-baseline --no-extras --secondary config3 --steps 5 > gpurun_out/j_bench.json 2> gpurun_out/j_bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/j_bench.json').read().strip().splitlines()[-1])
+c=d['secondary']['config3']; print('config3', round(c['value']), 'samples/s', round(c['ms_per_step'],3), 'eager', round(c['eager_ms_per_step'],3), 'launches', c['gpu_launches_per_step'])
+PY

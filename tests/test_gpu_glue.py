@@ -67,8 +67,8 @@ def test_bilinear_upsample_matches_torch(dtype, tol, cfg):
 
 
 def test_unet_with_library_glue_equals_torch_glue():
-    """UNetUndirected (QConv2d children) with the library BatchNorm2d / Upsample vs the same net run with the torch
-    modules (identical weights): outputs and gradients agree to float64 round-off of the glue."""
+    """UNetUndirected (QConv2d children) with the library BatchNorm2d (ReLU fused) / Upsample / MaxPool2d vs the same net run
+    with the torch modules (identical weights): outputs and gradients agree to float64 round-off of the glue."""
     from qiddm_b200 import nn
     torch.manual_seed(6)
     net = nn.UNetUndirected(depth=3, start_channels=4, qdepth=2).cuda()
@@ -87,6 +87,10 @@ def test_unet_with_library_glue_equals_torch_glue():
                 setattr(m, name, t)
             elif isinstance(child, nn.glue.Upsample):
                 setattr(m, name, torch.nn.Upsample(scale_factor=2, mode="bilinear"))
+            elif isinstance(child, nn.glue.FusedReLU):
+                setattr(m, name, torch.nn.ReLU())            # the fused pair becomes torch's BatchNorm2d + ReLU again
+            elif isinstance(child, nn.glue.MaxPool2d):
+                setattr(m, name, torch.nn.MaxPool2d(kernel_size=2, stride=2))
             else:
                 to_torch(child)
     to_torch(net)
@@ -156,3 +160,64 @@ def test_diffusion_step_fused_glue_equals_torch_glue():
 class _TorchMSE(torch.nn.Module):          # not `type(...) is MSELoss` -> Diffusion keeps the torch loss path
     def forward(self, a, b):
         return torch.nn.functional.mse_loss(a, b)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("mode", ["post", "pre"])
+def test_batchnorm_with_fused_relu_matches_the_torch_pair(dtype, tol, mode):
+    """nn/unet.py:92-108 `Conv -> BN -> ReLU` ("post") and :55-63 `Conv -> ReLU -> BN` ("pre"): the ReLU computed inside the
+    BatchNorm kernels equals the two torch modules, forward, input gradient, affine gradients and running statistics."""
+    from qiddm_b200.nn.glue import BatchNorm2d
+    torch.manual_seed(3)
+    x = torch.randn(6, 5, 9, 7, dtype=dtype, device="cuda")
+    go = torch.randn(6, 5, 9, 7, dtype=dtype, device="cuda")
+    ours = BatchNorm2d(5, dtype=dtype).cuda()
+    ours.fuse_relu = mode
+    ref = torch.nn.BatchNorm2d(5, dtype=dtype).cuda()
+    with torch.no_grad():
+        for m in (ours, ref):
+            m.weight.copy_(torch.linspace(-1.0, 1.5, 5))
+            m.bias.copy_(torch.linspace(-0.5, 0.5, 5))
+    xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yo = ours(xo)
+    yr = torch.relu(ref(xr)) if mode == "post" else ref(torch.relu(xr))
+    (yo * go).sum().backward()
+    (yr * go).sum().backward()
+    assert rel_to_max(yo, yr) <= tol
+    assert rel_to_max(xo.grad, xr.grad) <= tol * 50
+    assert rel_to_max(ours.weight.grad, ref.weight.grad) <= tol * 50
+    assert rel_to_max(ours.bias.grad, ref.bias.grad) <= tol * 50
+    assert rel_to_max(ours.running_mean, ref.running_mean) <= tol and rel_to_max(ours.running_var, ref.running_var) <= tol * 10
+    ours.eval(), ref.eval()
+    ye = ours(x)
+    yre = torch.relu(ref(x)) if mode == "post" else ref(torch.relu(x))
+    assert rel_to_max(ye, yre) <= max(tol, 1e-6 if dtype == torch.float32 else 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", [(3, 4, 8, 8), (2, 3, 7, 9), (1, 1, 28, 28)])
+def test_maxpool2d_matches_torch_including_ties(dtype, shape):
+    from qiddm_b200.nn.glue import MaxPool2d
+    torch.manual_seed(4)
+    x = torch.randn(*shape, dtype=dtype, device="cuda").clamp_min(0)          # ReLU-like input: many ties at 0
+    ours, ref = MaxPool2d(kernel_size=2, stride=2), torch.nn.MaxPool2d(kernel_size=2, stride=2)
+    xo, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yo, yr = ours(xo), ref(xr)
+    assert torch.equal(yo, yr)
+    go = torch.randn_like(yr)
+    (yo * go).sum().backward()
+    (yr * go).sum().backward()
+    assert torch.equal(xo.grad, xr.grad)
+
+
+def test_unet_blocks_fuse_their_relus_and_keep_the_state_dict_keys():
+    from qiddm_b200 import nn
+    from qiddm_b200.nn.glue import BatchNorm2d, FusedReLU
+    m = nn.UNetUndirected(3, 8, 0)
+    relus = [mod for mod in m.modules() if isinstance(mod, FusedReLU)]
+    bns = [mod for mod in m.modules() if isinstance(mod, BatchNorm2d)]
+    assert len(relus) == 10 and all(r.fused for r in relus)
+    assert sorted(b.fuse_relu for b in bns) == ["post"] * 8 + ["pre"] * 2
+    ref_keys = {"down_blocks.0.net.0.weight", "down_blocks.0.net.1.running_mean", "up_blocks.0.net.2.weight", "up_blocks.1.net.4.bias",
+                "final_conv.weight"}
+    assert ref_keys <= set(m.state_dict().keys())
