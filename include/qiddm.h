@@ -128,6 +128,15 @@ int qiddm_qconv_backward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold
                          const void *weights, int weights_dtype, const float *grad_out, float *grad_img,
                          void *grad_weights, void *workspace, int64_t n_images, qiddm_stream_t stream);
 
+/* The same with img / out / grad tensors of io_dtype (QIDDM_DTYPE_F32, or QIDDM_DTYPE_F64 as the reference's float64 UNet
+ * passes them: read and written in place of cast kernels; the simulation itself is fp32). */
+int qiddm_qconv_forward_io(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int io_dtype, const void *img,
+                           const void *weights, int weights_dtype, void *out, void *workspace, int64_t n_images,
+                           qiddm_stream_t stream);
+int qiddm_qconv_backward_io(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int io_dtype, const void *img,
+                            const void *weights, int weights_dtype, const void *grad_out, void *grad_img, void *grad_weights,
+                            void *workspace, int64_t n_images, qiddm_stream_t stream);
+
 /* Collapse the weight-only part of a circuit into its 2^n x 2^n unitary — the eval-mode matrix
  * of nn/qconv.py:92-126.  Stored TRANSPOSED (row c = U|c>, i.e. unitary[c][k] = U[k][c]),
  * interleaved re/im fp32, 2 * 4^n floats. */

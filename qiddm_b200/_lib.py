@@ -59,6 +59,7 @@ EXPORTS = [
     "qiddm_state_bytes", "qiddm_forward_save", "qiddm_backward_saved",
     "qiddm_noisy_workspace_bytes", "qiddm_noisy_forward",
     "qiddm_batchnorm_relu_forward", "qiddm_batchnorm_relu_backward", "qiddm_maxpool2d_forward", "qiddm_maxpool2d_backward",
+    "qiddm_qconv_forward_io", "qiddm_qconv_backward_io",
 ]
 
 _lib = None
@@ -113,6 +114,10 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_qconv_forward.argtypes = [vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, i64, vp]
         lib.qiddm_qconv_backward.restype = i32
         lib.qiddm_qconv_backward.argtypes = [vp, C.POINTER(UnfoldDesc), vp, vp, i32, vp, vp, vp, vp, i64, vp]
+        lib.qiddm_qconv_forward_io.restype = i32
+        lib.qiddm_qconv_forward_io.argtypes = [vp, C.POINTER(UnfoldDesc), i32, vp, vp, i32, vp, vp, i64, vp]
+        lib.qiddm_qconv_backward_io.restype = i32
+        lib.qiddm_qconv_backward_io.argtypes = [vp, C.POINTER(UnfoldDesc), i32, vp, vp, i32, vp, vp, vp, vp, i64, vp]
         lib.qiddm_build_unitary.restype = i32
         lib.qiddm_build_unitary.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.qiddm_launch_count.restype = i64
@@ -483,31 +488,35 @@ class Plan:
         w = self._check_weights(weights)
         _require_cuda(img, "input")
         dev = w.device
-        img = img.to(torch.float32).contiguous()
+        # float64 images (the reference's UNet) are read and written in place of a cast; the simulation is fp32
+        io = torch.float64 if img.dtype == torch.float64 else torch.float32
+        img = img.to(io).contiguous()
         n, c, h, wd = img.shape
         ho = h + 2 * unfold.pad_h - unfold.kernel_h + 1
         wo = wd + 2 * unfold.pad_w - unfold.kernel_w + 1
-        out = torch.empty((n, self.spec.read_count, ho, wo), dtype=torch.float32, device=dev)
+        out = torch.empty((n, self.spec.read_count, ho, wo), dtype=io, device=dev)
         ws = self._workspace(n * ho * wo, dev)
         with torch.cuda.device(dev):
-            check(self.lib.qiddm_qconv_forward(self.handle, C.byref(unfold), _ptr(img), _ptr(w), _wdtype(w),
-                                               _ptr(out), _ptr(ws), n, self._stream(dev)), "qiddm_qconv_forward")
+            check(self.lib.qiddm_qconv_forward_io(self.handle, C.byref(unfold), DTYPE_F64 if io == torch.float64 else DTYPE_F32,
+                                                  _ptr(img), _ptr(w), _wdtype(w), _ptr(out), _ptr(ws), n, self._stream(dev)),
+                  "qiddm_qconv_forward")
         return out
 
     def qconv_backward(self, img: torch.Tensor, weights: torch.Tensor, grad_out: torch.Tensor, unfold: UnfoldDesc,
                        need_grad_in: bool = True, need_grad_w: bool = True):
         w = self._check_weights(weights)
         dev = w.device
-        img = img.to(torch.float32).contiguous()
-        go = grad_out.to(torch.float32).contiguous()
+        io = torch.float64 if img.dtype == torch.float64 else torch.float32
+        img = img.to(io).contiguous()
+        go = grad_out.to(io).contiguous()
         n = img.shape[0]
         grad_img = torch.empty_like(img) if need_grad_in else None
         grad_w = torch.empty_like(w) if need_grad_w else None
         ws = self._workspace(n * go.shape[2] * go.shape[3], dev)
         with torch.cuda.device(dev):
-            check(self.lib.qiddm_qconv_backward(self.handle, C.byref(unfold), _ptr(img), _ptr(w), _wdtype(w),
-                                                _ptr(go), _ptr(grad_img), _ptr(grad_w), _ptr(ws), n,
-                                                self._stream(dev)), "qiddm_qconv_backward")
+            check(self.lib.qiddm_qconv_backward_io(self.handle, C.byref(unfold), DTYPE_F64 if io == torch.float64 else DTYPE_F32,
+                                                   _ptr(img), _ptr(w), _wdtype(w), _ptr(go), _ptr(grad_img), _ptr(grad_w),
+                                                   _ptr(ws), n, self._stream(dev)), "qiddm_qconv_backward")
         return grad_img, grad_w
 
     # ------------------------------------------------------------------ unitary-collapse (GEMM) path

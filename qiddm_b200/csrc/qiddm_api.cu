@@ -144,7 +144,7 @@ size_t gates_bytes(const qiddm_plan *pl) {
 
 int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
                  const void *weights, int wdtype, float *out, void *ws, long long B, cudaStream_t s, float *state = nullptr,
-                 const float *init_state = nullptr, int in_shift = 0) {
+                 const float *init_state = nullptr, int in_shift = 0, int io64 = 0) {
     if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     if (B == 0) return QIDDM_OK;
@@ -155,6 +155,7 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
     p.in = in; p.basis = basis; p.gates = gates; p.out = out;
     p.state = (state != nullptr && gate_state_compatible(pl->d.n_qubits, p)) ? state : nullptr;
     p.init_state = init_state; p.in_shift = in_shift;
+    p.io64 = (u != nullptr && io64) ? 1 : 0;
     if (pl->d.init == QIDDM_INIT_STATE && !init_state) return QIDDM_EINVAL;
     cudaError_t e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, false, p, gates, s);
     if (e != cudaSuccess) return (int)e;
@@ -166,7 +167,7 @@ int forward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *
 
 int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float *in, const int32_t *basis,
                   const void *weights, int wdtype, const float *grad_out, float *grad_in, void *grad_weights,
-                  void *ws, long long B, long long grad_in_elems, cudaStream_t s, const float *state = nullptr) {
+                  void *ws, long long B, long long grad_in_elems, cudaStream_t s, const float *state = nullptr, int io64 = 0) {
     if (!pl || !weights || !ws || B < 0) return QIDDM_EINVAL;
     if (wdtype != QIDDM_DTYPE_F32 && wdtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
     if (B > 0 && (!grad_out || (n_inputs(&pl->d) > 0 && !in))) return QIDDM_EINVAL;
@@ -177,6 +178,7 @@ int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float 
     p.in = in; p.basis = basis; p.gates = gates; p.out = nullptr;
     p.grad_out = grad_out; p.grad_in = grad_in; p.partials = partials;
     p.state = (state != nullptr && gate_state_compatible(pl->d.n_qubits, p)) ? const_cast<float *>(state) : nullptr;
+    p.io64 = (u != nullptr && io64) ? 1 : 0;
     cudaError_t e;
     if (B == 0) {
         if (grad_weights) {
@@ -186,7 +188,8 @@ int backward_impl(const qiddm_plan *pl, const qiddm_unfold_desc *u, const float 
         return QIDDM_OK;
     }
     if (u && grad_in) {
-        if ((e = cudaMemsetAsync(grad_in, 0, (size_t)grad_in_elems * sizeof(float), s)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(grad_in, 0, (size_t)grad_in_elems * (p.io64 ? sizeof(double) : sizeof(float)), s)) != cudaSuccess)
+            return (int)e;
     }
     if ((e = launch_prepare_tables(weights, wdtype, pl->d.remap, pl->d.n_qubits, true, p, gates, s)) != cudaSuccess)
         return (int)e;
@@ -305,6 +308,31 @@ int qiddm_qconv_backward(const qiddm_plan *plan, const qiddm_unfold_desc *unfold
     const long long img_elems = n_images * unfold->channels * unfold->height * unfold->width;
     return backward_impl(plan, unfold, img, nullptr, weights, weights_dtype, grad_out, grad_img, grad_weights,
                          workspace, n_images * P, img_elems, (cudaStream_t)stream);
+}
+
+int qiddm_qconv_forward_io(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int io_dtype, const void *img,
+                           const void *weights, int weights_dtype, void *out, void *workspace, int64_t n_images,
+                           qiddm_stream_t stream) {
+    if (!plan || !unfold_valid(plan, unfold) || n_images < 0) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    const long long P = (long long)(unfold->height + 2 * unfold->pad_h - unfold->kernel_h + 1) *
+                        (unfold->width + 2 * unfold->pad_w - unfold->kernel_w + 1);
+    return forward_impl(plan, unfold, reinterpret_cast<const float *>(img), nullptr, weights, weights_dtype,
+                        reinterpret_cast<float *>(out), workspace, n_images * P, (cudaStream_t)stream, nullptr, nullptr, 0,
+                        io_dtype == QIDDM_DTYPE_F64);
+}
+
+int qiddm_qconv_backward_io(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int io_dtype, const void *img,
+                            const void *weights, int weights_dtype, const void *grad_out, void *grad_img, void *grad_weights,
+                            void *workspace, int64_t n_images, qiddm_stream_t stream) {
+    if (!plan || !unfold_valid(plan, unfold) || n_images < 0) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    const long long P = (long long)(unfold->height + 2 * unfold->pad_h - unfold->kernel_h + 1) *
+                        (unfold->width + 2 * unfold->pad_w - unfold->kernel_w + 1);
+    const long long img_elems = n_images * unfold->channels * unfold->height * unfold->width;
+    return backward_impl(plan, unfold, reinterpret_cast<const float *>(img), nullptr, weights, weights_dtype,
+                         reinterpret_cast<const float *>(grad_out), reinterpret_cast<float *>(grad_img), grad_weights, workspace,
+                         n_images * P, img_elems, (cudaStream_t)stream, nullptr, io_dtype == QIDDM_DTYPE_F64);
 }
 
 int qiddm_build_unitary(const qiddm_plan *plan, const void *weights, int weights_dtype, float *unitary,

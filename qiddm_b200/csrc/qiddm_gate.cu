@@ -492,7 +492,8 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
                     if (active) {
                         if (p.unfold) {
                             const long long off = unfold_offset(p, geo, foff, fyx, k);
-                            x = off >= 0 ? __ldg(p.in + off) : 0.f;
+                            // io64: the image is float64 (the reference's UNet), read in place of a cast kernel
+                            x = off < 0 ? 0.f : (p.io64 ? (float)__ldg(reinterpret_cast<const double *>(p.in) + off) : __ldg(p.in + off));
                         } else {
                             x = __ldg(p.in + geo.in_base + k);
                         }
@@ -667,7 +668,11 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
                     const float2 a = psi[slot_of<RB>(m * p.read_stride)];
                     float v = p.post_scale * (a.x * a.x + a.y * a.y);
                     if (p.clamp) v = fminf(fmaxf(v, p.clamp_lo), p.clamp_hi);
-                    if (active) p.out[geo.out_base + (long long)m * geo.out_stride] = v;
+                    if (active) {
+                        const long long oi = geo.out_base + (long long)m * geo.out_stride;
+                        if (p.unfold && p.io64) reinterpret_cast<double *>(p.out)[oi] = (double)v;
+                        else p.out[oi] = v;
+                    }
                 }
             } else if (p.readout == QIDDM_READ_EXPVAL_Z) {
                 float ez[NQ];
@@ -712,7 +717,10 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
                     if (m * p.read_stride == k && m < p.read_count && active) {
                         const float v = p.post_scale * (a.x * a.x + a.y * a.y);
                         const bool pass = !p.clamp || (v >= p.clamp_lo && v <= p.clamp_hi);
-                        const float c = pass ? p.post_scale * __ldg(p.grad_out + geo.out_base + (long long)m * geo.out_stride) : 0.f;
+                        const long long gi_ = geo.out_base + (long long)m * geo.out_stride;
+                        const float go_ = (p.unfold && p.io64) ? (float)__ldg(reinterpret_cast<const double *>(p.grad_out) + gi_)
+                                                               : __ldg(p.grad_out + gi_);
+                        const float c = pass ? p.post_scale * go_ : 0.f;
                         l = make_float2(c * a.x, c * a.y);
                     }
                 } else if (p.readout == QIDDM_READ_EXPVAL_Z) {
@@ -927,7 +935,10 @@ __global__ void __launch_bounds__(Cfg<NQ, RB>::T, min_blocks<NQ, RB, BWD>()) gat
                             const float gvv = (2.f * lam[a].x - psi[a].x * dot) * inv_norm;
                             if (p.unfold) {
                                 const long long off = unfold_offset(p, geo, foff, fyx, k);
-                                if (off >= 0) atomicAdd(p.grad_in + off, gvv);
+                                if (off >= 0) {
+                                    if (p.io64) atomicAdd(reinterpret_cast<double *>(p.grad_in) + off, (double)gvv);
+                                    else atomicAdd(p.grad_in + off, gvv);
+                                }
                             } else {
                                 p.grad_in[geo.in_base + k] = gvv;
                             }
