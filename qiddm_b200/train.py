@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import copy
 import os
+import warnings
 from typing import Iterable, List, Optional
 
 import torch
@@ -217,7 +218,8 @@ class GraphedTrainStep:
         torch.cuda.current_stream(example_x.device).wait_stream(side)
         torch.cuda.synchronize(example_x.device)
         had_state = len(opt_state["state"]) > 0
-        with torch.no_grad():
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")                # QConv2d warns when a CHECKPOINT is loaded; this is our own snapshot
             diff.load_state_dict(model_state)              # in place: the parameter tensors stay the same objects
             if had_state:
                 optimizer.load_state_dict(opt_state)
