@@ -247,6 +247,7 @@ struct GemmParams {
     const unsigned int *gmax_bits;
     float add_offset;
     int dbg_pfd, dbg_nostore;   // tuning knobs (QIDDM_GEMM_PFD, QIDDM_GEMM_NOSTORE)
+    int dbg_skip;               // QIDDM_GEMM_SKIP_LOADS (timing experiments)
     int l2_hints;               // bit 0: epilogue TMA stores evict_first; bit 1: weight-side (B) operand loads evict_last;
                                 // bit 2: activation-side (A) operand loads evict_first; bit 3: LSU epilogue stores st.global.cs
     int out_f64;             // EPI_PROBS, QConv: `out` is a float64 tensor
@@ -852,10 +853,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 if (issuer) {
                     const uint32_t fb = fb0 + 8u * stage;
-                    if (leader) mbar_expect_tx(full_bar(stage), 2 * stage_bytes);
+                    // timing experiments only (QIDDM_GEMM_SKIP_LOADS: bit 0 = A operand, bit 1 = B operand; results are garbage)
+                    const bool skip_a = (p.dbg_skip & 1) != 0, skip_b = (p.dbg_skip & 2) != 0;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * ((skip_a ? 0u : N_A * a_bytes) + (skip_b ? 0u : N_B * b_bytes)));
                     const uint32_t sa = smem_base + stage * stage_bytes;
 #pragma unroll
-                    for (uint32_t i = 0; i < N_A; ++i) {
+                    for (uint32_t i = 0; i < (skip_a ? 0u : N_A); ++i) {
                         const uint32_t dst = sa + i * a_bytes;
                         if (AMN) {   // two (64 M) x (64 K) boxes from the row-major (K, M) array
                             tma_load_2d_pair(dst, &p.a_map[i], fb, m0, kb * BKT);
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                         }
                     }
 #pragma unroll
-                    for (uint32_t i = 0; i < N_B; ++i) {
+                    for (uint32_t i = 0; i < (skip_b ? 0u : N_B); ++i) {
                         const uint32_t dst = sa + N_A * a_bytes + i * b_bytes;
                         if (bmn) {   // (64 N) x (64 K) boxes from the row-major (K, N) array; columns past N/2 are not read
                             for (uint32_t j = 0; j < b_boxes; ++j)
@@ -1636,6 +1639,9 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         static int hints = -1;
         if (hints < 0) { const char *e = getenv("QIDDM_GEMM_L2_HINTS"); hints = e ? atoi(e) : 0; }
         p.l2_hints = hints;
+        static int skip = -1;
+        if (skip < 0) { const char *e = getenv("QIDDM_GEMM_SKIP_LOADS"); skip = e ? atoi(e) : 0; }
+        p.dbg_skip = skip;
     }
     static int bk32 = -1;
     if (bk32 < 0) { const char *e = getenv("QIDDM_GEMM_BK32"); bk32 = e ? atoi(e) : 0; }
