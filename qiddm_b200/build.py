@@ -44,9 +44,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     inc = [f"-I{ROOT / 'include'}", f"-I{CSRC}"]
     # one nvcc per translation unit, in parallel; then link
     procs, objs = [], []
+    hdr_t = max(d.stat().st_mtime for d in [*CSRC.glob("*.h"), *CSRC.glob("*.cuh"), ROOT / "include" / "qiddm.h"] if d.exists())
     for src in sources():
         obj = obj_dir / (src.stem + ".o")
         objs.append(obj)
+        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_t):
+            continue          # this translation unit is up to date
         cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", "-o", str(obj), str(src)]
         if verbose:
             print(" ".join(cmd))

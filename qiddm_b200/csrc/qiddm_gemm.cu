@@ -144,10 +144,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_k32(uint32_t addr) {
 
 // MN-major, SWIZZLE_128B: each K row is 128 B of 64 contiguous M elements; 8 K rows form a 1024-B atom
 // (SBO); the next 64 M elements start LBO = 8192 B later (second TMA box of the 128-row tile).
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo = 8192) {
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(lbo >> 4) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
@@ -230,6 +230,8 @@ struct GemmParams {
     int bn;               // BLOCK_N: multiple of 16, <= 256
     int bn_last;          // pair kernel: width of the LAST N tile (multiple of 16, <= bn): N = (tiles_n - 1) * bn + (<= bn_last)
     int stages;
+    int dual_n;           // pair kernel, MN-major operands: a work item = TWO neighbouring N tiles fed from one staged A tile
+                          // (both TMEM accumulators live at once, no epilogue overlap: for long split-K items)
     int k_splits;         // > 1: fp32 atomics into `out` (must be zeroed)
     int epi;
     float *out;
@@ -265,6 +267,13 @@ __device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
     int e;
     frexpf(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)
     return ldexpf(1.f, 14 - e);
+}
+// The scale every consumer of G uses.  bits[0]: the PROVISIONAL bound (sampled rows x margin, g_bound_kernel) the first
+// grad_y pass worked with; bits[1]: the exact bound over all rows, a by-product of that pass.  Only if the exact bound
+// exceeds the provisional one (an outlier row outside the sample) did grad_y run again with it.
+__device__ __forceinline__ float g_scale_final(const unsigned int *bits) {
+    const unsigned int b0 = bits[0], b1 = bits[1];
+    return g_scale_from_max(b1 > b0 ? b1 : b0);
 }
 
 // Epilogue of one accumulator tile for one warp: TMEM lanes [q*32, q*32+32), columns [cbeg, cend) -> registers ->
@@ -382,7 +391,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams &p, uint32_t tmem
     const float rs = (p.epi == EPI_PROBS && row < p.M) ? p.row_scale[row] * p.post_scale : 0.f;
     float dx_a = 0.f, dx_b = 0.f;
     if (p.epi == EPI_DX && row < p.M) {
-        dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
+        dx_a = 1.f / g_scale_final(p.gmax_bits);
         dx_b = p.dx_x != nullptr ? -2.f * p.row_scale[row] * p.dx_S[row] : 0.f;
     }
     uint32_t ra[16], rb[16];
@@ -582,7 +591,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams &p, uint32_t 
     const float rs = (p.epi == EPI_PROBS && row_ok) ? p.row_scale[row] * p.post_scale : 0.f;
     float dx_a = 0.f, dx_b = 0.f;
     if (p.epi == EPI_DX && row_ok) {
-        dx_a = 1.f / g_scale_from_max(*p.gmax_bits);
+        dx_a = 1.f / g_scale_final(p.gmax_bits);
         dx_b = p.dx_x != nullptr ? -2.f * p.row_scale[row] * p.dx_S[row] : 0.f;
     }
     const uint32_t sw = (uint32_t)((lane >> 1) & 3);       // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
@@ -764,18 +773,23 @@ __device__ __forceinline__ void epilogue_tile_lsu(const GemmParams &p, uint32_t 
     }
 }
 
-template <int NSEG, bool AMN, int BKT>
+// DUAL (MN-major operands only): a work item is TWO neighbouring N tiles fed from one staged A tile -- both TMEM accumulator
+// stages live at once, plain epilogue after the item (long split-K items: the dW GEMM of big batches).
+template <int NSEG, bool AMN, int BKT, bool DUAL = false>
 __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    static_assert(BKT == 64 || (BKT == 32 && !AMN), "K-major tiles: 64 or 32 fp16 per row; MN-major: 64");
+    static_assert(BKT == 64 || BKT == 32, "K-major tiles: 64 or 32 fp16 per row; MN-major: 64 or 32 K rows per box");
     constexpr uint32_t N_A = NSEG > 1 ? 2 : 1, N_B = NSEG > 1 ? 2 : 1;   // hi (and lo) tiles of each operand per stage
     constexpr uint32_t a_bytes = BM * BKT * 2;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     // this CTA's half of the B tile: K-major rows of BKT elements, or (MN-major) whole 64-column boxes of 64 K rows
     const bool bmn = AMN && p.b_mn != 0;
     const uint32_t b_boxes = (uint32_t)(p.bn / 2 + 63) / 64;
-    const uint32_t b_bytes = bmn ? b_boxes * 8192u : (uint32_t)(p.bn / 2) * BKT * 2;
-    const uint32_t stage_bytes = N_A * a_bytes + N_B * b_bytes;
+    constexpr uint32_t mn_box = 64u * BKT * 2u;                       // one (64 M or N) x (BKT K rows) box
+    const uint32_t b_bytes = bmn ? b_boxes * mn_box : (uint32_t)(p.bn / 2) * BKT * 2;
+    static_assert(!DUAL || AMN, "dual-N items: MN-major operands");
+    constexpr bool dual = DUAL;
+    const uint32_t stage_bytes = N_A * a_bytes + N_B * b_bytes * (dual ? 2u : 1u);
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -811,7 +825,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);       // 256-row tiles
-    const int tiles_n = (p.N + p.bn - 1) / p.bn;
+    const int tiles_n_all = (p.N + p.bn - 1) / p.bn;
+    const int tiles_n = dual ? (tiles_n_all + 1) / 2 : tiles_n_all;     // dual: items along N, each two tiles wide
     const int KB = (p.K + BKT - 1) / BKT;
     const long long tiles_mn = (long long)tiles_m * tiles_n;
     const long long total = tiles_mn * p.k_splits;
@@ -831,7 +846,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             const int tm = (int)(tile / tiles_n), tn = (int)((tile % tiles_n + tm) % tiles_n);   // skewed by tm (see the MMA warp)
             const int m0 = tm * 2 * BM + (int)rank * BM;
             const int bn_t = tn == tiles_n - 1 ? p.bn_last : p.bn;      // the last N tile may be narrower (no padded MMA columns)
-            const int nb0 = tn * p.bn + (int)rank * (bn_t / 2);
+            const int nb0 = (dual ? 2 * tn : tn) * p.bn + (int)rank * (bn_t / 2);
+            const uint32_t nt = (dual && 2 * tn + 1 < tiles_n_all) ? 2u : 1u;   // N tiles of this item
             const int kb0 = (int)((long long)split * KB / p.k_splits);
             const int kb1 = (int)((long long)(split + 1) * KB / p.k_splits);
             // where this pair's next work item starts (for prefetching across the tile boundary)
@@ -855,7 +871,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     const uint32_t fb = fb0 + 8u * stage;
                     // timing experiments only (QIDDM_GEMM_SKIP_LOADS: bit 0 = A operand, bit 1 = B operand; results are garbage)
                     const bool skip_a = (p.dbg_skip & 1) != 0, skip_b = (p.dbg_skip & 2) != 0;
-                    if (leader) mbar_expect_tx(full_bar(stage), 2 * ((skip_a ? 0u : N_A * a_bytes) + (skip_b ? 0u : N_B * b_bytes)));
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * ((skip_a ? 0u : N_A * a_bytes) + (skip_b ? 0u : nt * N_B * b_bytes)));
                     const uint32_t sa = smem_base + stage * stage_bytes;
 #pragma unroll
                     for (uint32_t i = 0; i < (skip_a ? 0u : N_A); ++i) {
@@ -872,9 +888,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
 #pragma unroll
                     for (uint32_t i = 0; i < (skip_b ? 0u : N_B); ++i) {
                         const uint32_t dst = sa + N_A * a_bytes + i * b_bytes;
-                        if (bmn) {   // (64 N) x (64 K) boxes from the row-major (K, N) array; columns past N/2 are not read
-                            for (uint32_t j = 0; j < b_boxes; ++j)
-                                tma_load_2d_pair(dst + j * 8192u, &p.b_map[i], fb, nb0 + 64 * (int)j, kb * BKT);
+                        if (bmn) {   // (64 N) x (BKT K) boxes from the row-major (K, N) array; columns past N/2 are not read
+                            for (uint32_t t = 0; t < nt; ++t)
+                                for (uint32_t j = 0; j < b_boxes; ++j)
+                                    tma_load_2d_pair(dst + t * N_B * b_bytes + j * mn_box, &p.b_map[i], fb,
+                                                     nb0 + (int)t * p.bn + 64 * (int)j, kb * BKT);
                         } else if (p.l2_hints & 2) {
                             tma_load_2d_pair_hint(dst, &p.b_map[i], fb, kb * BKT, nb0, pol_last);
                         } else {
@@ -914,7 +932,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                 // N tile of item w, skewed by its M tile: with a narrower last N tile the items are not equally long, and the
                 // persistent round-robin (pair p takes w = p, p + n_pairs, ...) must not hand some pairs only the wide ones
                 const long long tile_w = w % tiles_mn;
-                const int bn_t = (int)((tile_w % tiles_n + tile_w / tiles_n) % tiles_n) == tiles_n - 1 ? p.bn_last : p.bn;
+                const int tn_w = (int)((tile_w % tiles_n + tile_w / tiles_n) % tiles_n);
+                const int bn_t = tn_w == tiles_n - 1 ? p.bn_last : p.bn;
+                const bool two = dual && 2 * tn_w + 1 < tiles_n_all;          // second N tile of a dual item
                 const uint32_t idesc = idesc0 | ((uint32_t)(bn_t >> 3) << 17);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
@@ -923,12 +943,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    const uint64_t ad0 = AMN ? make_smem_desc_mn(sa) : (BKT == 64 ? make_smem_desc(sa) : make_smem_desc_k32(sa));
-                    const uint64_t ad1 = AMN ? make_smem_desc_mn(sa + a_bytes)
+                    const uint64_t ad0 = AMN ? make_smem_desc_mn(sa, mn_box) : (BKT == 64 ? make_smem_desc(sa) : make_smem_desc_k32(sa));
+                    const uint64_t ad1 = AMN ? make_smem_desc_mn(sa + a_bytes, mn_box)
                                              : (BKT == 64 ? make_smem_desc(sa + a_bytes) : make_smem_desc_k32(sa + a_bytes));
-                    const uint64_t bd0 = bmn ? make_smem_desc_mn(sa + N_A * a_bytes)
+                    const uint64_t bd0 = bmn ? make_smem_desc_mn(sa + N_A * a_bytes, mn_box)
                                              : (BKT == 64 ? make_smem_desc(sa + N_A * a_bytes) : make_smem_desc_k32(sa + N_A * a_bytes));
                     const uint64_t bstep = (uint64_t)(b_bytes >> 4);
+                    const uint64_t btile = (uint64_t)((N_B * b_bytes) >> 4);        // dual: the second N tile's operand
                     // the last k-block of the operands only issues the 16-wide steps that hold data (the rest is zero fill)
                     const int ksteps = kb == KB - 1 ? (p.K - kb * BKT + UMMA_K - 1) / UMMA_K : BKT / UMMA_K;
                     if (issuer) {
@@ -938,9 +959,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                             const uint64_t bdesc = seg == 2 ? bd0 + bstep : bd0;
 #pragma unroll
                             for (int k = 0; k < BKT / UMMA_K; ++k)
-                                if (k < ksteps)
-                                    tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc,
-                                                    (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u);
+                                if (k < ksteps) {
+                                    const uint32_t accum = (kb > kb0 || seg > 0 || k > 0) ? 1u : 0u;
+                                    tc_mma_f16_pair(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, accum);
+                                    if (two) tc_mma_f16_pair(d_tmem + ACC_COLS, adesc + a_step * k, bdesc + btile + b_step * k, idesc, accum);
+                                }
                         }
                         tc_commit_pair(empty_bar(stage));
                         if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc));
@@ -948,7 +971,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (dual) acc_phase ^= 1;                    // one accumulator stage holding both tiles
+                else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -964,7 +988,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int bn_t = tn == tiles_n - 1 ? p.bn_last : p.bn;
-            if (p.tma_epi == 2)
+            if constexpr (DUAL) {
+                const int row0 = tm * 2 * BM + (int)rank * BM;
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t)        // not unrolled: one copy of the epilogue body
+                    if (2 * tn + t < tiles_n_all)
+                        epilogue_tile(p, tmem_base + (uint32_t)t * ACC_COLS, row0, (2 * tn + t) * p.bn, q, lane, 0, p.bn);
+            } else if (p.tma_epi == 2)
                 epilogue_tile_lsu(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, bn_t);
             else if (p.tma_epi)
                 epilogue_tile_tma(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, buf, bn_t);
@@ -973,7 +1003,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(te0 + 8u * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (dual) acc_phase ^= 1;
+            else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (p.tma_epi == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -1377,8 +1408,12 @@ __global__ void fold_bias_kernel(const float *bias, int N, int Kp, int F, __half
 
 // Upper bound of max |G| (for the fp16 range) without touching Y: |Y'| <= w_scale * |f| (U is unitary), so
 // |G[b,n]| = 2 |g| scale inv_n2 |Y'| <= 2 max_m|g[b,m]| * scale * sqrt(inv_n2[b]) * w_scale.
+// Only every `row_stride`-th row is read (B = number of SAMPLED rows) and the result is multiplied by `margin`: a provisional
+// bound -- fp16 hi/lo operands keep 22 bits of anything within 2^16 of the largest element, so a scale that is a few binades
+// conservative costs nothing, and grad_y_kernel checks it against the exact bound as it streams every row anyway.
 __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const float *inv_n2, long long B, int n_out,
-                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P, int gw, int go_f64) {
+                                                      float scale, float w_scale, unsigned int *gmax_bits, int go_P, int gw, int go_f64,
+                                                      long long row_stride, float margin) {
     // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp (small QConv rows keep the lanes busy)
     const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1386,8 +1421,9 @@ __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const flo
     const bool vec = gw == 32 && go_P == 0 && (n_out & 3) == 0 && ((uintptr_t)go & 15) == 0;
     float best = 0.f;
     for (long long rbase = warp0 * rpw; rbase < B; rbase += nwarps * rpw) {
-        const long long row = rbase + lane / gw;
-        const bool active = row < B;
+        const long long srow = rbase + lane / gw;
+        const bool active = srow < B;
+        const long long row = srow * row_stride;
         float mx = 0.f;
         if (!active) {
         } else if (go_P > 0) {        // QConv: grad_out is NCHW, element (row, m) at ((b * n_out + m) * P + r)
@@ -1407,21 +1443,29 @@ __global__ void __launch_bounds__(256) g_bound_kernel(const float *go, const flo
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    best *= margin;
     if (lane == 0 && best > 0.f && best < 3.0e38f) atomicMax(gmax_bits, __float_as_uint(best));
 }
 
 // One streaming pass over Y (= X W' + bias', saved by the forward GEMM) and grad_out, one warp per row:
 //   out = scale inv_n2 |Y|^2, mask = !clamp || lo <= out <= hi,  G[2m+ri] = 2 g mask scale inv_n2 Y[2m+ri]
 // written as scaled fp16 (hi, lo) row-major (B,Np); S[b] = sum_m g mask out (normalisation term of dX).
+// Scale of G: pass 0 (retry == 0) works with the provisional bound gmax_bits[0] and, reading every row of grad_out anyway,
+// leaves the exact bound (same formula as g_bound_kernel) in gmax_bits[1]; pass 1 (retry == 1, launched only when the
+// provisional bound came from a sample of the rows) returns at once unless the exact bound turned out larger, and then
+// redoes the pass with it.  Consumers use g_scale_final().
 __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float *go, const float *inv_n2, long long B,
                                                      int N, int Np, int n_out, float scale, int clamp, float lo,
-                                                     float hi, const unsigned int *gmax_bits, __half *Gh, __half *Gl,
-                                                     float *S, int want_lo, int go_P, int gw, int go_f64) {
+                                                     float hi, unsigned int *gmax_bits, __half *Gh, __half *Gl,
+                                                     float *S, int want_lo, int go_P, int gw, int go_f64, float w_scale,
+                                                     int retry) {
     // a group of `gw` lanes (power of two <= 32) per row, 32 / gw rows per warp
     const int lane = threadIdx.x & 31, sub = lane & (gw - 1), rpw = 32 / gw;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const float gsc = g_scale_from_max(*gmax_bits);
+    if (retry && gmax_bits[1] <= gmax_bits[0]) return;
+    const float gsc = g_scale_from_max(gmax_bits[retry ? 1 : 0]);
+    float bound = 0.f;      // pass 0: this lane's share of max_b 2 max_m |g[b,m]| scale sqrt(inv_n2[b]) w_scale
     // 4 outputs (8 columns of Y / G) per lane and iteration when everything is 16-byte aligned
     const bool vec = gw == 32 && go_P == 0 && (n_out & 3) == 0 && Np == N &&
                      (((uintptr_t)Y | (uintptr_t)go | (uintptr_t)Gh | (uintptr_t)Gl) & 15) == 0;
@@ -1430,7 +1474,7 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
         const bool active = r < B;
         const float in2 = active ? inv_n2[r] : 0.f;
         const float k0 = scale * in2, k1 = 2.f * scale * in2 * gsc;
-        float s_part = 0.f;
+        float s_part = 0.f, mx = 0.f;
         if (vec) {
             const float4 *y4 = reinterpret_cast<const float4 *>(Y + r * N);
             const float4 *g4 = reinterpret_cast<const float4 *>(go + r * n_out);
@@ -1439,6 +1483,7 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
                 const float4 ya = __ldg(y4 + 2 * i), yb = __ldg(y4 + 2 * i + 1), gg = __ldg(g4 + i);
                 const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
                 const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(gg.x), fabsf(gg.y))), fmaxf(fabsf(gg.z), fabsf(gg.w)));
                 __half2 hh[4], ll[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -1468,7 +1513,9 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
                     const float outv = k0 * (y.x * y.x + y.y * y.y);
                     const bool pass = !clamp || (outv >= lo && outv <= hi);
                     const long long gi = go_P > 0 ? ((r / go_P) * n_out + m) * go_P + (r % go_P) : r * n_out + m;
-                    const float g = pass ? (go_P > 0 ? ld_io(go, gi, go_f64) : __ldg(go + gi)) : 0.f;
+                    const float graw = go_P > 0 ? ld_io(go, gi, go_f64) : __ldg(go + gi);
+                    mx = fmaxf(mx, fabsf(graw));
+                    const float g = pass ? graw : 0.f;
                     gre = k1 * g * y.x;
                     gim = k1 * g * y.y;
                     s_part += g * outv;
@@ -1484,6 +1531,12 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
         for (int o = 16; o > 0; o >>= 1)
             if (o < gw) s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
         if (sub == 0 && active) S[r] = s_part;
+        if (active) bound = fmaxf(bound, 2.f * mx * scale * sqrtf(in2) * w_scale);   // lanes of a row group hold partial maxima
+    }
+    if (!retry) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        if (lane == 0 && bound > 0.f && bound < 3.0e38f) atomicMax(gmax_bits + 1, __float_as_uint(bound));
     }
 }
 
@@ -1492,7 +1545,7 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
 // dWT[n][F] is the ones-column entry = sum_b G[b,n].
 __global__ void assemble_gut_kernel(const float *dWT, const unsigned int *gmax_bits, int A, int F, int ldw, int N,
                                     int stride, float w_scale, float pad, float *gUT) {
-    const float k = w_scale / g_scale_from_max(*gmax_bits);
+    const float k = w_scale / g_scale_final(gmax_bits);
     const long long total = (long long)A * A * 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ri = (int)(i & 1);
@@ -1645,14 +1698,21 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
     }
     static int bk32 = -1;
     if (bk32 < 0) { const char *e = getenv("QIDDM_GEMM_BK32"); bk32 = e ? atoi(e) : 0; }
-    const int bkt = (pair && !a_mn && bk32) ? 32 : BK;       // optional 32-wide k-blocks (finer stages; measured slower)
+    // MN-major dual-N items (p.dual_n, set by the caller): 32-row k-blocks keep four 48 KB stages in flight where 64-row
+    // ones would leave two of 96 KB; K-major: optional 32-wide k-blocks (finer stages; measured slower)
+    static int dw_bk = -1;
+    if (dw_bk < 0) { const char *e = getenv("QIDDM_GEMM_DW_BK"); dw_bk = e ? atoi(e) : 32; }
+    if (!(b_mn && pair)) p.dual_n = 0;
+    if (p.dual_n) p.bn_last = p.bn;
+    const int bkt = a_mn ? ((pair && p.dual_n && dw_bk == 32) ? 32 : BK) : ((pair && bk32) ? 32 : BK);
     const __half *as[2] = {A.h, A.l};
     const __half *bs[2] = {Bm.h, Bm.l};
     int rc;
     for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
-        if ((rc = make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, a_mn ? 64 : BM, bkt)) != QIDDM_OK) return rc;
+        if ((rc = a_mn ? make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, bkt, 64)      // (64 M) x (bkt K rows) boxes
+                       : make_map(&p.a_map[i], as[i], a_rows, a_cols, a_pitch, BM, bkt)) != QIDDM_OK) return rc;
     for (int i = 0; i < (n_seg > 1 ? 2 : 1); ++i)
-        if ((rc = b_mn ? make_map(&p.b_map[i], bs[i], b_rows, b_cols, b_pitch, 64, 64)
+        if ((rc = b_mn ? make_map(&p.b_map[i], bs[i], b_rows, b_cols, b_pitch, bkt, 64)
                        : make_map(&p.b_map[i], bs[i], b_rows, K, b_pitch, pair ? p.bn / 2 : p.bn, bkt)) != QIDDM_OK) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1688,8 +1748,8 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
                 p.tma_epi = 2;
         }
         const int epi_bytes = p.tma_epi ? 4 * 2 * EPI_STAGE_BYTES + 512 : 0;
-        const int b_tile_bytes = b_mn ? ((p.bn / 2 + 63) / 64) * 8192 : (p.bn / 2) * bkt * 2;
-        const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + b_tile_bytes);
+        const int b_tile_bytes = b_mn ? ((p.bn / 2 + 63) / 64) * (64 * bkt * 2) : (p.bn / 2) * bkt * 2;
+        const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + b_tile_bytes * (p.dual_n ? 2 : 1));
         int stages = (226 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes;
         static int max_stages = -1;
         if (max_stages < 0) { const char *ev = getenv("QIDDM_GEMM_STAGES"); max_stages = ev ? atoi(ev) : 8; }
@@ -1699,18 +1759,21 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         p.stages = stages;
         const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
         void (*kern)(const GemmParams);
-        if (a_mn) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64> : gemm_pair_kernel<1, true, 64>;
+        if (a_mn && p.dual_n && bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 32, true> : gemm_pair_kernel<1, true, 32, true>;
+        else if (a_mn && p.dual_n) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64, true> : gemm_pair_kernel<1, true, 64, true>;
+        else if (a_mn) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64> : gemm_pair_kernel<1, true, 64>;
         else if (bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, false, 32> : gemm_pair_kernel<1, false, 32>;
         else kern = n_seg > 1 ? gemm_pair_kernel<3, false, 64> : gemm_pair_kernel<1, false, 64>;
         // the opt-in shared-memory limit of a function is per device: remembered per (device, instantiation)
-        static std::atomic<bool> attr_set2[64][6];
-        const int ki = (n_seg > 1 ? 3 : 0) + (a_mn ? 2 : (bkt == 32 ? 1 : 0));
+        static std::atomic<bool> attr_set2[64][10];
+        const int ki = p.dual_n ? (bkt == 32 ? 6 : 8) + (n_seg > 1 ? 1 : 0) : (n_seg > 1 ? 3 : 0) + (a_mn ? 2 : (bkt == 32 ? 1 : 0));
         if (!attr_set2[dev & 63][ki].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_set2[dev & 63][ki].store(true, std::memory_order_release);
         }
-        const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + p.bn - 1) / p.bn) * k_splits;
+        const int tiles_n = (N + p.bn - 1) / p.bn;
+        const long long tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * (p.dual_n ? (tiles_n + 1) / 2 : tiles_n) * k_splits;
         const int pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
@@ -1954,23 +2017,33 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     cudaError_t e;
     const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
     // (1) scale bound, then one streaming pass: G splits (row-major) and S
-    if ((e = cudaMemsetAsync(gmax, 0, 4, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(gmax, 0, 8, s)) != cudaSuccess) return (int)e;
     const int warps = 8;
     timing_begin(TK_G_BOUND, 0.0, s);
     int gw = 32;                                       // lanes per row: smallest power of two >= Np / 2
     while (gw > 1 && gw / 2 >= g.Np / 2) gw >>= 1;
     const long long row_warps = (B * gw + 31) / 32;
     const unsigned ew_grid = (unsigned)((row_warps + warps - 1) / warps < 148 * 8 ? (row_warps + warps - 1) / warps : 148 * 8);
-    g_bound_kernel<<<ew_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, B, g.n_out, eff_scale, g.w_scale, gmax, go_P, gw,
-                                                  gp.unfold ? gp.io64 : 0);
+    // large batches: the provisional bound reads every 64th row only (x 2^6 margin: the hi/lo operands have 2^16 of slack)
+    // and grad_y verifies it against the exact bound it accumulates on the way (second, normally empty, launch below)
+    static int gsample = -1;
+    if (gsample < 0) { const char *ev = getenv("QIDDM_GEMM_GSAMPLE"); gsample = ev ? atoi(ev) : 64; if (gsample < 1) gsample = 1; }
+    const long long g_stride = (gsample > 1 && B >= 16384) ? gsample : 1;
+    const long long Bs = (B + g_stride - 1) / g_stride;
+    const long long s_warps = (Bs * gw + 31) / 32;
+    const unsigned s_grid = (unsigned)((s_warps + warps - 1) / warps < 148 * 8 ? (s_warps + warps - 1) / warps : 148 * 8);
+    g_bound_kernel<<<s_grid, warps * 32, 0, s>>>(grad_out, w.inv_n2, Bs, g.n_out, eff_scale, g.w_scale, gmax, go_P, gw,
+                                                 gp.unfold ? gp.io64 : 0, g_stride, g_stride > 1 ? 64.f : 1.f);
     timing_end(s);
     count_launch();
     timing_begin(TK_GRAD_Y, 0.0, s);
-    grad_y_kernel<<<ew_grid, warps * 32, 0, s>>>(
-        w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
-        Gs[1], S, n_seg > 1, go_P, gw, gp.unfold ? gp.io64 : 0);
+    for (int retry = 0; retry < (g_stride > 1 ? 2 : 1); ++retry) {
+        grad_y_kernel<<<ew_grid, warps * 32, 0, s>>>(
+            w.Y, grad_out, w.inv_n2, B, g.N, g.Np, g.n_out, eff_scale, gp.clamp, gp.clamp_lo, gp.clamp_hi, gmax, Gs[0],
+            Gs[1], S, n_seg > 1, go_P, gw, gp.unfold ? gp.io64 : 0, g.w_scale, retry);
+        count_launch();
+    }
     timing_end(s);
-    count_launch();
     GemmParams p;
     int rc;
     ActOperand Go{Gs[0], Gs[1]};
@@ -2011,7 +2084,14 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
         const int bn = xt ? pick_bn(g.Fx) : pick_bn_mn(g.Fx);
         const bool pair = use_pair_kernel();
         const int bm = pair ? 2 * BM : BM;
-        const int tiles = ((g.N + bm - 1) / bm) * ((g.Fx + bn - 1) / bn);
+        // long split-K items (big batches) of the MN-major GEMM: two neighbouring N tiles per item share one staged G tile
+        // (25 % fewer operand bytes per MMA through L2 -> shared memory, and G is read once per tile PAIR)
+        static int dw_dual = -1;
+        if (dw_dual < 0) { const char *ev = getenv("QIDDM_GEMM_DW_DUAL"); dw_dual = ev ? atoi(ev) : 1; }
+        const int tiles_n = (g.Fx + bn - 1) / bn;
+        const bool dual = dw_dual && !xt && pair && tiles_n >= 2 && Bp >= 65536;
+        p.dual_n = dual ? 1 : 0;
+        const int tiles = ((g.N + bm - 1) / bm) * (dual ? (tiles_n + 1) / 2 : tiles_n);
         const long long kt = pair ? (Bp + BK - 1) / BK : (long long)n_seg * ((Bp + BK - 1) / BK);
         // split-K over the batch: fill whole waves of the persistent grid (items = tiles * splits close to a multiple of the
         // number of CTAs / pairs), with a small price per split for its fp32 atomics
