@@ -168,6 +168,22 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
                         int weights_dtype, const float *grad_out, const void *saved, float *grad_in,
                         void *grad_weights, void *workspace, int64_t batch, int precision, qiddm_stream_t stream);
 
+/* Fused diffusion TRAINING STEP of a single amplitude-embedding layer on the unitary-collapse path: what
+ * `Diffusion.run_training_step_data / _noise` (src/models.py:44-104) do around `QDenseUndirected_old[_noise].forward`
+ * (nn/qdense.py:56-66, :95-111) with `add_normal_noise_multiple` (src/noise.py:105-126) and MSELoss -- noise ladder ->
+ * circuit -> loss -> d loss / d weights -- in four launches with no (rows x pixels) fp32 intermediate in HBM:
+ *   rows (b, t), t < T:  in = level_{t+1}(b),  out = layer(in),  d = a out + b - (c0 level_t(b) + c1 level_{t+1}(b)),
+ *   level_k(b) = clamp(x[b] (1 - w[k]) + eps[b] w[k], 0, 1),  loss = mean(d^2)  (goal "data": a 1, b 0, c0 1, c1 0;
+ *   goal "noise": a 0.1, b -0.05, c0 -1, c1 1),  grad_weights = d loss / d weights (written, not accumulated).
+ * x: (n_images, n_features) float32 / float64 (io_dtype), eps: (n_images, n_features) float32, w: (T + 1) level weights in
+ * io_dtype, loss: one io_dtype scalar on the device.  Needs read_count == n_features (the layer reconstructs its input).
+ * `collapsed` from qiddm_gemm_prepare for the same weights.  workspace: qiddm_dense_mse_step_workspace_bytes. */
+size_t qiddm_dense_mse_step_workspace_bytes(const qiddm_plan *plan, int64_t n_images, int T);
+int qiddm_dense_mse_step(const qiddm_plan *plan, const void *collapsed, const void *x, const float *eps, const void *w,
+                         int io_dtype, int64_t n_images, int T, double a, double b, double c0, double c1,
+                         const void *weights, int weights_dtype, void *loss, void *grad_weights, void *workspace,
+                         int precision, int bwd_precision, qiddm_stream_t stream);
+
 /* QConv on the unitary-collapse path (replaces torch.nn.Unfold + einops + the missing QNode call of
  * nn/qconv.py:76-86 and, in eval mode, the QubitUnitary path of nn/qconv.py:92-126): `collapsed` comes from
  * qiddm_gemm_prepare; img (n_images, C, H, W) and out / grad_out (n_images, read_count, H_out, W_out) are NCHW tensors

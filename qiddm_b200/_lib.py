@@ -60,6 +60,7 @@ EXPORTS = [
     "qiddm_noisy_workspace_bytes", "qiddm_noisy_forward",
     "qiddm_batchnorm_relu_forward", "qiddm_batchnorm_relu_backward", "qiddm_maxpool2d_forward", "qiddm_maxpool2d_backward",
     "qiddm_qconv_forward_io", "qiddm_qconv_backward_io",
+    "qiddm_dense_mse_step_workspace_bytes", "qiddm_dense_mse_step",
 ]
 
 _lib = None
@@ -139,6 +140,10 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_maxpool2d_forward.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp]
         lib.qiddm_maxpool2d_backward.restype = i32
         lib.qiddm_maxpool2d_backward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp]
+        lib.qiddm_dense_mse_step_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_dense_mse_step_workspace_bytes.argtypes = [vp, i64, i32]
+        lib.qiddm_dense_mse_step.restype = i32
+        lib.qiddm_dense_mse_step.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, f64, f64, f64, f64, vp, i32, vp, vp, vp, i32, i32, vp]
         lib.qiddm_noise_ladder.restype = i32
         lib.qiddm_noise_ladder.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]
         lib.qiddm_mse_workspace_bytes.restype = C.c_size_t
@@ -646,6 +651,34 @@ class Plan:
                                                _ptr(saved), _ptr(grad_in), _ptr(grad_w), _ptr(ws), batch,
                                                self.spec.bwd_precision, self._stream(dev)), "qiddm_gemm_backward")
         return grad_in, grad_w
+
+    def dense_mse_step(self, x: torch.Tensor, eps: torch.Tensor, level_w: torch.Tensor, T: int, weights: torch.Tensor,
+                       a: float = 1.0, b: float = 0.0, c0: float = 1.0, c1: float = 0.0):
+        """Fused diffusion training step of a single amplitude-embedding layer (qiddm_dense_mse_step): images x
+        (n, pixels) float32 / float64, noise draw eps (n, pixels) float32, level weights (T + 1) -> (loss 0-d tensor in
+        x.dtype, d loss / d weights).  Rows (b, t): in = level_{t+1}, target = c0 level_t + c1 level_{t+1}, d = a out + b - target."""
+        _require_cuda(x, "images")
+        w = self._check_weights(weights)
+        col = self.gemm_prepare(weights)
+        dev = col.device
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float32)
+        x = x.contiguous()
+        eps = eps.to(device=dev, dtype=torch.float32).contiguous()
+        level_w = level_w.to(device=dev, dtype=x.dtype).contiguous()
+        if x.dim() != 2 or eps.shape != x.shape or level_w.numel() != T + 1 or x.shape[1] != self.spec.n_in:
+            raise QiddmError(f"dense_mse_step: images {tuple(x.shape)}, eps {tuple(eps.shape)}, {level_w.numel()} level weights for T = {T}")
+        n = x.shape[0]
+        loss = torch.empty((), dtype=x.dtype, device=dev)
+        grad_w = torch.empty_like(w)
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(int(self.lib.qiddm_dense_mse_step_workspace_bytes(self.handle, n, T)), 256), dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_dense_mse_step(self.handle, _ptr(col), _ptr(x), _ptr(eps), _ptr(level_w),
+                                                DTYPE_F64 if x.dtype == torch.float64 else DTYPE_F32, n, T, float(a), float(b),
+                                                float(c0), float(c1), _ptr(w), _wdtype(w), _ptr(loss), _ptr(grad_w), _ptr(ws),
+                                                self.spec.gemm_precision, self.spec.bwd_precision, self._stream(dev)),
+                  "qiddm_dense_mse_step")
+        return loss, grad_w
 
     # ------------------------------------------------------------------ QConv on the unitary-collapse path
     @staticmethod

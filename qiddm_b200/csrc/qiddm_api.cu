@@ -454,6 +454,40 @@ int qiddm_gemm_backward(const qiddm_plan *plan, const void *collapsed, const flo
                          t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
 }
 
+// ---- fused diffusion training step of one amplitude-embedding layer (include/qiddm.h)
+size_t qiddm_dense_mse_step_workspace_bytes(const qiddm_plan *plan, int64_t n_images, int T) {
+    if (!plan || !gemm_eligible(plan) || n_images < 0 || T < 1) return 0;
+    GateParams gp = make_params(plan, nullptr, 1);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    const long long B = (n_images > 0 ? n_images : 1) * (long long)T;
+    return align_up(gemm_dense_mse_ws_bytes(g, B)) + basis_ws_bytes(plan) + 256;
+}
+
+int qiddm_dense_mse_step(const qiddm_plan *plan, const void *collapsed, const void *x, const float *eps, const void *w,
+                         int io_dtype, int64_t n_images, int T, double a, double b, double c0, double c1,
+                         const void *weights, int weights_dtype, void *loss, void *grad_weights, void *workspace,
+                         int precision, int bwd_precision, qiddm_stream_t stream) {
+    if (!plan || !collapsed || !workspace || !weights || !loss || !grad_weights || n_images < 1 || T < 1) return QIDDM_EINVAL;
+    if (!x || !eps || !w) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    if ((precision != 1 && precision != 3) || (bwd_precision != 1 && bwd_precision != 3)) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    const long long B = (long long)n_images * T;
+    if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    if (plan->d.read_count != plan->d.n_features || plan->d.read_stride != 1) return QIDDM_EUNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    GateParams gp = make_params(plan, nullptr, B);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    float *gut = nullptr;
+    int rc = gemm_dense_mse_step(g, gp, collapsed, x, eps, w, io_dtype == QIDDM_DTYPE_F64 ? 1 : 0, n_images, T, (float)a, (float)b,
+                                 (float)c0, (float)c1, loss, &gut, workspace, precision, bwd_precision, s);
+    if (rc != QIDDM_OK) return rc;
+    qiddm_plan t = basis_plan(plan);
+    char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_dense_mse_ws_bytes(g, B));
+    return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
+                         t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
+}
+
 // ---- QConv on the unitary-collapse path: the same GEMMs with the patch-unfold fused into the operand preparation,
 // probabilities written straight to NCHW, grad_out read from NCHW and the col2im of dX in one gather kernel.
 static long long unfold_patches(const qiddm_unfold_desc *u) {

@@ -26,6 +26,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "qiddm_internal.h"
 
 namespace qiddm {
@@ -254,11 +255,31 @@ struct GemmParams {
                                 // bit 2: activation-side (A) operand loads evict_first; bit 3: LSU epilogue stores st.global.cs
     int out_f64;             // EPI_PROBS, QConv: `out` is a float64 tensor
     int out_P;               // EPI_PROBS, QConv: > 0 -> row = (image b, patch r), out[(b * n_out + m) * out_P + r] (NCHW)
+    // EPI_PROBS fused with the diffusion step's MSE loss and dL/dY (tma_epi == 3, epilogue_tile_mse): row = (image b, level t),
+    // target recomputed from the image and its noise draw (src/noise.py:105-126), no out / Y / grad_out arrays
+    struct {
+        const void *x;            // (n_images, P) images, float32 / float64 (f64)
+        const float *eps;         // (n_images, P) noise draw
+        const void *w;            // (T + 1) level weights, dtype of x
+        int T, f64, P, want_lo;   // want_lo: the gradient GEMMs run the 3-term split and need the lo part of G
+        float a, b, c0, c1;       // d = a out + b - (c0 level_t + c1 level_{t+1})
+        double kk;                // grad_out = kk d  (= 2 a / numel)
+        __half *gh, *gl;          // G = dL/dY' splits, (M, ldg) row-major
+        long long ldg;
+        double *loss_partial;     // [gridDim.x * 4]: per epilogue warp sum of d^2
+    } mse;
     // pair kernel: epilogue through shared memory + TMA stores (fp32 boxes of 32 rows)
     int tma_epi;
     alignas(64) CUtensorMap y_map;      // EPI_PROBS: Y (M, N), box 16 x 32, SWIZZLE_64B
     alignas(64) CUtensorMap o_map;      // EPI_PROBS: out (M, n_out), box 8 x 32; EPI_DX: dX (M, N), box 16 x 32, SWIZZLE_64B
 };
+
+// fp32 -> fp16 hi + fp16 lo (22 mantissa bits; the tensor cores take fp16 subnormals, so lo needs no scaling --
+// measured: 7e-6 rel-to-max on the n = 10, K = 784 layer with inputs down to 2^-17)
+__device__ __forceinline__ void split_act(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
 
 // power-of-two scale that maps the bound on max |G| into [2^13, 2^14)
 __device__ __forceinline__ float g_scale_from_max(unsigned int bits) {
@@ -773,9 +794,153 @@ __device__ __forceinline__ void epilogue_tile_lsu(const GemmParams &p, uint32_t 
     }
 }
 
+// EPI_PROBS + MSE + dL/dY in the epilogue (the diffusion training step of a single amplitude-embedding layer:
+// src/models.py:65-67 / :95-99 around nn/qdense.py:95-111).  Per output (row = (b, t), m):
+//   out = clamp(|Y'|^2 rs),  target = c0 level_t + c1 level_{t+1},  level_k = clamp(x (1 - w_k) + eps w_k, 0, 1),
+//   d = a out + b - target,  loss += d^2,  g = kk d (0 where the clamp is active),  G[2m + ri] = 2 g rs gsc Y'[2m + ri]
+// and G leaves as the scaled fp16 (hi, lo) operand of the dW GEMM: what the unfused path does with the `out` store, the
+// MSE pass (read out + clean, write grad) and grad_y_kernel (read Y + grad, write G) -- 13 GB of HBM traffic per step at the
+// bench size -- happens on the accumulator tile in registers.  The scale gsc comes from an analytic bound (the clamp bounds
+// |d|), so no pass over the gradient is needed.
+template <bool F64>
+__device__ __forceinline__ void epilogue_tile_mse(const GemmParams &p, uint32_t tmem_acc, int row0, int n0, int q, int lane,
+                                                  uint32_t stage0, int bn_t, double &loss_acc) {
+    typedef typename std::conditional<F64, double, float>::type T;
+    const int rbase = row0 + q * 32;
+    const int row = rbase + lane;
+    const bool row_ok = row < p.M;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const float rs = row_ok ? p.row_scale[row] * p.post_scale : 0.f;
+    const float k1 = 2.f * rs * g_scale_final(p.gmax_bits);
+    const long long b = row_ok ? row / p.mse.T : 0;
+    const int t = row_ok ? row - (int)b * p.mse.T : 0;
+    const T *wl = reinterpret_cast<const T *>(p.mse.w);
+    const T w0 = wl[t], w1 = wl[t + 1];
+    const T *xr = reinterpret_cast<const T *>(p.mse.x) + b * p.mse.P;
+    const float *er = p.mse.eps + b * p.mse.P;
+    const uint32_t hbase = stage0, lbase = stage0 + 2048u;
+    const bool vec = (p.mse.P & 3) == 0 && ((((uintptr_t)p.mse.x) | ((uintptr_t)p.mse.eps)) & 15) == 0;
+    uint32_t ra[32], rb[32];
+    // image pixels and noise draw of this lane's row for the 16 outputs of a chunk; issued one chunk ahead (L2 latency)
+    auto load_xe = [&](int c0, T (&xv)[16], float (&ev)[16]) {
+        const int col = n0 + c0;
+        if (col >= (int)p.mse.ldg || rbase >= p.M) return;             // warp-uniform
+        const int m0 = col >> 1;
+        if (row_ok && vec && m0 + 16 <= p.n_out) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 e4 = __ldg(reinterpret_cast<const float4 *>(er + m0) + j);
+                ev[4 * j] = e4.x; ev[4 * j + 1] = e4.y; ev[4 * j + 2] = e4.z; ev[4 * j + 3] = e4.w;
+            }
+            if (F64) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double2 x2 = __ldg(reinterpret_cast<const double2 *>(xr + m0) + j);
+                    xv[2 * j] = (T)x2.x; xv[2 * j + 1] = (T)x2.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x4 = __ldg(reinterpret_cast<const float4 *>(xr + m0) + j);
+                    xv[4 * j] = (T)x4.x; xv[4 * j + 1] = (T)x4.y; xv[4 * j + 2] = (T)x4.z; xv[4 * j + 3] = (T)x4.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const bool ok = row_ok && m0 + j < p.n_out;
+                xv[j] = ok ? __ldg(xr + m0 + j) : (T)0;
+                ev[j] = ok ? __ldg(er + m0 + j) : 0.f;
+            }
+        }
+    };
+    auto chunk = [&](const uint32_t (&r)[32], int c0, const T (&xv)[16], const float (&ev)[16]) {
+        const int col = n0 + c0;
+        if (col >= (int)p.mse.ldg || rbase >= p.M) return;             // warp-uniform
+        const int m0 = col >> 1;
+        __half2 hh[16], ll[16];
+        // float32 models: d in float32 (the difference of two float32 numbers of similar size is exact or rounds at 6e-8 of the
+        // larger), the 16 squares of a chunk summed in float32 and added to the float64 accumulator once per chunk -- float64
+        // arithmetic and conversions per OUTPUT made this epilogue the bottleneck of the forward GEMM
+        T part = (T)0;
+        const T ka = (T)p.mse.a, kb = (T)p.mse.b, kkT = (T)p.mse.kk;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float re = __uint_as_float(r[2 * j]), im = __uint_as_float(r[2 * j + 1]);
+            const float pr = (re * re + im * im) * rs;
+            const bool pass = !p.clamp || (pr >= p.clamp_lo && pr <= p.clamp_hi);
+            const float outv = p.clamp ? fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi) : pr;
+            T l0 = xv[j] * ((T)1 - w0) + (T)ev[j] * w0;
+            l0 = l0 < (T)0 ? (T)0 : (l0 > (T)1 ? (T)1 : l0);
+            T tgt = (T)p.mse.c0 * l0;
+            if (p.mse.c1 != 0.f) {
+                T l1 = xv[j] * ((T)1 - w1) + (T)ev[j] * w1;
+                l1 = l1 < (T)0 ? (T)0 : (l1 > (T)1 ? (T)1 : l1);
+                tgt += (T)p.mse.c1 * l1;
+            }
+            const bool live = row_ok && m0 + j < p.n_out && c0 + 2 * j < bn_t;     // columns past the tile's width hold no data
+            const T d = live ? ka * (T)outv + kb - tgt : (T)0;
+            part += d * d;
+            const float coef = pass ? k1 * (float)(kkT * d) : 0.f;
+            __half h0, q0, h1, q1;
+            split_act(coef * re, h0, q0);
+            split_act(coef * im, h1, q1);
+            hh[j] = __halves2half2(h0, h1);
+            ll[j] = __halves2half2(q0, q1);
+        }
+        loss_acc += (double)part;
+        __syncwarp();                                       // the previous chunk's block has been read back by every lane
+        const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t off = (uint32_t)lane * 64u + ((j ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hbase + off), "r"(*reinterpret_cast<uint32_t *>(&hh[4 * j])),
+                         "r"(*reinterpret_cast<uint32_t *>(&hh[4 * j + 1])), "r"(*reinterpret_cast<uint32_t *>(&hh[4 * j + 2])),
+                         "r"(*reinterpret_cast<uint32_t *>(&hh[4 * j + 3])) : "memory");
+            if (p.mse.want_lo)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lbase + off), "r"(*reinterpret_cast<uint32_t *>(&ll[4 * j])),
+                             "r"(*reinterpret_cast<uint32_t *>(&ll[4 * j + 1])), "r"(*reinterpret_cast<uint32_t *>(&ll[4 * j + 2])),
+                             "r"(*reinterpret_cast<uint32_t *>(&ll[4 * j + 3])) : "memory");
+        }
+        __syncwarp();
+        const uint32_t c = (uint32_t)lane & 3u;
+        const int gcol = col + 8 * (int)c;                  // 8 fp16 columns = 16 bytes
+#pragma unroll
+        for (uint32_t it = 0; it < 4; ++it) {
+            const uint32_t r_ = it * 8u + ((uint32_t)lane >> 2);
+            const int grow = rbase + (int)r_;
+            if (grow < p.M && gcol < (int)p.mse.ldg && c0 + 8 * (int)c < bn_t) {
+                const uint32_t off = r_ * 64u + ((c ^ ((r_ >> 1) & 3u)) << 4);
+                const float4 vh = ld_shared_f4(hbase + off);
+                *reinterpret_cast<float4 *>(p.mse.gh + (long long)grow * p.mse.ldg + gcol) = vh;
+                if (p.mse.want_lo) {
+                    const float4 vl = ld_shared_f4(lbase + off);
+                    *reinterpret_cast<float4 *>(p.mse.gl + (long long)grow * p.mse.ldg + gcol) = vl;
+                }
+            }
+        }
+    };
+    T xa[16], xb[16];
+    float ea[16], eb[16];
+    tc_ld32_issue(taddr, ra);
+    load_xe(0, xa, ea);
+    for (int c0 = 0; c0 < bn_t; c0 += 64) {
+        tc_ld_wait32(ra);
+        if (c0 + 32 < bn_t) { tc_ld32_issue(taddr + c0 + 32, rb); load_xe(c0 + 32, xb, eb); }
+        chunk(ra, c0, xa, ea);
+        if (c0 + 32 < bn_t) {
+            tc_ld_wait32(rb);
+            if (c0 + 64 < bn_t) { tc_ld32_issue(taddr + c0 + 64, ra); load_xe(c0 + 64, xa, ea); }
+            chunk(rb, c0 + 32, xb, eb);
+        }
+    }
+}
+
 // DUAL (MN-major operands only): a work item is TWO neighbouring N tiles fed from one staged A tile -- both TMEM accumulator
 // stages live at once, plain epilogue after the item (long split-K items: the dW GEMM of big batches).
-template <int NSEG, bool AMN, int BKT, bool DUAL = false>
+// MSE (K-major operands only): 1 / 2 = the fused readout + MSE + dL/dY epilogue for float32 / float64 images (own
+// instantiations: its register needs must not weigh on the plain forward kernel).
+template <int NSEG, bool AMN, int BKT, bool DUAL = false, int MSE = 0>
 __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     static_assert(BKT == 64 || BKT == 32, "K-major tiles: 64 or 32 fp16 per row; MN-major: 64 or 32 K rows per box");
@@ -982,6 +1147,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
         const uint32_t stage0 = epi_base + (uint32_t)q * 2u * EPI_STAGE_BYTES;
         int acc = 0, buf = 0;
         uint32_t acc_phase = 0;
+        double loss_acc = 0.0;                        // tma_epi == 3: this lane's sum of d^2 over its rows of every tile
         for (long long w = pair; w < total; w += n_pairs) {
             const long long tile = w % tiles_mn;
             const int tm = (int)(tile / tiles_n), tn = (int)((tile % tiles_n + tm) % tiles_n);
@@ -994,6 +1160,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                 for (int t = 0; t < 2; ++t)        // not unrolled: one copy of the epilogue body
                     if (2 * tn + t < tiles_n_all)
                         epilogue_tile(p, tmem_base + (uint32_t)t * ACC_COLS, row0, (2 * tn + t) * p.bn, q, lane, 0, p.bn);
+            } else if constexpr (MSE != 0) {
+                epilogue_tile_mse<MSE == 2>(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, bn_t, loss_acc);
             } else if (p.tma_epi == 2)
                 epilogue_tile_lsu(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, bn_t);
             else if (p.tma_epi)
@@ -1007,6 +1175,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
             else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (p.tma_epi == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if constexpr (MSE != 0) {  // one slot per epilogue warp of the persistent grid: summed in a fixed order afterwards
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+            if (lane == 0) p.mse.loss_partial[(long long)blockIdx.x * 4 + q] = loss_acc;
+        }
     }
 
     tc_fence_before();
@@ -1020,12 +1193,6 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
 // ------------------------------------------------------------------------------------------
 // elementwise helpers
 // ------------------------------------------------------------------------------------------
-// fp32 -> fp16 hi + fp16 lo (22 mantissa bits; the tensor cores take fp16 subnormals, so lo needs no scaling --
-// measured: 7e-6 rel-to-max on the n = 10, K = 784 layer with inputs down to 2^-17)
-__device__ __forceinline__ void split_act(float v, __half &hi, __half &lo) {
-    hi = __float2half_rn(v);
-    lo = __float2half_rn(v - __half2float(hi));
-}
 
 // x (B,F) fp32 -> Xh/Xl (B,Kp) fp16 (hi, lo*2^11) and inv_n2[b] = 1 / (sum f^2 + n_pad * pad^2).  One warp per row.
 // Column F (when the state has constant pad rows) is a column of ones: it meets zero weights in the forward
@@ -1540,6 +1707,106 @@ __global__ void __launch_bounds__(256) grad_y_kernel(const float *Y, const float
     }
 }
 
+// Fused diffusion step, operand side: the noisy rows (level t + 1 of image b's ladder, src/noise.py:105-126 as sliced by
+// src/models.py:46-63) are never written as fp32 -- a warp forms row (b, t) from the image and its noise draw and stores
+// the fp16 (hi, lo) splits and 1 / |f|^2 the forward GEMM consumes (what qiddm_noise_ladder + prep_x_dense_kernel do in two
+// passes through HBM).  in2max_bits: max over the rows of 1 / |f|^2 (for the analytic bound on |G|).
+// One warp per IMAGE: its pixels and noise draw stay in registers (ITS x 8 values per lane) while the T rows are formed
+// and stored -- the images are read once (an image's rows re-reading them through L2 made the pass L2-bound).
+template <typename T, int ITS>
+__global__ void __launch_bounds__(256) ladder_prep_kernel(const T *x, const float *eps, const T *w, long long n_img, int steps,
+                                                          int F, int Kp, int n_pad, float add_offset, float pad, __half *Xh,
+                                                          __half *Xl, float *inv_n2, int want_lo, unsigned int *in2max_bits) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const bool vec = (F & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)eps)) & 15) == 0;
+    float best = 0.f;
+    for (long long b = warp0; b < n_img; b += nwarps) {
+        const T *xs = x + b * F;
+        const float *es = eps + b * F;
+        T xv[ITS][8];
+        float ev[ITS][8];
+#pragma unroll
+        for (int it = 0; it < ITS; ++it) {
+            const int c = 8 * lane + 256 * it;
+            if (vec && c + 8 <= F) {
+                const float4 e0 = __ldg(reinterpret_cast<const float4 *>(es + c)), e1 = __ldg(reinterpret_cast<const float4 *>(es + c) + 1);
+                ev[it][0] = e0.x; ev[it][1] = e0.y; ev[it][2] = e0.z; ev[it][3] = e0.w;
+                ev[it][4] = e1.x; ev[it][5] = e1.y; ev[it][6] = e1.z; ev[it][7] = e1.w;
+                if (sizeof(T) == 8) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 t2 = __ldg(reinterpret_cast<const double2 *>(xs + c) + j);
+                        xv[it][2 * j] = (T)t2.x; xv[it][2 * j + 1] = (T)t2.y;
+                    }
+                } else {
+                    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(xs + c)), a1 = __ldg(reinterpret_cast<const float4 *>(xs + c) + 1);
+                    xv[it][0] = (T)a0.x; xv[it][1] = (T)a0.y; xv[it][2] = (T)a0.z; xv[it][3] = (T)a0.w;
+                    xv[it][4] = (T)a1.x; xv[it][5] = (T)a1.y; xv[it][6] = (T)a1.z; xv[it][7] = (T)a1.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xv[it][j] = c + j < F ? __ldg(xs + c + j) : (T)0;
+                    ev[it][j] = c + j < F ? __ldg(es + c + j) : 0.f;
+                }
+            }
+        }
+        for (int t = 0; t < steps; ++t) {
+            const T wt = w[t + 1];
+            const long long row = b * steps + t;
+            float ss = 0.f;
+#pragma unroll
+            for (int it = 0; it < ITS; ++it) {
+                const int c = 8 * lane + 256 * it;
+                if (c < Kp) {
+                    __half hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float f = 0.f;
+                        if (c + j < F) {
+                            T v = xv[it][j] * ((T)1 - wt) + (T)ev[it][j] * wt;
+                            v = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+                            f = (float)v + add_offset;
+                        }
+                        ss += f * f;
+                        split_act((c + j == F && n_pad > 0) ? 1.f : f, hi[j], lo[j]);
+                    }
+                    *reinterpret_cast<uint4 *>(Xh + row * Kp + c) = *reinterpret_cast<const uint4 *>(hi);       // Kp is a multiple of 8
+                    if (want_lo) *reinterpret_cast<uint4 *>(Xl + row * Kp + c) = *reinterpret_cast<const uint4 *>(lo);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            ss += (float)n_pad * pad * pad;
+            const float in2 = ss > 0.f ? 1.0f / ss : 0.f;
+            if (lane == 0) inv_n2[row] = in2;
+            best = fmaxf(best, in2);
+        }
+    }
+    if (lane == 0 && best > 0.f && best < 3.0e38f) atomicMax(in2max_bits, __float_as_uint(best));
+}
+
+// bits[0] = bound on max |G| = c sqrt(max_rows 1/|f|^2)  (|Y'| <= w_scale |f|; c holds the analytic bound on |grad_out|), bits[1] = 0
+__global__ void set_g_bound_kernel(unsigned int *bits, const unsigned int *in2max_bits, float c) {
+    const float v = c * sqrtf(__uint_as_float(*in2max_bits));
+    bits[0] = (v > 0.f && v < 3.0e38f) ? __float_as_uint(v) : 0u;
+    bits[1] = 0u;
+}
+
+// loss = sum(partial) / n in a fixed order (one warp); `loss` is float32 or float64
+__global__ void loss_finalize_kernel(const double *partial, int n_partial, double n, void *loss, int f64) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+        if (f64) *reinterpret_cast<double *>(loss) = s / n;
+        else *reinterpret_cast<float *>(loss) = (float)(s / n);
+    }
+}
+
 // Assemble the READ_STATE cotangent of UT for the adjoint gate kernel:
 //   gUT[c][k_m].{re,im} = w_scale / gsc * ( c < F ? dWT[n][c] : pad * dWT[n][F] )   (n = 2m+ri), 0 elsewhere;
 // dWT[n][F] is the ones-column entry = sum_b G[b,n].
@@ -1701,7 +1968,7 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
     // MN-major dual-N items (p.dual_n, set by the caller): 32-row k-blocks keep four 48 KB stages in flight where 64-row
     // ones would leave two of 96 KB; K-major: optional 32-wide k-blocks (finer stages; measured slower)
     static int dw_bk = -1;
-    if (dw_bk < 0) { const char *e = getenv("QIDDM_GEMM_DW_BK"); dw_bk = e ? atoi(e) : 32; }
+    if (dw_bk < 0) { const char *e = getenv("QIDDM_GEMM_DW_BK"); dw_bk = e ? atoi(e) : 64; }
     if (!(b_mn && pair)) p.dual_n = 0;
     if (p.dual_n) p.bn_last = p.bn;
     const int bkt = a_mn ? ((pair && p.dual_n && dw_bk == 32) ? 32 : BK) : ((pair && bk32) ? 32 : BK);
@@ -1747,6 +2014,10 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
                 (((uintptr_t)p.y_out | (uintptr_t)p.out) & 15) == 0)
                 p.tma_epi = 2;
         }
+        if (p.mse.gh != nullptr) {
+            if (p.epi != EPI_PROBS || a_mn || bkt != 64 || k_splits != 1) return QIDDM_EINVAL;
+            p.tma_epi = 3;      // readout + MSE + dL/dY in the epilogue (epilogue_tile_mse)
+        }
         const int epi_bytes = p.tma_epi ? 4 * 2 * EPI_STAGE_BYTES + 512 : 0;
         const int b_tile_bytes = b_mn ? ((p.bn / 2 + 63) / 64) * (64 * bkt * 2) : (p.bn / 2) * bkt * 2;
         const int stage_bytes = (n_seg > 1 ? 2 : 1) * (BM * bkt * 2 + b_tile_bytes * (p.dual_n ? 2 : 1));
@@ -1759,14 +2030,17 @@ int run_gemm(const ActOperand &A, long long a_rows, long long a_cols, long long 
         p.stages = stages;
         const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
         void (*kern)(const GemmParams);
-        if (a_mn && p.dual_n && bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 32, true> : gemm_pair_kernel<1, true, 32, true>;
+        if (p.tma_epi == 3)
+            kern = p.mse.f64 ? (n_seg > 1 ? gemm_pair_kernel<3, false, 64, false, 2> : gemm_pair_kernel<1, false, 64, false, 2>)
+                             : (n_seg > 1 ? gemm_pair_kernel<3, false, 64, false, 1> : gemm_pair_kernel<1, false, 64, false, 1>);
+        else if (a_mn && p.dual_n && bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 32, true> : gemm_pair_kernel<1, true, 32, true>;
         else if (a_mn && p.dual_n) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64, true> : gemm_pair_kernel<1, true, 64, true>;
         else if (a_mn) kern = n_seg > 1 ? gemm_pair_kernel<3, true, 64> : gemm_pair_kernel<1, true, 64>;
         else if (bkt == 32) kern = n_seg > 1 ? gemm_pair_kernel<3, false, 32> : gemm_pair_kernel<1, false, 32>;
         else kern = n_seg > 1 ? gemm_pair_kernel<3, false, 64> : gemm_pair_kernel<1, false, 64>;
         // the opt-in shared-memory limit of a function is per device: remembered per (device, instantiation)
-        static std::atomic<bool> attr_set2[64][10];
-        const int ki = p.dual_n ? (bkt == 32 ? 6 : 8) + (n_seg > 1 ? 1 : 0) : (n_seg > 1 ? 3 : 0) + (a_mn ? 2 : (bkt == 32 ? 1 : 0));
+        static std::atomic<bool> attr_set2[64][14];
+        const int ki = p.tma_epi == 3 ? 10 + (p.mse.f64 ? 2 : 0) + (n_seg > 1 ? 1 : 0) : p.dual_n ? (bkt == 32 ? 6 : 8) + (n_seg > 1 ? 1 : 0) : (n_seg > 1 ? 3 : 0) + (a_mn ? 2 : (bkt == 32 ? 1 : 0));
         if (!attr_set2[dev & 63][ki].load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;
@@ -1819,6 +2093,9 @@ inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 // ------------------------------------------------------------------------------------------
 // layout of the collapsed operator, the saved forward state and the per-call workspace
 // ------------------------------------------------------------------------------------------
+int gemm_dw_and_assemble(const GemmShape &g, const GateParams &gp, __half *const X[2], __half *const XT[2], __half *const Gs[2],
+                         const unsigned int *gmax, float *dWT, float *gUT, long long B, int n_seg, cudaStream_t s);
+
 GemmShape gemm_shape(const GateParams &gp, int n_qubits) {
     GemmShape g;
     g.A = 1 << n_qubits;
@@ -2074,13 +2351,25 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
             count_launch();
         }
     }
-    // (3) dW^T[n][c] = sum_b G[b,n] f[b,c]: G consumed row-major as an MN-major operand, split-K over the batch
+    return gemm_dw_and_assemble(g, gp, w.X, w.XT, Gs, gmax, dWT, gUT, B, n_seg, s);
+}
+
+// dW^T[n][c] = sum_b G[b,n] f[b,c] (G consumed row-major as an MN-major operand, split-K over the batch), then the READ_STATE
+// cotangent gUT for the adjoint gate kernel.  Shared by gemm_backward and the fused diffusion step.
+int gemm_dw_and_assemble(const GemmShape &g, const GateParams &gp, __half *const X[2], __half *const XT[2], __half *const Gs[2],
+                         const unsigned int *gmax, float *dWT, float *gUT, long long B, int n_seg, cudaStream_t s) {
+    const long long Bp = (B + 7) & ~7LL;
+    const int ldw = (g.Fx + 3) & ~3;
+    cudaError_t e;
+    int rc;
+    GemmParams p;
+    ActOperand Go{Gs[0], Gs[1]};
     if ((e = cudaMemsetAsync(dWT, 0, (size_t)g.N * ldw * 4, s)) != cudaSuccess) return (int)e;
     {
         memset(&p, 0, sizeof(p));
         p.epi = EPI_STORE; p.out = dWT; p.ldo = ldw; p.out_scale = 1.f;
         const bool xt = use_xt();
-        WgtOperand XTo{xt ? w.XT[0] : w.X[0], xt ? w.XT[1] : w.X[1]};
+        WgtOperand XTo{xt ? XT[0] : X[0], xt ? XT[1] : X[1]};
         const int bn = xt ? pick_bn(g.Fx) : pick_bn_mn(g.Fx);
         const bool pair = use_pair_kernel();
         const int bm = pair ? 2 * BM : BM;
@@ -2120,6 +2409,104 @@ int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapse
     count_launch();
     e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Fused diffusion training step of ONE amplitude-embedding layer (Diffusion(QDenseUndirected_old[_noise]) of
+// src/models.py:44-104 around nn/qdense.py:95-111): ladder -> splits, forward GEMM with the MSE loss and dL/dY in its
+// epilogue, dW GEMM, cotangent of U^T.  Rows = (image b, level t), t < T; no grad_in (the layer is the first one).
+// ------------------------------------------------------------------------------------------
+size_t gemm_dense_mse_ws_bytes(const GemmShape &g, long long B) {
+    size_t b = 2 * al((size_t)B * g.Kp * 2) + al((size_t)B * 4) + al(256);      // X splits, 1/|f|^2, gmax words
+    b += 2 * al((size_t)B * g.Np * 2);                                          // G splits
+    b += al((size_t)g.N * ((g.Fx + 3) & ~3) * 4);                               // dWT
+    b += al((size_t)g.A * g.A * 8);                                             // gUT
+    b += al((size_t)8 * 4 * 2 * 148);                                           // loss partials (one per epilogue warp)
+    return b;
+}
+
+int gemm_dense_mse_step(const GemmShape &g, const GateParams &gp, const void *collapsed, const void *x, const float *eps,
+                        const void *w, int io64, long long n_img, int T, float a, float bshift, float c0, float c1,
+                        void *loss_out, float **gut_out, void *ws, int n_seg_fwd, int n_seg_bwd, cudaStream_t s) {
+    if (gp.unfold || g.n_out != g.F || !use_pair_kernel() || use_xt() || T < 1) return QIDDM_EUNSUPPORTED;
+    CollapsedView v = collapsed_view(g, const_cast<void *>(collapsed));
+    const long long B = n_img * T;
+    char *p8 = reinterpret_cast<char *>(ws);
+    __half *X[2], *XT[2] = {nullptr, nullptr}, *Gs[2];
+    for (int i = 0; i < 2; ++i) { X[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Kp * 2); }
+    float *inv_n2 = reinterpret_cast<float *>(p8); p8 += al((size_t)B * 4);
+    unsigned int *gmax = reinterpret_cast<unsigned int *>(p8); p8 += al(256);
+    for (int i = 0; i < 2; ++i) { Gs[i] = reinterpret_cast<__half *>(p8); p8 += al((size_t)B * g.Np * 2); }
+    const int ldw = (g.Fx + 3) & ~3;
+    float *dWT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.N * ldw * 4);
+    float *gUT = reinterpret_cast<float *>(p8); p8 += al((size_t)g.A * g.A * 8);
+    double *partial = reinterpret_cast<double *>(p8);
+    *gut_out = gUT;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > 2 * 148) return QIDDM_EUNSUPPORTED;
+
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(gmax, 0, 256, s)) != cudaSuccess) return (int)e;
+    // (1) noisy rows straight to the GEMM operand splits
+    const bool want_lo = n_seg_fwd > 1 || n_seg_bwd > 1;
+    const long long blocks = (n_img + 7) / 8;
+    const unsigned grid = (unsigned)(blocks < 148 * 8 ? blocks : 148 * 8);
+    const int its = (g.Kp + 255) / 256;              // 8 values per lane and iteration
+    if (its > 5) return QIDDM_EUNSUPPORTED;          // n <= 10 (Kp <= 1032); larger layers take the unfused sequence
+    timing_begin(TK_PREP_X, 0.0, s);
+#define QIDDM_LADDER_PREP(TT, ITS_)                                                                                              \
+    ladder_prep_kernel<TT, ITS_><<<grid, 256, 0, s>>>(reinterpret_cast<const TT *>(x), eps, reinterpret_cast<const TT *>(w), n_img, \
+                                                      T, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, X[0], X[1], inv_n2,   \
+                                                      want_lo, gmax + 2)
+    if (io64) {
+        if (its <= 1) QIDDM_LADDER_PREP(double, 1); else if (its == 2) QIDDM_LADDER_PREP(double, 2);
+        else if (its <= 4) QIDDM_LADDER_PREP(double, 4); else QIDDM_LADDER_PREP(double, 5);
+    } else {
+        if (its <= 1) QIDDM_LADDER_PREP(float, 1); else if (its == 2) QIDDM_LADDER_PREP(float, 2);
+        else if (its <= 4) QIDDM_LADDER_PREP(float, 4); else QIDDM_LADDER_PREP(float, 5);
+    }
+#undef QIDDM_LADDER_PREP
+    timing_end(s);
+    count_launch();
+    // (2) analytic bound on |G|: |d| <= |a| max|out| + |b| + |c0| + |c1| (levels are clamped to [0, 1]), |grad_out| = |kk d|,
+    //     |G| = 2 |grad_out| post inv_n2 |Y'| <= 2 |grad_out| post w_scale sqrt(inv_n2)
+    const float eff_scale = gp.post_scale / (g.w_scale * g.w_scale);
+    const double out_max = gp.clamp ? fmax(fabs((double)gp.clamp_lo), fabs((double)gp.clamp_hi)) : fabs((double)gp.post_scale);
+    const double d_max = fabs((double)a) * out_max + fabs((double)bshift) + fabs((double)c0) + fabs((double)c1);
+    const double kk = 2.0 * (double)a / ((double)B * (double)g.n_out);
+    const double cbound = 2.0 * fabs(kk) * d_max * (double)eff_scale * (double)g.w_scale;
+    set_g_bound_kernel<<<1, 1, 0, s>>>(gmax, gmax + 2, (float)cbound);
+    count_launch();
+    // (3) forward GEMM, epilogue = readout + MSE + dL/dY -> G splits, loss partials
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.epi = EPI_PROBS;
+    p.out = nullptr; p.ldo = g.n_out; p.out_scale = 1.f;
+    p.y_out = nullptr;
+    p.bias = nullptr; p.row_scale = inv_n2;
+    p.post_scale = eff_scale;
+    p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi;
+    p.n_out = g.n_out;
+    p.gmax_bits = gmax;
+    p.mse.x = x; p.mse.eps = eps; p.mse.w = w; p.mse.T = T; p.mse.f64 = io64; p.mse.P = g.F;
+    p.mse.a = a; p.mse.b = bshift; p.mse.c0 = c0; p.mse.c1 = c1; p.mse.kk = kk;
+    p.mse.gh = Gs[0]; p.mse.gl = Gs[1]; p.mse.ldg = g.Np; p.mse.want_lo = n_seg_bwd > 1 ? 1 : 0;
+    p.mse.loss_partial = partial;
+    if ((e = cudaMemsetAsync(partial, 0, (size_t)8 * 4 * sms, s)) != cudaSuccess) return (int)e;
+    ActOperand A{X[0], X[1]};
+    WgtOperand Bm{v.Wn[0], v.Wn[1]};
+    timing_set_gemm_kind(TK_GEMM_FWD);
+    // the G splits carry what the gradient GEMMs need: with single-pass gradients (n_seg_bwd == 1) only the hi part is written
+    int rc = run_gemm(A, B, g.Kp, g.Kp, false, Bm, g.N, g.Kp, (int)B, g.N, g.Kp, n_seg_fwd, 1, p, s);
+    if (rc != QIDDM_OK) return rc;
+    loss_finalize_kernel<<<1, 32, 0, s>>>(partial, 4 * sms, (double)B * (double)g.n_out, loss_out, io64);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    // (4) dW GEMM + cotangent of U^T
+    return gemm_dw_and_assemble(g, gp, X, XT, Gs, gmax, dWT, gUT, B, n_seg_bwd, s);
 }
 
 }  // namespace qiddm

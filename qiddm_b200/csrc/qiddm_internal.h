@@ -79,6 +79,11 @@ int gemm_forward(const GemmShape &g, const GateParams &gp, const void *collapsed
 int gemm_backward(const GemmShape &g, const GateParams &gp, const void *collapsed, const float *x,
                   const float *grad_out, const void *saved, float *grad_in, float **gut_out, void *ws, long long B,
                   int n_seg, cudaStream_t s);
+// fused diffusion step of one amplitude-embedding layer (ladder -> splits, forward GEMM with MSE + dL/dY epilogue, dW GEMM)
+size_t gemm_dense_mse_ws_bytes(const GemmShape &g, long long B);
+int gemm_dense_mse_step(const GemmShape &g, const GateParams &gp, const void *collapsed, const void *x, const float *eps,
+                        const void *w, int io64, long long n_img, int T, float a, float bshift, float c0, float c1,
+                        void *loss_out, float **gut_out, void *ws, int n_seg_fwd, int n_seg_bwd, cudaStream_t s);
 
 // qiddm_dm.cu — density-matrix pieces for the mid-circuit noise channels (tau = rho^T, (B, 2^n, 2^n) complex fp32)
 size_t dm_state_bytes(int n_qubits, long long B);

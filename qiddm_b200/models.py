@@ -1,6 +1,7 @@
 """Diffusion wrapper (reference `src/models.py:8-150`): training step (noise ladder -> net -> MSE ->
 `.backward()` INSIDE forward, as the reference does) and the fixed-point sampler.  Same constructor,
 `forward(x, T=..., verbose=...)`, `sample(...)` and `save_name()`; tensors stay on the device."""
+import os
 import typing
 
 import torch
@@ -42,7 +43,21 @@ class Diffusion(torch.nn.Module):
         return (not verbose and recon.is_cuda and type(self.loss) is torch.nn.MSELoss and self.loss.reduction in ("mean", "none")
                 and recon.dtype in (torch.float32, torch.float64) and recon.requires_grad)
 
+    def _fused_step(self, x: torch.Tensor, kwargs):
+        """Single-layer nets that offer `fused_mse_step` (the amplitude-embedding QDense layers on the unitary-collapse path)
+        run ladder -> layer -> MSE -> backward as ONE library call; None = not applicable, take the unfused sequence.
+        QIDDM_FUSED_STEP=0 switches it off."""
+        fn = getattr(self.net, "fused_mse_step", None)
+        if (fn is None or kwargs.get("verbose", False) or os.environ.get("QIDDM_FUSED_STEP", "1") == "0"
+                or self.add_noise is not _noise.add_normal_noise_multiple or type(self.loss) is not torch.nn.MSELoss
+                or self.loss.reduction not in ("mean", "none") or (self.width * self.height) != x.shape[-1]):
+            return None
+        return fn(x, kwargs["T"], self.prediction_goal, decay_mod=3.0)
+
     def run_training_step_data(self, x: torch.Tensor, **kwargs):
+        loss = self._fused_step(x, kwargs)
+        if loss is not None:
+            return (loss.abs(),)
         noisy, clean = self._ladder(x, kwargs["T"])
         recon = self.net.forward(x=noisy)
         if self._fused_mse(recon, kwargs.get("verbose", False)):
@@ -57,6 +72,9 @@ class Diffusion(torch.nn.Module):
         return (batch_loss_mean.abs(),)
 
     def run_training_step_noise(self, x: torch.Tensor, **kwargs):
+        loss = self._fused_step(x, kwargs)
+        if loss is not None:
+            return (loss,)
         noisy, clean = self._ladder(x, kwargs["T"])
         out = self.net.forward(x=noisy)
         if self._fused_mse(out, kwargs.get("verbose", False)):

@@ -149,10 +149,39 @@ class _AmplitudeDense(nn.Module):
         self.qnode = self._circuit
 
     def _spec(self):
+        # `path` / `gemm_precision` / `gemm_bwd_precision` may be set on the instance (tests, bench.py); default: dispatcher, x3
         return L.StageSpec(n_qubits=self.wires, n_blocks=1, layers_per_block=self.qdepth,
                            init=L.INIT_AMPLITUDE, n_features=self.pixels, pad_value=0.1,
                            imprimitive=L.IMP_CNOT, remap=self._remap, readout=L.READ_PROBS,
-                           read_count=self.pixels, post_scale=float(self.pixels), clamp=True)
+                           read_count=self.pixels, post_scale=float(self.pixels), clamp=True,
+                           path=getattr(self, "path", L.PATH_AUTO), gemm_precision=getattr(self, "gemm_precision", 3),
+                           gemm_bwd_precision=getattr(self, "gemm_bwd_precision", 0))
+
+    def fused_mse_step(self, x, T, goal, decay_mod=3.0):
+        """The whole diffusion training step of this layer in one library call (`Plan.dense_mse_step`): noise ladder of
+        src/noise.py:105-126, this layer's forward (nn/qdense.py:56-66 / :95-111), MSELoss + `.mean().backward()` of
+        src/models.py:65-67 (goal "data") / :95-99 (goal "noise").  `weights.grad` is accumulated as autograd would; returns
+        the loss (0-d tensor), or None when the step does not qualify (the caller then runs the unfused sequence): needs
+        the unitary-collapse path, CUDA float32 / float64 images (n, pixels), no noise channel, a trainable `weights`."""
+        noise = getattr(self, "add_noise", 0)
+        if (not x.is_cuda or x.dim() != 2 or x.shape[1] != self.pixels or x.dtype not in (torch.float32, torch.float64)
+                or self.wires > 10            # the ladder -> splits kernel keeps an image in registers: up to 1280 features
+                or channel_matrix(noise, self._noise_params.get(noise, 0.0)) is not None
+                or not (self.weights.requires_grad and torch.is_grad_enabled()) or self.weights.device != x.device):
+            return None
+        plan = L.Plan.get(self._spec())
+        if not plan.use_gemm(x.shape[0] * T):
+            return None
+        from ..noise import _level_weights
+        eps = torch.normal(mean=0.5, std=0.2, size=tuple(x.shape), device=x.device)       # the draw of noise.ladder_pair
+        coeffs = (1.0, 0.0, 1.0, 0.0) if goal == "data" else (0.1, -0.05, -1.0, 1.0)
+        loss, gw = plan.dense_mse_step(x, eps, _level_weights(T + 1, decay_mod, x.device, x.dtype), T, self.weights, *coeffs)
+        gw = gw.view_as(self.weights)
+        if self.weights.grad is None:
+            self.weights.grad = gw
+        else:
+            self.weights.grad.add_(gw)
+        return loss
 
     def _circuit(self, inp):
         """Full probs of the circuit, (B, 2**wires) un-scaled (what the reference QNode returns)."""

@@ -74,7 +74,7 @@ def test_provisional_g_scale_is_redone_when_an_unsampled_row_dominates(outlier_r
     g = torch.Generator().manual_seed(5)
     W = (torch.randn(1, 3, n, 3, generator=g, dtype=torch.float64) * 0.4).cuda()
     x = torch.rand(B, F, generator=g, dtype=torch.float32).cuda()
-    go = torch.rand(B, K, generator=g, dtype=torch.float32).cuda() * 1e-6
+    go = (torch.rand(B, K, generator=g, dtype=torch.float32).cuda() - 0.5) * 2e-6       # mixed signs (see the same-sign note above)
     if outlier_row is not None:
         go[outlier_row] = torch.rand(K, generator=g, dtype=torch.float32).cuda() * 1e3
     o1, w1, x1 = _grads(_spec(d, L.PATH_GEMM), x, W, go)
