@@ -67,8 +67,12 @@ def workload_config(batch, n_gpus):
                              "(cpu_baseline, --impl reference): forward + weight gradient (the layer is the first one of the "
                              "Diffusion step, its input needs no gradient -- src/models.py:64-67)",
             "parallelism": f"dp{n_gpus} (instances sharded, weight-grad all-reduce only)",
-            "step": "device-resident step = forward + backward for BOTH the input and the weight gradients; the e2e "
-                    "Diffusion step (first layer: the noisy images need no gradient) skips the dX GEMM, as the reference does",
+            "step": "device-resident step (`value`, what `roofline` explains) = the layer's generic forward + backward for BOTH "
+                    "the input and the weight gradients given an upstream gradient tensor; the e2e Diffusion training step (first "
+                    "layer: the noisy images need no gradient, so no dX GEMM, as in the reference) runs as the FUSED step "
+                    "qiddm_dense_mse_step: noise ladder -> fp16 operand splits in one pass, forward GEMM whose epilogue forms the "
+                    "MSE loss and dL/dY on the accumulator tile (no out / Y / grad_out arrays, no separate MSE and dL/dY passes), "
+                    "dW GEMM, adjoint sweep on the basis columns (QIDDM_FUSED_STEP=0: the unfused kernel sequence)",
             "l2": "inputs+grads per step (>=2x%.0f MB) exceed the 126 MB L2" % (batch * PIXELS * 4 / 1e6)}
 
 
@@ -323,6 +327,16 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = t.item()
     e2e_val = imgs * TAU * world / (ms_e / ke * 1e-3)
+    # per-kernel times of the e2e step (library timers, two extra steps outside the timed region)
+    L.timing_enable(True)
+    L.timing_collect()
+    e2e_launches0 = qiddm_b200.launch_count()
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_launches = (qiddm_b200.launch_count() - e2e_launches0) // 2
+    e2e_kinds = {k: round(v["ms"] / 2, 4) for k, v in L.timing_collect().items() if v["launches"]}
+    L.timing_enable(False)
     # clocks sampled over both timed regions (device-resident steps and the end-to-end steps)
     clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
     if clocks is not None and "sw_power_cap" in (clocks.get("reasons") or []):
@@ -421,7 +435,10 @@ def run_b200(args):
                     "d2h_bytes_per_step": res_h.numel() * 8, "ms_per_step": ms_e / ke,
                     "api": "qiddm_b200.models.Diffusion(QDenseUndirected_old_noise(60,28)).forward(x, T=10): "
                            f"{imgs} pinned host images/step -> {imgs * TAU} circuit instances, loss+grad to host; "
-                           "H2D double-buffered on a copy stream (qiddm_b200.train.DevicePrefetcher), one copy per step"},
+                           "H2D double-buffered on a copy stream (qiddm_b200.train.DevicePrefetcher), one copy per step; "
+                           + ("fused step (qiddm_dense_mse_step)" if os.environ.get("QIDDM_FUSED_STEP", "1") != "0" and use_gemm
+                              else "unfused kernel sequence"),
+                    "kernel_ms_per_step": e2e_kinds, "gpu_launches_per_step": int(e2e_launches)},
             "path": ("gemm_x%d_bwd_x%d" % (args.precision, bwdp)) if use_gemm else "gate",
             "gpu_launches": int(launches), "roofline": roofline}
 

@@ -811,16 +811,20 @@ __device__ __forceinline__ void epilogue_tile_mse(const GemmParams &p, uint32_t 
     const bool row_ok = row < p.M;
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
     const float rs = row_ok ? p.row_scale[row] * p.post_scale : 0.f;
-    const float k1 = 2.f * rs * g_scale_final(p.gmax_bits);
+    const float kq = 2.f * rs * g_scale_final(p.gmax_bits) * (float)p.mse.kk;      // G = kq d Y' on unclamped outputs
     const long long b = row_ok ? row / p.mse.T : 0;
     const int t = row_ok ? row - (int)b * p.mse.T : 0;
     const T *wl = reinterpret_cast<const T *>(p.mse.w);
-    const T w0 = wl[t], w1 = wl[t + 1];
+    const T w0 = wl[t], w1 = wl[t + 1], omw0 = (T)1 - w0, omw1 = (T)1 - w1;
+    const T ka = (T)p.mse.a, kb = (T)p.mse.b, kc0 = (T)p.mse.c0, kc1 = (T)p.mse.c1;
+    const bool do_clamp = p.clamp != 0, two_levels = p.mse.c1 != 0.f;
     const T *xr = reinterpret_cast<const T *>(p.mse.x) + b * p.mse.P;
     const float *er = p.mse.eps + b * p.mse.P;
     const uint32_t hbase = stage0, lbase = stage0 + 2048u;
     const bool vec = (p.mse.P & 3) == 0 && ((((uintptr_t)p.mse.x) | ((uintptr_t)p.mse.eps)) & 15) == 0;
     uint32_t ra[32], rb[32];
+    T tile_part = (T)0;       // float32 models: one float64 add per TILE (ncu: the per-chunk conversion + DADD stalled the
+                              // epilogue warps on the fp64 pipe for 9 % of their time)
     // image pixels and noise draw of this lane's row for the 16 outputs of a chunk; issued one chunk ahead (L2 latency)
     auto load_xe = [&](int c0, T (&xv)[16], float (&ev)[16]) {
         const int col = n0 + c0;
@@ -861,34 +865,36 @@ __device__ __forceinline__ void epilogue_tile_mse(const GemmParams &p, uint32_t 
         __half2 hh[16], ll[16];
         // float32 models: d in float32 (the difference of two float32 numbers of similar size is exact or rounds at 6e-8 of the
         // larger), the 16 squares of a chunk summed in float32 and added to the float64 accumulator once per chunk -- float64
-        // arithmetic and conversions per OUTPUT made this epilogue the bottleneck of the forward GEMM
+        // arithmetic and conversions per OUTPUT made this epilogue the bottleneck of the forward GEMM.  The instruction count
+        // per output is what bounds the fused forward (4 epilogue warps per CTA, one per scheduler): bounds hoisted to one
+        // count per chunk, constants folded per row, packed fp16 conversions.
         T part = (T)0;
-        const T ka = (T)p.mse.a, kb = (T)p.mse.b, kkT = (T)p.mse.kk;
+        int nlive = p.n_out - m0;                                   // outputs of this chunk that exist and lie inside the tile
+        if ((bn_t - c0) >> 1 < nlive) nlive = (bn_t - c0) >> 1;
+        if (!row_ok) nlive = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float re = __uint_as_float(r[2 * j]), im = __uint_as_float(r[2 * j + 1]);
             const float pr = (re * re + im * im) * rs;
-            const bool pass = !p.clamp || (pr >= p.clamp_lo && pr <= p.clamp_hi);
-            const float outv = p.clamp ? fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi) : pr;
-            T l0 = xv[j] * ((T)1 - w0) + (T)ev[j] * w0;
+            const float outv = do_clamp ? fminf(fmaxf(pr, p.clamp_lo), p.clamp_hi) : pr;
+            T l0 = xv[j] * omw0 + (T)ev[j] * w0;
             l0 = l0 < (T)0 ? (T)0 : (l0 > (T)1 ? (T)1 : l0);
-            T tgt = (T)p.mse.c0 * l0;
-            if (p.mse.c1 != 0.f) {
-                T l1 = xv[j] * ((T)1 - w1) + (T)ev[j] * w1;
+            T tgt = kc0 * l0;
+            if (two_levels) {
+                T l1 = xv[j] * omw1 + (T)ev[j] * w1;
                 l1 = l1 < (T)0 ? (T)0 : (l1 > (T)1 ? (T)1 : l1);
-                tgt += (T)p.mse.c1 * l1;
+                tgt += kc1 * l1;
             }
-            const bool live = row_ok && m0 + j < p.n_out && c0 + 2 * j < bn_t;     // columns past the tile's width hold no data
-            const T d = live ? ka * (T)outv + kb - tgt : (T)0;
+            const T d = j < nlive ? ka * (T)outv + kb - tgt : (T)0;
             part += d * d;
-            const float coef = pass ? k1 * (float)(kkT * d) : 0.f;
-            __half h0, q0, h1, q1;
-            split_act(coef * re, h0, q0);
-            split_act(coef * im, h1, q1);
-            hh[j] = __halves2half2(h0, h1);
-            ll[j] = __halves2half2(q0, q1);
+            // the clamp passes the gradient where it left the value alone (inclusive bounds, like torch.clamp)
+            const float coef = outv == pr ? kq * (float)d : 0.f;
+            const __half2 h2 = __floats2half2_rn(coef * re, coef * im);
+            const float2 hf = __half22float2(h2);
+            hh[j] = h2;
+            ll[j] = __floats2half2_rn(coef * re - hf.x, coef * im - hf.y);
         }
-        loss_acc += (double)part;
+        tile_part += part;
         __syncwarp();                                       // the previous chunk's block has been read back by every lane
         const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
@@ -934,6 +940,24 @@ __device__ __forceinline__ void epilogue_tile_mse(const GemmParams &p, uint32_t 
             chunk(rb, c0 + 32, xb, eb);
         }
     }
+    loss_acc += (double)tile_part;
+}
+
+// The image pixels / noise draw the NEXT tile of this CTA will read in its epilogue, pulled into L2 a tile ahead: they are
+// first touched here (330 MB at the bench size, 5 % of the launch's traffic) and their DRAM latency stalled the epilogue
+// warps for 21 % of their time (ncu, long scoreboard at the first use).
+__device__ __forceinline__ void prefetch_tile_xe(const GemmParams &p, int row0, int n0, int q, int lane, int bn_t) {
+    const int row = row0 + q * 32 + lane;
+    if (row >= p.M) return;
+    const long long b = row / p.mse.T;
+    if (lane > 0 && (row - 1) / p.mse.T == b) return;                  // one lane per image
+    const int esz = p.mse.f64 ? 8 : 4;
+    const char *xs = reinterpret_cast<const char *>(p.mse.x) + (b * p.mse.P + (n0 >> 1)) * esz;
+    const char *es = reinterpret_cast<const char *>(p.mse.eps + b * p.mse.P + (n0 >> 1));
+    int m1 = bn_t >> 1;
+    if ((n0 >> 1) + m1 > p.n_out) m1 = p.n_out - (n0 >> 1);
+    for (int o = 0; o < m1 * esz; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + o));
+    for (int o = 0; o < m1 * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(es + o));
 }
 
 // DUAL (MN-major operands only): a work item is TWO neighbouring N tiles fed from one staged A tile -- both TMEM accumulator
@@ -1161,6 +1185,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) gemm_pair_kernel(const __grid
                     if (2 * tn + t < tiles_n_all)
                         epilogue_tile(p, tmem_base + (uint32_t)t * ACC_COLS, row0, (2 * tn + t) * p.bn, q, lane, 0, p.bn);
             } else if constexpr (MSE != 0) {
+                if (w + n_pairs < total) {
+                    const long long tile2 = (w + n_pairs) % tiles_mn;
+                    const int tm2 = (int)(tile2 / tiles_n), tn2 = (int)((tile2 % tiles_n + tm2) % tiles_n);
+                    prefetch_tile_xe(p, tm2 * 2 * BM + (int)rank * BM, tn2 * p.bn, q, lane, tn2 == tiles_n - 1 ? p.bn_last : p.bn);
+                }
                 epilogue_tile_mse<MSE == 2>(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, bn_t, loss_acc);
             } else if (p.tma_epi == 2)
                 epilogue_tile_lsu(p, tmem_base + (uint32_t)acc * ACC_COLS, tm * 2 * BM + (int)rank * BM, tn * p.bn, q, lane, stage0, bn_t);
