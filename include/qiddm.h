@@ -256,6 +256,18 @@ int qiddm_maxpool2d_forward(const void *x, void *y, int dtype, int64_t planes, i
 int qiddm_maxpool2d_backward(const void *x, const void *grad_y, void *grad_x, int dtype, int64_t planes, int h, int w, int kernel,
                              qiddm_stream_t stream);
 
+/* Linear layers with one narrow side (min(in, out) <= 16) next to the circuits: `linear_down` (pixels -> qubits) and
+ * `linear_up` (qubits -> pixels) of nn/qdense.py:219-386, :565-670 (torch.nn.Linear there, float64).  y = x W^T + b with
+ * x (rows, in), W (out, in) row-major, b (out) or NULL, as streaming kernels in the tensors' dtype; the backward writes
+ * grad_x (rows, in), grad_weight (out, in), grad_bias (out) -- each may be NULL (grad_bias needs grad_weight) -- with
+ * deterministic two-stage sums.  workspace (backward): qiddm_skinny_linear_workspace_bytes. */
+size_t qiddm_skinny_linear_workspace_bytes(int64_t rows, int in_features, int out_features);
+int qiddm_skinny_linear_forward(const void *x, const void *weight, const void *bias, void *y, int dtype, int64_t rows,
+                                int in_features, int out_features, qiddm_stream_t stream);
+int qiddm_skinny_linear_backward(const void *x, const void *weight, const void *grad_y, void *grad_x, void *grad_weight,
+                                 void *grad_bias, int dtype, int64_t rows, int in_features, int out_features, void *workspace,
+                                 qiddm_stream_t stream);
+
 /* Diffusion-step glue.  qiddm_noise_ladder = src/noise.py:105-126 (`add_normal_noise_multiple`) fused with the slicing of
  * src/models.py:50-63: for x, eps (batch, pixels) (eps float32 as the reference draws it) and the level weights w[tau]
  * (tensor dtype), level_t = clamp(x (1 - w_t) + eps w_t, 0, 1); writes noisy[(b, t)] = level_{t+1} and clean[(b, t)] =

@@ -61,6 +61,7 @@ EXPORTS = [
     "qiddm_batchnorm_relu_forward", "qiddm_batchnorm_relu_backward", "qiddm_maxpool2d_forward", "qiddm_maxpool2d_backward",
     "qiddm_qconv_forward_io", "qiddm_qconv_backward_io",
     "qiddm_dense_mse_step_workspace_bytes", "qiddm_dense_mse_step",
+    "qiddm_skinny_linear_workspace_bytes", "qiddm_skinny_linear_forward", "qiddm_skinny_linear_backward",
 ]
 
 _lib = None
@@ -144,6 +145,12 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_dense_mse_step_workspace_bytes.argtypes = [vp, i64, i32]
         lib.qiddm_dense_mse_step.restype = i32
         lib.qiddm_dense_mse_step.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, f64, f64, f64, f64, vp, i32, vp, vp, vp, i32, i32, vp]
+        lib.qiddm_skinny_linear_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_skinny_linear_workspace_bytes.argtypes = [i64, i32, i32]
+        lib.qiddm_skinny_linear_forward.restype = i32
+        lib.qiddm_skinny_linear_forward.argtypes = [vp, vp, vp, vp, i32, i64, i32, i32, vp]
+        lib.qiddm_skinny_linear_backward.restype = i32
+        lib.qiddm_skinny_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp, vp]
         lib.qiddm_noise_ladder.restype = i32
         lib.qiddm_noise_ladder.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]
         lib.qiddm_mse_workspace_bytes.restype = C.c_size_t

@@ -696,6 +696,20 @@ int qiddm_maxpool2d_backward(const void *x, const void *grad_y, void *grad_x, in
     return qiddm::maxpool2d(x, grad_y, grad_x, dtype, true, planes, h, w, kernel, (cudaStream_t)stream);
 }
 
+size_t qiddm_skinny_linear_workspace_bytes(int64_t rows, int in_features, int out_features) {
+    return qiddm::skinny_linear_ws_bytes(rows, in_features, out_features);
+}
+int qiddm_skinny_linear_forward(const void *x, const void *weight, const void *bias, void *y, int dtype, int64_t rows,
+                                int in_features, int out_features, qiddm_stream_t stream) {
+    return qiddm::skinny_linear_forward(x, weight, bias, y, dtype, rows, in_features, out_features, (cudaStream_t)stream);
+}
+int qiddm_skinny_linear_backward(const void *x, const void *weight, const void *grad_y, void *grad_x, void *grad_weight,
+                                 void *grad_bias, int dtype, int64_t rows, int in_features, int out_features, void *workspace,
+                                 qiddm_stream_t stream) {
+    return qiddm::skinny_linear_backward(x, weight, grad_y, grad_x, grad_weight, grad_bias, dtype, rows, in_features, out_features,
+                                         workspace, (cudaStream_t)stream);
+}
+
 int qiddm_noise_ladder(const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels, int tau,
                        void *noisy, void *clean, qiddm_stream_t stream) {
     return qiddm::noise_ladder(x, eps, w, dtype, batch, pixels, tau, noisy, clean, (cudaStream_t)stream);

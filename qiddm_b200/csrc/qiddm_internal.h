@@ -120,4 +120,11 @@ int batchnorm_backward(const void *x, const void *dy, void *dx, int dtype, int N
 int maxpool2d(const void *x, const void *gy, void *out, int dtype, bool backward, long long planes, int H, int W, int k,
               cudaStream_t s);
 
+// qiddm_linear.cu — Linear layers with one narrow side (linear_down / linear_up of the re-upload families)
+size_t skinny_linear_ws_bytes(long long rows, int in_f, int out_f);
+int skinny_linear_forward(const void *x, const void *w, const void *bias, void *y, int dtype, long long rows, int in_f, int out_f,
+                          cudaStream_t s);
+int skinny_linear_backward(const void *x, const void *w, const void *grad_y, void *grad_x, void *grad_w, void *grad_b, int dtype,
+                           long long rows, int in_f, int out_f, void *ws, cudaStream_t s);
+
 }  // namespace qiddm

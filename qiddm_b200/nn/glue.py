@@ -227,3 +227,62 @@ class Upsample(torch.nn.Upsample):
             h_out, w_out = int(h * fh), int(w * fw)       # floor, as torch computes the output size
             sh, sw = 1.0 / fh, 1.0 / fw                   # the given scale factor drives the source coordinates
         return _UpsampleFunction.apply(x, h_out, w_out, float(sh), float(sw))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Linear layers with one narrow side (linear_down: pixels -> qubits, linear_up: qubits -> pixels; nn/qdense.py:219-386, :565-670)
+# ------------------------------------------------------------------------------------------------------------------
+SKINNY_MAX = 16          # narrow side the streaming kernels are instantiated for
+SKINNY_MIN_WIDE = 128    # below this the layer is tiny either way: torch
+SKINNY_MIN_ROWS = 4096   # streaming kernels pay above a few thousand rows (2560 rows x 4096: the library GEMM was faster)
+
+
+class _SkinnyLinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = L.load_library()
+        x = x.contiguous()
+        w = weight.detach().to(x.dtype).contiguous()
+        b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
+        rows, in_f = x.shape
+        out_f = w.shape[0]
+        y = torch.empty((rows, out_f), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.qiddm_skinny_linear_forward(L._ptr(x), L._ptr(w), L._ptr(b), L._ptr(y), _DT[x.dtype], rows, in_f, out_f,
+                                                    _stream(x.device)), "qiddm_skinny_linear_forward")
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        ctx.w_dtype = weight.dtype
+        ctx.b_dtype = bias.dtype if bias is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load_library()
+        x, w = ctx.saved_tensors
+        gy = gy.to(x.dtype).contiguous()
+        rows, in_f = x.shape
+        out_f = w.shape[0]
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty_like(w) if (need_w or need_b) else None
+        gb = torch.empty(out_f, dtype=x.dtype, device=x.device) if need_b else None
+        if rows == 0:
+            return (gx, torch.zeros_like(w).to(ctx.w_dtype) if need_w else None,
+                    torch.zeros(out_f, dtype=ctx.b_dtype, device=x.device) if need_b else None)
+        with torch.cuda.device(x.device):
+            ws = torch.empty(int(lib.qiddm_skinny_linear_workspace_bytes(rows, in_f, out_f)), dtype=torch.uint8, device=x.device)
+            L.check(lib.qiddm_skinny_linear_backward(L._ptr(x), L._ptr(w), L._ptr(gy), L._ptr(gx), L._ptr(gw), L._ptr(gb),
+                                                     _DT[x.dtype], rows, in_f, out_f, L._ptr(ws), _stream(x.device)),
+                    "qiddm_skinny_linear_backward")
+        return (gx, gw.to(ctx.w_dtype) if need_w else None, gb.to(ctx.b_dtype) if need_b else None)
+
+
+def skinny_linear(x: torch.Tensor, layer: torch.nn.Linear) -> torch.Tensor:
+    """`layer(x)` for a (rows, in) CUDA float32 / float64 input through the streaming kernels when one side of the layer is
+    narrow (<= 16) and the other wide; anything else (CPU tensors, other shapes / dtypes) goes through torch."""
+    in_f, out_f = layer.in_features, layer.out_features
+    if (x.is_cuda and x.dim() == 2 and x.dtype in _DT and min(in_f, out_f) <= SKINNY_MAX and max(in_f, out_f) >= SKINNY_MIN_WIDE
+            and layer.weight.is_cuda and x.shape[0] >= SKINNY_MIN_ROWS):
+        return _SkinnyLinearFunction.apply(x, layer.weight, layer.bias)
+    return layer(x)

@@ -29,6 +29,7 @@ import torch.nn as nn
 from .. import _lib as L
 from ..channels import apply_readout_channel, channel_matrix, run_noisy_stage
 from ..functional import run_stage
+from .glue import skinny_linear
 from ..pca import DevicePCA
 
 QDEV_NAME = "qiddm_b200:sm_100a"
@@ -273,7 +274,7 @@ class QNN_A(nn.Module):
 
     def forward(self, x):
         x = einops.rearrange(x, "b 1 w h -> b (w h)")
-        x = self.linear_down(x)
+        x = skinny_linear(x, self.linear_down)
         noise = self.add_noise
         if channel_matrix(noise, self._noise_params.get(noise, 0.0)) is not None:
             _check_noise(noise, True, readout_channels=True)
@@ -336,14 +337,14 @@ class _QNNBase(_SaveLoadMixin, nn.Module):
     def forward(self, x):
         b, c, w, h = x.shape
         x = x.view(b, -1).to(self.linear_down.weight.dtype)
-        x_reduced = self.linear_down(x)
+        x_reduced = skinny_linear(x, self.linear_down)
         if getattr(self, "add_noise", 0) == 3:
             x_reduced = self._noisy_expvals(b) + 0.0 * x_reduced.sum()       # keeps linear_down in the graph (zero gradient)
         else:
             x_reduced = self._circuit(x_reduced)       # add_noise 1 / 2: the channels act on |0..0> and change nothing
         if self.detach_quantum:
             x_reduced = x_reduced.detach()
-        x_restored = self.linear_up(x_reduced.to(self.linear_up.weight.dtype))
+        x_restored = skinny_linear(x_reduced.to(self.linear_up.weight.dtype), self.linear_up)
         return x_restored.view(b, c, w, h)
 
 
@@ -668,7 +669,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
             return a.to(ref.device).to(ref.dtype)
         if self._reduce == "conv":
             return self.conv_layer(x).view(b, self.hidden_features, -1).mean(dim=2)
-        return self.linear_down(x.reshape(b, -1).to(self.linear_down.weight.dtype))
+        return skinny_linear(x.reshape(b, -1).to(self.linear_down.weight.dtype), self.linear_down)
 
     def _between_stages(self, a):
         return a
@@ -702,7 +703,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
                 a = a.detach()
         a = a.view(b, -1)
         if self._restore == "linear":
-            out = self.linear_up(a.to(self.linear_up.weight.dtype))
+            out = skinny_linear(a.to(self.linear_up.weight.dtype), self.linear_up)
         else:
             out = _pca_call(self.pca, "inverse_transform", a, getattr(self, "pca_group", None)).to(x.dtype).requires_grad_(True)
         return out.view(b, c, w, h)

@@ -221,3 +221,50 @@ def test_unet_blocks_fuse_their_relus_and_keep_the_state_dict_keys():
     ref_keys = {"down_blocks.0.net.0.weight", "down_blocks.0.net.1.running_mean", "up_blocks.0.net.2.weight", "up_blocks.1.net.4.bias",
                 "final_conv.weight"}
     assert ref_keys <= set(m.state_dict().keys())
+
+
+@pytest.mark.parametrize("rows,in_f,out_f,dtype,bias", [(1000, 784, 6, torch.float64, True), (1000, 6, 784, torch.float64, True),
+                                                        (333, 4096, 8, torch.float32, True), (257, 8, 4096, torch.float32, True),
+                                                        (64, 784, 16, torch.float64, False), (5000, 784, 6, torch.float32, False),
+                                                        (31, 1, 300, torch.float64, True), (40960, 784, 6, torch.float64, True)])
+def test_skinny_linear_matches_torch(rows, in_f, out_f, dtype, bias, monkeypatch):
+    """linear_down / linear_up shapes of nn/qdense.py:219-386, :565-670 (and the 64 x 64 ones of config 5): forward, grad_x,
+    grad_weight, grad_bias against torch.nn.functional.linear in the same dtype."""
+    from qiddm_b200.nn import glue
+    from qiddm_b200.nn.glue import skinny_linear
+    monkeypatch.setattr(glue, "SKINNY_MIN_ROWS", 1)        # the kernels themselves, also below the dispatch threshold
+    torch.manual_seed(rows + in_f)
+    layer = torch.nn.Linear(in_f, out_f, bias=bias).to("cuda", dtype)
+    x = torch.randn(rows, in_f, device="cuda", dtype=dtype, requires_grad=True)
+    gy = torch.randn(rows, out_f, device="cuda", dtype=dtype)
+    y = skinny_linear(x, layer)
+    assert y.grad_fn is not None and type(y.grad_fn).__name__.startswith("_SkinnyLinear"), "the streaming kernels were not taken"
+    y.backward(gy)
+    got = (y.detach(), x.grad.clone(), layer.weight.grad.clone(), layer.bias.grad.clone() if bias else None)
+    x.grad = None
+    layer.zero_grad()
+    yr = torch.nn.functional.linear(x, layer.weight, layer.bias)
+    yr.backward(gy)
+    ref = (yr.detach(), x.grad, layer.weight.grad, layer.bias.grad if bias else None)
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    for a, b, name in zip(got, ref, ("y", "grad_x", "grad_w", "grad_b")):
+        if b is not None:
+            assert rel_to_max(a, b) <= tol, name
+
+
+def test_skinny_linear_partial_gradients_and_fallback():
+    """Only the gradients autograd asks for are computed (first layer: no grad_x); shapes outside the kernels go to torch."""
+    from qiddm_b200.nn.glue import skinny_linear
+    layer = torch.nn.Linear(784, 6).to("cuda", torch.float64)
+    x = torch.randn(5000, 784, device="cuda", dtype=torch.float64)          # no grad
+    y = skinny_linear(x, layer)
+    y.sum().backward()
+    ref = torch.nn.functional.linear(x, layer.weight.detach(), layer.bias.detach())
+    assert rel_to_max(y, ref) <= 1e-12
+    assert rel_to_max(layer.weight.grad, x.sum(0, keepdim=True).expand(6, -1)) <= 1e-12
+    assert rel_to_max(layer.bias.grad, torch.full((6,), 5000.0, dtype=torch.float64)) <= 1e-12
+    small = torch.nn.Linear(16, 8).to("cuda", torch.float64)
+    ys = skinny_linear(torch.randn(10, 16, device="cuda", dtype=torch.float64), small)
+    assert not type(ys.grad_fn).__name__.startswith("_SkinnyLinear")
+    few = skinny_linear(torch.randn(100, 784, device="cuda", dtype=torch.float64), layer)      # below SKINNY_MIN_ROWS
+    assert not type(few.grad_fn).__name__.startswith("_SkinnyLinear")
