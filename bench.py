@@ -340,8 +340,8 @@ def run_b200(args):
     # clocks sampled over both timed regions (device-resident steps and the end-to-end steps)
     clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
     if clocks is not None and "sw_power_cap" in (clocks.get("reasons") or []):
-        # nvidia-smi's polled clocks.sm does not resolve the cap: ncu reports 1.17-1.43 GHz inside the GEMM launches
-        clocks["note"] = "power cap active: ncu shows 1.17-1.43 GHz SM clock inside the GEMM launches (profiles/r1_gemm_pair_summary.md)"
+        # nvidia-smi's polled clocks.sm does not resolve the cap: ncu reports 1.27-1.45 GHz inside the GEMM launches
+        clocks["note"] = "power cap active: ncu shows 1.27-1.45 GHz SM clock inside the GEMM launches (profiles/r2b_summary.md)"
 
     # --- sustained rate: the same device-resident step back to back for >= 3 s (the "sustained" tensor peak is a 4 s loop)
     sustained = None
@@ -402,8 +402,8 @@ def run_b200(args):
                     "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                     "frac": achieved / tc_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the step's three GEMM launches, from
-                    # the committed `ncu --set full` capture of this command (profiles/r1_gemm_pair_ncu_full_raw.csv; 8.3-11.2e9
-                    # across the captures of the round: the dW launch's L2 re-reads vary with the box, profiles/r1_gemm_pair_summary.md)
+                    # the committed `ncu --set full` capture of this command (profiles/r2b_gemm_pair_ncu_full_raw.csv via
+                    # profiles/r2_gemm_traffic.json; not measured in this run -- `traffic_source` says which capture)
                     "traffic": traffic, "traffic_source": traffic_src,
                     "traffic_unit": "DRAM bytes/launch, mean of the step's GEMM launches; the algorithm's own bytes per launch "
                                     "(fp32 x / grad_out in, out / grad_in out, shared by the step's 3 launches): %.3g"
