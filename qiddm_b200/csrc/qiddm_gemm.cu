@@ -2416,10 +2416,15 @@ int gemm_dw_and_assemble(const GemmShape &g, const GateParams &gp, __half *const
         const int workers = pair ? 74 : 148;
         int splits = 1;
         double best = 1e30;
-        for (int sp = 1; sp <= 64 && sp <= kt; ++sp) {
+        // ... and, for the pair kernel, a price on the LENGTH of an item's accumulation chain: every tcgen05.mma accumulate
+        // truncates, so a same-sign sum over r batch rows comes out low by about 3.5e-8 r relative (measured through the
+        // parameter gradient, profiles/r2b_summary.md); 74 instead of 37 splits at 2^19 rows cost 0.5 % of the launch
+        const int max_splits = pair ? 128 : 64;
+        for (int sp = 1; sp <= max_splits && sp <= kt; ++sp) {
             const long long items = (long long)tiles * sp;
             const long long waves = (items + workers - 1) / workers;
-            const double cost = (double)(waves * workers) / (double)items + 0.004 * sp + (items < workers ? 10.0 : 0.0);
+            const double per_split = pair ? 0.0005 * sp + 4e-6 * (double)Bp / sp : 0.004 * sp;
+            const double cost = (double)(waves * workers) / (double)items + per_split + (items < workers ? 10.0 : 0.0);
             if (cost < best) { best = cost; splits = sp; }
         }
         {
