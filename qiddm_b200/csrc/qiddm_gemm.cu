@@ -1783,24 +1783,31 @@ __global__ void __launch_bounds__(256) ladder_prep_kernel(const T *x, const floa
             }
         }
         for (int t = 0; t < steps; ++t) {
-            const T wt = w[t + 1];
+            const T wt = w[t + 1], omw = (T)1 - wt;
             const long long row = b * steps + t;
             float ss = 0.f;
 #pragma unroll
             for (int it = 0; it < ITS; ++it) {
                 const int c = 8 * lane + 256 * it;
                 if (c < Kp) {
-                    __half hi[8], lo[8];
+                    float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float f = 0.f;
+                        f[j] = 0.f;
                         if (c + j < F) {
-                            T v = xv[it][j] * ((T)1 - wt) + (T)ev[it][j] * wt;
+                            T v = xv[it][j] * omw + (T)ev[it][j] * wt;
                             v = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
-                            f = (float)v + add_offset;
+                            f[j] = (float)v + add_offset;
                         }
-                        ss += f * f;
-                        split_act((c + j == F && n_pad > 0) ? 1.f : f, hi[j], lo[j]);
+                        ss += f[j] * f[j];
+                    }
+                    if (n_pad > 0 && c <= F && F < c + 8) f[F - c] = 1.f;       // the ones column (one lane of one chunk per row)
+                    __half2 hi[4], lo[4];                                        // packed conversions: two features per instruction
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        hi[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                        const float2 hf = __half22float2(hi[j]);
+                        lo[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
                     }
                     *reinterpret_cast<uint4 *>(Xh + row * Kp + c) = *reinterpret_cast<const uint4 *>(hi);       // Kp is a multiple of 8
                     if (want_lo) *reinterpret_cast<uint4 *>(Xl + row * Kp + c) = *reinterpret_cast<const uint4 *>(lo);

@@ -101,3 +101,17 @@ def test_fused_step_with_single_pass_gradients_and_graph_capture():
     losses = [float(step.step(x)) for _ in range(3)]
     assert all(l == l and l > 0 for l in losses)
     assert not torch.equal(net.weights.detach(), w0)
+
+
+def test_fused_step_at_the_bench_size_equals_the_unfused_sequence():
+    """bench.py's e2e configuration (QDenseUndirected_old_noise(60, 28), 52 428 images x 10 levels = 524 280 circuit instances,
+    float32): the fused step against the un-fused kernel sequence on the same noise draw -- the size-independent property
+    that stands in for the oracle, which needs hours at this size."""
+    torch.manual_seed(1)
+    net, diff = _make("data", 60, 28, torch.float32)
+    x = torch.rand(52428, 784, device="cuda")
+    l1, g1 = _step(diff, net, x, 10, seed=4, fused=True)
+    l0, g0 = _step(diff, net, x, 10, seed=4, fused=False)
+    assert abs(l1.item() - l0.item()) <= 2e-6 * abs(l0.item()), (l1.item(), l0.item())
+    assert rel_to_max(g1, g0) <= 3e-5
+    assert torch.isfinite(g1).all() and g1.abs().max().item() > 0

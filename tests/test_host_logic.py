@@ -1,6 +1,7 @@
 """CPU tests of the host-side mirror of the reference interface: constructors, state_dict contract (F2),
 save_name strings, noise ladder, Diffusion wrapper semantics, UNet glue helpers."""
 import json
+import os
 
 import pytest
 import torch
@@ -214,3 +215,26 @@ def test_path_dispatch_cost_model_against_the_measured_sweep():
     assert not FakePlan(spec).use_gemm(1 << 20)
     spec = L.StageSpec(n_qubits=10, layers_per_block=60, init=L.INIT_AMPLITUDE, n_features=784, read_count=784, path=L.PATH_GEMM)
     assert FakePlan(spec).use_gemm(1)
+
+
+def test_fused_step_dispatch_conditions_on_the_host():
+    """`Diffusion._fused_step` only hands the training step to the library for nets that offer `fused_mse_step`, the reference's
+    ladder and MSELoss, and non-verbose calls; a QDense net declines CPU tensors itself (no CPU path anywhere)."""
+    import torch
+    from qiddm_b200 import models, nn, noise
+    net = nn.QDenseUndirected_old_noise(2, 4)
+    diff = models.Diffusion(net, noise.add_normal_noise_multiple, "data", (4, 4), torch.nn.MSELoss())
+    x = torch.rand(3, 16)
+    assert diff._fused_step(x, {"T": 4}) is None                       # CPU tensor: the net declines
+    assert diff._fused_step(x, {"T": 4, "verbose": True}) is None
+    diff2 = models.Diffusion(net, lambda d, tau, decay_mod: d, "data", (4, 4), torch.nn.MSELoss())
+    assert diff2._fused_step(x, {"T": 4}) is None                      # custom noise schedule
+    diff3 = models.Diffusion(net, noise.add_normal_noise_multiple, "data", (4, 4), torch.nn.L1Loss())
+    assert diff3._fused_step(x, {"T": 4}) is None                      # another loss
+    diff4 = models.Diffusion(torch.nn.Linear(16, 16), noise.add_normal_noise_multiple, "data", (4, 4), torch.nn.MSELoss())
+    assert diff4._fused_step(x, {"T": 4}) is None                      # a net without the hook
+    os.environ["QIDDM_FUSED_STEP"] = "0"
+    try:
+        assert diff._fused_step(x, {"T": 4}) is None
+    finally:
+        os.environ.pop("QIDDM_FUSED_STEP", None)
