@@ -1824,6 +1824,55 @@ __global__ void __launch_bounds__(256) ladder_prep_kernel(const T *x, const floa
     if (lane == 0 && best > 0.f && best < 3.0e38f) atomicMax(in2max_bits, __float_as_uint(best));
 }
 
+// Wide rows (Kp > 1280: n = 11, 12): one warp per ROW, the image re-read per level through L1 / L2 (no register staging).
+template <typename T>
+__global__ void __launch_bounds__(256) ladder_prep_rows_kernel(const T *x, const float *eps, const T *w, long long n_img, int steps,
+                                                               int F, int Kp, int n_pad, float add_offset, float pad, __half *Xh,
+                                                               __half *Xl, float *inv_n2, int want_lo, unsigned int *in2max_bits) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long B = n_img * steps;
+    float best = 0.f;
+    for (long long row = warp0; row < B; row += nwarps) {
+        const long long b = row / steps;
+        const T wt = w[(int)(row - b * steps) + 1], omw = (T)1 - wt;
+        const T *xs = x + b * F;
+        const float *es = eps + b * F;
+        float ss = 0.f;
+        for (int c = 8 * lane; c < Kp; c += 256) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                f[j] = 0.f;
+                if (c + j < F) {
+                    T v = __ldg(xs + c + j) * omw + (T)__ldg(es + c + j) * wt;
+                    v = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+                    f[j] = (float)v + add_offset;
+                }
+                ss += f[j] * f[j];
+            }
+            if (n_pad > 0 && c <= F && F < c + 8) f[F - c] = 1.f;
+            __half2 hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hi[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                const float2 hf = __half22float2(hi[j]);
+                lo[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+            }
+            *reinterpret_cast<uint4 *>(Xh + row * Kp + c) = *reinterpret_cast<const uint4 *>(hi);
+            if (want_lo) *reinterpret_cast<uint4 *>(Xl + row * Kp + c) = *reinterpret_cast<const uint4 *>(lo);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        ss += (float)n_pad * pad * pad;
+        const float in2 = ss > 0.f ? 1.0f / ss : 0.f;
+        if (lane == 0) inv_n2[row] = in2;
+        best = fmaxf(best, in2);
+    }
+    if (lane == 0 && best > 0.f && best < 3.0e38f) atomicMax(in2max_bits, __float_as_uint(best));
+}
+
 // bits[0] = bound on max |G| = c sqrt(max_rows 1/|f|^2)  (|Y'| <= w_scale |f|; c holds the analytic bound on |grad_out|), bits[1] = 0
 __global__ void set_g_bound_kernel(unsigned int *bits, const unsigned int *in2max_bits, float c) {
     const float v = c * sqrtf(__uint_as_float(*in2max_bits));
@@ -2496,8 +2545,19 @@ int gemm_dense_mse_step(const GemmShape &g, const GateParams &gp, const void *co
     const long long blocks = (n_img + 7) / 8;
     const unsigned grid = (unsigned)(blocks < 148 * 8 ? blocks : 148 * 8);
     const int its = (g.Kp + 255) / 256;              // 8 values per lane and iteration
-    if (its > 5) return QIDDM_EUNSUPPORTED;          // n <= 10 (Kp <= 1032); larger layers take the unfused sequence
     timing_begin(TK_PREP_X, 0.0, s);
+    if (its > 5) {                                   // n = 11, 12: one warp per row
+        const long long rblocks = (n_img * T + 7) / 8;
+        const unsigned rgrid = (unsigned)(rblocks < 148 * 16 ? rblocks : 148 * 16);
+        if (io64)
+            ladder_prep_rows_kernel<double><<<rgrid, 256, 0, s>>>(reinterpret_cast<const double *>(x), eps, reinterpret_cast<const double *>(w),
+                                                                  n_img, T, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, X[0], X[1],
+                                                                  inv_n2, want_lo, gmax + 2);
+        else
+            ladder_prep_rows_kernel<float><<<rgrid, 256, 0, s>>>(reinterpret_cast<const float *>(x), eps, reinterpret_cast<const float *>(w),
+                                                                 n_img, T, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, X[0], X[1],
+                                                                 inv_n2, want_lo, gmax + 2);
+    } else
 #define QIDDM_LADDER_PREP(TT, ITS_)                                                                                              \
     ladder_prep_kernel<TT, ITS_><<<grid, 256, 0, s>>>(reinterpret_cast<const TT *>(x), eps, reinterpret_cast<const TT *>(w), n_img, \
                                                       T, g.F, g.Kp, g.A - g.F, gp.add_offset, gp.pad_value, X[0], X[1], inv_n2,   \

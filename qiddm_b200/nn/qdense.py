@@ -166,7 +166,6 @@ class _AmplitudeDense(nn.Module):
         the unitary-collapse path, CUDA float32 / float64 images (n, pixels), no noise channel, a trainable `weights`."""
         noise = getattr(self, "add_noise", 0)
         if (not x.is_cuda or x.dim() != 2 or x.shape[1] != self.pixels or x.dtype not in (torch.float32, torch.float64)
-                or self.wires > 10            # the ladder -> splits kernel keeps an image in registers: up to 1280 features
                 or channel_matrix(noise, self._noise_params.get(noise, 0.0)) is not None
                 or not (self.weights.requires_grad and torch.is_grad_enabled()) or self.weights.device != x.device
                 or x.requires_grad):          # a gradient with respect to the images needs the autograd sequence

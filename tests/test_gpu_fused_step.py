@@ -60,10 +60,11 @@ def test_fused_step_matches_oracle(goal, dtype):
 
 
 @pytest.mark.parametrize("goal,side,depth,n,dtype", [("data", 28, 4, 300, torch.float32), ("noise", 28, 3, 77, torch.float64),
-                                                     ("data", 16, 5, 1000, torch.float64), ("data", 12, 3, 130, torch.float32)])
+                                                     ("data", 16, 5, 1000, torch.float64), ("data", 12, 3, 130, torch.float32),
+                                                     ("noise", 40, 2, 30, torch.float32)])
 def test_fused_step_equals_the_unfused_sequence(goal, side, depth, n, dtype):
     """Multi-tile shapes (28 x 28: 7 N tiles; 3 000 rows: 12 M tiles with a ragged last one; 12 x 12 = 144 of 256 amplitudes:
-    pad rows + ones column) against ladder_pair -> run_stage -> mse_loss_and_grad -> autograd of the same library."""
+    pad rows + ones column; 40 x 40 = 1600 pixels: n = 11, the row-per-warp ladder kernel) against ladder_pair -> run_stage -> mse_loss_and_grad -> autograd of the same library."""
     torch.manual_seed(5)
     net, diff = _make(goal, depth, side, dtype, remap_cls="old" if side == 16 else "noise")
     x = torch.rand(n, side * side, dtype=dtype, device="cuda")
