@@ -327,6 +327,30 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = t.item()
     e2e_val = imgs * TAU * world / (ms_e / ke * 1e-3)
+    # the same e2e step with the fusion switched off (QIDDM_FUSED_STEP is read per call): the un-fused kernel sequence, for scale
+    e2e_unfused = None
+    if use_gemm and not args.no_extras and os.environ.get("QIDDM_FUSED_STEP", "1") != "0":
+        os.environ["QIDDM_FUSED_STEP"] = "0"
+        try:
+            for _ in range(2):
+                step_e2e()
+            sync_all()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(3):
+                step_e2e()
+            e1.record()
+            sync_all()
+            ms_u = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms_u], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_u = t.item()
+            e2e_unfused = {"value": imgs * TAU * world / (ms_u / 3 * 1e-3), "unit": UNIT, "ms_per_step": ms_u / 3,
+                           "what": "the same Diffusion.forward step as `e2e` with QIDDM_FUSED_STEP=0 (ladder, prep_x, forward GEMM "
+                                   "with out + Y stores, MSE pass, G pass, dW GEMM, adjoint)"}
+        finally:
+            os.environ.pop("QIDDM_FUSED_STEP", None)
     # per-kernel times of the e2e step (library timers, two extra steps outside the timed region)
     L.timing_enable(True)
     L.timing_collect()
@@ -448,6 +472,8 @@ def run_b200(args):
         line["extras"] = extras(dev) if world == 1 else {}
         if sustained is not None:
             line["extras"]["sustained_3s"] = sustained
+        if e2e_unfused is not None:
+            line["extras"]["e2e_unfused"] = e2e_unfused
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_oracle_rate(cpu_sample_size(args.cpu_instances, 4), steps=3, warmup=1, best=True)
         line["cpu_baseline"] = cb

@@ -176,7 +176,15 @@ class _AmplitudeDense(nn.Module):
         from ..noise import _level_weights
         eps = torch.normal(mean=0.5, std=0.2, size=tuple(x.shape), device=x.device)       # the draw of noise.ladder_pair
         coeffs = (1.0, 0.0, 1.0, 0.0) if goal == "data" else (0.1, -0.05, -1.0, 1.0)
-        loss, gw = plan.dense_mse_step(x, eps, _level_weights(T + 1, decay_mod, x.device, x.dtype), T, self.weights, *coeffs)
+        key = (T, float(decay_mod), x.device, x.dtype)          # the level weights are constants of the schedule: built once
+        cache = self.__dict__.setdefault("_level_w_cache", {})
+        if key not in cache or torch.cuda.is_current_stream_capturing():
+            level_w = _level_weights(T + 1, decay_mod, x.device, x.dtype)
+            if not torch.cuda.is_current_stream_capturing():
+                cache[key] = level_w
+        else:
+            level_w = cache[key]
+        loss, gw = plan.dense_mse_step(x, eps, level_w, T, self.weights, *coeffs)
         gw = gw.view_as(self.weights)
         if self.weights.grad is None:
             self.weights.grad = gw
