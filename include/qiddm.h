@@ -190,6 +190,11 @@ int qiddm_dense_mse_step(const qiddm_plan *plan, const void *collapsed, const vo
  * of io_dtype (QIDDM_DTYPE_F32, or QIDDM_DTYPE_F64 as the reference's float64 UNet passes them — read and written in
  * place of a cast; the simulation itself is fp32); the patch-unfold is fused into the operand preparation and the col2im of the image gradient runs as one
  * gather kernel (grad_img is OVERWRITTEN; may be NULL). */
+/* 1 when the layer runs as a direct fp32 convolution behind the qconv_gemm entry points (csrc/qiddm_conv.cu): 1x1 / 3x3 windows
+ * with "same" padding and at most 16 output channels (N = 2 out_channels <= 32 rows of U).  The staged image band and the N
+ * accumulators of a patch stay on chip: no patch matrix, no fp16 operand splits; results are plain fp32 (QIDDM_QCONV_DIRECT=0
+ * turns it off).  The backward then needs the `saved` buffer of its forward. */
+int qiddm_qconv_direct_supported(const qiddm_plan *plan, const qiddm_unfold_desc *unfold);
 size_t qiddm_qconv_gemm_saved_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images);
 size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images);
 int qiddm_qconv_gemm_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,

@@ -50,7 +50,7 @@ EXPORTS = [
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
-    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id",
+    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported",
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
@@ -190,6 +190,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         for f in (lib.qiddm_qconv_gemm_saved_bytes, lib.qiddm_qconv_gemm_workspace_bytes):
             f.restype = C.c_size_t
             f.argtypes = [vp, C.POINTER(UnfoldDesc), i64]
+        lib.qiddm_qconv_direct_supported.restype = i32
+        lib.qiddm_qconv_direct_supported.argtypes = [vp, C.POINTER(UnfoldDesc)]
         lib.qiddm_qconv_gemm_forward.restype = i32
         lib.qiddm_qconv_gemm_forward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), i32, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_qconv_gemm_backward.restype = i32
@@ -688,6 +690,25 @@ class Plan:
         return loss, grad_w
 
     # ------------------------------------------------------------------ QConv on the unitary-collapse path
+    def qconv_direct(self, unfold: UnfoldDesc) -> bool:
+        """True when the layer has a direct fp32 convolution behind the qconv_gemm entry points (csrc/qiddm_conv.cu)."""
+        key = (unfold.channels, unfold.height, unfold.width, unfold.kernel_h, unfold.kernel_w, unfold.pad_h, unfold.pad_w)
+        cache = self.__dict__.setdefault("_direct", {})
+        v = cache.get(key)
+        if v is None:
+            v = cache[key] = bool(self.lib.qiddm_qconv_direct_supported(self.handle, C.byref(unfold)))
+        return v
+
+    def use_collapse_qconv(self, unfold: UnfoldDesc, patches: int) -> bool:
+        """QConv dispatch: the collapse path (direct convolution where the shape has one, else the tcgen05 GEMM) or gate by
+        gate.  The direct form costs F * N FMAs per patch and pass plus the collapse on 2^n basis columns: it wins as soon as
+        there are at least as many patches as basis columns."""
+        if self.spec.path == PATH_GATE or not self.gemm_supported():
+            return False
+        if self.spec.path == PATH_AUTO and self.qconv_direct(unfold):
+            return patches >= self.spec.dim
+        return self.use_gemm(patches)
+
     @staticmethod
     def _out_hw(img: torch.Tensor, unfold: UnfoldDesc):
         return (img.shape[2] + 2 * unfold.pad_h - unfold.kernel_h + 1,

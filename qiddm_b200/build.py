@@ -11,7 +11,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libqiddm_b200.so"
-SOURCES = ["qiddm_gate.cu", "qiddm_gemm.cu", "qiddm_pca.cu", "qiddm_glue.cu", "qiddm_dm.cu", "qiddm_linear.cu", "qiddm_api.cu"]
+SOURCES = ["qiddm_gate.cu", "qiddm_gemm.cu", "qiddm_pca.cu", "qiddm_glue.cu", "qiddm_dm.cu", "qiddm_linear.cu", "qiddm_conv.cu", "qiddm_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

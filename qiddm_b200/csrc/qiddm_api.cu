@@ -494,8 +494,22 @@ static long long unfold_patches(const qiddm_unfold_desc *u) {
     return (long long)(u->height + 2 * u->pad_h - u->kernel_h + 1) * (u->width + 2 * u->pad_w - u->kernel_w + 1);
 }
 
+// direct fp32 convolution (qiddm_conv.cu) behind the same entry points when the layer's shape has one
+static bool qconv_direct(const qiddm_plan *plan, const qiddm_unfold_desc *unfold) {
+    if (!plan || !gemm_eligible(plan) || !unfold_valid(plan, unfold)) return false;
+    if (plan->d.path == QIDDM_PATH_GEMM) return false;        // an explicit request for the tcgen05 GEMM is honoured
+    GateParams gp = make_params(plan, unfold, 1);
+    return conv_direct_supported(gemm_shape(gp, plan->d.n_qubits), gp);
+}
+
+int qiddm_qconv_direct_supported(const qiddm_plan *plan, const qiddm_unfold_desc *unfold) { return qconv_direct(plan, unfold) ? 1 : 0; }
+
 size_t qiddm_qconv_gemm_saved_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images) {
     if (!plan || !gemm_eligible(plan) || !unfold_valid(plan, unfold) || n_images < 0) return 0;
+    if (qconv_direct(plan, unfold)) {
+        GateParams gp = make_params(plan, unfold, 1);
+        return conv_direct_saved_bytes(gemm_shape(gp, plan->d.n_qubits), gp, n_images > 0 ? n_images : 1);
+    }
     return qiddm_gemm_saved_bytes(plan, n_images * unfold_patches(unfold));
 }
 
@@ -504,6 +518,10 @@ size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfo
     const long long B = n_images > 0 ? n_images * unfold_patches(unfold) : 1;
     GateParams gp = make_params(plan, nullptr, 1);
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    if (qconv_direct(plan, unfold)) {
+        GateParams gu = make_params(plan, unfold, 1);
+        return align_up(conv_direct_ws_bytes(g, gu)) + basis_ws_bytes(plan) + 256;
+    }
     return gemm_backward_ws_bytes(g, B, true) + basis_ws_bytes(plan) + 256;
 }
 
@@ -521,6 +539,9 @@ int qiddm_qconv_gemm_forward(const qiddm_plan *plan, const void *collapsed, cons
     GateParams gp = make_params(plan, unfold, B);
     gp.io64 = io_dtype == QIDDM_DTYPE_F64 ? 1 : 0;
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    if (qconv_direct(plan, unfold))
+        return conv_direct_forward(g, gp, gemm_collapsed_wd(g, const_cast<void *>(collapsed)), img, out, saved, n_images,
+                                   (cudaStream_t)stream);
     return gemm_forward(g, gp, collapsed, reinterpret_cast<const float *>(img), reinterpret_cast<float *>(out), saved, workspace,
                         B, precision, (cudaStream_t)stream);
 }
@@ -549,12 +570,21 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
     gp.io64 = io_dtype == QIDDM_DTYPE_F64 ? 1 : 0;
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
     float *gut = nullptr;
-    int rc = gemm_backward(g, gp, collapsed, reinterpret_cast<const float *>(img), reinterpret_cast<const float *>(grad_out), saved,
+    const bool direct = qconv_direct(plan, unfold);
+    int rc;
+    if (direct) {
+        if (!saved) return QIDDM_EINVAL;      // the direct path keeps Y from its forward (no re-materialisation)
+        rc = conv_direct_backward(g, gp, gemm_collapsed_wd(g, const_cast<void *>(collapsed)), img, grad_out, saved, grad_img, &gut,
+                                  workspace, n_images, s);
+    } else {
+        rc = gemm_backward(g, gp, collapsed, reinterpret_cast<const float *>(img), reinterpret_cast<const float *>(grad_out), saved,
                            reinterpret_cast<float *>(grad_img), &gut, workspace, B, precision, s);
+    }
     if (rc != QIDDM_OK) return rc;
     if (!grad_weights) return QIDDM_OK;
     qiddm_plan t = basis_plan(plan);
-    char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(gemm_backward_ws_bytes(g, B, true));
+    char *gate_ws = reinterpret_cast<char *>(workspace) +
+                    (direct ? align_up(conv_direct_ws_bytes(g, gp)) : align_up(gemm_backward_ws_bytes(g, B, true)));
     return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
                          t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
 }

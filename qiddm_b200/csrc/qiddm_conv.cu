@@ -1,0 +1,708 @@
+// QConv2d on the unitary-collapse path as a DIRECT fp32 convolution (no materialised patch matrix, no operand splits).
+//
+// With the SEL block collapsed into U (qiddm_gemm_prepare), `_QConv2d_FAST` (reference nn/qconv.py:51-56, :71-90 with the
+// H1 line restored) reads only `out_channels` amplitudes of every patch's state, i.e. N = 2 * out_channels real rows of U:
+//     f      = patch + 0.1                                  (F = C kh kw features, zero padding of torch.nn.Unfold)
+//     Y[n]   = sum_c f[c] Wd[c][n] + bias[n]                Wd[c][n] = part_n(U^T[c][m stride]), bias = pad * (rows c >= F)
+//     out[m] = clamp(post / (|f|^2 + n_pad pad^2) * (Y[2m]^2 + Y[2m+1]^2))
+// which is a convolution with N <= 32 output channels, a square, and a division by a box filter of f^2.  For the UNet's
+// layers (F = 9 ... 288, N = 2 ... 32) the tcgen05 path spends its time writing and re-reading the fp16 hi / lo patch
+// matrix (320 B per patch and pass at F = 72 against 64 B of image), the gate path simulates every patch gate by gate.
+// Here a CTA stages a band of image rows (with halo) in shared memory once and every thread keeps the N accumulators of
+// two patches in registers; the FP32 FMA pipe is the bound (F N FMAs per patch and pass), the image is read once.
+//
+//   conv_fwd_kernel       out (NCHW, io dtype), optionally Y (N, Bp) + 1/|f|^2 for the backward
+//   conv_bwd_data_kernel  G = dL/dY from (Y, grad_out) into a haloed tile; gather form of the transposed convolution with
+//                         the normalisation term of the amplitude embedding:  d img = sum_taps (G . Wd) - 2 f sum_taps S / |f|^2
+//   conv_bwd_w_kernel     dWd[c][n] = sum_patches f[c] G[n]: a lane owns one (channel, ky) row of the kernel window (kw taps,
+//                         sliding along x) x 16 outputs in registers for the whole launch; per-CTA partials
+//   conv_reduce_kernel / conv_assemble_kernel  fixed-order fp64 sum of the partials -> READ_STATE cotangent of U^T for the
+//                         adjoint gate kernel
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include "qiddm_internal.h"
+
+namespace qiddm {
+
+namespace {
+
+constexpr int CONV_MAX_WGRID = 320;      // per-CTA dW partials the workspace is sized for
+
+struct ConvParams {
+    const void *img;
+    void *out;
+    const void *go;
+    void *gimg;
+    const float *Wd;           // [(F + 1)][NP], row F = bias
+    float *Y;                  // [N][Bp]
+    float *inv_n2;             // [Bp]
+    float *partials;           // [grid][(F + 1) NP]
+    long long Bp;
+    int n_images, C, H, W, F, N, n_out, bands, TH, TC, CS, units, clamp;
+    int wr, parts;             // conv_bwd_w_kernel: warps per n-chunk (rows / 32), pixel-row parts
+    float add_offset, pad2, post_scale, clamp_lo, clamp_hi;
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// band of image rows [y0 - PH, y0 + th + PH) x columns [-PH, W + PH) of all channels, + add_offset (the zero padding of
+// torch.nn.Unfold becomes add_offset: the reference adds 0.1 to the unfolded patch)
+template <typename IO, int KS>
+__device__ __forceinline__ void stage_image(const ConvParams &p, const IO *ib, int y0, int th, float *tile, int tid, int T) {
+    // one warp per (channel, row) line of the tile, four lines in flight per warp (the loads are the latency to hide)
+    constexpr int PH = KS / 2;
+    const int tr = th + KS - 1, HW = p.H * p.W;
+    const int nrows = p.C * tr, nw = T >> 5, warp = tid >> 5, lane = tid & 31;
+    for (int row0 = warp; row0 < nrows; row0 += 4 * nw) {
+        for (int c = lane; c < p.TC; c += 32) {
+            const int ix = c - PH;
+            const bool colin = ix >= 0 && ix < p.W;
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = row0 + u * nw;
+                const int ch = row / tr, r = row - ch * tr;
+                const int iy = y0 - PH + r;
+                v[u] = 0.f;
+                if (row < nrows && colin && iy >= 0 && iy < p.H) v[u] = (float)__ldg(ib + (long long)ch * HW + iy * p.W + ix);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = row0 + u * nw;
+                const int ch = row / tr, r = row - ch * tr;
+                if (row < nrows) tile[ch * p.CS + r * p.TC + c] = v[u] + p.add_offset;
+            }
+        }
+    }
+}
+
+// dL/dY of one patch from the saved Y and the upstream gradient; g[0..NP) and (WITH_S) g[NP] = S / |f|^2 with
+// S = sum_m go_m out_m (unclamped, passing outputs): the normalisation term of d out / d f.  All loads are issued first.
+template <typename IO, int NP, bool WITH_S>
+__device__ __forceinline__ void patch_grad(const ConvParams &p, const IO *gob, long long gp, int pix, int HW, float *g) {
+    constexpr int M = NP / 2;
+    float a[M], b[M], go[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        a[m] = b[m] = go[m] = 0.f;
+        if (m < p.n_out) {
+            a[m] = __ldg(p.Y + (long long)(2 * m) * p.Bp + gp);
+            b[m] = __ldg(p.Y + (long long)(2 * m + 1) * p.Bp + gp);
+            go[m] = (float)__ldg(gob + (long long)m * HW + pix);
+        }
+    }
+    const float inv = __ldg(p.inv_n2 + gp);
+    float S = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const float pr = a[m] * a[m] + b[m] * b[m];
+        const float v = p.post_scale * inv * pr;
+        const bool pass = !p.clamp || (v >= p.clamp_lo && v <= p.clamp_hi);
+        const float cm = pass ? p.post_scale * go[m] : 0.f;
+        *reinterpret_cast<float2 *>(g + 2 * m) = f2(2.f * cm * inv * a[m], 2.f * cm * inv * b[m]);
+        S += cm * inv * pr;
+    }
+    if (WITH_S) g[NP] = inv * S;
+}
+
+// ------------------------------------------------------------------------------------------------------------ forward
+template <typename IO, int KS, int NP>
+__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvParams p) {
+    extern __shared__ float4 conv_smem[];
+    constexpr int KK = KS * KS;
+    float *wd = reinterpret_cast<float *>(conv_smem);
+    float *tile = wd + (((p.F + 1) * NP + 3) & ~3);
+    const int T = blockDim.x, tid = threadIdx.x;
+    for (int i = tid; i < (p.F + 1) * NP; i += T) wd[i] = __ldg(p.Wd + i);
+    const int HW = p.H * p.W;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int b = unit / p.bands, band = unit - b * p.bands;
+        const int y0 = band * p.TH;
+        const int th = min(p.TH, p.H - y0);
+        __syncthreads();
+        stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
+        __syncthreads();
+        const int npx = th * p.W;
+        int q[2], base[2];
+        bool ok[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            q[k] = tid + k * T;
+            ok[k] = q[k] < npx;
+            const int qq = ok[k] ? q[k] : 0;
+            const int y = qq / p.W, x = qq - y * p.W;
+            base[k] = y * p.TC + x;
+        }
+        float2 acc[2][NP / 2];
+#pragma unroll
+        for (int j = 0; j < NP / 2; ++j) acc[0][j] = acc[1][j] = *reinterpret_cast<const float2 *>(wd + p.F * NP + 2 * j);
+        float ss[2] = {0.f, 0.f};
+#pragma unroll 1
+        for (int ch = 0; ch < p.C; ++ch) {
+            const float *t0 = tile + ch * p.CS + base[0], *t1 = tile + ch * p.CS + base[1];
+            const float4 *w4 = reinterpret_cast<const float4 *>(wd + ch * KK * NP);
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    const float f0 = t0[ky * p.TC + kx], f1 = t1[ky * p.TC + kx];
+                    ss[0] = fmaf(f0, f0, ss[0]);
+                    ss[1] = fmaf(f1, f1, ss[1]);
+                    const float2 ff0 = f2(f0, f0), ff1 = f2(f1, f1);
+#pragma unroll
+                    for (int j = 0; j < NP / 4; ++j) {
+                        const float4 w = w4[(ky * KS + kx) * (NP / 4) + j];
+                        acc[0][2 * j] = __ffma2_rn(f2(w.x, w.y), ff0, acc[0][2 * j]);
+                        acc[0][2 * j + 1] = __ffma2_rn(f2(w.z, w.w), ff0, acc[0][2 * j + 1]);
+                        acc[1][2 * j] = __ffma2_rn(f2(w.x, w.y), ff1, acc[1][2 * j]);
+                        acc[1][2 * j + 1] = __ffma2_rn(f2(w.z, w.w), ff1, acc[1][2 * j + 1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!ok[k]) continue;
+            const int pix = y0 * p.W + q[k];
+            const long long gp = (long long)b * HW + pix;
+            const float s = ss[k] + p.pad2;
+            const float inv = s > 0.f ? 1.0f / s : 0.f;
+            if (p.Y != nullptr) {
+                p.inv_n2[gp] = inv;
+#pragma unroll
+                for (int j = 0; j < NP / 2; ++j) {
+                    if (2 * j < p.N) {
+                        p.Y[(long long)(2 * j) * p.Bp + gp] = acc[k][j].x;
+                        p.Y[(long long)(2 * j + 1) * p.Bp + gp] = acc[k][j].y;
+                    }
+                }
+            }
+            IO *ob = reinterpret_cast<IO *>(p.out) + (long long)b * p.n_out * HW + pix;
+#pragma unroll
+            for (int m = 0; m < NP / 2; ++m) {
+                if (m < p.n_out) {
+                    float v = p.post_scale * inv * (acc[k][m].x * acc[k][m].x + acc[k][m].y * acc[k][m].y);
+                    if (p.clamp) v = fminf(fmaxf(v, p.clamp_lo), p.clamp_hi);
+                    ob[(long long)m * HW] = (IO)v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- image gradient (gather)
+template <typename IO, int KS, int NP, int CT>
+__global__ void __launch_bounds__(256) conv_bwd_data_kernel(const ConvParams p) {
+    extern __shared__ float4 conv_smem[];
+    constexpr int KK = KS * KS, PH = KS / 2, GS = NP + 4, NC = NP < 16 ? NP : 16, NQ = NC / 4;
+    const int c_pad = (p.C + CT - 1) / CT * CT;
+    float *wd = reinterpret_cast<float *>(conv_smem);               // [c_pad KK][NP], rows >= F zero
+    float *gt = wd + c_pad * KK * NP;                               // [th + KS - 1][W + KS - 1][GS]
+    const int T = blockDim.x, tid = threadIdx.x;
+    for (int i = tid; i < c_pad * KK * NP; i += T) wd[i] = i < p.F * NP ? __ldg(p.Wd + i) : 0.f;
+    const int HW = p.H * p.W, tcg = p.W + KS - 1;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int b = unit / p.bands, band = unit - b * p.bands;
+        const int y0 = band * p.TH;
+        const int th = min(p.TH, p.H - y0);
+        __syncthreads();
+        const IO *gob = reinterpret_cast<const IO *>(p.go) + (long long)b * p.n_out * HW;
+        for (int i = tid; i < (th + KS - 1) * tcg; i += T) {
+            const int r = i / tcg, c = i - r * tcg;
+            const int py = y0 - PH + r, px = c - PH;
+            float *g = gt + i * GS;
+            if (py >= 0 && py < p.H && px >= 0 && px < p.W) {
+                patch_grad<IO, NP, true>(p, gob, (long long)b * HW + py * p.W + px, py * p.W + px, HW, g);
+            } else {
+#pragma unroll
+                for (int n = 0; n <= NP; ++n) g[n] = 0.f;
+            }
+        }
+        __syncthreads();
+        const int npx = th * p.W;
+        int q[2], gbase[2];
+        bool ok[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            q[k] = tid + k * T;
+            ok[k] = q[k] < npx;
+            const int qq = ok[k] ? q[k] : 0;
+            const int y = qq / p.W, x = qq - y * p.W;
+            gbase[k] = ((y + KS - 1) * tcg + (x + KS - 1)) * GS;      // tap (ky, kx) reads the patch at (y - ky + PH, x - kx + PH)
+        }
+        float nsum[2] = {0.f, 0.f};
+#pragma unroll 1
+        for (int ct = 0; ct < c_pad; ct += CT) {
+            float2 acc[2][CT];
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) acc[0][ch] = acc[1][ch] = f2(0.f, 0.f);
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    const float *g0 = gt + gbase[0] - (ky * tcg + kx) * GS, *g1 = gt + gbase[1] - (ky * tcg + kx) * GS;
+                    if (ct == 0) {
+                        nsum[0] += g0[NP];
+                        nsum[1] += g1[NP];
+                    }
+#pragma unroll
+                    for (int nc = 0; nc < NP / NC; ++nc) {
+                        float4 G0[NQ], G1[NQ];
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) {
+                            G0[j] = *reinterpret_cast<const float4 *>(g0 + nc * NC + 4 * j);
+                            G1[j] = *reinterpret_cast<const float4 *>(g1 + nc * NC + 4 * j);
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < CT; ++ch) {
+                            const float4 *w4 = reinterpret_cast<const float4 *>(wd + ((ct + ch) * KK + ky * KS + kx) * NP + nc * NC);
+#pragma unroll
+                            for (int j = 0; j < NQ; ++j) {
+                                const float4 w = w4[j];
+                                acc[0][ch] = __ffma2_rn(f2(G0[j].x, G0[j].y), f2(w.x, w.y), acc[0][ch]);
+                                acc[0][ch] = __ffma2_rn(f2(G0[j].z, G0[j].w), f2(w.z, w.w), acc[0][ch]);
+                                acc[1][ch] = __ffma2_rn(f2(G1[j].x, G1[j].y), f2(w.x, w.y), acc[1][ch]);
+                                acc[1][ch] = __ffma2_rn(f2(G1[j].z, G1[j].w), f2(w.z, w.w), acc[1][ch]);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (!ok[k]) continue;
+                const int pix = y0 * p.W + q[k];
+#pragma unroll
+                for (int ch = 0; ch < CT; ++ch) {
+                    const int c = ct + ch;
+                    if (c < p.C) {
+                        const long long idx = ((long long)b * p.C + c) * HW + pix;
+                        const float f = (float)__ldg(reinterpret_cast<const IO *>(p.img) + idx) + p.add_offset;
+                        reinterpret_cast<IO *>(p.gimg)[idx] = (IO)((acc[k][ch].x + acc[k][ch].y) - 2.f * f * nsum[k]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- weight gradient
+template <typename IO, int KS, int NP>
+__global__ void __launch_bounds__(256) conv_bwd_w_kernel(const ConvParams p) {
+    extern __shared__ float4 conv_smem[];
+    constexpr int KK = KS * KS, GS = NP + 4, NC = NP < 16 ? NP : 16, NQ = NC / 4;
+    float *dacc = reinterpret_cast<float *>(conv_smem);             // [(F + 1)][NP] sums of this CTA
+    float *tile = dacc + (((p.F + 1) * NP + 3) & ~3);               // [C][CS]
+    float *gt = tile + ((p.C * p.CS + 3) & ~3);                     // [TH W][GS]
+    const int T = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (p.F + 1) * NP; i += T) dacc[i] = 0.f;
+    const int HW = p.H * p.W;
+    // warp -> (n-chunk, 32 rows of the kernel window, part of the band's pixel rows)
+    const int ig = warp % (p.wr * (NP / NC)), part = warp / (p.wr * (NP / NC));
+    const int nchunk = ig / p.wr;
+    const int row = (ig % p.wr) * 32 + lane;                        // (channel, ky)
+    const bool rowok = row < p.C * KS;
+    const int ch = rowok ? row / KS : 0, ky = rowok ? row - ch * KS : 0;
+    float2 acc[KS][NC / 2];
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+        for (int j = 0; j < NC / 2; ++j) acc[kx][j] = f2(0.f, 0.f);
+
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int b = unit / p.bands, band = unit - b * p.bands;
+        const int y0 = band * p.TH;
+        const int th = min(p.TH, p.H - y0);
+        const int npx = th * p.W;
+        __syncthreads();
+        stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
+        const IO *gob = reinterpret_cast<const IO *>(p.go) + (long long)b * p.n_out * HW;
+        for (int i = tid; i < npx; i += T)
+            patch_grad<IO, NP, false>(p, gob, (long long)b * HW + y0 * p.W + i, y0 * p.W + i, HW, gt + i * GS);
+        __syncthreads();
+        {   // bias row: column sums of G
+            const int n = tid % NP, sub = tid / NP, nsub = T / NP;
+            if (sub < nsub) {
+                float s = 0.f;
+                for (int i = sub; i < npx; i += nsub) s += gt[i * GS + n];
+                atomicAdd(dacc + p.F * NP + n, s);
+            }
+        }
+        if (part < p.parts) {
+            for (int y = part; y < th; y += p.parts) {
+                const float *fr = tile + ch * p.CS + (y + ky) * p.TC;
+                const float *g = gt + (y * p.W) * GS + nchunk * NC;
+                float f0 = fr[0], f1 = KS > 1 ? fr[1] : 0.f;
+#pragma unroll 2
+                for (int x = 0; x < p.W; ++x) {
+                    const float fn = fr[x + KS - 1];
+                    float4 G[NQ];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) G[j] = *reinterpret_cast<const float4 *>(g + 4 * j);
+                    g += GS;
+                    if constexpr (KS == 3) {
+                        const float2 a = f2(f0, f0), bb = f2(f1, f1), c = f2(fn, fn);
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) {
+                            const float2 lo = f2(G[j].x, G[j].y), hi = f2(G[j].z, G[j].w);
+                            acc[0][2 * j] = __ffma2_rn(lo, a, acc[0][2 * j]);
+                            acc[0][2 * j + 1] = __ffma2_rn(hi, a, acc[0][2 * j + 1]);
+                            acc[1][2 * j] = __ffma2_rn(lo, bb, acc[1][2 * j]);
+                            acc[1][2 * j + 1] = __ffma2_rn(hi, bb, acc[1][2 * j + 1]);
+                            acc[2][2 * j] = __ffma2_rn(lo, c, acc[2][2 * j]);
+                            acc[2][2 * j + 1] = __ffma2_rn(hi, c, acc[2][2 * j + 1]);
+                        }
+                        f0 = f1;
+                        f1 = fn;
+                    } else {
+                        const float2 c = f2(fn, fn);
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) {
+                            acc[0][2 * j] = __ffma2_rn(f2(G[j].x, G[j].y), c, acc[0][2 * j]);
+                            acc[0][2 * j + 1] = __ffma2_rn(f2(G[j].z, G[j].w), c, acc[0][2 * j + 1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (part < p.parts && rowok) {
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+            float *d = dacc + ((ch * KK + ky * KS + kx) * NP + nchunk * NC);
+#pragma unroll
+            for (int j = 0; j < NC / 2; ++j) {
+                atomicAdd(d + 2 * j, acc[kx][j].x);
+                atomicAdd(d + 2 * j + 1, acc[kx][j].y);
+            }
+        }
+    }
+    __syncthreads();
+    float *dst = p.partials + (long long)blockIdx.x * (p.F + 1) * NP;
+    for (int i = tid; i < (p.F + 1) * NP; i += T) dst[i] = dacc[i];
+}
+
+// dWd[(F + 1) NP] = sum of the per-CTA partials, fixed order, double precision: 32 outputs x 8 slices of the partials per CTA
+__global__ void __launch_bounds__(256) conv_reduce_kernel(const float *partials, int n_part, int total, double *sum) {
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (o < total) {
+        const float *src = partials + o;
+        int j = slice;
+        for (; j + 24 < n_part; j += 32) {
+            const float v0 = __ldg(src + (long long)j * total), v1 = __ldg(src + (long long)(j + 8) * total);
+            const float v2 = __ldg(src + (long long)(j + 16) * total), v3 = __ldg(src + (long long)(j + 24) * total);
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; j < n_part; j += 8) s0 += __ldg(src + (long long)j * total);
+    }
+    red[slice][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (slice == 0 && o < total) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][lane];
+        sum[o] = s;
+    }
+}
+
+// READ_STATE cotangent of U^T: gUT[c][m stride].{re,im} = c < F ? dWd[c][n] : pad * dbias[n], n = 2m + ri
+__global__ void __launch_bounds__(256) conv_assemble_kernel(const double *sum, int A, int F, int N, int NP, int stride, float pad,
+                                                            float *gUT) {
+    const long long total = (long long)A * A * 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ri = (int)(i & 1);
+        const long long ck = i >> 1;
+        const int c = (int)(ck / A), kk = (int)(ck % A);
+        float v = 0.f;
+        if (kk % stride == 0) {
+            const int n = 2 * (kk / stride) + ri;
+            if (n < N) v = (float)(c < F ? sum[c * NP + n] : (double)pad * sum[F * NP + n]);
+        }
+        gUT[i] = v;
+    }
+}
+
+// Wd[c][n] = part_n(U^T[c][m stride]) (c < F), row F = pad * sum over the pad rows c >= F; columns n >= N are zero
+__global__ void build_wd_kernel(const float2 *UT, int A, int F, int N, int NP, int stride, float pad, float *Wd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (F + 1) * NP) return;
+    const int c = i / NP, n = i - c * NP;
+    float v = 0.f;
+    if (n < N) {
+        const int k = (n >> 1) * stride;
+        if (c < F) {
+            const float2 u = UT[(long long)c * A + k];
+            v = (n & 1) ? u.y : u.x;
+        } else {
+            double s = 0.0;
+            for (int r = F; r < A; ++r) {
+                const float2 u = UT[(long long)r * A + k];
+                s += (n & 1) ? u.y : u.x;
+            }
+            v = (float)((double)pad * s);
+        }
+    }
+    Wd[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------ host side
+struct ConvTiling {
+    int TH, T, TC, CS, bands, wr, parts, Tw, ct;
+    size_t smem_fwd, smem_data, smem_w;
+};
+
+constexpr size_t CONV_SMEM_MAX = 200 * 1024;
+
+bool conv_tiling(const GemmShape &g, const GateParams &gp, int NP, ConvTiling *t) {
+    const int KS = gp.kh, GS = NP + 4, NC = NP < 16 ? NP : 16;
+    const int wr = (gp.C * KS + 31) / 32, ig = wr * (NP / NC);
+    if (ig > 8) return false;
+    const int ct = gp.C > 8 ? 16 : 8;
+    const int c_pad = (gp.C + ct - 1) / ct * ct;
+    double best = 0.0;
+    bool found = false;
+    for (int th = 1; th <= gp.H; ++th) {
+        const int pu = th * gp.W;
+        if (pu > 512) break;
+        int T = ((pu + 63) / 64) * 32;
+        if (T < 64) T = 64;
+        const int bands = (gp.H + th - 1) / th;
+        const int tc = (gp.W + KS - 1) | 1;
+        const int trtc = (th + KS - 1) * tc;
+        const int cs = trtc + ((3 - trtc % 32) + 32) % 32;
+        const size_t wdf = (size_t)(((g.F + 1) * NP + 3) & ~3);
+        const size_t s_fwd = 4 * (wdf + (size_t)gp.C * cs);
+        const size_t s_data = 4 * ((size_t)c_pad * KS * KS * NP + (size_t)(th + KS - 1) * (gp.W + KS - 1) * GS);
+        const size_t s_w = 4 * (wdf + (((size_t)gp.C * cs + 3) & ~(size_t)3) + (size_t)pu * GS);
+        if (s_fwd > CONV_SMEM_MAX || s_data > CONV_SMEM_MAX || s_w > CONV_SMEM_MAX) continue;
+        const double eff = (double)gp.H * gp.W / ((double)bands * 2 * T) * (1.0 - 0.02 * (KS - 1) / th);
+        if (eff > best + 1e-9) {
+            best = eff;
+            found = true;
+            t->TH = th; t->T = T; t->TC = tc; t->CS = cs; t->bands = bands;
+            t->smem_fwd = s_fwd; t->smem_data = s_data; t->smem_w = s_w;
+        }
+    }
+    if (!found) return false;
+    t->wr = wr;
+    t->parts = 8 / ig;
+    t->Tw = 32 * ig * t->parts;
+    t->ct = ct;
+    return true;
+}
+
+template <typename K>
+int conv_grid(K kern, int T, size_t smem, int units, int cap_ctas) {
+    // attribute / occupancy queries remembered per kernel, device and launch shape (they cost ~10 us of host time)
+    struct Entry { const void *k; int dev, T; size_t smem; int per_sm, sms; };
+    thread_local Entry cache[64];
+    thread_local int n_cache = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void *kp = reinterpret_cast<const void *>(kern);
+    int per_sm = 0, sms = 0;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].k == kp && cache[i].dev == dev && cache[i].T == T && cache[i].smem == smem) { per_sm = cache[i].per_sm; sms = cache[i].sms; }
+    if (per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_MAX) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem) != cudaSuccess || per_sm < 1) return -1;
+        if (n_cache < 64) cache[n_cache++] = Entry{kp, dev, T, smem, per_sm, sms};
+    }
+    long long cap = (long long)per_sm * sms;
+    if (cap_ctas > 0 && cap > cap_ctas) cap = cap_ctas;
+    return (int)(units < cap ? units : cap);
+}
+
+ConvParams conv_params(const GemmShape &g, const GateParams &gp, const ConvTiling &t, long long n_images) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_images = (int)n_images; p.C = gp.C; p.H = gp.H; p.W = gp.W; p.F = g.F; p.N = g.N; p.n_out = g.n_out;
+    p.bands = t.bands; p.TH = t.TH; p.TC = t.TC; p.CS = t.CS; p.units = (int)(n_images * t.bands);
+    p.clamp = gp.clamp; p.clamp_lo = gp.clamp_lo; p.clamp_hi = gp.clamp_hi; p.post_scale = gp.post_scale;
+    p.add_offset = gp.add_offset;
+    p.pad2 = (float)(g.A - g.F) * gp.pad_value * gp.pad_value;
+    p.wr = t.wr; p.parts = t.parts;
+    p.Bp = (n_images * gp.H * gp.W + 3) & ~3LL;
+    return p;
+}
+
+#define CONV_DISPATCH_NP(CALL)                   \
+    do {                                         \
+        if (NP == 4) { CALL(4); }                \
+        else if (NP == 16) { CALL(16); }         \
+        else { CALL(32); }                       \
+    } while (0)
+
+template <typename IO, int KS>
+int conv_forward_t(const ConvParams &p, const ConvTiling &t, int NP, cudaStream_t s) {
+#define CALL(NP_)                                                                                   \
+    {                                                                                               \
+        auto k = conv_fwd_kernel<IO, KS, NP_>;                                                      \
+        const int grid = conv_grid(k, t.T, t.smem_fwd, p.units, 0);                                 \
+        if (grid < 1) return QIDDM_EUNSUPPORTED;                                                    \
+        k<<<grid, t.T, t.smem_fwd, s>>>(p);                                                         \
+    }
+    CONV_DISPATCH_NP(CALL);
+#undef CALL
+    return QIDDM_OK;
+}
+
+template <typename IO, int KS>
+int conv_bwd_data_t(const ConvParams &p, const ConvTiling &t, int NP, cudaStream_t s) {
+#define CALL(NP_)                                                                                   \
+    {                                                                                               \
+        if (t.ct == 8) {                                                                            \
+            auto k = conv_bwd_data_kernel<IO, KS, NP_, 8>;                                          \
+            const int grid = conv_grid(k, t.T, t.smem_data, p.units, 0);                            \
+            if (grid < 1) return QIDDM_EUNSUPPORTED;                                                \
+            k<<<grid, t.T, t.smem_data, s>>>(p);                                                    \
+        } else {                                                                                    \
+            auto k = conv_bwd_data_kernel<IO, KS, NP_, 16>;                                         \
+            const int grid = conv_grid(k, t.T, t.smem_data, p.units, 0);                            \
+            if (grid < 1) return QIDDM_EUNSUPPORTED;                                                \
+            k<<<grid, t.T, t.smem_data, s>>>(p);                                                    \
+        }                                                                                           \
+    }
+    CONV_DISPATCH_NP(CALL);
+#undef CALL
+    return QIDDM_OK;
+}
+
+template <typename IO, int KS>
+int conv_bwd_w_t(ConvParams &p, const ConvTiling &t, int NP, int *grid_out, cudaStream_t s) {
+#define CALL(NP_)                                                                                   \
+    {                                                                                               \
+        auto k = conv_bwd_w_kernel<IO, KS, NP_>;                                                    \
+        const int grid = conv_grid(k, t.Tw, t.smem_w, p.units, CONV_MAX_WGRID);                     \
+        if (grid < 1) return QIDDM_EUNSUPPORTED;                                                    \
+        *grid_out = grid;                                                                           \
+        k<<<grid, t.Tw, t.smem_w, s>>>(p);                                                          \
+    }
+    CONV_DISPATCH_NP(CALL);
+#undef CALL
+    return QIDDM_OK;
+}
+
+struct ConvSaved {
+    float *Y, *inv_n2;
+};
+ConvSaved conv_saved_view(const GemmShape &g, long long Bp, void *buf) {
+    ConvSaved v;
+    v.Y = reinterpret_cast<float *>(buf);
+    v.inv_n2 = v.Y + (size_t)g.N * Bp;
+    return v;
+}
+
+}  // namespace
+
+int conv_np(int N) { return N <= 4 ? 4 : (N <= 16 ? 16 : (N <= 32 ? 32 : 0)); }
+
+size_t conv_wd_bytes(const GemmShape &g) {
+    const int NP = conv_np(g.N);
+    return NP ? (((size_t)(g.F + 1) * NP * 4 + 255) & ~(size_t)255) : 0;
+}
+
+int conv_build_wd(const GemmShape &g, const GateParams &gp, const float *UT, float *Wd, cudaStream_t s) {
+    const int NP = conv_np(g.N);
+    if (!NP) return QIDDM_OK;
+    const int total = (g.F + 1) * NP;
+    build_wd_kernel<<<(total + 127) / 128, 128, 0, s>>>(reinterpret_cast<const float2 *>(UT), g.A, g.F, g.N, NP, g.stride,
+                                                        gp.pad_value, Wd);
+    count_launch();
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+bool conv_direct_supported(const GemmShape &g, const GateParams &gp) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("QIDDM_QCONV_DIRECT"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (!on || !gp.unfold) return false;
+    if (gp.kh != gp.kw || (gp.kh != 1 && gp.kh != 3)) return false;
+    if (gp.ph != gp.kh / 2 || gp.pw != gp.kw / 2) return false;       // "same" geometry: one patch per pixel
+    if (g.F != gp.C * gp.kh * gp.kw) return false;
+    const int NP = conv_np(g.N);
+    if (!NP) return false;
+    ConvTiling t;
+    return conv_tiling(g, gp, NP, &t);
+}
+
+size_t conv_direct_saved_bytes(const GemmShape &g, const GateParams &gp, long long n_images) {
+    const long long Bp = (n_images * gp.H * gp.W + 3) & ~3LL;
+    return (size_t)(g.N + 1) * Bp * 4 + 256;
+}
+
+size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp) {
+    const int NP = conv_np(g.N);
+    return (((size_t)CONV_MAX_WGRID * (g.F + 1) * NP * 4 + 255) & ~(size_t)255) + (((size_t)g.A * g.A * 8 + 255) & ~(size_t)255) +
+           (((size_t)(g.F + 1) * NP * 8 + 255) & ~(size_t)255);
+}
+
+// out (NCHW, io dtype); `saved` non-null (training): Y and 1/|f|^2 are kept for conv_direct_backward
+int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, void *out, void *saved,
+                        long long n_images, cudaStream_t s) {
+    const int NP = conv_np(g.N);
+    ConvTiling t;
+    if (!NP || !conv_tiling(g, gp, NP, &t)) return QIDDM_EUNSUPPORTED;
+    ConvParams p = conv_params(g, gp, t, n_images);
+    p.img = img; p.out = out; p.Wd = Wd;
+    if (saved != nullptr) {
+        const ConvSaved v = conv_saved_view(g, p.Bp, saved);
+        p.Y = v.Y; p.inv_n2 = v.inv_n2;
+    }
+    timing_begin(TK_CONV_FWD, 2.0 * (double)n_images * gp.H * gp.W * g.F * g.N, s);
+    int rc;
+    if (gp.io64) rc = gp.kh == 3 ? conv_forward_t<double, 3>(p, t, NP, s) : conv_forward_t<double, 1>(p, t, NP, s);
+    else rc = gp.kh == 3 ? conv_forward_t<float, 3>(p, t, NP, s) : conv_forward_t<float, 1>(p, t, NP, s);
+    timing_end(s);
+    count_launch();
+    if (rc != QIDDM_OK) return rc;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+// grad_img (nullable, overwritten) and the READ_STATE cotangent gUT (inside `ws`) for the adjoint gate kernel
+int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, const void *grad_out,
+                         const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s) {
+    const int NP = conv_np(g.N);
+    ConvTiling t;
+    if (!NP || !conv_tiling(g, gp, NP, &t) || saved == nullptr) return QIDDM_EUNSUPPORTED;
+    ConvParams p = conv_params(g, gp, t, n_images);
+    const ConvSaved v = conv_saved_view(g, p.Bp, const_cast<void *>(saved));
+    p.img = img; p.go = grad_out; p.gimg = grad_img; p.Wd = Wd; p.Y = v.Y; p.inv_n2 = v.inv_n2;
+    p.partials = reinterpret_cast<float *>(ws);
+    float *gUT = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) +
+                                           (((size_t)CONV_MAX_WGRID * (g.F + 1) * NP * 4 + 255) & ~(size_t)255));
+    *gut_out = gUT;
+    int rc = QIDDM_OK;
+    timing_begin(TK_CONV_BWD, (grad_img ? 4.0 : 2.0) * (double)n_images * gp.H * gp.W * g.F * g.N, s);
+    if (grad_img != nullptr) {
+        if (gp.io64) rc = gp.kh == 3 ? conv_bwd_data_t<double, 3>(p, t, NP, s) : conv_bwd_data_t<double, 1>(p, t, NP, s);
+        else rc = gp.kh == 3 ? conv_bwd_data_t<float, 3>(p, t, NP, s) : conv_bwd_data_t<float, 1>(p, t, NP, s);
+        count_launch();
+    }
+    int wgrid = 0;
+    if (rc == QIDDM_OK) {
+        if (gp.io64) rc = gp.kh == 3 ? conv_bwd_w_t<double, 3>(p, t, NP, &wgrid, s) : conv_bwd_w_t<double, 1>(p, t, NP, &wgrid, s);
+        else rc = gp.kh == 3 ? conv_bwd_w_t<float, 3>(p, t, NP, &wgrid, s) : conv_bwd_w_t<float, 1>(p, t, NP, &wgrid, s);
+        count_launch();
+    }
+    timing_end(s);
+    if (rc != QIDDM_OK) return rc;
+    const int total = (g.F + 1) * NP;
+    double *sum = reinterpret_cast<double *>(reinterpret_cast<char *>(gUT) + (((size_t)g.A * g.A * 8 + 255) & ~(size_t)255));
+    conv_reduce_kernel<<<(total + 31) / 32, 256, 0, s>>>(p.partials, wgrid, total, sum);
+    const long long elems = (long long)g.A * g.A * 2;
+    conv_assemble_kernel<<<(unsigned)((elems + 255) / 256 < 592 ? (elems + 255) / 256 : 592), 256, 0, s>>>(
+        sum, g.A, g.F, g.N, NP, g.stride, gp.pad_value, gUT);
+    count_launch(2);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
+}  // namespace qiddm

@@ -2201,6 +2201,7 @@ size_t gemm_collapsed_bytes(const GemmShape &g) {
     b += 2 * al((size_t)g.N * g.Kp * 2);             // Wn hi/lo
     b += 2 * al((size_t)g.F * g.Np * 2);             // Wt hi/lo
     b += al((size_t)g.N * 4);                        // bias
+    b += conv_wd_bytes(g);                           // fp32 rows of U for the direct QConv path
     return b;
 }
 
@@ -2208,6 +2209,7 @@ struct CollapsedView {
     float2 *UT;
     __half *Wn[2], *Wt[2];
     float *bias;
+    float *Wd;
 };
 static CollapsedView collapsed_view(const GemmShape &g, void *buf) {
     CollapsedView v;
@@ -2215,7 +2217,8 @@ static CollapsedView collapsed_view(const GemmShape &g, void *buf) {
     v.UT = reinterpret_cast<float2 *>(p); p += al((size_t)g.A * g.A * 8);
     for (int i = 0; i < 2; ++i) { v.Wn[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.N * g.Kp * 2); }
     for (int i = 0; i < 2; ++i) { v.Wt[i] = reinterpret_cast<__half *>(p); p += al((size_t)g.F * g.Np * 2); }
-    v.bias = reinterpret_cast<float *>(p);
+    v.bias = reinterpret_cast<float *>(p); p += al((size_t)g.N * 4);
+    v.Wd = reinterpret_cast<float *>(p);
     return v;
 }
 
@@ -2232,9 +2235,11 @@ int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapse
     timing_end(s);
     count_launch();
     e = cudaGetLastError();
-    return e == cudaSuccess ? QIDDM_OK : (int)e;
+    if (e != cudaSuccess) return (int)e;
+    return conv_build_wd(g, gp, reinterpret_cast<const float *>(v.UT), v.Wd, s);
 }
 
+float *gemm_collapsed_wd(const GemmShape &g, void *collapsed) { return collapsed_view(g, collapsed).Wd; }
 float *gemm_collapsed_ut(const GemmShape &g, void *collapsed) { return reinterpret_cast<float *>(collapsed_view(g, collapsed).UT); }
 
 size_t gemm_saved_bytes(const GemmShape &g, long long B) {

@@ -57,7 +57,7 @@ void count_launch(int n = 1);
 // the launches of one kind; off by default.
 enum { TK_GATE_FWD = 0, TK_GATE_BWD = 1, TK_GEMM = 2, TK_OTHER = 3, TK_GEMM_FWD = 4, TK_GEMM_DX = 5, TK_GEMM_DW = 6,
        TK_PREP_X = 7, TK_TRANSPOSE_X = 8, TK_G_BOUND = 9, TK_GRAD_Y = 10, TK_FINISH_DX = 11, TK_ASSEMBLE = 12,
-       TK_BUILD_W = 13, TK_COUNT = 16 };
+       TK_BUILD_W = 13, TK_CONV_FWD = 14, TK_CONV_BWD = 15, TK_COUNT = 16 };
 void timing_begin(int kind, double work, cudaStream_t s);   // work = algorithmic flops (or bytes) of the launch
 void timing_end(cudaStream_t s);
 void timing_set_gemm_kind(int kind);
@@ -70,6 +70,7 @@ struct GemmShape {
 GemmShape gemm_shape(const GateParams &gp, int n_qubits);
 size_t gemm_collapsed_bytes(const GemmShape &g);
 float *gemm_collapsed_ut(const GemmShape &g, void *collapsed);
+float *gemm_collapsed_wd(const GemmShape &g, void *collapsed);      // fp32 rows of U for the direct QConv path (qiddm_conv.cu)
 int gemm_build_operands(const GemmShape &g, const GateParams &gp, void *collapsed, cudaStream_t s);
 size_t gemm_saved_bytes(const GemmShape &g, long long B);
 size_t gemm_forward_ws_bytes(const GemmShape &g, long long B);
@@ -84,6 +85,18 @@ size_t gemm_dense_mse_ws_bytes(const GemmShape &g, long long B);
 int gemm_dense_mse_step(const GemmShape &g, const GateParams &gp, const void *collapsed, const void *x, const float *eps,
                         const void *w, int io64, long long n_img, int T, float a, float bshift, float c0, float c1,
                         void *loss_out, float **gut_out, void *ws, int n_seg_fwd, int n_seg_bwd, cudaStream_t s);
+
+// qiddm_conv.cu — QConv2d on the collapse path as a direct fp32 convolution (N = 2 out_channels <= 32, 1x1 / 3x3 "same" windows)
+int conv_np(int N);
+size_t conv_wd_bytes(const GemmShape &g);
+int conv_build_wd(const GemmShape &g, const GateParams &gp, const float *UT, float *Wd, cudaStream_t s);
+bool conv_direct_supported(const GemmShape &g, const GateParams &gp);
+size_t conv_direct_saved_bytes(const GemmShape &g, const GateParams &gp, long long n_images);
+size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp);
+int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, void *out, void *saved,
+                        long long n_images, cudaStream_t s);
+int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, const void *grad_out,
+                         const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s);
 
 // qiddm_dm.cu — density-matrix pieces for the mid-circuit noise channels (tau = rho^T, (B, 2^n, 2^n) complex fp32)
 size_t dm_state_bytes(int n_qubits, long long B);

@@ -69,7 +69,7 @@ class _QConvFunction(torch.autograd.Function):
         ctx.plan, ctx.unfold = plan, unfold
         ho = img.shape[2] + 2 * unfold.pad_h - unfold.kernel_h + 1
         wo = img.shape[3] + 2 * unfold.pad_w - unfold.kernel_w + 1
-        ctx.gemm = plan.use_gemm(img.shape[0] * ho * wo)       # circuit instances = patches
+        ctx.gemm = plan.use_collapse_qconv(unfold, img.shape[0] * ho * wo)       # circuit instances = patches
         ctx.gemm_saved = None
         if ctx.gemm:
             if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:

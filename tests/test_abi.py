@@ -103,5 +103,14 @@ def test_host_side_argument_checks_of_the_new_entry_points(lib):
     bad = L.UnfoldDesc(4, 28, 28, 3, 3, 1, 1)           # 4*9 != 72 features
     assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(good), 10) > 0
     assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(bad), 10) == 0
-    assert lib.qiddm_qconv_gemm_workspace_bytes(plan.handle, C.byref(good), 10) > lib.qiddm_gemm_workspace_bytes(plan.handle, 7840) - 1
+    # this layer (3x3 "same" window, 8 output channels) has the direct fp32 convolution behind the same entry points ...
+    assert lib.qiddm_qconv_direct_supported(plan.handle, C.byref(good)) == 1
+    assert lib.qiddm_qconv_direct_supported(plan.handle, C.byref(bad)) == 0
+    assert lib.qiddm_qconv_gemm_workspace_bytes(plan.handle, C.byref(good), 10) > 0
+    # ... unless the tcgen05 GEMM is asked for explicitly; a valid geometry without "same" padding has no direct form either
+    import dataclasses
+    plan_g = L.Plan(dataclasses.replace(s, path=L.PATH_GEMM))
+    assert lib.qiddm_qconv_direct_supported(plan_g.handle, C.byref(good)) == 0
+    assert lib.qiddm_qconv_direct_supported(plan.handle, C.byref(L.UnfoldDesc(8, 28, 28, 3, 3, 0, 0))) == 0
+    assert lib.qiddm_qconv_gemm_workspace_bytes(plan_g.handle, C.byref(good), 10) > lib.qiddm_gemm_workspace_bytes(plan_g.handle, 7840) - 1
     assert lib.qiddm_qconv_gemm_forward(plan.handle, None, C.byref(good), 0, None, None, None, None, 1, 3, None) == -1

@@ -1,0 +1,115 @@
+"""QConv2d as a direct fp32 convolution on the collapse path (csrc/qiddm_conv.cu) against the oracle (unfold + circuit +
+re-layout, reference nn/qconv.py:51-56, :71-90 with the H1 line restored), against the gate-by-gate path and against the
+tcgen05 GEMM path, at every layer shape of UNetUndirected(3, 8, 3) and at ragged sizes."""
+import pytest
+import torch
+
+from conftest import rel_to_max
+from oracle import qiddm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-6             # plain fp32 FMAs, at most 289 terms per output
+GTOL = 1e-5
+
+
+def _module(cin, cout, k, depth=3, seed=3):
+    from qiddm_b200 import nn
+    torch.manual_seed(seed)
+    return nn.QConv2d(cin, cout, kernel_size=k, padding=k // 2, qdepth=depth).cuda()
+
+
+def _is_direct(m, x):
+    from qiddm_b200 import _lib as L
+    u = L.UnfoldDesc(x.shape[1], x.shape[2], x.shape[3], m.kernel_size[0], m.kernel_size[1], m.padding[0], m.padding[1])
+    plan = L.Plan.get(m._spec())
+    return plan.qconv_direct(u) and plan.use_collapse_qconv(u, x.shape[0] * x.shape[2] * x.shape[3])
+
+
+# (in, out, kernel, H, W, images): the UNet's layers at reduced batch, then ragged / narrow / multi-band shapes
+CASES = [(1, 8, 3, 28, 28, 3), (8, 8, 3, 28, 28, 2), (16, 8, 3, 28, 28, 2), (16, 8, 1, 28, 28, 2), (8, 1, 1, 28, 28, 2),
+         (8, 16, 3, 14, 14, 3), (16, 16, 3, 14, 14, 3), (32, 16, 3, 14, 14, 3), (32, 16, 1, 14, 14, 3),
+         (3, 5, 3, 9, 11, 4), (6, 3, 1, 5, 7, 5), (8, 8, 3, 40, 17, 2), (4, 2, 3, 1, 1, 70), (6, 12, 3, 3, 70, 2)]
+
+
+@pytest.mark.parametrize("cfg", CASES)
+def test_direct_conv_matches_oracle_forward_and_both_gradients(cfg):
+    cin, cout, k, H, W, n = cfg
+    m = _module(cin, cout, k)
+    x = torch.rand(n, cin, H, W, dtype=torch.float64)
+    assert _is_direct(m, x)
+    xr = x.clone().requires_grad_(True)
+    Wr = m.weights.detach().cpu().clone().requires_grad_(True)
+    ref = O.qconv_forward(xr, Wr, cout, m.kernel_size, m.padding)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    out = m(xd)
+    assert out.shape == ref.shape and out.dtype == torch.float64
+    assert rel_to_max(out, ref) <= TOL
+    (out * g.cuda()).sum().backward()
+    assert rel_to_max(m.weights.grad, Wr.grad) <= GTOL
+    assert rel_to_max(xd.grad, xr.grad) <= GTOL
+    # inference forward (nothing saved) and float32 tensors give the same numbers
+    with torch.no_grad():
+        assert rel_to_max(m(x.cuda()), out) <= 1e-7
+        o32 = m(x.cuda().float())
+        assert o32.dtype == torch.float32 and rel_to_max(o32.double(), ref) <= TOL
+
+
+def test_direct_conv_float32_gradients_and_no_image_gradient():
+    m = _module(8, 8, 3)
+    x = torch.rand(3, 8, 12, 13, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    Wr = m.weights.detach().cpu().clone().requires_grad_(True)
+    ref = O.qconv_forward(xr, Wr, 8, m.kernel_size, m.padding)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    xd = x.cuda().float().requires_grad_(True)
+    out = m(xd)
+    (out * g.cuda().float()).sum().backward()
+    assert xd.grad.dtype == torch.float32
+    assert rel_to_max(m.weights.grad, Wr.grad) <= GTOL and rel_to_max(xd.grad.double(), xr.grad) <= GTOL
+    # first UNet layer: the image needs no gradient -> only the weight-gradient kernel runs
+    m.weights.grad = None
+    out = m(x.cuda())
+    (out * g.cuda()).sum().backward()
+    assert rel_to_max(m.weights.grad, Wr.grad) <= GTOL
+
+
+def test_direct_conv_agrees_with_gate_and_gemm_paths_and_respects_the_clamp():
+    """Same module, three paths; the input is scaled so that a good share of the outputs sits on the clamp (gradient 0 there)."""
+    from qiddm_b200 import _lib as L
+    m = _module(8, 8, 3, seed=9)
+    x = torch.rand(4, 8, 14, 14, dtype=torch.float64, device="cuda")
+    x[:, :, :, :7] *= 0.02                       # nearly uniform patches -> concentrated amplitudes -> clamped outputs
+    g = torch.randn(4, 8, 14, 14, dtype=torch.float64, device="cuda")
+    res = {}
+    for name, path in (("direct", L.PATH_AUTO), ("gate", L.PATH_GATE), ("gemm", L.PATH_GEMM)):
+        m.path = path
+        m.weights.grad = None
+        xd = x.clone().requires_grad_(True)
+        out = m(xd)
+        (out * g).sum().backward()
+        res[name] = (out.detach(), m.weights.grad.clone(), xd.grad.clone())
+    m.path = L.PATH_AUTO
+    assert _is_direct(m, x)
+    clamped = ((res["gate"][0] <= 0) | (res["gate"][0] >= 1)).double().mean().item()
+    assert clamped > 0.01
+    for other, tol in (("gate", 1e-5), ("gemm", 3e-5)):
+        for i in range(3):
+            assert rel_to_max(res["direct"][i], res[other][i]) <= tol, (other, i)
+
+
+def test_direct_conv_large_batch_is_deterministic():
+    """640 images x 28 x 28 (the UNet step's first level): per-CTA partials summed in a fixed order -> bitwise repeatable."""
+    m = _module(8, 8, 3)
+    x = torch.rand(640, 8, 28, 28, dtype=torch.float64, device="cuda")
+    g = torch.randn(640, 8, 28, 28, dtype=torch.float64, device="cuda")
+    grads = []
+    for _ in range(2):
+        m.weights.grad = None
+        xd = x.clone().requires_grad_(True)
+        (m(xd) * g).sum().backward()
+        grads.append((m.weights.grad.clone(), xd.grad.clone()))
+    assert torch.equal(grads[0][1], grads[1][1])
+    assert rel_to_max(grads[0][0], grads[1][0]) <= 1e-6      # shared-memory float atomics inside a CTA reorder the last bits
