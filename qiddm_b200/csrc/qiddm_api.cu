@@ -520,7 +520,7 @@ size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfo
     const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
     if (qconv_direct(plan, unfold)) {
         GateParams gu = make_params(plan, unfold, 1);
-        return align_up(conv_direct_ws_bytes(g, gu)) + basis_ws_bytes(plan) + 256;
+        return align_up(conv_direct_ws_bytes(g, gu, n_images > 0 ? n_images : 1)) + basis_ws_bytes(plan) + 256;
     }
     return gemm_backward_ws_bytes(g, B, true) + basis_ws_bytes(plan) + 256;
 }
@@ -584,7 +584,7 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
     if (!grad_weights) return QIDDM_OK;
     qiddm_plan t = basis_plan(plan);
     char *gate_ws = reinterpret_cast<char *>(workspace) +
-                    (direct ? align_up(conv_direct_ws_bytes(g, gp)) : align_up(gemm_backward_ws_bytes(g, B, true)));
+                    (direct ? align_up(conv_direct_ws_bytes(g, gp, n_images)) : align_up(gemm_backward_ws_bytes(g, B, true)));
     return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
                          t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
 }

@@ -10,10 +10,15 @@
 // matrix (320 B per patch and pass at F = 72 against 64 B of image), the gate path simulates every patch gate by gate.
 // Here a CTA stages a band of image rows (with halo) in shared memory once and every thread keeps the N accumulators of
 // two patches in registers; the FP32 FMA pipe is the bound (F N FMAs per patch and pass), the image is read once.
+// Every kernel is persistent over (image, band) units; shared-memory footprints are kept small enough for three or more
+// CTAs per SM, whose staging and compute phases overlap (measured: an explicit cp.async pipeline with raw staging buffers
+// lost more to the lower occupancy than it gained, profiles/r2c_conv_summary.md).
 //
-//   conv_fwd_kernel       out (NCHW, io dtype), optionally Y (N, Bp) + 1/|f|^2 for the backward
-//   conv_bwd_data_kernel  G = dL/dY from (Y, grad_out) into a haloed tile; gather form of the transposed convolution with
-//                         the normalisation term of the amplitude embedding:  d img = sum_taps (G . Wd) - 2 f sum_taps S / |f|^2
+//   conv_fwd_kernel       out (NCHW, io dtype), optionally one row [Y (NP), 1/|f|^2] per patch for the backward
+//   conv_grad_kernel      G = dL/dY per patch from (Y, grad_out, clamp mask) + the normalisation term S / |f|^2: one streaming
+//                         pass, rows of NP + 4 floats that both gradient kernels copy into their tiles with 16-byte cp.async
+//   conv_bwd_data_kernel  gather form of the transposed convolution over a haloed G tile:
+//                         d img = sum_taps (G . Wd) - 2 f sum_taps S / |f|^2
 //   conv_bwd_w_kernel     dWd[c][n] = sum_patches f[c] G[n]: a lane owns one (channel, ky) row of the kernel window (kw taps,
 //                         sliding along x) x 16 outputs in registers for the whole launch; per-CTA partials
 //   conv_reduce_kernel / conv_assemble_kernel  fixed-order fp64 sum of the partials -> READ_STATE cotangent of U^T for the
@@ -35,16 +40,22 @@ struct ConvParams {
     const void *go;
     void *gimg;
     const float *Wd;           // [(F + 1)][NP], row F = bias
-    float *Y;                  // [N][Bp]
-    float *inv_n2;             // [Bp]
+    float *Y;                  // [Bp][NP + 4]: Y (columns >= N zero), 1/|f|^2 at column NP
+    float *G;                  // [Bp][NP + 4]: dL/dY, S / |f|^2 at column NP
     float *partials;           // [grid][(F + 1) NP]
-    long long Bp;
+    long long B;               // patches
     int n_images, C, H, W, F, N, n_out, bands, TH, TC, CS, units, clamp;
     int wr, parts;             // conv_bwd_w_kernel: warps per n-chunk (rows / 32), pixel-row parts
     float add_offset, pad2, post_scale, clamp_lo, clamp_hi;
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // band of image rows [y0 - PH, y0 + th + PH) x columns [-PH, W + PH) of all channels, + add_offset (the zero padding of
 // torch.nn.Unfold becomes add_offset: the reference adds 0.1 to the unfolded patch)
@@ -77,40 +88,11 @@ __device__ __forceinline__ void stage_image(const ConvParams &p, const IO *ib, i
     }
 }
 
-// dL/dY of one patch from the saved Y and the upstream gradient; g[0..NP) and (WITH_S) g[NP] = S / |f|^2 with
-// S = sum_m go_m out_m (unclamped, passing outputs): the normalisation term of d out / d f.  All loads are issued first.
-template <typename IO, int NP, bool WITH_S>
-__device__ __forceinline__ void patch_grad(const ConvParams &p, const IO *gob, long long gp, int pix, int HW, float *g) {
-    constexpr int M = NP / 2;
-    float a[M], b[M], go[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        a[m] = b[m] = go[m] = 0.f;
-        if (m < p.n_out) {
-            a[m] = __ldg(p.Y + (long long)(2 * m) * p.Bp + gp);
-            b[m] = __ldg(p.Y + (long long)(2 * m + 1) * p.Bp + gp);
-            go[m] = (float)__ldg(gob + (long long)m * HW + pix);
-        }
-    }
-    const float inv = __ldg(p.inv_n2 + gp);
-    float S = 0.f;
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const float pr = a[m] * a[m] + b[m] * b[m];
-        const float v = p.post_scale * inv * pr;
-        const bool pass = !p.clamp || (v >= p.clamp_lo && v <= p.clamp_hi);
-        const float cm = pass ? p.post_scale * go[m] : 0.f;
-        *reinterpret_cast<float2 *>(g + 2 * m) = f2(2.f * cm * inv * a[m], 2.f * cm * inv * b[m]);
-        S += cm * inv * pr;
-    }
-    if (WITH_S) g[NP] = inv * S;
-}
-
 // ------------------------------------------------------------------------------------------------------------ forward
 template <typename IO, int KS, int NP>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(256, NP >= 32 ? 2 : 3) conv_fwd_kernel(const ConvParams p) {
     extern __shared__ float4 conv_smem[];
-    constexpr int KK = KS * KS;
+    constexpr int KK = KS * KS, YS = NP + 4;
     float *wd = reinterpret_cast<float *>(conv_smem);
     float *tile = wd + (((p.F + 1) * NP + 3) & ~3);
     const int T = blockDim.x, tid = threadIdx.x;
@@ -169,14 +151,10 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvParams p) {
             const float s = ss[k] + p.pad2;
             const float inv = s > 0.f ? 1.0f / s : 0.f;
             if (p.Y != nullptr) {
-                p.inv_n2[gp] = inv;
+                float4 *yr = reinterpret_cast<float4 *>(p.Y + gp * YS);
 #pragma unroll
-                for (int j = 0; j < NP / 2; ++j) {
-                    if (2 * j < p.N) {
-                        p.Y[(long long)(2 * j) * p.Bp + gp] = acc[k][j].x;
-                        p.Y[(long long)(2 * j + 1) * p.Bp + gp] = acc[k][j].y;
-                    }
-                }
+                for (int j = 0; j < NP / 4; ++j) yr[j] = make_float4(acc[k][2 * j].x, acc[k][2 * j].y, acc[k][2 * j + 1].x, acc[k][2 * j + 1].y);
+                yr[NP / 4] = make_float4(inv, 0.f, 0.f, 0.f);
             }
             IO *ob = reinterpret_cast<IO *>(p.out) + (long long)b * p.n_out * HW + pix;
 #pragma unroll
@@ -191,9 +169,50 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ dL/dY per patch
+// G[n] = 2 c_m Y[n] / |f|^2 with c_m = post * grad_out_m on the outputs the clamp passes, and S / |f|^2 with
+// S = sum_m c_m |Y_m|^2 / |f|^2 (the normalisation term of d out / d f) at column NP.
+template <typename IO, int NP>
+__global__ void __launch_bounds__(256) conv_grad_kernel(const ConvParams p) {
+    constexpr int YS = NP + 4, M = NP / 2;
+    const int HW = p.H * p.W;
+    for (long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x; gp < p.B; gp += (long long)gridDim.x * blockDim.x) {
+        const long long b = gp / HW;
+        const int pix = (int)(gp - b * HW);
+        const IO *gob = reinterpret_cast<const IO *>(p.go) + b * p.n_out * HW + pix;
+        const float4 *yr = reinterpret_cast<const float4 *>(p.Y + gp * YS);
+        float4 y4[NP / 4];
+#pragma unroll
+        for (int j = 0; j < NP / 4; ++j) y4[j] = __ldg(yr + j);
+        const float inv = __ldg(reinterpret_cast<const float *>(yr + NP / 4));
+        float go[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) go[m] = m < p.n_out ? (float)__ldg(gob + (long long)m * HW) : 0.f;
+        float4 *gr = reinterpret_cast<float4 *>(p.G + gp * YS);
+        float S = 0.f;
+#pragma unroll
+        for (int j = 0; j < NP / 4; ++j) {
+            float o[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float a = h ? y4[j].z : y4[j].x, bb = h ? y4[j].w : y4[j].y;
+                const float pr = a * a + bb * bb;
+                const float v = p.post_scale * inv * pr;
+                const bool pass = !p.clamp || (v >= p.clamp_lo && v <= p.clamp_hi);
+                const float cm = pass ? p.post_scale * go[2 * j + h] : 0.f;
+                o[2 * h] = 2.f * cm * inv * a;
+                o[2 * h + 1] = 2.f * cm * inv * bb;
+                S += cm * inv * pr;
+            }
+            gr[j] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        gr[NP / 4] = make_float4(inv * S, 0.f, 0.f, 0.f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- image gradient (gather)
 template <typename IO, int KS, int NP, int CT>
-__global__ void __launch_bounds__(256) conv_bwd_data_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(256, 2) conv_bwd_data_kernel(const ConvParams p) {
     extern __shared__ float4 conv_smem[];
     constexpr int KK = KS * KS, PH = KS / 2, GS = NP + 4, NC = NP < 16 ? NP : 16, NQ = NC / 4;
     const int c_pad = (p.C + CT - 1) / CT * CT;
@@ -207,18 +226,20 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const ConvParams p) 
         const int y0 = band * p.TH;
         const int th = min(p.TH, p.H - y0);
         __syncthreads();
-        const IO *gob = reinterpret_cast<const IO *>(p.go) + (long long)b * p.n_out * HW;
         for (int i = tid; i < (th + KS - 1) * tcg; i += T) {
             const int r = i / tcg, c = i - r * tcg;
             const int py = y0 - PH + r, px = c - PH;
-            float *g = gt + i * GS;
+            float4 *g = reinterpret_cast<float4 *>(gt + i * GS);
             if (py >= 0 && py < p.H && px >= 0 && px < p.W) {
-                patch_grad<IO, NP, true>(p, gob, (long long)b * HW + py * p.W + px, py * p.W + px, HW, g);
+                const float4 *src = reinterpret_cast<const float4 *>(p.G + ((long long)b * HW + py * p.W + px) * GS);
+#pragma unroll
+                for (int j = 0; j < GS / 4; ++j) cp_async16(g + j, src + j);
             } else {
 #pragma unroll
-                for (int n = 0; n <= NP; ++n) g[n] = 0.f;
+                for (int j = 0; j < GS / 4; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        cp_async_wait_all();
         __syncthreads();
         const int npx = th * p.W;
         int q[2], gbase[2];
@@ -269,6 +290,18 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const ConvParams p) 
                     }
                 }
             }
+            // the image values of the normalisation term: every load issued before the first store (the compiler keeps the
+            // order of a load behind a store to another global pointer: one DRAM latency per channel otherwise)
+            float fv[2][CT];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int pix = y0 * p.W + (ok[k] ? q[k] : 0);
+#pragma unroll
+                for (int ch = 0; ch < CT; ++ch) {
+                    const int c = ct + ch < p.C ? ct + ch : p.C - 1;
+                    fv[k][ch] = (float)__ldg(reinterpret_cast<const IO *>(p.img) + ((long long)b * p.C + c) * HW + pix);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (!ok[k]) continue;
@@ -278,8 +311,8 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const ConvParams p) 
                     const int c = ct + ch;
                     if (c < p.C) {
                         const long long idx = ((long long)b * p.C + c) * HW + pix;
-                        const float f = (float)__ldg(reinterpret_cast<const IO *>(p.img) + idx) + p.add_offset;
-                        reinterpret_cast<IO *>(p.gimg)[idx] = (IO)((acc[k][ch].x + acc[k][ch].y) - 2.f * f * nsum[k]);
+                        reinterpret_cast<IO *>(p.gimg)[idx] =
+                            (IO)((acc[k][ch].x + acc[k][ch].y) - 2.f * (fv[k][ch] + p.add_offset) * nsum[k]);
                     }
                 }
             }
@@ -289,7 +322,7 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const ConvParams p) 
 
 // ------------------------------------------------------------------------------------------------- weight gradient
 template <typename IO, int KS, int NP>
-__global__ void __launch_bounds__(256) conv_bwd_w_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) {
     extern __shared__ float4 conv_smem[];
     constexpr int KK = KS * KS, GS = NP + 4, NC = NP < 16 ? NP : 16, NQ = NC / 4;
     float *dacc = reinterpret_cast<float *>(conv_smem);             // [(F + 1)][NP] sums of this CTA
@@ -316,10 +349,13 @@ __global__ void __launch_bounds__(256) conv_bwd_w_kernel(const ConvParams p) {
         const int th = min(p.TH, p.H - y0);
         const int npx = th * p.W;
         __syncthreads();
+        {   // the band's rows of G are one contiguous run
+            const float4 *src = reinterpret_cast<const float4 *>(p.G + ((long long)b * HW + y0 * p.W) * GS);
+            float4 *dst = reinterpret_cast<float4 *>(gt);
+            for (int i = tid; i < npx * (GS / 4); i += T) cp_async16(dst + i, src + i);
+        }
         stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
-        const IO *gob = reinterpret_cast<const IO *>(p.go) + (long long)b * p.n_out * HW;
-        for (int i = tid; i < npx; i += T)
-            patch_grad<IO, NP, false>(p, gob, (long long)b * HW + y0 * p.W + i, y0 * p.W + i, HW, gt + i * GS);
+        cp_async_wait_all();
         __syncthreads();
         {   // bias row: column sums of G
             const int n = tid % NP, sub = tid / NP, nsub = T / NP;
@@ -451,48 +487,62 @@ __global__ void build_wd_kernel(const float2 *UT, int A, int F, int N, int NP, i
 }
 
 // ------------------------------------------------------------------------------------------------------ host side
-struct ConvTiling {
-    int TH, T, TC, CS, bands, wr, parts, Tw, ct;
-    size_t smem_fwd, smem_data, smem_w;
+enum { KIND_FWD = 0, KIND_DATA = 1, KIND_W = 2 };
+
+struct ConvTile {
+    int TH, T, TC, CS, bands, wr, parts, ct;
+    size_t smem;
 };
 
 constexpr size_t CONV_SMEM_MAX = 200 * 1024;
+constexpr size_t CONV_SMEM_PREF = 72 * 1024;       // three CTAs per SM
 
-bool conv_tiling(const GemmShape &g, const GateParams &gp, int NP, ConvTiling *t) {
+// Band height of one kernel: fills the 2-pixels-per-thread CTA (forward / image gradient) or balances the pixel rows over the
+// warps (weight gradient) with the least halo, preferring a footprint that leaves three CTAs per SM.
+bool conv_tile(const GemmShape &g, const GateParams &gp, int NP, int kind, ConvTile *t) {
     const int KS = gp.kh, GS = NP + 4, NC = NP < 16 ? NP : 16;
     const int wr = (gp.C * KS + 31) / 32, ig = wr * (NP / NC);
     if (ig > 8) return false;
+    const int parts = 8 / ig, Tw = 32 * ig * parts;
     const int ct = gp.C > 8 ? 16 : 8;
     const int c_pad = (gp.C + ct - 1) / ct * ct;
-    double best = 0.0;
-    bool found = false;
+    const size_t wdf = (size_t)(((g.F + 1) * NP + 3) & ~3);
+    double best[2] = {0.0, 0.0};       // [0]: any footprint, [1]: preferred footprint
+    ConvTile cand[2];
     for (int th = 1; th <= gp.H; ++th) {
         const int pu = th * gp.W;
-        if (pu > 512) break;
+        if (kind != KIND_W && pu > 512) break;
+        if (kind == KIND_W && pu > 2048) break;
         int T = ((pu + 63) / 64) * 32;
         if (T < 64) T = 64;
+        if (kind == KIND_W) T = Tw;
         const int bands = (gp.H + th - 1) / th;
         const int tc = (gp.W + KS - 1) | 1;
         const int trtc = (th + KS - 1) * tc;
         const int cs = trtc + ((3 - trtc % 32) + 32) % 32;
-        const size_t wdf = (size_t)(((g.F + 1) * NP + 3) & ~3);
-        const size_t s_fwd = 4 * (wdf + (size_t)gp.C * cs);
-        const size_t s_data = 4 * ((size_t)c_pad * KS * KS * NP + (size_t)(th + KS - 1) * (gp.W + KS - 1) * GS);
-        const size_t s_w = 4 * (wdf + (((size_t)gp.C * cs + 3) & ~(size_t)3) + (size_t)pu * GS);
-        if (s_fwd > CONV_SMEM_MAX || s_data > CONV_SMEM_MAX || s_w > CONV_SMEM_MAX) continue;
-        const double eff = (double)gp.H * gp.W / ((double)bands * 2 * T) * (1.0 - 0.02 * (KS - 1) / th);
-        if (eff > best + 1e-9) {
-            best = eff;
-            found = true;
-            t->TH = th; t->T = T; t->TC = tc; t->CS = cs; t->bands = bands;
-            t->smem_fwd = s_fwd; t->smem_data = s_data; t->smem_w = s_w;
+        const size_t tile = ((size_t)gp.C * cs + 3) & ~(size_t)3;
+        size_t smem;
+        double eff;
+        if (kind == KIND_FWD) {
+            smem = 4 * (wdf + tile);
+            eff = (double)gp.H * gp.W / ((double)bands * 2 * T) * (1.0 - 0.02 * (KS - 1) / th);
+        } else if (kind == KIND_DATA) {
+            smem = 4 * ((size_t)c_pad * KS * KS * NP + (size_t)(th + KS - 1) * (gp.W + KS - 1) * GS);
+            eff = (double)gp.H * gp.W / ((double)bands * 2 * T) * ((double)th / (th + KS - 1));
+        } else {
+            smem = 4 * (wdf + tile + (size_t)pu * GS);
+            const int rounds = (th + parts - 1) / parts;
+            eff = (double)gp.H / ((double)bands * rounds * parts) * ((double)th / (th + KS - 1));
         }
+        if (smem > CONV_SMEM_MAX) continue;
+        ConvTile c;
+        c.TH = th; c.T = T; c.TC = tc; c.CS = cs; c.bands = bands; c.wr = wr; c.parts = parts; c.ct = ct; c.smem = smem;
+        // ties go to the taller band (fewer units, less halo)
+        if (eff > best[0] - 1e-9) { best[0] = eff > best[0] ? eff : best[0]; cand[0] = c; }
+        if (smem <= CONV_SMEM_PREF && eff > best[1] - 1e-9) { best[1] = eff > best[1] ? eff : best[1]; cand[1] = c; }
     }
-    if (!found) return false;
-    t->wr = wr;
-    t->parts = 8 / ig;
-    t->Tw = 32 * ig * t->parts;
-    t->ct = ct;
+    if (best[0] <= 0.0) return false;
+    *t = (best[1] >= 0.75 * best[0]) ? cand[1] : cand[0];
     return true;
 }
 
@@ -500,7 +550,7 @@ template <typename K>
 int conv_grid(K kern, int T, size_t smem, int units, int cap_ctas) {
     // attribute / occupancy queries remembered per kernel, device and launch shape (they cost ~10 us of host time)
     struct Entry { const void *k; int dev, T; size_t smem; int per_sm, sms; };
-    thread_local Entry cache[64];
+    thread_local Entry cache[96];
     thread_local int n_cache = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -512,14 +562,14 @@ int conv_grid(K kern, int T, size_t smem, int units, int cap_ctas) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_MAX) != cudaSuccess) return -1;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem) != cudaSuccess || per_sm < 1) return -1;
-        if (n_cache < 64) cache[n_cache++] = Entry{kp, dev, T, smem, per_sm, sms};
+        if (n_cache < 96) cache[n_cache++] = Entry{kp, dev, T, smem, per_sm, sms};
     }
     long long cap = (long long)per_sm * sms;
     if (cap_ctas > 0 && cap > cap_ctas) cap = cap_ctas;
     return (int)(units < cap ? units : cap);
 }
 
-ConvParams conv_params(const GemmShape &g, const GateParams &gp, const ConvTiling &t, long long n_images) {
+ConvParams conv_params(const GemmShape &g, const GateParams &gp, const ConvTile &t, long long n_images) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.n_images = (int)n_images; p.C = gp.C; p.H = gp.H; p.W = gp.W; p.F = g.F; p.N = g.N; p.n_out = g.n_out;
@@ -528,7 +578,7 @@ ConvParams conv_params(const GemmShape &g, const GateParams &gp, const ConvTilin
     p.add_offset = gp.add_offset;
     p.pad2 = (float)(g.A - g.F) * gp.pad_value * gp.pad_value;
     p.wr = t.wr; p.parts = t.parts;
-    p.Bp = (n_images * gp.H * gp.W + 3) & ~3LL;
+    p.B = n_images * gp.H * gp.W;
     return p;
 }
 
@@ -540,13 +590,13 @@ ConvParams conv_params(const GemmShape &g, const GateParams &gp, const ConvTilin
     } while (0)
 
 template <typename IO, int KS>
-int conv_forward_t(const ConvParams &p, const ConvTiling &t, int NP, cudaStream_t s) {
+int conv_forward_t(const ConvParams &p, const ConvTile &t, int NP, cudaStream_t s) {
 #define CALL(NP_)                                                                                   \
     {                                                                                               \
         auto k = conv_fwd_kernel<IO, KS, NP_>;                                                      \
-        const int grid = conv_grid(k, t.T, t.smem_fwd, p.units, 0);                                 \
+        const int grid = conv_grid(k, t.T, t.smem, p.units, 0);                                     \
         if (grid < 1) return QIDDM_EUNSUPPORTED;                                                    \
-        k<<<grid, t.T, t.smem_fwd, s>>>(p);                                                         \
+        k<<<grid, t.T, t.smem, s>>>(p);                                                             \
     }
     CONV_DISPATCH_NP(CALL);
 #undef CALL
@@ -554,19 +604,19 @@ int conv_forward_t(const ConvParams &p, const ConvTiling &t, int NP, cudaStream_
 }
 
 template <typename IO, int KS>
-int conv_bwd_data_t(const ConvParams &p, const ConvTiling &t, int NP, cudaStream_t s) {
+int conv_bwd_data_t(const ConvParams &p, const ConvTile &t, int NP, cudaStream_t s) {
 #define CALL(NP_)                                                                                   \
     {                                                                                               \
         if (t.ct == 8) {                                                                            \
             auto k = conv_bwd_data_kernel<IO, KS, NP_, 8>;                                          \
-            const int grid = conv_grid(k, t.T, t.smem_data, p.units, 0);                            \
+            const int grid = conv_grid(k, t.T, t.smem, p.units, 0);                                 \
             if (grid < 1) return QIDDM_EUNSUPPORTED;                                                \
-            k<<<grid, t.T, t.smem_data, s>>>(p);                                                    \
+            k<<<grid, t.T, t.smem, s>>>(p);                                                         \
         } else {                                                                                    \
             auto k = conv_bwd_data_kernel<IO, KS, NP_, 16>;                                         \
-            const int grid = conv_grid(k, t.T, t.smem_data, p.units, 0);                            \
+            const int grid = conv_grid(k, t.T, t.smem, p.units, 0);                                 \
             if (grid < 1) return QIDDM_EUNSUPPORTED;                                                \
-            k<<<grid, t.T, t.smem_data, s>>>(p);                                                    \
+            k<<<grid, t.T, t.smem, s>>>(p);                                                         \
         }                                                                                           \
     }
     CONV_DISPATCH_NP(CALL);
@@ -575,28 +625,18 @@ int conv_bwd_data_t(const ConvParams &p, const ConvTiling &t, int NP, cudaStream
 }
 
 template <typename IO, int KS>
-int conv_bwd_w_t(ConvParams &p, const ConvTiling &t, int NP, int *grid_out, cudaStream_t s) {
+int conv_bwd_w_t(ConvParams &p, const ConvTile &t, int NP, int *grid_out, cudaStream_t s) {
 #define CALL(NP_)                                                                                   \
     {                                                                                               \
         auto k = conv_bwd_w_kernel<IO, KS, NP_>;                                                    \
-        const int grid = conv_grid(k, t.Tw, t.smem_w, p.units, CONV_MAX_WGRID);                     \
+        const int grid = conv_grid(k, t.T, t.smem, p.units, CONV_MAX_WGRID);                        \
         if (grid < 1) return QIDDM_EUNSUPPORTED;                                                    \
         *grid_out = grid;                                                                           \
-        k<<<grid, t.Tw, t.smem_w, s>>>(p);                                                          \
+        k<<<grid, t.T, t.smem, s>>>(p);                                                             \
     }
     CONV_DISPATCH_NP(CALL);
 #undef CALL
     return QIDDM_OK;
-}
-
-struct ConvSaved {
-    float *Y, *inv_n2;
-};
-ConvSaved conv_saved_view(const GemmShape &g, long long Bp, void *buf) {
-    ConvSaved v;
-    v.Y = reinterpret_cast<float *>(buf);
-    v.inv_n2 = v.Y + (size_t)g.N * Bp;
-    return v;
 }
 
 }  // namespace
@@ -628,33 +668,35 @@ bool conv_direct_supported(const GemmShape &g, const GateParams &gp) {
     if (g.F != gp.C * gp.kh * gp.kw) return false;
     const int NP = conv_np(g.N);
     if (!NP) return false;
-    ConvTiling t;
-    return conv_tiling(g, gp, NP, &t);
+    ConvTile t;
+    for (int kind = KIND_FWD; kind <= KIND_W; ++kind)
+        if (!conv_tile(g, gp, NP, kind, &t)) return false;
+    return true;
 }
 
 size_t conv_direct_saved_bytes(const GemmShape &g, const GateParams &gp, long long n_images) {
-    const long long Bp = (n_images * gp.H * gp.W + 3) & ~3LL;
-    return (size_t)(g.N + 1) * Bp * 4 + 256;
+    return (size_t)n_images * gp.H * gp.W * (conv_np(g.N) + 4) * 4 + 256;        // one row [Y (NP), 1/|f|^2, pad] per patch
 }
 
-size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp) {
+static size_t conv_partials_bytes(const GemmShape &g, int NP) { return ((size_t)CONV_MAX_WGRID * (g.F + 1) * NP * 4 + 255) & ~(size_t)255; }
+static size_t conv_gut_bytes(const GemmShape &g) { return ((size_t)g.A * g.A * 8 + 255) & ~(size_t)255; }
+static size_t conv_sum_bytes(const GemmShape &g, int NP) { return ((size_t)(g.F + 1) * NP * 8 + 255) & ~(size_t)255; }
+
+size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp, long long n_images) {
     const int NP = conv_np(g.N);
-    return (((size_t)CONV_MAX_WGRID * (g.F + 1) * NP * 4 + 255) & ~(size_t)255) + (((size_t)g.A * g.A * 8 + 255) & ~(size_t)255) +
-           (((size_t)(g.F + 1) * NP * 8 + 255) & ~(size_t)255);
+    return conv_partials_bytes(g, NP) + conv_gut_bytes(g) + conv_sum_bytes(g, NP) +
+           (((size_t)n_images * gp.H * gp.W * (NP + 4) * 4 + 255) & ~(size_t)255);                 // G rows
 }
 
 // out (NCHW, io dtype); `saved` non-null (training): Y and 1/|f|^2 are kept for conv_direct_backward
 int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, void *out, void *saved,
                         long long n_images, cudaStream_t s) {
     const int NP = conv_np(g.N);
-    ConvTiling t;
-    if (!NP || !conv_tiling(g, gp, NP, &t)) return QIDDM_EUNSUPPORTED;
+    ConvTile t;
+    if (!NP || !conv_tile(g, gp, NP, KIND_FWD, &t)) return QIDDM_EUNSUPPORTED;
     ConvParams p = conv_params(g, gp, t, n_images);
     p.img = img; p.out = out; p.Wd = Wd;
-    if (saved != nullptr) {
-        const ConvSaved v = conv_saved_view(g, p.Bp, saved);
-        p.Y = v.Y; p.inv_n2 = v.inv_n2;
-    }
+    p.Y = reinterpret_cast<float *>(saved);
     timing_begin(TK_CONV_FWD, 2.0 * (double)n_images * gp.H * gp.W * g.F * g.N, s);
     int rc;
     if (gp.io64) rc = gp.kh == 3 ? conv_forward_t<double, 3>(p, t, NP, s) : conv_forward_t<double, 1>(p, t, NP, s);
@@ -670,33 +712,50 @@ int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *W
 int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, const void *grad_out,
                          const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s) {
     const int NP = conv_np(g.N);
-    ConvTiling t;
-    if (!NP || !conv_tiling(g, gp, NP, &t) || saved == nullptr) return QIDDM_EUNSUPPORTED;
-    ConvParams p = conv_params(g, gp, t, n_images);
-    const ConvSaved v = conv_saved_view(g, p.Bp, const_cast<void *>(saved));
-    p.img = img; p.go = grad_out; p.gimg = grad_img; p.Wd = Wd; p.Y = v.Y; p.inv_n2 = v.inv_n2;
-    p.partials = reinterpret_cast<float *>(ws);
-    float *gUT = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) +
-                                           (((size_t)CONV_MAX_WGRID * (g.F + 1) * NP * 4 + 255) & ~(size_t)255));
+    ConvTile td, tw;
+    if (!NP || saved == nullptr || !conv_tile(g, gp, NP, KIND_DATA, &td) || !conv_tile(g, gp, NP, KIND_W, &tw))
+        return QIDDM_EUNSUPPORTED;
+    char *w8 = reinterpret_cast<char *>(ws);
+    float *partials = reinterpret_cast<float *>(w8); w8 += conv_partials_bytes(g, NP);
+    float *gUT = reinterpret_cast<float *>(w8); w8 += conv_gut_bytes(g);
+    double *sum = reinterpret_cast<double *>(w8); w8 += conv_sum_bytes(g, NP);
+    float *G = reinterpret_cast<float *>(w8);
     *gut_out = gUT;
     int rc = QIDDM_OK;
     timing_begin(TK_CONV_BWD, (grad_img ? 4.0 : 2.0) * (double)n_images * gp.H * gp.W * g.F * g.N, s);
+    {   // dL/dY rows, shared by the two gradient kernels
+        ConvParams p = conv_params(g, gp, td, n_images);
+        p.go = grad_out; p.Y = reinterpret_cast<float *>(const_cast<void *>(saved)); p.G = G;
+        const long long blocks = (p.B + 255) / 256;
+        const unsigned grid = (unsigned)(blocks < 148 * 8 ? blocks : 148 * 8);
+#define CALL(NP_)                                                               \
+        {                                                                       \
+            if (gp.io64) conv_grad_kernel<double, NP_><<<grid, 256, 0, s>>>(p); \
+            else conv_grad_kernel<float, NP_><<<grid, 256, 0, s>>>(p);          \
+        }
+        CONV_DISPATCH_NP(CALL);
+#undef CALL
+        count_launch();
+    }
     if (grad_img != nullptr) {
-        if (gp.io64) rc = gp.kh == 3 ? conv_bwd_data_t<double, 3>(p, t, NP, s) : conv_bwd_data_t<double, 1>(p, t, NP, s);
-        else rc = gp.kh == 3 ? conv_bwd_data_t<float, 3>(p, t, NP, s) : conv_bwd_data_t<float, 1>(p, t, NP, s);
+        ConvParams p = conv_params(g, gp, td, n_images);
+        p.img = img; p.gimg = grad_img; p.Wd = Wd; p.G = G;
+        if (gp.io64) rc = gp.kh == 3 ? conv_bwd_data_t<double, 3>(p, td, NP, s) : conv_bwd_data_t<double, 1>(p, td, NP, s);
+        else rc = gp.kh == 3 ? conv_bwd_data_t<float, 3>(p, td, NP, s) : conv_bwd_data_t<float, 1>(p, td, NP, s);
         count_launch();
     }
     int wgrid = 0;
     if (rc == QIDDM_OK) {
-        if (gp.io64) rc = gp.kh == 3 ? conv_bwd_w_t<double, 3>(p, t, NP, &wgrid, s) : conv_bwd_w_t<double, 1>(p, t, NP, &wgrid, s);
-        else rc = gp.kh == 3 ? conv_bwd_w_t<float, 3>(p, t, NP, &wgrid, s) : conv_bwd_w_t<float, 1>(p, t, NP, &wgrid, s);
+        ConvParams p = conv_params(g, gp, tw, n_images);
+        p.img = img; p.G = G; p.partials = partials;
+        if (gp.io64) rc = gp.kh == 3 ? conv_bwd_w_t<double, 3>(p, tw, NP, &wgrid, s) : conv_bwd_w_t<double, 1>(p, tw, NP, &wgrid, s);
+        else rc = gp.kh == 3 ? conv_bwd_w_t<float, 3>(p, tw, NP, &wgrid, s) : conv_bwd_w_t<float, 1>(p, tw, NP, &wgrid, s);
         count_launch();
     }
     timing_end(s);
     if (rc != QIDDM_OK) return rc;
     const int total = (g.F + 1) * NP;
-    double *sum = reinterpret_cast<double *>(reinterpret_cast<char *>(gUT) + (((size_t)g.A * g.A * 8 + 255) & ~(size_t)255));
-    conv_reduce_kernel<<<(total + 31) / 32, 256, 0, s>>>(p.partials, wgrid, total, sum);
+    conv_reduce_kernel<<<(total + 31) / 32, 256, 0, s>>>(partials, wgrid, total, sum);
     const long long elems = (long long)g.A * g.A * 2;
     conv_assemble_kernel<<<(unsigned)((elems + 255) / 256 < 592 ? (elems + 255) / 256 : 592), 256, 0, s>>>(
         sum, g.A, g.F, g.N, NP, g.stride, gp.pad_value, gUT);

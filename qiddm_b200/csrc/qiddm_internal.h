@@ -92,7 +92,7 @@ size_t conv_wd_bytes(const GemmShape &g);
 int conv_build_wd(const GemmShape &g, const GateParams &gp, const float *UT, float *Wd, cudaStream_t s);
 bool conv_direct_supported(const GemmShape &g, const GateParams &gp);
 size_t conv_direct_saved_bytes(const GemmShape &g, const GateParams &gp, long long n_images);
-size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp);
+size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp, long long n_images);
 int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, void *out, void *saved,
                         long long n_images, cudaStream_t s);
 int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, const void *grad_out,
