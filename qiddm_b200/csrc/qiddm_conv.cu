@@ -56,34 +56,58 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem)); }
+
+// A CTA knows its next (image, band) unit: while it computes the current one, the next one's rows are pulled into L2, so the
+// staging loads of the next iteration see L2 latency instead of DRAM latency (they are the exposed latency of these kernels).
+template <typename IO>
+__device__ __forceinline__ void prefetch_image_rows(const IO *ib, int C, int HW, int W, int lo, int hi, int tid, int T) {
+    const int bytes = (hi - lo) * W * (int)sizeof(IO);
+    const int lines = (bytes + 127) >> 7;
+    for (int i = tid; i < C * lines; i += T) {
+        const int ch = i / lines, l = i - ch * lines;
+        prefetch_l2(reinterpret_cast<const char *>(ib + (long long)ch * HW + lo * W) + (l << 7));
+    }
+}
+__device__ __forceinline__ void prefetch_span(const void *base, long long bytes, int tid, int T) {
+    const int lines = (int)((bytes + 127) >> 7);
+    for (int i = tid; i < lines; i += T) prefetch_l2(reinterpret_cast<const char *>(base) + ((long long)i << 7));
+}
 
 // band of image rows [y0 - PH, y0 + th + PH) x columns [-PH, W + PH) of all channels, + add_offset (the zero padding of
-// torch.nn.Unfold becomes add_offset: the reference adds 0.1 to the unfolded patch)
+// torch.nn.Unfold becomes add_offset: the reference adds 0.1 to the unfolded patch).  The rows that exist are one contiguous
+// run per channel: a thread keeps three positions of that run (its tile offsets computed once per band) and walks the
+// channels with twelve loads in flight; everything else in the tile is add_offset, written first.
 template <typename IO, int KS>
 __device__ __forceinline__ void stage_image(const ConvParams &p, const IO *ib, int y0, int th, float *tile, int tid, int T) {
-    // one warp per (channel, row) line of the tile, four lines in flight per warp (the loads are the latency to hide)
     constexpr int PH = KS / 2;
-    const int tr = th + KS - 1, HW = p.H * p.W;
-    const int nrows = p.C * tr, nw = T >> 5, warp = tid >> 5, lane = tid & 31;
-    for (int row0 = warp; row0 < nrows; row0 += 4 * nw) {
-        for (int c = lane; c < p.TC; c += 32) {
-            const int ix = c - PH;
-            const bool colin = ix >= 0 && ix < p.W;
-            float v[4];
+    const int HW = p.H * p.W;
+    const int lo = max(y0 - PH, 0), hi = min(y0 + th + PH, p.H);
+    const int len = (hi - lo) * p.W, rofs = lo - (y0 - PH);
+    {
+        const float4 o4 = make_float4(p.add_offset, p.add_offset, p.add_offset, p.add_offset);
+        float4 *t4 = reinterpret_cast<float4 *>(tile);
+        const int n4 = (p.C * p.CS + 3) >> 2;
+        for (int i = tid; i < n4; i += T) t4[i] = o4;
+    }
+    __syncthreads();
+    const IO *src = ib + lo * p.W;
+    for (int i0 = tid; i0 < len; i0 += 3 * T) {
+        int idx[3], dst[3];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int row = row0 + u * nw;
-                const int ch = row / tr, r = row - ch * tr;
-                const int iy = y0 - PH + r;
-                v[u] = 0.f;
-                if (row < nrows && colin && iy >= 0 && iy < p.H) v[u] = (float)__ldg(ib + (long long)ch * HW + iy * p.W + ix);
-            }
+        for (int k = 0; k < 3; ++k) {
+            idx[k] = i0 + k * T;
+            const int r = idx[k] / p.W, x = idx[k] - r * p.W;
+            dst[k] = (r + rofs) * p.TC + x + PH;
+        }
+#pragma unroll 4
+        for (int ch = 0; ch < p.C; ++ch) {
+            float v[3];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int row = row0 + u * nw;
-                const int ch = row / tr, r = row - ch * tr;
-                if (row < nrows) tile[ch * p.CS + r * p.TC + c] = v[u] + p.add_offset;
-            }
+            for (int k = 0; k < 3; ++k) v[k] = idx[k] < len ? (float)__ldg(src + (long long)ch * HW + idx[k]) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (idx[k] < len) tile[ch * p.CS + dst[k]] = v[k] + p.add_offset;
         }
     }
 }
@@ -105,6 +129,11 @@ __global__ void __launch_bounds__(256, NP >= 32 ? 2 : 3) conv_fwd_kernel(const C
         __syncthreads();
         stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
         __syncthreads();
+        if (unit + gridDim.x < p.units) {
+            const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
+            prefetch_image_rows<IO>(reinterpret_cast<const IO *>(p.img) + (long long)nb * p.C * HW, p.C, HW, p.W, max(ny0 - KS / 2, 0),
+                                    min(ny0 + min(p.TH, p.H - ny0) + KS / 2, p.H), tid, T);
+        }
         const int npx = th * p.W;
         int q[2], base[2];
         bool ok[2];
@@ -241,6 +270,11 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_data_kernel(const ConvParams 
         }
         cp_async_wait_all();
         __syncthreads();
+        if (unit + gridDim.x < p.units) {
+            const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
+            const int lo = max(ny0 - PH, 0), hi = min(ny0 + min(p.TH, p.H - ny0) + PH, p.H);
+            prefetch_span(p.G + ((long long)nb * HW + lo * p.W) * GS, (long long)(hi - lo) * p.W * GS * 4, tid, T);
+        }
         const int npx = th * p.W;
         int q[2], gbase[2];
         bool ok[2];
@@ -342,6 +376,7 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) 
     for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
         for (int j = 0; j < NC / 2; ++j) acc[kx][j] = f2(0.f, 0.f);
+    float bsum = 0.f;
 
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         const int b = unit / p.bands, band = unit - b * p.bands;
@@ -357,13 +392,17 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) 
         stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
         cp_async_wait_all();
         __syncthreads();
-        {   // bias row: column sums of G
+        if (unit + gridDim.x < p.units) {
+            const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
+            const int nth = min(p.TH, p.H - ny0);
+            prefetch_span(p.G + ((long long)nb * HW + ny0 * p.W) * GS, (long long)nth * p.W * GS * 4, tid, T);
+            prefetch_image_rows<IO>(reinterpret_cast<const IO *>(p.img) + (long long)nb * p.C * HW, p.C, HW, p.W, max(ny0 - KS / 2, 0),
+                                    min(ny0 + nth + KS / 2, p.H), tid, T);
+        }
+        {   // bias row: column sums of G, kept per thread until the end of the launch
             const int n = tid % NP, sub = tid / NP, nsub = T / NP;
-            if (sub < nsub) {
-                float s = 0.f;
-                for (int i = sub; i < npx; i += nsub) s += gt[i * GS + n];
-                atomicAdd(dacc + p.F * NP + n, s);
-            }
+            if (sub < nsub)
+                for (int i = sub; i < npx; i += nsub) bsum += gt[i * GS + n];
         }
         if (part < p.parts) {
             for (int y = part; y < th; y += p.parts) {
@@ -404,16 +443,28 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) 
         }
     }
     __syncthreads();
-    if (part < p.parts && rowok) {
+    // the warps of one pixel-row part own distinct (row, n-chunk) entries: the parts add in turn (no atomics, fixed order)
+    for (int pt = 0; pt < p.parts; ++pt) {
+        if (part == pt && rowok) {
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
-            float *d = dacc + ((ch * KK + ky * KS + kx) * NP + nchunk * NC);
+            for (int kx = 0; kx < KS; ++kx) {
+                float *d = dacc + ((ch * KK + ky * KS + kx) * NP + nchunk * NC);
 #pragma unroll
-            for (int j = 0; j < NC / 2; ++j) {
-                atomicAdd(d + 2 * j, acc[kx][j].x);
-                atomicAdd(d + 2 * j + 1, acc[kx][j].y);
+                for (int j = 0; j < NC / 2; ++j) {
+                    d[2 * j] += acc[kx][j].x;
+                    d[2 * j + 1] += acc[kx][j].y;
+                }
             }
         }
+        __syncthreads();
+    }
+    float *bred = gt + p.TH * p.W * GS;  // [sub][n] partial column sums of G
+    bred[tid] = bsum;
+    __syncthreads();
+    if (tid < NP) {
+        float sb = 0.f;
+        for (int sub = 0; sub < T / NP; ++sub) sb += bred[sub * NP + tid];
+        dacc[p.F * NP + tid] = sb;
     }
     __syncthreads();
     float *dst = p.partials + (long long)blockIdx.x * (p.F + 1) * NP;
@@ -530,7 +581,7 @@ bool conv_tile(const GemmShape &g, const GateParams &gp, int NP, int kind, ConvT
             smem = 4 * ((size_t)c_pad * KS * KS * NP + (size_t)(th + KS - 1) * (gp.W + KS - 1) * GS);
             eff = (double)gp.H * gp.W / ((double)bands * 2 * T) * ((double)th / (th + KS - 1));
         } else {
-            smem = 4 * (wdf + tile + (size_t)pu * GS);
+            smem = 4 * (wdf + tile + (size_t)pu * GS + 256);
             const int rounds = (th + parts - 1) / parts;
             eff = (double)gp.H / ((double)bands * rounds * parts) * ((double)th / (th + KS - 1));
         }
