@@ -67,10 +67,31 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const T *gout, T *gin
         if (oy1 > Hout - 1) oy1 = Hout - 1;
         if (ox1 > Wout - 1) ox1 = Wout - 1;
         double acc = 0.0;
+        // column weights once per input pixel (they do not depend on the output row): a 2x upsample has 7 candidate
+        // columns and rows, 4 of each with a non-zero weight -- 16 loads instead of 49 lerp evaluations
+        constexpr int WMAX = 12;
+        double wxs[WMAX];
+        const bool pre = ox1 - ox0 < WMAX;
+        if (pre) {
+#pragma unroll
+            for (int k = 0; k < WMAX; ++k) {
+                const int ox = ox0 + k;
+                const Lerp x = lerp_of(ox <= ox1 ? ox : ox1, sw, Win);
+                wxs[k] = ox <= ox1 ? (x.i0 == ix ? x.l0 : 0.0) + (x.i1 == ix ? x.l1 : 0.0) : 0.0;
+            }
+        }
         for (int oy = oy0; oy <= oy1; ++oy) {
             const Lerp y = lerp_of(oy, sh, Hin);
             const double wy = (y.i0 == iy ? y.l0 : 0.0) + (y.i1 == iy ? y.l1 : 0.0);
             if (wy == 0.0) continue;
+            if (pre) {
+                double row = 0.0;
+#pragma unroll
+                for (int k = 0; k < WMAX; ++k)
+                    if (wxs[k] != 0.0) row += wxs[k] * (double)g[oy * Wout + ox0 + k];
+                acc += wy * row;
+                continue;
+            }
             for (int ox = ox0; ox <= ox1; ++ox) {
                 const Lerp x = lerp_of(ox, sw, Win);
                 const double wx = (x.i0 == ix ? x.l0 : 0.0) + (x.i1 == ix ? x.l1 : 0.0);

@@ -238,3 +238,35 @@ def test_fused_step_dispatch_conditions_on_the_host():
         assert diff._fused_step(x, {"T": 4}) is None
     finally:
         os.environ.pop("QIDDM_FUSED_STEP", None)
+
+
+def test_qconv_dispatch_direct_convolution_gemm_or_gate():
+    """Plan.use_collapse_qconv: every layer shape of UNetUndirected(3, 8, 3) except the 32-output-channel ones has the direct
+    fp32 convolution (csrc/qiddm_conv.cu) and takes it once the call has at least 2^n patches; an explicit PATH_GEMM / PATH_GATE
+    is honoured; other windows fall back to the GEMM-vs-gate cost model.  Host logic only (the library answers without a GPU)."""
+    import dataclasses
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import nn
+
+    def plan_of(cin, cout, k, path=L.PATH_AUTO):
+        m = nn.QConv2d(cin, cout, kernel_size=k, padding=k // 2, qdepth=3)
+        return L.Plan.get(dataclasses.replace(m._spec(), path=path)), m
+
+    for cin, cout, k, hw in ((1, 8, 3, 28), (8, 8, 3, 28), (16, 8, 3, 28), (16, 8, 1, 28), (8, 1, 1, 28), (8, 16, 3, 14),
+                             (16, 16, 3, 14), (32, 16, 3, 14), (32, 16, 1, 14)):
+        plan, m = plan_of(cin, cout, k)
+        u = L.UnfoldDesc(cin, hw, hw, k, k, k // 2, k // 2)
+        assert plan.qconv_direct(u), (cin, cout, k)
+        assert plan.use_collapse_qconv(u, plan.spec.dim)             # as many patches as basis columns: direct
+        assert not plan.use_collapse_qconv(u, plan.spec.dim - 1)     # fewer: gate by gate (no collapse to pay for)
+        assert not plan_of(cin, cout, k, L.PATH_GATE)[0].use_collapse_qconv(u, 10 ** 6)
+        pg = plan_of(cin, cout, k, L.PATH_GEMM)[0]
+        assert not pg.qconv_direct(u) and pg.use_collapse_qconv(u, 1)
+    for cin, cout, k, hw in ((16, 32, 3, 7), (32, 32, 3, 7)):            # N = 64 rows of U: tcgen05 GEMM or gate path
+        plan, m = plan_of(cin, cout, k)
+        u = L.UnfoldDesc(cin, hw, hw, k, k, 1, 1)
+        assert not plan.qconv_direct(u)
+        assert plan.use_collapse_qconv(u, 31360) == plan.use_gemm(31360)
+    plan, m = plan_of(8, 8, 3)
+    assert not plan.qconv_direct(L.UnfoldDesc(8, 28, 28, 3, 3, 0, 0))       # not "same" padding
+    assert not plan.qconv_direct(L.UnfoldDesc(8, 4, 600, 3, 3, 1, 1))       # a row wider than a 512-pixel band
