@@ -572,6 +572,21 @@ def secondary_train(dev, world, rank, steps, only=None):
                                  "note": "algorithmic flops of the adjoint counted as 3x the forward (un-apply on psi, apply-dagger "
                                          "on lambda, inner products); psi_final comes from the forward launch, no recomputation"},
                     "share_of_eager_step": (gf["ms"] + gb["ms"]) / 2 / eager_ms}
+        cf, cb = kinds["conv_forward"], kinds["conv_backward"]
+        if rank == 0 and cf["launches"] and cb["launches"] and cf["ms"] + cb["ms"] > gf["ms"] + gb["ms"]:
+            # QConv networks: the direct-convolution kernels (csrc/qiddm_conv.cu) carry the step, not the gate kernels
+            tf_f = cf["work"] / (cf["ms"] * 1e-3) / 1e12
+            tf_b = cb["work"] / (cb["ms"] * 1e-3) / 1e12
+            tf_all = (cf["work"] + cb["work"]) / ((cf["ms"] + cb["ms"]) * 1e-3) / 1e12
+            roof = {"kernel": "conv_fwd_kernel / conv_grad + conv_bwd_data + conv_bwd_w kernels (QConv2d as a direct fp32 convolution)",
+                    "bound": "fp32", "unit": "TFLOP/s", "achieved": tf_all, "peak": fp32_peak,
+                    "frac": tf_all / fp32_peak if fp32_peak else None,
+                    "peak_source": "qiddm_probe_fp32_fma, this run (burst rate of packed FFMA2 chains)",
+                    "algorithmic_flops": "2 F N per patch and pass (F = C k k features, N = 2 out_channels rows of U); backward = image "
+                                         "gradient + weight gradient (the first layer has no image gradient)",
+                    "forward": {"achieved": tf_f, "frac": tf_f / fp32_peak, "ms_per_step": cf["ms"] / 2},
+                    "backward": {"achieved": tf_b, "frac": tf_b / fp32_peak, "ms_per_step": cb["ms"] / 2},
+                    "share_of_eager_step": (cf["ms"] + cb["ms"]) / 2 / eager_ms}
         kshares = {k: round(v["ms"] / 2 / eager_ms, 4) for k, v in kinds.items() if v["launches"] and v["ms"] / 2 / eager_ms >= 0.01}
         evals_per_image = {"config3": 10 * 5782}.get(key, 10 * 2)         # tau x (circuits per image-forward)
         out[key] = {"model": name, "reference": src, "goal": goal, "images_per_gpu": imgs, "value": imgs * world / (ms * 1e-3),

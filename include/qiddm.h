@@ -195,6 +195,11 @@ int qiddm_dense_mse_step(const qiddm_plan *plan, const void *collapsed, const vo
  * accumulators of a patch stay on chip: no patch matrix, no fp16 operand splits; results are plain fp32 (QIDDM_QCONV_DIRECT=0
  * turns it off).  The backward then needs the `saved` buffer of its forward. */
 int qiddm_qconv_direct_supported(const qiddm_plan *plan, const qiddm_unfold_desc *unfold);
+/* `qiddm_gemm_prepare` for a layer whose every call takes the direct convolution: the collapse (U^T) and its fp32 filter rows,
+ * without the fp16 GEMM operands.  The buffer has the size and layout of qiddm_gemm_collapsed_bytes; the GEMM entry points must
+ * not be used with it. */
+int qiddm_gemm_prepare_direct(const qiddm_plan *plan, const void *weights, int weights_dtype, void *collapsed,
+                              void *workspace, qiddm_stream_t stream);
 size_t qiddm_qconv_gemm_saved_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images);
 size_t qiddm_qconv_gemm_workspace_bytes(const qiddm_plan *plan, const qiddm_unfold_desc *unfold, int64_t n_images);
 int qiddm_qconv_gemm_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold,
@@ -218,7 +223,8 @@ int qiddm_qconv_reference_map_backward(const qiddm_unfold_desc *unfold, int dtyp
 /* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
  * launching stream around each main kernel.  collect() synchronises on them and returns, per kind
  * (0 gate forward, 1 gate adjoint backward, 2 tcgen05 GEMM (all), 3 other, 4/5/6 GEMM forward / dX / dW,
- * 7 prep_x, 8 transpose_x, 9 g_bound, 10 grad_y, 11 finish_dx, 12 assemble, 13 build_w), the summed
+ * 7 prep_x, 8 transpose_x, 9 g_bound, 10 grad_y, 11 finish_dx, 12 assemble, 13 build_w, 14 / 15 direct QConv forward / backward
+ * kernels), the summed
  * milliseconds, the summed algorithmic work (flops) and the launch count, then clears the record.
  * Arrays of QIDDM_TIMING_KINDS = 16. */
 #define QIDDM_TIMING_KINDS 16

@@ -50,7 +50,7 @@ EXPORTS = [
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
-    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported",
+    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported", "qiddm_gemm_prepare_direct",
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
@@ -173,6 +173,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_gemm_workspace_bytes.argtypes = [vp, i64]
         lib.qiddm_gemm_prepare.restype = i32
         lib.qiddm_gemm_prepare.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.qiddm_gemm_prepare_direct.restype = i32
+        lib.qiddm_gemm_prepare_direct.argtypes = [vp, vp, i32, vp, vp, vp]
         lib.qiddm_gemm_forward.restype = i32
         lib.qiddm_gemm_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
         lib.qiddm_gemm_backward.restype = i32
@@ -218,7 +220,7 @@ def launch_count() -> int:
 
 
 TIMING_KINDS = ("gate_forward", "gate_backward", "gemm", "other", "gemm_forward", "gemm_dx", "gemm_dw", "prep_x",
-                "transpose_x", "g_bound", "grad_y", "finish_dx", "assemble", "build_w", "k14", "k15")
+                "transpose_x", "g_bound", "grad_y", "finish_dx", "assemble", "build_w", "conv_forward", "conv_backward")
 
 
 def timing_enable(on: bool) -> None:
@@ -577,10 +579,10 @@ class Plan:
         for p in plans:
             p.invalidate()
 
-    def gemm_prepare(self, weights: torch.Tensor) -> torch.Tensor:
-        """Collapsed operator (U^T + fp16 GEMM operands) for the current weights; cached per weight tensor and version
-        (modules with equal StageSpecs share the Plan but not the operator: a UNet's same-shaped QConv layers keep one
-        entry each)."""
+    def gemm_prepare(self, weights: torch.Tensor, direct: bool = False) -> torch.Tensor:
+        """Collapsed operator (U^T + fp16 GEMM operands; `direct`: U^T + the fp32 filter rows of the direct QConv path only)
+        for the current weights; cached per weight tensor and version (modules with equal StageSpecs share the Plan but not
+        the operator: a UNet's same-shaped QConv layers keep one entry each)."""
         w = self._check_weights(weights)
         # identity of the (base) tensor object + its version counter; the cache keeps a strong reference
         # to that object, so its address cannot be recycled by another tensor while the entry lives
@@ -590,7 +592,7 @@ class Plan:
         # buffer belongs to the graph's pool: neither read nor update the eager cache
         dev = w.device
         capture = int(self.lib.qiddm_stream_capture_id(self._stream(dev)))
-        slot = (id(base), weights.storage_offset(), weights.numel())
+        slot = (id(base), weights.storage_offset(), weights.numel(), bool(direct))
         with self._cache_lock:
             if not isinstance(getattr(self, "_collapsed", None), dict):
                 self._collapsed, self._collapsed_capture = {}, {}
@@ -602,11 +604,12 @@ class Plan:
                 cache[slot] = cache.pop(slot)          # most recently used last
                 return cached[2]
         # zero-filled: the fp16 operand rows are padded to 16 bytes and the padding meets zero columns of the other operand
-        buf = torch.zeros(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
+        # (the direct form writes every byte it later reads: no fill)
+        buf = (torch.empty if direct else torch.zeros)(int(self.lib.qiddm_gemm_collapsed_bytes(self.handle)), dtype=torch.uint8, device=dev)
         ws = self._workspace(self.spec.dim, dev)
         with torch.cuda.device(dev):
-            check(self.lib.qiddm_gemm_prepare(self.handle, _ptr(w), _wdtype(w), _ptr(buf), _ptr(ws),
-                                              self._stream(dev)), "qiddm_gemm_prepare")
+            prep = self.lib.qiddm_gemm_prepare_direct if direct else self.lib.qiddm_gemm_prepare
+            check(prep(self.handle, _ptr(w), _wdtype(w), _ptr(buf), _ptr(ws), self._stream(dev)), "qiddm_gemm_prepare")
         with self._cache_lock:
             cache.pop(slot, None)
             cache[slot] = (base, key, buf)
@@ -717,7 +720,7 @@ class Plan:
     def qconv_gemm_forward(self, img: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc, save: bool = False):
         """(N,C,H,W) -> (N,read_count,H_out,W_out); with `save` also returns the operand splits + Y for the backward."""
         _require_cuda(img, "input")
-        col = self.gemm_prepare(weights)
+        col = self.gemm_prepare(weights, direct=self.qconv_direct(unfold))
         dev = col.device
         # float64 images (the reference's UNet) are read and written in place of a cast; the simulation is fp32
         io = torch.float64 if img.dtype == torch.float64 else torch.float32
@@ -744,7 +747,7 @@ class Plan:
                             need_grad_in: bool = True, need_grad_w: bool = True,
                             saved: Optional[torch.Tensor] = None):
         w = self._check_weights(weights)
-        col = self.gemm_prepare(weights)
+        col = self.gemm_prepare(weights, direct=self.qconv_direct(unfold))
         dev = col.device
         io = torch.float64 if img.dtype == torch.float64 else torch.float32
         img = img.to(io).contiguous()

@@ -398,6 +398,21 @@ int qiddm_gemm_prepare(const qiddm_plan *plan, const void *weights, int weights_
     return gemm_build_operands(g, gp, collapsed, (cudaStream_t)stream);
 }
 
+// Collapse for a layer that runs as a direct convolution: U^T and its fp32 filter rows only (no fp16 GEMM operands)
+int qiddm_gemm_prepare_direct(const qiddm_plan *plan, const void *weights, int weights_dtype, void *collapsed,
+                              void *workspace, qiddm_stream_t stream) {
+    if (!plan || !weights || !collapsed || !workspace) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan)) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, nullptr, 1);
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    if (conv_wd_bytes(g) == 0) return QIDDM_EUNSUPPORTED;
+    qiddm_plan t = basis_plan(plan);
+    int rc = forward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gemm_collapsed_ut(g, collapsed),
+                          workspace, t.dim, (cudaStream_t)stream);
+    if (rc != QIDDM_OK) return rc;
+    return conv_build_wd(g, gp, gemm_collapsed_ut(g, collapsed), gemm_collapsed_wd(g, collapsed), (cudaStream_t)stream);
+}
+
 size_t qiddm_gemm_forward_workspace_bytes(const qiddm_plan *plan, int64_t batch) {
     if (!plan || !gemm_eligible(plan) || batch < 0) return 0;
     GateParams gp = make_params(plan, nullptr, 1);

