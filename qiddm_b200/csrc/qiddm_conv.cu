@@ -93,21 +93,30 @@ __device__ __forceinline__ void stage_image(const ConvParams &p, const IO *ib, i
     __syncthreads();
     const IO *src = ib + lo * p.W;
     for (int i0 = tid; i0 < len; i0 += 3 * T) {
-        int idx[3], dst[3];
+        const IO *sp[3];
+        float *dp[3];
+        bool in[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            idx[k] = i0 + k * T;
-            const int r = idx[k] / p.W, x = idx[k] - r * p.W;
-            dst[k] = (r + rofs) * p.TC + x + PH;
+            const int idx = i0 + k * T;
+            in[k] = idx < len;
+            const int r = idx / p.W, x = idx - r * p.W;
+            sp[k] = src + (in[k] ? idx : 0);
+            dp[k] = tile + (r + rofs) * p.TC + x + PH;
         }
 #pragma unroll 4
         for (int ch = 0; ch < p.C; ++ch) {
             float v[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) v[k] = idx[k] < len ? (float)__ldg(src + (long long)ch * HW + idx[k]) : 0.f;
+            for (int k = 0; k < 3; ++k) {
+                v[k] = (float)__ldg(sp[k]);
+                sp[k] += HW;
+            }
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (idx[k] < len) tile[ch * p.CS + dst[k]] = v[k] + p.add_offset;
+            for (int k = 0; k < 3; ++k) {
+                if (in[k]) *dp[k] = v[k] + p.add_offset;
+                dp[k] += p.CS;
+            }
         }
     }
 }
@@ -480,10 +489,14 @@ __global__ void __launch_bounds__(256) conv_reduce_kernel(const float *partials,
     if (o < total) {
         const float *src = partials + o;
         int j = slice;
-        for (; j + 24 < n_part; j += 32) {
-            const float v0 = __ldg(src + (long long)j * total), v1 = __ldg(src + (long long)(j + 8) * total);
-            const float v2 = __ldg(src + (long long)(j + 16) * total), v3 = __ldg(src + (long long)(j + 24) * total);
-            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        for (; j + 56 < n_part; j += 64) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (long long)(j + 8 * u) * total);
+            s0 += (double)v[0] + (double)v[4];
+            s1 += (double)v[1] + (double)v[5];
+            s2 += (double)v[2] + (double)v[6];
+            s3 += (double)v[3] + (double)v[7];
         }
         for (; j < n_part; j += 8) s0 += __ldg(src + (long long)j * total);
     }

@@ -136,7 +136,24 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *x, int N,
     const int c = blockIdx.x, sp = blockIdx.y;
     const I M = (I)N * (I)HW;
     double s = 0.0, q = 0.0;
-    for (I i = (I)sp * BN_THREADS + threadIdx.x; i < M; i += (I)BN_SPLITS * BN_THREADS) {
+    constexpr I STEP = (I)BN_SPLITS * BN_THREADS;
+    I i = (I)sp * BN_THREADS + threadIdx.x;
+    for (; i + 3 * STEP < M; i += 4 * STEP) {             // four loads in flight per thread
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const I iu = i + (I)u * STEP;
+            const I n = iu / (I)HW;
+            v[u] = (double)x[(n * (I)C + (I)c) * (I)HW + (iu - n * (I)HW)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (relu == 2 && !(v[u] > 0.0)) v[u] = 0.0;
+            s += v[u];
+            q += v[u] * v[u];
+        }
+    }
+    for (; i < M; i += STEP) {
         const I n = i / (I)HW;
         const I hw = i - n * (I)HW;
         double v = (double)x[(n * (I)C + (I)c) * (I)HW + hw];
@@ -200,7 +217,30 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *x, c
     const double mu = mean[c], rs = rstd[c];
     const double gm = gamma ? (double)gamma[c] : 1.0, bt = beta ? (double)beta[c] : 0.0;
     double s = 0.0, q = 0.0;
-    for (I i = (I)sp * BN_THREADS + threadIdx.x; i < M; i += (I)BN_SPLITS * BN_THREADS) {
+    constexpr I STEP = (I)BN_SPLITS * BN_THREADS;
+    I i = (I)sp * BN_THREADS + threadIdx.x;
+    for (; i + STEP < M; i += 2 * STEP) {                 // two (x, dy) pairs in flight per thread
+        double xv[2], gv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const I iu = i + (I)u * STEP;
+            const I n = iu / (I)HW;
+            const I idx = (n * (I)C + (I)c) * (I)HW + (iu - n * (I)HW);
+            xv[u] = (double)x[idx];
+            gv[u] = (double)dy[idx];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            double xin = xv[u];
+            if (relu == 2 && !(xin > 0.0)) xin = 0.0;
+            const double xh = (xin - mu) * rs;
+            double g = gv[u];
+            if (relu == 1 && !(xh * gm + bt > 0.0)) g = 0.0;
+            s += g;
+            q += g * xh;
+        }
+    }
+    for (; i < M; i += STEP) {
         const I n = i / (I)HW;
         const I hw = i - n * (I)HW;
         const I idx = (n * (I)C + (I)c) * (I)HW + hw;
