@@ -210,6 +210,22 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
                               const void *saved, void *grad_img, void *grad_weights, void *workspace,
                               int64_t n_images, int precision, qiddm_stream_t stream);
 
+/* Bilinear Upsample (align_corners = False) followed by a 1 x 1 QConv2d -- `UpBlock.up_conv` of nn/unet.py:36-41 -- in one pass:
+ * `img_src` is the (n_images, C, h_in, w_in) tensor in front of the upsample, `unfold` the geometry of the 1 x 1 convolution on the
+ * upsampled (height, width) image, scale_h / scale_w the source-coordinate scales (1 / scale_factor, or in / out for size=).  The
+ * interpolation runs inside the staging of the direct-convolution kernels: the upsampled tensor never exists.  Direct-convolution
+ * layers only (qiddm_qconv_direct_supported, kernel 1 x 1; else QIDDM_EUNSUPPORTED); `collapsed` from qiddm_gemm_prepare[_direct],
+ * `saved` / `workspace` sized by qiddm_qconv_gemm_saved_bytes / _workspace_bytes for `unfold`.  The backward writes grad_up, the
+ * gradient w.r.t. the UPSAMPLED image (n_images, C, height, width; may be NULL): qiddm_upsample_bilinear_backward maps it to the
+ * source. */
+int qiddm_qconv_up_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold, int io_dtype,
+                           const void *img_src, int h_in, int w_in, double scale_h, double scale_w, void *out, void *saved,
+                           int64_t n_images, qiddm_stream_t stream);
+int qiddm_qconv_up_backward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold, int io_dtype,
+                            const void *img_src, int h_in, int w_in, double scale_h, double scale_w, const void *weights,
+                            int weights_dtype, const void *grad_out, const void *saved, void *grad_up, void *grad_weights,
+                            void *workspace, int64_t n_images, qiddm_stream_t stream);
+
 /* Compatibility: the forward `_QConv2d_FAST` LITERALLY executes (nn/qconv.py:71-90 -- the QNode call is missing there, SURVEY.md
  * H1): out[b, j, y, x] = clamp((patch feature 2j + 0.1) * F * 0.5, 0, 1), F = C * kernel_h * kernel_w, feature = (ch, ky, kx)
  * in torch.nn.Unfold order, zero padding; out_channels = min(module out_channels, ceil(F / 2)).  img / out / grad tensors

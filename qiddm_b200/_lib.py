@@ -50,7 +50,7 @@ EXPORTS = [
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
-    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported", "qiddm_gemm_prepare_direct",
+    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported", "qiddm_gemm_prepare_direct", "qiddm_qconv_up_forward", "qiddm_qconv_up_backward",
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
@@ -192,6 +192,11 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         for f in (lib.qiddm_qconv_gemm_saved_bytes, lib.qiddm_qconv_gemm_workspace_bytes):
             f.restype = C.c_size_t
             f.argtypes = [vp, C.POINTER(UnfoldDesc), i64]
+        lib.qiddm_qconv_up_forward.restype = i32
+        lib.qiddm_qconv_up_forward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), i32, vp, i32, i32, f64, f64, vp, vp, i64, vp]
+        lib.qiddm_qconv_up_backward.restype = i32
+        lib.qiddm_qconv_up_backward.argtypes = [vp, vp, C.POINTER(UnfoldDesc), i32, vp, i32, i32, f64, f64, vp, i32, vp, vp, vp, vp,
+                                                vp, i64, vp]
         lib.qiddm_qconv_direct_supported.restype = i32
         lib.qiddm_qconv_direct_supported.argtypes = [vp, C.POINTER(UnfoldDesc)]
         lib.qiddm_qconv_gemm_forward.restype = i32
@@ -764,6 +769,48 @@ class Plan:
                                                      _ptr(ws), n, self.spec.bwd_precision, self._stream(dev)),
                   "qiddm_qconv_gemm_backward")
         return grad_img, grad_w
+
+    # ------------------------------------------------------------------ bilinear Upsample -> 1 x 1 QConv in one pass
+    def qconv_up_forward(self, src: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc, scale_h: float, scale_w: float,
+                         save: bool = False):
+        """(N, C, h, w) source of the upsample -> (N, read_count, H, W) of the 1 x 1 QConv on the (H, W) = unfold geometry."""
+        _require_cuda(src, "input")
+        col = self.gemm_prepare(weights, direct=True)
+        dev = col.device
+        io = torch.float64 if src.dtype == torch.float64 else torch.float32
+        src = src.to(io).contiguous()
+        n = src.shape[0]
+        out = torch.empty((n, self.spec.read_count, unfold.height, unfold.width), dtype=io, device=dev)
+        saved = None
+        with torch.cuda.device(dev):
+            if save:
+                saved = torch.empty(int(self.lib.qiddm_qconv_gemm_saved_bytes(self.handle, C.byref(unfold), n)),
+                                    dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_qconv_up_forward(self.handle, _ptr(col), C.byref(unfold), DTYPE_F64 if io == torch.float64 else DTYPE_F32,
+                                                  _ptr(src), src.shape[2], src.shape[3], float(scale_h), float(scale_w), _ptr(out),
+                                                  _ptr(saved), n, self._stream(dev)), "qiddm_qconv_up_forward")
+        return (out, saved) if save else out
+
+    def qconv_up_backward(self, src: torch.Tensor, weights: torch.Tensor, grad_out: torch.Tensor, unfold: UnfoldDesc,
+                          scale_h: float, scale_w: float, saved: torch.Tensor, need_grad_in: bool = True, need_grad_w: bool = True):
+        """Returns (gradient w.r.t. the UPSAMPLED image or None, gradient w.r.t. the circuit weights or None)."""
+        w = self._check_weights(weights)
+        col = self.gemm_prepare(weights, direct=True)
+        dev = col.device
+        io = torch.float64 if src.dtype == torch.float64 else torch.float32
+        src = src.to(io).contiguous()
+        go = grad_out.to(io).contiguous()
+        n = src.shape[0]
+        grad_up = torch.empty((n, src.shape[1], unfold.height, unfold.width), dtype=io, device=dev) if need_grad_in else None
+        grad_w = torch.empty_like(w) if need_grad_w else None
+        with torch.cuda.device(dev):
+            ws = torch.empty(int(self.lib.qiddm_qconv_gemm_workspace_bytes(self.handle, C.byref(unfold), n)),
+                             dtype=torch.uint8, device=dev)
+            check(self.lib.qiddm_qconv_up_backward(self.handle, _ptr(col), C.byref(unfold), DTYPE_F64 if io == torch.float64 else DTYPE_F32,
+                                                   _ptr(src), src.shape[2], src.shape[3], float(scale_h), float(scale_w), _ptr(w),
+                                                   _wdtype(w), _ptr(go), _ptr(saved), _ptr(grad_up), _ptr(grad_w), _ptr(ws), n,
+                                                   self._stream(dev)), "qiddm_qconv_up_backward")
+        return grad_up, grad_w
 
     def build_unitary(self, weights: torch.Tensor) -> torch.Tensor:
         """Returns U as a (2^n, 2^n) complex64 tensor (the library writes U^T, row c = U|c>)."""

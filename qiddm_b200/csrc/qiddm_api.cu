@@ -604,6 +604,58 @@ int qiddm_qconv_gemm_backward(const qiddm_plan *plan, const void *collapsed, con
                          t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
 }
 
+// ---- bilinear Upsample -> 1 x 1 QConv2d (nn/unet.py:36-41) in one pass: `img_src` is the (n, C, h_in, w_in) tensor in front of the
+// upsample, `unfold` the geometry of the 1 x 1 convolution on the upsampled (height, width) image.  Direct-convolution layers only.
+static bool up_args_ok(const qiddm_plan *plan, const qiddm_unfold_desc *u, int h_in, int w_in, double sh, double sw) {
+    return qconv_direct(plan, u) && u->kernel_h == 1 && u->kernel_w == 1 && h_in > 0 && w_in > 0 && sh > 0.0 && sw > 0.0;
+}
+
+int qiddm_qconv_up_forward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold, int io_dtype,
+                           const void *img_src, int h_in, int w_in, double scale_h, double scale_w, void *out, void *saved,
+                           int64_t n_images, qiddm_stream_t stream) {
+    if (!plan || !collapsed || n_images < 0) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan) || !unfold_valid(plan, unfold)) return QIDDM_EINVAL;
+    if (!up_args_ok(plan, unfold, h_in, w_in, scale_h, scale_w)) return QIDDM_EUNSUPPORTED;
+    if (n_images == 0) return QIDDM_OK;
+    if (!img_src || !out) return QIDDM_EINVAL;
+    const long long B = n_images * unfold_patches(unfold);
+    if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, unfold, B);
+    gp.io64 = io_dtype == QIDDM_DTYPE_F64 ? 1 : 0;
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    const ConvUp up{h_in, w_in, scale_h, scale_w};
+    return conv_direct_forward(g, gp, gemm_collapsed_wd(g, const_cast<void *>(collapsed)), img_src, out, saved, n_images,
+                               (cudaStream_t)stream, &up);
+}
+
+int qiddm_qconv_up_backward(const qiddm_plan *plan, const void *collapsed, const qiddm_unfold_desc *unfold, int io_dtype,
+                            const void *img_src, int h_in, int w_in, double scale_h, double scale_w, const void *weights,
+                            int weights_dtype, const void *grad_out, const void *saved, void *grad_up, void *grad_weights,
+                            void *workspace, int64_t n_images, qiddm_stream_t stream) {
+    if (!plan || !collapsed || !workspace || !weights || n_images < 1) return QIDDM_EINVAL;
+    if (io_dtype != QIDDM_DTYPE_F32 && io_dtype != QIDDM_DTYPE_F64) return QIDDM_EINVAL;
+    if (!gemm_eligible(plan) || !unfold_valid(plan, unfold)) return QIDDM_EINVAL;
+    if (!up_args_ok(plan, unfold, h_in, w_in, scale_h, scale_w)) return QIDDM_EUNSUPPORTED;
+    if (!img_src || !grad_out || !saved) return QIDDM_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long B = n_images * unfold_patches(unfold);
+    if (B > 0x7fffffffLL - 256) return QIDDM_EUNSUPPORTED;
+    GateParams gp = make_params(plan, unfold, B);
+    gp.io64 = io_dtype == QIDDM_DTYPE_F64 ? 1 : 0;
+    const GemmShape g = gemm_shape(gp, plan->d.n_qubits);
+    const ConvUp up{h_in, w_in, scale_h, scale_w};
+    float *gut = nullptr;
+    int rc = conv_direct_backward(g, gp, gemm_collapsed_wd(g, const_cast<void *>(collapsed)), img_src, grad_out, saved, grad_up, &gut,
+                                  workspace, n_images, s, &up);
+    if (rc != QIDDM_OK) return rc;
+    if (!grad_weights) return QIDDM_OK;
+    qiddm_plan t = basis_plan(plan);
+    char *gate_ws = reinterpret_cast<char *>(workspace) + align_up(conv_direct_ws_bytes(g, gp, n_images));
+    return backward_impl(&t, nullptr, nullptr, nullptr, weights, weights_dtype, gut, nullptr, grad_weights, gate_ws,
+                         t.dim, 0, s, gemm_collapsed_ut(g, const_cast<void *>(collapsed)));
+}
+
 // ----------------------------------------------------------------------------- mid-circuit noise (density matrix)
 static bool noisy_eligible(const qiddm_plan *pl) {
     const qiddm_circuit_desc &d = pl->d;

@@ -47,7 +47,36 @@ struct ConvParams {
     int n_images, C, H, W, F, N, n_out, bands, TH, TC, CS, units, clamp;
     int wr, parts;             // conv_bwd_w_kernel: warps per n-chunk (rows / 32), pixel-row parts
     float add_offset, pad2, post_scale, clamp_lo, clamp_hi;
+    // fused bilinear upsample in front of a 1 x 1 window (nn/unet.py:36-41): `img` is the (n, C, Hin, Win) source and (H, W)
+    // the upsampled size the convolution runs on; source coordinate = max((dst + 0.5) * scale - 0.5, 0) (align_corners = False)
+    int up, Hin, Win;
+    double sh, sw;
 };
+
+// bilinear taps of one upsampled pixel: four source offsets inside a channel plane and their weights
+struct Lerp4 {
+    int o00, o01, o10, o11;
+    float w00, w01, w10, w11;
+};
+__device__ __forceinline__ Lerp4 lerp4_of(const ConvParams &p, int iy, int ix) {
+    double sy = ((double)iy + 0.5) * p.sh - 0.5, sx = ((double)ix + 0.5) * p.sw - 0.5;
+    if (sy < 0.0) sy = 0.0;
+    if (sx < 0.0) sx = 0.0;
+    int y0 = (int)sy, x0 = (int)sx;
+    if (y0 > p.Hin - 1) y0 = p.Hin - 1;
+    if (x0 > p.Win - 1) x0 = p.Win - 1;
+    const int y1 = y0 + (y0 < p.Hin - 1 ? 1 : 0), x1 = x0 + (x0 < p.Win - 1 ? 1 : 0);
+    const double ly1 = sy - (double)y0, lx1 = sx - (double)x0, ly0 = 1.0 - ly1, lx0 = 1.0 - lx1;
+    Lerp4 l;
+    l.o00 = y0 * p.Win + x0; l.o01 = y0 * p.Win + x1; l.o10 = y1 * p.Win + x0; l.o11 = y1 * p.Win + x1;
+    l.w00 = (float)(ly0 * lx0); l.w01 = (float)(ly0 * lx1); l.w10 = (float)(ly1 * lx0); l.w11 = (float)(ly1 * lx1);
+    return l;
+}
+template <typename IO>
+__device__ __forceinline__ float lerp_load(const IO *plane, const Lerp4 &l) {
+    return l.w00 * (float)__ldg(plane + l.o00) + l.w01 * (float)__ldg(plane + l.o01) + l.w10 * (float)__ldg(plane + l.o10) +
+           l.w11 * (float)__ldg(plane + l.o11);
+}
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
@@ -121,8 +150,39 @@ __device__ __forceinline__ void stage_image(const ConvParams &p, const IO *ib, i
     }
 }
 
+// the same tile for a 1 x 1 window on the bilinear upsample of `ib` (n-th image of the (C, Hin, Win) source): the taps of a
+// position are computed once and reused for every channel
+template <typename IO>
+__device__ __forceinline__ void stage_image_up(const ConvParams &p, const IO *ib, int y0, int th, float *tile, int tid, int T) {
+    const int len = th * p.W, HWs = p.Hin * p.Win;
+    for (int i0 = tid; i0 < len; i0 += 2 * T) {
+        Lerp4 l[2];
+        float *dp[2];
+        bool in[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int idx = i0 + k * T;
+            in[k] = idx < len;
+            const int r = idx / p.W, x = idx - r * p.W;
+            l[k] = lerp4_of(p, in[k] ? y0 + r : y0, in[k] ? x : 0);
+            dp[k] = tile + r * p.TC + x;
+        }
+#pragma unroll 2
+        for (int ch = 0; ch < p.C; ++ch) {
+            float v[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) v[k] = lerp_load(ib + (long long)ch * HWs, l[k]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (in[k]) *dp[k] = v[k] + p.add_offset;
+                dp[k] += p.CS;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------ forward
-template <typename IO, int KS, int NP>
+template <typename IO, int KS, int NP, bool UP = false>
 __global__ void __launch_bounds__(256, NP >= 32 ? 2 : 3) conv_fwd_kernel(const ConvParams p) {
     extern __shared__ float4 conv_smem[];
     constexpr int KK = KS * KS, YS = NP + 4;
@@ -136,9 +196,13 @@ __global__ void __launch_bounds__(256, NP >= 32 ? 2 : 3) conv_fwd_kernel(const C
         const int y0 = band * p.TH;
         const int th = min(p.TH, p.H - y0);
         __syncthreads();
-        stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
+        if constexpr (UP) {
+            stage_image_up<IO>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * p.Hin * p.Win, y0, th, tile, tid, T);
+        } else {
+            stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
+        }
         __syncthreads();
-        if (unit + gridDim.x < p.units) {
+        if (!UP && unit + gridDim.x < p.units) {
             const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
             prefetch_image_rows<IO>(reinterpret_cast<const IO *>(p.img) + (long long)nb * p.C * HW, p.C, HW, p.W, max(ny0 - KS / 2, 0),
                                     min(ny0 + min(p.TH, p.H - ny0) + KS / 2, p.H), tid, T);
@@ -249,7 +313,7 @@ __global__ void __launch_bounds__(256) conv_grad_kernel(const ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------- image gradient (gather)
-template <typename IO, int KS, int NP, int CT>
+template <typename IO, int KS, int NP, int CT, bool UP = false>
 __global__ void __launch_bounds__(256, 2) conv_bwd_data_kernel(const ConvParams p) {
     extern __shared__ float4 conv_smem[];
     constexpr int KK = KS * KS, PH = KS / 2, GS = NP + 4, NC = NP < 16 ? NP : 16, NQ = NC / 4;
@@ -339,10 +403,20 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_data_kernel(const ConvParams 
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int pix = y0 * p.W + (ok[k] ? q[k] : 0);
+                if constexpr (UP) {       // the convolution's input is the bilinear upsample of p.img: re-interpolated here
+                    const int iy = pix / p.W;
+                    const Lerp4 l = lerp4_of(p, iy, pix - iy * p.W);
 #pragma unroll
-                for (int ch = 0; ch < CT; ++ch) {
-                    const int c = ct + ch < p.C ? ct + ch : p.C - 1;
-                    fv[k][ch] = (float)__ldg(reinterpret_cast<const IO *>(p.img) + ((long long)b * p.C + c) * HW + pix);
+                    for (int ch = 0; ch < CT; ++ch) {
+                        const int c = ct + ch < p.C ? ct + ch : p.C - 1;
+                        fv[k][ch] = lerp_load(reinterpret_cast<const IO *>(p.img) + ((long long)b * p.C + c) * p.Hin * p.Win, l);
+                    }
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < CT; ++ch) {
+                        const int c = ct + ch < p.C ? ct + ch : p.C - 1;
+                        fv[k][ch] = (float)__ldg(reinterpret_cast<const IO *>(p.img) + ((long long)b * p.C + c) * HW + pix);
+                    }
                 }
             }
 #pragma unroll
@@ -364,7 +438,7 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_data_kernel(const ConvParams 
 }
 
 // ------------------------------------------------------------------------------------------------- weight gradient
-template <typename IO, int KS, int NP>
+template <typename IO, int KS, int NP, bool UP = false>
 __global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) {
     extern __shared__ float4 conv_smem[];
     constexpr int KK = KS * KS, GS = NP + 4, NC = NP < 16 ? NP : 16, NQ = NC / 4;
@@ -398,10 +472,14 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) 
             float4 *dst = reinterpret_cast<float4 *>(gt);
             for (int i = tid; i < npx * (GS / 4); i += T) cp_async16(dst + i, src + i);
         }
-        stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
+        if constexpr (UP) {
+            stage_image_up<IO>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * p.Hin * p.Win, y0, th, tile, tid, T);
+        } else {
+            stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
+        }
         cp_async_wait_all();
         __syncthreads();
-        if (unit + gridDim.x < p.units) {
+        if (!UP && unit + gridDim.x < p.units) {
             const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
             const int nth = min(p.TH, p.H - ny0);
             prefetch_span(p.G + ((long long)nb * HW + ny0 * p.W) * GS, (long long)nth * p.W * GS * 4, tid, T);
@@ -657,7 +735,8 @@ template <typename IO, int KS>
 int conv_forward_t(const ConvParams &p, const ConvTile &t, int NP, cudaStream_t s) {
 #define CALL(NP_)                                                                                   \
     {                                                                                               \
-        auto k = conv_fwd_kernel<IO, KS, NP_>;                                                      \
+        auto k = conv_fwd_kernel<IO, KS, NP_, false>;                                               \
+        if constexpr (KS == 1) { if (p.up) k = conv_fwd_kernel<IO, KS, NP_, true>; }                \
         const int grid = conv_grid(k, t.T, t.smem, p.units, 0);                                     \
         if (grid < 1) return QIDDM_EUNSUPPORTED;                                                    \
         k<<<grid, t.T, t.smem, s>>>(p);                                                             \
@@ -672,12 +751,14 @@ int conv_bwd_data_t(const ConvParams &p, const ConvTile &t, int NP, cudaStream_t
 #define CALL(NP_)                                                                                   \
     {                                                                                               \
         if (t.ct == 8) {                                                                            \
-            auto k = conv_bwd_data_kernel<IO, KS, NP_, 8>;                                          \
+            auto k = conv_bwd_data_kernel<IO, KS, NP_, 8, false>;                                   \
+            if constexpr (KS == 1) { if (p.up) k = conv_bwd_data_kernel<IO, KS, NP_, 8, true>; }    \
             const int grid = conv_grid(k, t.T, t.smem, p.units, 0);                                 \
             if (grid < 1) return QIDDM_EUNSUPPORTED;                                                \
             k<<<grid, t.T, t.smem, s>>>(p);                                                         \
         } else {                                                                                    \
-            auto k = conv_bwd_data_kernel<IO, KS, NP_, 16>;                                         \
+            auto k = conv_bwd_data_kernel<IO, KS, NP_, 16, false>;                                  \
+            if constexpr (KS == 1) { if (p.up) k = conv_bwd_data_kernel<IO, KS, NP_, 16, true>; }   \
             const int grid = conv_grid(k, t.T, t.smem, p.units, 0);                                 \
             if (grid < 1) return QIDDM_EUNSUPPORTED;                                                \
             k<<<grid, t.T, t.smem, s>>>(p);                                                         \
@@ -692,7 +773,8 @@ template <typename IO, int KS>
 int conv_bwd_w_t(ConvParams &p, const ConvTile &t, int NP, int *grid_out, cudaStream_t s) {
 #define CALL(NP_)                                                                                   \
     {                                                                                               \
-        auto k = conv_bwd_w_kernel<IO, KS, NP_>;                                                    \
+        auto k = conv_bwd_w_kernel<IO, KS, NP_, false>;                                             \
+        if constexpr (KS == 1) { if (p.up) k = conv_bwd_w_kernel<IO, KS, NP_, true>; }              \
         const int grid = conv_grid(k, t.T, t.smem, p.units, CONV_MAX_WGRID);                        \
         if (grid < 1) return QIDDM_EUNSUPPORTED;                                                    \
         *grid_out = grid;                                                                           \
@@ -753,12 +835,20 @@ size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp, long long 
 }
 
 // out (NCHW, io dtype); `saved` non-null (training): Y and 1/|f|^2 are kept for conv_direct_backward
+static int conv_set_up(ConvParams &p, const GateParams &gp, const ConvUp *up) {
+    if (up == nullptr || up->h_in <= 0) return QIDDM_OK;
+    if (gp.kh != 1 || up->w_in <= 0 || !(up->scale_h > 0.0) || !(up->scale_w > 0.0)) return QIDDM_EUNSUPPORTED;
+    p.up = 1; p.Hin = up->h_in; p.Win = up->w_in; p.sh = up->scale_h; p.sw = up->scale_w;
+    return QIDDM_OK;
+}
+
 int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, void *out, void *saved,
-                        long long n_images, cudaStream_t s) {
+                        long long n_images, cudaStream_t s, const ConvUp *up) {
     const int NP = conv_np(g.N);
     ConvTile t;
     if (!NP || !conv_tile(g, gp, NP, KIND_FWD, &t)) return QIDDM_EUNSUPPORTED;
     ConvParams p = conv_params(g, gp, t, n_images);
+    if (conv_set_up(p, gp, up) != QIDDM_OK) return QIDDM_EUNSUPPORTED;
     p.img = img; p.out = out; p.Wd = Wd;
     p.Y = reinterpret_cast<float *>(saved);
     timing_begin(TK_CONV_FWD, 2.0 * (double)n_images * gp.H * gp.W * g.F * g.N, s);
@@ -774,7 +864,8 @@ int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *W
 
 // grad_img (nullable, overwritten) and the READ_STATE cotangent gUT (inside `ws`) for the adjoint gate kernel
 int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, const void *grad_out,
-                         const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s) {
+                         const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s,
+                         const ConvUp *up) {
     const int NP = conv_np(g.N);
     ConvTile td, tw;
     if (!NP || saved == nullptr || !conv_tile(g, gp, NP, KIND_DATA, &td) || !conv_tile(g, gp, NP, KIND_W, &tw))
@@ -803,6 +894,7 @@ int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *
     }
     if (grad_img != nullptr) {
         ConvParams p = conv_params(g, gp, td, n_images);
+        if (conv_set_up(p, gp, up) != QIDDM_OK) return QIDDM_EUNSUPPORTED;
         p.img = img; p.gimg = grad_img; p.Wd = Wd; p.G = G;
         if (gp.io64) rc = gp.kh == 3 ? conv_bwd_data_t<double, 3>(p, td, NP, s) : conv_bwd_data_t<double, 1>(p, td, NP, s);
         else rc = gp.kh == 3 ? conv_bwd_data_t<float, 3>(p, td, NP, s) : conv_bwd_data_t<float, 1>(p, td, NP, s);
@@ -811,6 +903,7 @@ int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *
     int wgrid = 0;
     if (rc == QIDDM_OK) {
         ConvParams p = conv_params(g, gp, tw, n_images);
+        if (conv_set_up(p, gp, up) != QIDDM_OK) return QIDDM_EUNSUPPORTED;
         p.img = img; p.G = G; p.partials = partials;
         if (gp.io64) rc = gp.kh == 3 ? conv_bwd_w_t<double, 3>(p, tw, NP, &wgrid, s) : conv_bwd_w_t<double, 1>(p, tw, NP, &wgrid, s);
         else rc = gp.kh == 3 ? conv_bwd_w_t<float, 3>(p, tw, NP, &wgrid, s) : conv_bwd_w_t<float, 1>(p, tw, NP, &wgrid, s);

@@ -93,10 +93,18 @@ int conv_build_wd(const GemmShape &g, const GateParams &gp, const float *UT, flo
 bool conv_direct_supported(const GemmShape &g, const GateParams &gp);
 size_t conv_direct_saved_bytes(const GemmShape &g, const GateParams &gp, long long n_images);
 size_t conv_direct_ws_bytes(const GemmShape &g, const GateParams &gp, long long n_images);
+// `up` (1 x 1 windows only): `img` is the (n, C, h_in, w_in) SOURCE of a bilinear upsample to the unfold geometry's (H, W), the
+// interpolation runs inside the staging of the kernels (nn/unet.py:36-41: Upsample -> 1 x 1 Conv2d); grad_img is then the gradient
+// w.r.t. the UPSAMPLED image (the caller applies the transpose of the interpolation)
+struct ConvUp {
+    int h_in, w_in;
+    double scale_h, scale_w;
+};
 int conv_direct_forward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, void *out, void *saved,
-                        long long n_images, cudaStream_t s);
+                        long long n_images, cudaStream_t s, const ConvUp *up = nullptr);
 int conv_direct_backward(const GemmShape &g, const GateParams &gp, const float *Wd, const void *img, const void *grad_out,
-                         const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s);
+                         const void *saved, void *grad_img, float **gut_out, void *ws, long long n_images, cudaStream_t s,
+                         const ConvUp *up = nullptr);
 
 // qiddm_dm.cu — density-matrix pieces for the mid-circuit noise channels (tau = rho^T, (B, 2^n, 2^n) complex fp32)
 size_t dm_state_bytes(int n_qubits, long long B);

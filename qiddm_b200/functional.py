@@ -105,6 +105,54 @@ def run_qconv(spec: StageSpec, img: torch.Tensor, weights: torch.Tensor, kernel_
     return _QConvFunction.apply(Plan.get(spec), img, weights, unfold)
 
 
+class _QConvUpFunction(torch.autograd.Function):
+    """Bilinear Upsample -> 1 x 1 QConv2d (nn/unet.py:36-41) with the interpolation inside the convolution's staging."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, src: torch.Tensor, weights: torch.Tensor, unfold: UnfoldDesc, scale_h: float, scale_w: float):
+        ctx.plan, ctx.unfold, ctx.scales = plan, unfold, (scale_h, scale_w)
+        ctx.saved_y = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            out, ctx.saved_y = plan.qconv_up_forward(src.detach(), weights, unfold, scale_h, scale_w, save=True)
+        else:
+            out = plan.qconv_up_forward(src.detach(), weights, unfold, scale_h, scale_w)
+        ctx.save_for_backward(src, weights)
+        return out.to(src.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import _lib as L
+        src, weights = ctx.saved_tensors
+        sh, sw = ctx.scales
+        g_up, gw = ctx.plan.qconv_up_backward(src, weights, grad_out, ctx.unfold, sh, sw, ctx.saved_y,
+                                              need_grad_in=ctx.needs_input_grad[1], need_grad_w=ctx.needs_input_grad[2])
+        ctx.saved_y = None
+        gi = None
+        if g_up is not None:      # transpose of the interpolation: gradient of the upsampled image -> gradient of the source
+            n, c, h, w = src.shape
+            gi = torch.empty((n, c, h, w), dtype=g_up.dtype, device=g_up.device)
+            with torch.cuda.device(g_up.device):
+                L.check(L.load_library().qiddm_upsample_bilinear_backward(
+                    L._ptr(g_up), L._ptr(gi), L.DTYPE_F64 if g_up.dtype == torch.float64 else L.DTYPE_F32, n * c, h, w,
+                    ctx.unfold.height, ctx.unfold.width, float(sh), float(sw),
+                    L.C.c_void_p(torch.cuda.current_stream(g_up.device).cuda_stream)), "qiddm_upsample_bilinear_backward")
+            gi = gi.to(src.dtype)
+        return None, gi, (gw.view_as(weights) if gw is not None else None), None, None, None
+
+
+def run_qconv_up(spec: StageSpec, src: torch.Tensor, weights: torch.Tensor, h_out: int, w_out: int, scale_h: float,
+                 scale_w: float):
+    """Upsample(bilinear, align_corners=False) to (h_out, w_out) followed by a 1 x 1 QConv, fused; None when the layer has no
+    direct-convolution form (the caller then runs the two modules)."""
+    if not src.is_cuda or src.dim() != 4 or src.dtype not in (torch.float32, torch.float64) or src.numel() == 0:
+        return None
+    unfold = UnfoldDesc(src.shape[1], h_out, w_out, 1, 1, 0, 0)
+    plan = Plan.get(spec)
+    if not (plan.qconv_direct(unfold) and plan.use_collapse_qconv(unfold, src.shape[0] * h_out * w_out)):
+        return None
+    return _QConvUpFunction.apply(plan, src, weights, unfold, float(scale_h), float(scale_w))
+
+
 class _QConvReferenceMap(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img: torch.Tensor, unfold: UnfoldDesc, out_channels: int):

@@ -1,11 +1,21 @@
 """UNet callers of QConv2d (reference `nn/unet.py:9-190`).  Float64 glue like the reference; the Conv2d factory's
 quantum branch is the B200 QConv2d, and BatchNorm2d / the bilinear Upsample run the library's own kernels on CUDA
 (qiddm_b200.nn.glue: same parameters and state_dict keys as the torch modules)."""
+import os
+
 import torch
 
+from ..functional import run_qconv_up
 from .glue import BatchNorm2d, FusedReLU, MaxPool2d, Upsample, fuse_bn_relu
 from .qconv import QConv2d
 from .utils import autopad, get_label_embedding
+
+
+# Upsample -> 1 x 1 QConv in one pass (functional.run_qconv_up).  Measured on UNetUndirected(3, 8, 3), 64 images: 3.94 ms per step
+# fused against 3.91 ms with the two modules -- the interpolation is redone in the staging of three kernels (forward, weight
+# gradient, normalisation term of the image gradient), which costs what the upsample kernel and its 64 MB tensor saved; the
+# fused form saves that tensor's memory.  Off by default; QIDDM_UPCONV_FUSION=1 turns it on.
+UPCONV_FUSION = os.environ.get("QIDDM_UPCONV_FUSION", "0").lower() in ("1", "true", "yes")
 
 
 def Conv2d(**kwargs):
@@ -37,8 +47,23 @@ class UpBlock(torch.nn.Module):
             FusedReLU(),
         )).double()
 
+    def _up_conv(self, x):
+        """`Upsample -> 1 x 1 Conv2d` (nn/unet.py:36-41); with a quantum convolution that has the direct form the interpolation
+        runs inside the convolution's staging and the upsampled tensor never exists (opt-in: QIDDM_UPCONV_FUSION=1)."""
+        up, conv = self.up_conv[0], self.up_conv[1]
+        if (UPCONV_FUSION and isinstance(up, Upsample) and isinstance(conv, QConv2d) and not conv.reference_forward
+                and conv.kernel_size == (1, 1) and conv.padding == (0, 0) and up.mode == "bilinear" and not up.align_corners
+                and up.size is None and up.scale_factor is not None and not getattr(up, "recompute_scale_factor", None)
+                and x.dim() == 4 and x.shape[1] == conv.in_channels):
+            sf = up.scale_factor
+            fh, fw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
+            out = run_qconv_up(conv._spec(), x, conv.weights, int(x.shape[2] * fh), int(x.shape[3] * fw), 1.0 / fh, 1.0 / fw)
+            if out is not None:
+                return out
+        return self.up_conv(x)
+
     def forward(self, from_down, from_up):
-        from_up = self.up_conv(from_up)
+        from_up = self._up_conv(from_up)
         from_down, from_up = autopad(from_down.double(), from_up.double())
         return self.net(torch.cat([from_up, from_down], dim=1).double())
 

@@ -113,3 +113,58 @@ def test_direct_conv_large_batch_is_deterministic():
         grads.append((m.weights.grad.clone(), xd.grad.clone()))
     assert torch.equal(grads[0][1], grads[1][1])
     assert rel_to_max(grads[0][0], grads[1][0]) <= 1e-6      # the adjoint gate kernel sums a CTA's angle gradients with shared-memory atomics
+
+
+@pytest.mark.parametrize("cfg", [(32, 16, 7, 7, 3), (16, 8, 14, 14, 2), (6, 3, 5, 9, 4), (8, 4, 13, 3, 5)])
+def test_fused_upsample_1x1_qconv_equals_the_two_modules_and_the_oracle(cfg):
+    """`Upsample(scale_factor=2, bilinear) -> 1 x 1 QConv2d` of UpBlock (reference nn/unet.py:36-41) with the interpolation inside the
+    convolution's staging (qiddm_qconv_up_forward / _backward) against the two modules run one after the other, and against
+    torch's interpolation + the oracle's QConv."""
+    from qiddm_b200 import nn
+    from qiddm_b200.functional import run_qconv_up
+    from qiddm_b200.nn.glue import Upsample
+    cin, cout, h, w, n = cfg
+    torch.manual_seed(4)
+    conv = nn.QConv2d(cin, cout, kernel_size=1, padding=0, qdepth=3).cuda()
+    up = Upsample(scale_factor=2, mode="bilinear")
+    x = torch.rand(n, cin, h, w, dtype=torch.float64)
+    g = torch.randn(n, cout, 2 * h, 2 * w, dtype=torch.float64)
+    # oracle: torch's bilinear interpolation, then the restated QConv
+    xr = x.clone().requires_grad_(True)
+    Wr = conv.weights.detach().cpu().clone().requires_grad_(True)
+    ref = O.qconv_forward(torch.nn.functional.interpolate(xr, scale_factor=2, mode="bilinear"), Wr, cout, (1, 1), (0, 0))
+    (ref * g).sum().backward()
+    # the two modules
+    x2 = x.cuda().requires_grad_(True)
+    o2 = conv(up(x2))
+    (o2 * g.cuda()).sum().backward()
+    gw2, gx2 = conv.weights.grad.clone(), x2.grad.clone()
+    # fused
+    conv.weights.grad = None
+    x1 = x.cuda().requires_grad_(True)
+    o1 = run_qconv_up(conv._spec(), x1, conv.weights, 2 * h, 2 * w, 0.5, 0.5)
+    assert o1 is not None and o1.shape == ref.shape and o1.dtype == torch.float64
+    (o1 * g.cuda()).sum().backward()
+    assert rel_to_max(o1, o2) <= 1e-6 and rel_to_max(o1, ref) <= TOL
+    assert rel_to_max(conv.weights.grad, gw2) <= 3e-6 and rel_to_max(conv.weights.grad, Wr.grad) <= GTOL
+    assert rel_to_max(x1.grad, gx2) <= 3e-6 and rel_to_max(x1.grad, xr.grad) <= GTOL
+    with torch.no_grad():
+        assert rel_to_max(run_qconv_up(conv._spec(), x.cuda().float(), conv.weights, 2 * h, 2 * w, 0.5, 0.5).double(), ref) <= TOL
+
+
+def test_unet_with_and_without_the_upsample_fusion(monkeypatch):
+    from qiddm_b200 import nn
+    from qiddm_b200.nn import unet as U
+    torch.manual_seed(1)
+    net = nn.UNetUndirected(3, 8, 3).cuda()
+    x = torch.rand(4, 1, 28, 28, dtype=torch.float64, device="cuda")
+    outs, grads = [], []
+    for fused in (True, False):
+        monkeypatch.setattr(U, "UPCONV_FUSION", fused)
+        net.zero_grad(set_to_none=True)
+        o = net(x)
+        o.square().sum().backward()
+        outs.append(o.detach())
+        grads.append(torch.cat([p.grad.flatten() for p in net.parameters() if p.grad is not None]))
+    assert rel_to_max(outs[0], outs[1]) <= 1e-6
+    assert rel_to_max(grads[0], grads[1]) <= 1e-5
