@@ -30,15 +30,16 @@ __device__ __forceinline__ Lerp lerp_of(int dst, double scale, int in_size) {
     return r;
 }
 
-template <typename T>
+// (I = unsigned when every index fits 32 bits: the 64-bit div / mod per element was the instruction cost of these kernels)
+template <typename T, typename I>
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const T *in, T *out, long long planes, int Hin, int Win, int Hout,
                                                            int Wout, double sh, double sw) {
-    const long long total = planes * Hout * Wout;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % Wout);
-        const long long t = i / Wout;
-        const int oy = (int)(t % Hout);
-        const long long pl = t / Hout;
+    const I total = (I)(planes * Hout * Wout);
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % (I)Wout);
+        const I t = i / (I)Wout;
+        const int oy = (int)(t % (I)Hout);
+        const I pl = t / (I)Hout;
         const Lerp y = lerp_of(oy, sh, Hin), x = lerp_of(ox, sw, Win);
         const T *p = in + pl * Hin * Win;
         const double v = y.l0 * (x.l0 * (double)p[y.i0 * Win + x.i0] + x.l1 * (double)p[y.i0 * Win + x.i1]) +
@@ -48,18 +49,18 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const T *in, T *out, 
 }
 
 // gather form of the transpose: every input pixel sums the output pixels that read it (deterministic, no atomics)
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const T *gout, T *gin, long long planes, int Hin, int Win, int Hout,
                                                            int Wout, double sh, double sw) {
-    const long long total = planes * Hin * Win;
+    const I total = (I)(planes * Hin * Win);
     // output rows that can touch input row iy: (iy - 1) / sh - 1 .. (iy + 1) / sh + 1
     const double ish = 1.0 / sh, isw = 1.0 / sw;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ix = (int)(i % Win);
-        const long long t = i / Win;
-        const int iy = (int)(t % Hin);
-        const long long pl = t / Hin;
-        const T *g = gout + pl * Hout * Wout;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % (I)Win);
+        const I t = i / (I)Win;
+        const int iy = (int)(t % (I)Hin);
+        const I pl = t / (I)Hin;
+        const T *g = gout + pl * (I)(Hout * Wout);
         int oy0 = (int)(((double)iy - 1.0) * ish) - 1, oy1 = (int)(((double)iy + 1.0) * ish) + 1;
         int ox0 = (int)(((double)ix - 1.0) * isw) - 1, ox1 = (int)(((double)ix + 1.0) * isw) + 1;
         if (oy0 < 0) oy0 = 0;
@@ -296,14 +297,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *x, const T *
 
 // MaxPool2d(kernel k, stride k) on (planes, H, W) -> (planes, H / k, W / k) (nn/unet.py:110: MaxPool2d(2, 2)); the backward
 // recomputes the window's first maximum (row-major scan, strict >, as torch's kernel) instead of storing indices
-template <typename T>
-__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T *x, T *y, long long total, int H, int W, int Ho, int Wo, int k) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % Wo);
-        const long long t = i / Wo;
-        const int oy = (int)(t % Ho);
-        const long long pl = t / Ho;
-        const T *src = x + (pl * H + (long long)oy * k) * W + (long long)ox * k;
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T *x, T *y, long long total_, int H, int W, int Ho, int Wo, int k) {
+    const I total = (I)total_;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % (I)Wo);
+        const I t = i / (I)Wo;
+        const int oy = (int)(t % (I)Ho);
+        const I pl = t / (I)Ho;
+        const T *src = x + (pl * (I)H + (I)(oy * k)) * (I)W + (I)(ox * k);
         T m = src[0];
         for (int dy = 0; dy < k; ++dy)
             for (int dx = 0; dx < k; ++dx) {
@@ -313,18 +315,19 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T *x, T *y, long
         y[i] = m;
     }
 }
-template <typename T>
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *x, const T *gy, T *gx, long long total, int H, int W, int Ho,
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *x, const T *gy, T *gx, long long total_, int H, int W, int Ho,
                                                           int Wo, int k) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ix = (int)(i % W);
-        const long long t = i / W;
-        const int iy = (int)(t % H);
-        const long long pl = t / H;
+    const I total = (I)total_;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % (I)W);
+        const I t = i / (I)W;
+        const int iy = (int)(t % (I)H);
+        const I pl = t / (I)H;
         const int oy = iy / k, ox = ix / k;
         T g = (T)0;
         if (oy < Ho && ox < Wo) {
-            const T *src = x + (pl * H + (long long)oy * k) * W + (long long)ox * k;
+            const T *src = x + (pl * (I)H + (I)(oy * k)) * (I)W + (I)(ox * k);
             T m = src[0];
             int arg = 0;
             for (int dy = 0; dy < k; ++dy)
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *x, const T *g
                     const T v = src[(long long)dy * W + dx];
                     if (v > m) { m = v; arg = dy * k + dx; }
                 }
-            if (arg == (iy - oy * k) * k + (ix - ox * k)) g = gy[(pl * Ho + oy) * Wo + ox];
+            if (arg == (iy - oy * k) * k + (ix - ox * k)) g = gy[(pl * (I)Ho + (I)oy) * (I)Wo + (I)ox];
         }
         gx[i] = g;
     }
@@ -492,12 +495,16 @@ inline unsigned ew_grid(long long total) {
 template <typename T>
 int upsample_impl(const void *in, void *out, bool backward, long long planes, int Hin, int Win, int Hout, int Wout, double sh,
                   double sw, cudaStream_t s) {
-    if (backward)   // `in` = grad_out (planes, Hout, Wout), `out` = grad_in (planes, Hin, Win)
-        upsample_bwd_kernel<T><<<ew_grid(planes * Hin * Win), 256, 0, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out),
-                                                                          planes, Hin, Win, Hout, Wout, sh, sw);
-    else
-        upsample_fwd_kernel<T><<<ew_grid(planes * Hout * Wout), 256, 0, s>>>(reinterpret_cast<const T *>(in), reinterpret_cast<T *>(out),
-                                                                            planes, Hin, Win, Hout, Wout, sh, sw);
+    const bool small = planes * Hout * Wout < (1LL << 31) && planes * Hin * Win < (1LL << 31);
+    const T *src = reinterpret_cast<const T *>(in);
+    T *dst = reinterpret_cast<T *>(out);
+    if (backward) {  // `in` = grad_out (planes, Hout, Wout), `out` = grad_in (planes, Hin, Win)
+        // (measured: the gather kernel is SLOWER with 32-bit indices, 85 vs 57 us per launch at 640 x 16 x 28 x 28 -- kept on 64-bit)
+        upsample_bwd_kernel<T, long long><<<ew_grid(planes * Hin * Win), 256, 0, s>>>(src, dst, planes, Hin, Win, Hout, Wout, sh, sw);
+    } else {
+        if (small) upsample_fwd_kernel<T, unsigned><<<ew_grid(planes * Hout * Wout), 256, 0, s>>>(src, dst, planes, Hin, Win, Hout, Wout, sh, sw);
+        else upsample_fwd_kernel<T, long long><<<ew_grid(planes * Hout * Wout), 256, 0, s>>>(src, dst, planes, Hin, Win, Hout, Wout, sh, sw);
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
@@ -708,15 +715,22 @@ int maxpool2d(const void *x, const void *gy, void *out, int dtype, bool backward
     if (Ho < 1 || Wo < 1) return QIDDM_EINVAL;
     if (planes == 0) return QIDDM_OK;
     const long long total = backward ? planes * H * W : planes * Ho * Wo;
+    const bool small = planes * H * W < (1LL << 31);
+#define QIDDM_POOL(T, I)                                                                                                            \
+    do {                                                                                                                            \
+        if (backward) maxpool_bwd_kernel<T, I><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<const T *>(gy), \
+                                                                              reinterpret_cast<T *>(out), total, H, W, Ho, Wo, k); \
+        else maxpool_fwd_kernel<T, I><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const T *>(x), reinterpret_cast<T *>(out), total, H, W, \
+                                                                     Ho, Wo, k);                                                   \
+    } while (0)
     if (dtype == QIDDM_DTYPE_F64) {
-        if (backward) maxpool_bwd_kernel<double><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const double *>(x), reinterpret_cast<const double *>(gy), reinterpret_cast<double *>(out), total, H, W, Ho, Wo, k);
-        else maxpool_fwd_kernel<double><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const double *>(x), reinterpret_cast<double *>(out), total, H, W, Ho, Wo, k);
+        if (small) QIDDM_POOL(double, unsigned); else QIDDM_POOL(double, long long);
     } else if (dtype == QIDDM_DTYPE_F32) {
-        if (backward) maxpool_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float *>(x), reinterpret_cast<const float *>(gy), reinterpret_cast<float *>(out), total, H, W, Ho, Wo, k);
-        else maxpool_fwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float *>(x), reinterpret_cast<float *>(out), total, H, W, Ho, Wo, k);
+        if (small) QIDDM_POOL(float, unsigned); else QIDDM_POOL(float, long long);
     } else {
         return QIDDM_EINVAL;
     }
+#undef QIDDM_POOL
     count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
