@@ -10,7 +10,7 @@
 // matrix (320 B per patch and pass at F = 72 against 64 B of image), the gate path simulates every patch gate by gate.
 // Here a CTA stages a band of image rows (with halo) in shared memory once and every thread keeps the N accumulators of
 // two patches in registers; the FP32 FMA pipe is the bound (F N FMAs per patch and pass), the image is read once.
-// Every kernel is persistent over (image, band) units; shared-memory footprints are kept small enough for three or more
+// Every kernel is persistent over (image, band) units; shared-memory footprints and register counts leave two to three
 // CTAs per SM, whose staging and compute phases overlap (measured: an explicit cp.async pipeline with raw staging buffers
 // lost more to the lower occupancy than it gained, profiles/r2c_conv_summary.md).
 //
@@ -85,23 +85,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void *gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem)); }
-
-// A CTA knows its next (image, band) unit: while it computes the current one, the next one's rows are pulled into L2, so the
-// staging loads of the next iteration see L2 latency instead of DRAM latency (they are the exposed latency of these kernels).
-template <typename IO>
-__device__ __forceinline__ void prefetch_image_rows(const IO *ib, int C, int HW, int W, int lo, int hi, int tid, int T) {
-    const int bytes = (hi - lo) * W * (int)sizeof(IO);
-    const int lines = (bytes + 127) >> 7;
-    for (int i = tid; i < C * lines; i += T) {
-        const int ch = i / lines, l = i - ch * lines;
-        prefetch_l2(reinterpret_cast<const char *>(ib + (long long)ch * HW + lo * W) + (l << 7));
-    }
-}
-__device__ __forceinline__ void prefetch_span(const void *base, long long bytes, int tid, int T) {
-    const int lines = (int)((bytes + 127) >> 7);
-    for (int i = tid; i < lines; i += T) prefetch_l2(reinterpret_cast<const char *>(base) + ((long long)i << 7));
-}
 
 // band of image rows [y0 - PH, y0 + th + PH) x columns [-PH, W + PH) of all channels, + add_offset (the zero padding of
 // torch.nn.Unfold becomes add_offset: the reference adds 0.1 to the unfolded patch).  The rows that exist are one contiguous
@@ -202,11 +185,6 @@ __global__ void __launch_bounds__(256, NP >= 32 ? 2 : 3) conv_fwd_kernel(const C
             stage_image<IO, KS>(p, reinterpret_cast<const IO *>(p.img) + (long long)b * p.C * HW, y0, th, tile, tid, T);
         }
         __syncthreads();
-        if (!UP && unit + gridDim.x < p.units) {
-            const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
-            prefetch_image_rows<IO>(reinterpret_cast<const IO *>(p.img) + (long long)nb * p.C * HW, p.C, HW, p.W, max(ny0 - KS / 2, 0),
-                                    min(ny0 + min(p.TH, p.H - ny0) + KS / 2, p.H), tid, T);
-        }
         const int npx = th * p.W;
         int q[2], base[2];
         bool ok[2];
@@ -343,11 +321,6 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_data_kernel(const ConvParams 
         }
         cp_async_wait_all();
         __syncthreads();
-        if (unit + gridDim.x < p.units) {
-            const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
-            const int lo = max(ny0 - PH, 0), hi = min(ny0 + min(p.TH, p.H - ny0) + PH, p.H);
-            prefetch_span(p.G + ((long long)nb * HW + lo * p.W) * GS, (long long)(hi - lo) * p.W * GS * 4, tid, T);
-        }
         const int npx = th * p.W;
         int q[2], gbase[2];
         bool ok[2];
@@ -479,13 +452,6 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_w_kernel(const ConvParams p) 
         }
         cp_async_wait_all();
         __syncthreads();
-        if (!UP && unit + gridDim.x < p.units) {
-            const int nu = unit + gridDim.x, nb = nu / p.bands, ny0 = (nu - nb * p.bands) * p.TH;
-            const int nth = min(p.TH, p.H - ny0);
-            prefetch_span(p.G + ((long long)nb * HW + ny0 * p.W) * GS, (long long)nth * p.W * GS * 4, tid, T);
-            prefetch_image_rows<IO>(reinterpret_cast<const IO *>(p.img) + (long long)nb * p.C * HW, p.C, HW, p.W, max(ny0 - KS / 2, 0),
-                                    min(ny0 + nth + KS / 2, p.H), tid, T);
-        }
         {   // bias row: column sums of G, kept per thread until the end of the launch
             const int n = tid % NP, sub = tid / NP, nsub = T / NP;
             if (sub < nsub)
