@@ -298,7 +298,7 @@ int qiddm_skinny_linear_backward(const void *x, const void *weight, const void *
 /* Diffusion-step glue.  qiddm_noise_ladder = src/noise.py:105-126 (`add_normal_noise_multiple`) fused with the slicing of
  * src/models.py:50-63: for x, eps (batch, pixels) (eps float32 as the reference draws it) and the level weights w[tau]
  * (tensor dtype), level_t = clamp(x (1 - w_t) + eps w_t, 0, 1); writes noisy[(b, t)] = level_{t+1} and clean[(b, t)] =
- * level_t for t < tau - 1, both (batch * (tau - 1), pixels).  qiddm_mse_loss_grad = MSELoss + `.mean().backward()` seed
+ * level_t for t < tau - 1, both (batch * (tau - 1), pixels); clean may be NULL.  qiddm_mse_loss_grad = MSELoss + `.mean().backward()` seed
  * (src/models.py:65-67, :95-99): d = scale * pred + shift - target (+ target_add when non-NULL); loss[0] = mean(d^2),
  * grad = 2 scale d / n (deterministic two-stage sum).  workspace: qiddm_mse_workspace_bytes(). */
 int qiddm_noise_ladder(const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels, int tau,
@@ -306,6 +306,13 @@ int qiddm_noise_ladder(const void *x, const float *eps, const void *w, int dtype
 size_t qiddm_mse_workspace_bytes(void);
 int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target_add, int dtype, double scale, double shift,
                         int64_t n, void *grad, void *loss, void *workspace, qiddm_stream_t stream);
+/* The same loss with the target recomputed from the image and its noise draw (`clean` of qiddm_noise_ladder may then be NULL):
+ * row (b, t) of pred (batch * (tau - 1), pixels): d = scale * pred + shift - (c0 * level_t + c1 * level_{t+1}); goal "data"
+ * (src/models.py:65-67): c0 = 1, c1 = 0; goal "noise" (:95-99): scale 0.1, shift -0.05, c0 = -1, c1 = 1.  The pass reads pred and
+ * (x, eps) once per tau - 1 rows instead of pred and one or two ladder tensors. */
+int qiddm_mse_ladder_loss_grad(const void *pred, const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels,
+                               int tau, double scale, double shift, double c0, double c1, void *grad, void *loss, void *workspace,
+                               qiddm_stream_t stream);
 
 /* Noise channels right before a probability readout (the `add_noise` branch of nn/qdense.py:98-104, :174-180, :431-439,
  * run on `default.mixed` by src/mnist_noise.py:211-229): the same single-qubit channel on every wire immediately before

@@ -817,6 +817,13 @@ int qiddm_mse_loss_grad(const void *pred, const void *target, const void *target
     return qiddm::mse_loss_grad(pred, target, target_add, dtype, scale, shift, n, grad, loss, workspace, (cudaStream_t)stream);
 }
 
+int qiddm_mse_ladder_loss_grad(const void *pred, const void *x, const float *eps, const void *w, int dtype, int64_t batch, int pixels,
+                               int tau, double scale, double shift, double c0, double c1, void *grad, void *loss, void *workspace,
+                               qiddm_stream_t stream) {
+    return qiddm::mse_ladder_loss_grad(pred, x, eps, w, dtype, batch, pixels, tau, scale, shift, c0, c1, grad, loss, workspace,
+                                       (cudaStream_t)stream);
+}
+
 int qiddm_readout_channel(const void *probs_in, void *probs_out, int dtype, int64_t batch, int n_qubits, double m00, double m01,
                           double m10, double m11, qiddm_stream_t stream) {
     return qiddm::prob_channel(probs_in, probs_out, dtype, batch, n_qubits, m00, m01, m10, m11, (cudaStream_t)stream);

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256) noise_ladder_kernel(const T *x, const flo
             if (t > 0) {
                 const long long o = (b * steps + (t - 1)) * P + p;
                 noisy[o] = v;
-                clean[o] = prev;
+                if (clean != nullptr) clean[o] = prev;
             }
             prev = v;
         }
@@ -400,6 +400,56 @@ __global__ void mse_finalize_kernel(const double *partial, int n_partial, long l
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (threadIdx.x == 0) loss[0] = (T)(s / (double)n);
+}
+
+// The same loss with the target RECOMPUTED from the image and its noise draw instead of read from a materialised ladder:
+// row (b, t) of pred, t < T = tau - 1:  d = a pred + b - (c0 level_t + c1 level_{t+1}),  level_t = clamp(x (1 - w_t) + eps w_t, 0, 1)
+// evaluated exactly as noise_ladder_kernel does.  Goal "data": c0 = 1, c1 = 0; goal "noise": a = 0.1, b = -0.05, c0 = -1, c1 = 1.
+// Reads pred + (x, eps) / T instead of pred + one or two ladder tensors: a third to a half of the pass's bytes.
+template <typename T>
+__global__ void __launch_bounds__(256) mse_ladder_grad_kernel(const T *r, const T *x, const float *eps, const T *w, long long batch,
+                                                              int P, int steps, double a, double b, double c0, double c1, T *grad,
+                                                              double *partial) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    const long long n_bp = batch * P;
+    const double k = 2.0 * a / ((double)n_bp * (double)steps);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bp; i += (long long)gridDim.x * blockDim.x) {
+        const long long bi = i / P;
+        const int p = (int)(i - bi * P);
+        const T xv = __ldg(x + i), ev = (T)__ldg(eps + i);
+        const T *rp = r + bi * steps * P + p;
+        T *gp = grad + bi * steps * P + p;
+        const T w0 = __ldg(w);
+        T prev = xv * ((T)1 - w0) + ev * w0;                             // level_0
+        prev = prev < (T)0 ? (T)0 : (prev > (T)1 ? (T)1 : prev);
+        for (int t0 = 0; t0 < steps; t0 += 4) {                          // rows t0 .. t0 + 3: four loads of pred in flight
+            T rv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = t0 + j < steps ? __ldg(rp + (long long)(t0 + j) * P) : (T)0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (t0 + j < steps) {
+                    const T wt = __ldg(w + t0 + j + 1);
+                    T v = xv * ((T)1 - wt) + ev * wt;
+                    v = v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+                    const double d = a * (double)rv[j] + b - (c0 * (double)prev + c1 * (double)v);
+                    acc += d * d;
+                    gp[(long long)(t0 + j) * P] = (T)(k * d);
+                    prev = v;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        partial[blockIdx.x] = s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -569,6 +619,20 @@ int mse_impl(const void *r, const void *t1, const void *t2, double a, double b, 
     return e == cudaSuccess ? QIDDM_OK : (int)e;
 }
 
+template <typename T>
+int mse_ladder_impl(const void *r, const void *x, const float *eps, const void *w, long long batch, int P, int tau, double a,
+                    double b, double c0, double c1, void *grad, void *loss, double *ws, cudaStream_t s) {
+    const long long n_bp = batch * P;
+    const int blocks = (int)((n_bp + 255) / 256 < MSE_BLOCKS ? (n_bp + 255) / 256 : MSE_BLOCKS);
+    mse_ladder_grad_kernel<T><<<blocks, 256, 0, s>>>(reinterpret_cast<const T *>(r), reinterpret_cast<const T *>(x), eps,
+                                                     reinterpret_cast<const T *>(w), batch, P, tau - 1, a, b, c0, c1,
+                                                     reinterpret_cast<T *>(grad), ws);
+    mse_finalize_kernel<T><<<1, 32, 0, s>>>(ws, blocks, n_bp * (tau - 1), reinterpret_cast<T *>(loss));
+    count_launch(2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+
 }  // namespace
 
 int prob_channel(const void *p_in, void *p_out, int dtype, long long batch, int n, double m00, double m01, double m10, double m11,
@@ -655,7 +719,7 @@ size_t mse_ws_bytes() { return (size_t)MSE_BLOCKS * sizeof(double); }
 
 int noise_ladder(const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau, void *noisy,
                  void *clean, cudaStream_t s) {
-    if (!x || !eps || !w || !noisy || !clean || batch < 0 || P < 1 || tau < 2) return QIDDM_EINVAL;
+    if (!x || !eps || !w || !noisy || batch < 0 || P < 1 || tau < 2) return QIDDM_EINVAL;       // clean may be NULL
     if (batch == 0) return QIDDM_OK;
     if (dtype == QIDDM_DTYPE_F64) return ladder_impl<double>(x, eps, w, batch, P, tau, noisy, clean, s);
     if (dtype == QIDDM_DTYPE_F32) return ladder_impl<float>(x, eps, w, batch, P, tau, noisy, clean, s);
@@ -667,6 +731,16 @@ int mse_loss_grad(const void *r, const void *t1, const void *t2, int dtype, doub
     if (!r || !t1 || !grad || !loss || !ws || n < 1) return QIDDM_EINVAL;
     if (dtype == QIDDM_DTYPE_F64) return mse_impl<double>(r, t1, t2, a, b, n, grad, loss, reinterpret_cast<double *>(ws), s);
     if (dtype == QIDDM_DTYPE_F32) return mse_impl<float>(r, t1, t2, a, b, n, grad, loss, reinterpret_cast<double *>(ws), s);
+    return QIDDM_EINVAL;
+}
+
+int mse_ladder_loss_grad(const void *r, const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau,
+                         double a, double b, double c0, double c1, void *grad, void *loss, void *ws, cudaStream_t s) {
+    if (!r || !x || !eps || !w || !grad || !loss || !ws || batch < 1 || P < 1 || tau < 2) return QIDDM_EINVAL;
+    if (dtype == QIDDM_DTYPE_F64)
+        return mse_ladder_impl<double>(r, x, eps, w, batch, P, tau, a, b, c0, c1, grad, loss, reinterpret_cast<double *>(ws), s);
+    if (dtype == QIDDM_DTYPE_F32)
+        return mse_ladder_impl<float>(r, x, eps, w, batch, P, tau, a, b, c0, c1, grad, loss, reinterpret_cast<double *>(ws), s);
     return QIDDM_EINVAL;
 }
 

@@ -130,6 +130,8 @@ int noise_ladder(const void *x, const float *eps, const void *w, int dtype, long
                  void *clean, cudaStream_t s);
 int mse_loss_grad(const void *r, const void *t1, const void *t2, int dtype, double a, double b, long long n, void *grad,
                   void *loss, void *ws, cudaStream_t s);
+int mse_ladder_loss_grad(const void *r, const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau,
+                         double a, double b, double c0, double c1, void *grad, void *loss, void *ws, cudaStream_t s);
 int upsample_bilinear(const void *in, void *out, int dtype, bool backward, long long planes, int Hin, int Win, int Hout, int Wout,
                       double scale_h, double scale_w, cudaStream_t s);
 int batchnorm_forward(const void *x, void *y, int dtype, int N, int C, int HW, const void *gamma, const void *beta,

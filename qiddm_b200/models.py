@@ -27,16 +27,30 @@ class Diffusion(torch.nn.Module):
             return self.run_training_step_noise(x, **kwargs)
         return self.sample(first_x=x, **kwargs)
 
-    def _ladder(self, x: torch.Tensor, T: int):
+    def _ladder(self, x: torch.Tensor, T: int, want_clean: bool = True):
         """src/models.py:46-63: (batch, T+1, pixels) ladder -> noisy = steps 1..T, clean = steps 0..T-1.
-        On CUDA with the reference schedule the pair comes out of one kernel (noise.ladder_pair)."""
+        On CUDA with the reference schedule the pair comes out of one kernel (noise.ladder_pair); with `want_clean=False`
+        only `noisy` is written and the third return value is the draw (images, eps, level weights) from which the loss
+        kernel recomputes its target.  Returns (noisy, clean or None, draw or None)."""
         shape = (-1, 1, self.width, self.height)
         if (x.is_cuda and self.add_noise is _noise.add_normal_noise_multiple
                 and x.dtype in (torch.float32, torch.float64) and x.dim() == 2):
-            noisy, clean = _noise.ladder_pair(x, T, decay_mod=3.0)
-            return noisy.reshape(shape), clean.reshape(shape)
+            noisy, clean, draw = _noise.ladder_pair(x, T, decay_mod=3.0, want_clean=want_clean, return_draw=True)
+            return noisy.reshape(shape), (clean.reshape(shape) if clean is not None else None), draw
         whole = self.add_noise(x, tau=T + 1, decay_mod=3.0).reshape(-1, T + 1, x.shape[-1])
-        return whole[:, 1:, :].reshape(shape), whole[:, :-1, :].reshape(shape)
+        return whole[:, 1:, :].reshape(shape), whole[:, :-1, :].reshape(shape), None
+
+    def _recompute_target(self, x: torch.Tensor, verbose: bool) -> bool:
+        """The loss kernel can recompute the clean ladder levels from the images and the noise draw (no `clean` tensor: a third
+        to a half of the ladder's and the loss pass's bytes).  QIDDM_MSE_LADDER=0 switches it off."""
+        return (not verbose and os.environ.get("QIDDM_MSE_LADDER", "1") != "0" and x.is_cuda and x.dim() == 2
+                and self.add_noise is _noise.add_normal_noise_multiple and x.dtype in (torch.float32, torch.float64)
+                and type(self.loss) is torch.nn.MSELoss and self.loss.reduction in ("mean", "none"))
+
+    def _clean_of(self, x, T, draw):
+        """The clean levels after all (the net's output cannot take the fused loss): same draw, same kernel."""
+        _, clean = _noise.ladder_pair(x, T, decay_mod=3.0, eps=draw[1])
+        return clean.reshape(-1, 1, self.width, self.height)
 
     def _fused_mse(self, recon: torch.Tensor, verbose: bool) -> bool:
         """MSELoss followed by `.mean().backward()` == one kernel giving the loss and d loss / d recon."""
@@ -58,12 +72,19 @@ class Diffusion(torch.nn.Module):
         loss = self._fused_step(x, kwargs)
         if loss is not None:
             return (loss.abs(),)
-        noisy, clean = self._ladder(x, kwargs["T"])
+        T, verbose = kwargs["T"], kwargs.get("verbose", False)
+        noisy, clean, draw = self._ladder(x, T, want_clean=not self._recompute_target(x, verbose))
         recon = self.net.forward(x=noisy)
-        if self._fused_mse(recon, kwargs.get("verbose", False)):
-            loss, grad = _noise.mse_loss_and_grad(recon, clean)
+        if self._fused_mse(recon, verbose):
+            if clean is None and recon.dtype == x.dtype and recon.numel() == noisy.numel():
+                loss, grad = _noise.mse_ladder_loss_and_grad(recon, draw, T)                  # target = level_t
+            else:
+                clean = clean if clean is not None else self._clean_of(x, T, draw)
+                loss, grad = _noise.mse_loss_and_grad(recon, clean)
             recon.backward(grad)
             return (loss.abs(),)
+        if clean is None:
+            clean = self._clean_of(x, T, draw)
         batch_loss = self.loss(recon, clean)
         batch_loss_mean = batch_loss.mean()
         batch_loss_mean.backward()
@@ -75,13 +96,20 @@ class Diffusion(torch.nn.Module):
         loss = self._fused_step(x, kwargs)
         if loss is not None:
             return (loss,)
-        noisy, clean = self._ladder(x, kwargs["T"])
+        T, verbose = kwargs["T"], kwargs.get("verbose", False)
+        noisy, clean, draw = self._ladder(x, T, want_clean=not self._recompute_target(x, verbose))
         out = self.net.forward(x=noisy)
-        if self._fused_mse(out, kwargs.get("verbose", False)):
-            # predicted_noise = (out - 0.5) * 0.1, target = noisy - clean
-            loss, grad = _noise.mse_loss_and_grad(out, noisy.reshape(out.shape), clean.reshape(out.shape), scale=0.1, shift=-0.05)
+        if self._fused_mse(out, verbose):
+            # predicted_noise = (out - 0.5) * 0.1, target = noisy - clean = level_{t+1} - level_t
+            if clean is None and out.dtype == x.dtype and out.numel() == noisy.numel():
+                loss, grad = _noise.mse_ladder_loss_and_grad(out, draw, T, scale=0.1, shift=-0.05, c0=-1.0, c1=1.0)
+            else:
+                clean = clean if clean is not None else self._clean_of(x, T, draw)
+                loss, grad = _noise.mse_loss_and_grad(out, noisy.reshape(out.shape), clean.reshape(out.shape), scale=0.1, shift=-0.05)
             out.backward(grad)
             return (loss,)
+        if clean is None:
+            clean = self._clean_of(x, T, draw)
         predicted_noise = (out - 0.5) * 0.1
         batch_loss = self.loss(predicted_noise, noisy - clean)
         batch_loss_mean = batch_loss.mean()

@@ -23,10 +23,13 @@ def _level_weights(tau: int, decay_mod: float, device, dtype) -> torch.Tensor:
     return (w / w.max()).to(dtype)
 
 
-def ladder_pair(data: torch.Tensor, T: int, decay_mod: float = 3.0, eps: torch.Tensor = None):
+def ladder_pair(data: torch.Tensor, T: int, decay_mod: float = 3.0, eps: torch.Tensor = None, want_clean: bool = True,
+                return_draw: bool = False):
     """(noisy, clean) of the training step in one kernel launch (qiddm_noise_ladder): the tau = T + 1 level ladder of
     `add_normal_noise_multiple` (src/noise.py:105-126) written directly as noisy = levels 1..T and clean = levels 0..T-1,
-    each ((batch T), pixels) batch-major -- what src/models.py:46-63 slices out of the full ladder.  CUDA tensors only."""
+    each ((batch T), pixels) batch-major -- what src/models.py:46-63 slices out of the full ladder.  CUDA tensors only.
+    `want_clean=False`: only `noisy` is materialised (clean = None); `return_draw`: also (images, eps, level weights), from
+    which mse_ladder_loss_and_grad recomputes the target."""
     import ctypes as C
     from . import _lib as L
     if not data.is_cuda:
@@ -41,13 +44,40 @@ def ladder_pair(data: torch.Tensor, T: int, decay_mod: float = 3.0, eps: torch.T
     dt = {torch.float32: L.DTYPE_F32, torch.float64: L.DTYPE_F64}[data.dtype]
     w = _level_weights(T + 1, decay_mod, data.device, data.dtype)
     noisy = torch.empty((batch * T, pixels), dtype=data.dtype, device=data.device)
-    clean = torch.empty_like(noisy)
+    clean = torch.empty_like(noisy) if want_clean else None
     with torch.cuda.device(data.device):
         L.check(L.load_library().qiddm_noise_ladder(L._ptr(data), L._ptr(eps), L._ptr(w), dt, batch, pixels, T + 1,
                                                     L._ptr(noisy), L._ptr(clean),
                                                     C.c_void_p(torch.cuda.current_stream(data.device).cuda_stream)),
                 "qiddm_noise_ladder")
+    if return_draw:
+        return noisy, clean, (data, eps, w)
     return noisy, clean
+
+
+def mse_ladder_loss_and_grad(pred: torch.Tensor, draw, T: int, scale: float = 1.0, shift: float = 0.0, c0: float = 1.0,
+                             c1: float = 0.0):
+    """loss = mean((scale * pred + shift - (c0 level_t + c1 level_{t+1}))^2) and d loss / d pred with the ladder levels
+    recomputed from `draw` = (images, eps, level weights) of ladder_pair(..., return_draw=True) (qiddm_mse_ladder_loss_grad):
+    goal "data" c0 = 1, c1 = 0 (src/models.py:65-67); goal "noise" scale 0.1, shift -0.05, c0 = -1, c1 = 1 (:95-99)."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load_library()
+    data, eps, w = draw
+    pred_c = pred.detach().contiguous()
+    batch, pixels = data.shape
+    if pred_c.numel() != batch * T * pixels or pred_c.dtype != data.dtype:
+        raise L.QiddmError(f"mse_ladder_loss_and_grad: pred {tuple(pred_c.shape)} {pred_c.dtype} vs {batch} x {T} x {pixels} {data.dtype}")
+    dt = {torch.float32: L.DTYPE_F32, torch.float64: L.DTYPE_F64}[pred_c.dtype]
+    grad = torch.empty_like(pred_c)
+    loss = torch.empty((), dtype=pred_c.dtype, device=pred_c.device)
+    ws = torch.empty(int(lib.qiddm_mse_workspace_bytes()), dtype=torch.uint8, device=pred_c.device)
+    with torch.cuda.device(pred_c.device):
+        L.check(lib.qiddm_mse_ladder_loss_grad(L._ptr(pred_c), L._ptr(data), L._ptr(eps), L._ptr(w), dt, batch, pixels, T + 1,
+                                               float(scale), float(shift), float(c0), float(c1), L._ptr(grad), L._ptr(loss),
+                                               L._ptr(ws), C.c_void_p(torch.cuda.current_stream(pred_c.device).cuda_stream)),
+                "qiddm_mse_ladder_loss_grad")
+    return loss, grad
 
 
 def mse_loss_and_grad(pred: torch.Tensor, target: torch.Tensor, target_add: torch.Tensor = None, scale: float = 1.0,

@@ -134,6 +134,45 @@ def test_fused_mse_loss_and_grad_matches_torch(dtype, tol):
     assert abs(loss.item() - ref.item()) <= tol * ref.item() and rel_to_max(grad, p.grad) <= tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-13), (torch.float32, 1e-5)])
+def test_mse_with_the_target_recomputed_from_the_noise_draw(dtype, tol):
+    """noise.mse_ladder_loss_and_grad (no `clean` tensor: the ladder levels are recomputed from images + eps) == the loss over
+    the materialised ladder, both goals (src/models.py:65-67, :95-99); the clean-less ladder writes the same `noisy`."""
+    from qiddm_b200 import noise
+    torch.manual_seed(5)
+    T = 7
+    x = torch.rand(9, 33, dtype=dtype, device="cuda") * 1.4 - 0.2          # some levels hit the clamp
+    eps = torch.normal(0.5, 0.2, size=(9, 33), device="cuda")
+    noisy, clean = noise.ladder_pair(x, T, 3.0, eps=eps)
+    noisy2, none, draw = noise.ladder_pair(x, T, 3.0, eps=eps, want_clean=False, return_draw=True)
+    assert none is None and torch.equal(noisy, noisy2)
+    pred = torch.rand(9 * T, 33, dtype=dtype, device="cuda")
+    l_ref, g_ref = noise.mse_loss_and_grad(pred, clean)
+    l_new, g_new = noise.mse_ladder_loss_and_grad(pred, draw, T)
+    assert abs(l_new.item() - l_ref.item()) <= tol * l_ref.item() and rel_to_max(g_new, g_ref) <= tol
+    l_ref, g_ref = noise.mse_loss_and_grad(pred, noisy, clean, scale=0.1, shift=-0.05)
+    l_new, g_new = noise.mse_ladder_loss_and_grad(pred, draw, T, scale=0.1, shift=-0.05, c0=-1.0, c1=1.0)
+    assert abs(l_new.item() - l_ref.item()) <= tol * l_ref.item() and rel_to_max(g_new, g_ref) <= tol
+
+
+def test_diffusion_step_with_and_without_the_recomputed_target(monkeypatch):
+    from qiddm_b200 import models, nn, noise
+    for goal in ("data", "noise"):
+        res = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("QIDDM_MSE_LADDER", flag)
+            torch.manual_seed(3)
+            net = nn.QIDDM_LL_noise(64, 4, 3, 2)
+            d = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (8, 8), torch.nn.MSELoss()).to("cuda", torch.float64)
+            d.train()
+            x = torch.rand(5, 64, dtype=torch.float64, device="cuda")
+            torch.manual_seed(11)
+            (loss,) = d(x=x, T=6)
+            res.append((loss.item(), torch.cat([p.grad.flatten() for p in net.parameters()])))
+        assert abs(res[0][0] - res[1][0]) <= 1e-12 * abs(res[1][0])
+        assert rel_to_max(res[0][1], res[1][1]) <= 1e-9
+
+
 def test_diffusion_step_fused_glue_equals_torch_glue():
     """Diffusion.forward with the fused ladder + MSE kernels vs the same step through the torch ops (custom add_noise /
     verbose path), both goals: same loss and parameter gradients."""
