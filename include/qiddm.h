@@ -314,6 +314,17 @@ int qiddm_mse_ladder_loss_grad(const void *pred, const void *x, const float *eps
                                int tau, double scale, double shift, double c0, double c1, void *grad, void *loss, void *workspace,
                                qiddm_stream_t stream);
 
+/* Tail of the re-upload families' training step in one pass: `linear_up` (nn/qdense.py:642, :676: Linear(hidden -> pixels)) +
+ * MSELoss + `.mean().backward()` (src/models.py:65-67, :95-99) with the target recomputed from the noise draw as in
+ * qiddm_mse_ladder_loss_grad.  h (batch * (tau - 1), hidden <= 16), weight (pixels, hidden), bias (pixels, may be NULL), x / eps
+ * (batch, pixels), w[tau]; writes loss[0], grad_weight (pixels, hidden), grad_bias (pixels, may be NULL) and grad_h (like h, may be
+ * NULL).  Neither the layer's output nor its gradient (batch * (tau - 1) x pixels each) is materialised.  Deterministic. */
+size_t qiddm_linear_up_mse_workspace_bytes(int pixels, int hidden);
+int qiddm_linear_up_mse_step(const void *h, const void *weight, const void *bias, const void *x, const float *eps, const void *w,
+                             int dtype, int64_t batch, int pixels, int tau, int hidden, double scale, double shift, double c0,
+                             double c1, void *loss, void *grad_weight, void *grad_bias, void *grad_h, void *workspace,
+                             qiddm_stream_t stream);
+
 /* Noise channels right before a probability readout (the `add_noise` branch of nn/qdense.py:98-104, :174-180, :431-439,
  * run on `default.mixed` by src/mnist_noise.py:211-229): the same single-qubit channel on every wire immediately before
  * probs() acts on the probability vector as p' = (M x ... x M) p with one 2 x 2 column-stochastic M = [[m00, m01], [m10,

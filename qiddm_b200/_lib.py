@@ -50,7 +50,7 @@ EXPORTS = [
     "qiddm_gemm_supported", "qiddm_gemm_collapsed_bytes", "qiddm_gemm_workspace_bytes", "qiddm_gemm_prepare",
     "qiddm_gemm_forward", "qiddm_gemm_backward", "qiddm_gemm_saved_bytes", "qiddm_timing_enable",
     "qiddm_timing_collect", "qiddm_qconv_gemm_saved_bytes", "qiddm_qconv_gemm_workspace_bytes",
-    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported", "qiddm_gemm_prepare_direct", "qiddm_qconv_up_forward", "qiddm_qconv_up_backward", "qiddm_mse_ladder_loss_grad",
+    "qiddm_qconv_gemm_forward", "qiddm_qconv_gemm_backward", "qiddm_stream_capture_id", "qiddm_qconv_direct_supported", "qiddm_gemm_prepare_direct", "qiddm_qconv_up_forward", "qiddm_qconv_up_backward", "qiddm_mse_ladder_loss_grad", "qiddm_linear_up_mse_workspace_bytes", "qiddm_linear_up_mse_step",
     "qiddm_sym_eigh_max_dim", "qiddm_sym_eigh_f64", "qiddm_sym_eigh_f64_batched", "qiddm_upsample_bilinear_forward",
     "qiddm_upsample_bilinear_backward", "qiddm_batchnorm_workspace_bytes", "qiddm_batchnorm_forward",
     "qiddm_batchnorm_backward", "qiddm_noise_ladder", "qiddm_mse_workspace_bytes", "qiddm_mse_loss_grad",
@@ -156,6 +156,11 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         lib.qiddm_mse_workspace_bytes.restype = C.c_size_t
         lib.qiddm_mse_loss_grad.restype = i32
         lib.qiddm_mse_loss_grad.argtypes = [vp, vp, vp, i32, f64, f64, i64, vp, vp, vp, vp]
+        lib.qiddm_linear_up_mse_workspace_bytes.restype = C.c_size_t
+        lib.qiddm_linear_up_mse_workspace_bytes.argtypes = [i32, i32]
+        lib.qiddm_linear_up_mse_step.restype = i32
+        lib.qiddm_linear_up_mse_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, f64, f64, f64, f64, vp, vp, vp, vp,
+                                                 vp, vp]
         lib.qiddm_mse_ladder_loss_grad.restype = i32
         lib.qiddm_mse_ladder_loss_grad.argtypes = [vp, vp, vp, vp, i32, i64, i32, i32, f64, f64, f64, f64, vp, vp, vp, vp]
         lib.qiddm_readout_channel.restype = i32

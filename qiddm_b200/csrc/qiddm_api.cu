@@ -824,6 +824,17 @@ int qiddm_mse_ladder_loss_grad(const void *pred, const void *x, const float *eps
                                        (cudaStream_t)stream);
 }
 
+size_t qiddm_linear_up_mse_workspace_bytes(int pixels, int hidden) {
+    return (pixels > 0 && hidden > 0 && hidden <= 16) ? qiddm::linear_up_mse_ws_bytes(pixels, hidden) : 0;
+}
+int qiddm_linear_up_mse_step(const void *h, const void *weight, const void *bias, const void *x, const float *eps, const void *w,
+                             int dtype, int64_t batch, int pixels, int tau, int hidden, double scale, double shift, double c0,
+                             double c1, void *loss, void *grad_weight, void *grad_bias, void *grad_h, void *workspace,
+                             qiddm_stream_t stream) {
+    return qiddm::linear_up_mse_step(h, weight, bias, x, eps, w, dtype, batch, pixels, tau, hidden, scale, shift, c0, c1, loss,
+                                     grad_weight, grad_bias, grad_h, workspace, (cudaStream_t)stream);
+}
+
 int qiddm_readout_channel(const void *probs_in, void *probs_out, int dtype, int64_t batch, int n_qubits, double m00, double m01,
                           double m10, double m11, qiddm_stream_t stream) {
     return qiddm::prob_channel(probs_in, probs_out, dtype, batch, n_qubits, m00, m01, m10, m11, (cudaStream_t)stream);

@@ -453,6 +453,147 @@ __global__ void __launch_bounds__(256) mse_ladder_grad_kernel(const T *r, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Tail of the re-upload families' training step in one pass (nn/qdense.py:642, :676 `linear_up` + src/models.py:65-67, :95-99):
+//   out[r][p] = sum_k h[r][k] W[p][k] + bias[p]        (rows r = (image, ladder step t), K = hidden features <= 16, P pixels)
+//   d = a out + b - (c0 level_t + c1 level_{t+1}),  loss = mean d^2,  g = 2 a d / n
+//   dW[p][k] = sum_r g h[r][k],  dbias[p] = sum_r g,  dh[r][k] = sum_p g W[p][k]
+// Neither `out` nor dL/dout (rows x P each) is materialised: the un-fused sequence writes out (wide_out), reads it with the
+// target and writes the gradient (MSE), then reads the gradient twice (narrow product for dh, outer product for dW) -- five
+// passes over (rows x P) arrays; here the images and their noise draw ((rows / T) x P) are read twice.
+//   tail_w_kernel: a thread owns one pixel (its W row, dW row and dbias in registers) and walks a slice of the images
+//   tail_h_kernel: a warp owns one row, its lanes stride over the pixels (W, bias in shared memory), warp-sum of the K partials
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TAIL_KMAX = 16;
+constexpr int TAIL_SLICES = 96;          // image slices of tail_w_kernel (per-CTA partial sums, fixed-order reduction)
+
+template <typename T>
+__device__ __forceinline__ T ladder_level(T xv, T ev, T wt) {
+    T v = xv * ((T)1 - wt) + ev * wt;
+    return v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(128) tail_w_kernel(const T *h, const T *W, const T *bias, const T *x, const float *eps, const T *w,
+                                                     long long batch, int P, int steps, double a, double b, double c0, double c1,
+                                                     double *part_w, double *part_loss) {
+    __shared__ double hs[32 * TAIL_KMAX];        // the K hidden features of the current image's rows (steps <= 32 per pass)
+    __shared__ double red[4];
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    const bool live = p < P;
+    const long long per = (batch + gridDim.y - 1) / gridDim.y;
+    const long long i0 = (long long)blockIdx.y * per, i1 = i0 + per < batch ? i0 + per : batch;
+    double wr[K], dw[K], db = 0.0, acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        wr[k] = live ? (double)W[(long long)p * K + k] : 0.0;
+        dw[k] = 0.0;
+    }
+    const double bp = (live && bias != nullptr) ? (double)bias[p] : 0.0;
+    const double kk = 2.0 * a / ((double)batch * (double)steps * (double)P);
+    for (long long img = i0; img < i1; ++img) {
+        const T xv = live ? __ldg(x + img * P + p) : (T)0, ev = live ? (T)__ldg(eps + img * P + p) : (T)0;
+        T prev = ladder_level<T>(xv, ev, __ldg(w));
+        for (int t0 = 0; t0 < steps; t0 += 32) {
+            const int nt = steps - t0 < 32 ? steps - t0 : 32;
+            __syncthreads();
+            for (int i = threadIdx.x; i < nt * K; i += 128) hs[i] = (double)__ldg(h + (img * steps + t0) * K + i);
+            __syncthreads();
+            for (int t = 0; t < nt; ++t) {
+                const T lv = ladder_level<T>(xv, ev, __ldg(w + t0 + t + 1));
+                double out = bp;
+#pragma unroll
+                for (int k = 0; k < K; ++k) out += hs[t * K + k] * wr[k];
+                const double d = a * out + b - (c0 * (double)prev + c1 * (double)lv);
+                prev = lv;
+                if (live) {
+                    acc += d * d;
+                    const double g = kk * d;
+                    db += g;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) dw[k] += g * hs[t * K + k];
+                }
+            }
+        }
+    }
+    if (live) {
+        double *dst = part_w + ((long long)blockIdx.y * P + p) * (K + 1);
+#pragma unroll
+        for (int k = 0; k < K; ++k) dst[k] = dw[k];
+        dst[K] = db;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) part_loss[blockIdx.y * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// fixed-order sums of the slice partials: dW (P, K), dbias (P), and the loss
+template <typename T, int K>
+__global__ void tail_reduce_kernel(const double *part_w, const double *part_loss, int n_slices, int n_loss, int P, double n_total,
+                                   T *dW, T *dbias, T *loss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P * (K + 1)) {
+        double s = 0.0;
+        for (int sl = 0; sl < n_slices; ++sl) s += part_w[(long long)sl * P * (K + 1) + i];
+        const int p = i / (K + 1), k = i - p * (K + 1);
+        if (k < K) dW[(long long)p * K + k] = (T)s;
+        else if (dbias != nullptr) dbias[p] = (T)s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < n_loss; j += 32) s += part_loss[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) loss[0] = (T)(s / n_total);
+    }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) tail_h_kernel(const T *h, const T *W, const T *bias, const T *x, const float *eps, const T *w,
+                                                     long long batch, int P, int steps, double a, double b, double c0, double c1,
+                                                     T *dh) {
+    extern __shared__ double tail_smem[];        // W (P, K) then bias (P)
+    double *Ws = tail_smem, *bs = tail_smem + (size_t)P * K;
+    for (int i = threadIdx.x; i < P * K; i += 256) Ws[i] = (double)W[i];
+    for (int i = threadIdx.x; i < P; i += 256) bs[i] = bias != nullptr ? (double)bias[i] : 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long rows = batch * steps;
+    const double kk = 2.0 * a / ((double)rows * (double)P);
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+        const long long img = r / steps;
+        const int t = (int)(r - img * steps);
+        const T w0 = __ldg(w + t), w1 = __ldg(w + t + 1);
+        double hr[K], acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            hr[k] = (double)__ldg(h + r * K + k);
+            acc[k] = 0.0;
+        }
+        for (int p = lane; p < P; p += 32) {
+            const T xv = __ldg(x + img * P + p), ev = (T)__ldg(eps + img * P + p);
+            double out = bs[p];
+#pragma unroll
+            for (int k = 0; k < K; ++k) out += hr[k] * Ws[p * K + k];
+            const double d = a * out + b - (c0 * (double)ladder_level<T>(xv, ev, w0) + c1 * (double)ladder_level<T>(xv, ev, w1));
+            const double g = kk * d;
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += g * Ws[p * K + k];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) dh[r * K + k] = (T)acc[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Noise channels right before a computational-basis readout (nn/qdense.py:98-104, :174-180, :431-439 on default.mixed;
 // src/mnist_noise.py:211-229).  A single-qubit channel applied to every wire immediately before probs() only moves
 // population: PhaseShift / PhaseDamping are diagonal (no effect), AmplitudeDamping(g) maps (p0, p1) -> (p0 + g p1,
@@ -741,6 +882,64 @@ int mse_ladder_loss_grad(const void *r, const void *x, const float *eps, const v
         return mse_ladder_impl<double>(r, x, eps, w, batch, P, tau, a, b, c0, c1, grad, loss, reinterpret_cast<double *>(ws), s);
     if (dtype == QIDDM_DTYPE_F32)
         return mse_ladder_impl<float>(r, x, eps, w, batch, P, tau, a, b, c0, c1, grad, loss, reinterpret_cast<double *>(ws), s);
+    return QIDDM_EINVAL;
+}
+
+size_t linear_up_mse_ws_bytes(int P, int K) {
+    return ((size_t)TAIL_SLICES * P * (K + 1) + (size_t)TAIL_SLICES * ((P + 127) / 128)) * sizeof(double) + 256;
+}
+
+namespace {
+template <typename T, int K>
+int tail_impl(const void *h, const void *W, const void *bias, const void *x, const float *eps, const void *w, long long batch, int P,
+              int tau, double a, double b, double c0, double c1, void *loss, void *dW, void *dbias, void *dh, void *ws, cudaStream_t s) {
+    const int steps = tau - 1, pb = (P + 127) / 128;
+    const int slices = (int)(batch < TAIL_SLICES ? batch : TAIL_SLICES);
+    double *part_w = reinterpret_cast<double *>(ws);
+    double *part_loss = part_w + (size_t)TAIL_SLICES * P * (K + 1);
+    const T *hp = reinterpret_cast<const T *>(h), *Wp = reinterpret_cast<const T *>(W), *bp = reinterpret_cast<const T *>(bias);
+    const T *xp = reinterpret_cast<const T *>(x), *wp = reinterpret_cast<const T *>(w);
+    tail_w_kernel<T, K><<<dim3(pb, slices), 128, 0, s>>>(hp, Wp, bp, xp, eps, wp, batch, P, steps, a, b, c0, c1, part_w, part_loss);
+    tail_reduce_kernel<T, K><<<(P * (K + 1) + 255) / 256, 256, 0, s>>>(part_w, part_loss, slices, slices * pb, P,
+                                                                        (double)batch * steps * P, reinterpret_cast<T *>(dW),
+                                                                        reinterpret_cast<T *>(dbias), reinterpret_cast<T *>(loss));
+    int launches = 2;
+    if (dh != nullptr) {
+        const size_t smem = (size_t)P * (K + 1) * sizeof(double);
+        auto kern = tail_h_kernel<T, K>;
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return QIDDM_EUNSUPPORTED;
+        const long long rows = batch * steps;
+        const long long need = (rows + 7) / 8;
+        kern<<<(unsigned)(need < 148 * 4 ? need : 148 * 4), 256, smem, s>>>(hp, Wp, bp, xp, eps, wp, batch, P, steps, a, b, c0, c1,
+                                                                             reinterpret_cast<T *>(dh));
+        ++launches;
+    }
+    count_launch(launches);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QIDDM_OK : (int)e;
+}
+template <typename T>
+int tail_k(int K, const void *h, const void *W, const void *bias, const void *x, const float *eps, const void *w, long long batch,
+           int P, int tau, double a, double b, double c0, double c1, void *loss, void *dW, void *dbias, void *dh, void *ws,
+           cudaStream_t s) {
+#define QIDDM_TAIL(K_) case K_: return tail_impl<T, K_>(h, W, bias, x, eps, w, batch, P, tau, a, b, c0, c1, loss, dW, dbias, dh, ws, s)
+    switch (K) {
+        QIDDM_TAIL(1); QIDDM_TAIL(2); QIDDM_TAIL(3); QIDDM_TAIL(4); QIDDM_TAIL(5); QIDDM_TAIL(6); QIDDM_TAIL(7); QIDDM_TAIL(8);
+        QIDDM_TAIL(9); QIDDM_TAIL(10); QIDDM_TAIL(11); QIDDM_TAIL(12); QIDDM_TAIL(13); QIDDM_TAIL(14); QIDDM_TAIL(15); QIDDM_TAIL(16);
+    }
+#undef QIDDM_TAIL
+    return QIDDM_EUNSUPPORTED;
+}
+}  // namespace
+
+int linear_up_mse_step(const void *h, const void *W, const void *bias, const void *x, const float *eps, const void *w, int dtype,
+                       long long batch, int P, int tau, int K, double a, double b, double c0, double c1, void *loss, void *dW,
+                       void *dbias, void *dh, void *ws, cudaStream_t s) {
+    if (!h || !W || !x || !eps || !w || !loss || !dW || !ws || batch < 1 || P < 1 || tau < 2) return QIDDM_EINVAL;
+    if (K < 1 || K > TAIL_KMAX || (size_t)P * (K + 1) * sizeof(double) > 200 * 1024) return QIDDM_EUNSUPPORTED;
+    if (dtype == QIDDM_DTYPE_F64) return tail_k<double>(K, h, W, bias, x, eps, w, batch, P, tau, a, b, c0, c1, loss, dW, dbias, dh, ws, s);
+    if (dtype == QIDDM_DTYPE_F32) return tail_k<float>(K, h, W, bias, x, eps, w, batch, P, tau, a, b, c0, c1, loss, dW, dbias, dh, ws, s);
     return QIDDM_EINVAL;
 }
 

@@ -130,6 +130,10 @@ int noise_ladder(const void *x, const float *eps, const void *w, int dtype, long
                  void *clean, cudaStream_t s);
 int mse_loss_grad(const void *r, const void *t1, const void *t2, int dtype, double a, double b, long long n, void *grad,
                   void *loss, void *ws, cudaStream_t s);
+size_t linear_up_mse_ws_bytes(int P, int K);
+int linear_up_mse_step(const void *h, const void *W, const void *bias, const void *x, const float *eps, const void *w, int dtype,
+                       long long batch, int P, int tau, int K, double a, double b, double c0, double c1, void *loss, void *dW,
+                       void *dbias, void *dh, void *ws, cudaStream_t s);
 int mse_ladder_loss_grad(const void *r, const void *x, const float *eps, const void *w, int dtype, long long batch, int P, int tau,
                          double a, double b, double c0, double c1, void *grad, void *loss, void *ws, cudaStream_t s);
 int upsample_bilinear(const void *in, void *out, int dtype, bool backward, long long planes, int Hin, int Win, int Hout, int Wout,

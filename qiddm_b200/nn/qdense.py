@@ -695,7 +695,7 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
         _check_noise(noise, allow_phase=False)
         return 0
 
-    def forward(self, x):
+    def forward(self, x, hidden_only: bool = False):
         b, c, w, h = x.shape
         noise = self._check_noise_at_call()
         a = self._reduce_input(x)
@@ -710,11 +710,20 @@ class _QIDDMExpval(_SaveLoadMixin, nn.Module):
             if self.detach_quantum:
                 a = a.detach()
         a = a.view(b, -1)
+        if hidden_only:
+            return a.to(self.linear_up.weight.dtype)
         if self._restore == "linear":
             out = skinny_linear(a.to(self.linear_up.weight.dtype), self.linear_up)
         else:
             out = _pca_call(self.pca, "inverse_transform", a, getattr(self, "pca_group", None)).to(x.dtype).requires_grad_(True)
         return out.view(b, c, w, h)
+
+    def forward_hidden(self, x):
+        """Everything in front of `linear_up`: (rows, hidden) -- for the fused tail of the diffusion step (linear_up + loss in
+        one pass, qiddm_b200.noise.linear_up_mse_loss); None when the class restores through the PCA instead."""
+        if self._restore != "linear":
+            return None
+        return self.forward(x, hidden_only=True)
 
     def __repr__(self):
         return f"{self._repr_name}(qlayer={self.spectrum_layer}, features={self.hidden_features}, N={self.N})"

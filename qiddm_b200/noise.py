@@ -101,3 +101,57 @@ def mse_loss_and_grad(pred: torch.Tensor, target: torch.Tensor, target_add: torc
                                         C.c_void_p(torch.cuda.current_stream(pred_c.device).cuda_stream)),
                 "qiddm_mse_loss_grad")
     return loss, grad
+
+
+class _LinearUpMSE(torch.autograd.Function):
+    """loss = mean((scale * linear_up(h) + shift - target)^2) with the target recomputed from the noise draw; the loss and all
+    three gradients come out of the forward call (qiddm_linear_up_mse_step), the backward hands them to autograd."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, data, eps, w, T, scale, shift, c0, c1):
+        import ctypes as C
+        from . import _lib as L
+        lib = L.load_library()
+        dt = {torch.float32: L.DTYPE_F32, torch.float64: L.DTYPE_F64}[h.dtype]
+        hc = h.detach().contiguous()
+        wc = weight.detach().to(h.dtype).contiguous()
+        bc = bias.detach().to(h.dtype).contiguous() if bias is not None else None
+        batch, pixels = data.shape
+        hidden = wc.shape[1]
+        need_h = ctx.needs_input_grad[0]
+        loss = torch.empty((), dtype=h.dtype, device=h.device)
+        gw = torch.empty_like(wc)
+        gb = torch.empty(pixels, dtype=h.dtype, device=h.device) if bias is not None else None
+        gh = torch.empty_like(hc) if need_h else None
+        ws = torch.empty(int(lib.qiddm_linear_up_mse_workspace_bytes(pixels, hidden)), dtype=torch.uint8, device=h.device)
+        with torch.cuda.device(h.device):
+            L.check(lib.qiddm_linear_up_mse_step(L._ptr(hc), L._ptr(wc), L._ptr(bc), L._ptr(data), L._ptr(eps), L._ptr(w), dt, batch,
+                                                 pixels, T + 1, hidden, float(scale), float(shift), float(c0), float(c1), L._ptr(loss),
+                                                 L._ptr(gw), L._ptr(gb), L._ptr(gh), L._ptr(ws),
+                                                 C.c_void_p(torch.cuda.current_stream(h.device).cuda_stream)),
+                    "qiddm_linear_up_mse_step")
+        ctx.grads = (gh, gw.to(weight.dtype), gb.to(bias.dtype) if gb is not None else None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gh, gw, gb = ctx.grads
+        ctx.grads = None
+        return (gh * g if gh is not None else None, gw * g, gb * g if gb is not None else None,
+                None, None, None, None, None, None, None, None)
+
+
+def linear_up_mse_ok(h: torch.Tensor, layer: torch.nn.Linear, draw, T: int) -> bool:
+    data = draw[0]
+    return (h.is_cuda and h.dim() == 2 and h.dtype in (torch.float32, torch.float64) and h.dtype == data.dtype
+            and isinstance(layer, torch.nn.Linear) and layer.in_features <= 16 and layer.in_features == h.shape[1]
+            and layer.out_features == data.shape[1] and h.shape[0] == data.shape[0] * T and layer.weight.is_cuda
+            and data.shape[1] * (layer.in_features + 1) * 8 <= 200 * 1024)
+
+
+def linear_up_mse_loss(h: torch.Tensor, layer: torch.nn.Linear, draw, T: int, scale: float = 1.0, shift: float = 0.0,
+                       c0: float = 1.0, c1: float = 0.0) -> torch.Tensor:
+    """Differentiable scalar: the tail `linear_up -> MSELoss(..., target).mean()` of a re-upload network's training step with the
+    ladder target recomputed from `draw` (ladder_pair(..., return_draw=True)); see qiddm_linear_up_mse_step."""
+    data, eps, w = draw
+    return _LinearUpMSE.apply(h, layer.weight, layer.bias, data, eps, w, T, scale, shift, c0, c1)

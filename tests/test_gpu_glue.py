@@ -173,6 +173,60 @@ def test_diffusion_step_with_and_without_the_recomputed_target(monkeypatch):
         assert rel_to_max(res[0][1], res[1][1]) <= 1e-9
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("hidden,bias", [(6, True), (8, False), (16, True), (1, True)])
+def test_fused_linear_up_mse_tail_matches_torch(dtype, tol, hidden, bias):
+    """noise.linear_up_mse_loss (qiddm_linear_up_mse_step: Linear(hidden -> pixels) + MSE against the recomputed ladder target,
+    loss and all three gradients in one pass) against the same tail written with torch ops, both goals."""
+    from qiddm_b200 import noise
+    torch.manual_seed(7)
+    T, batch, P = 5, 37, 150
+    x = torch.rand(batch, P, dtype=dtype, device="cuda") * 1.3 - 0.1
+    eps = torch.normal(0.5, 0.2, size=(batch, P), device="cuda")
+    noisy, clean, draw = noise.ladder_pair(x, T, 3.0, eps=eps, return_draw=True)
+    layer = torch.nn.Linear(hidden, P, bias=bias).to("cuda", dtype)
+    for coef, target, pre in (({}, clean, lambda o: o),
+                              (dict(scale=0.1, shift=-0.05, c0=-1.0, c1=1.0), noisy - clean, lambda o: (o - 0.5) * 0.1)):
+        h1 = torch.randn(batch * T, hidden, dtype=dtype, device="cuda", requires_grad=True)
+        h2 = h1.detach().clone().requires_grad_(True)
+        layer.zero_grad()
+        ref = torch.nn.functional.mse_loss(pre(layer(h2)), target)
+        ref.backward()
+        gw, gb = layer.weight.grad.clone(), (layer.bias.grad.clone() if bias else None)
+        layer.zero_grad()
+        assert noise.linear_up_mse_ok(h1, layer, draw, T)
+        loss = noise.linear_up_mse_loss(h1, layer, draw, T, **coef)
+        loss.backward()
+        assert abs(loss.item() - ref.item()) <= tol * abs(ref.item())
+        assert rel_to_max(h1.grad, h2.grad) <= tol and rel_to_max(layer.weight.grad, gw) <= tol
+        if bias:
+            assert rel_to_max(layer.bias.grad, gb) <= tol
+
+
+@pytest.mark.parametrize("cls_args", [("QIDDM_LL_noise", (64, 4, 3, 2)), ("QIDDM_PL_noise", (64, 4, 3, 2))])
+def test_diffusion_step_with_and_without_the_fused_tail(cls_args, monkeypatch):
+    """Whole training step of a re-upload network with `linear_up + loss` fused (QIDDM_FUSED_TAIL=1, from 4096 rows on) against the same step
+    through the separate kernels: same loss, same gradients of every parameter."""
+    from qiddm_b200 import models, nn, noise
+    name, args = cls_args
+    for goal in ("data", "noise"):
+        res = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("QIDDM_FUSED_TAIL", flag)
+            torch.manual_seed(3)
+            net = getattr(nn, name)(*args)
+            d = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (8, 8), torch.nn.MSELoss()).to("cuda", torch.float64)
+            d.train()
+            x = torch.rand(600, 64, dtype=torch.float64, device="cuda")
+            torch.manual_seed(11)
+            (loss,) = d(x=x, T=8)
+            res.append((loss.item(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+        assert abs(res[0][0] - res[1][0]) <= 1e-10 * abs(res[1][0]), goal
+        assert res[0][1].keys() == res[1][1].keys()
+        for k in res[0][1]:
+            assert rel_to_max(res[0][1][k], res[1][1][k], floor=1e-14) <= 1e-6, (goal, k)
+
+
 def test_diffusion_step_fused_glue_equals_torch_glue():
     """Diffusion.forward with the fused ladder + MSE kernels vs the same step through the torch ops (custom add_noise /
     verbose path), both goals: same loss and parameter gradients."""
