@@ -317,8 +317,9 @@ int qiddm_mse_ladder_loss_grad(const void *pred, const void *x, const float *eps
 /* Tail of the re-upload families' training step in one pass: `linear_up` (nn/qdense.py:642, :676: Linear(hidden -> pixels)) +
  * MSELoss + `.mean().backward()` (src/models.py:65-67, :95-99) with the target recomputed from the noise draw as in
  * qiddm_mse_ladder_loss_grad.  h (batch * (tau - 1), hidden <= 16), weight (pixels, hidden), bias (pixels, may be NULL), x / eps
- * (batch, pixels), w[tau]; writes loss[0], grad_weight (pixels, hidden), grad_bias (pixels, may be NULL) and grad_h (like h, may be
- * NULL).  Neither the layer's output nor its gradient (batch * (tau - 1) x pixels each) is materialised.  Deterministic. */
+ * (batch, pixels), w[tau], tau <= 33; writes loss[0], grad_weight (pixels, hidden), grad_bias (pixels, may be NULL) and grad_h (like
+ * h).  Neither the layer's output nor its gradient (batch * (tau - 1) x pixels each) is materialised; the products are expanded
+ * (second moments of weight and h) so that only K + 4 and K + 8 FP64 operations touch every (row, pixel).  Deterministic. */
 size_t qiddm_linear_up_mse_workspace_bytes(int pixels, int hidden);
 int qiddm_linear_up_mse_step(const void *h, const void *weight, const void *bias, const void *x, const float *eps, const void *w,
                              int dtype, int64_t batch, int pixels, int tau, int hidden, double scale, double shift, double c0,

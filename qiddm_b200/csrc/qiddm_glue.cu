@@ -454,17 +454,23 @@ __global__ void __launch_bounds__(256) mse_ladder_grad_kernel(const T *r, const 
 
 // ------------------------------------------------------------------------------------------------------------------
 // Tail of the re-upload families' training step in one pass (nn/qdense.py:642, :676 `linear_up` + src/models.py:65-67, :95-99):
-//   out[r][p] = sum_k h[r][k] W[p][k] + bias[p]        (rows r = (image, ladder step t), K = hidden features <= 16, P pixels)
-//   d = a out + b - (c0 level_t + c1 level_{t+1}),  loss = mean d^2,  g = 2 a d / n
-//   dW[p][k] = sum_r g h[r][k],  dbias[p] = sum_r g,  dh[r][k] = sum_p g W[p][k]
-// Neither `out` nor dL/dout (rows x P each) is materialised: the un-fused sequence writes out (wide_out), reads it with the
-// target and writes the gradient (MSE), then reads the gradient twice (narrow product for dh, outer product for dW) -- five
-// passes over (rows x P) arrays; here the images and their noise draw ((rows / T) x P) are read twice.
-//   tail_w_kernel: a thread owns one pixel (its W row, dW row and dbias in registers) and walks a slice of the images
-//   tail_h_kernel: a warp owns one row, its lanes stride over the pixels (W, bias in shared memory), warp-sum of the K partials
+//   out[r][p] = h_r . W_p + bias_p        (rows r = (image, ladder step t), K = hidden features <= 16, P pixels)
+//   d = a out + b - tau_rp,  tau_rp = c0 level_t + c1 level_{t+1},  loss = mean d^2,  g = (2 a / n) d
+//   dW_p = sum_r g h_r,  dbias_p = sum_r g,  dh_r = sum_p g W_p
+// Neither `out` nor dL/dout (rows x P each) is materialised (the un-fused sequence makes five passes over such arrays).  The
+// plain FP64 FMA rate bounds this GPU here (measured ~5 TFLOP/s), so the products are expanded: with beta_p = a bias_p + b,
+//   M = sum_p W_p W_p^T, cb = sum_p beta_p W_p, sb2 = sum_p beta_p^2, H2 = sum_r h_r h_r^T, hs = sum_r h_r        (small)
+//   dh_r    = (2a/n) [a M h_r + cb - V_r],             V_r  = sum_p tau_rp W_p
+//   dW_p    = (2a/n) [a H2 W_p + beta_p hs - Q_p],     Q_p  = sum_r tau_rp h_r
+//   dbias_p = (2a/n) [a W_p . hs + beta_p R - st_p],   st_p = sum_r tau_rp
+//   n loss  = a^2 tr(M H2) + R sb2 + sum tau^2 + 2a hs . cb - 2a sum_r h_r . V_r - 2 sum_p beta_p st_p
+// and only V (per image: the T + 1 ladder levels dotted with W, one warp per image) and Q / st / sum tau^2 (a thread per pixel
+// walking a slice of the images) touch every (row, pixel): K + 4 and K + 8 FP64 operations instead of 2 x (2K + 12).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TAIL_KMAX = 16;
-constexpr int TAIL_SLICES = 96;          // image slices of tail_w_kernel (per-CTA partial sums, fixed-order reduction)
+constexpr int TAIL_SLICES = 96;          // image slices of tail_q_kernel (per-CTA partial sums, fixed-order reduction)
+constexpr int TAIL_HSLICES = 148;        // row slices of the h moments
+constexpr int TAIL_TMAX = 32;            // ladder steps held per image in tail_v_kernel
 
 template <typename T>
 __device__ __forceinline__ T ladder_level(T xv, T ev, T wt) {
@@ -472,24 +478,152 @@ __device__ __forceinline__ T ladder_level(T xv, T ev, T wt) {
     return v < (T)0 ? (T)0 : (v > (T)1 ? (T)1 : v);
 }
 
+// mom_w = [M (K x K) | cb (K) | sb2] (device function: run by the extra last block of tail_hmom_kernel, W staged in shared memory)
 template <typename T, int K>
-__global__ void __launch_bounds__(128) tail_w_kernel(const T *h, const T *W, const T *bias, const T *x, const float *eps, const T *w,
-                                                     long long batch, int P, int steps, double a, double b, double c0, double c1,
-                                                     double *part_w, double *part_loss) {
-    __shared__ double hs[32 * TAIL_KMAX];        // the K hidden features of the current image's rows (steps <= 32 per pass)
+__device__ __forceinline__ void tail_wmom(const T *W, const T *bias, int P, double a, double b, double *mom_w, double *smem) {
+    double *Ws = smem, *bs = smem + (size_t)P * K;
+    for (int i = threadIdx.x; i < P * K; i += 256) Ws[i] = (double)__ldg(W + i);
+    for (int i = threadIdx.x; i < P; i += 256) bs[i] = a * (bias != nullptr ? (double)__ldg(bias + i) : 0.0) + b;
+    __syncthreads();
+    for (int o = threadIdx.x; o < K * K + K + 1; o += 256) {
+        double s0 = 0.0, s1 = 0.0;
+        if (o < K * K) {
+            const int i = o / K, j = o - i * K;
+            int p = 0;
+            for (; p + 1 < P; p += 2) {
+                s0 += Ws[p * K + i] * Ws[p * K + j];
+                s1 += Ws[(p + 1) * K + i] * Ws[(p + 1) * K + j];
+            }
+            if (p < P) s0 += Ws[p * K + i] * Ws[p * K + j];
+        } else if (o < K * K + K) {
+            const int k = o - K * K;
+            for (int p = 0; p < P; ++p) s0 += bs[p] * Ws[p * K + k];
+        } else {
+            for (int p = 0; p < P; ++p) s0 += bs[p] * bs[p];
+        }
+        mom_w[o] = s0 + s1;
+    }
+}
+
+// part_h[slice] = [H2 (K x K) | hs (K)] of a slice of the rows
+template <typename T, int K>
+__global__ void __launch_bounds__(256) tail_hmom_kernel(const T *h, long long rows, double *part_h, const T *W, const T *bias, int P,
+                                                        double a, double b, double *mom_w) {
+    extern __shared__ double tail_smem[];
+    __shared__ double hsm[64 * TAIL_KMAX];
+    if (blockIdx.x == gridDim.x - 1) {           // the W moments ride in the same launch
+        tail_wmom<T, K>(W, bias, P, a, b, mom_w, tail_smem);
+        return;
+    }
+    const int n_sl = gridDim.x - 1;
+    const long long per = (rows + n_sl - 1) / n_sl;
+    const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+    constexpr int NO = K * K + K, PER = (NO + 255) / 256;          // outputs per thread (2 for K = 16)
+    double s[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) s[u] = 0.0;
+    for (long long c0 = r0; c0 < r1; c0 += 64) {
+        const int nr = (int)(r1 - c0 < 64 ? r1 - c0 : 64);
+        __syncthreads();
+        for (int q = threadIdx.x; q < nr * K; q += 256) hsm[q] = (double)__ldg(h + c0 * K + q);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int o = threadIdx.x + u * 256;
+            if (o < K * K) {
+                const int i = o / K, j = o - i * K;
+                for (int r = 0; r < nr; ++r) s[u] += hsm[r * K + i] * hsm[r * K + j];
+            } else if (o < NO) {
+                const int j = o - K * K;
+                for (int r = 0; r < nr; ++r) s[u] += hsm[r * K + j];
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int o = threadIdx.x + u * 256;
+        if (o < NO) part_h[(long long)blockIdx.x * NO + o] = s[u];
+    }
+}
+
+// one warp per image: Vl[t] = sum_p level_t W_p for the T + 1 levels, then dh of the image's T rows and its share of sum_r h_r . V_r
+template <typename T, int K>
+__global__ void __launch_bounds__(256) tail_v_kernel(const T *h, const T *W, const T *x, const float *eps, const T *w,
+                                                     const double *mom_w, long long batch, int P, int steps, double a, double c0,
+                                                     double c1, double kk, T *dh, double *part_hv) {
+    extern __shared__ double tail_smem[];
+    double *Ws = tail_smem;                                  // W (P, K)
+    double *Vs = tail_smem + (size_t)P * K;                  // [8 warps][TAIL_TMAX + 1][K]
+    __shared__ double red[8];
+    for (int i = threadIdx.x; i < P * K; i += 256) Ws[i] = (double)W[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *Vw = Vs + (size_t)warp * (TAIL_TMAX + 1) * K;
+    double hv = 0.0;
+    for (long long img = (long long)blockIdx.x * 8 + warp; img < batch; img += (long long)gridDim.x * 8) {
+        for (int t = 0; t <= steps; ++t) {
+            const T wt = __ldg(w + t);
+            double acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = 0.0;
+            for (int p = lane; p < P; p += 32) {
+                const double lv = (double)ladder_level<T>(__ldg(x + img * P + p), (T)__ldg(eps + img * P + p), wt);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] += lv * Ws[p * K + k];
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) Vw[t * K + k] = acc[k];
+            }
+        }
+        __syncwarp();
+        // rows of the image: lane t < steps
+        for (int t = lane; t < steps; t += 32) {
+            const long long r = img * steps + t;
+            double hr[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) hr[k] = (double)__ldg(h + r * K + k);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double v = c0 * Vw[t * K + k] + c1 * Vw[(t + 1) * K + k];
+                double mh = 0.0;
+#pragma unroll
+                for (int j = 0; j < K; ++j) mh += mom_w[k * K + j] * hr[j];
+                dh[r * K + k] = (T)(kk * (a * mh + mom_w[K * K + k] - v));
+                hv += hr[k] * v;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hv += __shfl_xor_sync(0xffffffffu, hv, o);
+    if (lane == 0) red[warp] = hv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        part_hv[blockIdx.x] = s;
+    }
+}
+
+// a thread per pixel walking a slice of the images: Q_p = sum_r tau_rp h_r, st_p = sum_r tau_rp, and the slice's sum of tau^2
+template <typename T, int K>
+__global__ void __launch_bounds__(128) tail_q_kernel(const T *h, const T *x, const float *eps, const T *w, long long batch, int P,
+                                                     int steps, double c0, double c1, double *part_q, double *part_t2) {
+    __shared__ double hs[32 * TAIL_KMAX];        // the K hidden features of up to 32 rows of the current image
     __shared__ double red[4];
     const int p = blockIdx.x * 128 + threadIdx.x;
     const bool live = p < P;
     const long long per = (batch + gridDim.y - 1) / gridDim.y;
     const long long i0 = (long long)blockIdx.y * per, i1 = i0 + per < batch ? i0 + per : batch;
-    double wr[K], dw[K], db = 0.0, acc = 0.0;
+    double q[K], st = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        wr[k] = live ? (double)W[(long long)p * K + k] : 0.0;
-        dw[k] = 0.0;
-    }
-    const double bp = (live && bias != nullptr) ? (double)bias[p] : 0.0;
-    const double kk = 2.0 * a / ((double)batch * (double)steps * (double)P);
+    for (int k = 0; k < K; ++k) q[k] = 0.0;
     for (long long img = i0; img < i1; ++img) {
         const T xv = live ? __ldg(x + img * P + p) : (T)0, ev = live ? (T)__ldg(eps + img * P + p) : (T)0;
         T prev = ladder_level<T>(xv, ev, __ldg(w));
@@ -500,97 +634,108 @@ __global__ void __launch_bounds__(128) tail_w_kernel(const T *h, const T *W, con
             __syncthreads();
             for (int t = 0; t < nt; ++t) {
                 const T lv = ladder_level<T>(xv, ev, __ldg(w + t0 + t + 1));
-                double out = bp;
-#pragma unroll
-                for (int k = 0; k < K; ++k) out += hs[t * K + k] * wr[k];
-                const double d = a * out + b - (c0 * (double)prev + c1 * (double)lv);
+                const double tau = c0 * (double)prev + c1 * (double)lv;
                 prev = lv;
-                if (live) {
-                    acc += d * d;
-                    const double g = kk * d;
-                    db += g;
+                st += tau;
+                t2 += tau * tau;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) dw[k] += g * hs[t * K + k];
-                }
+                for (int k = 0; k < K; ++k) q[k] += tau * hs[t * K + k];
             }
         }
     }
     if (live) {
-        double *dst = part_w + ((long long)blockIdx.y * P + p) * (K + 1);
+        double *dst = part_q + ((long long)blockIdx.y * P + p) * (K + 1);
 #pragma unroll
-        for (int k = 0; k < K; ++k) dst[k] = dw[k];
-        dst[K] = db;
+        for (int k = 0; k < K; ++k) dst[k] = q[k];
+        dst[K] = st;
+    } else {
+        t2 = 0.0;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    for (int o = 16; o > 0; o >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t2;
     __syncthreads();
-    if (threadIdx.x == 0) part_loss[blockIdx.y * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    if (threadIdx.x == 0) part_t2[blockIdx.y * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
 }
 
-// fixed-order sums of the slice partials: dW (P, K), dbias (P), and the loss
+// fixed-order sums of the partials and the assembly of dW (P, K) and dbias (P): a thread per (pixel, k) element (k = K: bias)
 template <typename T, int K>
-__global__ void tail_reduce_kernel(const double *part_w, const double *part_loss, int n_slices, int n_loss, int P, double n_total,
-                                   T *dW, T *dbias, T *loss) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P * (K + 1)) {
-        double s = 0.0;
-        for (int sl = 0; sl < n_slices; ++sl) s += part_w[(long long)sl * P * (K + 1) + i];
-        const int p = i / (K + 1), k = i - p * (K + 1);
-        if (k < K) dW[(long long)p * K + k] = (T)s;
-        else if (dbias != nullptr) dbias[p] = (T)s;
+__global__ void __launch_bounds__(256) tail_final_kernel(const T *W, const T *bias, const double *part_h, int n_hs,
+                                                         const double *part_q, int n_slices, int P, double rows, double a, double b,
+                                                         double kk, T *dW, T *dbias, double *mom_h, double *stb_part) {
+    __shared__ double H2[TAIL_KMAX * TAIL_KMAX + TAIL_KMAX];     // H2 then hs
+    __shared__ double red[8];
+    for (int o = threadIdx.x; o < K * K + K; o += 256) {
+        double s0 = 0.0, s1 = 0.0;
+        int j = 0;
+        for (; j + 1 < n_hs; j += 2) {
+            s0 += part_h[(long long)j * (K * K + K) + o];
+            s1 += part_h[(long long)(j + 1) * (K * K + K) + o];
+        }
+        if (j < n_hs) s0 += part_h[(long long)j * (K * K + K) + o];
+        H2[o] = s0 + s1;
+        if (blockIdx.x == 0) mom_h[o] = s0 + s1;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        double s = 0.0;
-        for (int j = threadIdx.x; j < n_loss; j += 32) s += part_loss[j];
+    __syncthreads();
+    const double *hsum = H2 + K * K;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    double stb = 0.0;
+    if (e < P * (K + 1)) {
+        const int p = e / (K + 1), k = e - p * (K + 1);
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+        const double *src = part_q + e;
+        const long long st = (long long)P * (K + 1);
+        int sl = 0;
+        for (; sl + 3 < n_slices; sl += 4) {
+            q0 += src[sl * st];
+            q1 += src[(sl + 1) * st];
+            q2 += src[(sl + 2) * st];
+            q3 += src[(sl + 3) * st];
+        }
+        for (; sl < n_slices; ++sl) q0 += src[sl * st];
+        const double q = (q0 + q1) + (q2 + q3);
+        const double beta = a * (bias != nullptr ? (double)bias[p] : 0.0) + b;
+        double acc = 0.0;
+        if (k < K) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) loss[0] = (T)(s / n_total);
+            for (int j = 0; j < K; ++j) acc += H2[k * K + j] * (double)W[(long long)p * K + j];
+            dW[(long long)p * K + k] = (T)(kk * (a * acc + beta * hsum[k] - q));
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc += (double)W[(long long)p * K + j] * hsum[j];
+            if (dbias != nullptr) dbias[p] = (T)(kk * (a * acc + beta * rows - q));
+            stb = beta * q;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) stb += __shfl_xor_sync(0xffffffffu, stb, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = stb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        stb_part[blockIdx.x] = s;
     }
 }
 
 template <typename T, int K>
-__global__ void __launch_bounds__(256) tail_h_kernel(const T *h, const T *W, const T *bias, const T *x, const float *eps, const T *w,
-                                                     long long batch, int P, int steps, double a, double b, double c0, double c1,
-                                                     T *dh) {
-    extern __shared__ double tail_smem[];        // W (P, K) then bias (P)
-    double *Ws = tail_smem, *bs = tail_smem + (size_t)P * K;
-    for (int i = threadIdx.x; i < P * K; i += 256) Ws[i] = (double)W[i];
-    for (int i = threadIdx.x; i < P; i += 256) bs[i] = bias != nullptr ? (double)bias[i] : 0.0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long rows = batch * steps;
-    const double kk = 2.0 * a / ((double)rows * (double)P);
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
-        const long long img = r / steps;
-        const int t = (int)(r - img * steps);
-        const T w0 = __ldg(w + t), w1 = __ldg(w + t + 1);
-        double hr[K], acc[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            hr[k] = (double)__ldg(h + r * K + k);
-            acc[k] = 0.0;
-        }
-        for (int p = lane; p < P; p += 32) {
-            const T xv = __ldg(x + img * P + p), ev = (T)__ldg(eps + img * P + p);
-            double out = bs[p];
-#pragma unroll
-            for (int k = 0; k < K; ++k) out += hr[k] * Ws[p * K + k];
-            const double d = a * out + b - (c0 * (double)ladder_level<T>(xv, ev, w0) + c1 * (double)ladder_level<T>(xv, ev, w1));
-            const double g = kk * d;
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += g * Ws[p * K + k];
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) dh[r * K + k] = (T)acc[k];
-        }
+__global__ void tail_loss_kernel(const double *mom_w, const double *mom_h, const double *part_t2, int n_t2, const double *part_hv,
+                                 int n_hv, const double *stb_part, int n_stb, double rows, double n_total, double a, T *loss) {
+    // one warp; every sum in a fixed order
+    const int lane = threadIdx.x;
+    double tr = 0.0, hcb = 0.0;
+    for (int o = lane; o < K * K + K; o += 32) {
+        if (o < K * K) tr += mom_w[o] * mom_h[o];        // tr(M H2): both symmetric, same index
+        else hcb += mom_h[o] * mom_w[o];                 // hs . cb (same offset K * K + k in both)
     }
+    double t2 = 0.0, hv = 0.0, stb = 0.0;
+    for (int j = lane; j < n_t2; j += 32) t2 += part_t2[j];
+    for (int j = lane; j < n_hv; j += 32) hv += part_hv[j];
+    for (int j = lane; j < n_stb; j += 32) stb += stb_part[j];
+    double tot = a * a * tr + 2.0 * a * hcb + t2 - 2.0 * a * hv - 2.0 * stb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) loss[0] = (T)((tot + rows * mom_w[K * K + K]) / n_total);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -886,7 +1031,9 @@ int mse_ladder_loss_grad(const void *r, const void *x, const float *eps, const v
 }
 
 size_t linear_up_mse_ws_bytes(int P, int K) {
-    return ((size_t)TAIL_SLICES * P * (K + 1) + (size_t)TAIL_SLICES * ((P + 127) / 128)) * sizeof(double) + 256;
+    const size_t pb = (size_t)(P + 127) / 128;
+    return ((size_t)TAIL_SLICES * P * (K + 1) + TAIL_SLICES * pb + (size_t)K * K + K + 1 + (size_t)(TAIL_HSLICES + 1) * (K * K + K) +
+            148 * 4 + ((size_t)P * (K + 1) + 255) / 256 + 64) * sizeof(double) + 256;
 }
 
 namespace {
@@ -894,28 +1041,40 @@ template <typename T, int K>
 int tail_impl(const void *h, const void *W, const void *bias, const void *x, const float *eps, const void *w, long long batch, int P,
               int tau, double a, double b, double c0, double c1, void *loss, void *dW, void *dbias, void *dh, void *ws, cudaStream_t s) {
     const int steps = tau - 1, pb = (P + 127) / 128;
+    if (steps > TAIL_TMAX) return QIDDM_EUNSUPPORTED;
+    const long long rows = batch * steps;
     const int slices = (int)(batch < TAIL_SLICES ? batch : TAIL_SLICES);
-    double *part_w = reinterpret_cast<double *>(ws);
-    double *part_loss = part_w + (size_t)TAIL_SLICES * P * (K + 1);
+    const int hslices = (int)(rows < TAIL_HSLICES ? rows : TAIL_HSLICES);
+    const int vgrid = (int)((batch + 7) / 8 < 148 * 4 ? (batch + 7) / 8 : 148 * 4);
+    const int fgrid = (P * (K + 1) + 255) / 256;
+    double *part_q = reinterpret_cast<double *>(ws);
+    double *part_t2 = part_q + (size_t)TAIL_SLICES * P * (K + 1);
+    double *mom_w = part_t2 + (size_t)TAIL_SLICES * pb;
+    double *part_h = mom_w + (K * K + K + 1);
+    double *mom_h = part_h + (size_t)TAIL_HSLICES * (K * K + K);
+    double *part_hv = mom_h + (K * K + K);
+    double *stb_part = part_hv + 148 * 4;
     const T *hp = reinterpret_cast<const T *>(h), *Wp = reinterpret_cast<const T *>(W), *bp = reinterpret_cast<const T *>(bias);
     const T *xp = reinterpret_cast<const T *>(x), *wp = reinterpret_cast<const T *>(w);
-    tail_w_kernel<T, K><<<dim3(pb, slices), 128, 0, s>>>(hp, Wp, bp, xp, eps, wp, batch, P, steps, a, b, c0, c1, part_w, part_loss);
-    tail_reduce_kernel<T, K><<<(P * (K + 1) + 255) / 256, 256, 0, s>>>(part_w, part_loss, slices, slices * pb, P,
-                                                                        (double)batch * steps * P, reinterpret_cast<T *>(dW),
-                                                                        reinterpret_cast<T *>(dbias), reinterpret_cast<T *>(loss));
-    int launches = 2;
-    if (dh != nullptr) {
-        const size_t smem = (size_t)P * (K + 1) * sizeof(double);
-        auto kern = tail_h_kernel<T, K>;
-        if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return QIDDM_EUNSUPPORTED;
-        const long long rows = batch * steps;
-        const long long need = (rows + 7) / 8;
-        kern<<<(unsigned)(need < 148 * 4 ? need : 148 * 4), 256, smem, s>>>(hp, Wp, bp, xp, eps, wp, batch, P, steps, a, b, c0, c1,
-                                                                             reinterpret_cast<T *>(dh));
-        ++launches;
-    }
-    count_launch(launches);
+    const double kk = 2.0 * a / ((double)rows * (double)P);
+    const size_t smem_w = (size_t)P * (K + 1) * sizeof(double);
+    const size_t smem_v = ((size_t)P * K + (size_t)8 * (TAIL_TMAX + 1) * K) * sizeof(double);
+    auto km = tail_hmom_kernel<T, K>;
+    auto kv = tail_v_kernel<T, K>;
+    if (smem_w > 40 * 1024 && cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w) != cudaSuccess)
+        return QIDDM_EUNSUPPORTED;
+    if (smem_v > 48 * 1024 && cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v) != cudaSuccess)
+        return QIDDM_EUNSUPPORTED;
+    T *dh_out = reinterpret_cast<T *>(dh);
+    if (dh_out == nullptr) return QIDDM_EUNSUPPORTED;        // V also feeds the loss: grad_h is always written
+    km<<<hslices + 1, 256, smem_w, s>>>(hp, rows, part_h, Wp, bp, P, a, b, mom_w);
+    tail_q_kernel<T, K><<<dim3(pb, slices), 128, 0, s>>>(hp, xp, eps, wp, batch, P, steps, c0, c1, part_q, part_t2);
+    kv<<<vgrid, 256, smem_v, s>>>(hp, Wp, xp, eps, wp, mom_w, batch, P, steps, a, c0, c1, kk, dh_out, part_hv);
+    tail_final_kernel<T, K><<<fgrid, 256, 0, s>>>(Wp, bp, part_h, hslices, part_q, slices, P, (double)rows, a, b, kk,
+                                                   reinterpret_cast<T *>(dW), reinterpret_cast<T *>(dbias), mom_h, stb_part);
+    tail_loss_kernel<T, K><<<1, 32, 0, s>>>(mom_w, mom_h, part_t2, slices * pb, part_hv, vgrid, stb_part, fgrid, (double)rows,
+                                            (double)rows * P, a, reinterpret_cast<T *>(loss));
+    count_launch(5);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? QIDDM_OK : (int)e;
 }
@@ -937,7 +1096,8 @@ int linear_up_mse_step(const void *h, const void *W, const void *bias, const voi
                        long long batch, int P, int tau, int K, double a, double b, double c0, double c1, void *loss, void *dW,
                        void *dbias, void *dh, void *ws, cudaStream_t s) {
     if (!h || !W || !x || !eps || !w || !loss || !dW || !ws || batch < 1 || P < 1 || tau < 2) return QIDDM_EINVAL;
-    if (K < 1 || K > TAIL_KMAX || (size_t)P * (K + 1) * sizeof(double) > 200 * 1024) return QIDDM_EUNSUPPORTED;
+    if (K < 1 || K > TAIL_KMAX || ((size_t)P * K + (size_t)8 * (TAIL_TMAX + 1) * K) * sizeof(double) > 200 * 1024 || !dh)
+        return QIDDM_EUNSUPPORTED;       // W and the per-warp level sums must fit in shared memory; grad_h is always written
     if (dtype == QIDDM_DTYPE_F64) return tail_k<double>(K, h, W, bias, x, eps, w, batch, P, tau, a, b, c0, c1, loss, dW, dbias, dh, ws, s);
     if (dtype == QIDDM_DTYPE_F32) return tail_k<float>(K, h, W, bias, x, eps, w, batch, P, tau, a, b, c0, c1, loss, dW, dbias, dh, ws, s);
     return QIDDM_EINVAL;

@@ -50,17 +50,17 @@ class Diffusion(torch.nn.Module):
     def _fused_tail(self, noisy, draw, T, verbose, **coef):
         """Re-upload networks that end in `linear_up` (nn/qdense.py:642, :676): hidden features -> loss in ONE pass
         (noise.linear_up_mse_loss: no (rows x pixels) output / gradient tensors).  Returns the loss after `.backward()`, or None
-        when not applicable.  Opt-in (QIDDM_FUSED_TAIL=1): measured on B200 the two fused kernels are bound by the plain FP64 FMA
-        rate (~5 TFLOP/s: 273 us at 40 960 x 784 x 6 against 326 us for the four streaming kernels they replace) -- config 1
-        1.816 -> 1.806 ms per step, config 4 1.174 -> 1.189 ms: a memory saving (two (rows x pixels) float64 tensors), not a speed-up."""
+        when not applicable.  The plain FP64 FMA rate bounds the B200 here (~5 TFLOP/s), so the kernels work on expanded
+        products (second moments of the weight and of h): 222 us at 40 960 x 784 x 6 against 326 us for the four streaming
+        kernels they replace; from 16 384 rows on (below, its five launches cost what it saves).  QIDDM_FUSED_TAIL=0: off."""
         fh = getattr(self.net, "forward_hidden", None)
-        if (fh is None or draw is None or verbose or os.environ.get("QIDDM_FUSED_TAIL", "0") != "1"
+        if (fh is None or draw is None or verbose or os.environ.get("QIDDM_FUSED_TAIL", "1") == "0"
                 or type(self.loss) is not torch.nn.MSELoss or self.loss.reduction not in ("mean", "none")):
             return None
         layer = getattr(self.net, "linear_up", None)
         if not isinstance(layer, torch.nn.Linear) or getattr(self.net, "_restore", "linear") != "linear":
             return None
-        if not (layer.in_features <= 16 and noisy.shape[0] >= 4096):          # small batches: the separate kernels are as fast
+        if not (layer.in_features <= 16 and noisy.shape[0] >= 16384):         # below: its five launches cost what it saves
             return None
         h = fh(noisy)
         if h is None or not _noise.linear_up_mse_ok(h, layer, draw, T) or not (h.requires_grad or layer.weight.requires_grad):

@@ -122,7 +122,7 @@ class _LinearUpMSE(torch.autograd.Function):
         loss = torch.empty((), dtype=h.dtype, device=h.device)
         gw = torch.empty_like(wc)
         gb = torch.empty(pixels, dtype=h.dtype, device=h.device) if bias is not None else None
-        gh = torch.empty_like(hc) if need_h else None
+        gh = torch.empty_like(hc)                      # always written (its V term also feeds the loss)
         ws = torch.empty(int(lib.qiddm_linear_up_mse_workspace_bytes(pixels, hidden)), dtype=torch.uint8, device=h.device)
         with torch.cuda.device(h.device):
             L.check(lib.qiddm_linear_up_mse_step(L._ptr(hc), L._ptr(wc), L._ptr(bc), L._ptr(data), L._ptr(eps), L._ptr(w), dt, batch,
@@ -130,7 +130,7 @@ class _LinearUpMSE(torch.autograd.Function):
                                                  L._ptr(gw), L._ptr(gb), L._ptr(gh), L._ptr(ws),
                                                  C.c_void_p(torch.cuda.current_stream(h.device).cuda_stream)),
                     "qiddm_linear_up_mse_step")
-        ctx.grads = (gh, gw.to(weight.dtype), gb.to(bias.dtype) if gb is not None else None)
+        ctx.grads = (gh if need_h else None, gw.to(weight.dtype), gb.to(bias.dtype) if gb is not None else None)
         return loss
 
     @staticmethod
@@ -146,7 +146,7 @@ def linear_up_mse_ok(h: torch.Tensor, layer: torch.nn.Linear, draw, T: int) -> b
     return (h.is_cuda and h.dim() == 2 and h.dtype in (torch.float32, torch.float64) and h.dtype == data.dtype
             and isinstance(layer, torch.nn.Linear) and layer.in_features <= 16 and layer.in_features == h.shape[1]
             and layer.out_features == data.shape[1] and h.shape[0] == data.shape[0] * T and layer.weight.is_cuda
-            and data.shape[1] * (layer.in_features + 1) * 8 <= 200 * 1024)
+            and (data.shape[1] + 8 * 33) * layer.in_features * 8 <= 200 * 1024 and T <= 32)
 
 
 def linear_up_mse_loss(h: torch.Tensor, layer: torch.nn.Linear, draw, T: int, scale: float = 1.0, shift: float = 0.0,

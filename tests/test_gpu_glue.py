@@ -205,7 +205,7 @@ def test_fused_linear_up_mse_tail_matches_torch(dtype, tol, hidden, bias):
 
 @pytest.mark.parametrize("cls_args", [("QIDDM_LL_noise", (64, 4, 3, 2)), ("QIDDM_PL_noise", (64, 4, 3, 2))])
 def test_diffusion_step_with_and_without_the_fused_tail(cls_args, monkeypatch):
-    """Whole training step of a re-upload network with `linear_up + loss` fused (QIDDM_FUSED_TAIL=1, from 4096 rows on) against the same step
+    """Whole training step of a re-upload network with `linear_up + loss` fused (QIDDM_FUSED_TAIL=1, from 16 384 rows on) against the same step
     through the separate kernels: same loss, same gradients of every parameter."""
     from qiddm_b200 import models, nn, noise
     name, args = cls_args
@@ -217,7 +217,7 @@ def test_diffusion_step_with_and_without_the_fused_tail(cls_args, monkeypatch):
             net = getattr(nn, name)(*args)
             d = models.Diffusion(net, noise.add_normal_noise_multiple, goal, (8, 8), torch.nn.MSELoss()).to("cuda", torch.float64)
             d.train()
-            x = torch.rand(600, 64, dtype=torch.float64, device="cuda")
+            x = torch.rand(2100, 64, dtype=torch.float64, device="cuda")          # 16 800 rows: above the fused tail's threshold
             torch.manual_seed(11)
             (loss,) = d(x=x, T=8)
             res.append((loss.item(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
