@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) mse_ladder_grad_kernel(const T *r, const 
 // walking a slice of the images) touch every (row, pixel): K + 4 and K + 8 FP64 operations instead of 2 x (2K + 12).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TAIL_KMAX = 16;
-constexpr int TAIL_SLICES = 96;          // image slices of tail_q_kernel (per-CTA partial sums, fixed-order reduction)
+constexpr int TAIL_SLICES = 192;         // image slices of tail_q_kernel (per-CTA partial sums, fixed-order reduction)
 constexpr int TAIL_HSLICES = 148;        // row slices of the h moments
 constexpr int TAIL_TMAX = 32;            // ladder steps held per image in tail_v_kernel
 
