@@ -270,3 +270,49 @@ def test_qconv_dispatch_direct_convolution_gemm_or_gate():
     plan, m = plan_of(8, 8, 3)
     assert not plan.qconv_direct(L.UnfoldDesc(8, 28, 28, 3, 3, 0, 0))       # not "same" padding
     assert not plan.qconv_direct(L.UnfoldDesc(8, 4, 600, 3, 3, 1, 1))       # a row wider than a 512-pixel band
+
+
+def test_qconv_direct_support_answers_over_a_sweep_of_shapes():
+    """qiddm_qconv_direct_supported (the band / tile chooser behind it) over many layer shapes: it answers without a GPU, says yes
+    exactly for 1 x 1 / 3 x 3 "same" windows with <= 16 output channels whose band fits (a row of at most 512 pixels, the weight-
+    gradient kernel's warp layout), and the sizes it reports for such layers cover the saved rows and the dL/dY rows."""
+    import ctypes as C
+    import random
+    from qiddm_b200 import _lib as L
+    from qiddm_b200 import nn
+    lib = L.load_library()
+    rng = random.Random(0)
+    seen_yes = seen_no = 0
+    for _ in range(120):
+        cin, cout = rng.choice([1, 2, 3, 8, 16, 32, 48]), rng.choice([1, 2, 5, 8, 16, 24, 32])
+        k = rng.choice([1, 3, 5])
+        h, w = rng.choice([1, 7, 14, 28, 64, 100]), rng.choice([1, 7, 14, 28, 64, 511, 512, 513])
+        if cin * k * k > 1024:
+            continue
+        m = nn.QConv2d(cin, cout, kernel_size=k, padding=k // 2, qdepth=2)
+        if 2 * cout > 2 ** m.wires:          # `[:, ::2][:, :out_channels]` of nn/qconv.py:69-70 needs 2 out_channels amplitudes
+            continue
+        plan = L.Plan.get(m._spec())
+        u = L.UnfoldDesc(cin, h, w, k, k, k // 2, k // 2)
+        ok = bool(lib.qiddm_qconv_direct_supported(plan.handle, C.byref(u)))
+        n_out = plan.spec.read_count
+        np_ = 4 if 2 * n_out <= 4 else (16 if 2 * n_out <= 16 else 32)
+        # shared-memory footprints of the thinnest band (one row): weights + image tile, + the dL/dY rows
+        tc = (w + k - 1) | 1
+        cs = k * tc + ((3 - (k * tc) % 32) + 32) % 32
+        tile, wdf = (cin * cs + 3) & ~3, ((cin * k * k + 1) * np_ + 3) & ~3
+        ct = 16 if cin > 8 else 8
+        fits = (4 * (wdf + tile + w * (np_ + 4) + 256) <= 200 * 1024
+                and 4 * (-(-cin // ct) * ct * k * k * np_ + k * (w + k - 1) * (np_ + 4)) <= 200 * 1024)
+        expect = (m.wires >= 3 and k in (1, 3) and 2 * n_out <= 32 and w <= 512 and fits
+                  and -(-cin * k // 32) * (2 if 2 * n_out > 16 else 1) <= 8)
+        assert ok == expect, (cin, cout, k, h, w, m.wires, n_out)
+        if ok:
+            seen_yes += 1
+            n_img = 3
+            rows = n_img * h * w * (np_ + 4) * 4
+            assert lib.qiddm_qconv_gemm_saved_bytes(plan.handle, C.byref(u), n_img) >= rows
+            assert lib.qiddm_qconv_gemm_workspace_bytes(plan.handle, C.byref(u), n_img) >= rows
+        else:
+            seen_no += 1
+    assert seen_yes >= 20 and seen_no >= 20
